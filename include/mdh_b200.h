@@ -1,0 +1,179 @@
+/*
+ * mdh_b200.h -- C ABI of libmdh_b200.so, the B200 (sm_100a) implementation of
+ * mdhelper's per-frame structural-analysis hot path.
+ *
+ * The reference (bbye98/mdhelper) is pure Python and has no FFI boundary of its
+ * own; the seams this ABI sits under are (paths relative to the reference root):
+ *
+ *   seam #1  radial_histogram(pos1, pos2, n_bins, range, dims, *, exclusion)
+ *            src/mdhelper/analysis/structure.py:32-104, called per frame from
+ *            RadialDistributionFunction._single_frame (:750-791) and
+ *            _single_frame_parallel (:793-835)             -> mdh_rdf_*
+ *   seam #2  self._delta_fourier_transform_sum(qs, rs) -> c16[N_q]
+ *            src/mdhelper/algorithm/accelerated.py:81-165, called per frame from
+ *            StructureFactor._single_frame (structure.py:1481-1527), followed by
+ *            ssf += |rho|^2 or 2 Re(rho_j rho_k*)           -> mdh_sq_*
+ *   frame loop  MDAnalysis AnalysisBase.run / ParallelAnalysisBase.run
+ *            src/mdhelper/analysis/base.py:137-172, 312-507 -> the *_accumulate
+ *            entry points take a BATCH of frames; the host keeps the loop.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - every function returns MDH_OK (0) or a negative MDH_E* code; the message is
+ *     in a thread-local string returned by mdh_last_error().  Nothing throws or
+ *     aborts across the ABI.
+ *   - the caller owns every buffer it passes and must keep host buffers alive
+ *     until mdh_sync() (accumulate calls are asynchronous w.r.t. the host when
+ *     the host buffers are pinned).  The context owns all device memory.
+ *   - a context is bound to one CUDA device and one stream; calls on one context
+ *     are not re-entrant; different contexts may be driven from different host
+ *     threads.
+ *   - coordinates are float32, row-major [frame][particle][3]; frame_stride is
+ *     the distance between consecutive frames in FLOATS (>= 3*n), so a slice of
+ *     a larger [F][N][3] trajectory array can be passed without repacking.
+ *   - boxes are float32 [frame][3] (orthorhombic edge lengths; this is
+ *     ts.dimensions[:3] of the reference).  Triclinic cells are rejected by the
+ *     host layer.
+ */
+#ifndef MDH_B200_H
+#define MDH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDH_ABI_VERSION 1
+
+enum {
+    MDH_OK = 0,
+    MDH_EINVAL = -1,   /* bad argument (Python layer raises ValueError)      */
+    MDH_ECUDA = -2,    /* CUDA runtime failure (RuntimeError)                */
+    MDH_ESTATE = -3,   /* call sequence error, e.g. accumulate before configure */
+    MDH_ENOMEM = -4    /* host or device allocation failed                   */
+};
+
+/* where a coordinate pointer lives */
+enum { MDH_HOST = 0, MDH_DEVICE = 1 };
+
+/* pair-kernel strategy */
+enum {
+    MDH_RDF_AUTO = 0,      /* choose from n, box and cut-off per batch       */
+    MDH_RDF_ALLPAIRS = 1,  /* tiled all-pairs (r_max up to half the box)     */
+    MDH_RDF_CELLS = 2      /* cell list, 27-cell stencil (cut-off runs)      */
+};
+
+/* histogram privatisation inside the pair kernels (same counts either way) */
+enum {
+    MDH_HIST_AUTO = 0,
+    MDH_HIST_WARP_ATOMIC = 1,  /* one u32 histogram per warp, shared-memory atomics */
+    MDH_HIST_LANE_PRIVATE = 2  /* one packed 8-bit histogram per lane, no atomics   */
+};
+
+/* S(q) kernel strategy */
+enum {
+    MDH_SQ_AUTO = 0,
+    MDH_SQ_LATTICE_FP64 = 1,  /* q = n*b: per-axis phase factors, fp64 complex FMA */
+    MDH_SQ_LATTICE_SFU = 2,   /* q = n*b: 32-bit fixed-point phase, MUFU sin/cos,
+                                 fp64 accumulation (approximate: ~1e-6 abs/term) */
+    MDH_SQ_GENERAL_FP64 = 3,  /* arbitrary q: fp64 dot product + fp64 sincos     */
+    MDH_SQ_LATTICE_FP32 = 4   /* q = n*b: the FP64 scheme on the FP32 pipe
+                                 (approximate: ~1e-7 relative per term)          */
+};
+
+typedef struct mdh_ctx mdh_ctx;
+
+/* ---- context ----------------------------------------------------------------- */
+
+int mdh_abi_version(void);
+const char *mdh_last_error(void);
+
+/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream),
+ * or NULL to let the context create its own non-blocking stream. */
+int mdh_ctx_create(int device, void *cuda_stream, mdh_ctx **out);
+int mdh_ctx_destroy(mdh_ctx *ctx);
+int mdh_sync(mdh_ctx *ctx);
+
+/* Device-side time (ms, CUDA events on the context's stream) spent in the pair
+ * kernels / S(q) kernels by the LAST accumulate call, and launches issued by the
+ * context since creation.  Both calls synchronise the stream. */
+int mdh_last_kernel_ms(mdh_ctx *ctx, float *rdf_ms, float *sq_ms);
+int mdh_launch_count(mdh_ctx *ctx, int64_t *launches);
+
+/* ---- seam #1: radial histogram ------------------------------------------------- */
+
+/*
+ * n1, n2        particles in the two groups; same_group != 0 means pos2 is pos1
+ *               (the reference's ag1 is ag2 case: ordered pairs, self pairs
+ *               included, exactly as structure.py:93-104 counts them).
+ * n_bins        number of histogram bins.
+ * thresholds_sq n_bins+1 doubles, strictly increasing: bin k receives a pair iff
+ *               thresholds_sq[k] <= d^2 < thresholds_sq[k+1], d^2 being the fp64
+ *               squared minimum-image distance.  The host layer derives them from
+ *               np.linspace(range) so that this is exactly numpy.histogram of
+ *               sqrt(d^2) plus capped_distance's cut-offs (see
+ *               mdhelper_b200/analysis/_binning.py).
+ * r_lo, r_hi    the histogram range (only seeds the bin-index guess).
+ * excl1, excl2  exclusion block sizes: pairs with i/excl1 == j/excl2 are dropped
+ *               (structure.py:100-102); 0, 0 disables.
+ * drop_axis     -1, or 0/1/2: that coordinate is zeroed before the distance
+ *               (structure.py:766-767; the caller passes the widened box edge).
+ * mode, hist    MDH_RDF_* / MDH_HIST_* selectors.
+ * Resets the accumulated counts.
+ */
+int mdh_rdf_configure(mdh_ctx *ctx, int64_t n1, int64_t n2, int same_group, int n_bins,
+                      const double *thresholds_sq, double r_lo, double r_hi,
+                      int64_t excl1, int64_t excl2, int drop_axis, int mode, int hist);
+
+/* Adds the histograms of n_frames frames to the context's int64 counts.
+ * pos2 is ignored when same_group.  box is a HOST pointer, [n_frames][3]. */
+int mdh_rdf_accumulate(mdh_ctx *ctx, const float *pos1, int64_t frame_stride1,
+                       const float *pos2, int64_t frame_stride2, int location,
+                       const float *box, int n_frames);
+
+int mdh_rdf_fetch(mdh_ctx *ctx, int64_t *counts /* [n_bins] host */);
+int mdh_rdf_reset(mdh_ctx *ctx);
+/* device address of the int64[n_bins] accumulator (for NCCL reductions) */
+int mdh_rdf_counts_device(mdh_ctx *ctx, void **dptr);
+/* pair evaluations performed so far (what the kernels computed, for rooflines) */
+int mdh_rdf_pair_evaluations(mdh_ctx *ctx, int64_t *evals);
+
+/* ---- seam #2: direct-sum structure factor ------------------------------------ */
+
+/*
+ * n_total       particles per frame (all groups, concatenated in group order).
+ * n_groups, group_offsets[n_groups+1]
+ *               particle ranges of the groups inside a frame.
+ * n_q, wavevectors[n_q][3]   fp64 wavevectors.
+ * lattice_n[n_q][3], lattice_b[3]
+ *               if non-NULL: wavevectors[i][k] == lattice_n[i][k] * lattice_b[k]
+ *               (the reference's default reciprocal-lattice grid,
+ *               structure.py:1376-1416); enables the MDH_SQ_LATTICE_* kernels.
+ * n_pairs, pairs[n_pairs][2]
+ *               group index pairs (j, k) per output row: row += |rho_j|^2 if
+ *               j == k else 2 Re(rho_j conj(rho_k)) (structure.py:1496-1508);
+ *               the pair (-1, -1) means all particles together (mode=None,
+ *               structure.py:1491-1494).
+ * Resets the accumulator.
+ */
+int mdh_sq_configure(mdh_ctx *ctx, int64_t n_total, int n_groups,
+                     const int64_t *group_offsets, int n_q, const double *wavevectors,
+                     const int32_t *lattice_n, const double *lattice_b, int n_pairs,
+                     const int32_t *pairs, int mode);
+
+/* Adds sum over frames of the per-frame |rho|^2 terms to the fp64 accumulator. */
+int mdh_sq_accumulate(mdh_ctx *ctx, const float *pos, int64_t frame_stride, int location,
+                      int n_frames);
+
+int mdh_sq_fetch(mdh_ctx *ctx, double *ssf /* [n_pairs][n_q] host */);
+int mdh_sq_reset(mdh_ctx *ctx);
+int mdh_sq_accum_device(mdh_ctx *ctx, void **dptr);
+/* rho(q) of the LAST frame of the last batch: [n_rho][n_q][2] (re, im), n_rho =
+ * n_groups (or 1 for the (-1,-1) pair).  Debug / parity aid for seam #2. */
+int mdh_sq_fetch_rho(mdh_ctx *ctx, double *rho);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDH_B200_H */

@@ -1,0 +1,218 @@
+"""
+ctypes binding of ``libmdh_b200.so`` (C ABI: ``include/mdh_b200.h``).
+
+There is NO CPU fallback: if the shared library is missing or cannot be loaded,
+:func:`lib` raises.  Build it with ``make -C mdhelper_b200/csrc`` (or
+``__graft_entry__.build()``).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import pathlib
+
+import numpy as np
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libmdh_b200.so"
+
+MDH_OK, MDH_EINVAL, MDH_ECUDA, MDH_ESTATE, MDH_ENOMEM = 0, -1, -2, -3, -4
+MDH_HOST, MDH_DEVICE = 0, 1
+RDF_MODES = {"auto": 0, "allpairs": 1, "cells": 2}
+HIST_MODES = {"auto": 0, "warp_atomic": 1, "lane_private": 2}
+SQ_MODES = {"auto": 0, "lattice_fp64": 1, "lattice_sfu": 2, "general_fp64": 3,
+            "lattice_fp32": 4}
+
+_i32, _i64, _f64 = ctypes.c_int, ctypes.c_int64, ctypes.c_double
+_p = ctypes.c_void_p
+
+# name -> (restype, argtypes); every symbol include/mdh_b200.h declares
+SIGNATURES = {
+    "mdh_abi_version": (_i32, []),
+    "mdh_last_error": (ctypes.c_char_p, []),
+    "mdh_ctx_create": (_i32, [_i32, _p, ctypes.POINTER(_p)]),
+    "mdh_ctx_destroy": (_i32, [_p]),
+    "mdh_sync": (_i32, [_p]),
+    "mdh_last_kernel_ms": (_i32, [_p, ctypes.POINTER(ctypes.c_float),
+                                  ctypes.POINTER(ctypes.c_float)]),
+    "mdh_launch_count": (_i32, [_p, ctypes.POINTER(_i64)]),
+    "mdh_rdf_configure": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _f64, _f64, _i64,
+                                 _i64, _i32, _i32, _i32]),
+    "mdh_rdf_accumulate": (_i32, [_p, _p, _i64, _p, _i64, _i32, _p, _i32]),
+    "mdh_rdf_fetch": (_i32, [_p, _p]),
+    "mdh_rdf_reset": (_i32, [_p]),
+    "mdh_rdf_counts_device": (_i32, [_p, ctypes.POINTER(_p)]),
+    "mdh_rdf_pair_evaluations": (_i32, [_p, ctypes.POINTER(_i64)]),
+    "mdh_sq_configure": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i32, _p, _i32]),
+    "mdh_sq_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
+    "mdh_sq_fetch": (_i32, [_p, _p]),
+    "mdh_sq_reset": (_i32, [_p]),
+    "mdh_sq_accum_device": (_i32, [_p, ctypes.POINTER(_p)]),
+    "mdh_sq_fetch_rho": (_i32, [_p, _p]),
+}
+
+_LIB = None
+
+
+def lib() -> ctypes.CDLL:
+    """Loads ``libmdh_b200.so``; raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA library has not been built "
+                "(run `make -C mdhelper_b200/csrc`). mdhelper_b200 has no CPU "
+                "fallback."
+            )
+        L = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.mdh_abi_version() != 1:
+            raise RuntimeError("libmdh_b200.so ABI version mismatch")
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int) -> None:
+    """Maps an ``MDH_E*`` return code to the reference-style Python exception."""
+    if rc == MDH_OK:
+        return
+    msg = lib().mdh_last_error().decode(errors="replace")
+    if rc == MDH_EINVAL:
+        raise ValueError(msg)
+    if rc == MDH_ENOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(f"libmdh_b200 error {rc}: {msg}")
+
+
+def _ptr(a):
+    """Address of a numpy array, a torch tensor or a raw integer address."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()          # torch.Tensor
+
+
+class Context:
+    """
+    One device, one stream (``mdh_ctx``).  ``stream=None`` uses torch's current
+    stream on that device so that torch events and NCCL collectives order
+    correctly against the kernels.
+    """
+
+    def __init__(self, device: int = 0, stream=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("mdhelper_b200 needs a CUDA device (B200, sm_100a); "
+                               "there is no CPU fallback.")
+        self._lib = lib()
+        self.device = int(device)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        h = _p()
+        check(self._lib.mdh_ctx_create(self.device, _p(stream), ctypes.byref(h)))
+        self._h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mdh_ctx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def sync(self):
+        check(self._lib.mdh_sync(self._h))
+        self._keep.clear()
+
+    def last_kernel_ms(self):
+        a, b = ctypes.c_float(), ctypes.c_float()
+        check(self._lib.mdh_last_kernel_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def launch_count(self) -> int:
+        n = _i64()
+        check(self._lib.mdh_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    # ---- seam #1 ----
+    def rdf_configure(self, n1, n2, same_group, thresholds_sq, r_lo, r_hi, *,
+                      exclusion=None, drop_axis=None, mode="auto", hist="auto"):
+        thr = np.ascontiguousarray(thresholds_sq, dtype=np.float64)
+        e1, e2 = (0, 0) if exclusion is None else (int(exclusion[0]), int(exclusion[1]))
+        check(self._lib.mdh_rdf_configure(
+            self._h, int(n1), int(n2), int(bool(same_group)), len(thr) - 1,
+            thr.ctypes.data, float(r_lo), float(r_hi), e1, e2,
+            -1 if drop_axis is None else int(drop_axis),
+            RDF_MODES[mode], HIST_MODES[hist]))
+        self._n_bins = len(thr) - 1
+
+    def rdf_accumulate(self, pos1, stride1, pos2, stride2, box, n_frames, *,
+                       device=False, keepalive=None):
+        box = np.ascontiguousarray(box, dtype=np.float32)
+        if box.shape != (n_frames, 3):
+            raise ValueError("box must have shape (n_frames, 3)")
+        check(self._lib.mdh_rdf_accumulate(
+            self._h, _ptr(pos1), int(stride1), _ptr(pos2), int(stride2),
+            MDH_DEVICE if device else MDH_HOST, box.ctypes.data, int(n_frames)))
+        if keepalive is not None:
+            self._keep.append(keepalive)
+
+    def rdf_fetch(self) -> np.ndarray:
+        out = np.empty(self._n_bins, dtype=np.int64)
+        check(self._lib.mdh_rdf_fetch(self._h, out.ctypes.data))
+        self._keep.clear()
+        return out
+
+    def rdf_reset(self):
+        check(self._lib.mdh_rdf_reset(self._h))
+
+    def rdf_pair_evaluations(self) -> int:
+        n = _i64()
+        check(self._lib.mdh_rdf_pair_evaluations(self._h, ctypes.byref(n)))
+        return n.value
+
+    # ---- seam #2 ----
+    def sq_configure(self, n_total, group_offsets, wavevectors, pairs, *,
+                     lattice_n=None, lattice_b=None, mode="auto"):
+        goff = np.ascontiguousarray(group_offsets, dtype=np.int64)
+        wv = np.ascontiguousarray(wavevectors, dtype=np.float64)
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        ln = lb = None
+        if lattice_n is not None:
+            ln = np.ascontiguousarray(lattice_n, dtype=np.int32)
+            lb = np.ascontiguousarray(lattice_b, dtype=np.float64)
+            if ln.shape != wv.shape or lb.shape != (3,):
+                raise ValueError("lattice_n must match wavevectors; lattice_b is (3,)")
+        check(self._lib.mdh_sq_configure(
+            self._h, int(n_total), len(goff) - 1, goff.ctypes.data, len(wv),
+            wv.ctypes.data, _ptr(ln), _ptr(lb), len(pr), pr.ctypes.data,
+            SQ_MODES[mode]))
+        self._sq_shape = (len(pr), len(wv))
+        self._sq_nrho = 1 if (pr < 0).any() else len(goff) - 1
+
+    def sq_accumulate(self, pos, stride, n_frames, *, device=False, keepalive=None):
+        check(self._lib.mdh_sq_accumulate(
+            self._h, _ptr(pos), int(stride),
+            MDH_DEVICE if device else MDH_HOST, int(n_frames)))
+        if keepalive is not None:
+            self._keep.append(keepalive)
+
+    def sq_fetch(self) -> np.ndarray:
+        out = np.empty(self._sq_shape, dtype=np.float64)
+        check(self._lib.mdh_sq_fetch(self._h, out.ctypes.data))
+        self._keep.clear()
+        return out
+
+    def sq_reset(self):
+        check(self._lib.mdh_sq_reset(self._h))
+
+    def sq_fetch_rho(self) -> np.ndarray:
+        out = np.empty((self._sq_nrho, self._sq_shape[1]), dtype=np.complex128)
+        check(self._lib.mdh_sq_fetch_rho(self._h, out.ctypes.data))
+        return out

@@ -1,0 +1,315 @@
+"""
+Analysis base class for the GPU hot path
+========================================
+
+Host-side mirror of the reference's frame loop.  In the reference the loop is
+MDAnalysis' ``AnalysisBase.run`` (serial; ``/root/reference/src/mdhelper/
+analysis/base.py:137-172``) or ``ParallelAnalysisBase.run`` (a process pool over
+frames; ``base.py:312-507``).  Here the per-frame work happens on the GPU, so
+the loop hands BATCHES of frames to the C ABI and, when several ranks are
+running (``torch.distributed`` initialised, one process per GPU), shards the
+frames exactly as the reference's blocked parallel mode does
+(``np.array_split(frames, n_jobs)``, ``base.py:433-437``) and combines the
+per-rank accumulators with one all-reduce in :meth:`_conclude`.
+
+The protocol seen by subclasses is the reference's: ``_prepare()`` ->
+per-batch work -> ``_conclude()``; ``run()`` returns ``self`` and fills
+``self.results``.
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import TextIO, Union
+
+import numpy as np
+
+
+class Hash(dict):
+    """``dict`` with attribute access (the reference's results container,
+    ``analysis/base.py:79-113``)."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            return None
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+    def __delattr__(self, name):
+        try:
+            del self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+
+def world():
+    """``(rank, world_size)`` of the running job (``(0, 1)`` when not distributed)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def all_reduce_sum(array: np.ndarray, device=None) -> np.ndarray:
+    """
+    Sums ``array`` over all ranks (one collective).  int64 sums are exact and
+    order independent, so histogram counts are bit-identical at any GPU count.
+    With the NCCL backend the payload travels as a CUDA tensor over NVLink.
+    """
+    rank, size = world()
+    if size == 1:
+        return array
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(array))
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+class Batch:
+    """A run of frames ready for the C ABI."""
+
+    __slots__ = ("n_frames", "ptrs", "strides", "dims", "keepalive", "event")
+
+    def __init__(self, n_frames, ptrs, strides, dims, keepalive):
+        self.n_frames = n_frames
+        self.ptrs = ptrs            # host addresses, one per index set
+        self.strides = strides      # floats between consecutive frames
+        self.dims = dims            # float32 [n_frames, 6]
+        self.keepalive = keepalive
+        self.event = None
+
+
+class FrameFeeder:
+    """
+    Turns (trajectory, atom index sets, frame list) into batches of host
+    pointers.
+
+    * zero-copy: the trajectory exposes one float32 ``[F, N, 3]`` array
+      (``trajectory.coordinates``), the frames are evenly spaced and every
+      index set is a contiguous range -> pointers straight into that (pinned)
+      array, frame stride ``step * N * 3``; nothing is copied on the host.
+    * staged: anything else (any MDAnalysis reader, scattered selections,
+      centres of mass) -> frames are read one by one on the host
+      (``trajectory[f]``) and gathered into two alternating pinned staging
+      buffers.
+    """
+
+    def __init__(self, trajectory, index_sets, frames, batch_frames,
+                 positions_fn=None):
+        self.trajectory = trajectory
+        self.index_sets = [np.asarray(ix, dtype=np.intp) for ix in index_sets]
+        self.frames = np.asarray(frames, dtype=np.intp)
+        self.batch_frames = max(1, int(batch_frames))
+        self.positions_fn = positions_fn
+        coords = getattr(trajectory, "coordinates", None)
+        steps = np.diff(self.frames)
+        uniform = (len(self.frames) <= 1
+                   or (steps[0] > 0 and bool(np.all(steps == steps[0]))))
+        contiguous = all(
+            ix.size > 0 and ix[-1] - ix[0] + 1 == ix.size
+            and (ix.size == 1 or bool(np.all(np.diff(ix) == 1)))
+            for ix in self.index_sets
+        )
+        self.zero_copy = (
+            positions_fn is None and uniform and contiguous
+            and isinstance(coords, np.ndarray) and coords.dtype == np.float32
+            and coords.ndim == 3 and coords.flags.c_contiguous
+        )
+        self._coords = coords if self.zero_copy else None
+        self._step = int(steps[0]) if len(self.frames) > 1 else 1
+        self._staging = None
+
+    def _dims(self, frames):
+        cells = getattr(self.trajectory, "unitcells", None)
+        if isinstance(cells, np.ndarray):
+            return np.ascontiguousarray(cells[frames], dtype=np.float32)
+        out = np.empty((len(frames), 6), dtype=np.float32)
+        for b, f in enumerate(frames):
+            out[b] = self.trajectory[int(f)].dimensions
+        return out
+
+    def __iter__(self):
+        if self.zero_copy:
+            yield from self._iter_zero_copy()
+        else:
+            yield from self._iter_staged()
+
+    def _iter_zero_copy(self):
+        c = self._coords
+        n = c.shape[1]
+        for b0 in range(0, len(self.frames), self.batch_frames):
+            fr = self.frames[b0:b0 + self.batch_frames]
+            ptrs = [c.ctypes.data + 4 * 3 * (int(fr[0]) * n + int(ix[0]))
+                    for ix in self.index_sets]
+            strides = [self._step * n * 3] * len(self.index_sets)
+            yield Batch(len(fr), ptrs, strides, self._dims(fr), c)
+
+    def _iter_staged(self):
+        from ..universe import pinned_empty
+        sizes = [ix.size for ix in self.index_sets]
+        if self._staging is None:
+            self._staging = [
+                [pinned_empty((self.batch_frames, n, 3)) for n in sizes]
+                for _ in range(2)
+            ]
+        self._events = [None, None]
+        which = 0
+        for b0 in range(0, len(self.frames), self.batch_frames):
+            fr = self.frames[b0:b0 + self.batch_frames]
+            bufs = self._staging[which]
+            if self._events[which] is not None:       # previous user of this buffer
+                self._events[which].synchronize()
+            dims = np.empty((len(fr), 6), dtype=np.float32)
+            for b, f in enumerate(fr):
+                ts = self.trajectory[int(f)]
+                dims[b] = ts.dimensions
+                if self.positions_fn is not None:
+                    for (arr, _), p in zip(bufs, self.positions_fn(ts)):
+                        arr[b] = p
+                else:
+                    pos = ts.positions
+                    for (arr, _), ix in zip(bufs, self.index_sets):
+                        np.take(pos, ix, axis=0, out=arr[b])
+            batch = Batch(len(fr), [arr.ctypes.data for arr, _ in bufs],
+                          [n * 3 for n in sizes], dims, bufs)
+            yield batch
+            self._events[which] = batch.event
+            which ^= 1
+
+
+class GpuAnalysisBase:
+    """
+    Base class of the GPU analyses.
+
+    Parameters
+    ----------
+    trajectory : reader
+        Anything with the MDAnalysis reader protocol the loop needs
+        (``len``, ``trajectory[i]``, ``check_slice_indices``), e.g.
+        ``MDAnalysis.Universe.trajectory`` or
+        :class:`mdhelper_b200.universe.MemoryTrajectory`.
+    verbose : `bool`, default: :code:`False`
+        Determines whether progress is logged.
+    device : `int`, keyword-only, optional
+        CUDA device; default: ``LOCAL_RANK`` when distributed, else the current
+        torch device.
+    batch_frames : `int`, keyword-only, optional
+        Frames handed to the GPU per call (default: sized to ~128 MB of
+        coordinates).
+    """
+
+    def __init__(self, trajectory, verbose: bool = False, *, device: int = None,
+                 batch_frames: int = None, **kwargs):
+        self._trajectory = trajectory
+        self._verbose = verbose
+        self._device = device
+        self._batch_frames = batch_frames
+        self.results = Hash()
+        self._ctx = None
+
+    # ---- frame bookkeeping (same contract as MDAnalysis' _setup_frames) ----
+    def _setup_frames(self, trajectory, start=None, stop=None, step=None,
+                      frames=None):
+        self._trajectory = trajectory
+        if frames is not None:
+            if not all(o is None for o in (start, stop, step)):
+                raise ValueError("start/stop/step cannot be combined with frames")
+            frames = np.asarray(frames)
+            if frames.dtype == bool:
+                frames = np.nonzero(frames)[0]
+            self.start = self.stop = self.step = None
+            self._frame_list = frames.astype(np.intp)
+        else:
+            start, stop, step = trajectory.check_slice_indices(start, stop, step)
+            self.start, self.stop, self.step = start, stop, step
+            self._frame_list = np.arange(start, stop, step, dtype=np.intp)
+        self.n_frames = len(self._frame_list)
+        self.frames = self._frame_list.copy()
+        dt = getattr(trajectory, "dt", 1.0)
+        self.times = self.frames * dt
+
+    def _context(self):
+        if self._ctx is None:
+            import os
+            import torch
+            from .._lib import Context
+            dev = self._device
+            if dev is None:
+                dev = (int(os.environ.get("LOCAL_RANK", 0)) if world()[1] > 1
+                       else (torch.cuda.current_device()
+                             if torch.cuda.is_available() else 0))
+            if torch.cuda.is_available():
+                torch.cuda.set_device(dev)
+            self._ctx = Context(dev)
+            self._device = dev
+        return self._ctx
+
+    def _default_batch(self, bytes_per_frame: int) -> int:
+        if self._batch_frames:
+            return int(self._batch_frames)
+        return int(min(512, max(1, (128 << 20) // max(1, bytes_per_frame))))
+
+    def _prepare(self):
+        pass
+
+    def _process(self, frames: np.ndarray):
+        raise NotImplementedError
+
+    def _conclude(self):
+        pass
+
+    def run(self, start: int = None, stop: int = None, step: int = None,
+            frames: Union[slice, np.ndarray] = None, verbose: bool = None,
+            **kwargs) -> "GpuAnalysisBase":
+        """
+        Performs the calculation.
+
+        Parameters
+        ----------
+        start, stop, step : `int`, optional
+            Frame slice to analyse.
+        frames : array-like, optional
+            Explicit frame indices (or a boolean mask) instead of a slice.
+        verbose : `bool`, optional
+            Determines whether progress is logged.
+        **kwargs
+            ``n_jobs``, ``module``, ``block``, ``method``, ``n_threads`` of the
+            reference's CPU schedulers are accepted and ignored.
+
+        Returns
+        -------
+        self
+        """
+        verbose = self._verbose if verbose is None else verbose
+        log = logging.getLogger("mdhelper_b200")
+        self._setup_frames(self._trajectory, start=start, stop=stop, step=step,
+                           frames=frames)
+        self._prepare()
+        rank, size = world()
+        local = np.array_split(self._frame_list, size)[rank]
+        self.n_local_frames = len(local)
+        if verbose:
+            log.info("rank %d/%d: %d of %d frames", rank, size, len(local),
+                     self.n_frames)
+        self._process(local)
+        self._conclude()
+        return self
+
+    def save(self, file: Union[str, TextIO], archive: bool = True,
+             compress: bool = True, **kwargs) -> None:
+        """Saves ``results`` in NumPy format (reference: ``base.py:174-210``)."""
+        data = {k: v for k, v in self.results.items()}
+        if archive:
+            (np.savez_compressed if compress else np.savez)(file, **data, **kwargs)
+        else:
+            for k, v in data.items():
+                np.save(f"{file}_{k}", v, **kwargs)

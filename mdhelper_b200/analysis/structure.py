@@ -1,0 +1,626 @@
+"""
+Bulk structural analysis on B200
+================================
+
+GPU drop-ins for the two classes of ``mdhelper.analysis.structure`` that sit on
+the per-frame hot path (reference: ``/root/reference/src/mdhelper/analysis/
+structure.py``):
+
+* :func:`radial_histogram` -- seam #1, ``structure.py:32-104``.
+* :class:`RadialDistributionFunction` -- ``structure.py:444-1032``.
+* :class:`StructureFactor` -- ``structure.py:1034-1550``.
+
+Constructors, ``run(start, stop, step, frames)`` and ``results.*`` follow the
+reference.  The distance / binning loop and the Fourier sums run in
+``libmdh_b200.so``; everything that is O(n_bins) or O(N_q) (edges,
+normalisation, unique-|q| grouping, sorting) stays in numpy so that identical
+counts give identical ``results.rdf``.
+"""
+
+from __future__ import annotations
+
+from itertools import combinations_with_replacement
+from typing import Union
+
+import numpy as np
+
+from ._binning import squared_thresholds
+from .base import FrameFeeder, GpuAnalysisBase, all_reduce_sum, world
+
+_GROUPINGS_RDF = {"atoms", "residues", "segments"}
+_GROUPINGS_SSF = {"atoms", "residues"}
+
+
+def _check_orthorhombic(dims: np.ndarray) -> None:
+    if dims is None:
+        raise ValueError("Trajectory does not contain system dimension "
+                         "information.")
+    dims = np.atleast_2d(dims)
+    if dims.shape[1] >= 6 and not np.all(dims[:, 3:6] == 90):
+        raise NotImplementedError(
+            "mdhelper_b200 supports orthorhombic cells only (triclinic "
+            "minimum image is not implemented)."
+        )
+
+
+def _record(batch):
+    import torch
+    batch.event = torch.cuda.Event()
+    batch.event.record()
+
+
+def _centers_of_mass(group, grouping: str, positions: np.ndarray) -> np.ndarray:
+    """
+    Centres of mass of the residues / segments of ``group`` (host-side helper;
+    reference: ``algorithm/molecule.py:15-310`` as used at
+    ``structure.py:753-756``).  float64 mass-weighted mean of the float32
+    coordinates.
+    """
+    key = group.resindices if grouping == "residues" else group.segindices
+    _, inv = np.unique(key, return_inverse=True)
+    m = np.asarray(group.masses, dtype=np.float64)
+    tot = np.bincount(inv, weights=m)
+    com = np.empty((tot.size, 3))
+    for k in range(3):
+        com[:, k] = np.bincount(inv, weights=m * positions[:, k]) / tot
+    return com
+
+
+def _n_entities(group, grouping: str) -> int:
+    return int(getattr(group, f"n_{grouping}"))
+
+
+def radial_histogram(
+        pos1: np.ndarray, pos2: np.ndarray, n_bins: int, range: tuple,
+        dims: tuple, *, exclusion: tuple = None, mode: str = "auto",
+        hist: str = "auto", device: int = None) -> np.ndarray:
+    """
+    Computes the radial histogram of distances between particles of the same
+    type or two different types (GPU version of ``structure.py:32-104``).
+
+    Parameters
+    ----------
+    pos1, pos2 : `numpy.ndarray`
+        Positions of the two groups, shapes :math:`(N_1,\\,3)` and
+        :math:`(N_2,\\,3)` (a single ``(3,)`` coordinate is one particle).
+        Converted to float32, as ``capped_distance`` does.
+    n_bins : `int`
+        Number of histogram bins.
+    range : array-like
+        Range of radii values, shape ``(2,)``.
+    dims : array-like
+        System dimensions and orthogonality, shape ``(6,)``.
+    exclusion : array-like, keyword-only, optional
+        Tiles to exclude: pairs with ``i // exclusion[0] == j // exclusion[1]``
+        are dropped.
+    mode, hist : `str`, keyword-only
+        Kernel selectors (``"auto"``, ``"allpairs"``, ``"cells"``;
+        ``"auto"``, ``"warp_atomic"``, ``"lane_private"``).  Counts do not
+        depend on them.
+
+    Returns
+    -------
+    histogram : `numpy.ndarray`
+        Radial histogram, int64, shape :math:`(N_\\mathrm{bins},)`.
+    """
+    from .._lib import Context
+    p1 = np.ascontiguousarray(np.atleast_2d(np.asarray(pos1)), dtype=np.float32)
+    p2 = np.ascontiguousarray(np.atleast_2d(np.asarray(pos2)), dtype=np.float32)
+    dims = np.asarray(dims, dtype=np.float32)
+    _check_orthorhombic(dims)
+    import torch
+    dev = torch.cuda.current_device() if device is None else device
+    ctx = Context(dev)
+    try:
+        ctx.rdf_configure(len(p1), len(p2), False,
+                          squared_thresholds(n_bins, range), range[0], range[1],
+                          exclusion=exclusion, mode=mode, hist=hist)
+        ctx.rdf_accumulate(p1, 3 * len(p1), p2, 3 * len(p2),
+                           dims[None, :3], 1)
+        return ctx.rdf_fetch()
+    finally:
+        ctx.close()
+
+
+class RadialDistributionFunction(GpuAnalysisBase):
+    r"""
+    Radial distribution function :math:`g_{ij}(r)` between two groups for two-
+    and three-dimensional periodic systems, computed on the GPU.
+
+    Same constructor and results as the reference class
+    (``structure.py:444-1032``); the differences are listed under *Notes*.
+
+    Parameters
+    ----------
+    ag1, ag2 : atom groups
+        First and (optionally) second group; ``ag2=None`` means ``ag1``.
+    n_bins : `int`, default: :code:`201`
+        Number of histogram bins.
+    range : array-like, default: :code:`(0.0, 15.0)`
+        Range of radii values.
+    drop_axis : `int` or `str`, keyword-only, optional
+        Axis to ignore for two-dimensional systems (``0/1/2`` or ``"x"/"y"/"z"``).
+    norm : `str`, keyword-only, default: :code:`"rdf"`
+        ``"rdf"``, ``"density"`` or :code:`None` (raw counts).
+    exclusion : array-like, keyword-only, optional
+        Tiles to exclude from the interparticle distances, e.g. ``(1, 1)``.
+    groupings : `str` or array-like, keyword-only, default: :code:`"atoms"`
+        ``"atoms"``, ``"residues"`` or ``"segments"`` (centres of mass, computed
+        on the host).
+    reduced : `bool`, keyword-only, default: :code:`False`
+        Whether the data is in reduced units.
+    n_batches : `int`, keyword-only, optional
+        Accepted for compatibility and ignored: the GPU kernels never
+        materialise the pair list, so the range does not need to be split.
+    parallel : `bool`, keyword-only, default: :code:`False`
+        Accepted for compatibility; frames are sharded over GPUs whenever
+        ``torch.distributed`` is initialised.
+    verbose : `bool`, keyword-only, default: :code:`True`
+        Determines whether progress is logged.
+    mode, hist : `str`, keyword-only
+        Kernel selectors, see :func:`radial_histogram`.
+
+    Attributes
+    ----------
+    results.edges, results.bins, results.counts, results.rdf
+        As in the reference; ``results.counts`` is int64 and bit-exact.
+
+    Notes
+    -----
+    * ``n_batches`` has no effect (the reference documents that its batched
+      mode can be off by a few counts, ``structure.py:601-607``; the GPU result
+      is the unbatched one).
+    * Orthorhombic cells only.
+    """
+
+    def __init__(
+            self, ag1, ag2=None, n_bins: int = 201,
+            range: tuple = (0.0, 15.0), *, drop_axis: Union[int, str] = None,
+            norm: str = "rdf", exclusion: tuple = None,
+            groupings: Union[str, tuple] = "atoms", reduced: bool = False,
+            n_batches: int = None, parallel: bool = False,
+            verbose: bool = True, mode: str = "auto", hist: str = "auto",
+            **kwargs) -> None:
+
+        self.ag1 = ag1
+        self.ag2 = ag1 if ag2 is None else ag2
+        self.universe = self.ag1.universe
+        if self.universe.dimensions is None:
+            raise ValueError("Trajectory does not contain system "
+                             "dimension information.")
+
+        super().__init__(self.universe.trajectory, verbose, **kwargs)
+        self._parallel = parallel
+
+        if isinstance(groupings, str):
+            if groupings not in _GROUPINGS_RDF:
+                emsg = (f"Invalid grouping '{groupings}'. The options are "
+                        "'atoms', 'residues', and 'segments'.")
+                raise ValueError(emsg)
+            self._groupings = 2 * [groupings]
+        else:
+            for g in groupings:
+                if g not in _GROUPINGS_RDF:
+                    emsg = (f"Invalid grouping '{g}'. The options are "
+                            "'atoms', 'residues', and 'segments'.")
+                    raise ValueError(emsg)
+            self._groupings = (2 * list(groupings) if len(groupings) == 1
+                               else list(groupings))
+
+        self._drop_axis = (ord(drop_axis) - 120 if isinstance(drop_axis, str)
+                           else drop_axis)
+        if self._drop_axis not in {0, 1, 2, None}:
+            raise ValueError("Invalid axis to drop.")
+
+        self._n_bins = n_bins
+        self._range = range
+        self._norm = norm
+        self._exclusion = exclusion
+        self._reduced = reduced
+        self._n_batches = n_batches
+        self._verbose = verbose
+        self._mode = mode
+        self._hist = hist
+
+    def _prepare(self) -> None:
+        # reference: structure.py:734-748
+        self.results.edges = np.linspace(*self._range, self._n_bins + 1)
+        self.results.bins = (self.results.edges[:-1]
+                             + self.results.edges[1:]) / 2
+        self.results.counts = np.zeros(self._n_bins, dtype=int)
+        self.results.units = {"results.bins": "angstrom",
+                              "results.edges": "angstrom"}
+        self._area_or_volume = 0.0
+
+    def _process(self, frames: np.ndarray) -> None:
+        ctx = self._context()
+        n1 = _n_entities(self.ag1, self._groupings[0])
+        n2 = _n_entities(self.ag2, self._groupings[1])
+        same = (self.ag1 is self.ag2
+                or np.array_equal(self.ag1.ix, self.ag2.ix)) \
+            and self._groupings[0] == self._groupings[1]
+        ctx.rdf_configure(
+            n1, n2, same, squared_thresholds(self._n_bins, self._range),
+            self._range[0], self._range[1], exclusion=self._exclusion,
+            drop_axis=self._drop_axis, mode=self._mode, hist=self._hist
+        )
+        self._kernel_ms = 0.0
+        if len(frames) == 0:
+            self._local_counts = np.zeros(self._n_bins, dtype=np.int64)
+            return
+
+        atoms_only = self._groupings[0] == self._groupings[1] == "atoms"
+        sets = [self.ag1.ix] if same else [self.ag1.ix, self.ag2.ix]
+        positions_fn = None
+        if not atoms_only:
+            groups = [self.ag1] if same else [self.ag1, self.ag2]
+            grps = self._groupings[:len(groups)]
+
+            def positions_fn(ts, groups=groups, grps=grps):
+                return [ts.positions[g.ix] if gr == "atoms"
+                        else _centers_of_mass(g, gr, ts.positions[g.ix])
+                        for g, gr in zip(groups, grps)]
+            sets = [np.arange(n1)] if same else [np.arange(n1), np.arange(n2)]
+
+        feeder = FrameFeeder(self._trajectory, sets, frames,
+                             self._default_batch(12 * (n1 + n2)), positions_fn)
+        for batch in feeder:
+            _check_orthorhombic(batch.dims)
+            box = batch.dims[:, :3].copy()
+            if self._drop_axis is None:
+                # ts.volume: float64 product of the float32 edges
+                for v in box.astype(np.float64).prod(axis=1):
+                    self._area_or_volume += v
+            else:
+                # reference: structure.py:764-770
+                box[:, self._drop_axis] = box.max(axis=1)
+                keep = [k for k in (0, 1, 2) if k != self._drop_axis]
+                for v in box[:, keep].astype(np.float64).prod(axis=1):
+                    self._area_or_volume += v
+            ctx.rdf_accumulate(
+                batch.ptrs[0], batch.strides[0],
+                None if same else batch.ptrs[1],
+                0 if same else batch.strides[1],
+                box, batch.n_frames, keepalive=batch.keepalive
+            )
+            _record(batch)
+        self._local_counts = ctx.rdf_fetch()
+        self._pair_evaluations = ctx.rdf_pair_evaluations()
+
+    def _conclude(self) -> None:
+        # one all-reduce: counts (exact) and the accumulated volume
+        counts = all_reduce_sum(self._local_counts, self._device)
+        vol = all_reduce_sum(np.array([self._area_or_volume]), self._device)[0]
+        self.results.counts[:] = counts
+        self._area_or_volume = float(vol)
+
+        # normalisation, reference: structure.py:844-862
+        norm = self.n_frames
+        if self._norm is not None:
+            if self._drop_axis is None:
+                norm = norm * (4 * np.pi * np.diff(self.results.edges ** 3) / 3)
+            else:
+                norm = norm * (np.pi * np.diff(self.results.edges ** 2))
+            if self._norm == "rdf":
+                _N2 = _n_entities(self.ag2, self._groupings[1])
+                if self._exclusion:
+                    _N2 -= self._exclusion[1]
+                norm = norm * (_n_entities(self.ag1, self._groupings[0]) * _N2
+                               * self.n_frames / self._area_or_volume)
+        self.results.rdf = self.results.counts / norm
+
+    def _get_rdf(self) -> np.ndarray:
+        """
+        Returns the radial distribution function whatever ``norm`` was
+        (reference: ``structure.py:864-891``).
+        """
+        if self._norm == "rdf":
+            return self.results.rdf
+        _N2 = _n_entities(self.ag2, self._groupings[1])
+        if self._exclusion:
+            _N2 -= self._exclusion[1]
+        if self._drop_axis is None:
+            norm = 4 * np.diff(self.results.edges ** 3) / 3
+        else:
+            norm = np.diff(self.results.edges ** 2)
+        return self._area_or_volume * self.results.counts / (
+            np.pi * self.n_frames ** 2 * _N2 * norm
+            * _n_entities(self.ag1, self._groupings[0])
+        )
+
+
+def _lattice_indices(wavevectors: np.ndarray, dimensions) -> tuple:
+    """
+    If every wavevector is a non-negative integer multiple of the reciprocal
+    lattice basis ``b_k = 2 pi / L_k``, returns ``(n, b)``; else ``(None, None)``.
+    """
+    if dimensions is None:
+        return None, None
+    b = 2 * np.pi / np.asarray(dimensions, dtype=np.float64)
+    n = np.rint(wavevectors / b)
+    if (n < 0).any() or (n > 1023).any():
+        return None, None
+    if not np.allclose(n * b, wavevectors, rtol=1e-12, atol=1e-12 * b.max()):
+        return None, None
+    n = n.astype(np.int32)
+    if len(np.unique(n, axis=0)) != len(n):
+        return None, None
+    return n, b
+
+
+class StructureFactor(GpuAnalysisBase):
+    r"""
+    Static (or partial) structure factor by direct summation,
+
+    .. math::
+
+       S(\mathbf{q})=\frac{1}{N}\left\langle\left|\sum_{j=1}^N
+       \exp(i\mathbf{q}\cdot\mathbf{r}_j)\right|^2\right\rangle,
+
+    on the first-octant reciprocal-lattice grid of the box (or on user supplied
+    wavevectors), computed on the GPU.  Same constructor and results as the
+    reference class (``structure.py:1034-1550``).
+
+    Parameters
+    ----------
+    groups : atom group or sequence of atom groups
+    groupings : `str` or sequence, default: :code:`"atoms"`
+        ``"atoms"`` or ``"residues"`` (centres of mass, computed on the host).
+    mode : `str`, keyword-only, optional
+        :code:`None` (all particles together), ``"pair"`` or ``"partial"``.
+    form : `str`, keyword-only, default: :code:`"exp"`
+        ``"exp"`` or ``"trig"``; both are served by the same kernels
+        (``|sum exp|^2 == (sum cos)^2 + (sum sin)^2``).
+    dimensions, n_points, n_surfaces, n_surface_points, q_max, wavevectors,
+    sort, unique
+        As in the reference (``structure.py:1366-1416``).
+    parallel : `bool`, keyword-only
+        Accepted for compatibility (the reference's numba thread switch).
+    precision : `str`, keyword-only, default: :code:`"fp64"`
+        ``"fp64"`` (default, ~1e-13 relative to the reference), or ``"fp32"``
+        (lattice wavevectors only: phase factors and accumulation on the FP32
+        pipe, ~1e-6 relative).
+
+    Attributes
+    ----------
+    results.pairs, results.wavenumbers, results.ssf
+        As in the reference.
+    """
+
+    def __init__(
+            self, groups, groupings: Union[str, tuple] = "atoms", *,
+            mode: str = None, form: str = "exp", dimensions=None,
+            n_points: int = 32, n_surfaces: int = None,
+            n_surface_points: int = 8, q_max: float = None,
+            wavevectors: np.ndarray = None, sort: bool = True,
+            unique: bool = True, parallel: bool = False, verbose: bool = True,
+            precision: str = "fp64", kernel: str = None, **kwargs) -> None:
+
+        self._groups = ([groups] if hasattr(groups, "universe")
+                        and hasattr(groups, "positions") else list(groups))
+        self.universe = self._groups[0].universe
+
+        super().__init__(self.universe.trajectory, verbose, **kwargs)
+
+        self._n_groups = len(self._groups)
+        if isinstance(groupings, str):
+            if groupings not in _GROUPINGS_SSF:
+                emsg = (f"Invalid grouping '{groupings}'. Valid "
+                        f"values: {', '.join(sorted(_GROUPINGS_SSF))}.")
+                raise ValueError(emsg)
+            self._groupings = self._n_groups * [groupings]
+        else:
+            if self._n_groups != len(groupings):
+                emsg = ("The number of grouping values is not equal to "
+                        "the number of groups.")
+                raise ValueError(emsg)
+            for g in groupings:
+                if g not in _GROUPINGS_SSF:
+                    emsg = (f"Invalid grouping '{g}'. Valid "
+                            f"values: {', '.join(sorted(_GROUPINGS_SSF))}.")
+                    raise ValueError(emsg)
+            self._groupings = list(groupings)
+
+        self._mode = mode
+        if self._mode not in {None, "pair", "partial"}:
+            raise ValueError("Invalid mode. Valid values: None, 'pair', "
+                             "'partial'.")
+        if self._mode == "pair" and not 1 <= len(self._groups) <= 2:
+            emsg = "There must be exactly one or two groups when mode='pair'."
+            raise ValueError(emsg)
+        elif self._mode is None:
+            if sum(g.n_atoms for g in self._groups) \
+                    != self.universe.atoms.n_atoms:
+                emsg = ("The provided atom groups do not contain all atoms "
+                        "in the universe.")
+                raise ValueError(emsg)
+        if form not in {"exp", "trig"}:
+            raise ValueError("Invalid form. Valid values: 'exp', 'trig'.")
+        if precision not in {"fp64", "fp32"}:
+            raise ValueError("Invalid precision. Valid values: 'fp64', 'fp32'.")
+
+        self._dimensions = None
+        if dimensions is not None:
+            if len(dimensions) != 3:
+                raise ValueError("'dimensions' must have length 3.")
+            self._dimensions = np.asarray(dimensions)
+        elif self.universe.dimensions is not None:
+            self._dimensions = self.universe.dimensions[:3].copy()
+        elif wavevectors is None:
+            raise ValueError("No system dimensions found or provided.")
+
+        # Wavevectors (reference: structure.py:1375-1416).  The grid spacing
+        # uses the box edge as stored (float32 from the universe) promoted to
+        # float64, and the np.meshgrid 'xy' ordering: row (i, j, k) of the
+        # reshaped grid holds (g[j], g[i], g[k]).
+        self._lattice_n = self._lattice_b = None
+        if wavevectors is not None:
+            self._wavevectors = np.asarray(wavevectors, dtype=np.float64)
+            self._lattice_n, self._lattice_b = _lattice_indices(
+                self._wavevectors, self._dimensions)
+        else:
+            cubic = np.allclose(self._dimensions, self._dimensions[0])
+            idx = np.arange(n_points)
+            if cubic:
+                grids = 3 * [2 * np.pi * idx / self._dimensions[0]]
+            else:
+                grids = [2 * np.pi * idx / L for L in self._dimensions]
+            ii, jj, kk = np.meshgrid(idx, idx, idx, indexing="ij")
+            n = np.stack((jj, ii, kk), axis=-1).reshape(-1, 3)
+            self._wavevectors = np.stack(
+                (grids[0][n[:, 0]], grids[1][n[:, 1]], grids[2][n[:, 2]]), axis=-1
+            )
+            self._lattice_n = n.astype(np.int32)
+            self._lattice_b = np.array([g[1] if n_points > 1 else 1.0
+                                        for g in grids])
+            if n_surfaces:
+                if not cubic:
+                    raise ValueError("'n_surfaces' requires a cubic box.")
+                self._wavevectors = np.vstack(
+                    (self._wavevectors,
+                     _surface_wavevectors(grids[0], n_surfaces,
+                                          n_surface_points))
+                )
+                self._lattice_n = self._lattice_b = None
+        self._wavenumbers = np.linalg.norm(self._wavevectors, axis=1)
+
+        if q_max is not None:
+            keep = self._wavenumbers <= q_max
+            self._wavevectors = self._wavevectors[keep]
+            self._wavenumbers = self._wavenumbers[keep]
+            if self._lattice_n is not None:
+                self._lattice_n = self._lattice_n[keep]
+
+        self._Ns = np.fromiter(
+            (_n_entities(a, g) for a, g in zip(self._groups, self._groupings)),
+            dtype=int, count=self._n_groups
+        )
+        self._N = self._Ns.sum()
+        self._form = form
+        self._sort = sort
+        self._unique = unique
+        self._verbose = verbose
+        self._precision = precision
+        self._kernel = kernel
+
+    def _prepare(self) -> None:
+        # reference: structure.py:1456-1479
+        self.results.pairs = (
+            tuple(combinations_with_replacement(range(self._n_groups), 2))
+            if self._mode == "partial"
+            else ((0, self._n_groups - 1),) if self._mode == "pair"
+            else ((None, None),)
+        )
+        self.results.ssf = np.zeros((len(self.results.pairs),
+                                     len(self._wavenumbers)))
+        self.results.wavenumbers = (np.unique(self._wavenumbers.round(11))
+                                    if self._unique else self._wavenumbers)
+        self.results.units = {"results.wavenumbers": "angstrom^-1"}
+
+    def _process(self, frames: np.ndarray) -> None:
+        ctx = self._context()
+        offsets = np.concatenate(([0], np.cumsum(self._Ns)))
+        pairs = np.array([(-1, -1) if p[0] is None else p
+                          for p in self.results.pairs], dtype=np.int32)
+        if self._kernel is not None:
+            mode = self._kernel
+        elif self._lattice_n is None:
+            mode = "general_fp64"
+        else:
+            mode = "lattice_fp32" if self._precision == "fp32" else "lattice_fp64"
+        ctx.sq_configure(int(self._N), offsets, self._wavevectors, pairs,
+                         lattice_n=self._lattice_n, lattice_b=self._lattice_b,
+                         mode=mode)
+        if len(frames) == 0:
+            self._local_ssf = np.zeros_like(self.results.ssf)
+            return
+
+        atoms_only = all(g == "atoms" for g in self._groupings)
+        if atoms_only:
+            sets = [np.concatenate([g.ix for g in self._groups])]
+            positions_fn = None
+        else:
+            sets = [np.arange(self._N)]
+
+            def positions_fn(ts):
+                return [np.concatenate([
+                    ts.positions[g.ix] if gr == "atoms"
+                    else _centers_of_mass(g, gr, ts.positions[g.ix])
+                    for g, gr in zip(self._groups, self._groupings)
+                ])]
+
+        feeder = FrameFeeder(self._trajectory, sets, frames,
+                             self._default_batch(12 * int(self._N)),
+                             positions_fn)
+        for batch in feeder:
+            ctx.sq_accumulate(batch.ptrs[0], batch.strides[0], batch.n_frames,
+                              keepalive=batch.keepalive)
+            _record(batch)
+        self._local_ssf = ctx.sq_fetch()
+
+    def _conclude(self) -> None:
+        # reference: structure.py:1529-1550
+        self.results.ssf = all_reduce_sum(self._local_ssf, self._device)
+        self.results.ssf /= self.n_frames * self._N
+
+        if self._unique:
+            self.results.ssf = np.hstack(
+                [self.results.ssf[:, np.isclose(q, self._wavenumbers)]
+                 .mean(axis=1, keepdims=True)
+                 for q in self.results.wavenumbers]
+            )
+        if self._sort:
+            order = np.argsort(self.results.wavenumbers)
+            self.results.wavenumbers = self.results.wavenumbers[order]
+            self.results.ssf = self.results.ssf[:, order]
+
+
+def _closest_factor_pair(value: int) -> tuple:
+    """
+    Two factors of ``value`` that are close to each other, larger first: the
+    greedy assignment of prime factors (largest first) to the slot that stays
+    at or below ``round(sqrt(value))`` -- the same pairing as the reference's
+    ``get_closest_factors(value, 2, reverse=True)``
+    (``algorithm/utility.py:15-72``), which fixes how many polar and azimuthal
+    points ``n_surface_points`` is split into.
+    """
+    root = float(value) ** 0.5
+    root_int = int(np.round(root))
+    if np.isclose(root, root_int):
+        return root_int, root_int
+    primes, rest, d = [], int(value), 2
+    while d * d <= rest:
+        while rest % d == 0:
+            primes.append(d)
+            rest //= d
+        d += 1
+    if rest > 1:
+        primes.append(rest)
+    slots, i = [1, 1], 0
+    for j, f in enumerate(reversed(primes)):
+        while i < 2:
+            if slots[i] * f <= root_int or (j < 2 and slots[i] == 1):
+                slots[i] *= f
+                break
+            i += 1
+        else:
+            slots[slots.index(min(slots))] *= f
+    return max(slots), min(slots)
+
+
+def _surface_wavevectors(grid: np.ndarray, n_surfaces: int,
+                         n_surface_points: int) -> np.ndarray:
+    """
+    Extra off-lattice wavevectors on first-octant spherical surfaces of radii
+    ``grid[1..n_surfaces]`` (reference: ``structure.py:1382-1403``).
+    """
+    n_theta, n_phi = _closest_factor_pair(n_surface_points)
+    theta = np.linspace(np.pi / (2 * n_theta + 4),
+                        np.pi / 2 - np.pi / (2 * n_theta + 4), n_theta)
+    phi = np.linspace(np.pi / (2 * n_phi + 4),
+                      np.pi / 2 - np.pi / (2 * n_phi + 4), n_phi)
+    unit = np.stack((np.sin(theta) * np.cos(phi)[:, None],
+                     np.sin(theta) * np.sin(phi)[:, None],
+                     np.tile(np.cos(theta)[None, :], (n_phi, 1))), axis=-1)
+    return np.einsum("o,tpd->otpd", grid[1:n_surfaces + 1], unit).reshape(
+        (n_surfaces * n_surface_points, 3))

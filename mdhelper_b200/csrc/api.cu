@@ -1,0 +1,271 @@
+// api.cu -- the C ABI declared in include/mdh_b200.h (context, fetch, errors).
+
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void mdh_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::reserve(size_t bytes)
+{
+    if (bytes <= cap) return MDH_OK;
+    if (p) {
+        // the buffer may still be in use by work queued on the context's stream
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaFree(p);
+        if (e != cudaSuccess) {
+            mdh_set_error("cudaFree failed: %s", cudaGetErrorString(e));
+            return MDH_ECUDA;
+        }
+        p = nullptr;
+        cap = 0;
+    }
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        mdh_set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        cudaGetLastError();
+        return MDH_ENOMEM;
+    }
+    cap = want;
+    return MDH_OK;
+}
+
+void DevBuf::release()
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+#define CTX_GUARD(ctx)                                                         \
+    do {                                                                       \
+        MDH_REQUIRE((ctx) != nullptr, MDH_EINVAL, "context is NULL");          \
+        MDH_CUDA(cudaSetDevice((ctx)->device));                                \
+    } while (0)
+
+extern "C" {
+
+int mdh_abi_version(void) { return MDH_ABI_VERSION; }
+
+const char *mdh_last_error(void) { return g_err; }
+
+int mdh_ctx_create(int device, void *cuda_stream, mdh_ctx **out)
+{
+    MDH_REQUIRE(out != nullptr, MDH_EINVAL, "out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    MDH_CUDA(cudaGetDeviceCount(&n_dev));
+    MDH_REQUIRE(device >= 0 && device < n_dev, MDH_EINVAL, "device %d out of range (%d visible)",
+                device, n_dev);
+    MDH_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MDH_CUDA(cudaGetDeviceProperties(&prop, device));
+    MDH_REQUIRE(prop.major == 10, MDH_EINVAL,
+                "libmdh_b200 contains sm_100a code only; device %d is sm_%d%d", device,
+                prop.major, prop.minor);
+    mdh_ctx *c = new (std::nothrow) mdh_ctx();
+    MDH_REQUIRE(c != nullptr, MDH_ENOMEM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) {
+        c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            mdh_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+            return MDH_ECUDA;
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return MDH_OK;
+}
+
+int mdh_ctx_destroy(mdh_ctx *c)
+{
+    if (!c) return MDH_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    RdfState &R = c->rdf;
+    R.thr.release(); R.counts.release(); R.raw1.release(); R.raw2.release();
+    R.pk1.release(); R.pk2.release(); R.boxes.release();
+    for (auto &b : R.cell) b.release();
+    if (R.h_boxes_pinned) cudaFreeHost(R.h_boxes_pinned);
+    if (R.ev_boxes) cudaEventDestroy(R.ev_boxes);
+    SqState &S = c->sq;
+    S.qv.release(); S.items.release(); S.qidx.release(); S.d_pairs.release();
+    S.chunks.release(); S.raw.release(); S.rho.release(); S.ssf.release();
+    for (cudaEvent_t e : {c->ev_rdf0, c->ev_rdf1, c->ev_sq0, c->ev_sq1})
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return MDH_OK;
+}
+
+int mdh_sync(mdh_ctx *c)
+{
+    CTX_GUARD(c);
+    MDH_CUDA(cudaStreamSynchronize(c->stream));
+    return MDH_OK;
+}
+
+int mdh_last_kernel_ms(mdh_ctx *c, float *rdf_ms, float *sq_ms)
+{
+    CTX_GUARD(c);
+    MDH_CUDA(cudaStreamSynchronize(c->stream));
+    if (rdf_ms) {
+        *rdf_ms = 0.f;
+        if (c->rdf_timed) MDH_CUDA(cudaEventElapsedTime(rdf_ms, c->ev_rdf0, c->ev_rdf1));
+    }
+    if (sq_ms) {
+        *sq_ms = 0.f;
+        if (c->sq_timed) MDH_CUDA(cudaEventElapsedTime(sq_ms, c->ev_sq0, c->ev_sq1));
+    }
+    return MDH_OK;
+}
+
+int mdh_launch_count(mdh_ctx *c, int64_t *launches)
+{
+    MDH_REQUIRE(c && launches, MDH_EINVAL, "NULL argument");
+    *launches = c->launches;
+    return MDH_OK;
+}
+
+/* ---- seam #1 ---- */
+
+int mdh_rdf_configure(mdh_ctx *c, int64_t n1, int64_t n2, int same_group, int n_bins,
+                      const double *thresholds_sq, double r_lo, double r_hi, int64_t excl1,
+                      int64_t excl2, int drop_axis, int mode, int hist)
+{
+    CTX_GUARD(c);
+    return rdf_configure_impl(c, n1, n2, same_group, n_bins, thresholds_sq, r_lo, r_hi, excl1,
+                              excl2, drop_axis, mode, hist);
+}
+
+int mdh_rdf_accumulate(mdh_ctx *c, const float *pos1, int64_t frame_stride1, const float *pos2,
+                       int64_t frame_stride2, int location, const float *box, int n_frames)
+{
+    CTX_GUARD(c);
+    return rdf_accumulate_impl(c, pos1, frame_stride1, pos2, frame_stride2, location, box,
+                               n_frames);
+}
+
+int mdh_rdf_fetch(mdh_ctx *c, int64_t *counts)
+{
+    CTX_GUARD(c);
+    MDH_REQUIRE(c->rdf.configured, MDH_ESTATE, "rdf: fetch before configure");
+    MDH_REQUIRE(counts != nullptr, MDH_EINVAL, "rdf: counts is NULL");
+    MDH_CUDA(cudaMemcpyAsync(counts, c->rdf.counts.p, sizeof(int64_t) * c->rdf.n_bins,
+                             cudaMemcpyDeviceToHost, c->stream));
+    MDH_CUDA(cudaStreamSynchronize(c->stream));
+    return MDH_OK;
+}
+
+int mdh_rdf_reset(mdh_ctx *c)
+{
+    CTX_GUARD(c);
+    MDH_REQUIRE(c->rdf.configured, MDH_ESTATE, "rdf: reset before configure");
+    MDH_CUDA(cudaMemsetAsync(c->rdf.counts.p, 0, sizeof(int64_t) * c->rdf.n_bins, c->stream));
+    if (c->rdf.evals_dev_init)
+        MDH_CUDA(cudaMemsetAsync(c->rdf.cell[9].p, 0, sizeof(unsigned long long), c->stream));
+    c->rdf.evals = 0;
+    return MDH_OK;
+}
+
+int mdh_rdf_counts_device(mdh_ctx *c, void **dptr)
+{
+    MDH_REQUIRE(c && dptr, MDH_EINVAL, "NULL argument");
+    MDH_REQUIRE(c->rdf.configured, MDH_ESTATE, "rdf: not configured");
+    *dptr = c->rdf.counts.p;
+    return MDH_OK;
+}
+
+int mdh_rdf_pair_evaluations(mdh_ctx *c, int64_t *evals)
+{
+    CTX_GUARD(c);
+    MDH_REQUIRE(evals != nullptr, MDH_EINVAL, "evals is NULL");
+    unsigned long long dev = 0;
+    if (c->rdf.evals_dev_init) {
+        MDH_CUDA(cudaMemcpyAsync(&dev, c->rdf.cell[9].p, sizeof(dev), cudaMemcpyDeviceToHost,
+                                 c->stream));
+        MDH_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    *evals = c->rdf.evals + (int64_t)dev;
+    return MDH_OK;
+}
+
+/* ---- seam #2 ---- */
+
+int mdh_sq_configure(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *group_offsets,
+                     int n_q, const double *wavevectors, const int32_t *lattice_n,
+                     const double *lattice_b, int n_pairs, const int32_t *pairs, int mode)
+{
+    CTX_GUARD(c);
+    return sq_configure_impl(c, n_total, n_groups, group_offsets, n_q, wavevectors, lattice_n,
+                             lattice_b, n_pairs, pairs, mode);
+}
+
+int mdh_sq_accumulate(mdh_ctx *c, const float *pos, int64_t frame_stride, int location,
+                      int n_frames)
+{
+    CTX_GUARD(c);
+    return sq_accumulate_impl(c, pos, frame_stride, location, n_frames);
+}
+
+int mdh_sq_fetch(mdh_ctx *c, double *ssf)
+{
+    CTX_GUARD(c);
+    MDH_REQUIRE(c->sq.configured, MDH_ESTATE, "sq: fetch before configure");
+    MDH_REQUIRE(ssf != nullptr, MDH_EINVAL, "sq: ssf is NULL");
+    MDH_CUDA(cudaMemcpyAsync(ssf, c->sq.ssf.p,
+                             sizeof(double) * (size_t)c->sq.n_pairs * c->sq.n_q,
+                             cudaMemcpyDeviceToHost, c->stream));
+    MDH_CUDA(cudaStreamSynchronize(c->stream));
+    return MDH_OK;
+}
+
+int mdh_sq_reset(mdh_ctx *c)
+{
+    CTX_GUARD(c);
+    MDH_REQUIRE(c->sq.configured, MDH_ESTATE, "sq: reset before configure");
+    MDH_CUDA(cudaMemsetAsync(c->sq.ssf.p, 0, sizeof(double) * (size_t)c->sq.n_pairs * c->sq.n_q,
+                             c->stream));
+    return MDH_OK;
+}
+
+int mdh_sq_accum_device(mdh_ctx *c, void **dptr)
+{
+    MDH_REQUIRE(c && dptr, MDH_EINVAL, "NULL argument");
+    MDH_REQUIRE(c->sq.configured, MDH_ESTATE, "sq: not configured");
+    *dptr = c->sq.ssf.p;
+    return MDH_OK;
+}
+
+int mdh_sq_fetch_rho(mdh_ctx *c, double *rho)
+{
+    CTX_GUARD(c);
+    SqState &S = c->sq;
+    MDH_REQUIRE(S.configured && S.rho_frames > 0, MDH_ESTATE, "sq: no frame has been processed");
+    MDH_REQUIRE(rho != nullptr, MDH_EINVAL, "sq: rho is NULL");
+    const size_t per_frame = (size_t)2 * S.n_rho * S.n_q;
+    MDH_CUDA(cudaMemcpyAsync(rho, S.rho.as<double>() + per_frame * (S.rho_frames - 1),
+                             sizeof(double) * per_frame, cudaMemcpyDeviceToHost, c->stream));
+    MDH_CUDA(cudaStreamSynchronize(c->stream));
+    return MDH_OK;
+}
+
+}  // extern "C"

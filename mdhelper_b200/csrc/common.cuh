@@ -1,0 +1,119 @@
+// common.cuh -- shared declarations of libmdh_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mdh_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmdh_b200 is written for sm_100a (B200) only"
+#endif
+
+void mdh_set_error(const char *fmt, ...);
+
+#define MDH_CUDA(call)                                                          \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess) {                                                \
+            mdh_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,  \
+                          cudaGetErrorString(e_));                              \
+            return MDH_ECUDA;                                                   \
+        }                                                                       \
+    } while (0)
+
+#define MDH_REQUIRE(cond, code, ...)                                            \
+    do {                                                                        \
+        if (!(cond)) {                                                          \
+            mdh_set_error(__VA_ARGS__);                                         \
+            return (code);                                                      \
+        }                                                                       \
+    } while (0)
+
+// Device buffer that only ever grows; owned by the context.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct FrameBox {          // per frame, device side
+    double box[3];         // (double)box_f32
+    double inv[3];         // (double)(float)(1.0 / (double)box_f32)
+};
+
+struct RdfState {
+    bool configured = false;
+    int64_t n1 = 0, n2 = 0;
+    int same = 0, n_bins = 0, drop_axis = -1, mode = 0, hist = 0;
+    int64_t excl1 = 0, excl2 = 0;
+    double r_lo = 0, r_hi = 0, thr_hi = 0;
+    DevBuf thr;            // double[n_bins + 2]: thresholds, then +inf
+    DevBuf counts;         // unsigned long long[n_bins]
+    DevBuf raw1, raw2;     // float[F][n][3] staging for host input
+    DevBuf pk1, pk2;       // float4[F][npad]
+    DevBuf boxes;          // FrameBox[F]
+    DevBuf cell[10];       // cell-list scratch (grids, counts, starts, ranks, sorted, evals)
+    bool evals_dev_init = false;
+    std::vector<FrameBox> h_boxes;
+    FrameBox *h_boxes_pinned = nullptr;   // staging for the async box upload
+    size_t h_boxes_cap = 0;
+    cudaEvent_t ev_boxes = nullptr;       // previous box upload has been consumed
+    int64_t evals = 0;     // all-pairs evaluations (host-side count)
+};
+
+struct SqWorkItem {        // one thread's column segment of the lattice kernels
+    int nx, ny, nz0, len;
+};
+
+struct SqState {
+    bool configured = false;
+    int64_t n_total = 0;
+    int n_groups = 0, n_q = 0, n_pairs = 0, mode = 0, n_rho = 0;
+    bool lattice = false;
+    int nmax[3] = {0, 0, 0};
+    double b[3] = {0, 0, 0};
+    int rz = 0, n_items = 0;
+    std::vector<int64_t> group_offsets;
+    std::vector<int32_t> pairs;
+    DevBuf qv;             // double[n_q][3]
+    DevBuf items;          // SqWorkItem[n_items]
+    DevBuf qidx;           // int[n_items][rz]
+    DevBuf d_pairs;        // int[n_pairs][2]
+    DevBuf chunks;         // int4[n_chunks]: {start, end, rho_row, 0}
+    int n_chunks = 0, chunk_len = 0;
+    DevBuf raw;            // float[F][n][3]
+    DevBuf rho;            // double[F][n_rho][n_q][2]
+    DevBuf ssf;            // double[n_pairs][n_q]
+    int rho_frames = 0;    // frames held in rho from the last batch
+};
+
+struct mdh_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int64_t launches = 0;
+    cudaEvent_t ev_rdf0 = nullptr, ev_rdf1 = nullptr, ev_sq0 = nullptr, ev_sq1 = nullptr;
+    bool rdf_timed = false, sq_timed = false;
+    RdfState rdf;
+    SqState sq;
+};
+
+// rdf.cu
+int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
+                       const double *thr, double r_lo, double r_hi, int64_t e1, int64_t e2,
+                       int drop_axis, int mode, int hist);
+int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *pos2,
+                        int64_t s2, int location, const float *box, int n_frames);
+// sq.cu
+int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *goff,
+                      int n_q, const double *wv, const int32_t *lat_n, const double *lat_b,
+                      int n_pairs, const int32_t *pairs, int mode);
+int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
+                       int n_frames);

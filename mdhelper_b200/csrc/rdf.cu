@@ -1,0 +1,385 @@
+// rdf.cu -- minimum-image pair-distance histogram kernels (seam #1).
+//
+// Replaces, per frame, the reference's radial_histogram
+// (/root/reference/src/mdhelper/analysis/structure.py:32-104), i.e. the
+// third-party MDAnalysis capped_distance (arithmetic: SURVEY.md Appendix A)
+// followed by the exclusion mask and numpy.histogram, without ever
+// materialising the pair list.
+//
+// Per pair (i in group 1, j in group 2), bit for bit what the reference does:
+//     dx_k = (double)(float)(pos2[j][k] - pos1[i][k])          fp32 subtract
+//     s    = (double)inv_k * dx_k            inv_k = (float)(1.0 / box_k)
+//     dx_k = (double)box_k * (s - round(s))
+//     d2   = (dx0*dx0 + dx1*dx1) + dx2*dx2   every product rounded (no FMA)
+// round() is evaluated with the 1.5*2^52 magic-number add (round-half-even);
+// it differs from C round() only when s is exactly k+1/2, where s - round(s)
+// is +-1/2 either way and the squared term is identical.  sqrt is never
+// taken: IEEE sqrt is monotone, so numpy.histogram's "edges[k] <= d < edges[k+1]"
+// is evaluated on d2 against thresholds T[k] = min{x : sqrt(x) >= edges[k]}
+// prepared on the host (mdhelper_b200/analysis/_binning.py).
+//
+// All FP64 arithmetic on the path uses __dmul_rn/__dadd_rn/__dsub_rn so nvcc
+// can never contract it; the file is additionally built with -fmad=false.
+
+#include <string.h>
+
+#include <algorithm>
+
+#include "rdf_device.cuh"
+
+using namespace rdfdev;
+
+namespace {
+
+// ---- all-pairs kernel -----------------------------------------------------------
+
+struct PairParams {
+    const float4 *p1, *p2;
+    int64_t pad1, pad2;            // float4 per frame
+    int n1, n2;
+    const FrameBox *boxes;
+    const double *thr;             // T[0..n_bins]
+    int n_bins, n_words;
+    float g_scale, g_off;
+    int same;
+    int n_jchunks, jtiles_per_chunk, n_jtiles;
+    unsigned long long *counts;
+};
+
+template <int HIST, bool EXCL>
+__global__ void __launch_bounds__(kThreads, 2) rdf_allpairs_kernel(const PairParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    double2 *sT2 = reinterpret_cast<double2 *>(smem);
+    float4 *sJ = reinterpret_cast<float4 *>(smem + align16(sizeof(double2) * P.n_bins));
+    unsigned *sH = reinterpret_cast<unsigned *>(sJ + 2 * kTile);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.y;
+    const int it = blockIdx.x / P.n_jchunks;
+    const int jc = blockIdx.x - it * P.n_jchunks;
+    int jt0 = jc * P.jtiles_per_chunk;
+    const int jt1 = min(P.n_jtiles, jt0 + P.jtiles_per_chunk);
+    if (P.same) jt0 = max(jt0, it);       // upper triangle of tile pairs
+    if (jt0 >= jt1) return;
+
+    const int n_bins = P.n_bins;
+    for (int k = tid; k < n_bins; k += kThreads)
+        sT2[k] = make_double2(P.thr[k], P.thr[k + 1]);
+    const int n_hist_words = (HIST == MDH_HIST_WARP_ATOMIC)
+                                 ? kWarps * n_bins
+                                 : kWarps * P.n_words * 32 + n_bins;
+    for (int k = tid; k < n_hist_words; k += kThreads) sH[k] = 0;
+
+    const float4 *f1 = P.p1 + (int64_t)frame * P.pad1;
+    const float4 *f2 = P.same ? f1 : P.p2 + (int64_t)frame * P.pad2;
+    const FrameBox fb = P.boxes[frame];
+
+    float xi[kIPT], yi[kIPT], zi[kIPT];
+    int gi[kIPT];
+    unsigned wv[kIPT];
+#pragma unroll
+    for (int ii = 0; ii < kIPT; ++ii) {
+        const int i = it * kTile + ii * kThreads + tid;
+        wv[ii] = i < P.n1 ? 1u : 0u;
+        const float4 a = f1[min(i, P.n1 - 1)];
+        xi[ii] = a.x; yi[ii] = a.y; zi[ii] = a.z; gi[ii] = __float_as_int(a.w);
+    }
+
+    unsigned *myhist = (HIST == MDH_HIST_WARP_ATOMIC)
+                           ? sH + warp * n_bins
+                           : sH + (size_t)warp * P.n_words * 32;
+    unsigned *bhist = sH + (size_t)kWarps * P.n_words * 32;   // LANE_PRIVATE only
+
+    // stage the first j tile (packed buffers are padded to whole tiles)
+    auto stage_tile = [&](int jt, int buf) {
+        const float4 *src = f2 + (int64_t)jt * kTile;
+        float4 *dst = sJ + buf * kTile;
+#pragma unroll
+        for (int q = 0; q < kIPT; ++q)
+            __pipeline_memcpy_async(dst + q * kThreads + tid, src + q * kThreads + tid,
+                                    sizeof(float4));
+        __pipeline_commit();
+    };
+    stage_tile(jt0, 0);
+
+    int buf = 0;
+    for (int jt = jt0; jt < jt1; ++jt) {
+        if (jt + 1 < jt1) {
+            stage_tile(jt + 1, buf ^ 1);
+            __pipeline_wait_prior(1);
+        } else {
+            __pipeline_wait_prior(0);
+        }
+        __syncthreads();
+
+        const unsigned weight = (P.same && jt > it) ? 2u : 1u;
+        const int jn = min(kTile, P.n2 - jt * kTile);
+        const float4 *tile = sJ + buf * kTile;
+
+        if (HIST == MDH_HIST_WARP_ATOMIC) {
+#pragma unroll 2
+            for (int jj = 0; jj < jn; ++jj) {
+                const float4 pj = tile[jj];
+#pragma unroll
+                for (int ii = 0; ii < kIPT; ++ii) {
+                    const double d2 = pair_d2(xi[ii], yi[ii], zi[ii], pj, fb);
+                    int k = bin_index(d2, sT2, n_bins, P.g_scale, P.g_off);
+                    if (EXCL && gi[ii] == __float_as_int(pj.w)) k = n_bins;
+                    if (k < n_bins && wv[ii]) atomicAdd(&myhist[k], weight);
+                }
+            }
+        } else {
+            constexpr int kSeg = 254 / kIPT;      // increments per lane per flush <= 254
+            for (int j0 = 0; j0 < jn; j0 += kSeg) {
+                const int j1 = min(jn, j0 + kSeg);
+#pragma unroll 2
+                for (int jj = j0; jj < j1; ++jj) {
+                    const float4 pj = tile[jj];
+#pragma unroll
+                    for (int ii = 0; ii < kIPT; ++ii) {
+                        const double d2 = pair_d2(xi[ii], yi[ii], zi[ii], pj, fb);
+                        int k = bin_index(d2, sT2, n_bins, P.g_scale, P.g_off);
+                        if (EXCL && gi[ii] == __float_as_int(pj.w)) k = n_bins;
+                        unsigned *w = myhist + (k >> 2) * 32 + lane;
+                        *w += wv[ii] << ((k & 3) * 8);
+                    }
+                }
+                priv_flush(myhist, bhist, P.n_words, n_bins, lane, weight);
+            }
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+
+    // merge into the global int64 histogram
+    for (int k = tid; k < n_bins; k += kThreads) {
+        unsigned long long s = 0;
+        if (HIST == MDH_HIST_WARP_ATOMIC) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += sH[w * n_bins + k];
+        } else {
+            s = bhist[k];
+        }
+        if (s) atomicAdd(&P.counts[k], s);
+    }
+}
+
+template <int HIST, bool EXCL>
+int launch_allpairs(mdh_ctx *c, const PairParams &P, dim3 grid)
+{
+    const size_t smem = pair_smem_bytes<HIST>(P.n_bins, P.n_words);
+    auto kern = rdf_allpairs_kernel<HIST, EXCL>;
+    MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    kern<<<grid, kThreads, smem, c->stream>>>(P);
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    return MDH_OK;
+}
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------
+
+int rdf_cells_accumulate(mdh_ctx *c, int n_frames);   // rdf_cells.cu
+
+int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
+                       const double *thr, double r_lo, double r_hi, int64_t e1, int64_t e2,
+                       int drop_axis, int mode, int hist)
+{
+    RdfState &R = c->rdf;
+    MDH_REQUIRE(n1 > 0 && n2 > 0, MDH_EINVAL, "rdf: both groups must be non-empty");
+    MDH_REQUIRE(n1 < (1ll << 30) && n2 < (1ll << 30), MDH_EINVAL,
+                "rdf: at most 2^30 particles per group");
+    MDH_REQUIRE(!same || n1 == n2, MDH_EINVAL, "rdf: same_group requires n1 == n2");
+    MDH_REQUIRE(n_bins >= 1 && n_bins <= 65536, MDH_EINVAL,
+                "rdf: n_bins must be in [1, 65536]");
+    MDH_REQUIRE(thr != nullptr, MDH_EINVAL, "rdf: thresholds_sq is NULL");
+    for (int k = 0; k < n_bins; ++k)
+        MDH_REQUIRE(thr[k] < thr[k + 1], MDH_EINVAL,
+                    "rdf: thresholds_sq must be strictly increasing (k=%d)", k);
+    MDH_REQUIRE(thr[0] >= 0.0, MDH_EINVAL, "rdf: thresholds_sq[0] must be >= 0");
+    MDH_REQUIRE((e1 > 0) == (e2 > 0) && e1 >= 0, MDH_EINVAL,
+                "rdf: exclusion sizes must both be positive or both zero");
+    MDH_REQUIRE(drop_axis >= -1 && drop_axis <= 2, MDH_EINVAL, "rdf: invalid drop_axis");
+    MDH_REQUIRE(mode >= MDH_RDF_AUTO && mode <= MDH_RDF_CELLS, MDH_EINVAL,
+                "rdf: invalid mode");
+    MDH_REQUIRE(hist >= MDH_HIST_AUTO && hist <= MDH_HIST_LANE_PRIVATE, MDH_EINVAL,
+                "rdf: invalid hist");
+    MDH_REQUIRE(r_hi > r_lo, MDH_EINVAL, "rdf: empty range");
+
+    const int n_words = (n_bins + 1 + 3) / 4;
+    if (hist == MDH_HIST_AUTO)
+        hist = pair_smem_bytes<MDH_HIST_LANE_PRIVATE>(n_bins, n_words) <= 100 * 1024
+                   ? MDH_HIST_LANE_PRIVATE : MDH_HIST_WARP_ATOMIC;
+    const size_t need = hist == MDH_HIST_LANE_PRIVATE
+                            ? pair_smem_bytes<MDH_HIST_LANE_PRIVATE>(n_bins, n_words)
+                            : pair_smem_bytes<MDH_HIST_WARP_ATOMIC>(n_bins, n_words);
+    MDH_REQUIRE(need <= kMaxSmem, MDH_EINVAL,
+                "rdf: n_bins=%d needs %zu bytes of shared memory (> %zu)", n_bins, need,
+                kMaxSmem);
+
+    R.configured = false;
+    R.n1 = n1; R.n2 = n2; R.same = same ? 1 : 0; R.n_bins = n_bins;
+    R.excl1 = e1; R.excl2 = e2; R.drop_axis = drop_axis; R.mode = mode; R.hist = hist;
+    R.r_lo = r_lo; R.r_hi = r_hi; R.thr_hi = thr[n_bins];
+    R.evals = 0;
+
+    if (int rc = R.thr.reserve(sizeof(double) * (n_bins + 2))) return rc;
+    if (int rc = R.counts.reserve(sizeof(unsigned long long) * n_bins)) return rc;
+    std::vector<double> t(thr, thr + n_bins + 1);
+    t.push_back(INFINITY);
+    MDH_CUDA(cudaMemcpyAsync(R.thr.p, t.data(), sizeof(double) * t.size(),
+                             cudaMemcpyHostToDevice, c->stream));
+    MDH_CUDA(cudaMemsetAsync(R.counts.p, 0, sizeof(unsigned long long) * n_bins, c->stream));
+    MDH_CUDA(cudaStreamSynchronize(c->stream));   // t is a local
+    R.configured = true;
+    return MDH_OK;
+}
+
+static int rdf_upload_group(mdh_ctx *c, const float *pos, int64_t stride, int location,
+                            int64_t n, int64_t npad, int64_t excl, int n_frames,
+                            DevBuf &raw, DevBuf &pk)
+{
+    RdfState &R = c->rdf;
+    MDH_REQUIRE(pos != nullptr, MDH_EINVAL, "rdf: coordinate pointer is NULL");
+    MDH_REQUIRE(stride >= 3 * n, MDH_EINVAL, "rdf: frame_stride (%lld) < 3*n (%lld)",
+                (long long)stride, (long long)(3 * n));
+    if (int rc = pk.reserve(sizeof(float4) * npad * n_frames)) return rc;
+    const float *dsrc = pos;
+    int64_t dstride = stride;
+    if (location == MDH_HOST) {
+        if (int rc = raw.reserve(sizeof(float) * 3 * n * n_frames)) return rc;
+        MDH_CUDA(cudaMemcpy2DAsync(raw.p, sizeof(float) * 3 * n, pos, sizeof(float) * stride,
+                                   sizeof(float) * 3 * n, n_frames, cudaMemcpyHostToDevice,
+                                   c->stream));
+        dsrc = raw.as<float>();
+        dstride = 3 * n;
+    }
+    dim3 grid((unsigned)std::min<int64_t>((npad + 255) / 256, 1024), n_frames);
+    rdf_pack_kernel<<<grid, 256, 0, c->stream>>>(dsrc, dstride, pk.as<float4>(), n, npad, excl,
+                                                 R.drop_axis);
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    return MDH_OK;
+}
+
+int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *pos2,
+                        int64_t s2, int location, const float *box, int n_frames)
+{
+    RdfState &R = c->rdf;
+    MDH_REQUIRE(R.configured, MDH_ESTATE, "rdf: accumulate before configure");
+    MDH_REQUIRE(n_frames >= 1 && n_frames <= 65535, MDH_EINVAL,
+                "rdf: n_frames per call must be in [1, 65535]");
+    MDH_REQUIRE(box != nullptr, MDH_EINVAL, "rdf: box is NULL");
+    MDH_REQUIRE(location == MDH_HOST || location == MDH_DEVICE, MDH_EINVAL,
+                "rdf: invalid location");
+
+    // per-frame box: box_k and inv_k = (float)(1.0 / (double)box_k)  (Appendix A item 3)
+    R.h_boxes.resize(n_frames);
+    float min_edge = FLT_MAX;
+    for (int f = 0; f < n_frames; ++f)
+        for (int k = 0; k < 3; ++k) {
+            const float b = box[3 * f + k];
+            MDH_REQUIRE(b > FLT_EPSILON && std::isfinite(b), MDH_EINVAL,
+                        "rdf: box edge %d of frame %d is not a positive length", k, f);
+            R.h_boxes[f].box[k] = (double)b;
+            R.h_boxes[f].inv[k] = (double)(float)(1.0 / (double)b);
+            if (k != R.drop_axis) min_edge = std::min(min_edge, b);
+        }
+    if (int rc = R.boxes.reserve(sizeof(FrameBox) * n_frames)) return rc;
+    // upload through a pinned staging buffer so the call stays asynchronous; the
+    // event guards the buffer against being rewritten before the copy has run
+    if (R.h_boxes_cap < (size_t)n_frames) {
+        if (R.h_boxes_pinned) {
+            MDH_CUDA(cudaStreamSynchronize(c->stream));
+            MDH_CUDA(cudaFreeHost(R.h_boxes_pinned));
+            R.h_boxes_pinned = nullptr;
+        }
+        R.h_boxes_cap = std::max<size_t>(256, (size_t)n_frames);
+        MDH_CUDA(cudaMallocHost(&R.h_boxes_pinned, sizeof(FrameBox) * R.h_boxes_cap));
+    }
+    if (!R.ev_boxes) MDH_CUDA(cudaEventCreateWithFlags(&R.ev_boxes, cudaEventDisableTiming));
+    else MDH_CUDA(cudaEventSynchronize(R.ev_boxes));
+    memcpy(R.h_boxes_pinned, R.h_boxes.data(), sizeof(FrameBox) * n_frames);
+    MDH_CUDA(cudaMemcpyAsync(R.boxes.p, R.h_boxes_pinned, sizeof(FrameBox) * n_frames,
+                             cudaMemcpyHostToDevice, c->stream));
+    MDH_CUDA(cudaEventRecord(R.ev_boxes, c->stream));
+
+    const int64_t pad1 = (R.n1 + kTile - 1) / kTile * kTile;
+    const int64_t pad2 = (R.n2 + kTile - 1) / kTile * kTile;
+    if (int rc = rdf_upload_group(c, pos1, s1, location, R.n1, pad1, R.excl1, n_frames,
+                                  R.raw1, R.pk1)) return rc;
+    if (!R.same)
+        if (int rc = rdf_upload_group(c, pos2, s2, location, R.n2, pad2, R.excl2, n_frames,
+                                      R.raw2, R.pk2)) return rc;
+
+    int mode = R.mode;
+    if (mode == MDH_RDF_AUTO) {
+        // cells pay off when the cut-off sphere is a small part of the box
+        const double r_cut = sqrt(R.thr_hi);
+        const bool cells_ok = min_edge / (r_cut * 1.00001) >= 4.0 &&
+                              (double)R.n1 * (double)R.n2 >= 4e6 && R.drop_axis < 0;
+        mode = cells_ok ? MDH_RDF_CELLS : MDH_RDF_ALLPAIRS;
+    }
+
+    if (!c->ev_rdf0) {
+        MDH_CUDA(cudaEventCreate(&c->ev_rdf0));
+        MDH_CUDA(cudaEventCreate(&c->ev_rdf1));
+    }
+    MDH_CUDA(cudaEventRecord(c->ev_rdf0, c->stream));
+
+    if (mode == MDH_RDF_CELLS) {
+        if (int rc = rdf_cells_accumulate(c, n_frames)) return rc;
+    } else {
+        PairParams P;
+        P.p1 = R.pk1.as<float4>();
+        P.p2 = R.same ? P.p1 : R.pk2.as<float4>();
+        P.pad1 = pad1; P.pad2 = R.same ? pad1 : pad2;
+        P.n1 = (int)R.n1; P.n2 = (int)R.n2;
+        P.boxes = R.boxes.as<FrameBox>();
+        P.thr = R.thr.as<double>();
+        P.n_bins = R.n_bins;
+        P.n_words = (R.n_bins + 1 + 3) / 4;
+        P.g_scale = (float)(R.n_bins / (R.r_hi - R.r_lo));
+        P.g_off = (float)(-R.r_lo * R.n_bins / (R.r_hi - R.r_lo));
+        P.same = R.same;
+        P.counts = R.counts.as<unsigned long long>();
+        const int n_itiles = (int)(pad1 / kTile);
+        P.n_jtiles = (int)(P.pad2 / kTile);
+        const int64_t target = (int64_t)c->sm_count * 2 * 6;
+        int64_t n_jchunks = (target + (int64_t)n_itiles * n_frames - 1) /
+                            ((int64_t)n_itiles * n_frames);
+        n_jchunks = std::max<int64_t>(1, std::min<int64_t>(n_jchunks, P.n_jtiles));
+        n_jchunks = std::max<int64_t>(n_jchunks, (P.n_jtiles + 4095) / 4096);
+        P.jtiles_per_chunk = (int)((P.n_jtiles + n_jchunks - 1) / n_jchunks);
+        P.n_jchunks = (int)((P.n_jtiles + P.jtiles_per_chunk - 1) / P.jtiles_per_chunk);
+        dim3 grid((unsigned)(n_itiles * P.n_jchunks), (unsigned)n_frames);
+        const bool excl = R.excl1 > 0;
+        int rc;
+        if (R.hist == MDH_HIST_LANE_PRIVATE)
+            rc = excl ? launch_allpairs<MDH_HIST_LANE_PRIVATE, true>(c, P, grid)
+                      : launch_allpairs<MDH_HIST_LANE_PRIVATE, false>(c, P, grid);
+        else
+            rc = excl ? launch_allpairs<MDH_HIST_WARP_ATOMIC, true>(c, P, grid)
+                      : launch_allpairs<MDH_HIST_WARP_ATOMIC, false>(c, P, grid);
+        if (rc) return rc;
+        // pair evaluations the kernel performs (upper-triangle tiles when same_group)
+        int64_t ev;
+        if (R.same) {
+            ev = 0;
+            for (int a = 0; a < n_itiles; ++a) {
+                const int64_t ca = std::min<int64_t>(kTile, R.n1 - (int64_t)a * kTile);
+                const int64_t rest = R.n1 - (int64_t)a * kTile;   // j >= a*kTile
+                ev += ca * rest;
+            }
+        } else {
+            ev = R.n1 * R.n2;
+        }
+        R.evals += ev * n_frames;
+    }
+    MDH_CUDA(cudaEventRecord(c->ev_rdf1, c->stream));
+    c->rdf_timed = true;
+    return MDH_OK;
+}

@@ -1,0 +1,360 @@
+// rdf_cells.cu -- cell-list variant of the pair histogram (cut-off runs).
+//
+// Same per-pair arithmetic and binning as rdf.cu (rdf_device.cuh); only the set
+// of candidate pairs shrinks: each frame's particles are counting-sorted into
+// cells of edge >= r_cut*(1+1e-5) and every i visits the 27 surrounding cells
+// of the j group.  This is the role MDAnalysis' grid search ("nsgrid") plays
+// behind capped_distance for the reference (call site
+// /root/reference/src/mdhelper/analysis/structure.py:93-96; SURVEY.md Appendix A
+// items 2 and 4).  Counts are identical to the all-pairs kernel by construction:
+// a pair closer than r_cut always lies in adjacent cells, and every other
+// candidate falls above the last threshold and is not counted.
+//
+// Ordered pairs are enumerated directly (i over group 1, j over group 2, both
+// orders and the self pair when the groups coincide), as the reference counts them.
+
+#include <algorithm>
+
+#include "rdf_device.cuh"
+
+using namespace rdfdev;
+
+namespace {
+
+struct CellGrid {          // per frame
+    double box[3];
+    double inv_w[3];       // nc / box
+    int nc[3];
+    int ncell;
+};
+
+__device__ __forceinline__ int cell_coord(float x, double box, double inv_w, int nc)
+{
+    double w = (double)x;
+    w -= floor(w / box) * box;               // into [0, box) for cell assignment only
+    int c = (int)(w * inv_w);
+    return min(max(c, 0), nc - 1);
+}
+
+__device__ __forceinline__ int cell_id(const float4 &p, const CellGrid &g, int &cx, int &cy,
+                                       int &cz)
+{
+    cx = cell_coord(p.x, g.box[0], g.inv_w[0], g.nc[0]);
+    cy = cell_coord(p.y, g.box[1], g.inv_w[1], g.nc[1]);
+    cz = cell_coord(p.z, g.box[2], g.inv_w[2], g.nc[2]);
+    return (cz * g.nc[1] + cy) * g.nc[0] + cx;
+}
+
+// count particles per cell; the old counter value is the particle's rank in its cell
+__global__ void cells_count_kernel(const float4 *__restrict__ p, int64_t npad, int n,
+                                   const CellGrid *__restrict__ grids, int *__restrict__ cnt,
+                                   int cstride, int *__restrict__ rank)
+{
+    const int frame = blockIdx.y;
+    const CellGrid g = grids[frame];
+    const float4 *pf = p + (int64_t)frame * npad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int cx, cy, cz;
+        const int c = cell_id(pf[i], g, cx, cy, cz);
+        rank[(int64_t)frame * n + i] = atomicAdd(&cnt[(int64_t)frame * cstride + c], 1);
+    }
+}
+
+// exclusive scan of the per-cell counts, one block per frame
+__global__ void __launch_bounds__(1024) cells_scan_kernel(const int *__restrict__ cnt,
+                                                          int *__restrict__ start, int cstride,
+                                                          const CellGrid *__restrict__ grids)
+{
+    __shared__ int warp_sums[32];
+    const int frame = blockIdx.x;
+    const int ncell = grids[frame].ncell;
+    const int *c = cnt + (int64_t)frame * cstride;
+    int *s = start + (int64_t)frame * cstride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (ncell + 1023) / 1024;
+    const int b = tid * chunk, e = min(ncell, b + chunk);
+    int local = 0;
+    for (int k = b; k < e; ++k) local += c[k];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    int run = incl - local + (warp ? warp_sums[warp - 1] : 0);
+    for (int k = b; k < e; ++k) {
+        s[k] = run;
+        run += c[k];
+    }
+    if (tid == 1023) s[ncell] = warp_sums[31];
+}
+
+__global__ void cells_scatter_kernel(const float4 *__restrict__ p, int64_t npad, int n,
+                                     const CellGrid *__restrict__ grids,
+                                     const int *__restrict__ start, int cstride,
+                                     const int *__restrict__ rank, float4 *__restrict__ sorted)
+{
+    const int frame = blockIdx.y;
+    const CellGrid g = grids[frame];
+    const float4 *pf = p + (int64_t)frame * npad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 v = pf[i];
+        int cx, cy, cz;
+        const int c = cell_id(v, g, cx, cy, cz);
+        const int dst = start[(int64_t)frame * cstride + c] + rank[(int64_t)frame * n + i];
+        sorted[(int64_t)frame * n + dst] = v;
+    }
+}
+
+struct CellParams {
+    const float4 *s1, *s2;        // cell-sorted particles, [F][n]
+    int n1, n2;
+    const int *start2;            // [F][cstride]
+    int cstride;
+    const CellGrid *grids;
+    const FrameBox *boxes;
+    const double *thr;
+    int n_bins, n_words;
+    float g_scale, g_off;
+    unsigned long long *counts;
+    unsigned long long *evals;
+};
+
+template <int HIST>
+__host__ __device__ inline size_t cells_smem_bytes(int n_bins, int n_words)
+{
+    size_t b = align16(sizeof(double2) * n_bins);
+    if (HIST == MDH_HIST_WARP_ATOMIC) b += sizeof(unsigned) * kWarps * n_bins;
+    else b += sizeof(unsigned) * ((size_t)kWarps * n_words * 32 + n_bins);
+    return b;
+}
+
+template <int HIST, bool EXCL>
+__global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    double2 *sT2 = reinterpret_cast<double2 *>(smem);
+    unsigned *sH = reinterpret_cast<unsigned *>(smem + align16(sizeof(double2) * P.n_bins));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.y;
+    const int n_bins = P.n_bins;
+    for (int k = tid; k < n_bins; k += kThreads)
+        sT2[k] = make_double2(P.thr[k], P.thr[k + 1]);
+    const int n_hist_words = (HIST == MDH_HIST_WARP_ATOMIC)
+                                 ? kWarps * n_bins
+                                 : kWarps * P.n_words * 32 + n_bins;
+    for (int k = tid; k < n_hist_words; k += kThreads) sH[k] = 0;
+    __syncthreads();
+
+    unsigned *myhist = (HIST == MDH_HIST_WARP_ATOMIC)
+                           ? sH + warp * n_bins
+                           : sH + (size_t)warp * P.n_words * 32;
+    unsigned *bhist = sH + (size_t)kWarps * P.n_words * 32;
+
+    const CellGrid g = P.grids[frame];
+    const FrameBox fb = P.boxes[frame];
+    const float4 *s1 = P.s1 + (int64_t)frame * P.n1;
+    const float4 *s2 = P.s2 + (int64_t)frame * P.n2;
+    const int *start = P.start2 + (int64_t)frame * P.cstride;
+
+    const int i = blockIdx.x * kThreads + tid;
+    const bool valid = i < P.n1;
+    const float4 pi = s1[min(i, P.n1 - 1)];
+    const int gi = __float_as_int(pi.w);
+    int cx, cy, cz;
+    cell_id(pi, g, cx, cy, cz);
+
+    int steps = 0;                       // warp-uniform: increments since the last flush
+    unsigned long long my_evals = 0;
+
+    auto sweep = [&](int b, int len) {
+        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+        my_evals += len;
+        for (int t = 0; t < maxlen; ++t) {
+            const bool act = t < len;
+            const float4 pj = __ldg(s2 + (act ? b + t : 0));
+            const double d2 = pair_d2(pi.x, pi.y, pi.z, pj, fb);
+            int k = bin_index(d2, sT2, n_bins, P.g_scale, P.g_off);
+            if (EXCL && gi == __float_as_int(pj.w)) k = n_bins;
+            if (!act) k = n_bins;
+            if (HIST == MDH_HIST_WARP_ATOMIC) {
+                if (k < n_bins) atomicAdd(&myhist[k], 1u);
+            } else {
+                unsigned *w = myhist + (k >> 2) * 32 + lane;
+                *w += 1u << ((k & 3) * 8);
+                if (++steps == 254) {
+                    priv_flush(myhist, bhist, P.n_words, n_bins, lane, 1u);
+                    steps = 0;
+                }
+            }
+        }
+    };
+
+    for (int dz = -1; dz <= 1; ++dz) {
+        int z = cz + dz;
+        z += (z < 0) ? g.nc[2] : 0;
+        z -= (z >= g.nc[2]) ? g.nc[2] : 0;
+        for (int dy = -1; dy <= 1; ++dy) {
+            int y = cy + dy;
+            y += (y < 0) ? g.nc[1] : 0;
+            y -= (y >= g.nc[1]) ? g.nc[1] : 0;
+            const int row = (z * g.nc[1] + y) * g.nc[0];
+            // x-adjacent cells are contiguous in the sorted array
+            const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nc[0] - 1);
+            const int b0 = start[row + xa];
+            sweep(b0, valid ? start[row + xb + 1] - b0 : 0);
+            // periodic wrap of the x stencil
+            const int xw = (cx == 0) ? g.nc[0] - 1 : (cx == g.nc[0] - 1 ? 0 : -1);
+            const int bw = xw >= 0 ? start[row + xw] : 0;
+            sweep(bw, (valid && xw >= 0) ? start[row + xw + 1] - bw : 0);
+        }
+    }
+    if (HIST == MDH_HIST_LANE_PRIVATE)
+        priv_flush(myhist, bhist, P.n_words, n_bins, lane, 1u);
+    __syncthreads();
+
+    for (int k = tid; k < n_bins; k += kThreads) {
+        unsigned long long s = 0;
+        if (HIST == MDH_HIST_WARP_ATOMIC) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += sH[w * n_bins + k];
+        } else {
+            s = bhist[k];
+        }
+        if (s) atomicAdd(&P.counts[k], s);
+    }
+    // evaluations actually performed (for the roofline bookkeeping)
+    for (int o = 16; o; o >>= 1) my_evals += __shfl_xor_sync(0xffffffffu, my_evals, o);
+    if (lane == 0 && my_evals) atomicAdd(P.evals, my_evals);
+}
+
+template <int HIST, bool EXCL>
+int launch_cells(mdh_ctx *c, const CellParams &P, dim3 grid)
+{
+    const size_t smem = cells_smem_bytes<HIST>(P.n_bins, P.n_words);
+    auto kern = rdf_cells_kernel<HIST, EXCL>;
+    MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    kern<<<grid, kThreads, smem, c->stream>>>(P);
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    return MDH_OK;
+}
+
+int sort_group(mdh_ctx *c, const float4 *pk, int64_t npad, int n, int n_frames,
+               const CellGrid *grids, int cstride, DevBuf &cnt, DevBuf &start, DevBuf &rank,
+               DevBuf &sorted)
+{
+    if (int rc = cnt.reserve(sizeof(int) * (size_t)cstride * n_frames)) return rc;
+    if (int rc = start.reserve(sizeof(int) * (size_t)cstride * n_frames)) return rc;
+    if (int rc = rank.reserve(sizeof(int) * (size_t)n * n_frames)) return rc;
+    if (int rc = sorted.reserve(sizeof(float4) * (size_t)n * n_frames)) return rc;
+    MDH_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int) * (size_t)cstride * n_frames, c->stream));
+    dim3 grid((unsigned)std::min((n + 255) / 256, 2048), n_frames);
+    cells_count_kernel<<<grid, 256, 0, c->stream>>>(pk, npad, n, grids, cnt.as<int>(), cstride,
+                                                    rank.as<int>());
+    MDH_CUDA(cudaGetLastError());
+    cells_scan_kernel<<<n_frames, 1024, 0, c->stream>>>(cnt.as<int>(), start.as<int>(), cstride,
+                                                        grids);
+    MDH_CUDA(cudaGetLastError());
+    cells_scatter_kernel<<<grid, 256, 0, c->stream>>>(pk, npad, n, grids, start.as<int>(),
+                                                      cstride, rank.as<int>(),
+                                                      sorted.as<float4>());
+    MDH_CUDA(cudaGetLastError());
+    c->launches += 3;
+    return MDH_OK;
+}
+
+}  // namespace
+
+// Called from rdf_accumulate_impl after the packed float4 arrays and the FrameBox
+// array of the batch are on the device.
+int rdf_cells_accumulate(mdh_ctx *c, int n_frames)
+{
+    RdfState &R = c->rdf;
+    MDH_REQUIRE(R.drop_axis < 0, MDH_EINVAL, "rdf: cell-list mode does not support drop_axis");
+    const double r_cut = sqrt(R.thr_hi) * 1.00001;
+    std::vector<CellGrid> grids(n_frames);
+    int ncell_max = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        CellGrid &g = grids[f];
+        double ncell = 1;
+        for (int k = 0; k < 3; ++k) {
+            g.box[k] = R.h_boxes[f].box[k];
+            int nc = (int)floor(g.box[k] / r_cut);
+            MDH_REQUIRE(nc >= 3, MDH_EINVAL,
+                        "rdf: cell-list mode needs box edge >= 3*r_max (frame %d axis %d)", f, k);
+            g.nc[k] = std::min(nc, 160);
+            ncell *= g.nc[k];
+        }
+        // keep at least ~2 particles per cell on average
+        const double want = std::max(27.0, (double)std::max(R.n1, R.n2) / 2.0);
+        while (ncell > want) {
+            int kmax = 0;
+            for (int k = 1; k < 3; ++k) if (g.nc[k] > g.nc[kmax]) kmax = k;
+            if (g.nc[kmax] <= 3) break;
+            ncell = ncell / g.nc[kmax] * (g.nc[kmax] - 1);
+            g.nc[kmax]--;
+        }
+        for (int k = 0; k < 3; ++k) g.inv_w[k] = g.nc[k] / g.box[k];
+        g.ncell = g.nc[0] * g.nc[1] * g.nc[2];
+        ncell_max = std::max(ncell_max, g.ncell);
+    }
+    const int cstride = ncell_max + 1;
+    DevBuf &d_grids = R.cell[0];
+    if (int rc = d_grids.reserve(sizeof(CellGrid) * n_frames)) return rc;
+    MDH_CUDA(cudaMemcpyAsync(d_grids.p, grids.data(), sizeof(CellGrid) * n_frames,
+                             cudaMemcpyHostToDevice, c->stream));
+    MDH_CUDA(cudaStreamSynchronize(c->stream));      // grids is a local
+
+    const int64_t pad1 = (R.n1 + kTile - 1) / kTile * kTile;
+    const int64_t pad2 = (R.n2 + kTile - 1) / kTile * kTile;
+    if (int rc = sort_group(c, R.pk1.as<float4>(), pad1, (int)R.n1, n_frames,
+                            d_grids.as<CellGrid>(), cstride, R.cell[1], R.cell[2], R.cell[3],
+                            R.cell[4])) return rc;
+    if (!R.same)
+        if (int rc = sort_group(c, R.pk2.as<float4>(), pad2, (int)R.n2, n_frames,
+                                d_grids.as<CellGrid>(), cstride, R.cell[5], R.cell[6],
+                                R.cell[7], R.cell[8])) return rc;
+    if (int rc = R.cell[9].reserve(sizeof(unsigned long long))) return rc;
+    if (!R.evals_dev_init) {
+        MDH_CUDA(cudaMemsetAsync(R.cell[9].p, 0, sizeof(unsigned long long), c->stream));
+        R.evals_dev_init = true;
+    }
+
+    CellParams P;
+    P.s1 = R.cell[4].as<float4>();
+    P.s2 = R.same ? P.s1 : R.cell[8].as<float4>();
+    P.n1 = (int)R.n1; P.n2 = (int)R.n2;
+    P.start2 = R.same ? R.cell[2].as<int>() : R.cell[6].as<int>();
+    P.cstride = cstride;
+    P.grids = d_grids.as<CellGrid>();
+    P.boxes = R.boxes.as<FrameBox>();
+    P.thr = R.thr.as<double>();
+    P.n_bins = R.n_bins;
+    P.n_words = (R.n_bins + 1 + 3) / 4;
+    P.g_scale = (float)(R.n_bins / (R.r_hi - R.r_lo));
+    P.g_off = (float)(-R.r_lo * R.n_bins / (R.r_hi - R.r_lo));
+    P.counts = R.counts.as<unsigned long long>();
+    P.evals = R.cell[9].as<unsigned long long>();
+    dim3 grid((unsigned)((R.n1 + kThreads - 1) / kThreads), (unsigned)n_frames);
+    const bool excl = R.excl1 > 0;
+    if (R.hist == MDH_HIST_LANE_PRIVATE)
+        return excl ? launch_cells<MDH_HIST_LANE_PRIVATE, true>(c, P, grid)
+                    : launch_cells<MDH_HIST_LANE_PRIVATE, false>(c, P, grid);
+    return excl ? launch_cells<MDH_HIST_WARP_ATOMIC, true>(c, P, grid)
+                : launch_cells<MDH_HIST_WARP_ATOMIC, false>(c, P, grid);
+}

@@ -1,0 +1,473 @@
+// sq.cu -- direct-sum structure factor kernels (seam #2).
+//
+// Replaces, per frame, the reference's
+//     rho[i] = sum_j exp(i q_i . r_j)
+// (delta_fourier_transform_sum_2d_2d and its prange twin,
+// /root/reference/src/mdhelper/algorithm/accelerated.py:81-165) and the
+// accumulation that follows it in StructureFactor._single_frame
+// (/root/reference/src/mdhelper/analysis/structure.py:1481-1508):
+//     ssf[p] += |rho_j|^2              (j == k, or all particles when mode=None)
+//     ssf[p] += 2 Re(rho_j conj(rho_k))  (j != k)
+// Normalisation, unique-|q| grouping and sorting stay on the host (numpy).
+//
+// Kernels
+//   sq_lattice_kernel<T, RZ>  wavevectors on the reciprocal lattice, q = n * b
+//       (the reference's default grid, structure.py:1376-1416).  exp(i q.r)
+//       factorises into per-axis phase factors E_a(n) = exp(i n b_a r_a): each
+//       block builds E_a(0..nmax_a) for a sub-chunk of particles in shared memory
+//       (one fp64 sincos per particle and axis, then the recurrence
+//       E(n+1) = E(n) E(1)), and each thread owns one (nx, ny) column segment of
+//       up to RZ wavevectors with register accumulators:
+//           A = E_x(nx) E_y(ny);   acc[r] += A * E_z(nz0 + r)     (4 FMA per term)
+//       T = double: fp64 throughout (default; ~1e-13 relative to the reference).
+//       T = float : same scheme on the FP32 pipe (approximate mode).
+//   sq_general_kernel        arbitrary wavevectors: fp64 dot product + fp64 sincos.
+//   sq_finalize_kernel       ssf += per-frame |rho|^2 / cross terms.
+
+#include <math.h>
+
+#include <algorithm>
+#include <map>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSqThreads = 256;
+constexpr int kPS = 32;            // particles per shared-memory sub-chunk
+
+template <typename T> struct C2;
+template <> struct C2<double> { using type = double2; };
+template <> struct C2<float> { using type = float2; };
+
+struct LatticeParams {
+    const float *raw;              // [F][stride]
+    int64_t stride;
+    const int4 *chunks;            // {start, end, rho_row, 0}
+    const SqWorkItem *items;
+    const int *qidx;               // [n_items][RZ]
+    double *rho;                   // [F][n_rho][n_q][2]
+    int n_rho, n_q;
+    double b[3];
+    int nmax[3];                   // largest n per axis
+    int offy, offz, nt;            // table layout per particle
+};
+
+template <typename T, int RZ>
+__global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const LatticeParams P)
+{
+    using T2 = typename C2<T>::type;
+    extern __shared__ __align__(16) unsigned char smem[];
+    T2 *tab = reinterpret_cast<T2 *>(smem);          // [kPS][nt]
+
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.z;
+    const int4 chunk = P.chunks[blockIdx.y];
+    const SqWorkItem item = P.items[blockIdx.x * kSqThreads + tid];
+    const int wlen = __reduce_max_sync(0xffffffffu, item.len);   // warp-uniform bound
+    const float *pos = P.raw + (int64_t)frame * P.stride;
+
+    T acc_re[RZ], acc_im[RZ];
+#pragma unroll
+    for (int r = 0; r < RZ; ++r) acc_re[r] = acc_im[r] = T(0);
+
+    const int nt = P.nt;
+    const int ix = item.nx, iy = P.offy + item.ny, iz = P.offz + item.nz0;
+
+    for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS) {
+        const int np = min(kPS, chunk.y - p0);
+        // ---- phase-factor tables for particles [p0, p0 + np) ----
+        if (tid < kPS * 3) {
+            const int p = tid / 3, a = tid - 3 * p;
+            T2 *row = tab + p * nt + (a == 0 ? 0 : (a == 1 ? P.offy : P.offz));
+            const int nm = P.nmax[a];
+            const int npad = (a == 2) ? (nt - P.offz) : nm + 1;
+            if (p < np) {
+                const double x = (double)pos[3 * (int64_t)(p0 + p) + a];
+                double s1, c1;
+                sincos(P.b[a] * x, &s1, &c1);
+                double er = 1.0, ei = 0.0;
+                for (int n = 0; n <= nm; ++n) {
+                    T2 v; v.x = (T)er; v.y = (T)ei;
+                    row[n] = v;
+                    const double nr = er * c1 - ei * s1;
+                    ei = er * s1 + ei * c1;
+                    er = nr;
+                }
+                for (int n = nm + 1; n < npad; ++n) { T2 v; v.x = T(0); v.y = T(0); row[n] = v; }
+            } else {
+                for (int n = 0; n < npad; ++n) { T2 v; v.x = T(0); v.y = T(0); row[n] = v; }
+            }
+        }
+        __syncthreads();
+        // ---- accumulate: particles beyond np have all-zero tables ----
+        if (wlen > 0) {
+#pragma unroll 2
+            for (int p = 0; p < kPS; ++p) {
+                const T2 *row = tab + p * nt;
+                const T2 ex = row[ix], ey = row[iy];
+                const T ar = ex.x * ey.x - ex.y * ey.y;
+                const T ai = ex.x * ey.y + ex.y * ey.x;
+#pragma unroll
+                for (int r = 0; r < RZ; ++r) {
+                    if (r < wlen) {
+                        const T2 ez = row[iz + r];
+                        acc_re[r] += ar * ez.x;
+                        acc_re[r] -= ai * ez.y;
+                        acc_im[r] += ar * ez.y;
+                        acc_im[r] += ai * ez.x;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
+    const int *qi = P.qidx + (int64_t)(blockIdx.x * kSqThreads + tid) * RZ;
+#pragma unroll
+    for (int r = 0; r < RZ; ++r) {
+        if (r < item.len) {
+            const int q = qi[r];
+            if (q >= 0) {
+                atomicAdd(out + 2 * q, (double)acc_re[r]);
+                atomicAdd(out + 2 * q + 1, (double)acc_im[r]);
+            }
+        }
+    }
+}
+
+struct GeneralParams {
+    const float *raw;
+    int64_t stride;
+    const int4 *chunks;
+    const double *qv;              // [n_q][3]
+    double *rho;
+    int n_rho, n_q;
+};
+
+__global__ void __launch_bounds__(128) sq_general_kernel(const GeneralParams P)
+{
+    __shared__ double sx[256], sy[256], sz[256];
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.z;
+    const int4 chunk = P.chunks[blockIdx.y];
+    const int q = blockIdx.x * 128 + tid;
+    const bool qvalid = q < P.n_q;
+    const double qx = qvalid ? P.qv[3 * q] : 0.0;
+    const double qy = qvalid ? P.qv[3 * q + 1] : 0.0;
+    const double qz = qvalid ? P.qv[3 * q + 2] : 0.0;
+    const float *pos = P.raw + (int64_t)frame * P.stride;
+    double re = 0.0, im = 0.0;
+    for (int p0 = chunk.x; p0 < chunk.y; p0 += 256) {
+        const int np = min(256, chunk.y - p0);
+        for (int p = tid; p < np; p += 128) {
+            sx[p] = (double)pos[3 * (int64_t)(p0 + p)];
+            sy[p] = (double)pos[3 * (int64_t)(p0 + p) + 1];
+            sz[p] = (double)pos[3 * (int64_t)(p0 + p) + 2];
+        }
+        __syncthreads();
+        if (qvalid) {
+            for (int p = 0; p < np; ++p) {
+                double s, c;
+                sincos(qx * sx[p] + qy * sy[p] + qz * sz[p], &s, &c);
+                re += c;
+                im += s;
+            }
+        }
+        __syncthreads();
+    }
+    if (qvalid) {
+        double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
+        atomicAdd(out + 2 * q, re);
+        atomicAdd(out + 2 * q + 1, im);
+    }
+}
+
+__global__ void sq_finalize_kernel(const double2 *__restrict__ rho, int n_frames, int n_rho,
+                                   int n_q, const int *__restrict__ pairs, int n_pairs,
+                                   double *__restrict__ ssf)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
+    if (q >= n_q) return;
+    int j = pairs[2 * p], k = pairs[2 * p + 1];
+    if (j < 0) j = k = 0;
+    double acc = 0.0;
+    for (int f = 0; f < n_frames; ++f) {
+        const double2 rj = rho[((int64_t)f * n_rho + j) * n_q + q];
+        if (j == k) {
+            acc += rj.x * rj.x + rj.y * rj.y;
+        } else {
+            const double2 rk = rho[((int64_t)f * n_rho + k) * n_q + q];
+            acc += 2.0 * (rj.x * rk.x + rj.y * rk.y);
+        }
+    }
+    ssf[(int64_t)p * n_q + q] += acc;
+}
+
+template <typename T, int RZ>
+int launch_lattice(mdh_ctx *c, const LatticeParams &P, dim3 grid)
+{
+    using T2 = typename C2<T>::type;
+    const size_t smem = sizeof(T2) * kPS * P.nt;
+    auto kern = sq_lattice_kernel<T, RZ>;
+    MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    kern<<<grid, kSqThreads, smem, c->stream>>>(P);
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    return MDH_OK;
+}
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------
+
+int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *goff,
+                      int n_q, const double *wv, const int32_t *lat_n, const double *lat_b,
+                      int n_pairs, const int32_t *pairs, int mode)
+{
+    SqState &S = c->sq;
+    MDH_REQUIRE(n_total > 0 && n_total < (1ll << 31) / 3, MDH_EINVAL,
+                "sq: n_total must be in [1, 2^31/3)");
+    MDH_REQUIRE(n_groups >= 1 && goff != nullptr, MDH_EINVAL, "sq: groups missing");
+    MDH_REQUIRE(goff[0] == 0 && goff[n_groups] == n_total, MDH_EINVAL,
+                "sq: group_offsets must run from 0 to n_total");
+    for (int g = 0; g < n_groups; ++g)
+        MDH_REQUIRE(goff[g] < goff[g + 1], MDH_EINVAL, "sq: group %d is empty", g);
+    MDH_REQUIRE(n_q >= 1 && wv != nullptr, MDH_EINVAL, "sq: wavevectors missing");
+    MDH_REQUIRE(n_pairs >= 1 && pairs != nullptr, MDH_EINVAL, "sq: pairs missing");
+    MDH_REQUIRE(mode >= MDH_SQ_AUTO && mode <= MDH_SQ_LATTICE_FP32, MDH_EINVAL,
+                "sq: invalid mode");
+    bool all = false;
+    for (int p = 0; p < n_pairs; ++p) {
+        const int j = pairs[2 * p], k = pairs[2 * p + 1];
+        if (j < 0 || k < 0) {
+            MDH_REQUIRE(j == -1 && k == -1 && n_pairs == 1, MDH_EINVAL,
+                        "sq: the pair (-1, -1) must be the only pair");
+            all = true;
+        } else {
+            MDH_REQUIRE(j < n_groups && k < n_groups, MDH_EINVAL,
+                        "sq: pair %d refers to a missing group", p);
+        }
+    }
+    const bool want_lattice = mode == MDH_SQ_LATTICE_FP64 || mode == MDH_SQ_LATTICE_FP32 ||
+                              mode == MDH_SQ_LATTICE_SFU;
+    MDH_REQUIRE(!want_lattice || (lat_n && lat_b), MDH_EINVAL,
+                "sq: a lattice kernel was requested without lattice_n / lattice_b");
+    MDH_REQUIRE(mode != MDH_SQ_LATTICE_SFU, MDH_EINVAL,
+                "sq: MDH_SQ_LATTICE_SFU is not available in this build");
+
+    S.configured = false;
+    S.n_total = n_total; S.n_groups = n_groups; S.n_q = n_q; S.n_pairs = n_pairs;
+    S.n_rho = all ? 1 : n_groups;
+    S.group_offsets.assign(goff, goff + n_groups + 1);
+    S.pairs.assign(pairs, pairs + 2 * n_pairs);
+    S.rho_frames = 0;
+
+    // ---- lattice work items ----
+    bool lattice = lat_n && lat_b && mode != MDH_SQ_GENERAL_FP64;
+    std::vector<SqWorkItem> items;
+    std::vector<int> qidx;
+    int rz = 16;
+    if (lattice) {
+        int nm[3] = {0, 0, 0};
+        for (int i = 0; i < n_q && lattice; ++i)
+            for (int k = 0; k < 3; ++k) {
+                const int n = lat_n[3 * i + k];
+                if (n < 0 || n > 1023) lattice = false;
+                else nm[k] = std::max(nm[k], n);
+            }
+        if (lattice) {
+            rz = nm[2] + 1 <= 8 ? 8 : 16;
+            std::map<std::pair<int, int>, std::vector<std::pair<int, int>>> cols;
+            for (int i = 0; i < n_q; ++i)
+                cols[{lat_n[3 * i], lat_n[3 * i + 1]}].push_back({lat_n[3 * i + 2], i});
+            for (auto &kv : cols) {
+                auto &v = kv.second;
+                std::sort(v.begin(), v.end());
+                for (size_t t = 1; t < v.size() && lattice; ++t)
+                    if (v[t].first == v[t - 1].first) lattice = false;   // duplicate wavevector
+                if (!lattice) break;
+                // split the column into segments [nz0, nz0 + rz), nz0 a multiple of rz
+                size_t t = 0;
+                while (t < v.size()) {
+                    const int nz0 = v[t].first / rz * rz;
+                    SqWorkItem it{kv.first.first, kv.first.second, nz0, 0};
+                    std::vector<int> qi(rz, -1);
+                    while (t < v.size() && v[t].first < nz0 + rz) {
+                        qi[v[t].first - nz0] = v[t].second;
+                        it.len = v[t].first - nz0 + 1;
+                        ++t;
+                    }
+                    items.push_back(it);
+                    qidx.insert(qidx.end(), qi.begin(), qi.end());
+                }
+            }
+            if (lattice) {
+                // sort so that warps share nz0 and have similar lengths
+                std::vector<int> order(items.size());
+                for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                    if (items[a].nz0 != items[b].nz0) return items[a].nz0 < items[b].nz0;
+                    return items[a].len > items[b].len;
+                });
+                std::vector<SqWorkItem> it2;
+                std::vector<int> q2;
+                for (int o : order) {
+                    it2.push_back(items[o]);
+                    q2.insert(q2.end(), qidx.begin() + (size_t)o * rz,
+                              qidx.begin() + (size_t)(o + 1) * rz);
+                }
+                while (it2.size() % kSqThreads) {
+                    it2.push_back(SqWorkItem{0, 0, 0, 0});
+                    q2.insert(q2.end(), rz, -1);
+                }
+                items.swap(it2);
+                qidx.swap(q2);
+                for (int k = 0; k < 3; ++k) { S.nmax[k] = nm[k]; S.b[k] = lat_b[k]; }
+            }
+        }
+    }
+    MDH_REQUIRE(lattice || !want_lattice, MDH_EINVAL,
+                "sq: wavevectors are not usable by the lattice kernels "
+                "(need 0 <= n <= 1023 and no duplicates)");
+    S.lattice = lattice;
+    S.mode = lattice ? (mode == MDH_SQ_LATTICE_FP32 ? MDH_SQ_LATTICE_FP32 : MDH_SQ_LATTICE_FP64)
+                     : MDH_SQ_GENERAL_FP64;
+    S.rz = rz;
+    S.n_items = (int)items.size();
+
+    if (int rc = S.qv.reserve(sizeof(double) * 3 * n_q)) return rc;
+    if (int rc = S.d_pairs.reserve(sizeof(int) * 2 * n_pairs)) return rc;
+    if (int rc = S.ssf.reserve(sizeof(double) * (size_t)n_pairs * n_q)) return rc;
+    MDH_CUDA(cudaMemcpyAsync(S.qv.p, wv, sizeof(double) * 3 * n_q, cudaMemcpyHostToDevice,
+                             c->stream));
+    MDH_CUDA(cudaMemcpyAsync(S.d_pairs.p, pairs, sizeof(int) * 2 * n_pairs,
+                             cudaMemcpyHostToDevice, c->stream));
+    MDH_CUDA(cudaMemsetAsync(S.ssf.p, 0, sizeof(double) * (size_t)n_pairs * n_q, c->stream));
+    if (lattice) {
+        if (int rc = S.items.reserve(sizeof(SqWorkItem) * items.size())) return rc;
+        if (int rc = S.qidx.reserve(sizeof(int) * qidx.size())) return rc;
+        MDH_CUDA(cudaMemcpyAsync(S.items.p, items.data(), sizeof(SqWorkItem) * items.size(),
+                                 cudaMemcpyHostToDevice, c->stream));
+        MDH_CUDA(cudaMemcpyAsync(S.qidx.p, qidx.data(), sizeof(int) * qidx.size(),
+                                 cudaMemcpyHostToDevice, c->stream));
+    }
+    MDH_CUDA(cudaStreamSynchronize(c->stream));   // host sources are caller/local memory
+    S.n_chunks = 0;
+    S.configured = true;
+    return MDH_OK;
+}
+
+// particle chunks: one rho row per group (or one row for everything)
+static int sq_build_chunks(mdh_ctx *c, int n_frames)
+{
+    SqState &S = c->sq;
+    const int item_blocks = S.lattice ? S.n_items / kSqThreads : (S.n_q + 127) / 128;
+    // enough blocks for ~6 waves, chunks a multiple of the sub-chunk length
+    int64_t want = ((int64_t)c->sm_count * 2 * 6 + (int64_t)item_blocks * n_frames - 1) /
+                   ((int64_t)item_blocks * n_frames);
+    int64_t len = (S.n_total + want - 1) / std::max<int64_t>(want, 1);
+    len = std::max<int64_t>(256, std::min<int64_t>(len, 4096));
+    len = (len + kPS - 1) / kPS * kPS;
+    if (S.n_chunks > 0 && S.chunk_len == (int)len) return MDH_OK;
+    std::vector<int4> ch;
+    if (S.n_rho == 1) {
+        for (int64_t s = 0; s < S.n_total; s += len)
+            ch.push_back(make_int4((int)s, (int)std::min<int64_t>(S.n_total, s + len), 0, 0));
+    } else {
+        for (int g = 0; g < S.n_groups; ++g)
+            for (int64_t s = S.group_offsets[g]; s < S.group_offsets[g + 1]; s += len)
+                ch.push_back(make_int4((int)s,
+                                       (int)std::min<int64_t>(S.group_offsets[g + 1], s + len),
+                                       g, 0));
+    }
+    MDH_REQUIRE(ch.size() <= 65535, MDH_EINVAL, "sq: too many particle chunks");
+    if (int rc = S.chunks.reserve(sizeof(int4) * ch.size())) return rc;
+    MDH_CUDA(cudaMemcpyAsync(S.chunks.p, ch.data(), sizeof(int4) * ch.size(),
+                             cudaMemcpyHostToDevice, c->stream));
+    MDH_CUDA(cudaStreamSynchronize(c->stream));
+    S.n_chunks = (int)ch.size();
+    S.chunk_len = (int)len;
+    return MDH_OK;
+}
+
+int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
+                       int n_frames)
+{
+    SqState &S = c->sq;
+    MDH_REQUIRE(S.configured, MDH_ESTATE, "sq: accumulate before configure");
+    MDH_REQUIRE(n_frames >= 1 && n_frames <= 65535, MDH_EINVAL,
+                "sq: n_frames per call must be in [1, 65535]");
+    MDH_REQUIRE(pos != nullptr, MDH_EINVAL, "sq: coordinate pointer is NULL");
+    MDH_REQUIRE(stride >= 3 * S.n_total, MDH_EINVAL, "sq: frame_stride < 3*n_total");
+    MDH_REQUIRE(location == MDH_HOST || location == MDH_DEVICE, MDH_EINVAL,
+                "sq: invalid location");
+
+    const float *dsrc = pos;
+    int64_t dstride = stride;
+    if (location == MDH_HOST) {
+        if (int rc = S.raw.reserve(sizeof(float) * 3 * S.n_total * n_frames)) return rc;
+        MDH_CUDA(cudaMemcpy2DAsync(S.raw.p, sizeof(float) * 3 * S.n_total, pos,
+                                   sizeof(float) * stride, sizeof(float) * 3 * S.n_total,
+                                   n_frames, cudaMemcpyHostToDevice, c->stream));
+        dsrc = S.raw.as<float>();
+        dstride = 3 * S.n_total;
+    }
+    if (int rc = sq_build_chunks(c, n_frames)) return rc;
+    const size_t rho_bytes = sizeof(double) * 2 * (size_t)n_frames * S.n_rho * S.n_q;
+    if (int rc = S.rho.reserve(rho_bytes)) return rc;
+
+    if (!c->ev_sq0) {
+        MDH_CUDA(cudaEventCreate(&c->ev_sq0));
+        MDH_CUDA(cudaEventCreate(&c->ev_sq1));
+    }
+    MDH_CUDA(cudaEventRecord(c->ev_sq0, c->stream));
+    MDH_CUDA(cudaMemsetAsync(S.rho.p, 0, rho_bytes, c->stream));
+
+    if (S.lattice) {
+        LatticeParams P;
+        P.raw = dsrc; P.stride = dstride;
+        P.chunks = S.chunks.as<int4>();
+        P.items = S.items.as<SqWorkItem>();
+        P.qidx = S.qidx.as<int>();
+        P.rho = S.rho.as<double>();
+        P.n_rho = S.n_rho; P.n_q = S.n_q;
+        for (int k = 0; k < 3; ++k) { P.b[k] = S.b[k]; P.nmax[k] = S.nmax[k]; }
+        P.offy = S.nmax[0] + 1;
+        P.offz = P.offy + S.nmax[1] + 1;
+        P.nt = P.offz + (S.nmax[2] + S.rz) / S.rz * S.rz;
+        dim3 grid(S.n_items / kSqThreads, S.n_chunks, n_frames);
+        int rc;
+        if (S.mode == MDH_SQ_LATTICE_FP32)
+            rc = S.rz == 8 ? launch_lattice<float, 8>(c, P, grid)
+                           : launch_lattice<float, 16>(c, P, grid);
+        else
+            rc = S.rz == 8 ? launch_lattice<double, 8>(c, P, grid)
+                           : launch_lattice<double, 16>(c, P, grid);
+        if (rc) return rc;
+    } else {
+        GeneralParams P;
+        P.raw = dsrc; P.stride = dstride;
+        P.chunks = S.chunks.as<int4>();
+        P.qv = S.qv.as<double>();
+        P.rho = S.rho.as<double>();
+        P.n_rho = S.n_rho; P.n_q = S.n_q;
+        dim3 grid((S.n_q + 127) / 128, S.n_chunks, n_frames);
+        sq_general_kernel<<<grid, 128, 0, c->stream>>>(P);
+        MDH_CUDA(cudaGetLastError());
+        c->launches++;
+    }
+    dim3 fgrid((S.n_q + 127) / 128, S.n_pairs);
+    sq_finalize_kernel<<<fgrid, 128, 0, c->stream>>>(S.rho.as<double2>(), n_frames, S.n_rho,
+                                                     S.n_q, S.d_pairs.as<int>(), S.n_pairs,
+                                                     S.ssf.as<double>());
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    MDH_CUDA(cudaEventRecord(c->ev_sq1, c->stream));
+    c->sq_timed = true;
+    S.rho_frames = n_frames;
+    return MDH_OK;
+}

@@ -1,0 +1,237 @@
+"""
+Generates the golden fixtures in this directory FROM THE REAL REFERENCE CODE.
+
+Run in the build container (needs ``/root/reference``; cannot run on the GPU box):
+
+    python tests/golden/make_golden.py
+
+What runs is the reference's own ``radial_histogram``,
+``RadialDistributionFunction`` and ``StructureFactor`` (including its numba
+kernels in ``algorithm/accelerated.py``), imported from ``/root/reference/src``
+behind the stubs described in ``oracle/ref_harness.py``.  The one piece that is
+NOT reference code is ``MDAnalysis.lib.distances.capped_distance`` (third-party,
+absent here): the restated C oracle is injected in its place, so the RDF
+fixtures pin "reference class code + restated capped_distance + real
+numpy.histogram", while the S(q) fixtures pin the reference end to end.
+
+Inputs are stored in the fixtures (small cases) or regenerated from a seed with
+a sha256 of the coordinates stored beside the expected output (large cases).
+"""
+
+import hashlib
+import pathlib
+import sys
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+from mdhelper_b200 import synthetic  # noqa: E402
+from mdhelper_b200.universe import SyntheticUniverse  # noqa: E402
+from oracle import ref_harness  # noqa: E402
+
+OUT = pathlib.Path(__file__).resolve().parent
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def kat_radial_histogram(S):
+    """The construction of tests/test_analysis_structure.py:21-40, seeded."""
+    rng = np.random.default_rng(20260001)
+    L = 20
+    half_L = L // 2
+    dims = np.array((L, L, L, 90, 90, 90), dtype=int)
+    origin = half_L * np.ones(3)
+    N = 1_000
+    norm = L // 2 * rng.random(N)
+    expected = np.histogram(norm, bins=half_L, range=(0, half_L + 1))[0]
+    neighbors = rng.random((N, 3))
+    neighbors *= norm[:, None] / np.linalg.norm(neighbors, axis=1, keepdims=True)
+    neighbors += dims[:3] / 2
+    got = S.radial_histogram(origin, neighbors, n_bins=half_L,
+                             range=(0, half_L + 1), dims=dims)
+    # the reference's own assertion (float32 rounding of the inputs can move a
+    # point across a bin edge; record both)
+    np.savez_compressed(OUT / "kat_radial_histogram.npz", origin=origin,
+                        neighbors=neighbors, dims=dims, n_bins=half_L,
+                        range=np.array((0, half_L + 1)),
+                        expected_from_norms=expected, reference_counts=got)
+    print("kat: reference == np.histogram(norms):", np.array_equal(expected, got))
+
+
+def rdf_cases(S):
+    cases = {}
+    # (2) LJ fluid, N=1000, 5 frames, same group
+    u = synthetic.lj_fluid(1000, 5, seed=20260001)
+    pos = u.trajectory.coordinates.copy()
+    dims = u.trajectory.unitcells[0].copy()
+    r = S.RadialDistributionFunction(u.atoms, n_bins=201, range=(0.0, 5.375),
+                                     verbose=False).run()
+    cases["lj1000"] = dict(positions=pos, dims=dims, n_bins=201,
+                           range=np.array((0.0, 5.375)),
+                           counts=r.results.counts, rdf=r.results.rdf,
+                           edges=r.results.edges, bins=r.results.bins)
+    # parallel=True of the reference must give the same counts
+    # (its per-frame worker and reduction are driven in-process: a fork pool
+    # cannot pickle the stubbed third-party modules)
+    rp = S.RadialDistributionFunction(u.atoms, n_bins=201, range=(0.0, 5.375),
+                                      parallel=True, verbose=False)
+    rp._setup_frames(rp._trajectory)
+    rp._prepare()
+    rp._results = [rp._single_frame_parallel(f, i)
+                   for i, f in enumerate(range(rp.n_frames))]
+    rp._conclude()
+    assert np.array_equal(rp.results.counts, r.results.counts)
+    assert np.allclose(rp.results.rdf, r.results.rdf, rtol=1e-12)
+
+    # (3) two groups + exclusions, N=600 (ions: 300 + 300), 3 frames
+    u, cat, an = synthetic.electrolyte(600, 3, seed=20260002)
+    pos = u.trajectory.coordinates.copy()
+    dims = u.trajectory.unitcells[0].copy()
+    L = float(dims[0])
+    r = S.RadialDistributionFunction(cat, an, n_bins=64, range=(0.0, L / 2),
+                                     verbose=False).run()
+    cases["twogroup"] = dict(positions=pos, dims=dims, n_cat=cat.n_atoms,
+                             n_bins=64, range=np.array((0.0, L / 2)),
+                             counts=r.results.counts, rdf=r.results.rdf)
+    r = S.RadialDistributionFunction(u.atoms, n_bins=50, range=(0.0, 4.0),
+                                     exclusion=(1, 1), verbose=False).run()
+    cases["excl11"] = dict(positions=pos, dims=dims, n_bins=50,
+                           range=np.array((0.0, 4.0)), exclusion=np.array((1, 1)),
+                           counts=r.results.counts, rdf=r.results.rdf)
+    r = S.RadialDistributionFunction(cat, an, n_bins=50, range=(0.5, 4.0),
+                                     exclusion=(4, 10), verbose=False).run()
+    cases["excl410"] = dict(positions=pos, dims=dims, n_cat=cat.n_atoms,
+                            n_bins=50, range=np.array((0.5, 4.0)),
+                            exclusion=np.array((4, 10)),
+                            counts=r.results.counts, rdf=r.results.rdf)
+    # (4) drop_axis=2 (two-dimensional RDF)
+    r = S.RadialDistributionFunction(u.atoms, n_bins=40, range=(0.0, 3.5),
+                                     drop_axis=2, verbose=False).run()
+    cases["dropz"] = dict(positions=pos, dims=dims, n_bins=40,
+                          range=np.array((0.0, 3.5)), drop_axis=2,
+                          counts=r.results.counts, rdf=r.results.rdf)
+    r = S.RadialDistributionFunction(cat, an, n_bins=40, range=(0.0, 3.5),
+                                     drop_axis="x", norm="density",
+                                     verbose=False).run()
+    cases["dropx_density"] = dict(positions=pos, dims=dims, n_cat=cat.n_atoms,
+                                  n_bins=40, range=np.array((0.0, 3.5)),
+                                  drop_axis=0, counts=r.results.counts,
+                                  rdf=r.results.rdf)
+
+    # (5) adversarial: perfect lattice, separations exactly L/2 (round half) and
+    # exactly on bin edges; non-cubic box; per-frame box change
+    m, a = 8, np.float32(1.25)
+    g = np.arange(m, dtype=np.float32) * a
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    pos = np.stack([lat, lat[::-1].copy(), np.roll(lat, 7, axis=0)]).astype(np.float32)
+    dims = np.array([[10.0, 10.0, 10.0, 90, 90, 90],
+                     [10.0, 10.0, 10.0, 90, 90, 90],
+                     [10.0, 10.0, 10.0, 90, 90, 90]], np.float32)
+    u = SyntheticUniverse(pos, dims)
+    r = S.RadialDistributionFunction(u.atoms, n_bins=20, range=(0.0, 5.0),
+                                     verbose=False).run()
+    cases["lattice_edges"] = dict(positions=pos, dims=dims, n_bins=20,
+                                  range=np.array((0.0, 5.0)),
+                                  counts=r.results.counts, rdf=r.results.rdf)
+    rng = np.random.default_rng(20260005)
+    dims = np.array([[9.0, 11.5, 14.25, 90, 90, 90],
+                     [9.5, 11.0, 14.0, 90, 90, 90]], np.float32)
+    pos = (rng.random((2, 700, 3)) * dims[:, None, :3]).astype(np.float32)
+    u = SyntheticUniverse(pos, dims)
+    r = S.RadialDistributionFunction(u.atoms, n_bins=33, range=(0.0, 4.4),
+                                     verbose=False).run()
+    cases["noncubic_npt"] = dict(positions=pos, dims=dims, n_bins=33,
+                                 range=np.array((0.0, 4.4)),
+                                 counts=r.results.counts, rdf=r.results.rdf)
+    # unwrapped coordinates (outside [0, L)): brute-force path of the reference
+    pos = ((rng.random((1, 500, 3)) * 3 - 1) * dims[0, None, :3]).astype(np.float32)
+    u = SyntheticUniverse(pos, dims[:1])
+    r = S.RadialDistributionFunction(u.atoms, n_bins=33, range=(0.0, 4.4),
+                                     verbose=False).run()
+    cases["unwrapped"] = dict(positions=pos, dims=dims[:1], n_bins=33,
+                              range=np.array((0.0, 4.4)),
+                              counts=r.results.counts, rdf=r.results.rdf)
+    for name, d in cases.items():
+        np.savez_compressed(OUT / f"rdf_{name}.npz", **d)
+        print("rdf", name, int(d["counts"].sum()))
+
+
+def sq_cases(S):
+    # (6a) N=1000, 2 frames, default lattice grid, all modes and both forms
+    u, cat, an = synthetic.electrolyte(1000, 2, seed=20260006)
+    pos = u.trajectory.coordinates.copy()
+    dims = u.trajectory.unitcells[0].copy()
+    L = float(dims[0])
+    out = dict(positions=pos, dims=dims, n_cat=cat.n_atoms, n_points=12,
+               q_max=2 * np.pi * 8 / L)
+    for mode, groups in ((None, [cat, an]), ("pair", [cat, an]),
+                         ("partial", [cat, an])):
+        for form in ("exp", "trig"):
+            s = S.StructureFactor(groups, mode=mode, form=form, n_points=12,
+                                  q_max=out["q_max"], verbose=False).run()
+            key = f"{mode}_{form}"
+            out[f"ssf_{key}"] = s.results.ssf
+            out[f"wavenumbers_{key}"] = s.results.wavenumbers
+    s = S.StructureFactor([u.atoms], n_points=12, q_max=out["q_max"],
+                          sort=False, unique=False, parallel=True,
+                          verbose=False).run()
+    out["ssf_raw"] = s.results.ssf
+    out["wavevectors_raw"] = s._wavevectors
+    # raw rho(q) of the last frame straight from the numba kernel (seam #2)
+    acc = ref_harness.accelerated()
+    out["rho_last"] = acc.delta_fourier_transform_sum_2d_2d(
+        s._wavevectors, pos[-1].astype(np.float64))
+    # off-lattice: n_surfaces, and user wavevectors
+    s = S.StructureFactor([u.atoms], n_points=6, n_surfaces=3,
+                          n_surface_points=8, verbose=False).run()
+    out["ssf_surfaces"] = s.results.ssf
+    out["wavenumbers_surfaces"] = s.results.wavenumbers
+    rng = np.random.default_rng(20260007)
+    wv = rng.normal(size=(37, 3)) * 2.0
+    s = S.StructureFactor([cat, an], mode="partial", wavevectors=wv, sort=False,
+                          unique=False, verbose=False).run()
+    out["wavevectors_user"] = wv
+    out["ssf_user"] = s.results.ssf
+    np.savez_compressed(OUT / "sq_small.npz", **out)
+    print("sq small", out["ssf_None_exp"].shape, out["ssf_partial_exp"].shape)
+
+    # (6b) non-cubic box
+    rng = np.random.default_rng(20260008)
+    dims = np.array([9.0, 11.5, 14.25, 90, 90, 90], np.float32)
+    pos = (rng.random((2, 300, 3)) * dims[:3]).astype(np.float32)
+    u = SyntheticUniverse(pos, dims)
+    s = S.StructureFactor([u.atoms], n_points=10, q_max=4.0, verbose=False).run()
+    np.savez_compressed(OUT / "sq_noncubic.npz", positions=pos, dims=dims,
+                        n_points=10, q_max=4.0, ssf=s.results.ssf,
+                        wavenumbers=s.results.wavenumbers)
+
+    # (6c) config-4 sized frame: N=50,000, n_max=16 (N_q=2446), one frame;
+    # coordinates regenerated from the seed (checksum stored)
+    u = synthetic.lj_fluid(50_000, 1, seed=20260004)
+    L = float(u.trajectory.unitcells[0, 0])
+    q_max = 2 * np.pi * 16 / L
+    s = S.StructureFactor([u.atoms], n_points=32, q_max=q_max, parallel=True,
+                          sort=False, unique=False, verbose=False).run()
+    su = S.StructureFactor([u.atoms], n_points=32, q_max=q_max, parallel=True,
+                           verbose=False).run()
+    np.savez_compressed(OUT / "sq_cfg4_frame.npz", n=50_000, seed=20260004,
+                        positions_sha256=sha(u.trajectory.coordinates),
+                        L=np.float32(L), q_max=q_max, ssf_raw=s.results.ssf,
+                        ssf_unique=su.results.ssf,
+                        wavenumbers_unique=su.results.wavenumbers)
+    print("sq cfg4", s.results.ssf.shape, su.results.ssf.shape)
+
+
+if __name__ == "__main__":
+    S = ref_harness.load()
+    which = sys.argv[1:] or ["kat", "rdf", "sq"]
+    if "kat" in which:
+        kat_radial_histogram(S)
+    if "rdf" in which:
+        rdf_cases(S)
+    if "sq" in which:
+        sq_cases(S)
