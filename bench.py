@@ -1,0 +1,544 @@
+#!/usr/bin/env python
+"""
+bench.py -- hot-path benchmark (contract: one JSON line on stdout from rank 0).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W      # CPU reference arm
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8(d) "cfg2"): two-group
+cation-anion partial RDF of a 20,000-ion electrolyte, n_bins=201, range (0, 14.5),
+2,000 synthetic frames per GPU.  One "step" = one batch of ``--frames-per-step``
+frames (default 100) through the pair-histogram hot path.
+
+* ``value``      pairs binned / s, coordinates already resident in HBM, device time
+                 (CUDA events on the launching stream), max over ranks.
+* ``e2e``        the same metric through the public class
+                 ``RadialDistributionFunction(cations, anions).run(start, stop)``
+                 from pinned HOST memory (H2D of every frame and D2H of the
+                 counts inside the timed region).
+* ``roofline``   pair kernel vs the FP64 pipe: pair evaluations/s x 21 FP64-pipe
+                 instructions per evaluation over the measured
+                 per-SM FP64 issue rate x SM count x the SM clock sampled during
+                 the run.  (Neither HBM- nor tensor-bound; the HBM figure is
+                 reported beside it for the record.)
+* ``cpu_baseline`` the restated reference CPU path (oracle/: C distances + real
+                 numpy.histogram), serial and frame-parallel over all host cores,
+                 on a bounded sample of the same frames.
+* ``secondary``  the S(q) half of the metric: frames/s of the direct-sum structure
+                 factor for N=50,000, N_q=2,446 (configs[3]) with its own roofline
+                 and CPU baseline.
+
+Multi-GPU: frames shard over ranks (weak scaling: every rank processes its own
+2,000-frame trajectory), no data-path collective; one NCCL all-reduce of the
+int64 counts at the end, inside the timed region.
+"""
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CFG2 = dict(n_ions=20_000, n_frames=2_000, n_bins=201, range=(0.0, 14.5), seed=20260002)
+CFG4 = dict(n=50_000, n_frames=1_000, n_points=32, n_max=16, seed=20260004)
+FP64_OPS_PER_PAIR = 21       # FP64-pipe instructions per pair evaluation
+FP64_OPS_PER_TERM = 4        # DFMA per (q, r) term of the lattice kernel
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=100)
+    ap.add_argument("--sq-frames-per-step", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--hist", default="auto")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(pw)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    out = {"hbm_gbs": 6650.0, "hbm_source": "fallback (B200_PROFILING.md)",
+           "fp64_per_clk_sm": 64.0, "sfu_per_clk_sm": 16.0,
+           "pipe_source": "nominal (no profiles/microbench_r01.json)"}
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            out["hbm_gbs"] = float(json.loads(p.read_text())["hbm_gbs"])
+            out["hbm_source"] = "MEASURED_PEAKS.json"
+        except (ValueError, KeyError):
+            pass
+    p = ROOT / "profiles" / "microbench_r01.json"
+    if p.exists():
+        try:
+            mb = json.loads(p.read_text())
+            out["fp64_per_clk_sm"] = float(mb["dfma"]["ops_per_clk_per_sm"])
+            out["sfu_per_clk_sm"] = float(mb["mufu_sin"]["ops_per_clk_per_sm"])
+            out["pipe_source"] = "measured: profiles/microbench_r01.json (tools/microbench.cu)"
+        except (ValueError, KeyError):
+            pass
+    return out
+
+
+# ---------------------------------------------------------------------------------
+# CPU reference path (restated): oracle distances + real numpy.histogram
+# ---------------------------------------------------------------------------------
+
+_CPU_STATE = {}
+
+
+def _cpu_rdf_frame(f):
+    from oracle import reference_port as rp
+    u, cat, an = _CPU_STATE["u"]
+    ts = u.trajectory[int(f)]
+    # mirrors _single_frame_parallel (structure.py:793-835): counts || volume
+    c = rp.radial_histogram(cat.positions, an.positions, CFG2["n_bins"], CFG2["range"],
+                            ts.dimensions, method="bruteforce")
+    return np.concatenate((c, [ts.volume]))
+
+
+def cpu_rdf(frames, n_jobs):
+    """Pairs binned per second by the restated reference path on `n_jobs` processes."""
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if n_jobs == 1:
+        res = [_cpu_rdf_frame(f) for f in frames]
+    else:
+        with mp.get_context("fork").Pool(n_jobs) as pool:      # base.py:477-501
+            res = pool.map(_cpu_rdf_frame, frames, chunksize=1)
+    dt = time.perf_counter() - t0
+    tot = np.vstack(res).sum(axis=0)                           # structure.py:842
+    return float(tot[:-1].sum()) / dt, dt, tot[:-1].astype(np.int64)
+
+
+def cpu_sq(u, wavevectors, n_frames, n_threads):
+    from oracle import reference_port as rp
+    pos = [u.trajectory.coordinates[f].astype(np.float64) for f in range(n_frames)]
+    rp.delta_fourier_transform_sum(wavevectors[:64], pos[0][:1000], n_threads)   # warm-up
+    t0 = time.perf_counter()
+    for p in pos:
+        rho = rp.delta_fourier_transform_sum(wavevectors, p, n_threads)
+        _ = (rho * rho.conj()).real
+    dt = time.perf_counter() - t0
+    return n_frames / dt, dt
+
+
+def make_cpu_sample(n_frames):
+    from mdhelper_b200 import synthetic
+    _CPU_STATE["u"] = synthetic.electrolyte(CFG2["n_ions"], n_frames, seed=CFG2["seed"],
+                                            pinned=False)
+
+
+# ---------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = len(os.sched_getaffinity(0))
+    fps = cores                                     # one frame per core per step
+    n_need = fps * (args.steps + args.warmup)
+    make_cpu_sample(min(n_need, 64))
+    n_have = len(_CPU_STATE["u"][0].trajectory)
+    for s in range(args.warmup):
+        cpu_rdf([(s * fps + i) % n_have for i in range(fps)], cores)
+    t0 = time.perf_counter()
+    binned = 0
+    for s in range(args.warmup, args.warmup + args.steps):
+        _, _, c = cpu_rdf([(s * fps + i) % n_have for i in range(fps)], cores)
+        binned += int(c.sum())
+    dt = time.perf_counter() - t0
+    value = binned / dt
+    sample = (f"{fps} frames per step ({fps * args.steps} of the workload's 2,000), "
+              f"multiprocessing fork pool of {cores} processes over frames "
+              "(mirrors base.py:477-501)")
+    line = {
+        "impl": "reference", "metric": "rdf_pairs_binned_per_s", "value": value,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(fps),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "restated reference CPU path: MDAnalysis is not installable here, so "
+                "capped_distance is the C restatement in oracle/ feeding the real "
+                "numpy.histogram",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(frames_per_step):
+    return {"workload": "cfg2: two-group cation-anion partial RDF, 20,000-ion electrolyte "
+                        "(10,000 x 10,000 ordered pairs per frame), n_bins=201, "
+                        "range=(0, 14.5), L=29.2402, 2,000 synthetic frames per GPU",
+            "frames_per_step": frames_per_step,
+            "pairs_per_frame": 100_000_000,
+            "cache": "inputs larger than L2: 480 MB of coordinates cycle through HBM, "
+                     "each step reads a different 24 MB batch",
+            "parallelism": "frames sharded over GPUs, one all-reduce at the end"}
+
+
+# ---------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    cores = len(os.sched_getaffinity(0))
+
+    # ---- CPU baselines first (fork pool before any CUDA context exists) ----
+    cpu = None
+    cpu_sq_res = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        oracle.build()
+        make_cpu_sample(2 * cores)
+        v1, dt1, _ = cpu_rdf([0], 1)
+        vp, dtp, _ = cpu_rdf(list(range(2 * cores)), cores)
+        cpu = {"value": vp, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "serial_value": v1,
+               "sample": f"serial: 1 frame in {dt1:.1f} s; parallel: {2 * cores} frames on a "
+                         f"fork pool of {cores} processes in {dtp:.1f} s (same cfg2 frames; "
+                         "restated reference path: C capped_distance + numpy.histogram)"}
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mdhelper_b200 import _lib, synthetic
+    from mdhelper_b200.analysis._binning import squared_thresholds
+    from mdhelper_b200.analysis.structure import RadialDistributionFunction, StructureFactor
+
+    K, W, fps = args.steps, args.warmup, args.frames_per_step
+    n_frames = CFG2["n_frames"]
+    u, cat, an = synthetic.electrolyte(CFG2["n_ions"], n_frames, seed=CFG2["seed"] + 1000 * rank)
+    n1, n2, N = cat.n_atoms, an.n_atoms, CFG2["n_ions"]
+    coords = u.trajectory.coordinates
+    boxes = np.ascontiguousarray(u.trajectory.unitcells[:, :3])
+
+    # ---- value: coordinates resident in HBM ----
+    dev = torch.from_numpy(coords).cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    ctx = _lib.Context(local)
+    thr = squared_thresholds(CFG2["n_bins"], CFG2["range"])
+    ctx.rdf_configure(n1, n2, False, thr, *CFG2["range"], hist=args.hist)
+    base = dev.data_ptr()
+
+    def step(s):
+        f0 = (s * fps) % n_frames
+        nf = min(fps, n_frames - f0)
+        ctx.rdf_accumulate(base + 4 * 3 * N * f0, 3 * N, base + 4 * 3 * (N * f0 + n1), 3 * N,
+                           boxes[f0:f0 + nf], nf, device=True)
+        return nf
+
+    for s in range(W):
+        step(s)
+    ctx.sync()
+    ctx.rdf_reset()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    ev0.record()
+    frames_done, kernel_ms = 0, 0.0
+    for s in range(W, W + K):
+        frames_done += step(s)
+    counts = torch.from_numpy(ctx.rdf_fetch()).cuda()
+    if world > 1:
+        dist.all_reduce(counts)
+    ev1.record()
+    torch.cuda.synchronize()
+    wall1 = time.time()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = ctx.launch_count() - launches0
+    binned_total = int(counts.sum().item())
+    evals_local = ctx.rdf_pair_evaluations()
+    # per-launch duration of the pair kernel, measured with CUDA events (untimed pass)
+    kern = []
+    for s in range(W + K, W + K + 5):
+        step(s)
+        kern.append(ctx.last_kernel_ms()[0])
+    kern_ms = float(np.mean(kern))
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    value = binned_total / (ms * 1e-3)
+
+    # ---- e2e: public class, pinned host memory, H2D + D2H inside the timed region ----
+    rdf = RadialDistributionFunction(cat, an, n_bins=CFG2["n_bins"], range=CFG2["range"],
+                                     verbose=False, batch_frames=fps, hist=args.hist)
+    for s in range(W):
+        f0 = (s * fps) % n_frames
+        rdf.run(start=f0, stop=min(n_frames, f0 + fps))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_binned = 0
+    for s in range(W, W + K):
+        f0 = (s * fps) % n_frames
+        rdf.run(start=f0, stop=min(n_frames, f0 + fps))
+        e2e_binned += int(rdf.results.counts.sum())       # already summed over ranks
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_binned / float(e2e_s.item())
+
+    # ---- secondary: S(q), cfg4 ----
+    secondary = None
+    if not args.no_secondary:
+        secondary = bench_sq(args, rank, world, local, cores, dist, torch)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    sm_mhz = clocks["sm_mhz"] or clocks.get("sm_max_mhz") or 1965.0
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    fp64_peak = peaks["fp64_per_clk_sm"] * n_sm * sm_mhz * 1e6        # instr/s
+    evals_per_launch = fps * n1 * n2
+    achieved = evals_per_launch * FP64_OPS_PER_PAIR / (kern_ms * 1e-3)
+    alg_bytes = fps * (n1 + n2) * 16 + CFG2["n_bins"] * 8            # float4 in, counts out
+    line = {
+        "metric": "rdf_pairs_binned_per_s", "value": value, "unit": "pairs/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(fps),
+        "pairs_evaluated_per_s": evals_local * world / (ms * 1e-3) * (K / (K + 0.0)),
+        "frames_per_s": frames_done * world / (ms * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "pairs/s",
+                "h2d_bytes_per_step": fps * (n1 + n2) * 12 + fps * 48,
+                "d2h_bytes_per_step": CFG2["n_bins"] * 8,
+                "api": "RadialDistributionFunction(cations, anions, n_bins=201, "
+                       "range=(0, 14.5)).run(start, stop) per step"},
+        "gpu_launches": launches,
+        "roofline": {
+            "kernel": "rdf_allpairs_kernel", "bound": "fp64_pipe",
+            "achieved": achieved / 1e9, "peak": fp64_peak / 1e9, "unit": "Ginstr/s",
+            "frac": achieved / fp64_peak, "traffic": None,
+            "per_unit": f"{FP64_OPS_PER_PAIR} FP64-pipe instructions per pair evaluation "
+                        "(no FMA fusion allowed)",
+            "units_per_launch": evals_per_launch, "launch_ms": kern_ms,
+            "peak_source": f"{peaks['pipe_source']}; {peaks['fp64_per_clk_sm']:.1f} "
+                           f"instr/clk/SM x {n_sm} SMs x {sm_mhz:.0f} MHz (sampled)",
+            "hbm": {"achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9,
+                    "peak_gbs": peaks["hbm_gbs"], "source": peaks["hbm_source"],
+                    "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        },
+        "cpu_baseline": cpu,
+        "secondary": secondary,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_sq(args, rank, world, local, cores, dist, torch):
+    """S(q) frames/s for cfg4 (N=50,000, N_q=2,446), device-resident and end to end."""
+    from mdhelper_b200 import _lib, synthetic
+    from mdhelper_b200.analysis.structure import StructureFactor
+    K, W, fps = args.steps, args.warmup, args.sq_frames_per_step
+    ring = 256                                    # distinct frames (154 MB > L2)
+    u = synthetic.lj_fluid(CFG4["n"], ring, seed=CFG4["seed"] + 1000 * rank)
+    L = float(u.trajectory.unitcells[0, 0])
+    q_max = 2 * np.pi * CFG4["n_max"] / L
+    sf = StructureFactor([u.atoms], n_points=CFG4["n_points"], q_max=q_max, verbose=False,
+                         batch_frames=fps)
+    n_q = len(sf._wavenumbers)
+    N = CFG4["n"]
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v1, dt1 = cpu_sq(u, sf._wavevectors, 1, 1)
+        vp, dtp = cpu_sq(u, sf._wavevectors, 3, cores)
+        cpu = {"value": vp, "unit": "frames/s", "cores": cores, "kind": "port",
+               "serial_value": v1,
+               "sample": f"serial: 1 frame in {dt1:.1f} s; {cores} OpenMP threads over "
+                         f"wavevectors: 3 frames in {dtp:.1f} s (C restatement of "
+                         "accelerated.py:81-165)"}
+
+    dev = torch.from_numpy(u.trajectory.coordinates).cuda()
+    ctx = _lib.Context(local)
+    ctx.sq_configure(N, [0, N], sf._wavevectors, [(-1, -1)], lattice_n=sf._lattice_n,
+                     lattice_b=sf._lattice_b, mode="lattice_fp64")
+    base = dev.data_ptr()
+
+    def step(s):
+        f0 = (s * fps) % ring
+        nf = min(fps, ring - f0)
+        ctx.sq_accumulate(base + 4 * 3 * N * f0, 3 * N, nf, device=True)
+        return nf
+
+    for s in range(W):
+        step(s)
+    ctx.sync()
+    ctx.sq_reset()
+    l0 = ctx.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    frames = 0
+    for s in range(W, W + K):
+        frames += step(s)
+    acc = torch.from_numpy(ctx.sq_fetch()).cuda()
+    if world > 1:
+        dist.all_reduce(acc)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = ctx.launch_count() - l0
+    kern = []
+    for s in range(W + K, W + K + 5):
+        nf = step(s)
+        kern.append(ctx.last_kernel_ms()[1] / nf * fps)
+    kern_ms = float(np.mean(kern))
+
+    for s in range(W):
+        f0 = (s * fps) % ring
+        sf.run(start=f0, stop=min(ring, f0 + fps))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_frames = 0
+    for s in range(W, W + K):
+        f0 = (s * fps) % ring
+        sf.run(start=f0, stop=min(ring, f0 + fps))
+        e2e_frames += sf.n_frames * world
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+
+    peaks = measured_peaks()
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    terms = fps * N * n_q
+    achieved = terms * FP64_OPS_PER_TERM / (kern_ms * 1e-3)
+    peak = peaks["fp64_per_clk_sm"] * n_sm * 1965e6
+    return {
+        "metric": "sq_frames_per_s", "value": frames * world / (ms * 1e-3), "unit": "frames/s",
+        "config": {"workload": f"cfg4: direct-sum S(q), N=50,000, n_points=32, "
+                               f"q_max=2*pi*16/L -> N_q={n_q}, mode=None, form=exp, fp64",
+                   "frames_per_step": fps, "terms_per_frame": N * n_q,
+                   "cache": f"ring of {ring} distinct frames (154 MB > L2)"},
+        "ms_per_step": ms / K, "gpu_launches": launches,
+        "e2e": {"value": e2e_frames / float(e2e_s.item()), "unit": "frames/s",
+                "h2d_bytes_per_step": fps * N * 12, "d2h_bytes_per_step": n_q * 8,
+                "api": "StructureFactor([atoms], n_points=32, q_max=...).run(start, stop)"},
+        "roofline": {"kernel": "sq_lattice_kernel<double,16>", "bound": "fp64_pipe",
+                     "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Ginstr/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "per_unit": f"{FP64_OPS_PER_TERM} DFMA per (q, r) term",
+                     "units_per_launch": terms, "launch_ms": kern_ms,
+                     "peak_source": f"{peaks['pipe_source']}; {peaks['fp64_per_clk_sm']:.1f} "
+                                    f"instr/clk/SM x {n_sm} SMs x 1965 MHz (max clock)",
+                     "sfu_equivalent_frac": (terms * 2 / (kern_ms * 1e-3))
+                     / (peaks["sfu_per_clk_sm"] * n_sm * 1965e6)},
+        "cpu_baseline": cpu,
+    }
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

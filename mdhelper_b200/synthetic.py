@@ -39,7 +39,7 @@ def _wrap_into(out: np.ndarray, pos: np.ndarray, L: np.float32) -> None:
 
 def fluid_positions(n: int, n_frames: int, *, rho: float = 0.8, seed: int = 0,
                     jitter: float = 0.15, step: float = 0.05,
-                    order: np.ndarray = None):
+                    order: np.ndarray = None, pinned: bool = True):
     """
     ``(positions float32 [F, n, 3], L float32)`` of a jittered-lattice fluid.
     ``order`` optionally permutes the particles (e.g. cations first).
@@ -50,22 +50,31 @@ def fluid_positions(n: int, n_frames: int, *, rho: float = 0.8, seed: int = 0,
     pos = (base + jitter * rng.standard_normal((n, 3))).astype(np.float32)
     if order is not None:
         pos = pos[order]
-    out, keep = pinned_empty((n_frames, n, 3), np.float32)
+    out, keep = _alloc((n_frames, n, 3), pinned)
     for f in range(n_frames):
         pos += np.float32(step) * rng.standard_normal((n, 3), dtype=np.float32)
         _wrap_into(out[f], pos, L)
     return out, L, keep
 
 
-def lj_fluid(n: int, n_frames: int, *, rho: float = 0.8, seed: int = 0):
+def _alloc(shape, pinned: bool):
+    if pinned:
+        return pinned_empty(shape, np.float32)
+    a = np.empty(shape, dtype=np.float32)
+    return a, a
+
+
+def lj_fluid(n: int, n_frames: int, *, rho: float = 0.8, seed: int = 0,
+             pinned: bool = True):
     """Universe of an ``n``-particle LJ-like fluid (configs 1 and 3)."""
-    pos, L, keep = fluid_positions(n, n_frames, rho=rho, seed=seed)
+    pos, L, keep = fluid_positions(n, n_frames, rho=rho, seed=seed, pinned=pinned)
     u = SyntheticUniverse(pos, np.array([L, L, L, 90, 90, 90], np.float32))
     u._keepalive = keep
     return u
 
 
-def electrolyte(n_ions: int, n_frames: int, *, rho: float = 0.8, seed: int = 0):
+def electrolyte(n_ions: int, n_frames: int, *, rho: float = 0.8, seed: int = 0,
+                pinned: bool = True):
     """
     Universe of ``n_ions`` ions, half cations and half anions with rock-salt
     species assignment on the jittered lattice (config 2).  Cations occupy
@@ -77,14 +86,16 @@ def electrolyte(n_ions: int, n_frames: int, *, rho: float = 0.8, seed: int = 0):
     parity = ijk.sum(axis=1) % 2
     order = np.concatenate((np.nonzero(parity == 0)[0], np.nonzero(parity == 1)[0]))
     n_cat = int((parity == 0).sum())
-    pos, L, keep = fluid_positions(n_ions, n_frames, rho=rho, seed=seed, order=order)
+    pos, L, keep = fluid_positions(n_ions, n_frames, rho=rho, seed=seed, order=order,
+                                   pinned=pinned)
     u = SyntheticUniverse(pos, np.array([L, L, L, 90, 90, 90], np.float32))
     u._keepalive = keep
     return u, u.select(slice(0, n_cat)), u.select(slice(n_cat, n_ions))
 
 
 def polymer_melt(n_chains: int, chain_length: int, n_frames: int, *,
-                 rho: float = 0.85, bond: float = 0.97, seed: int = 0):
+                 rho: float = 0.85, bond: float = 0.97, seed: int = 0,
+                 pinned: bool = True):
     """
     Universe of a coarse-grained melt: ``n_chains`` random-walk chains of
     ``chain_length`` beads (bond length ``bond``), wrapped (config 5).  One
@@ -98,7 +109,7 @@ def polymer_melt(n_chains: int, chain_length: int, n_frames: int, *,
     steps *= bond / np.linalg.norm(steps, axis=2, keepdims=True)
     steps[:, 0] = 0
     pos = (start + np.cumsum(steps, axis=1)).reshape(n, 3).astype(np.float32)
-    out, keep = pinned_empty((n_frames, n, 3), np.float32)
+    out, keep = _alloc((n_frames, n, 3), pinned)
     for f in range(n_frames):
         pos += np.float32(0.05) * rng.standard_normal((n, 3), dtype=np.float32)
         _wrap_into(out[f], pos, L)

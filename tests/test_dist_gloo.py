@@ -1,0 +1,58 @@
+"""CPU, world_size 2, gloo: frame sharding + the single all-reduce of the accumulators."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world_size, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from _fake import FakeRDF, FakeSSF
+        from mdhelper_b200.universe import SyntheticUniverse
+        g = dict(np.load(GOLDEN / "rdf_lj1000.npz"))
+        u = SyntheticUniverse(g["positions"], g["dims"])
+        r = FakeRDF(u.atoms, n_bins=int(g["n_bins"]), range=tuple(g["range"]),
+                    verbose=False).run()
+        # 5 frames over 2 ranks -> 3 + 2, as np.array_split does
+        assert r.n_local_frames == (3 if rank == 0 else 2)
+        assert r.n_frames == 5
+        assert np.array_equal(r.results.counts, g["counts"])
+        np.testing.assert_allclose(r.results.rdf, g["rdf"], rtol=1e-6)
+        # a strided selection and more ranks than frames on one side
+        r2 = FakeRDF(u.atoms, n_bins=int(g["n_bins"]), range=tuple(g["range"]),
+                     verbose=False).run(start=4)
+        assert r2.n_local_frames == (1 if rank == 0 else 0)
+
+        g = dict(np.load(GOLDEN / "sq_small.npz"))
+        u = SyntheticUniverse(g["positions"], g["dims"])
+        n = int(g["n_cat"])
+        cat, an = u.select(slice(0, n)), u.select(slice(n, u.atoms.n_atoms))
+        s = FakeSSF([cat, an], mode="partial", n_points=int(g["n_points"]),
+                    q_max=float(g["q_max"]), verbose=False).run()
+        assert s.n_local_frames == 1
+        np.testing.assert_allclose(s.results.ssf, g["ssf_partial_exp"], rtol=1e-9,
+                                   atol=1e-12)
+        np.save(os.path.join(out_dir, f"ok{rank}.npy"), r.results.counts)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_allreduce(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "ok0.npy")
+    b = np.load(tmp_path / "ok1.npy")
+    assert np.array_equal(a, b)          # every rank ends with the full result

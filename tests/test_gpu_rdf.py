@@ -1,0 +1,205 @@
+"""GPU: pair-histogram kernels through the C ABI vs the oracle / golden fixtures.
+Integer bin counts must be bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import universe_from
+from test_oracle import RDF_CASES, rdf_groups, rdf_kwargs
+
+pytestmark = pytest.mark.gpu
+
+HISTS = ["warp_atomic", "lane_private"]
+
+
+def _structure():
+    from mdhelper_b200.analysis import structure
+    return structure
+
+
+def _oracle():
+    from oracle import reference_port as rp
+    return rp
+
+
+def test_kat_radial_histogram(golden):
+    """The reference's own known-answer test (tests/test_analysis_structure.py:21-40)."""
+    g = golden("kat_radial_histogram")
+    for hist in HISTS:
+        got = _structure().radial_histogram(
+            g["origin"], g["neighbors"], int(g["n_bins"]), tuple(g["range"]), g["dims"],
+            hist=hist)
+        assert np.array_equal(got, g["expected_from_norms"])
+        assert np.array_equal(got, g["reference_counts"])
+
+
+@pytest.mark.parametrize("hist", HISTS)
+@pytest.mark.parametrize("name", RDF_CASES)
+def test_class_matches_golden(golden, name, hist):
+    g = golden(f"rdf_{name}")
+    u = universe_from(g)
+    ag1, ag2 = rdf_groups(u, g)
+    kw = rdf_kwargs(g)
+    if name == "dropx_density":
+        kw["norm"] = "density"
+    r = _structure().RadialDistributionFunction(
+        ag1, ag2, verbose=False, mode="allpairs", hist=hist, **kw).run()
+    assert r.results.counts.dtype == np.int64 or r.results.counts.dtype == int
+    assert np.array_equal(r.results.counts, g["counts"])
+    np.testing.assert_allclose(r.results.rdf, g["rdf"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("hist", HISTS)
+@pytest.mark.parametrize("name", ["lj1000", "twogroup", "excl11", "excl410",
+                                  "noncubic_npt", "unwrapped"])
+def test_cells_mode_matches_golden(golden, name, hist):
+    g = golden(f"rdf_{name}")
+    u = universe_from(g)
+    ag1, ag2 = rdf_groups(u, g)
+    kw = rdf_kwargs(g)
+    # the cell list needs >= 3 cells per axis: shorten the range where necessary
+    # and compare with the oracle instead of the stored counts
+    lmin = float(np.atleast_2d(g["dims"])[:, :3].min())
+    if kw["range"][1] * 1.00001 * 3 > lmin:
+        kw["range"] = (kw["range"][0], np.float32(lmin / 3.2).item())
+        want = _oracle().rdf_run(u, ag1, ag2, **kw)["counts"]
+    else:
+        want = g["counts"]
+    r = _structure().RadialDistributionFunction(
+        ag1, ag2, verbose=False, mode="cells", hist=hist, **kw).run()
+    assert np.array_equal(r.results.counts, want)
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (1, 700), (513, 511), (512, 1024), (33, 1537)])
+def test_ragged_sizes(n1, n2):
+    rng = np.random.default_rng(n1 * 10007 + n2)
+    dims = np.array([7.5, 8.25, 9.0, 90, 90, 90], np.float32)
+    p1 = (rng.random((n1, 3)) * dims[:3]).astype(np.float32)
+    p2 = (rng.random((n2, 3)) * dims[:3]).astype(np.float32)
+    want = _oracle().radial_histogram(p1, p2, 47, (0.0, 3.7), dims)
+    for hist in HISTS:
+        got = _structure().radial_histogram(p1, p2, 47, (0.0, 3.7), dims, hist=hist)
+        assert np.array_equal(got, want)
+
+
+def test_many_bins_falls_back_to_warp_atomics():
+    rng = np.random.default_rng(5)
+    dims = np.array([12, 12, 12, 90, 90, 90], np.float32)
+    p = (rng.random((900, 3)) * 12).astype(np.float32)
+    want = _oracle().radial_histogram(p, p, 3000, (0.0, 6.0), dims)
+    got = _structure().radial_histogram(p, p, 3000, (0.0, 6.0), dims)
+    assert np.array_equal(got, want)
+
+
+def test_same_group_symmetry_and_self_pairs():
+    """ag1 is ag2: ordered pairs, N self pairs in bin 0."""
+    from mdhelper_b200 import synthetic
+    u = synthetic.lj_fluid(1500, 2, seed=11)
+    L = float(u.dimensions[0])
+    S = _structure()
+    a = S.RadialDistributionFunction(u.atoms, n_bins=60, range=(0.0, L / 2),
+                                     norm=None, verbose=False).run()
+    b = S.RadialDistributionFunction(u.atoms, u.select(np.arange(1500)), n_bins=60,
+                                     range=(0.0, L / 2), norm=None, verbose=False).run()
+    assert np.array_equal(a.results.counts, b.results.counts)
+    want = _oracle().rdf_run(u, u.atoms, n_bins=60, range=(0.0, L / 2), norm=None)
+    assert np.array_equal(a.results.counts, want["counts"])
+    assert a.results.counts[0] >= 2 * 1500     # the self pairs, both frames
+    # swapping the groups of a two-group RDF cannot change the counts
+    g1, g2 = u.select(slice(0, 400)), u.select(slice(400, 1500))
+    c12 = S.RadialDistributionFunction(g1, g2, n_bins=60, range=(0.0, L / 2),
+                                       norm=None, verbose=False).run().results.counts
+    c21 = S.RadialDistributionFunction(g2, g1, n_bins=60, range=(0.0, L / 2),
+                                       norm=None, verbose=False).run().results.counts
+    assert np.array_equal(c12, c21)
+
+
+def test_frame_selection_batching_and_staged_feeder():
+    from mdhelper_b200 import synthetic
+    u = synthetic.lj_fluid(700, 9, seed=12)
+    S, rp = _structure(), _oracle()
+    kw = dict(n_bins=40, range=(0.0, 4.0))
+    r = S.RadialDistributionFunction(u.atoms, verbose=False, batch_frames=2, **kw).run(
+        start=1, stop=9, step=3)
+    want = rp.rdf_run(u, u.atoms, frames=[1, 4, 7], **kw)
+    assert np.array_equal(r.results.counts, want["counts"])
+    np.testing.assert_allclose(r.results.rdf, want["rdf"], rtol=1e-6)
+    # scattered selection -> staged (gather) feeder; explicit frame list
+    ix = np.random.default_rng(1).permutation(700)[:300]
+    grp = u.select(ix)
+    r = S.RadialDistributionFunction(grp, verbose=False, batch_frames=2, **kw).run(
+        frames=[0, 2, 3, 8])
+    want = rp.rdf_run(u, grp, frames=[0, 2, 3, 8], **kw)
+    assert np.array_equal(r.results.counts, want["counts"])
+
+
+def test_centre_of_mass_groupings():
+    from mdhelper_b200 import synthetic
+    u = synthetic.polymer_melt(40, 5, 2, seed=13)
+    S, rp = _structure(), _oracle()
+    L = float(u.dimensions[0])
+    r = S.RadialDistributionFunction(u.atoms, groupings="residues", n_bins=20,
+                                     range=(0.0, L / 2), verbose=False).run()
+    counts = np.zeros(20, dtype=np.int64)
+    for f in range(2):
+        ts = u.trajectory[f]
+        com = S._centers_of_mass(u.atoms, "residues", ts.positions)
+        counts += rp.radial_histogram(com, com, 20, (0.0, L / 2), ts.dimensions)
+    assert np.array_equal(r.results.counts, counts)
+
+
+def test_config2_sized_frame_against_oracle():
+    """One frame of the bench workload (10k x 10k two-group) vs the CPU oracle."""
+    from mdhelper_b200 import synthetic
+    u, cat, an = synthetic.electrolyte(20_000, 1, seed=20260002)
+    S, rp = _structure(), _oracle()
+    kw = dict(n_bins=201, range=(0.0, 14.5))
+    r = S.RadialDistributionFunction(cat, an, verbose=False, **kw).run()
+    want = rp.rdf_run(u, cat, an, method="bruteforce", **kw)
+    assert np.array_equal(r.results.counts, want["counts"])
+    np.testing.assert_allclose(r.results.rdf, want["rdf"], rtol=1e-6)
+    # pair conservation at full range: every ordered pair is within L*sqrt(3)/2
+    L = float(u.dimensions[0])
+    full = S.RadialDistributionFunction(cat, an, n_bins=64, range=(0.0, L),
+                                        norm=None, verbose=False).run()
+    assert full.results.counts.sum() == cat.n_atoms * an.n_atoms
+
+
+def test_large_cutoff_run_modes_agree():
+    """Size-independent property at a config-3-like scale: the all-pairs and the
+    cell-list kernels (and both histogram schemes) give identical counts."""
+    from mdhelper_b200 import synthetic
+    u = synthetic.lj_fluid(60_000, 2, seed=20260003)
+    S = _structure()
+    kw = dict(n_bins=100, range=(0.0, 2.5), norm=None, verbose=False)
+    ref = S.RadialDistributionFunction(u.atoms, mode="allpairs", **kw).run().results.counts
+    for hist in HISTS:
+        c = S.RadialDistributionFunction(u.atoms, mode="cells", hist=hist,
+                                         **kw).run().results.counts
+        assert np.array_equal(c, ref)
+    auto = S.RadialDistributionFunction(u.atoms, **kw).run().results.counts
+    assert np.array_equal(auto, ref)
+    # one frame against the oracle's grid search
+    want = _oracle().rdf_run(u, u.atoms, n_bins=100, range=(0.0, 2.5), norm=None,
+                             frames=[0], method="nsgrid")["counts"]
+    one = S.RadialDistributionFunction(u.atoms, **kw).run(stop=1).results.counts
+    assert np.array_equal(one, want)
+
+
+def test_argument_errors():
+    from mdhelper_b200 import _lib
+    ctx = _lib.Context(0)
+    with pytest.raises(RuntimeError):      # accumulate before configure
+        ctx.rdf_accumulate(np.zeros((2, 3), np.float32), 6, None, 0,
+                           np.ones((1, 3), np.float32), 1)
+    with pytest.raises(ValueError):
+        ctx.rdf_configure(4, 5, True, np.array([0.0, 1.0, 4.0]), 0.0, 2.0)
+    with pytest.raises(ValueError):
+        ctx.rdf_configure(4, 4, True, np.array([0.0, 4.0, 1.0]), 0.0, 2.0)
+    ctx.rdf_configure(4, 4, True, np.array([0.0, 1.0, 4.0]), 0.0, 2.0)
+    with pytest.raises(ValueError):        # non-positive box edge
+        ctx.rdf_accumulate(np.zeros((4, 3), np.float32), 12, None, 0,
+                           np.zeros((1, 3), np.float32), 1)
+    with pytest.raises(NotImplementedError):
+        _structure().radial_histogram(np.zeros((2, 3)), np.zeros((2, 3)), 4, (0, 1),
+                                      (5, 5, 5, 90, 60, 90))
+    ctx.close()

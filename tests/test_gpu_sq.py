@@ -1,0 +1,148 @@
+"""GPU: structure-factor kernels through the C ABI vs the oracle / golden fixtures
+(tolerance: 1e-6 relative per BASELINE.json; the fp64 kernels are held to 1e-9)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import universe_from
+
+pytestmark = pytest.mark.gpu
+
+
+def _S():
+    from mdhelper_b200.analysis import structure
+    return structure
+
+
+def _groups(u, g):
+    n = int(g["n_cat"])
+    return u.select(slice(0, n)), u.select(slice(n, u.atoms.n_atoms))
+
+
+@pytest.mark.parametrize("kernel", [None, "general_fp64"])
+@pytest.mark.parametrize("mode", [None, "pair", "partial"])
+def test_class_matches_golden(golden, mode, kernel):
+    g = golden("sq_small")
+    u = universe_from(g)
+    cat, an = _groups(u, g)
+    for form in ("exp", "trig"):
+        s = _S().StructureFactor([cat, an], mode=mode, form=form,
+                                 n_points=int(g["n_points"]), q_max=float(g["q_max"]),
+                                 kernel=kernel, verbose=False).run()
+        np.testing.assert_allclose(s.results.ssf, g[f"ssf_{mode}_{form}"], rtol=1e-9,
+                                   atol=1e-12)
+        np.testing.assert_allclose(s.results.wavenumbers,
+                                   g[f"wavenumbers_{mode}_{form}"], rtol=1e-13)
+    assert len(s.results.pairs) == (3 if mode == "partial" else 1)
+
+
+def test_raw_grid_order_and_rho(golden):
+    """sort=False, unique=False exposes the meshgrid ordering (Appendix B); rho(q)
+    of the last frame is seam #2 itself."""
+    g = golden("sq_small")
+    u = universe_from(g)
+    s = _S().StructureFactor([u.atoms], n_points=int(g["n_points"]),
+                             q_max=float(g["q_max"]), sort=False, unique=False,
+                             verbose=False).run()
+    assert np.array_equal(s._wavevectors, g["wavevectors_raw"])
+    np.testing.assert_allclose(s.results.ssf, g["ssf_raw"], rtol=1e-9, atol=1e-12)
+    rho = s._ctx.sq_fetch_rho()[0]
+    np.testing.assert_allclose(rho, g["rho_last"], rtol=0, atol=1e-9)
+    # S(q = 0) = N exactly
+    assert s.results.ssf[0, 0] == pytest.approx(u.atoms.n_atoms, rel=1e-14)
+
+
+def test_off_lattice_wavevectors(golden):
+    g = golden("sq_small")
+    u = universe_from(g)
+    cat, an = _groups(u, g)
+    s = _S().StructureFactor([u.atoms], n_points=6, n_surfaces=3, n_surface_points=8,
+                             verbose=False).run()
+    np.testing.assert_allclose(s.results.ssf, g["ssf_surfaces"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(s.results.wavenumbers, g["wavenumbers_surfaces"],
+                               rtol=1e-13)
+    s = _S().StructureFactor([cat, an], mode="partial",
+                             wavevectors=g["wavevectors_user"], sort=False, unique=False,
+                             verbose=False).run()
+    np.testing.assert_allclose(s.results.ssf, g["ssf_user"], rtol=1e-9, atol=1e-12)
+
+
+def test_noncubic(golden):
+    g = golden("sq_noncubic")
+    u = universe_from(g)
+    for kernel in (None, "general_fp64"):
+        s = _S().StructureFactor([u.atoms], n_points=int(g["n_points"]),
+                                 q_max=float(g["q_max"]), kernel=kernel,
+                                 verbose=False).run()
+        np.testing.assert_allclose(s.results.ssf, g["ssf"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(s.results.wavenumbers, g["wavenumbers"], rtol=1e-13)
+
+
+def test_config4_frame(golden):
+    """N = 50,000, n_max = 16 (N_q = 2,446): one frame of the bench workload against
+    the reference's numba kernel output."""
+    from mdhelper_b200 import synthetic
+    g = golden("sq_cfg4_frame")
+    u = synthetic.lj_fluid(int(g["n"]), 1, seed=int(g["seed"]))
+    sha = hashlib.sha256(np.ascontiguousarray(u.trajectory.coordinates).tobytes())
+    assert sha.hexdigest() == str(g["positions_sha256"]), "synthetic generator drifted"
+    s = _S().StructureFactor([u.atoms], n_points=32, q_max=float(g["q_max"]),
+                             sort=False, unique=False, verbose=False).run()
+    assert s.results.ssf.shape == (1, 2446)
+    np.testing.assert_allclose(s.results.ssf, g["ssf_raw"], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(s.results.ssf, g["ssf_raw"], rtol=1e-9, atol=1e-12)
+    su = _S().StructureFactor([u.atoms], n_points=32, q_max=float(g["q_max"]),
+                              verbose=False).run()
+    np.testing.assert_allclose(su.results.ssf, g["ssf_unique"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(su.results.wavenumbers, g["wavenumbers_unique"],
+                               rtol=1e-13)
+    # approximate FP32 mode: report, and hold to a loose bound
+    sf = _S().StructureFactor([u.atoms], n_points=32, q_max=float(g["q_max"]),
+                              sort=False, unique=False, precision="fp32",
+                              verbose=False).run()
+    rel = np.abs(sf.results.ssf - g["ssf_raw"]) / g["ssf_raw"]
+    print("fp32 mode: max rel err", rel.max(), "median", np.median(rel))
+    assert rel.max() < 1e-3
+
+
+def test_default_grid_n_points_32_no_qmax():
+    """32,768 wavevectors (nz up to 31: two column segments per (nx, ny))."""
+    from mdhelper_b200 import synthetic
+    from oracle import reference_port as rp
+    u = synthetic.lj_fluid(300, 2, seed=21)
+    s = _S().StructureFactor([u.atoms], sort=False, unique=False, verbose=False).run()
+    assert s.results.ssf.shape == (1, 32768)
+    want = rp.ssf_run(u, [u.atoms], sort=False, unique=False, n_threads=8)
+    np.testing.assert_allclose(s.results.ssf, want["ssf"], rtol=1e-9, atol=1e-11)
+
+
+def test_frame_additivity_and_selection():
+    from mdhelper_b200 import synthetic
+    from oracle import reference_port as rp
+    u = synthetic.lj_fluid(500, 7, seed=22)
+    kw = dict(n_points=8, q_max=3.0)
+    s = _S().StructureFactor([u.atoms], batch_frames=2, verbose=False, **kw).run(
+        start=1, step=2)
+    want = rp.ssf_run(u, [u.atoms], frames=[1, 3, 5], **kw)
+    np.testing.assert_allclose(s.results.ssf, want["ssf"], rtol=1e-9, atol=1e-12)
+    # residue centres of mass (host helper) on the general path
+    um = synthetic.polymer_melt(30, 4, 2, seed=23)
+    s = _S().StructureFactor([um.atoms], groupings="residues", mode="pair",
+                             verbose=False, **kw).run()
+    assert s.results.ssf.shape[0] == 1 and np.isfinite(s.results.ssf).all()
+
+
+def test_argument_errors():
+    from mdhelper_b200 import _lib
+    ctx = _lib.Context(0)
+    wv = np.eye(3)
+    with pytest.raises(RuntimeError):
+        ctx.sq_accumulate(np.zeros((4, 3), np.float32), 12, 1)
+    with pytest.raises(ValueError):
+        ctx.sq_configure(4, [0, 3], wv, [(-1, -1)])          # offsets do not reach n
+    with pytest.raises(ValueError):
+        ctx.sq_configure(4, [0, 4], wv, [(0, 1)])            # missing group
+    with pytest.raises(ValueError):
+        ctx.sq_configure(4, [0, 4], wv, [(-1, -1)], mode="lattice_fp64")  # no lattice
+    ctx.close()

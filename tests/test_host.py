@@ -1,0 +1,193 @@
+"""CPU: host-side logic (universe, frame feeder, frame selection, wavevectors, normalisation)."""
+import numpy as np
+import pytest
+
+from mdhelper_b200 import synthetic
+from mdhelper_b200.analysis import base, structure
+from mdhelper_b200.analysis._binning import squared_thresholds
+from mdhelper_b200.universe import SyntheticUniverse
+from oracle import reference_port as rp
+
+
+def test_thresholds_reproduce_numpy_histogram():
+    rng = np.random.default_rng(3)
+    for nb, rg in [(201, (0, 15.0)), (10, (0, 11)), (50, (1.0, 9.0)), (37, (2.0, 7.3))]:
+        T = squared_thresholds(nb, rg)
+        edges = np.linspace(*rg, nb + 1)
+        d2 = np.concatenate([rng.random(200_000) * (rg[1] * 1.2) ** 2, edges ** 2,
+                             np.nextafter(edges ** 2, np.inf),
+                             np.nextafter(edges ** 2, -np.inf), T,
+                             np.nextafter(T, -np.inf), np.nextafter(T, np.inf)])
+        d2 = d2[d2 >= 0]
+        d = np.sqrt(d2)
+        keep = (d > rg[0] - np.finfo(float).eps) & (d <= rg[1])
+        ref = np.histogram(d[keep], bins=nb, range=rg)[0]
+        k = np.searchsorted(T, d2, side="right") - 1
+        ok = (k >= 0) & (k < nb)
+        assert np.array_equal(ref, np.bincount(k[ok], minlength=nb))
+
+
+def test_thresholds_reject_bad_ranges():
+    with pytest.raises(ValueError):
+        squared_thresholds(10, (3.0, 1.0))
+    with pytest.raises(ValueError):
+        squared_thresholds(0, (0.0, 1.0))
+
+
+def test_universe_protocol():
+    u = synthetic.lj_fluid(100, 4, seed=2)
+    tr = u.trajectory
+    assert len(tr) == 4 and tr.n_atoms == 100
+    ts = tr[2]
+    assert ts.frame == 2 and ts.positions.dtype == np.float32
+    assert u.atoms.positions.shape == (100, 3)
+    L = float(ts.dimensions[0])
+    assert ts.volume == pytest.approx(L ** 3, rel=1e-12)
+    assert tr.check_slice_indices(None, None, None) == (0, 4, 1)
+    assert [t.frame for t in tr[1:4:2]] == [1, 3]
+    g = u.select(slice(10, 20))
+    assert g.n_atoms == 10 and g == u.select(np.arange(10, 20))
+    with pytest.raises(IndexError):
+        tr[7]
+
+
+def test_feeder_zero_copy_equals_staged():
+    u = synthetic.lj_fluid(50, 7, seed=4)
+    sets = [np.arange(5, 30)]
+    frames = np.arange(1, 7, 2)
+    zc = base.FrameFeeder(u.trajectory, sets, frames, 2)
+    assert zc.zero_copy
+    st = base.FrameFeeder(u.trajectory, [np.array([5, 7, 6] + list(range(8, 30)))],
+                          frames, 2)
+    assert not st.zero_copy
+    import ctypes
+    got = []
+    for b in zc:
+        for f in range(b.n_frames):
+            addr = b.ptrs[0] + 4 * b.strides[0] * f
+            a = np.ctypeslib.as_array((ctypes.c_float * 75).from_address(addr))
+            got.append(a.reshape(25, 3).copy())
+    want = [u.trajectory.coordinates[f, 5:30] for f in frames]
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    got = []
+    for b in st:
+        a = b.keepalive[0][0][:b.n_frames]
+        got.extend(x.copy() for x in a)
+    order = [5, 7, 6] + list(range(8, 30))
+    want = [u.trajectory.coordinates[f, order] for f in frames]
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+
+
+def test_setup_frames_semantics():
+    u = synthetic.lj_fluid(10, 9, seed=5)
+    a = base.GpuAnalysisBase(u.trajectory)
+    a._setup_frames(u.trajectory, 2, 9, 3)
+    assert list(a._frame_list) == [2, 5, 8] and a.n_frames == 3
+    a._setup_frames(u.trajectory, frames=[0, 4])
+    assert list(a._frame_list) == [0, 4]
+    a._setup_frames(u.trajectory, frames=np.array([True] + [False] * 7 + [True]))
+    assert list(a._frame_list) == [0, 8]
+    with pytest.raises(ValueError):
+        a._setup_frames(u.trajectory, start=1, frames=[0])
+
+
+def test_wavevector_grid_matches_reference_construction():
+    u = synthetic.lj_fluid(20, 1, seed=6)
+    for n_points, q_max in ((6, None), (9, 2.0)):
+        s = structure.StructureFactor([u.atoms], n_points=n_points, q_max=q_max)
+        wv, wn = rp.lattice_wavevectors(u.dimensions[:3].copy(), n_points, q_max)
+        assert np.array_equal(s._wavevectors, wv)
+        assert np.array_equal(s._wavenumbers, wn)
+        n, b = s._lattice_n, s._lattice_b
+        np.testing.assert_allclose(n * b, wv, rtol=4e-16, atol=0)
+    # non-cubic
+    u = SyntheticUniverse(np.zeros((1, 4, 3), np.float32),
+                          np.array([9, 11.5, 14.25, 90, 90, 90], np.float32))
+    s = structure.StructureFactor([u.atoms], n_points=5, q_max=3.0)
+    wv, _ = rp.lattice_wavevectors(u.dimensions[:3].copy(), 5, 3.0)
+    assert np.array_equal(s._wavevectors, wv)
+    # user wavevectors on / off the lattice
+    s2 = structure.StructureFactor([u.atoms], wavevectors=wv[::-1].copy())
+    assert s2._lattice_n is not None
+    s3 = structure.StructureFactor([u.atoms], wavevectors=wv + 0.01)
+    assert s3._lattice_n is None
+
+
+def test_constructor_errors_match_reference_messages():
+    u = synthetic.lj_fluid(20, 1, seed=6)
+    with pytest.raises(ValueError, match="Invalid grouping"):
+        structure.RadialDistributionFunction(u.atoms, groupings="molecules")
+    with pytest.raises(ValueError, match="Invalid axis to drop"):
+        structure.RadialDistributionFunction(u.atoms, drop_axis=5)
+    with pytest.raises(ValueError, match="exactly one or two groups"):
+        structure.StructureFactor([u.atoms[:5], u.atoms[5:10], u.atoms[10:]], mode="pair")
+    with pytest.raises(ValueError, match="do not contain all atoms"):
+        structure.StructureFactor([u.atoms[:5]])
+    with pytest.raises(ValueError, match="must have length 3"):
+        structure.StructureFactor([u.atoms], dimensions=(1, 2))
+    assert structure.RadialDistributionFunction(u.atoms, drop_axis="z")._drop_axis == 2
+
+
+from _fake import FakeRDF as _FakeRDF, FakeSSF  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["lj1000", "excl410", "dropz", "dropx_density",
+                                  "noncubic_npt"])
+def test_rdf_normalisation_matches_golden(golden, name):
+    from test_oracle import rdf_groups, rdf_kwargs
+    from conftest import universe_from
+    g = golden(f"rdf_{name}")
+    u = universe_from(g)
+    ag1, ag2 = rdf_groups(u, g)
+    kw = rdf_kwargs(g)
+    if name == "dropx_density":
+        kw["norm"] = "density"
+    r = _FakeRDF(ag1, ag2, verbose=False, **kw).run()
+    assert np.array_equal(r.results.counts, g["counts"])
+    np.testing.assert_allclose(r.results.rdf, g["rdf"], rtol=1e-6)
+    if "edges" in g:
+        assert np.array_equal(r.results.edges, g["edges"])
+        assert np.array_equal(r.results.bins, g["bins"])
+    np.testing.assert_allclose(r._get_rdf() if kw.get("norm", "rdf") == "rdf"
+                               else r.results.rdf, r.results.rdf)
+
+
+def test_results_container_and_save(tmp_path):
+    h = base.Hash()
+    h.x = np.arange(3)
+    assert h["x"] is h.x and h.missing is None
+    u = synthetic.lj_fluid(30, 2, seed=8)
+    r = _FakeRDF(u.atoms, n_bins=5, range=(0.0, 1.5), verbose=False).run()
+    r.results.pop("units")
+    r.save(str(tmp_path / "out"))
+    z = np.load(tmp_path / "out.npz")
+    assert np.array_equal(z["counts"], r.results.counts)
+
+
+def test_centres_of_mass_helper():
+    u = synthetic.polymer_melt(5, 4, 1, seed=9)
+    pos = u.trajectory[0].positions
+    com = structure._centers_of_mass(u.atoms, "residues", pos)
+    want = pos.reshape(5, 4, 3).astype(np.float64).mean(axis=1)
+    np.testing.assert_allclose(com, want, rtol=1e-12)
+    assert u.atoms.n_residues == 5
+
+
+def test_ssf_host_logic_matches_golden(golden):
+    from conftest import universe_from
+    g = golden("sq_small")
+    u = universe_from(g)
+    n = int(g["n_cat"])
+    cat, an = u.select(slice(0, n)), u.select(slice(n, u.atoms.n_atoms))
+    for mode in (None, "pair", "partial"):
+        s = FakeSSF([cat, an], mode=mode, n_points=int(g["n_points"]),
+                    q_max=float(g["q_max"]), verbose=False).run()
+        np.testing.assert_allclose(s.results.ssf, g[f"ssf_{mode}_exp"], rtol=1e-9,
+                                   atol=1e-12)
+        np.testing.assert_allclose(s.results.wavenumbers, g[f"wavenumbers_{mode}_exp"],
+                                   rtol=1e-13)
+    s = FakeSSF([u.atoms], n_points=6, n_surfaces=3, n_surface_points=8,
+                verbose=False).run()
+    np.testing.assert_allclose(s.results.ssf, g["ssf_surfaces"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(s.results.wavenumbers, g["wavenumbers_surfaces"],
+                               rtol=1e-13)

@@ -1,0 +1,112 @@
+"""CPU: the oracle against the golden fixtures (generated from the real reference)."""
+import numpy as np
+import pytest
+
+from conftest import universe_from
+from oracle import ref_harness, reference_port as rp
+
+RDF_CASES = ["lj1000", "twogroup", "excl11", "excl410", "dropz", "dropx_density",
+             "lattice_edges", "noncubic_npt", "unwrapped"]
+
+
+def rdf_kwargs(g):
+    kw = dict(n_bins=int(g["n_bins"]), range=tuple(float(x) for x in g["range"]))
+    if "exclusion" in g:
+        kw["exclusion"] = tuple(int(x) for x in g["exclusion"])
+    if "drop_axis" in g:
+        kw["drop_axis"] = int(g["drop_axis"])
+    return kw
+
+
+def rdf_groups(u, g):
+    if "n_cat" in g:
+        n = int(g["n_cat"])
+        return u.select(slice(0, n)), u.select(slice(n, u.atoms.n_atoms))
+    return u.atoms, None
+
+
+def test_kat_radial_histogram(golden):
+    """The reference's own known-answer construction
+    (tests/test_analysis_structure.py:21-40) pins the restated distances."""
+    g = golden("kat_radial_histogram")
+    got = rp.radial_histogram(g["origin"], g["neighbors"], int(g["n_bins"]),
+                              tuple(g["range"]), g["dims"])
+    assert np.array_equal(got, g["reference_counts"])
+    assert np.array_equal(got, g["expected_from_norms"])
+
+
+@pytest.mark.parametrize("name", RDF_CASES)
+def test_rdf_port_matches_golden(golden, name):
+    g = golden(f"rdf_{name}")
+    u = universe_from(g)
+    ag1, ag2 = rdf_groups(u, g)
+    kw = rdf_kwargs(g)
+    if name == "dropx_density":
+        kw["norm"] = "density"
+    out = rp.rdf_run(u, ag1, ag2, **kw)
+    assert np.array_equal(out["counts"], g["counts"])
+    np.testing.assert_allclose(out["rdf"], g["rdf"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["lj1000", "noncubic_npt", "excl11"])
+def test_bruteforce_equals_cells(golden, name):
+    """The two oracle search strategies must agree pair for pair."""
+    g = golden(f"rdf_{name}")
+    pos, dims = g["positions"][0], np.atleast_2d(g["dims"])[0]
+    rmax = float(min(g["range"][1], dims[:3].min() / 3.001))
+    pb, db = rp.capped_distance(pos, pos, rmax, -1e-16, box=dims, method="bruteforce")
+    pc, dc = rp.capped_distance(pos, pos, rmax, -1e-16, box=dims, method="nsgrid")
+    ob = np.lexsort((pb[:, 1], pb[:, 0]))
+    oc = np.lexsort((pc[:, 1], pc[:, 0]))
+    assert np.array_equal(pb[ob], pc[oc])
+    assert np.array_equal(db[ob], dc[oc])
+
+
+def test_sq_port_matches_golden(golden):
+    g = golden("sq_small")
+    u = universe_from(g)
+    n = int(g["n_cat"])
+    cat, an = u.select(slice(0, n)), u.select(slice(n, u.atoms.n_atoms))
+    for mode in (None, "pair", "partial"):
+        out = rp.ssf_run(u, [cat, an], mode=mode, n_points=int(g["n_points"]),
+                         q_max=float(g["q_max"]))
+        for form in ("exp", "trig"):
+            np.testing.assert_allclose(out["ssf"], g[f"ssf_{mode}_{form}"],
+                                       rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(out["wavenumbers"],
+                                       g[f"wavenumbers_{mode}_{form}"], rtol=1e-13)
+    out = rp.ssf_run(u, [u.atoms], n_points=int(g["n_points"]),
+                     q_max=float(g["q_max"]), sort=False, unique=False, n_threads=2)
+    np.testing.assert_allclose(out["ssf"], g["ssf_raw"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(out["wavevectors"], g["wavevectors_raw"], rtol=0, atol=0)
+    rho = rp.delta_fourier_transform_sum(g["wavevectors_raw"],
+                                         g["positions"][-1].astype(np.float64))
+    np.testing.assert_allclose(rho, g["rho_last"], rtol=1e-10, atol=1e-9)
+    out = rp.ssf_run(u, [cat, an], mode="partial", wavevectors=g["wavevectors_user"],
+                     sort=False, unique=False)
+    np.testing.assert_allclose(out["ssf"], g["ssf_user"], rtol=1e-9, atol=1e-12)
+
+
+def test_sq_port_noncubic(golden):
+    g = golden("sq_noncubic")
+    u = universe_from(g)
+    out = rp.ssf_run(u, [u.atoms], n_points=int(g["n_points"]), q_max=float(g["q_max"]))
+    np.testing.assert_allclose(out["ssf"], g["ssf"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(out["wavenumbers"], g["wavenumbers"], rtol=1e-13)
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="/root/reference not present")
+def test_port_matches_live_reference():
+    """Where the reference tree exists, the port is checked against the real classes."""
+    from mdhelper_b200 import synthetic
+    S = ref_harness.load()
+    u, cat, an = synthetic.electrolyte(250, 2, seed=7)
+    L = float(u.dimensions[0])
+    r = S.RadialDistributionFunction(cat, an, n_bins=31, range=(0.2, L / 2),
+                                     exclusion=(2, 3), verbose=False).run()
+    p = rp.rdf_run(u, cat, an, n_bins=31, range=(0.2, L / 2), exclusion=(2, 3))
+    assert np.array_equal(p["counts"], r.results.counts)
+    np.testing.assert_allclose(p["rdf"], r.results.rdf, rtol=1e-12)
+    s = S.StructureFactor([cat, an], mode="partial", n_points=5, verbose=False).run()
+    p = rp.ssf_run(u, [cat, an], mode="partial", n_points=5)
+    np.testing.assert_allclose(p["ssf"], s.results.ssf, rtol=1e-10, atol=1e-12)
