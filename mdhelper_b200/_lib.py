@@ -13,8 +13,11 @@ import pathlib
 
 import numpy as np
 
+import os
+
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libmdh_b200.so"
+# MDH_B200_LIB lets a profiling session A/B another build of the same ABI
+LIB_PATH = pathlib.Path(os.environ.get("MDH_B200_LIB", _HERE / "libmdh_b200.so"))
 
 MDH_OK, MDH_EINVAL, MDH_ECUDA, MDH_ESTATE, MDH_ENOMEM = 0, -1, -2, -3, -4
 MDH_HOST, MDH_DEVICE = 0, 1

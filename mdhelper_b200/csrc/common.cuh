@@ -65,6 +65,8 @@ struct RdfState {
     size_t h_boxes_cap = 0;
     cudaEvent_t ev_boxes = nullptr;       // previous box upload has been consumed
     int64_t evals = 0;     // all-pairs evaluations (host-side count)
+    int ipt = 2;           // i-particles per thread of the all-pairs kernel
+    bool fast_bins = false;  // branch-free bin guess certified for this configuration
 };
 
 struct SqWorkItem {        // one thread's column segment of the lattice kernels
@@ -78,7 +80,7 @@ struct SqState {
     bool lattice = false;
     int nmax[3] = {0, 0, 0};
     double b[3] = {0, 0, 0};
-    int rz = 0, n_items = 0;
+    int rz = 0, n_items = 0, block = 256;
     std::vector<int64_t> group_offsets;
     std::vector<int32_t> pairs;
     DevBuf qv;             // double[n_q][3]

@@ -20,7 +20,16 @@
 //
 // All FP64 arithmetic on the path uses __dmul_rn/__dadd_rn/__dsub_rn so nvcc
 // can never contract it; the file is additionally built with -fmad=false.
+//
+// Kernel shape (rdf_allpairs_kernel): 256 threads; every thread keeps IPT
+// i-particles in registers; j-tiles of 256*IPT particles are staged in shared
+// memory with cp.async (double buffered) and read as broadcast LDS.128; the
+// inner loop is branch-free (certified bin guess + one fp64 compare) so that
+// several pairs are in flight per thread; histograms are privatised per lane
+// (packed 8-bit counters, no atomics) or per warp (u32 shared atomics) and
+// merged into the global int64 histogram once per block.
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,28 +40,34 @@ using namespace rdfdev;
 
 namespace {
 
-// ---- all-pairs kernel -----------------------------------------------------------
-
 struct PairParams {
     const float4 *p1, *p2;
     int64_t pad1, pad2;            // float4 per frame
     int n1, n2;
     const FrameBox *boxes;
     const double *thr;             // T[0..n_bins]
-    int n_bins, n_words;
-    float g_scale, g_off;
+    int n_bins;
+    BinGuess guess;
     int same;
     int n_jchunks, jtiles_per_chunk, n_jtiles;
     unsigned long long *counts;
 };
 
-template <int HIST, bool EXCL>
+template <int HIST, int IPT>
+__host__ __device__ inline size_t pair_smem_bytes(int n_bins)
+{
+    return align16(sizeof(double) * (n_bins + 1)) + 2 * kThreads * IPT * sizeof(float4) +
+           hist_smem_bytes<HIST>(n_bins);
+}
+
+template <int HIST, bool EXCL, bool FAST, int IPT>
 __global__ void __launch_bounds__(kThreads, 2) rdf_allpairs_kernel(const PairParams P)
 {
+    constexpr int TILE = kThreads * IPT;
     extern __shared__ __align__(16) unsigned char smem[];
-    double2 *sT2 = reinterpret_cast<double2 *>(smem);
-    float4 *sJ = reinterpret_cast<float4 *>(smem + align16(sizeof(double2) * P.n_bins));
-    unsigned *sH = reinterpret_cast<unsigned *>(sJ + 2 * kTile);
+    double *sT = reinterpret_cast<double *>(smem);
+    float4 *sJ = reinterpret_cast<float4 *>(smem + align16(sizeof(double) * (P.n_bins + 1)));
+    unsigned *sH = reinterpret_cast<unsigned *>(sJ + 2 * TILE);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
@@ -64,39 +79,45 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_allpairs_kernel(const PairPar
     if (jt0 >= jt1) return;
 
     const int n_bins = P.n_bins;
-    for (int k = tid; k < n_bins; k += kThreads)
-        sT2[k] = make_double2(P.thr[k], P.thr[k + 1]);
-    const int n_hist_words = (HIST == MDH_HIST_WARP_ATOMIC)
-                                 ? kWarps * n_bins
-                                 : kWarps * P.n_words * 32 + n_bins;
+    const int n_words = priv_words(n_bins);
+    for (int k = tid; k <= n_bins; k += kThreads) sT[k] = P.thr[k];
+    const int n_hist_words = (int)(hist_smem_bytes<HIST>(n_bins) / sizeof(unsigned));
     for (int k = tid; k < n_hist_words; k += kThreads) sH[k] = 0;
 
     const float4 *f1 = P.p1 + (int64_t)frame * P.pad1;
     const float4 *f2 = P.same ? f1 : P.p2 + (int64_t)frame * P.pad2;
     const FrameBox fb = P.boxes[frame];
+    const BinGuess guess = P.guess;
 
-    float xi[kIPT], yi[kIPT], zi[kIPT];
-    int gi[kIPT];
-    unsigned wv[kIPT];
+    float xi[IPT], yi[IPT], zi[IPT];
+    int gi[IPT];
+    unsigned wv[IPT];
 #pragma unroll
-    for (int ii = 0; ii < kIPT; ++ii) {
-        const int i = it * kTile + ii * kThreads + tid;
+    for (int ii = 0; ii < IPT; ++ii) {
+        const int i = it * TILE + ii * kThreads + tid;
         wv[ii] = i < P.n1 ? 1u : 0u;
         const float4 a = f1[min(i, P.n1 - 1)];
-        xi[ii] = a.x; yi[ii] = a.y; zi[ii] = a.z; gi[ii] = __float_as_int(a.w);
+        // rows past the end of the group become NaN: every pair they form lands in
+        // the "not counted" slot, so the inner loop needs no validity test
+        xi[ii] = wv[ii] ? a.x : __int_as_float(0x7fc00000);
+        yi[ii] = a.y; zi[ii] = a.z; gi[ii] = __float_as_int(a.w);
     }
 
+    // warp-atomic layout per warp: [pad][n_bins bins][32 trash words]
     unsigned *myhist = (HIST == MDH_HIST_WARP_ATOMIC)
-                           ? sH + warp * n_bins
-                           : sH + (size_t)warp * P.n_words * 32;
-    unsigned *bhist = sH + (size_t)kWarps * P.n_words * 32;   // LANE_PRIVATE only
+                           ? sH + warp * warp_hist_words(n_bins) + 1
+                           : sH + (size_t)warp * n_words * 32;
+    unsigned *bhist = sH + (size_t)kWarps * n_words * 32;         // LANE_PRIVATE only
+    unsigned char *lane_base = reinterpret_cast<unsigned char *>(myhist) + 4 * lane;
+    const unsigned hist32 = (unsigned)__cvta_generic_to_shared(myhist);
+    const unsigned trash32 = hist32 + 4u * (unsigned)(n_bins + lane);
 
-    // stage the first j tile (packed buffers are padded to whole tiles)
+    // packed buffers are padded to whole tiles, so staging never reads out of bounds
     auto stage_tile = [&](int jt, int buf) {
-        const float4 *src = f2 + (int64_t)jt * kTile;
-        float4 *dst = sJ + buf * kTile;
+        const float4 *src = f2 + (int64_t)jt * TILE;
+        float4 *dst = sJ + buf * TILE;
 #pragma unroll
-        for (int q = 0; q < kIPT; ++q)
+        for (int q = 0; q < IPT; ++q)
             __pipeline_memcpy_async(dst + q * kThreads + tid, src + q * kThreads + tid,
                                     sizeof(float4));
         __pipeline_commit();
@@ -114,38 +135,50 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_allpairs_kernel(const PairPar
         __syncthreads();
 
         const unsigned weight = (P.same && jt > it) ? 2u : 1u;
-        const int jn = min(kTile, P.n2 - jt * kTile);
-        const float4 *tile = sJ + buf * kTile;
+        const int jn = min(TILE, P.n2 - jt * TILE);
+        const float4 *tile = sJ + buf * TILE;
 
         if (HIST == MDH_HIST_WARP_ATOMIC) {
 #pragma unroll 2
             for (int jj = 0; jj < jn; ++jj) {
                 const float4 pj = tile[jj];
 #pragma unroll
-                for (int ii = 0; ii < kIPT; ++ii) {
+                for (int ii = 0; ii < IPT; ++ii) {
                     const double d2 = pair_d2(xi[ii], yi[ii], zi[ii], pj, fb);
-                    int k = bin_index(d2, sT2, n_bins, P.g_scale, P.g_off);
-                    if (EXCL && gi[ii] == __float_as_int(pj.w)) k = n_bins;
-                    if (k < n_bins && wv[ii]) atomicAdd(&myhist[k], weight);
+                    const bool keep = !(EXCL && gi[ii] == __float_as_int(pj.w));
+                    if (FAST) {
+                        bool below;
+                        const int j = slot_fast_parts(d2, sT, n_bins, guess, below);
+                        // bin j - 1 if below else bin j; j == n_bins && !below (above
+                        // range, NaN rows, exclusions) goes to this lane's trash word
+                        unsigned a = (below ? hist32 - 4u : hist32) + 4u * (unsigned)j;
+                        if ((!below && j == n_bins) || !keep) a = trash32;
+                        red_shared(a, weight);
+                    } else {
+                        const int slot = slot_search(d2, sT, n_bins);
+                        if (keep && (unsigned)(slot - 1) < (unsigned)n_bins)
+                            atomicAdd(&myhist[slot - 1], weight);
+                    }
                 }
             }
         } else {
-            constexpr int kSeg = 254 / kIPT;      // increments per lane per flush <= 254
+            constexpr int kSeg = 254 / IPT;       // increments per lane per flush <= 254
             for (int j0 = 0; j0 < jn; j0 += kSeg) {
                 const int j1 = min(jn, j0 + kSeg);
 #pragma unroll 2
                 for (int jj = j0; jj < j1; ++jj) {
                     const float4 pj = tile[jj];
+                    int slot[IPT];
 #pragma unroll
-                    for (int ii = 0; ii < kIPT; ++ii) {
+                    for (int ii = 0; ii < IPT; ++ii) {
                         const double d2 = pair_d2(xi[ii], yi[ii], zi[ii], pj, fb);
-                        int k = bin_index(d2, sT2, n_bins, P.g_scale, P.g_off);
-                        if (EXCL && gi[ii] == __float_as_int(pj.w)) k = n_bins;
-                        unsigned *w = myhist + (k >> 2) * 32 + lane;
-                        *w += wv[ii] << ((k & 3) * 8);
+                        slot[ii] = slot_of<FAST>(d2, sT, n_bins, guess);
+                        if (EXCL && gi[ii] == __float_as_int(pj.w)) slot[ii] = 0;
                     }
+#pragma unroll
+                    for (int ii = 0; ii < IPT; ++ii) priv_add(lane_base, slot[ii], wv[ii]);
                 }
-                priv_flush(myhist, bhist, P.n_words, n_bins, lane, weight);
+                priv_flush(myhist, bhist, n_words, n_bins, lane, weight);
             }
         }
         __syncthreads();
@@ -157,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_allpairs_kernel(const PairPar
         unsigned long long s = 0;
         if (HIST == MDH_HIST_WARP_ATOMIC) {
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += sH[w * n_bins + k];
+            for (int w = 0; w < kWarps; ++w) s += sH[w * warp_hist_words(n_bins) + 1 + k];
         } else {
             s = bhist[k];
         }
@@ -165,11 +198,11 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_allpairs_kernel(const PairPar
     }
 }
 
-template <int HIST, bool EXCL>
+template <int HIST, bool EXCL, bool FAST, int IPT>
 int launch_allpairs(mdh_ctx *c, const PairParams &P, dim3 grid)
 {
-    const size_t smem = pair_smem_bytes<HIST>(P.n_bins, P.n_words);
-    auto kern = rdf_allpairs_kernel<HIST, EXCL>;
+    const size_t smem = pair_smem_bytes<HIST, IPT>(P.n_bins);
+    auto kern = rdf_allpairs_kernel<HIST, EXCL, FAST, IPT>;
     MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     kern<<<grid, kThreads, smem, c->stream>>>(P);
@@ -178,11 +211,39 @@ int launch_allpairs(mdh_ctx *c, const PairParams &P, dim3 grid)
     return MDH_OK;
 }
 
+template <int HIST, bool EXCL, bool FAST>
+int launch_allpairs_ipt(mdh_ctx *c, const PairParams &P, dim3 grid, int ipt)
+{
+    return ipt == 4 ? launch_allpairs<HIST, EXCL, FAST, 4>(c, P, grid)
+                    : launch_allpairs<HIST, EXCL, FAST, 2>(c, P, grid);
+}
+
+template <int HIST>
+int launch_allpairs_dyn(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl, bool fast,
+                        int ipt)
+{
+    if (excl)
+        return fast ? launch_allpairs_ipt<HIST, true, true>(c, P, grid, ipt)
+                    : launch_allpairs_ipt<HIST, true, false>(c, P, grid, ipt);
+    return fast ? launch_allpairs_ipt<HIST, false, true>(c, P, grid, ipt)
+                : launch_allpairs_ipt<HIST, false, false>(c, P, grid, ipt);
+}
+
 }  // namespace
 
 // ---- host side ------------------------------------------------------------------
 
 int rdf_cells_accumulate(mdh_ctx *c, int n_frames);   // rdf_cells.cu
+
+BinGuess rdf_bin_guess(const RdfState &R)
+{
+    BinGuess g;
+    const double scale = R.n_bins / (R.r_hi - R.r_lo);
+    const double margin = 1.0 / 64 + R.n_bins * (1.0 / 524288);
+    g.scale = (float)scale;
+    g.offset = (float)(-R.r_lo * scale + 0.5 - margin);
+    return g;
+}
 
 int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
                        const double *thr, double r_lo, double r_hi, int64_t e1, int64_t e2,
@@ -207,15 +268,20 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
                 "rdf: invalid mode");
     MDH_REQUIRE(hist >= MDH_HIST_AUTO && hist <= MDH_HIST_LANE_PRIVATE, MDH_EINVAL,
                 "rdf: invalid hist");
-    MDH_REQUIRE(r_hi > r_lo, MDH_EINVAL, "rdf: empty range");
+    MDH_REQUIRE(r_hi > r_lo && r_lo >= 0, MDH_EINVAL, "rdf: invalid range");
 
-    const int n_words = (n_bins + 1 + 3) / 4;
-    if (hist == MDH_HIST_AUTO)
-        hist = pair_smem_bytes<MDH_HIST_LANE_PRIVATE>(n_bins, n_words) <= 100 * 1024
-                   ? MDH_HIST_LANE_PRIVATE : MDH_HIST_WARP_ATOMIC;
+    // tuning knobs for experiments: MDH_TUNE="ipt=4,fast=0"
+    int ipt = 4, allow_fast = 1;
+    if (const char *t = getenv("MDH_TUNE")) {
+        if (const char *p = strstr(t, "ipt=")) ipt = atoi(p + 4) == 4 ? 4 : 2;
+        if (const char *p = strstr(t, "fast=")) allow_fast = atoi(p + 5) != 0;
+    }
+    // measured on B200 (profiles/): per-warp shared-memory atomics beat the
+    // lane-private byte counters at every bin count tried, and need less memory
+    if (hist == MDH_HIST_AUTO) hist = MDH_HIST_WARP_ATOMIC;
     const size_t need = hist == MDH_HIST_LANE_PRIVATE
-                            ? pair_smem_bytes<MDH_HIST_LANE_PRIVATE>(n_bins, n_words)
-                            : pair_smem_bytes<MDH_HIST_WARP_ATOMIC>(n_bins, n_words);
+                            ? pair_smem_bytes<MDH_HIST_LANE_PRIVATE, 4>(n_bins)
+                            : pair_smem_bytes<MDH_HIST_WARP_ATOMIC, 4>(n_bins);
     MDH_REQUIRE(need <= kMaxSmem, MDH_EINVAL,
                 "rdf: n_bins=%d needs %zu bytes of shared memory (> %zu)", n_bins, need,
                 kMaxSmem);
@@ -225,15 +291,30 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
     R.excl1 = e1; R.excl2 = e2; R.drop_axis = drop_axis; R.mode = mode; R.hist = hist;
     R.r_lo = r_lo; R.r_hi = r_hi; R.thr_hi = thr[n_bins];
     R.evals = 0;
+    R.ipt = ipt;
 
     if (int rc = R.thr.reserve(sizeof(double) * (n_bins + 2))) return rc;
     if (int rc = R.counts.reserve(sizeof(unsigned long long) * n_bins)) return rc;
+    if (int rc = R.cell[9].reserve(sizeof(unsigned long long) + sizeof(int))) return rc;
     std::vector<double> t(thr, thr + n_bins + 1);
     t.push_back(INFINITY);
     MDH_CUDA(cudaMemcpyAsync(R.thr.p, t.data(), sizeof(double) * t.size(),
                              cudaMemcpyHostToDevice, c->stream));
     MDH_CUDA(cudaMemsetAsync(R.counts.p, 0, sizeof(unsigned long long) * n_bins, c->stream));
-    MDH_CUDA(cudaStreamSynchronize(c->stream));   // t is a local
+    MDH_CUDA(cudaMemsetAsync(R.cell[9].p, 0, sizeof(unsigned long long) + sizeof(int),
+                             c->stream));
+    R.evals_dev_init = true;
+
+    // certify the branch-free bin guess for this configuration (else: binary search)
+    int *d_bad = reinterpret_cast<int *>(R.cell[9].as<unsigned long long>() + 1);
+    int h_bad = 0;
+    rdf_selfcheck_kernel<<<(n_bins + 1 + 127) / 128, 128, 0, c->stream>>>(
+        R.thr.as<double>(), n_bins, rdf_bin_guess(R), d_bad);
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    MDH_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MDH_CUDA(cudaStreamSynchronize(c->stream));   // also: t is a local
+    R.fast_bins = allow_fast && h_bad == 0;
     R.configured = true;
     return MDH_OK;
 }
@@ -307,8 +388,9 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
                              cudaMemcpyHostToDevice, c->stream));
     MDH_CUDA(cudaEventRecord(R.ev_boxes, c->stream));
 
-    const int64_t pad1 = (R.n1 + kTile - 1) / kTile * kTile;
-    const int64_t pad2 = (R.n2 + kTile - 1) / kTile * kTile;
+    const int tile = kThreads * R.ipt;
+    const int64_t pad1 = (R.n1 + tile - 1) / tile * tile;
+    const int64_t pad2 = (R.n2 + tile - 1) / tile * tile;
     if (int rc = rdf_upload_group(c, pos1, s1, location, R.n1, pad1, R.excl1, n_frames,
                                   R.raw1, R.pk1)) return rc;
     if (!R.same)
@@ -341,38 +423,34 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
         P.boxes = R.boxes.as<FrameBox>();
         P.thr = R.thr.as<double>();
         P.n_bins = R.n_bins;
-        P.n_words = (R.n_bins + 1 + 3) / 4;
-        P.g_scale = (float)(R.n_bins / (R.r_hi - R.r_lo));
-        P.g_off = (float)(-R.r_lo * R.n_bins / (R.r_hi - R.r_lo));
+        P.guess = rdf_bin_guess(R);
         P.same = R.same;
         P.counts = R.counts.as<unsigned long long>();
-        const int n_itiles = (int)(pad1 / kTile);
-        P.n_jtiles = (int)(P.pad2 / kTile);
+        const int n_itiles = (int)(pad1 / tile);
+        P.n_jtiles = (int)(P.pad2 / tile);
         const int64_t target = (int64_t)c->sm_count * 2 * 6;
         int64_t n_jchunks = (target + (int64_t)n_itiles * n_frames - 1) /
                             ((int64_t)n_itiles * n_frames);
         n_jchunks = std::max<int64_t>(1, std::min<int64_t>(n_jchunks, P.n_jtiles));
-        n_jchunks = std::max<int64_t>(n_jchunks, (P.n_jtiles + 4095) / 4096);
+        // a block's u32 partial histogram must not overflow: <= 2^31 weighted pairs
+        n_jchunks = std::max<int64_t>(n_jchunks, (P.n_jtiles + 1023) / 1024);
         P.jtiles_per_chunk = (int)((P.n_jtiles + n_jchunks - 1) / n_jchunks);
         P.n_jchunks = (int)((P.n_jtiles + P.jtiles_per_chunk - 1) / P.jtiles_per_chunk);
         dim3 grid((unsigned)(n_itiles * P.n_jchunks), (unsigned)n_frames);
         const bool excl = R.excl1 > 0;
-        int rc;
-        if (R.hist == MDH_HIST_LANE_PRIVATE)
-            rc = excl ? launch_allpairs<MDH_HIST_LANE_PRIVATE, true>(c, P, grid)
-                      : launch_allpairs<MDH_HIST_LANE_PRIVATE, false>(c, P, grid);
-        else
-            rc = excl ? launch_allpairs<MDH_HIST_WARP_ATOMIC, true>(c, P, grid)
-                      : launch_allpairs<MDH_HIST_WARP_ATOMIC, false>(c, P, grid);
+        int rc = R.hist == MDH_HIST_LANE_PRIVATE
+                     ? launch_allpairs_dyn<MDH_HIST_LANE_PRIVATE>(c, P, grid, excl, R.fast_bins,
+                                                                  R.ipt)
+                     : launch_allpairs_dyn<MDH_HIST_WARP_ATOMIC>(c, P, grid, excl, R.fast_bins,
+                                                                 R.ipt);
         if (rc) return rc;
         // pair evaluations the kernel performs (upper-triangle tiles when same_group)
         int64_t ev;
         if (R.same) {
             ev = 0;
             for (int a = 0; a < n_itiles; ++a) {
-                const int64_t ca = std::min<int64_t>(kTile, R.n1 - (int64_t)a * kTile);
-                const int64_t rest = R.n1 - (int64_t)a * kTile;   // j >= a*kTile
-                ev += ca * rest;
+                const int64_t ca = std::min<int64_t>(tile, R.n1 - (int64_t)a * tile);
+                ev += ca * (R.n1 - (int64_t)a * tile);          // j >= a*tile
             }
         } else {
             ev = R.n1 * R.n2;

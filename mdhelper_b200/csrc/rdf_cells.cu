@@ -126,43 +126,43 @@ struct CellParams {
     const CellGrid *grids;
     const FrameBox *boxes;
     const double *thr;
-    int n_bins, n_words;
-    float g_scale, g_off;
+    int n_bins;
+    BinGuess guess;
     unsigned long long *counts;
     unsigned long long *evals;
 };
 
 template <int HIST>
-__host__ __device__ inline size_t cells_smem_bytes(int n_bins, int n_words)
+__host__ __device__ inline size_t cells_smem_bytes(int n_bins)
 {
-    size_t b = align16(sizeof(double2) * n_bins);
-    if (HIST == MDH_HIST_WARP_ATOMIC) b += sizeof(unsigned) * kWarps * n_bins;
-    else b += sizeof(unsigned) * ((size_t)kWarps * n_words * 32 + n_bins);
-    return b;
+    return align16(sizeof(double) * (n_bins + 1)) + hist_smem_bytes<HIST>(n_bins);
 }
 
-template <int HIST, bool EXCL>
+template <int HIST, bool EXCL, bool FAST>
 __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    double2 *sT2 = reinterpret_cast<double2 *>(smem);
-    unsigned *sH = reinterpret_cast<unsigned *>(smem + align16(sizeof(double2) * P.n_bins));
+    double *sT = reinterpret_cast<double *>(smem);
+    unsigned *sH =
+        reinterpret_cast<unsigned *>(smem + align16(sizeof(double) * (P.n_bins + 1)));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
     const int n_bins = P.n_bins;
-    for (int k = tid; k < n_bins; k += kThreads)
-        sT2[k] = make_double2(P.thr[k], P.thr[k + 1]);
-    const int n_hist_words = (HIST == MDH_HIST_WARP_ATOMIC)
-                                 ? kWarps * n_bins
-                                 : kWarps * P.n_words * 32 + n_bins;
+    const int n_words = priv_words(n_bins);
+    for (int k = tid; k <= n_bins; k += kThreads) sT[k] = P.thr[k];
+    const int n_hist_words = (int)(hist_smem_bytes<HIST>(n_bins) / sizeof(unsigned));
     for (int k = tid; k < n_hist_words; k += kThreads) sH[k] = 0;
     __syncthreads();
 
     unsigned *myhist = (HIST == MDH_HIST_WARP_ATOMIC)
-                           ? sH + warp * n_bins
-                           : sH + (size_t)warp * P.n_words * 32;
-    unsigned *bhist = sH + (size_t)kWarps * P.n_words * 32;
+                           ? sH + warp * warp_hist_words(n_bins) + 1
+                           : sH + (size_t)warp * n_words * 32;
+    unsigned *bhist = sH + (size_t)kWarps * n_words * 32;
+    unsigned char *lane_base = reinterpret_cast<unsigned char *>(myhist) + 4 * lane;
+    const unsigned hist32 = (unsigned)__cvta_generic_to_shared(myhist);
+    const unsigned trash32 = hist32 + 4u * (unsigned)(n_bins + lane);
+    const BinGuess guess = P.guess;
 
     const CellGrid g = P.grids[frame];
     const FrameBox fb = P.boxes[frame];
@@ -187,17 +187,25 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
             const bool act = t < len;
             const float4 pj = __ldg(s2 + (act ? b + t : 0));
             const double d2 = pair_d2(pi.x, pi.y, pi.z, pj, fb);
-            int k = bin_index(d2, sT2, n_bins, P.g_scale, P.g_off);
-            if (EXCL && gi == __float_as_int(pj.w)) k = n_bins;
-            if (!act) k = n_bins;
-            if (HIST == MDH_HIST_WARP_ATOMIC) {
-                if (k < n_bins) atomicAdd(&myhist[k], 1u);
+            const bool keep = act && !(EXCL && gi == __float_as_int(pj.w));
+            if (HIST == MDH_HIST_WARP_ATOMIC && FAST) {
+                bool below;
+                const int j = slot_fast_parts(d2, sT, n_bins, guess, below);
+                unsigned a = (below ? hist32 - 4u : hist32) + 4u * (unsigned)j;
+                if ((!below && j == n_bins) || !keep) a = trash32;
+                red_shared(a, 1u);
             } else {
-                unsigned *w = myhist + (k >> 2) * 32 + lane;
-                *w += 1u << ((k & 3) * 8);
-                if (++steps == 254) {
-                    priv_flush(myhist, bhist, P.n_words, n_bins, lane, 1u);
-                    steps = 0;
+                int slot = slot_of<FAST>(d2, sT, n_bins, guess);
+                if (!keep) slot = 0;
+                if (HIST == MDH_HIST_WARP_ATOMIC) {
+                    if ((unsigned)(slot - 1) < (unsigned)n_bins)
+                        atomicAdd(&myhist[slot - 1], 1u);
+                } else {
+                    priv_add(lane_base, slot, 1u);
+                    if (++steps == 254) {
+                        priv_flush(myhist, bhist, n_words, n_bins, lane, 1u);
+                        steps = 0;
+                    }
                 }
             }
         }
@@ -223,14 +231,14 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
         }
     }
     if (HIST == MDH_HIST_LANE_PRIVATE)
-        priv_flush(myhist, bhist, P.n_words, n_bins, lane, 1u);
+        priv_flush(myhist, bhist, n_words, n_bins, lane, 1u);
     __syncthreads();
 
     for (int k = tid; k < n_bins; k += kThreads) {
         unsigned long long s = 0;
         if (HIST == MDH_HIST_WARP_ATOMIC) {
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) s += sH[w * n_bins + k];
+            for (int w = 0; w < kWarps; ++w) s += sH[w * warp_hist_words(n_bins) + 1 + k];
         } else {
             s = bhist[k];
         }
@@ -241,11 +249,11 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
     if (lane == 0 && my_evals) atomicAdd(P.evals, my_evals);
 }
 
-template <int HIST, bool EXCL>
+template <int HIST, bool EXCL, bool FAST>
 int launch_cells(mdh_ctx *c, const CellParams &P, dim3 grid)
 {
-    const size_t smem = cells_smem_bytes<HIST>(P.n_bins, P.n_words);
-    auto kern = rdf_cells_kernel<HIST, EXCL>;
+    const size_t smem = cells_smem_bytes<HIST>(P.n_bins);
+    auto kern = rdf_cells_kernel<HIST, EXCL, FAST>;
     MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     kern<<<grid, kThreads, smem, c->stream>>>(P);
@@ -320,8 +328,9 @@ int rdf_cells_accumulate(mdh_ctx *c, int n_frames)
                              cudaMemcpyHostToDevice, c->stream));
     MDH_CUDA(cudaStreamSynchronize(c->stream));      // grids is a local
 
-    const int64_t pad1 = (R.n1 + kTile - 1) / kTile * kTile;
-    const int64_t pad2 = (R.n2 + kTile - 1) / kTile * kTile;
+    const int tile = kThreads * R.ipt;
+    const int64_t pad1 = (R.n1 + tile - 1) / tile * tile;
+    const int64_t pad2 = (R.n2 + tile - 1) / tile * tile;
     if (int rc = sort_group(c, R.pk1.as<float4>(), pad1, (int)R.n1, n_frames,
                             d_grids.as<CellGrid>(), cstride, R.cell[1], R.cell[2], R.cell[3],
                             R.cell[4])) return rc;
@@ -329,11 +338,6 @@ int rdf_cells_accumulate(mdh_ctx *c, int n_frames)
         if (int rc = sort_group(c, R.pk2.as<float4>(), pad2, (int)R.n2, n_frames,
                                 d_grids.as<CellGrid>(), cstride, R.cell[5], R.cell[6],
                                 R.cell[7], R.cell[8])) return rc;
-    if (int rc = R.cell[9].reserve(sizeof(unsigned long long))) return rc;
-    if (!R.evals_dev_init) {
-        MDH_CUDA(cudaMemsetAsync(R.cell[9].p, 0, sizeof(unsigned long long), c->stream));
-        R.evals_dev_init = true;
-    }
 
     CellParams P;
     P.s1 = R.cell[4].as<float4>();
@@ -345,16 +349,21 @@ int rdf_cells_accumulate(mdh_ctx *c, int n_frames)
     P.boxes = R.boxes.as<FrameBox>();
     P.thr = R.thr.as<double>();
     P.n_bins = R.n_bins;
-    P.n_words = (R.n_bins + 1 + 3) / 4;
-    P.g_scale = (float)(R.n_bins / (R.r_hi - R.r_lo));
-    P.g_off = (float)(-R.r_lo * R.n_bins / (R.r_hi - R.r_lo));
+    P.guess = rdf_bin_guess(R);
     P.counts = R.counts.as<unsigned long long>();
     P.evals = R.cell[9].as<unsigned long long>();
     dim3 grid((unsigned)((R.n1 + kThreads - 1) / kThreads), (unsigned)n_frames);
-    const bool excl = R.excl1 > 0;
-    if (R.hist == MDH_HIST_LANE_PRIVATE)
-        return excl ? launch_cells<MDH_HIST_LANE_PRIVATE, true>(c, P, grid)
-                    : launch_cells<MDH_HIST_LANE_PRIVATE, false>(c, P, grid);
-    return excl ? launch_cells<MDH_HIST_WARP_ATOMIC, true>(c, P, grid)
-                : launch_cells<MDH_HIST_WARP_ATOMIC, false>(c, P, grid);
+    const bool excl = R.excl1 > 0, fast = R.fast_bins;
+    if (R.hist == MDH_HIST_LANE_PRIVATE) {
+        if (excl)
+            return fast ? launch_cells<MDH_HIST_LANE_PRIVATE, true, true>(c, P, grid)
+                        : launch_cells<MDH_HIST_LANE_PRIVATE, true, false>(c, P, grid);
+        return fast ? launch_cells<MDH_HIST_LANE_PRIVATE, false, true>(c, P, grid)
+                    : launch_cells<MDH_HIST_LANE_PRIVATE, false, false>(c, P, grid);
+    }
+    if (excl)
+        return fast ? launch_cells<MDH_HIST_WARP_ATOMIC, true, true>(c, P, grid)
+                    : launch_cells<MDH_HIST_WARP_ATOMIC, true, false>(c, P, grid);
+    return fast ? launch_cells<MDH_HIST_WARP_ATOMIC, false, true>(c, P, grid)
+                : launch_cells<MDH_HIST_WARP_ATOMIC, false, false>(c, P, grid);
 }

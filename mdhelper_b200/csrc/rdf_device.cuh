@@ -12,15 +12,15 @@ namespace rdfdev {
 
 constexpr int kThreads = 256;          // 8 warps
 constexpr int kWarps = kThreads / 32;
-constexpr int kIPT = 2;                // i-particles per thread
-constexpr int kTile = kThreads * kIPT; // 512: i-tile == j-tile (same-group symmetry)
 constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+constexpr float kMagicF = 12582912.0f;         // 1.5 * 2^23
+constexpr size_t kMaxSmem = 227 * 1024;
 
 // ---- pack: float[F][n][3] -> float4[F][npad] (x, y, z, exclusion block id) ------
 
 static __global__ void rdf_pack_kernel(const float *__restrict__ raw, int64_t frame_stride,
-                                float4 *__restrict__ out, int64_t n, int64_t npad,
-                                int64_t excl, int drop_axis)
+                                       float4 *__restrict__ out, int64_t n, int64_t npad,
+                                       int64_t excl, int drop_axis)
 {
     const int frame = blockIdx.y;
     const float *src = raw + (int64_t)frame * frame_stride;
@@ -62,51 +62,149 @@ __device__ __forceinline__ double pair_d2(float xi, float yi, float zi, const fl
     return __dadd_rn(__dadd_rn(sx, sy), sz);
 }
 
-// ---- bin lookup ---------------------------------------------------------------
-// sT2[k] = (T[k], T[k+1]), k in [0, n_bins).  Returns k in [0, n_bins) or n_bins
-// ("not counted": below T[0], at or above T[n_bins], or NaN).
+// ---- bin lookup -----------------------------------------------------------------
+// sT[0..n_bins] are the squared thresholds.  A "slot" is bin + 1: slot 0 = below
+// T[0] (or NaN), slots 1..n_bins = bins 0..n_bins-1, slot n_bins+1 = at or above
+// T[n_bins].  Slots 0 and n_bins+1 are never counted.
 
-static __device__ __noinline__ int bin_search(double d2, const double2 *sT2, int n_bins)
+struct BinGuess {
+    float scale;     // n_bins / (r_hi - r_lo)
+    float offset;    // -r_lo * scale + 0.5 - margin
+};
+
+// exact: binary search (always correct; used when the guess cannot be certified)
+static __device__ __noinline__ int slot_search(double d2, const double *sT, int n_bins)
 {
-    if (!(d2 >= sT2[0].x) || !(d2 < sT2[n_bins - 1].y)) return n_bins;
+    if (!(d2 < sT[n_bins])) return n_bins + 1;       // above range, inf, NaN
+    if (d2 < sT[0]) return 0;
     int lo = 0, hi = n_bins;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (d2 >= sT2[mid].x) lo = mid; else hi = mid;
+        if (d2 >= sT[mid]) lo = mid; else hi = mid;
     }
-    return lo;
+    return lo + 1;
 }
 
-__device__ __forceinline__ int bin_index(double d2, const double2 *sT2, int n_bins,
-                                         float g_scale, float g_off)
+// fast: branch-free.  A float estimate of (sqrt(d2) - r_lo) * scale, biased low by
+// `margin`, gives j = floor(estimate + 1) with  j - 1 <= true bin <= j  (certified
+// per configuration by rdf_selfcheck_kernel); one fp64 compare against T[j]
+// settles it.  No XU conversions: d2 -> float by bit manipulation (truncation),
+// float -> int by the 1.5*2^23 magic add.
+// Returns j in [0, n_bins] with  j - 1 <= true bin <= j  and sets below = (d2 < T[j]):
+// the pair belongs to bin j - 1 if below (not counted when j == 0), else to bin j
+// (not counted when j == n_bins, which is also where inf / NaN end up).
+__device__ __forceinline__ int slot_fast_parts(double d2, const double *sT, int n_bins,
+                                               const BinGuess g, bool &below)
 {
+    unsigned hi = (unsigned)__double2hiint(d2);
+    const unsigned lo = (unsigned)__double2loint(d2);
+    // clamp the exponent into float range: below 2^-127 (and 0) -> ~0; huge, inf
+    // and NaN -> ~2^127 (they end in the "above range" slot)
+    hi = min(max(hi, 0x38000000u), 0x47e00000u);
+    // fp64 -> fp32 bits by truncation: the shifted word carries exponent bit 8 in
+    // the sign position (cleared) and needs its 8-bit exponent re-biased by -896,
+    // i.e. bit 30 flipped
+    const float f =
+        __uint_as_float((__funnelshift_l(lo, hi, 3) & 0x7fffffffu) ^ 0x40000000u);
     float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__double2float_rn(d2)));
-    int k = __float2int_rd(fmaf(r, g_scale, g_off));
-    k = min(max(k, 0), n_bins - 1);
-    const double2 t = sT2[k];
-    if (!(d2 >= t.x && d2 < t.y)) k = bin_search(d2, sT2, n_bins);
-    return k;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f));
+    const float e = __fadd_rn(fmaf(r, g.scale, g.offset), kMagicF);
+    int j = __float_as_int(e) - 0x4B400000;          // rint(estimate + 0.5 - margin)
+    j = min(max(j, 0), n_bins);
+    below = d2 < sT[j];                              // false for NaN
+    return j;
+}
+
+__device__ __forceinline__ int slot_fast(double d2, const double *sT, int n_bins,
+                                         const BinGuess g)
+{
+    bool below;
+    const int j = slot_fast_parts(d2, sT, n_bins, g, below);
+    return j + (below ? 0 : 1);
+}
+
+template <bool FAST>
+__device__ __forceinline__ int slot_of(double d2, const double *sT, int n_bins,
+                                       const BinGuess g)
+{
+    return FAST ? slot_fast(d2, sT, n_bins, g) : slot_search(d2, sT, n_bins);
+}
+
+// Certifies slot_fast for one configuration: at every threshold and its fp64
+// neighbours (where a biased guess is most exposed) the fast slot must equal the
+// exact one.  *bad counts disagreements.
+static __global__ void rdf_selfcheck_kernel(const double *__restrict__ thr, int n_bins,
+                                            BinGuess g, int *bad)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n_bins) return;
+    const double t = thr[k];
+    // neighbours of a non-negative double through its bit pattern
+    auto up = [](double x) { return __longlong_as_double(__double_as_longlong(x) + 1); };
+    auto down = [](double x) {
+        return x > 0.0 ? __longlong_as_double(__double_as_longlong(x) - 1) : -1.0;
+    };
+    const double probes[5] = {
+        t, down(t), up(t),
+        k < n_bins ? 0.5 * (t + thr[k + 1]) : t * 1.5 + 1.0,
+        k < n_bins ? down(thr[k + 1]) : t * 4.0 + 1e30};
+    int wrong = 0;
+    for (int p = 0; p < 5; ++p) {
+        const double d2 = probes[p];
+        if (!(d2 >= 0.0)) continue;
+        if (slot_fast(d2, thr, n_bins, g) != slot_search(d2, thr, n_bins)) ++wrong;
+    }
+    if (k == 0) {
+        if (slot_fast(0.0, thr, n_bins, g) != slot_search(0.0, thr, n_bins)) ++wrong;
+        if (slot_fast(1e-300, thr, n_bins, g) != slot_search(1e-300, thr, n_bins)) ++wrong;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        if (slot_fast(nan, thr, n_bins, g) != n_bins + 1) ++wrong;
+        if (slot_fast(INFINITY, thr, n_bins, g) != n_bins + 1) ++wrong;
+        if (slot_fast(1e300, thr, n_bins, g) != n_bins + 1) ++wrong;
+    }
+    if (wrong) atomicAdd(bad, wrong);
+}
+
+// ---- shared-memory layout and histogram privatisation ------------------------------
+
+// Per-warp u32 histogram for the shared-atomic scheme: one pad word (receives the
+// rare "below range" pairs), n_bins bins, then 32 per-lane trash words so that the
+// many "above range" pairs never contend for one address.  Every pair then issues
+// exactly one unconditional RED.shared (no branch around the atomic).
+__host__ __device__ inline int warp_hist_words(int n_bins) { return n_bins + 33; }
+
+__device__ __forceinline__ void red_shared(unsigned smem_addr, unsigned v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(smem_addr), "r"(v) : "memory");
 }
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+__host__ __device__ inline int priv_words(int n_bins) { return (n_bins + 2 + 3) / 4; }
 
+// bytes of histogram storage behind the threshold table
 template <int HIST>
-__host__ __device__ inline size_t pair_smem_bytes(int n_bins, int n_words)
+__host__ __device__ inline size_t hist_smem_bytes(int n_bins)
 {
-    size_t b = align16(sizeof(double2) * n_bins) + 2 * kTile * sizeof(float4);
-    if (HIST == MDH_HIST_WARP_ATOMIC) b += sizeof(unsigned) * kWarps * n_bins;
-    else b += sizeof(unsigned) * ((size_t)kWarps * n_words * 32 + n_bins);
-    return b;
+    if (HIST == MDH_HIST_WARP_ATOMIC)
+        return sizeof(unsigned) * kWarps * warp_hist_words(n_bins);
+    return sizeof(unsigned) * ((size_t)kWarps * priv_words(n_bins) * 32 + n_bins);
 }
 
-// Lane-private packed histograms: lane l of warp w owns the words
-// priv[(w*n_words + word)*32 + l]; each word holds four 8-bit counters, so the
-// read-modify-write is bank-conflict free and needs no atomics.  A lane makes at
-// most 254 increments between flushes, so no counter can overflow.
+// Lane-private packed histograms: lane l of warp w owns the 32-bit words
+// priv[(w*n_words + word)*32 + l]; each word holds four 8-bit slot counters
+// (slot = 4*word + byte), so the byte read-modify-write is bank-conflict free and
+// needs no atomics.  A lane makes at most 254 increments between flushes, so no
+// counter can overflow.
+__device__ __forceinline__ void priv_add(unsigned char *lane_base, int slot, unsigned inc)
+{
+    unsigned char *p = lane_base + (((unsigned)slot & ~3u) << 5) + ((unsigned)slot & 3u);
+    *p = (unsigned char)(*p + inc);
+}
+
 __device__ __forceinline__ void priv_flush(unsigned *priv_w, unsigned *bhist, int n_words,
                                            int n_bins, int lane, unsigned weight)
 {
+    __syncwarp();
     for (int w = 0; w < n_words; ++w) {
         const unsigned v = priv_w[w * 32 + lane];
         if (__any_sync(0xffffffffu, v != 0)) {
@@ -116,15 +214,14 @@ __device__ __forceinline__ void priv_flush(unsigned *priv_w, unsigned *bhist, in
             if (lane < 4) {
                 unsigned val = (lane & 1) ? b : a;
                 val = (lane & 2) ? (val >> 16) : (val & 0xffffu);
-                const int bin = 4 * w + lane;
-                if (bin < n_bins && val) atomicAdd(&bhist[bin], val * weight);
+                const int bin = 4 * w + lane - 1;          // slot - 1
+                if (bin >= 0 && bin < n_bins && val) atomicAdd(&bhist[bin], val * weight);
             }
         }
     }
     __syncwarp();
 }
 
-
-constexpr size_t kMaxSmem = 227 * 1024;
-
 }  // namespace rdfdev
+
+rdfdev::BinGuess rdf_bin_guess(const RdfState &R);   // rdf.cu

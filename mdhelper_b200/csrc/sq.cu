@@ -53,8 +53,34 @@ struct LatticeParams {
     int offy, offz, nt;            // table layout per particle
 };
 
+// One sub-chunk of particles into the register accumulators; R (even) is the
+// warp-uniform number of z-terms actually needed, so that warps whose column
+// segments are short do not issue the unused FMAs at all.
+template <typename T, int RZ, int R>
+__device__ __forceinline__ void sq_accumulate_subchunk(const typename C2<T>::type *tab, int nt,
+                                                       int ix, int iy, int iz,
+                                                       T (&acc_re)[RZ], T (&acc_im)[RZ])
+{
+    using T2 = typename C2<T>::type;
+#pragma unroll 2
+    for (int p = 0; p < kPS; ++p) {
+        const T2 *row = tab + p * nt;
+        const T2 ex = row[ix], ey = row[iy];
+        const T ar = ex.x * ey.x - ex.y * ey.y;
+        const T ai = ex.x * ey.y + ex.y * ey.x;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const T2 ez = row[iz + r];
+            acc_re[r] += ar * ez.x;
+            acc_re[r] -= ai * ez.y;
+            acc_im[r] += ar * ez.y;
+            acc_im[r] += ai * ez.x;
+        }
+    }
+}
+
 template <typename T, int RZ>
-__global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const LatticeParams P)
+__global__ void __launch_bounds__(kSqThreads, 1) sq_lattice_kernel(const LatticeParams P)
 {
     using T2 = typename C2<T>::type;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -63,8 +89,10 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
     const int tid = threadIdx.x;
     const int frame = blockIdx.z;
     const int4 chunk = P.chunks[blockIdx.y];
-    const SqWorkItem item = P.items[blockIdx.x * kSqThreads + tid];
-    const int wlen = __reduce_max_sync(0xffffffffu, item.len);   // warp-uniform bound
+    const int item_index = blockIdx.x * blockDim.x + tid;
+    const SqWorkItem item = P.items[item_index];
+    // warp-uniform bound, rounded up to an even number of terms
+    const int wlen = (__reduce_max_sync(0xffffffffu, item.len) + 1) & ~1;
     const float *pos = P.raw + (int64_t)frame * P.stride;
 
     T acc_re[RZ], acc_im[RZ];
@@ -101,30 +129,23 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
         }
         __syncthreads();
         // ---- accumulate: particles beyond np have all-zero tables ----
-        if (wlen > 0) {
-#pragma unroll 2
-            for (int p = 0; p < kPS; ++p) {
-                const T2 *row = tab + p * nt;
-                const T2 ex = row[ix], ey = row[iy];
-                const T ar = ex.x * ey.x - ex.y * ey.y;
-                const T ai = ex.x * ey.y + ex.y * ey.x;
-#pragma unroll
-                for (int r = 0; r < RZ; ++r) {
-                    if (r < wlen) {
-                        const T2 ez = row[iz + r];
-                        acc_re[r] += ar * ez.x;
-                        acc_re[r] -= ai * ez.y;
-                        acc_im[r] += ar * ez.y;
-                        acc_im[r] += ai * ez.x;
-                    }
-                }
-            }
+        switch (wlen) {
+#define SQ_CASE(R)                                                                       \
+    case R:                                                                              \
+        if (R <= RZ)                                                                     \
+            sq_accumulate_subchunk<T, RZ, (R <= RZ ? R : RZ)>(tab, nt, ix, iy, iz,       \
+                                                              acc_re, acc_im);          \
+        break;
+            SQ_CASE(2) SQ_CASE(4) SQ_CASE(6) SQ_CASE(8)
+            SQ_CASE(10) SQ_CASE(12) SQ_CASE(14) SQ_CASE(16)
+#undef SQ_CASE
+            default: break;
         }
         __syncthreads();
     }
 
     double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
-    const int *qi = P.qidx + (int64_t)(blockIdx.x * kSqThreads + tid) * RZ;
+    const int *qi = P.qidx + (int64_t)item_index * RZ;
 #pragma unroll
     for (int r = 0; r < RZ; ++r) {
         if (r < item.len) {
@@ -207,14 +228,14 @@ __global__ void sq_finalize_kernel(const double2 *__restrict__ rho, int n_frames
 }
 
 template <typename T, int RZ>
-int launch_lattice(mdh_ctx *c, const LatticeParams &P, dim3 grid)
+int launch_lattice(mdh_ctx *c, const LatticeParams &P, dim3 grid, int block)
 {
     using T2 = typename C2<T>::type;
     const size_t smem = sizeof(T2) * kPS * P.nt;
     auto kern = sq_lattice_kernel<T, RZ>;
     MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    kern<<<grid, kSqThreads, smem, c->stream>>>(P);
+    kern<<<grid, block, smem, c->stream>>>(P);
     MDH_CUDA(cudaGetLastError());
     c->launches++;
     return MDH_OK;
@@ -320,7 +341,14 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                     q2.insert(q2.end(), qidx.begin() + (size_t)o * rz,
                               qidx.begin() + (size_t)(o + 1) * rz);
                 }
-                while (it2.size() % kSqThreads) {
+                // block size: whole warps, at most kSqThreads, at least the 96
+                // threads the table build needs; items padded to whole blocks
+                const int n_warps = (int)((it2.size() + 31) / 32);
+                const int n_blocks = (n_warps * 32 + kSqThreads - 1) / kSqThreads;
+                int block = ((n_warps + n_blocks - 1) / n_blocks) * 32;
+                block = std::max(block, 96);
+                S.block = block;
+                while (it2.size() % block) {
                     it2.push_back(SqWorkItem{0, 0, 0, 0});
                     q2.insert(q2.end(), rz, -1);
                 }
@@ -365,7 +393,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
 static int sq_build_chunks(mdh_ctx *c, int n_frames)
 {
     SqState &S = c->sq;
-    const int item_blocks = S.lattice ? S.n_items / kSqThreads : (S.n_q + 127) / 128;
+    const int item_blocks = S.lattice ? S.n_items / S.block : (S.n_q + 127) / 128;
     // enough blocks for ~6 waves, chunks a multiple of the sub-chunk length
     int64_t want = ((int64_t)c->sm_count * 2 * 6 + (int64_t)item_blocks * n_frames - 1) /
                    ((int64_t)item_blocks * n_frames);
@@ -439,14 +467,14 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
         P.offy = S.nmax[0] + 1;
         P.offz = P.offy + S.nmax[1] + 1;
         P.nt = P.offz + (S.nmax[2] + S.rz) / S.rz * S.rz;
-        dim3 grid(S.n_items / kSqThreads, S.n_chunks, n_frames);
+        dim3 grid(S.n_items / S.block, S.n_chunks, n_frames);
         int rc;
         if (S.mode == MDH_SQ_LATTICE_FP32)
-            rc = S.rz == 8 ? launch_lattice<float, 8>(c, P, grid)
-                           : launch_lattice<float, 16>(c, P, grid);
+            rc = S.rz == 8 ? launch_lattice<float, 8>(c, P, grid, S.block)
+                           : launch_lattice<float, 16>(c, P, grid, S.block);
         else
-            rc = S.rz == 8 ? launch_lattice<double, 8>(c, P, grid)
-                           : launch_lattice<double, 16>(c, P, grid);
+            rc = S.rz == 8 ? launch_lattice<double, 8>(c, P, grid, S.block)
+                           : launch_lattice<double, 16>(c, P, grid, S.block);
         if (rc) return rc;
     } else {
         GeneralParams P;
