@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=100)
-    ap.add_argument("--sq-frames-per-step", type=int, default=32)
+    ap.add_argument("--sq-frames-per-step", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--hist", default="auto")

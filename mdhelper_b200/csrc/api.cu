@@ -108,7 +108,7 @@ int mdh_ctx_destroy(mdh_ctx *c)
     if (R.ev_boxes) cudaEventDestroy(R.ev_boxes);
     SqState &S = c->sq;
     S.qv.release(); S.items.release(); S.qidx.release(); S.d_pairs.release();
-    S.chunks.release(); S.raw.release(); S.rho.release(); S.ssf.release();
+    S.chunks.release(); S.raw.release(); S.tab.release(); S.rho.release(); S.ssf.release();
     for (cudaEvent_t e : {c->ev_rdf0, c->ev_rdf1, c->ev_sq0, c->ev_sq1})
         if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);

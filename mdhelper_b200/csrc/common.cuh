@@ -69,9 +69,14 @@ struct RdfState {
     bool fast_bins = false;  // branch-free bin guess certified for this configuration
 };
 
-struct SqWorkItem {        // one thread's column segment of the lattice kernels
-    int nx, ny, nz0, len;
+struct SqWorkItem {        // one thread's tile of the lattice kernels: two (nx, ny)
+    int nx[2], ny[2];      // columns x one segment of kSqTN consecutive nz
+    int nz0;
+    int len[2];            // wavevectors wanted from each column (0..kSqTN)
+    int pad;
 };
+constexpr int kSqTM = 2;   // columns per thread
+constexpr int kSqTN = 8;   // nz values per thread
 
 struct SqState {
     bool configured = false;
@@ -80,16 +85,17 @@ struct SqState {
     bool lattice = false;
     int nmax[3] = {0, 0, 0};
     double b[3] = {0, 0, 0};
-    int rz = 0, n_items = 0, block = 256;
+    int n_items = 0, block = 256;
     std::vector<int64_t> group_offsets;
     std::vector<int32_t> pairs;
     DevBuf qv;             // double[n_q][3]
     DevBuf items;          // SqWorkItem[n_items]
-    DevBuf qidx;           // int[n_items][rz]
+    DevBuf qidx;           // int[n_items][kSqTM][kSqTN]
     DevBuf d_pairs;        // int[n_pairs][2]
     DevBuf chunks;         // int4[n_chunks]: {start, end, rho_row, 0}
     int n_chunks = 0, chunk_len = 0;
     DevBuf raw;            // float[F][n][3]
+    DevBuf tab;            // phase-factor tables of one group of frames
     DevBuf rho;            // double[F][n_rho][n_q][2]
     DevBuf ssf;            // double[n_pairs][n_q]
     int rho_frames = 0;    // frames held in rho from the last batch

@@ -14,16 +14,17 @@
 //   sq_lattice_kernel<T, RZ>  wavevectors on the reciprocal lattice, q = n * b
 //       (the reference's default grid, structure.py:1376-1416).  exp(i q.r)
 //       factorises into per-axis phase factors E_a(n) = exp(i n b_a r_a): each
-//       block builds E_a(0..nmax_a) for a sub-chunk of particles in shared memory
-//       (one fp64 sincos per particle and axis, then the recurrence
-//       E(n+1) = E(n) E(1)), and each thread owns one (nx, ny) column segment of
-//       up to RZ wavevectors with register accumulators:
+//       block builds E_a(0..nmax_a) for a sub-chunk of 32 particles in shared
+//       memory (one fp64 sincos per particle and axis, then the recurrence
+//       E(n+1) = E(n) E(1)), and each thread owns two (nx, ny) columns x 8
+//       consecutive nz with register accumulators:
 //           A = E_x(nx) E_y(ny);   acc[r] += A * E_z(nz0 + r)     (4 FMA per term)
 //       T = double: fp64 throughout (default; ~1e-13 relative to the reference).
 //       T = float : same scheme on the FP32 pipe (approximate mode).
 //   sq_general_kernel        arbitrary wavevectors: fp64 dot product + fp64 sincos.
 //   sq_finalize_kernel       ssf += per-frame |rho|^2 / cross terms.
 
+#include <cuda_pipeline.h>
 #include <math.h>
 
 #include <algorithm>
@@ -34,7 +35,10 @@
 namespace {
 
 constexpr int kSqThreads = 256;
-constexpr int kPS = 32;            // particles per shared-memory sub-chunk
+#ifndef MDH_SQ_KPS
+#define MDH_SQ_KPS 32
+#endif
+constexpr int kPS = MDH_SQ_KPS;    // particles per shared-memory sub-chunk
 
 template <typename T> struct C2;
 template <> struct C2<double> { using type = double2; };
@@ -45,7 +49,7 @@ struct LatticeParams {
     int64_t stride;
     const int4 *chunks;            // {start, end, rho_row, 0}
     const SqWorkItem *items;
-    const int *qidx;               // [n_items][RZ]
+    const int *qidx;               // [n_items][kSqTM][kSqTN]
     double *rho;                   // [F][n_rho][n_q][2]
     int n_rho, n_q;
     double b[3];
@@ -53,61 +57,79 @@ struct LatticeParams {
     int offy, offz, nt;            // table layout per particle
 };
 
-// One sub-chunk of particles into the register accumulators; R (even) is the
-// warp-uniform number of z-terms actually needed, so that warps whose column
-// segments are short do not issue the unused FMAs at all.
-template <typename T, int RZ, int R>
+// One sub-chunk of particles into the register accumulators.  The per-thread
+// tile is kSqTM columns x R z-terms (R even, warp-uniform), i.e. per particle
+// 2*kSqTM + R shared-memory loads feed 4*kSqTM*(R + 1) FP64 FMAs -- the kernel
+// is bounded by the FP64 pipe and the shared-memory pipe together, and the 2 x 8
+// tile is what balances them.
+template <typename T, int R>
 __device__ __forceinline__ void sq_accumulate_subchunk(const typename C2<T>::type *tab, int nt,
-                                                       int ix, int iy, int iz,
-                                                       T (&acc_re)[RZ], T (&acc_im)[RZ])
+                                                       const int (&ix)[kSqTM],
+                                                       const int (&iy)[kSqTM], int iz,
+                                                       T (&acc_re)[kSqTM][kSqTN],
+                                                       T (&acc_im)[kSqTM][kSqTN])
 {
     using T2 = typename C2<T>::type;
-#pragma unroll 2
+#pragma unroll 1
     for (int p = 0; p < kPS; ++p) {
         const T2 *row = tab + p * nt;
-        const T2 ex = row[ix], ey = row[iy];
-        const T ar = ex.x * ey.x - ex.y * ey.y;
-        const T ai = ex.x * ey.y + ex.y * ey.x;
+        T ar[kSqTM], ai[kSqTM];
+#pragma unroll
+        for (int m = 0; m < kSqTM; ++m) {
+            const T2 ex = row[ix[m]], ey = row[iy[m]];
+            ar[m] = ex.x * ey.x - ex.y * ey.y;
+            ai[m] = ex.x * ey.y + ex.y * ey.x;
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const T2 ez = row[iz + r];
-            acc_re[r] += ar * ez.x;
-            acc_re[r] -= ai * ez.y;
-            acc_im[r] += ar * ez.y;
-            acc_im[r] += ai * ez.x;
+#pragma unroll
+            for (int m = 0; m < kSqTM; ++m) {
+                acc_re[m][r] += ar[m] * ez.x;
+                acc_re[m][r] -= ai[m] * ez.y;
+                acc_im[m][r] += ar[m] * ez.y;
+                acc_im[m][r] += ai[m] * ez.x;
+            }
         }
     }
 }
 
-template <typename T, int RZ>
-__global__ void __launch_bounds__(kSqThreads, 1) sq_lattice_kernel(const LatticeParams P)
+template <typename T>
+__global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const LatticeParams P)
 {
     using T2 = typename C2<T>::type;
     extern __shared__ __align__(16) unsigned char smem[];
-    T2 *tab = reinterpret_cast<T2 *>(smem);          // [kPS][nt]
+    T2 *sTab = reinterpret_cast<T2 *>(smem);         // [kPS][nt]
 
     const int tid = threadIdx.x;
     const int frame = blockIdx.z;
     const int4 chunk = P.chunks[blockIdx.y];
     const int item_index = blockIdx.x * blockDim.x + tid;
     const SqWorkItem item = P.items[item_index];
-    // warp-uniform bound, rounded up to an even number of terms
-    const int wlen = (__reduce_max_sync(0xffffffffu, item.len) + 1) & ~1;
-    const float *pos = P.raw + (int64_t)frame * P.stride;
+    // warp-uniform number of z-terms, rounded up to an even count
+    const int wlen =
+        (__reduce_max_sync(0xffffffffu, max(item.len[0], item.len[1])) + 1) & ~1;
 
-    T acc_re[RZ], acc_im[RZ];
+    T acc_re[kSqTM][kSqTN], acc_im[kSqTM][kSqTN];
 #pragma unroll
-    for (int r = 0; r < RZ; ++r) acc_re[r] = acc_im[r] = T(0);
+    for (int m = 0; m < kSqTM; ++m)
+#pragma unroll
+        for (int r = 0; r < kSqTN; ++r) acc_re[m][r] = acc_im[m][r] = T(0);
 
     const int nt = P.nt;
-    const int ix = item.nx, iy = P.offy + item.ny, iz = P.offz + item.nz0;
+    int ix[kSqTM], iy[kSqTM];
+#pragma unroll
+    for (int m = 0; m < kSqTM; ++m) { ix[m] = item.nx[m]; iy[m] = P.offy + item.ny[m]; }
+    const int iz = P.offz + item.nz0;
 
+    const float *pos = P.raw + (int64_t)frame * P.stride;
     for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS) {
         const int np = min(kPS, chunk.y - p0);
-        // ---- phase-factor tables for particles [p0, p0 + np) ----
+        // ---- phase-factor tables for particles [p0, p0 + np): thread <-> (particle,
+        // axis); one fp64 sincos, then E(n+1) = E(n) E(1) ----
         if (tid < kPS * 3) {
             const int p = tid / 3, a = tid - 3 * p;
-            T2 *row = tab + p * nt + (a == 0 ? 0 : (a == 1 ? P.offy : P.offz));
+            T2 *row = sTab + p * nt + (a == 0 ? 0 : (a == 1 ? P.offy : P.offz));
             const int nm = P.nmax[a];
             const int npad = (a == 2) ? (nt - P.offz) : nm + 1;
             if (p < np) {
@@ -130,32 +152,29 @@ __global__ void __launch_bounds__(kSqThreads, 1) sq_lattice_kernel(const Lattice
         __syncthreads();
         // ---- accumulate: particles beyond np have all-zero tables ----
         switch (wlen) {
-#define SQ_CASE(R)                                                                       \
-    case R:                                                                              \
-        if (R <= RZ)                                                                     \
-            sq_accumulate_subchunk<T, RZ, (R <= RZ ? R : RZ)>(tab, nt, ix, iy, iz,       \
-                                                              acc_re, acc_im);          \
-        break;
-            SQ_CASE(2) SQ_CASE(4) SQ_CASE(6) SQ_CASE(8)
-            SQ_CASE(10) SQ_CASE(12) SQ_CASE(14) SQ_CASE(16)
-#undef SQ_CASE
+            case 2: sq_accumulate_subchunk<T, 2>(sTab, nt, ix, iy, iz, acc_re, acc_im); break;
+            case 4: sq_accumulate_subchunk<T, 4>(sTab, nt, ix, iy, iz, acc_re, acc_im); break;
+            case 6: sq_accumulate_subchunk<T, 6>(sTab, nt, ix, iy, iz, acc_re, acc_im); break;
+            case 8: sq_accumulate_subchunk<T, 8>(sTab, nt, ix, iy, iz, acc_re, acc_im); break;
             default: break;
         }
         __syncthreads();
     }
 
     double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
-    const int *qi = P.qidx + (int64_t)item_index * RZ;
+    const int *qi = P.qidx + (int64_t)item_index * (kSqTM * kSqTN);
 #pragma unroll
-    for (int r = 0; r < RZ; ++r) {
-        if (r < item.len) {
-            const int q = qi[r];
-            if (q >= 0) {
-                atomicAdd(out + 2 * q, (double)acc_re[r]);
-                atomicAdd(out + 2 * q + 1, (double)acc_im[r]);
+    for (int m = 0; m < kSqTM; ++m)
+#pragma unroll
+        for (int r = 0; r < kSqTN; ++r) {
+            if (r < item.len[m]) {
+                const int q = qi[m * kSqTN + r];
+                if (q >= 0) {
+                    atomicAdd(out + 2 * q, (double)acc_re[m][r]);
+                    atomicAdd(out + 2 * q + 1, (double)acc_im[m][r]);
+                }
             }
         }
-    }
 }
 
 struct GeneralParams {
@@ -227,12 +246,12 @@ __global__ void sq_finalize_kernel(const double2 *__restrict__ rho, int n_frames
     ssf[(int64_t)p * n_q + q] += acc;
 }
 
-template <typename T, int RZ>
+template <typename T>
 int launch_lattice(mdh_ctx *c, const LatticeParams &P, dim3 grid, int block)
 {
     using T2 = typename C2<T>::type;
     const size_t smem = sizeof(T2) * kPS * P.nt;
-    auto kern = sq_lattice_kernel<T, RZ>;
+    auto kern = sq_lattice_kernel<T>;
     MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     kern<<<grid, block, smem, c->stream>>>(P);
@@ -288,10 +307,11 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
     S.rho_frames = 0;
 
     // ---- lattice work items ----
+    // Columns (nx, ny) sorted by their number of wavevectors; thread tiles take two
+    // neighbouring columns (similar lengths) and one segment of kSqTN nz values.
     bool lattice = lat_n && lat_b && mode != MDH_SQ_GENERAL_FP64;
     std::vector<SqWorkItem> items;
     std::vector<int> qidx;
-    int rz = 16;
     if (lattice) {
         int nm[3] = {0, 0, 0};
         for (int i = 0; i < n_q && lattice; ++i)
@@ -300,62 +320,67 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                 if (n < 0 || n > 1023) lattice = false;
                 else nm[k] = std::max(nm[k], n);
             }
+        struct Column { int nx, ny; std::vector<int> q; };   // q[nz] = wavevector index
+        std::vector<Column> cols;
         if (lattice) {
-            rz = nm[2] + 1 <= 8 ? 8 : 16;
-            std::map<std::pair<int, int>, std::vector<std::pair<int, int>>> cols;
-            for (int i = 0; i < n_q; ++i)
-                cols[{lat_n[3 * i], lat_n[3 * i + 1]}].push_back({lat_n[3 * i + 2], i});
-            for (auto &kv : cols) {
-                auto &v = kv.second;
-                std::sort(v.begin(), v.end());
-                for (size_t t = 1; t < v.size() && lattice; ++t)
-                    if (v[t].first == v[t - 1].first) lattice = false;   // duplicate wavevector
-                if (!lattice) break;
-                // split the column into segments [nz0, nz0 + rz), nz0 a multiple of rz
-                size_t t = 0;
-                while (t < v.size()) {
-                    const int nz0 = v[t].first / rz * rz;
-                    SqWorkItem it{kv.first.first, kv.first.second, nz0, 0};
-                    std::vector<int> qi(rz, -1);
-                    while (t < v.size() && v[t].first < nz0 + rz) {
-                        qi[v[t].first - nz0] = v[t].second;
-                        it.len = v[t].first - nz0 + 1;
-                        ++t;
+            std::map<std::pair<int, int>, int> where;
+            for (int i = 0; i < n_q && lattice; ++i) {
+                const std::pair<int, int> key{lat_n[3 * i], lat_n[3 * i + 1]};
+                auto it = where.find(key);
+                if (it == where.end()) {
+                    it = where.emplace(key, (int)cols.size()).first;
+                    cols.push_back(Column{key.first, key.second,
+                                          std::vector<int>(nm[2] + 1, -1)});
+                }
+                int &slot = cols[it->second].q[lat_n[3 * i + 2]];
+                if (slot >= 0) lattice = false;               // duplicate wavevector
+                slot = i;
+            }
+        }
+        if (lattice) {
+            auto top = [](const Column &c) {                 // 1 + largest nz present
+                int t = 0;
+                for (int z = 0; z < (int)c.q.size(); ++z) if (c.q[z] >= 0) t = z + 1;
+                return t;
+            };
+            std::stable_sort(cols.begin(), cols.end(),
+                             [&](const Column &a, const Column &b) { return top(a) > top(b); });
+            const int n_seg = (nm[2] + kSqTN) / kSqTN;
+            for (int s = 0; s < n_seg; ++s)
+                for (size_t c0 = 0; c0 < cols.size(); c0 += kSqTM) {
+                    SqWorkItem it{};
+                    it.nz0 = s * kSqTN;
+                    std::vector<int> qi(kSqTM * kSqTN, -1);
+                    bool any = false;
+                    for (int m = 0; m < kSqTM; ++m) {
+                        if (c0 + m >= cols.size()) continue;
+                        const Column &c = cols[c0 + m];
+                        it.nx[m] = c.nx; it.ny[m] = c.ny;
+                        for (int r = 0; r < kSqTN; ++r) {
+                            const int z = it.nz0 + r;
+                            if (z < (int)c.q.size() && c.q[z] >= 0) {
+                                qi[m * kSqTN + r] = c.q[z];
+                                it.len[m] = r + 1;
+                                any = true;
+                            }
+                        }
                     }
+                    if (!any) continue;
                     items.push_back(it);
                     qidx.insert(qidx.end(), qi.begin(), qi.end());
                 }
+            // block size: whole warps, at most kSqThreads, at least the 96 threads
+            // the table build needs; items padded to whole blocks
+            const int n_warps = (int)((items.size() + 31) / 32);
+            const int n_blocks = (n_warps * 32 + kSqThreads - 1) / kSqThreads;
+            int block = ((n_warps + n_blocks - 1) / n_blocks) * 32;
+            block = std::max(block, 96);
+            S.block = block;
+            while (items.size() % block) {
+                items.push_back(SqWorkItem{});
+                qidx.insert(qidx.end(), kSqTM * kSqTN, -1);
             }
-            if (lattice) {
-                // sort so that warps share nz0 and have similar lengths
-                std::vector<int> order(items.size());
-                for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-                std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-                    if (items[a].nz0 != items[b].nz0) return items[a].nz0 < items[b].nz0;
-                    return items[a].len > items[b].len;
-                });
-                std::vector<SqWorkItem> it2;
-                std::vector<int> q2;
-                for (int o : order) {
-                    it2.push_back(items[o]);
-                    q2.insert(q2.end(), qidx.begin() + (size_t)o * rz,
-                              qidx.begin() + (size_t)(o + 1) * rz);
-                }
-                // block size: whole warps, at most kSqThreads, at least the 96
-                // threads the table build needs; items padded to whole blocks
-                const int n_warps = (int)((it2.size() + 31) / 32);
-                const int n_blocks = (n_warps * 32 + kSqThreads - 1) / kSqThreads;
-                int block = ((n_warps + n_blocks - 1) / n_blocks) * 32;
-                block = std::max(block, 96);
-                S.block = block;
-                while (it2.size() % block) {
-                    it2.push_back(SqWorkItem{0, 0, 0, 0});
-                    q2.insert(q2.end(), rz, -1);
-                }
-                items.swap(it2);
-                qidx.swap(q2);
-                for (int k = 0; k < 3; ++k) { S.nmax[k] = nm[k]; S.b[k] = lat_b[k]; }
-            }
+            for (int k = 0; k < 3; ++k) { S.nmax[k] = nm[k]; S.b[k] = lat_b[k]; }
         }
     }
     MDH_REQUIRE(lattice || !want_lattice, MDH_EINVAL,
@@ -364,7 +389,6 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
     S.lattice = lattice;
     S.mode = lattice ? (mode == MDH_SQ_LATTICE_FP32 ? MDH_SQ_LATTICE_FP32 : MDH_SQ_LATTICE_FP64)
                      : MDH_SQ_GENERAL_FP64;
-    S.rz = rz;
     S.n_items = (int)items.size();
 
     if (int rc = S.qv.reserve(sizeof(double) * 3 * n_q)) return rc;
@@ -444,6 +468,12 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
         dsrc = S.raw.as<float>();
         dstride = 3 * S.n_total;
     }
+    LatticeParams LP;
+    if (S.lattice) {
+        LP.offy = S.nmax[0] + 1;
+        LP.offz = LP.offy + S.nmax[1] + 1;
+        LP.nt = LP.offz + (S.nmax[2] + kSqTN) / kSqTN * kSqTN;
+    }
     if (int rc = sq_build_chunks(c, n_frames)) return rc;
     const size_t rho_bytes = sizeof(double) * 2 * (size_t)n_frames * S.n_rho * S.n_q;
     if (int rc = S.rho.reserve(rho_bytes)) return rc;
@@ -456,7 +486,7 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
     MDH_CUDA(cudaMemsetAsync(S.rho.p, 0, rho_bytes, c->stream));
 
     if (S.lattice) {
-        LatticeParams P;
+        LatticeParams P = LP;
         P.raw = dsrc; P.stride = dstride;
         P.chunks = S.chunks.as<int4>();
         P.items = S.items.as<SqWorkItem>();
@@ -464,17 +494,10 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
         P.rho = S.rho.as<double>();
         P.n_rho = S.n_rho; P.n_q = S.n_q;
         for (int k = 0; k < 3; ++k) { P.b[k] = S.b[k]; P.nmax[k] = S.nmax[k]; }
-        P.offy = S.nmax[0] + 1;
-        P.offz = P.offy + S.nmax[1] + 1;
-        P.nt = P.offz + (S.nmax[2] + S.rz) / S.rz * S.rz;
         dim3 grid(S.n_items / S.block, S.n_chunks, n_frames);
         int rc;
-        if (S.mode == MDH_SQ_LATTICE_FP32)
-            rc = S.rz == 8 ? launch_lattice<float, 8>(c, P, grid, S.block)
-                           : launch_lattice<float, 16>(c, P, grid, S.block);
-        else
-            rc = S.rz == 8 ? launch_lattice<double, 8>(c, P, grid, S.block)
-                           : launch_lattice<double, 16>(c, P, grid, S.block);
+        if (S.mode == MDH_SQ_LATTICE_FP32) rc = launch_lattice<float>(c, P, grid, S.block);
+        else rc = launch_lattice<double>(c, P, grid, S.block);
         if (rc) return rc;
     } else {
         GeneralParams P;
