@@ -144,9 +144,12 @@ def measured_peaks():
     p = ROOT / "profiles" / "microbench_r01.json"
     if p.exists():
         try:
+            # GPU-wide instruction rates timed with CUDA events at the 1965 MHz the
+            # run held (profiles/microbench_r01_clocks.csv) -> per clock and SM
             mb = json.loads(p.read_text())
-            out["fp64_per_clk_sm"] = float(mb["dfma"]["ops_per_clk_per_sm"])
-            out["sfu_per_clk_sm"] = float(mb["mufu_sin"]["ops_per_clk_per_sm"])
+            per = 1e9 / (mb["sms"] * mb["clock_khz"] * 1e3)
+            out["fp64_per_clk_sm"] = float(mb["dfma"]["gops_per_s"]) * per
+            out["sfu_per_clk_sm"] = float(mb["mufu_sin"]["gops_per_s"]) * per
             out["pipe_source"] = "measured: profiles/microbench_r01.json (tools/microbench.cu)"
         except (ValueError, KeyError):
             pass
@@ -247,6 +250,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def prewarm(step, ctx, seconds=0.75):
+    """Untimed: run steps until `seconds` of wall time have passed, so the timed
+    region starts with the SM clocks already raised."""
+    t0 = time.perf_counter()
+    s = 0
+    while time.perf_counter() - t0 < seconds:
+        step(s)
+        ctx.sync()
+        s += 1
+
+
 def workload_config(frames_per_step):
     return {"workload": "cfg2: two-group cation-anion partial RDF, 20,000-ion electrolyte "
                         "(10,000 x 10,000 ordered pairs per frame), n_bins=201, "
@@ -314,15 +328,18 @@ def run_ours(args):
                            boxes[f0:f0 + nf], nf, device=True)
         return nf
 
+    # the clock sampler starts first: nvidia-smi's own start-up (NVML init) must be
+    # over before the timed region; only samples inside [wall0, wall1] are used
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    prewarm(step, ctx, 1.5)                   # bring the clocks up (untimed, on top of W)
     for s in range(W):
         step(s)
     ctx.sync()
     ctx.rdf_reset()
+    ctx.kernel_time(reset=True)
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -345,12 +362,10 @@ def run_ours(args):
     launches = ctx.launch_count() - launches0
     binned_total = int(counts.sum().item())
     evals_local = ctx.rdf_pair_evaluations()
-    # per-launch duration of the pair kernel, measured with CUDA events (untimed pass)
-    kern = []
-    for s in range(W + K, W + K + 5):
-        step(s)
-        kern.append(ctx.last_kernel_ms()[0])
-    kern_ms = float(np.mean(kern))
+    # per-launch duration of the pair kernel: CUDA events recorded around every
+    # launch of the timed region, on the launching stream (mdh_kernel_time)
+    kern_total_ms, kern_calls, _, _ = ctx.kernel_time(reset=True)
+    kern_ms = kern_total_ms / max(kern_calls, 1)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     value = binned_total / (ms * 1e-3)
 
@@ -464,10 +479,12 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
         ctx.sq_accumulate(base + 4 * 3 * N * f0, 3 * N, nf, device=True)
         return nf
 
+    prewarm(step, ctx, 0.4)
     for s in range(W):
         step(s)
     ctx.sync()
     ctx.sq_reset()
+    ctx.kernel_time(reset=True)
     l0 = ctx.launch_count()
     if world > 1:
         dist.barrier()
@@ -487,11 +504,8 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = ctx.launch_count() - l0
-    kern = []
-    for s in range(W + K, W + K + 5):
-        nf = step(s)
-        kern.append(ctx.last_kernel_ms()[1] / nf * fps)
-    kern_ms = float(np.mean(kern))
+    _, _, kern_total_ms, kern_calls = ctx.kernel_time(reset=True)
+    kern_ms = kern_total_ms / max(kern_calls, 1) * (fps * K / max(frames, 1))
 
     for s in range(W):
         f0 = (s * fps) % ring

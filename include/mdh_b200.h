@@ -99,6 +99,10 @@ int mdh_sync(mdh_ctx *ctx);
  * kernels / S(q) kernels by the LAST accumulate call, and launches issued by the
  * context since creation.  Both calls synchronise the stream. */
 int mdh_last_kernel_ms(mdh_ctx *ctx, float *rdf_ms, float *sq_ms);
+/* Sum of those per-call device times, and the number of accumulate calls they cover,
+ * since the previous call with reset != 0 (synchronises the stream). */
+int mdh_kernel_time(mdh_ctx *ctx, int reset, double *rdf_ms, int64_t *rdf_calls,
+                    double *sq_ms, int64_t *sq_calls);
 int mdh_launch_count(mdh_ctx *ctx, int64_t *launches);
 
 /* ---- seam #1: radial histogram ------------------------------------------------- */

@@ -38,6 +38,8 @@ SIGNATURES = {
     "mdh_sync": (_i32, [_p]),
     "mdh_last_kernel_ms": (_i32, [_p, ctypes.POINTER(ctypes.c_float),
                                   ctypes.POINTER(ctypes.c_float)]),
+    "mdh_kernel_time": (_i32, [_p, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_i64),
+                               ctypes.POINTER(_f64), ctypes.POINTER(_i64)]),
     "mdh_launch_count": (_i32, [_p, ctypes.POINTER(_i64)]),
     "mdh_rdf_configure": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _f64, _f64, _i64,
                                  _i64, _i32, _i32, _i32]),
@@ -137,6 +139,14 @@ class Context:
         a, b = ctypes.c_float(), ctypes.c_float()
         check(self._lib.mdh_last_kernel_ms(self._h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
+
+    def kernel_time(self, reset: bool = False):
+        """``(rdf_ms, rdf_calls, sq_ms, sq_calls)`` since the last reset."""
+        a, b, na, nb = _f64(), _f64(), _i64(), _i64()
+        check(self._lib.mdh_kernel_time(self._h, int(reset), ctypes.byref(a),
+                                        ctypes.byref(na), ctypes.byref(b),
+                                        ctypes.byref(nb)))
+        return a.value, na.value, b.value, nb.value
 
     def launch_count(self) -> int:
         n = _i64()

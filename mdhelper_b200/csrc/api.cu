@@ -50,6 +50,60 @@ void DevBuf::release()
     cap = 0;
 }
 
+int KernelTimer::begin(cudaStream_t s)
+{
+    if (used == 512) {                       // ring full: fold what has been recorded
+        double ms; int64_t n;
+        if (int rc = collect(s, false, &ms, &n)) return rc;
+        folded_ms = ms; folded_n = n; used = 0;
+    }
+    while (ev.size() < 2 * (used + 1)) {
+        cudaEvent_t e;
+        MDH_CUDA(cudaEventCreate(&e));
+        ev.push_back(e);
+    }
+    MDH_CUDA(cudaEventRecord(ev[2 * used], s));
+    return MDH_OK;
+}
+
+int KernelTimer::end(cudaStream_t s)
+{
+    MDH_CUDA(cudaEventRecord(ev[2 * used + 1], s));
+    ++used;
+    return MDH_OK;
+}
+
+int KernelTimer::last(cudaStream_t s, float *ms)
+{
+    *ms = 0.f;
+    if (used == 0) return MDH_OK;
+    MDH_CUDA(cudaStreamSynchronize(s));
+    MDH_CUDA(cudaEventElapsedTime(ms, ev[2 * used - 2], ev[2 * used - 1]));
+    return MDH_OK;
+}
+
+int KernelTimer::collect(cudaStream_t s, bool reset, double *ms, int64_t *n)
+{
+    MDH_CUDA(cudaStreamSynchronize(s));
+    double tot = folded_ms;
+    for (size_t i = 0; i < used; ++i) {
+        float t;
+        MDH_CUDA(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+        tot += t;
+    }
+    *ms = tot;
+    *n = folded_n + (int64_t)used;
+    if (reset) { used = 0; folded_ms = 0; folded_n = 0; }
+    return MDH_OK;
+}
+
+void KernelTimer::destroy()
+{
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+    used = 0;
+}
+
 #define CTX_GUARD(ctx)                                                         \
     do {                                                                       \
         MDH_REQUIRE((ctx) != nullptr, MDH_EINVAL, "context is NULL");          \
@@ -109,8 +163,8 @@ int mdh_ctx_destroy(mdh_ctx *c)
     SqState &S = c->sq;
     S.qv.release(); S.items.release(); S.qidx.release(); S.d_pairs.release();
     S.chunks.release(); S.raw.release(); S.tab.release(); S.rho.release(); S.ssf.release();
-    for (cudaEvent_t e : {c->ev_rdf0, c->ev_rdf1, c->ev_sq0, c->ev_sq1})
-        if (e) cudaEventDestroy(e);
+    c->t_rdf.destroy();
+    c->t_sq.destroy();
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return MDH_OK;
@@ -126,16 +180,18 @@ int mdh_sync(mdh_ctx *c)
 int mdh_last_kernel_ms(mdh_ctx *c, float *rdf_ms, float *sq_ms)
 {
     CTX_GUARD(c);
-    MDH_CUDA(cudaStreamSynchronize(c->stream));
-    if (rdf_ms) {
-        *rdf_ms = 0.f;
-        if (c->rdf_timed) MDH_CUDA(cudaEventElapsedTime(rdf_ms, c->ev_rdf0, c->ev_rdf1));
-    }
-    if (sq_ms) {
-        *sq_ms = 0.f;
-        if (c->sq_timed) MDH_CUDA(cudaEventElapsedTime(sq_ms, c->ev_sq0, c->ev_sq1));
-    }
+    if (rdf_ms) if (int rc = c->t_rdf.last(c->stream, rdf_ms)) return rc;
+    if (sq_ms) if (int rc = c->t_sq.last(c->stream, sq_ms)) return rc;
     return MDH_OK;
+}
+
+int mdh_kernel_time(mdh_ctx *c, int reset, double *rdf_ms, int64_t *rdf_calls, double *sq_ms,
+                    int64_t *sq_calls)
+{
+    CTX_GUARD(c);
+    MDH_REQUIRE(rdf_ms && rdf_calls && sq_ms && sq_calls, MDH_EINVAL, "NULL argument");
+    if (int rc = c->t_rdf.collect(c->stream, reset != 0, rdf_ms, rdf_calls)) return rc;
+    return c->t_sq.collect(c->stream, reset != 0, sq_ms, sq_calls);
 }
 
 int mdh_launch_count(mdh_ctx *c, int64_t *launches)

@@ -101,14 +101,27 @@ struct SqState {
     int rho_frames = 0;    // frames held in rho from the last batch
 };
 
+// CUDA-event stopwatch around the hot kernels of every accumulate call, on the
+// context's stream.  Pairs are recorded without synchronising; collect() sums them.
+struct KernelTimer {
+    std::vector<cudaEvent_t> ev;   // ev[2i] start, ev[2i+1] stop
+    size_t used = 0;               // pairs recorded since the last reset / fold
+    double folded_ms = 0;          // pairs folded away because the ring was full
+    int64_t folded_n = 0;
+    int begin(cudaStream_t s);
+    int end(cudaStream_t s);
+    int last(cudaStream_t s, float *ms);                       // synchronises
+    int collect(cudaStream_t s, bool reset, double *ms, int64_t *n);   // synchronises
+    void destroy();
+};
+
 struct mdh_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
     int64_t launches = 0;
-    cudaEvent_t ev_rdf0 = nullptr, ev_rdf1 = nullptr, ev_sq0 = nullptr, ev_sq1 = nullptr;
-    bool rdf_timed = false, sq_timed = false;
+    KernelTimer t_rdf, t_sq;
     RdfState rdf;
     SqState sq;
 };

@@ -406,11 +406,7 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
         mode = cells_ok ? MDH_RDF_CELLS : MDH_RDF_ALLPAIRS;
     }
 
-    if (!c->ev_rdf0) {
-        MDH_CUDA(cudaEventCreate(&c->ev_rdf0));
-        MDH_CUDA(cudaEventCreate(&c->ev_rdf1));
-    }
-    MDH_CUDA(cudaEventRecord(c->ev_rdf0, c->stream));
+    if (int rc = c->t_rdf.begin(c->stream)) return rc;
 
     if (mode == MDH_RDF_CELLS) {
         if (int rc = rdf_cells_accumulate(c, n_frames)) return rc;
@@ -457,7 +453,5 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
         }
         R.evals += ev * n_frames;
     }
-    MDH_CUDA(cudaEventRecord(c->ev_rdf1, c->stream));
-    c->rdf_timed = true;
-    return MDH_OK;
+    return c->t_rdf.end(c->stream);
 }

@@ -130,6 +130,7 @@ struct CellParams {
     BinGuess guess;
     unsigned long long *counts;
     unsigned long long *evals;
+    int half;                     // same group: half stencil, weight 2
 };
 
 template <int HIST>
@@ -180,12 +181,19 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
     int steps = 0;                       // warp-uniform: increments since the last flush
     unsigned long long my_evals = 0;
 
-    auto sweep = [&](int b, int len) {
+    // One range of candidate partners [b, b + len) per lane; the loop bound is the
+    // warp maximum so that flushes stay warp-uniform.  The first partner carries
+    // weight w_first, the others w_rest (half-stencil runs: 1 for the self pair, 2
+    // for every unordered pair).  The next partner is fetched one iteration ahead.
+    auto sweep = [&](int b, int len, unsigned w_first, unsigned w_rest) {
         const int maxlen = __reduce_max_sync(0xffffffffu, len);
         my_evals += len;
+        float4 nxt = __ldg(s2 + (len > 0 ? b : 0));
         for (int t = 0; t < maxlen; ++t) {
             const bool act = t < len;
-            const float4 pj = __ldg(s2 + (act ? b + t : 0));
+            const float4 pj = nxt;
+            nxt = __ldg(s2 + (t + 1 < len ? b + t + 1 : 0));
+            const unsigned w = t == 0 ? w_first : w_rest;
             const double d2 = pair_d2(pi.x, pi.y, pi.z, pj, fb);
             const bool keep = act && !(EXCL && gi == __float_as_int(pj.w));
             if (HIST == MDH_HIST_WARP_ATOMIC && FAST) {
@@ -193,16 +201,17 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
                 const int j = slot_fast_parts(d2, sT, n_bins, guess, below);
                 unsigned a = (below ? hist32 - 4u : hist32) + 4u * (unsigned)j;
                 if ((!below && j == n_bins) || !keep) a = trash32;
-                red_shared(a, 1u);
+                red_shared(a, w);
             } else {
                 int slot = slot_of<FAST>(d2, sT, n_bins, guess);
                 if (!keep) slot = 0;
                 if (HIST == MDH_HIST_WARP_ATOMIC) {
                     if ((unsigned)(slot - 1) < (unsigned)n_bins)
-                        atomicAdd(&myhist[slot - 1], 1u);
+                        atomicAdd(&myhist[slot - 1], w);
                 } else {
-                    priv_add(lane_base, slot, 1u);
-                    if (++steps == 254) {
+                    priv_add(lane_base, slot, w);
+                    steps += 2;
+                    if (steps >= 253) {
                         priv_flush(myhist, bhist, n_words, n_bins, lane, 1u);
                         steps = 0;
                     }
@@ -210,25 +219,37 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
             }
         }
     };
+    auto wrap = [](int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); };
+    // the three x-adjacent cells of row (y, z) are one contiguous range of the sorted
+    // array, plus one more cell when the x stencil wraps around the box
+    auto sweep_row = [&](int y, int z, unsigned w) {
+        const int row = (z * g.nc[1] + y) * g.nc[0];
+        const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nc[0] - 1);
+        const int b0 = start[row + xa];
+        sweep(b0, valid ? start[row + xb + 1] - b0 : 0, w, w);
+        const int xw = (cx == 0) ? g.nc[0] - 1 : (cx == g.nc[0] - 1 ? 0 : -1);
+        const int bw = xw >= 0 ? start[row + xw] : 0;
+        sweep(bw, (valid && xw >= 0) ? start[row + xw + 1] - bw : 0, w, w);
+    };
 
-    for (int dz = -1; dz <= 1; ++dz) {
-        int z = cz + dz;
-        z += (z < 0) ? g.nc[2] : 0;
-        z -= (z >= g.nc[2]) ? g.nc[2] : 0;
-        for (int dy = -1; dy <= 1; ++dy) {
-            int y = cy + dy;
-            y += (y < 0) ? g.nc[1] : 0;
-            y -= (y >= g.nc[1]) ? g.nc[1] : 0;
-            const int row = (z * g.nc[1] + y) * g.nc[0];
-            // x-adjacent cells are contiguous in the sorted array
-            const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nc[0] - 1);
-            const int b0 = start[row + xa];
-            sweep(b0, valid ? start[row + xb + 1] - b0 : 0);
-            // periodic wrap of the x stencil
-            const int xw = (cx == 0) ? g.nc[0] - 1 : (cx == g.nc[0] - 1 ? 0 : -1);
-            const int bw = xw >= 0 ? start[row + xw] : 0;
-            sweep(bw, (valid && xw >= 0) ? start[row + xw + 1] - bw : 0);
-        }
+    if (!P.half) {
+        // full stencil: every ordered (i, j) pair once
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                sweep_row(wrap(cy + dy, g.nc[1]), wrap(cz + dz, g.nc[2]), 1u);
+    } else {
+        // same group: half stencil.  Forward offsets (dz, dy, dx) > (0, 0, 0) in
+        // lexicographic order visit every unordered pair of distinct cells exactly
+        // once (the reverse offset belongs to the partner cell); weight 2 stands for
+        // both orders.  The own cell contributes j >= i: the self pair once.
+        for (int dy = -1; dy <= 1; ++dy)
+            sweep_row(wrap(cy + dy, g.nc[1]), wrap(cz + 1, g.nc[2]), 2u);
+        sweep_row(wrap(cy + 1, g.nc[1]), cz, 2u);
+        const int row = (cz * g.nc[1] + cy) * g.nc[0];
+        const int xr = wrap(cx + 1, g.nc[0]);
+        const int br = start[row + xr];
+        sweep(br, valid ? start[row + xr + 1] - br : 0, 2u, 2u);
+        sweep(i, valid ? start[row + cx + 1] - i : 0, 1u, 2u);
     }
     if (HIST == MDH_HIST_LANE_PRIVATE)
         priv_flush(myhist, bhist, n_words, n_bins, lane, 1u);
@@ -352,6 +373,7 @@ int rdf_cells_accumulate(mdh_ctx *c, int n_frames)
     P.guess = rdf_bin_guess(R);
     P.counts = R.counts.as<unsigned long long>();
     P.evals = R.cell[9].as<unsigned long long>();
+    P.half = R.same;
     dim3 grid((unsigned)((R.n1 + kThreads - 1) / kThreads), (unsigned)n_frames);
     const bool excl = R.excl1 > 0, fast = R.fast_bins;
     if (R.hist == MDH_HIST_LANE_PRIVATE) {

@@ -478,11 +478,7 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
     const size_t rho_bytes = sizeof(double) * 2 * (size_t)n_frames * S.n_rho * S.n_q;
     if (int rc = S.rho.reserve(rho_bytes)) return rc;
 
-    if (!c->ev_sq0) {
-        MDH_CUDA(cudaEventCreate(&c->ev_sq0));
-        MDH_CUDA(cudaEventCreate(&c->ev_sq1));
-    }
-    MDH_CUDA(cudaEventRecord(c->ev_sq0, c->stream));
+    if (int rc = c->t_sq.begin(c->stream)) return rc;
     MDH_CUDA(cudaMemsetAsync(S.rho.p, 0, rho_bytes, c->stream));
 
     if (S.lattice) {
@@ -517,8 +513,6 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
                                                      S.ssf.as<double>());
     MDH_CUDA(cudaGetLastError());
     c->launches++;
-    MDH_CUDA(cudaEventRecord(c->ev_sq1, c->stream));
-    c->sq_timed = true;
     S.rho_frames = n_frames;
-    return MDH_OK;
+    return c->t_sq.end(c->stream);
 }

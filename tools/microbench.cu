@@ -9,7 +9,7 @@
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { \
     fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
-constexpr int ITERS = 4096;
+constexpr int ITERS = 32768;
 constexpr int ILP = 8;
 
 struct Cyc { unsigned long long c; };
@@ -122,14 +122,16 @@ static void run(const char *name, F launch, int blocks, int threads, double ops_
 {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    launch();                                   // warm-up
+    for (int w = 0; w < 8; ++w) launch();       // warm-up: let the clocks ramp
     CK(cudaDeviceSynchronize());
+    const int reps = 4;
     CK(cudaEventRecord(e0));
-    launch();
+    for (int r = 0; r < reps; ++r) launch();
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= reps;
     Cyc *h = (Cyc *)malloc(sizeof(Cyc) * blocks);
     CK(cudaMemcpy(h, d_cyc, sizeof(Cyc) * blocks, cudaMemcpyDeviceToHost));
     double mean = 0;
@@ -138,9 +140,10 @@ static void run(const char *name, F launch, int blocks, int threads, double ops_
     free(h);
     // all resident blocks of an SM run concurrently for ~mean cycles
     const double per_clk_sm = ops_per_thread * threads * blocks_per_sm / mean;
-    const double mhz = mean / (ms * 1e3);       // cycles per block / wall time
-    printf("  \"%s\": {\"ops_per_clk_per_sm\": %.2f, \"ms\": %.4f, \"eff_mhz\": %.0f}%s\n", name,
-           per_clk_sm, ms, mhz, last ? "" : ",");
+    const double mhz = mean / (ms * 1e3);       // clock64 ticks per block / wall time
+    const double gops = ops_per_thread * threads * blocks / (ms * 1e-3) / 1e9;   // whole GPU
+    printf("  \"%s\": {\"gops_per_s\": %.1f, \"ops_per_clk_per_sm\": %.2f, \"ms\": %.4f, "
+           "\"clock64_mhz\": %.0f}%s\n", name, gops, per_clk_sm, ms, mhz, last ? "" : ",");
 }
 
 int main()
