@@ -71,6 +71,16 @@ enum {
     MDH_HIST_LANE_PRIVATE = 2  /* one packed 8-bit histogram per lane, no atomics   */
 };
 
+/* arithmetic of the all-pairs kernel (same counts either way, bit for bit) */
+enum {
+    MDH_FILTER_AUTO = 0,   /* fp32 filter whenever the configuration is eligible      */
+    MDH_FILTER_OFF = 1,    /* every pair through the reference's fp64 arithmetic      */
+    MDH_FILTER_ON = 2,     /* as AUTO (kept for symmetry with the other selectors)    */
+    MDH_FILTER_AUDIT = 3   /* filter + every pair ALSO evaluated exactly and compared;
+                              violations are reported by mdh_rdf_filter_stats (slow,
+                              test aid)                                               */
+};
+
 /* S(q) kernel strategy */
 enum {
     MDH_SQ_AUTO = 0,
@@ -142,6 +152,20 @@ int mdh_rdf_reset(mdh_ctx *ctx);
 int mdh_rdf_counts_device(mdh_ctx *ctx, void **dptr);
 /* pair evaluations performed so far (what the kernels computed, for rooflines) */
 int mdh_rdf_pair_evaluations(mdh_ctx *ctx, int64_t *evals);
+
+/*
+ * The all-pairs kernel bins a pair from fp32 arithmetic when a rigorous error bound
+ * proves the reference's fp64 distance lies in the same bin, and re-evaluates every
+ * other pair with the fp64 arithmetic (rdf_filter.cu).  mode is an MDH_FILTER_*
+ * value; it persists across mdh_rdf_configure calls of the context.
+ */
+int mdh_rdf_set_filter(mdh_ctx *ctx, int mode);
+/* stats[0] pairs-of-IPT entries re-evaluated from the deferred lists, stats[1]
+ * entries re-evaluated inline (list overflow), stats[2] audit violations (must be
+ * 0), stats[3] uncertain pairs seen by the audit, stats[4] frames the filter
+ * declined (left to the exact kernel), stats[5] 1 if the current configuration is
+ * eligible for the filter.  Since the last configure / reset. */
+int mdh_rdf_filter_stats(mdh_ctx *ctx, int64_t *stats /* [6] host */);
 
 /* ---- seam #2: direct-sum structure factor ------------------------------------ */
 

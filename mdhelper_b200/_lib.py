@@ -23,6 +23,7 @@ MDH_OK, MDH_EINVAL, MDH_ECUDA, MDH_ESTATE, MDH_ENOMEM = 0, -1, -2, -3, -4
 MDH_HOST, MDH_DEVICE = 0, 1
 RDF_MODES = {"auto": 0, "allpairs": 1, "cells": 2}
 HIST_MODES = {"auto": 0, "warp_atomic": 1, "lane_private": 2}
+FILTER_MODES = {"auto": 0, "off": 1, "on": 2, "audit": 3}
 SQ_MODES = {"auto": 0, "lattice_fp64": 1, "lattice_sfu": 2, "general_fp64": 3,
             "lattice_fp32": 4}
 
@@ -48,6 +49,8 @@ SIGNATURES = {
     "mdh_rdf_reset": (_i32, [_p]),
     "mdh_rdf_counts_device": (_i32, [_p, ctypes.POINTER(_p)]),
     "mdh_rdf_pair_evaluations": (_i32, [_p, ctypes.POINTER(_i64)]),
+    "mdh_rdf_set_filter": (_i32, [_p, _i32]),
+    "mdh_rdf_filter_stats": (_i32, [_p, _p]),
     "mdh_sq_configure": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i32, _p, _i32]),
     "mdh_sq_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
     "mdh_sq_fetch": (_i32, [_p, _p]),
@@ -184,6 +187,17 @@ class Context:
 
     def rdf_reset(self):
         check(self._lib.mdh_rdf_reset(self._h))
+
+    def rdf_set_filter(self, mode: str = "auto"):
+        """fp32 filter of the all-pairs kernel: ``auto``, ``off``, ``on``, ``audit``."""
+        check(self._lib.mdh_rdf_set_filter(self._h, FILTER_MODES[mode]))
+
+    def rdf_filter_stats(self) -> dict:
+        out = np.zeros(6, dtype=np.int64)
+        check(self._lib.mdh_rdf_filter_stats(self._h, out.ctypes.data))
+        return dict(zip(("deferred_entries", "inline_entries", "audit_violations",
+                         "audit_uncertain_pairs", "declined_frames", "eligible"),
+                        (int(v) for v in out)))
 
     def rdf_pair_evaluations(self) -> int:
         n = _i64()

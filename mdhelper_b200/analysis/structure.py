@@ -73,7 +73,8 @@ def _n_entities(group, grouping: str) -> int:
 def radial_histogram(
         pos1: np.ndarray, pos2: np.ndarray, n_bins: int, range: tuple,
         dims: tuple, *, exclusion: tuple = None, mode: str = "auto",
-        hist: str = "auto", device: int = None) -> np.ndarray:
+        hist: str = "auto", arith: str = "auto", device: int = None,
+        stats: dict = None) -> np.ndarray:
     """
     Computes the radial histogram of distances between particles of the same
     type or two different types (GPU version of ``structure.py:32-104``).
@@ -97,6 +98,14 @@ def radial_histogram(
         Kernel selectors (``"auto"``, ``"allpairs"``, ``"cells"``;
         ``"auto"``, ``"warp_atomic"``, ``"lane_private"``).  Counts do not
         depend on them.
+    arith : `str`, keyword-only
+        ``"auto"``: fp32 filter in front of the reference's fp64 arithmetic
+        (pairs provably inside a bin are binned from fp32, all others are
+        re-evaluated exactly); ``"off"``: fp64 for every pair; ``"audit"``:
+        filter plus a full exact comparison (test aid).  Counts do not depend
+        on it either.
+    stats : `dict`, keyword-only, optional
+        If given, receives the filter statistics of the call.
 
     Returns
     -------
@@ -112,12 +121,16 @@ def radial_histogram(
     dev = torch.cuda.current_device() if device is None else device
     ctx = Context(dev)
     try:
+        ctx.rdf_set_filter(arith)
         ctx.rdf_configure(len(p1), len(p2), False,
                           squared_thresholds(n_bins, range), range[0], range[1],
                           exclusion=exclusion, mode=mode, hist=hist)
         ctx.rdf_accumulate(p1, 3 * len(p1), p2, 3 * len(p2),
                            dims[None, :3], 1)
-        return ctx.rdf_fetch()
+        out = ctx.rdf_fetch()
+        if stats is not None:
+            stats.update(ctx.rdf_filter_stats())
+        return out
     finally:
         ctx.close()
 
@@ -157,7 +170,7 @@ class RadialDistributionFunction(GpuAnalysisBase):
         ``torch.distributed`` is initialised.
     verbose : `bool`, keyword-only, default: :code:`True`
         Determines whether progress is logged.
-    mode, hist : `str`, keyword-only
+    mode, hist, arith : `str`, keyword-only
         Kernel selectors, see :func:`radial_histogram`.
 
     Attributes
@@ -180,7 +193,7 @@ class RadialDistributionFunction(GpuAnalysisBase):
             groupings: Union[str, tuple] = "atoms", reduced: bool = False,
             n_batches: int = None, parallel: bool = False,
             verbose: bool = True, mode: str = "auto", hist: str = "auto",
-            **kwargs) -> None:
+            arith: str = "auto", **kwargs) -> None:
 
         self.ag1 = ag1
         self.ag2 = ag1 if ag2 is None else ag2
@@ -221,6 +234,7 @@ class RadialDistributionFunction(GpuAnalysisBase):
         self._verbose = verbose
         self._mode = mode
         self._hist = hist
+        self._arith = arith
 
     def _prepare(self) -> None:
         # reference: structure.py:734-748
@@ -239,6 +253,7 @@ class RadialDistributionFunction(GpuAnalysisBase):
         same = (self.ag1 is self.ag2
                 or np.array_equal(self.ag1.ix, self.ag2.ix)) \
             and self._groupings[0] == self._groupings[1]
+        ctx.rdf_set_filter(self._arith)
         ctx.rdf_configure(
             n1, n2, same, squared_thresholds(self._n_bins, self._range),
             self._range[0], self._range[1], exclusion=self._exclusion,
@@ -286,6 +301,7 @@ class RadialDistributionFunction(GpuAnalysisBase):
             _record(batch)
         self._local_counts = ctx.rdf_fetch()
         self._pair_evaluations = ctx.rdf_pair_evaluations()
+        self._filter_stats = ctx.rdf_filter_stats()
 
     def _conclude(self) -> None:
         # one all-reduce: counts (exact) and the accumulated volume

@@ -157,6 +157,7 @@ int mdh_ctx_destroy(mdh_ctx *c)
     RdfState &R = c->rdf;
     R.thr.release(); R.counts.release(); R.raw1.release(); R.raw2.release();
     R.pk1.release(); R.pk2.release(); R.boxes.release();
+    R.ext1.release(); R.ext2.release(); R.filt.release(); R.fstats.release();
     for (auto &b : R.cell) b.release();
     if (R.h_boxes_pinned) cudaFreeHost(R.h_boxes_pinned);
     if (R.ev_boxes) cudaEventDestroy(R.ev_boxes);
@@ -238,6 +239,8 @@ int mdh_rdf_reset(mdh_ctx *c)
     MDH_CUDA(cudaMemsetAsync(c->rdf.counts.p, 0, sizeof(int64_t) * c->rdf.n_bins, c->stream));
     if (c->rdf.evals_dev_init)
         MDH_CUDA(cudaMemsetAsync(c->rdf.cell[9].p, 0, sizeof(unsigned long long), c->stream));
+    if (c->rdf.fstats.p)
+        MDH_CUDA(cudaMemsetAsync(c->rdf.fstats.p, 0, sizeof(unsigned long long) * 8, c->stream));
     c->rdf.evals = 0;
     return MDH_OK;
 }
@@ -261,6 +264,28 @@ int mdh_rdf_pair_evaluations(mdh_ctx *c, int64_t *evals)
         MDH_CUDA(cudaStreamSynchronize(c->stream));
     }
     *evals = c->rdf.evals + (int64_t)dev;
+    return MDH_OK;
+}
+
+int mdh_rdf_set_filter(mdh_ctx *c, int mode)
+{
+    MDH_REQUIRE(c != nullptr, MDH_EINVAL, "context is NULL");
+    MDH_REQUIRE(mode >= MDH_FILTER_AUTO && mode <= MDH_FILTER_AUDIT, MDH_EINVAL,
+                "rdf: invalid filter mode");
+    c->rdf.filter_mode = mode;
+    return MDH_OK;
+}
+
+int mdh_rdf_filter_stats(mdh_ctx *c, int64_t *stats)
+{
+    CTX_GUARD(c);
+    MDH_REQUIRE(stats != nullptr, MDH_EINVAL, "stats is NULL");
+    MDH_REQUIRE(c->rdf.configured, MDH_ESTATE, "rdf: not configured");
+    unsigned long long h[8] = {0};
+    MDH_CUDA(cudaMemcpyAsync(h, c->rdf.fstats.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    MDH_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 5; ++i) stats[i] = (int64_t)h[i];
+    stats[5] = c->rdf.filter_ok ? 1 : 0;
     return MDH_OK;
 }
 

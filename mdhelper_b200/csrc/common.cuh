@@ -47,6 +47,25 @@ struct FrameBox {          // per frame, device side
     double inv[3];         // (double)(float)(1.0 / (double)box_f32)
 };
 
+// fp32 filter, per frame (built on the device by rdf_filter_prepare_kernel)
+struct FrameFilter {
+    float nbox[3];         // -box_k
+    float inv[3];          // (float)(1.0 / box_k), the reference's float32 inverse box
+    unsigned madd;         // m << (32 - k): centres the uncertainty window on a bin edge
+    unsigned wthr;         // pair is uncertain iff (bits << (32 - k)) + madd < wthr;
+                           // 0 = frame not eligible (the exact kernel handles it)
+};
+
+struct FilterConst {       // per configuration (host)
+    float scale;           // (float)(n_bins / (r_hi - r_lo))
+    float offm;            // 1.5 * 2^(23-k) + off, off a multiple of 2^-k
+    unsigned cbits;        // bits of the float (1.5 * 2^(23-k)): slot 0 ("below range")
+    unsigned span;         // (n_bins + 2) << k: slots 0 .. n_bins + 1
+    int k;                 // fraction bits of the fixed-point bin coordinate
+    int sb;                // log2(sub-bins per bin) of the shared-memory histogram
+    int lower;             // r_lo > 0: pairs below the range exist
+};
+
 struct RdfState {
     bool configured = false;
     int64_t n1 = 0, n2 = 0;
@@ -67,6 +86,14 @@ struct RdfState {
     int64_t evals = 0;     // all-pairs evaluations (host-side count)
     int ipt = 2;           // i-particles per thread of the all-pairs kernel
     bool fast_bins = false;  // branch-free bin guess certified for this configuration
+    // fp32 filter in front of the exact arithmetic (rdf_filter.cu)
+    int filter_mode = MDH_FILTER_AUTO;   // survives configure
+    bool filter_ok = false;  // this configuration is eligible
+    int filter_occ = 2;      // blocks per SM the filter kernel is compiled for (2 or 3)
+    FilterConst fc;
+    DevBuf ext1, ext2;     // unsigned[F][6]: coordinate extents of each frame (keys)
+    DevBuf filt;           // FrameFilter[F]
+    DevBuf fstats;         // unsigned long long[4], see PairParams::fstats
 };
 
 struct SqWorkItem {        // one thread's tile of the lattice kernels: two (nx, ny)
@@ -132,6 +159,10 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
                        int drop_axis, int mode, int hist);
 int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *pos2,
                         int64_t s2, int location, const float *box, int n_frames);
+// rdf_filter.cu
+int rdf_filter_sqrt_error(mdh_ctx *c, double *err);
+bool rdf_filter_configure(RdfState &R, const double *thr, double sqrt_err);
+int rdf_filter_prepare(mdh_ctx *c, int n_frames, double sqrt_err);
 // sq.cu
 int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *goff,
                       int n_q, const double *wv, const int32_t *lat_n, const double *lat_b,

@@ -40,19 +40,6 @@ using namespace rdfdev;
 
 namespace {
 
-struct PairParams {
-    const float4 *p1, *p2;
-    int64_t pad1, pad2;            // float4 per frame
-    int n1, n2;
-    const FrameBox *boxes;
-    const double *thr;             // T[0..n_bins]
-    int n_bins;
-    BinGuess guess;
-    int same;
-    int n_jchunks, jtiles_per_chunk, n_jtiles;
-    unsigned long long *counts;
-};
-
 template <int HIST, int IPT>
 __host__ __device__ inline size_t pair_smem_bytes(int n_bins)
 {
@@ -77,6 +64,8 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_allpairs_kernel(const PairPar
     const int jt1 = min(P.n_jtiles, jt0 + P.jtiles_per_chunk);
     if (P.same) jt0 = max(jt0, it);       // upper triangle of tile pairs
     if (jt0 >= jt1) return;
+    // frames the fp32-filter kernel (rdf_filter.cu) has taken are not done again
+    if (P.filt != nullptr && P.filt[frame].wthr != 0u) return;
 
     const int n_bins = P.n_bins;
     const int n_words = priv_words(n_bins);
@@ -234,6 +223,10 @@ int launch_allpairs_dyn(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl, b
 // ---- host side ------------------------------------------------------------------
 
 int rdf_cells_accumulate(mdh_ctx *c, int n_frames);   // rdf_cells.cu
+int rdf_filter_launch(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl,
+                      bool audit);                     // rdf_filter.cu
+
+static double g_sqrt_err_cached = -1.0;
 
 BinGuess rdf_bin_guess(const RdfState &R)
 {
@@ -271,10 +264,12 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
     MDH_REQUIRE(r_hi > r_lo && r_lo >= 0, MDH_EINVAL, "rdf: invalid range");
 
     // tuning knobs for experiments: MDH_TUNE="ipt=4,fast=0"
-    int ipt = 4, allow_fast = 1;
+    int ipt = 4, allow_fast = 1, allow_filter = 1;
     if (const char *t = getenv("MDH_TUNE")) {
         if (const char *p = strstr(t, "ipt=")) ipt = atoi(p + 4) == 4 ? 4 : 2;
         if (const char *p = strstr(t, "fast=")) allow_fast = atoi(p + 5) != 0;
+        if (const char *p = strstr(t, "filter=")) allow_filter = atoi(p + 7) != 0;
+        if (const char *p = strstr(t, "occ=")) R.filter_occ = atoi(p + 4) == 3 ? 3 : 2;
     }
     // measured on B200 (profiles/): per-warp shared-memory atomics beat the
     // lane-private byte counters at every bin count tried, and need less memory
@@ -296,6 +291,8 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
     if (int rc = R.thr.reserve(sizeof(double) * (n_bins + 2))) return rc;
     if (int rc = R.counts.reserve(sizeof(unsigned long long) * n_bins)) return rc;
     if (int rc = R.cell[9].reserve(sizeof(unsigned long long) + sizeof(int))) return rc;
+    if (int rc = R.fstats.reserve(sizeof(unsigned long long) * 8)) return rc;
+    MDH_CUDA(cudaMemsetAsync(R.fstats.p, 0, sizeof(unsigned long long) * 8, c->stream));
     std::vector<double> t(thr, thr + n_bins + 1);
     t.push_back(INFINITY);
     MDH_CUDA(cudaMemcpyAsync(R.thr.p, t.data(), sizeof(double) * t.size(),
@@ -315,13 +312,21 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
     MDH_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     MDH_CUDA(cudaStreamSynchronize(c->stream));   // also: t is a local
     R.fast_bins = allow_fast && h_bad == 0;
+
+    // fp32 filter: needs the 4-particle tile, the shared-atomic histogram layout and
+    // uniform edges; the approximation error of MUFU.SQRT is measured, not assumed
+    R.filter_ok = false;
+    if (allow_filter && ipt == 4 && hist == MDH_HIST_WARP_ATOMIC) {
+        if (int rc = rdf_filter_sqrt_error(c, &g_sqrt_err_cached)) return rc;
+        rdf_filter_configure(R, thr, g_sqrt_err_cached);
+    }
     R.configured = true;
     return MDH_OK;
 }
 
 static int rdf_upload_group(mdh_ctx *c, const float *pos, int64_t stride, int location,
                             int64_t n, int64_t npad, int64_t excl, int n_frames,
-                            DevBuf &raw, DevBuf &pk)
+                            DevBuf &raw, DevBuf &pk, DevBuf *ext)
 {
     RdfState &R = c->rdf;
     MDH_REQUIRE(pos != nullptr, MDH_EINVAL, "rdf: coordinate pointer is NULL");
@@ -338,9 +343,19 @@ static int rdf_upload_group(mdh_ctx *c, const float *pos, int64_t stride, int lo
         dsrc = raw.as<float>();
         dstride = 3 * n;
     }
+    unsigned *d_ext = nullptr;
+    if (ext) {
+        // per frame {min x, y, z, max x, y, z} as order-preserving keys
+        if (int rc = ext->reserve(sizeof(unsigned) * 6 * n_frames)) return rc;
+        d_ext = ext->as<unsigned>();
+        rdf_ext_init_kernel<<<(6 * n_frames + 255) / 256, 256, 0, c->stream>>>(d_ext,
+                                                                              6 * n_frames);
+        MDH_CUDA(cudaGetLastError());
+        c->launches++;
+    }
     dim3 grid((unsigned)std::min<int64_t>((npad + 255) / 256, 1024), n_frames);
     rdf_pack_kernel<<<grid, 256, 0, c->stream>>>(dsrc, dstride, pk.as<float4>(), n, npad, excl,
-                                                 R.drop_axis);
+                                                 R.drop_axis, d_ext);
     MDH_CUDA(cudaGetLastError());
     c->launches++;
     return MDH_OK;
@@ -391,12 +406,6 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
     const int tile = kThreads * R.ipt;
     const int64_t pad1 = (R.n1 + tile - 1) / tile * tile;
     const int64_t pad2 = (R.n2 + tile - 1) / tile * tile;
-    if (int rc = rdf_upload_group(c, pos1, s1, location, R.n1, pad1, R.excl1, n_frames,
-                                  R.raw1, R.pk1)) return rc;
-    if (!R.same)
-        if (int rc = rdf_upload_group(c, pos2, s2, location, R.n2, pad2, R.excl2, n_frames,
-                                      R.raw2, R.pk2)) return rc;
-
     int mode = R.mode;
     if (mode == MDH_RDF_AUTO) {
         // cells pay off when the cut-off sphere is a small part of the box
@@ -405,6 +414,16 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
                               (double)R.n1 * (double)R.n2 >= 4e6 && R.drop_axis < 0;
         mode = cells_ok ? MDH_RDF_CELLS : MDH_RDF_ALLPAIRS;
     }
+    const bool use_filter = mode == MDH_RDF_ALLPAIRS && R.filter_ok &&
+                            R.filter_mode != MDH_FILTER_OFF;
+
+    if (int rc = rdf_upload_group(c, pos1, s1, location, R.n1, pad1, R.excl1, n_frames,
+                                  R.raw1, R.pk1, use_filter ? &R.ext1 : nullptr)) return rc;
+    if (!R.same)
+        if (int rc = rdf_upload_group(c, pos2, s2, location, R.n2, pad2, R.excl2, n_frames,
+                                      R.raw2, R.pk2, use_filter ? &R.ext2 : nullptr)) return rc;
+    if (use_filter)
+        if (int rc = rdf_filter_prepare(c, n_frames, g_sqrt_err_cached)) return rc;
 
     if (int rc = c->t_rdf.begin(c->stream)) return rc;
 
@@ -434,6 +453,17 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
         P.n_jchunks = (int)((P.n_jtiles + P.jtiles_per_chunk - 1) / P.jtiles_per_chunk);
         dim3 grid((unsigned)(n_itiles * P.n_jchunks), (unsigned)n_frames);
         const bool excl = R.excl1 > 0;
+        P.filt = nullptr;
+        P.fc = R.fc;
+        P.fast_bins = R.fast_bins ? 1 : 0;
+        P.fstats = R.fstats.as<unsigned long long>();
+        if (use_filter) {
+            // the filter kernel takes every frame whose error bound is small against a
+            // bin; the exact kernel below then only runs the frames it declined
+            P.filt = R.filt.as<FrameFilter>();
+            if (int rc = rdf_filter_launch(c, P, grid, excl,
+                                           R.filter_mode == MDH_FILTER_AUDIT)) return rc;
+        }
         int rc = R.hist == MDH_HIST_LANE_PRIVATE
                      ? launch_allpairs_dyn<MDH_HIST_LANE_PRIVATE>(c, P, grid, excl, R.fast_bins,
                                                                   R.ipt)

@@ -5,6 +5,7 @@
 #include <cuda_pipeline.h>
 #include <float.h>
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -17,14 +18,43 @@ constexpr float kMagicF = 12582912.0f;         // 1.5 * 2^23
 constexpr size_t kMaxSmem = 227 * 1024;
 
 // ---- pack: float[F][n][3] -> float4[F][npad] (x, y, z, exclusion block id) ------
+// Also reduces the coordinate extents of every frame (per axis minimum and maximum,
+// as order-preserving unsigned keys) for the error bound of the fp32 filter.
 
+__device__ __forceinline__ unsigned ext_key(float f)
+{
+    // the move is opaque on purpose: seeing a float, nvcc sets the sign bit with
+    // FADD -|x|, -0, which turns every NaN into the canonical 0x7fffffff (= key of -0)
+    unsigned b;
+    asm("mov.b32 %0, %1;" : "=r"(b) : "f"(f));
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float ext_unkey(unsigned k)
+{
+    const unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+static __global__ void rdf_ext_init_kernel(unsigned *ext, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ext[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
+}
+
+// ext: unsigned[F][6] = {min x, y, z, max x, y, z} keys, initialised by
+// rdf_ext_init_kernel (or nullptr)
 static __global__ void rdf_pack_kernel(const float *__restrict__ raw, int64_t frame_stride,
                                        float4 *__restrict__ out, int64_t n, int64_t npad,
-                                       int64_t excl, int drop_axis)
+                                       int64_t excl, int drop_axis, unsigned *__restrict__ ext)
 {
     const int frame = blockIdx.y;
     const float *src = raw + (int64_t)frame * frame_stride;
     float4 *dst = out + (int64_t)frame * npad;
+    unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npad;
          i += (int64_t)gridDim.x * blockDim.x) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -36,8 +66,23 @@ static __global__ void rdf_pack_kernel(const float *__restrict__ raw, int64_t fr
             if (drop_axis == 1) v.y = 0.f;
             if (drop_axis == 2) v.z = 0.f;
             v.w = __int_as_float((int)(excl > 0 ? i / excl : i));
+            const unsigned kx = ext_key(v.x), ky = ext_key(v.y), kz = ext_key(v.z);
+            lo[0] = min(lo[0], kx); hi[0] = max(hi[0], kx);
+            lo[1] = min(lo[1], ky); hi[1] = max(hi[1], ky);
+            lo[2] = min(lo[2], kz); hi[2] = max(hi[2], kz);
         }
         dst[i] = v;
+    }
+    if (ext) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned l = __reduce_min_sync(0xffffffffu, lo[k]);
+            const unsigned h = __reduce_max_sync(0xffffffffu, hi[k]);
+            if ((threadIdx.x & 31) == 0) {
+                if (l != 0xffffffffu) atomicMin(&ext[frame * 6 + k], l);
+                if (h != 0u) atomicMax(&ext[frame * 6 + 3 + k], h);
+            }
+        }
     }
 }
 
@@ -221,6 +266,28 @@ __device__ __forceinline__ void priv_flush(unsigned *priv_w, unsigned *bhist, in
     }
     __syncwarp();
 }
+
+// ---- parameters of the all-pairs kernels (rdf.cu, rdf_filter.cu) -------------------
+
+struct PairParams {
+    const float4 *p1, *p2;
+    int64_t pad1, pad2;            // float4 per frame
+    int n1, n2;
+    const FrameBox *boxes;
+    const double *thr;             // T[0..n_bins]
+    int n_bins;
+    BinGuess guess;
+    int same;
+    int n_jchunks, jtiles_per_chunk, n_jtiles;
+    unsigned long long *counts;
+    // fp32 filter (rdf_filter.cu); filt == nullptr: the exact kernel does every frame
+    const FrameFilter *filt;
+    FilterConst fc;
+    int fast_bins;                 // slot_fast certified (used by the exact re-evaluation)
+    unsigned long long *fstats;    // [0] deferred entries, [1] inline fixes, [2] audit
+                                   // violations, [3] audited uncertain pairs, [4] frames
+                                   // declined by the filter
+};
 
 }  // namespace rdfdev
 

@@ -1,0 +1,576 @@
+// rdf_filter.cu -- all-pairs histogram with an fp32 filter in front of the exact
+// fp64 arithmetic (seam #1, /root/reference/src/mdhelper/analysis/structure.py:32-104).
+//
+// The counts are the reference's, bit for bit: a pair is binned from fp32 arithmetic
+// only when a rigorous error bound proves that the reference's fp64 distance falls in
+// the same bin; every other pair ("uncertain": within the bound of a bin edge, about
+// 1 in 1,500 for the benchmark configurations) is re-evaluated with the exact
+// arithmetic of rdf_device.cuh::pair_d2 and corrected.  The fp32 path costs ~24
+// instructions per pair on the FP32/ALU pipes instead of 21 FP64-pipe instructions
+// plus conversions (46 in total) -- it removes the FP64 pipe as the bound.
+//
+// fp32 evaluation (filter_eval), per axis:
+//     df = xj - xi                      the reference's own float32 difference (exact copy)
+//     t  = fma(df, inv, 1.5*2^23)       -> 1.5*2^23 + rint(df * inv), one rounding
+//     r  = t - 1.5*2^23                 exact
+//     m  = fma(-box, r, df)             minimum image, one rounding
+// then d2 = mx*mx + my*my + mz*mz (fma chain), s = sqrt.approx(d2), and the bin
+// coordinate as a fixed-point number in the mantissa of one more fma:
+//     bits(fma(s, scale, 1.5*2^(23-k) + off)) - bits(1.5*2^(23-k)) = slot * 2^k + frac
+// slot = bin + 1 (slot 0: below the range, slot n_bins + 1: above).
+//
+// Error bound (rdf_filter_prepare_kernel, per frame, in bin units) -- see DESIGN.md
+// section 4.1b for the derivation.  With eps_b = |box*inv - 1| (the reference's
+// float32 inverse box makes its minimum image differ from df - box*r by eps_b*df),
+// D_k the largest |df| of the frame (coordinate extents from the pack kernel):
+//     | |m_f| - |m_ref| |  <=  a_k = 2^-24 (box_k/2 + eps_b D_k + 2^-24 D_k) + eps_b D_k
+//     | |m_f|_2 - d_ref |  <=  |a|_2                          (reverse triangle inequality)
+//     fp32 sum of squares: relative 3*2^-24 on d2 -> 1.5*2^-24 on d
+//     sqrt.approx: relative error measured exhaustively at start-up (<= 2^-22 required)
+//     scale rounding 2^-24, off rounding 2^-(k+1), fma rounding 2^-(k+1)
+// The window half-width is ceil(1.25 * bound * 2^k) + 1 units of 2^-k.  Frames whose
+// bound is not small against a bin (coordinates many boxes away, non-finite values)
+// are left to the exact kernel of rdf.cu.
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "rdf_device.cuh"
+
+using namespace rdfdev;
+
+namespace {
+
+constexpr int kListCap = 3072;           // deferred entries per block and tile
+
+template <int IPT>
+__host__ __device__ inline size_t filter_smem_bytes(int n_bins, int sb)
+{
+    return align16(sizeof(double) * (n_bins + 1)) + 2 * kThreads * IPT * sizeof(float4) +
+           sizeof(unsigned) * ((size_t)kWarps * (((size_t)(n_bins + 2) << sb) + 32)) +
+           sizeof(unsigned) * (kListCap + 4);
+}
+
+// ---- packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE round-to-nearest
+// operations per issue slot; a scalar operand is broadcast by the hardware) -----------
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// The fp32 evaluation of one tile row against TWO particles of group 1 (their
+// negated coordinates packed in nx, ny, nz): the fixed-point bin coordinates u0, u1
+// (relative to slot 0 when LOWER, else with the bits of 1.5*2^(23-k) still added).
+// The main loop and the re-evaluation in filter_fix both go through this function,
+// so they see identical bits.
+template <bool LOWER>
+__device__ __forceinline__ void filter_eval2(f32x2 nx, f32x2 ny, f32x2 nz, const float4 &pj,
+                                             const FrameFilter &ff, float scale, float offm,
+                                             unsigned cbits, unsigned &u0, unsigned &u1)
+{
+    const f32x2 magic = pk2(kMagicF, kMagicF), nmagic = pk2(-kMagicF, -kMagicF);
+    const f32x2 dx = add2(nx, pk2(pj.x, pj.x));
+    const f32x2 dy = add2(ny, pk2(pj.y, pj.y));
+    const f32x2 dz = add2(nz, pk2(pj.z, pj.z));
+    const f32x2 rx = add2(fma2(dx, pk2(ff.inv[0], ff.inv[0]), magic), nmagic);
+    const f32x2 ry = add2(fma2(dy, pk2(ff.inv[1], ff.inv[1]), magic), nmagic);
+    const f32x2 rz = add2(fma2(dz, pk2(ff.inv[2], ff.inv[2]), magic), nmagic);
+    const f32x2 mx = fma2(pk2(ff.nbox[0], ff.nbox[0]), rx, dx);
+    const f32x2 my = fma2(pk2(ff.nbox[1], ff.nbox[1]), ry, dy);
+    const f32x2 mz = fma2(pk2(ff.nbox[2], ff.nbox[2]), rz, dz);
+    const f32x2 d2 = fma2(mz, mz, fma2(my, my, mul2(mx, mx)));
+    float a, b, s0, s1;
+    upk2(d2, a, b);
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(a));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(b));
+    const f32x2 e = fma2(pk2(s0, s1), pk2(scale, scale), pk2(offm, offm));
+    upk2(e, a, b);
+    u0 = __float_as_uint(a) - (LOWER ? cbits : 0u);
+    u1 = __float_as_uint(b) - (LOWER ? cbits : 0u);
+}
+
+// RED without the "memory" clobber: the compiler may move the tile loads of the next
+// iteration across it (they never alias the histogram); __syncthreads() orders the
+// histogram against its final read.
+__device__ __forceinline__ void red_shared_hot(unsigned smem_addr, unsigned v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(smem_addr), "r"(v));
+}
+
+// Exact re-evaluation of the IPT pairs behind one deferred entry (thread te of the
+// block, tile row jj): every pair the main loop saw as uncertain has been added to
+// the slot the fp32 arithmetic suggested; move it if the fp64 arithmetic disagrees.
+template <bool EXCL, bool LOWER, int IPT>
+__device__ __noinline__ void filter_fix(const PairParams &P, int frame, int it, unsigned entry,
+                                        const float4 *tile, const double *sT, unsigned hist32,
+                                        unsigned weight)
+{
+    constexpr int TILE = kThreads * IPT;
+    const FrameFilter ff = P.filt[frame];
+    const FrameBox fb = P.boxes[frame];
+    const FilterConst fc = P.fc;
+    const int te = (int)(entry >> 16), jj = (int)(entry & 0xffffu);
+    const float4 pj = tile[jj];
+    const float4 *f1 = P.p1 + (int64_t)frame * P.pad1;
+    const unsigned span_l = LOWER ? fc.span : fc.cbits + fc.span;
+    for (int ip = 0; ip < IPT; ip += 2) {
+        // the same particle pairing as the main loop (rows past the end of the group
+        // repeat the last particle there; they carry weight 0 and are skipped here)
+        const int i0 = it * TILE + ip * kThreads + te, i1 = i0 + kThreads;
+        const float4 a0 = f1[min(i0, P.n1 - 1)], a1 = f1[min(i1, P.n1 - 1)];
+        unsigned uu[2];
+        filter_eval2<LOWER>(pk2(-a0.x, -a1.x), pk2(-a0.y, -a1.y), pk2(-a0.z, -a1.z), pj, ff,
+                            fc.scale, fc.offm, fc.cbits, uu[0], uu[1]);
+        for (int h = 0; h < 2; ++h) {
+            const int i = h ? i1 : i0;
+            const float4 a = h ? a1 : a0;
+            const unsigned u = uu[h];
+            if (i >= P.n1) continue;
+            if (!(u < span_l)) continue;
+            if (!((u << (32 - fc.k)) + ff.madd < ff.wthr)) continue;
+            if (EXCL && __float_as_int(a.w) == __float_as_int(pj.w)) continue;
+            const unsigned word = (LOWER ? u : u - fc.cbits) >> (fc.k - fc.sb);
+            const double d2 = pair_d2(a.x, a.y, a.z, pj, fb);
+            const int slot = P.fast_bins ? slot_fast(d2, sT, P.n_bins, P.guess)
+                                         : slot_search(d2, sT, P.n_bins);
+            if ((word >> fc.sb) == (unsigned)slot) continue;
+            // slots 0 and n_bins + 1 are scratch words, so no range test is needed
+            red_shared(hist32 + 4u * word, 0u - weight);
+            red_shared(hist32 + 4u * ((unsigned)slot << fc.sb), weight);
+        }
+    }
+}
+
+template <bool EXCL, bool LOWER, bool AUDIT, int IPT, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC)
+    rdf_filter_kernel(const __grid_constant__ PairParams P)
+{
+    constexpr int TILE = kThreads * IPT;
+    const int frame = blockIdx.y;
+    const FrameFilter ff = P.filt[frame];
+    if (ff.wthr == 0u) {                  // left to the exact kernel (whole block)
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.fstats[4], 1ull);
+        return;
+    }
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n_bins = P.n_bins;
+    const FilterConst fc = P.fc;
+    // per warp: (n_bins + 2) slots x 2^sb sub-bins, then 32 per-lane trash words
+    const int hwords = ((n_bins + 2) << fc.sb) + 32;
+    double *sT = reinterpret_cast<double *>(smem);
+    float4 *sJ = reinterpret_cast<float4 *>(smem + align16(sizeof(double) * (n_bins + 1)));
+    unsigned *sH = reinterpret_cast<unsigned *>(sJ + 2 * TILE);
+    unsigned *sList = sH + kWarps * hwords;
+    unsigned *sCount = sList + kListCap;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int it = blockIdx.x / P.n_jchunks;
+    const int jc = blockIdx.x - it * P.n_jchunks;
+    int jt0 = jc * P.jtiles_per_chunk;
+    const int jt1 = min(P.n_jtiles, jt0 + P.jtiles_per_chunk);
+    if (P.same) jt0 = max(jt0, it);       // upper triangle of tile pairs
+    if (jt0 >= jt1) return;
+
+    for (int k = tid; k <= n_bins; k += kThreads) sT[k] = P.thr[k];
+    for (int k = tid; k < kWarps * hwords; k += kThreads) sH[k] = 0;
+    if (tid == 0) *sCount = 0;
+
+    const float4 *f1 = P.p1 + (int64_t)frame * P.pad1;
+    const float4 *f2 = P.same ? f1 : P.p2 + (int64_t)frame * P.pad2;
+
+    static_assert(IPT % 2 == 0, "particles are processed in packed pairs");
+    float xi[IPT], yi[IPT], zi[IPT];
+    int gi[IPT];
+    bool vi[IPT];
+#pragma unroll
+    for (int ii = 0; ii < IPT; ++ii) {
+        const int i = it * TILE + ii * kThreads + tid;
+        vi[ii] = i < P.n1;
+        // rows past the end of the group repeat the last particle with weight 0
+        const float4 a = f1[min(i, P.n1 - 1)];
+        xi[ii] = a.x; yi[ii] = a.y; zi[ii] = a.z; gi[ii] = __float_as_int(a.w);
+    }
+    // negated coordinates of particle pairs (0,1), (2,3), ... for the packed arithmetic
+    f32x2 nx[IPT / 2], ny[IPT / 2], nz[IPT / 2];
+#pragma unroll
+    for (int ip = 0; ip < IPT / 2; ++ip) {
+        nx[ip] = pk2(-xi[2 * ip], -xi[2 * ip + 1]);
+        ny[ip] = pk2(-yi[2 * ip], -yi[2 * ip + 1]);
+        nz[ip] = pk2(-zi[2 * ip], -zi[2 * ip + 1]);
+    }
+
+    const unsigned hist32 = (unsigned)__cvta_generic_to_shared(sH + warp * hwords);
+    const int shift = fc.k - fc.sb;
+    // !LOWER: the bits of 1.5*2^(23-k) are still in u; fold them into the base
+    const unsigned hbase = hist32 - (LOWER ? 0u : ((fc.cbits >> shift) << 2));
+    const unsigned span_l = LOWER ? fc.span : fc.cbits + fc.span;
+    // word index of this lane's trash word (same offset convention as u >> shift):
+    // every pair issues one unconditional RED; pairs outside the range -- about half
+    // of them when the range ends at L/2 -- land here and never contend
+    const unsigned trash_w = (span_l >> shift) + (unsigned)lane;
+    // opaque to the compiler so that the window test is one IMAD, not shift + add
+    unsigned fmul;
+    asm volatile("mov.u32 %0, %1;" : "=r"(fmul) : "r"(1u << (32 - fc.k)));
+    const float scale = fc.scale, offm = fc.offm;
+
+    auto stage_tile = [&](int jt, int buf) {
+        const float4 *src = f2 + (int64_t)jt * TILE;
+        float4 *dst = sJ + buf * TILE;
+#pragma unroll
+        for (int q = 0; q < IPT; ++q)
+            __pipeline_memcpy_async(dst + q * kThreads + tid, src + q * kThreads + tid,
+                                    sizeof(float4));
+        __pipeline_commit();
+    };
+    stage_tile(jt0, 0);
+
+    unsigned long long audit_bad = 0, audit_unc = 0;
+    int buf = 0;
+    for (int jt = jt0; jt < jt1; ++jt) {
+        if (jt + 1 < jt1) {
+            stage_tile(jt + 1, buf ^ 1);
+            __pipeline_wait_prior(1);
+        } else {
+            __pipeline_wait_prior(0);
+        }
+        __syncthreads();
+
+        const unsigned weight = (P.same && jt > it) ? 2u : 1u;
+        unsigned wi[IPT];
+#pragma unroll
+        for (int ii = 0; ii < IPT; ++ii) wi[ii] = vi[ii] ? weight : 0u;
+        const int jn = min(TILE, P.n2 - jt * TILE);
+        const float4 *tile = sJ + buf * TILE;
+
+        // NR tile rows against the IPT particles of this thread: all the arithmetic
+        // and the REDs first (NR * IPT independent chains for the scheduler), then one
+        // rarely taken branch for the uncertain pairs of the whole group
+        auto rows = [&](const float4 *pj, int jj, auto nr_tag) {
+            constexpr int NR = decltype(nr_tag)::value;
+            unsigned uu[NR][IPT];
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+#pragma unroll
+                for (int ip = 0; ip < IPT / 2; ++ip)
+                    filter_eval2<LOWER>(nx[ip], ny[ip], nz[ip], pj[r], ff, scale, offm, fc.cbits,
+                                        uu[r][2 * ip], uu[r][2 * ip + 1]);
+            unsigned vmin[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                vmin[r] = 0xffffffffu;
+#pragma unroll
+                for (int ii = 0; ii < IPT; ++ii) {
+                    const unsigned u = uu[r][ii];
+                    // uncertain iff u * fmul + madd < wthr; keep the smallest per row
+                    vmin[r] = min(vmin[r], u * fmul + ff.madd);
+                    unsigned w = min(u >> shift, trash_w);
+                    if (EXCL && gi[ii] == __float_as_int(pj[r].w)) w = trash_w;
+                    red_shared_hot(hbase + (w << 2), wi[ii]);
+                    if (AUDIT) {
+                        const bool unc = u * fmul + ff.madd < ff.wthr;
+                        const bool in = u < span_l;
+                        const double d2 =
+                            pair_d2(xi[ii], yi[ii], zi[ii], pj[r], P.boxes[frame]);
+                        const int slot = slot_search(d2, sT, n_bins);
+                        const unsigned fs = in ? ((LOWER ? u : u - fc.cbits) >> fc.k)
+                                               : (unsigned)(n_bins + 1);
+                        const bool counted = slot >= 1 && slot <= n_bins;
+                        if (in && unc) ++audit_unc;
+                        // certain pairs must agree with the exact arithmetic wherever
+                        // a count is at stake
+                        if (!(in && unc) && (unsigned)slot != fs &&
+                            (counted || (fs >= 1u && fs <= (unsigned)n_bins)))
+                            ++audit_bad;
+                    }
+                }
+            }
+            unsigned vall = vmin[0];
+#pragma unroll
+            for (int r = 1; r < NR; ++r) vall = min(vall, vmin[r]);
+            if (vall < ff.wthr) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    if (vmin[r] < ff.wthr) {
+                        const unsigned entry = ((unsigned)tid << 16) | (unsigned)(jj + r);
+                        const unsigned idx = atomicAdd(sCount, 1u);
+                        if (idx < (unsigned)kListCap) sList[idx] = entry;
+                        else
+                            filter_fix<EXCL, LOWER, IPT>(P, frame, it, entry, tile, sT, hist32,
+                                                         weight);
+                    }
+                }
+            }
+        };
+        // two rows per iteration, the next two fetched before the arithmetic of the
+        // current ones (rows up to TILE - 1 always exist: the packed arrays are padded)
+        const int jn2 = jn & ~1;
+        float4 nxt[2] = {tile[0], tile[1]};
+        for (int jj = 0; jj < jn2; jj += 2) {
+            const float4 cur[2] = {nxt[0], nxt[1]};
+            const int jnext = min(jj + 2, TILE - 2);
+            nxt[0] = tile[jnext];
+            nxt[1] = tile[jnext + 1];
+            rows(cur, jj, std::integral_constant<int, 2>());
+        }
+        if (jn2 < jn) rows(tile + jn2, jn2, std::integral_constant<int, 1>());
+        __syncthreads();
+
+        // drain the deferred entries of this tile while it is still in shared memory
+        const unsigned n_push = *sCount;
+        const unsigned n_list = min(n_push, (unsigned)kListCap);
+        for (unsigned e = tid; e < n_list; e += kThreads)
+            filter_fix<EXCL, LOWER, IPT>(P, frame, it, sList[e], tile, sT, hist32, weight);
+        if (tid == 0 && n_push) {
+            atomicAdd(&P.fstats[0], (unsigned long long)n_list);
+            if (n_push > n_list) atomicAdd(&P.fstats[1], (unsigned long long)(n_push - n_list));
+        }
+        __syncthreads();
+        if (tid == 0) *sCount = 0;
+        buf ^= 1;
+    }
+
+    // merge into the global int64 histogram.  The warps' words are summed modulo
+    // 2^32 first: a correction may have been subtracted in another warp's copy than
+    // the one that was incremented; the block total itself is below 2^32.
+    for (int k = tid; k < n_bins; k += kThreads) {
+        unsigned s = 0;
+        for (int w = 0; w < kWarps; ++w)
+            for (int q = 0; q < (1 << fc.sb); ++q) s += sH[w * hwords + ((k + 1) << fc.sb) + q];
+        if (s) atomicAdd(&P.counts[k], (unsigned long long)s);
+    }
+    if (AUDIT) {
+        if (audit_bad) atomicAdd(&P.fstats[2], audit_bad);
+        if (audit_unc) atomicAdd(&P.fstats[3], audit_unc);
+    }
+}
+
+// Largest relative error of sqrt.approx.ftz.f32 over two binades [1, 4) -- all 2^24
+// inputs; the instruction works on the mantissa and the exponent parity, so this
+// covers every normal input.  Stored as the bits of a non-negative double.
+__global__ void sqrt_error_kernel(unsigned long long *out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;     // < 2^24
+    const float x = __uint_as_float(0x3f800000u + i);
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+    const double t = sqrt((double)x);
+    double err = fabs((double)s - t) / t;
+    for (int o = 16; o; o >>= 1) err = fmax(err, __shfl_xor_sync(0xffffffffu, err, o));
+    if ((threadIdx.x & 31) == 0 && err > 0.0)
+        atomicMax(out, (unsigned long long)__double_as_longlong(err));
+}
+
+struct PrepareParams {
+    const FrameBox *boxes;
+    const unsigned *ext1, *ext2;     // [F][6] keys
+    FrameFilter *out;
+    int n_frames;
+    int k;
+    double scale;                    // n_bins / (r_hi - r_lo)
+    double d_max;                    // largest distance that can still be binned
+    double sqrt_err;
+};
+
+__global__ void rdf_filter_prepare_kernel(const PrepareParams Q)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Q.n_frames) return;
+    const FrameBox fb = Q.boxes[f];
+    const double e24 = 1.0 / 16777216.0;
+    bool ok = true;
+    double a2 = 0.0;
+    FrameFilter ff;
+    for (int k = 0; k < 3; ++k) {
+        const float e4[4] = {ext_unkey(Q.ext1[f * 6 + k]), ext_unkey(Q.ext1[f * 6 + 3 + k]),
+                             ext_unkey(Q.ext2[f * 6 + k]), ext_unkey(Q.ext2[f * 6 + 3 + k])};
+        // inf / NaN coordinates (all-ones exponent) make the bound meaningless
+        for (int q = 0; q < 4; ++q)
+            if ((__float_as_uint(e4[q]) & 0x7f800000u) == 0x7f800000u) ok = false;
+        const double lo1 = (double)e4[0], hi1 = (double)e4[1];
+        const double lo2 = (double)e4[2], hi2 = (double)e4[3];
+        const double D = fmax(fmax(hi2 - lo1, hi1 - lo2), 0.0) * (1.0 + 2.0 * e24);
+        const double box = fb.box[k], inv = fb.inv[k];
+        // the magic-number rounding needs |df * inv| well inside 2^22
+        if (!(D * inv < 1048576.0)) ok = false;
+        const double eps_b = fabs(box * inv - 1.0);       // exact: 24-bit x 24-bit
+        const double a = e24 * (0.5 * box + eps_b * D + e24 * D) * (1.0 + 1e-6) + eps_b * D +
+                         1e-30;
+        a2 += a * a;
+        ff.nbox[k] = -(float)box;                          // box is a float32 value
+        ff.inv[k] = (float)inv;
+    }
+    const double two_k = (double)(1u << Q.k);
+    const double mu = Q.scale * (sqrt(a2) + Q.d_max * (1.5 * e24 * 1.001 + Q.sqrt_err)) +
+                      e24 * Q.scale * Q.d_max * 1.001 + 1.0 / two_k + 1e-9;
+    const double m = ceil(1.25 * mu * two_k) + 1.0;
+    if (!(m >= 1.0) || !(2.0 * m + 1.0 < two_k / 8.0)) ok = false;
+    if (ok) {
+        const unsigned mk = (unsigned)m;
+        ff.madd = mk << (32 - Q.k);
+        ff.wthr = (2u * mk + 1u) << (32 - Q.k);
+    } else {
+        ff.madd = 0u;
+        ff.wthr = 0u;
+    }
+    Q.out[f] = ff;
+}
+
+template <bool EXCL, bool LOWER, bool AUDIT, int OCC>
+int launch_filter_o(mdh_ctx *c, const PairParams &P, dim3 grid)
+{
+    const size_t smem = filter_smem_bytes<4>(P.n_bins, P.fc.sb);
+    auto kern = rdf_filter_kernel<EXCL, LOWER, AUDIT, 4, OCC>;
+    MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    kern<<<grid, kThreads, smem, c->stream>>>(P);
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    return MDH_OK;
+}
+
+template <bool EXCL, bool LOWER>
+int launch_filter_a(mdh_ctx *c, const PairParams &P, dim3 grid, bool audit)
+{
+    if (audit) return launch_filter_o<EXCL, LOWER, true, 2>(c, P, grid);
+    return c->rdf.filter_occ == 3 ? launch_filter_o<EXCL, LOWER, false, 3>(c, P, grid)
+                                  : launch_filter_o<EXCL, LOWER, false, 2>(c, P, grid);
+}
+
+}  // namespace
+
+// Measured once per process (thread-safe enough: a race recomputes the same number).
+static double g_sqrt_err = -1.0;
+
+int rdf_filter_sqrt_error(mdh_ctx *c, double *err)
+{
+    if (g_sqrt_err < 0.0) {
+        unsigned long long *d = nullptr, h = 0;
+        MDH_CUDA(cudaMalloc(&d, sizeof(h)));
+        MDH_CUDA(cudaMemsetAsync(d, 0, sizeof(h), c->stream));
+        sqrt_error_kernel<<<(1u << 24) / 256, 256, 0, c->stream>>>(d);
+        MDH_CUDA(cudaGetLastError());
+        c->launches++;
+        MDH_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        MDH_CUDA(cudaStreamSynchronize(c->stream));
+        MDH_CUDA(cudaFree(d));
+        double e;
+        memcpy(&e, &h, sizeof(e));
+        g_sqrt_err = e;
+    }
+    *err = g_sqrt_err;
+    return MDH_OK;
+}
+
+// Decides whether a configuration can use the filter and fills R.fc.
+bool rdf_filter_configure(RdfState &R, const double *thr, double sqrt_err)
+{
+    R.filter_ok = false;
+    const int n_bins = R.n_bins;
+    int lg = 0;
+    while ((1 << lg) < n_bins + 2) ++lg;
+    const int k = std::min(16, 22 - lg);
+    if (k < 9) return false;
+    if (!(sqrt_err >= 0.0 && sqrt_err <= 1.0 / 4194304.0)) return false;   // 2^-22
+    const double scale = n_bins / (R.r_hi - R.r_lo);
+    // the thresholds must be the uniform edges the bound assumes (to 1e-9 of a bin)
+    for (int i = 0; i <= n_bins; ++i) {
+        const double e = R.r_lo + i / scale;
+        if (!(fabs(sqrt(thr[i]) - e) * scale <= 1e-9)) return false;
+    }
+    FilterConst fc;
+    fc.k = k;
+    fc.scale = (float)scale;
+    const double two_k = (double)(1 << k);
+    const double magic = 1.5 * (double)(1 << (23 - k));
+    // slot = bin + 1: one scratch slot below the range
+    const double off = nearbyint((1.0 - R.r_lo * scale) * two_k) / two_k;
+    fc.offm = (float)(magic + off);
+    if ((double)fc.offm != magic + off) return false;
+    const float mf = (float)magic;
+    memcpy(&fc.cbits, &mf, 4);
+    fc.span = (unsigned)(n_bins + 2) << k;
+    fc.lower = R.r_lo > 0.0;
+    int sb = 2;
+    while (sb > 0 && sizeof(unsigned) * kWarps * (((size_t)(n_bins + 2) << sb) + 32) > 36864)
+        --sb;
+    fc.sb = std::min(sb, k);
+    if (filter_smem_bytes<4>(n_bins, fc.sb) > 200 * 1024) return false;
+    R.fc = fc;
+    R.filter_ok = true;
+    return true;
+}
+
+// Builds the per-frame filter parameters of a batch (device side, asynchronous).
+int rdf_filter_prepare(mdh_ctx *c, int n_frames, double sqrt_err)
+{
+    RdfState &R = c->rdf;
+    if (int rc = R.filt.reserve(sizeof(FrameFilter) * n_frames)) return rc;
+    PrepareParams Q;
+    Q.boxes = R.boxes.as<FrameBox>();
+    Q.ext1 = R.ext1.as<unsigned>();
+    Q.ext2 = R.same ? Q.ext1 : R.ext2.as<unsigned>();
+    Q.out = R.filt.as<FrameFilter>();
+    Q.n_frames = n_frames;
+    Q.k = R.fc.k;
+    Q.scale = R.n_bins / (R.r_hi - R.r_lo);
+    Q.d_max = R.r_hi + 2.0 / Q.scale;
+    Q.sqrt_err = sqrt_err;
+    rdf_filter_prepare_kernel<<<(n_frames + 127) / 128, 128, 0, c->stream>>>(Q);
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    if (getenv("MDH_DEBUG_EXT")) {
+        MDH_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<unsigned> e1(6 * n_frames), e2(6 * n_frames);
+        std::vector<FrameFilter> ff(n_frames);
+        cudaMemcpy(e1.data(), Q.ext1, 24 * n_frames, cudaMemcpyDeviceToHost);
+        cudaMemcpy(e2.data(), Q.ext2, 24 * n_frames, cudaMemcpyDeviceToHost);
+        cudaMemcpy(ff.data(), Q.out, sizeof(FrameFilter) * n_frames, cudaMemcpyDeviceToHost);
+        for (int f = 0; f < std::min(n_frames, 2); ++f) {
+            fprintf(stderr, "frame %d ext1:", f);
+            for (int i = 0; i < 6; ++i) fprintf(stderr, " %08x(%g)", e1[6 * f + i], ext_unkey(e1[6 * f + i]));
+            fprintf(stderr, "\n  ext2:");
+            for (int i = 0; i < 6; ++i) fprintf(stderr, " %08x(%g)", e2[6 * f + i], ext_unkey(e2[6 * f + i]));
+            fprintf(stderr, "\n  madd %08x wthr %08x\n", ff[f].madd, ff[f].wthr);
+        }
+    }
+    return MDH_OK;
+}
+
+int rdf_filter_launch(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl, bool audit)
+{
+    if (excl)
+        return P.fc.lower ? launch_filter_a<true, true>(c, P, grid, audit)
+                          : launch_filter_a<true, false>(c, P, grid, audit);
+    return P.fc.lower ? launch_filter_a<false, true>(c, P, grid, audit)
+                      : launch_filter_a<false, false>(c, P, grid, audit);
+}

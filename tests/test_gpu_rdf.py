@@ -9,6 +9,8 @@ from test_oracle import RDF_CASES, rdf_groups, rdf_kwargs
 pytestmark = pytest.mark.gpu
 
 HISTS = ["warp_atomic", "lane_private"]
+# (hist, arith): the fp32-filter kernel, the exact fp64 kernel with either histogram
+VARIANTS = [("warp_atomic", "auto"), ("warp_atomic", "off"), ("lane_private", "off")]
 
 
 def _structure():
@@ -24,17 +26,19 @@ def _oracle():
 def test_kat_radial_histogram(golden):
     """The reference's own known-answer test (tests/test_analysis_structure.py:21-40)."""
     g = golden("kat_radial_histogram")
-    for hist in HISTS:
+    for hist, arith in VARIANTS + [("warp_atomic", "audit")]:
+        st = {}
         got = _structure().radial_histogram(
             g["origin"], g["neighbors"], int(g["n_bins"]), tuple(g["range"]), g["dims"],
-            hist=hist)
+            hist=hist, arith=arith, stats=st)
         assert np.array_equal(got, g["expected_from_norms"])
         assert np.array_equal(got, g["reference_counts"])
+        assert st["audit_violations"] == 0
 
 
-@pytest.mark.parametrize("hist", HISTS)
+@pytest.mark.parametrize("hist,arith", VARIANTS)
 @pytest.mark.parametrize("name", RDF_CASES)
-def test_class_matches_golden(golden, name, hist):
+def test_class_matches_golden(golden, name, hist, arith):
     g = golden(f"rdf_{name}")
     u = universe_from(g)
     ag1, ag2 = rdf_groups(u, g)
@@ -42,7 +46,10 @@ def test_class_matches_golden(golden, name, hist):
     if name == "dropx_density":
         kw["norm"] = "density"
     r = _structure().RadialDistributionFunction(
-        ag1, ag2, verbose=False, mode="allpairs", hist=hist, **kw).run()
+        ag1, ag2, verbose=False, mode="allpairs", hist=hist, arith=arith, **kw).run()
+    if arith == "auto":
+        # every golden configuration is eligible for the filter
+        assert r._filter_stats["eligible"] == 1
     assert r.results.counts.dtype == np.int64 or r.results.counts.dtype == int
     assert np.array_equal(r.results.counts, g["counts"])
     np.testing.assert_allclose(r.results.rdf, g["rdf"], rtol=1e-6)
@@ -76,8 +83,9 @@ def test_ragged_sizes(n1, n2):
     p1 = (rng.random((n1, 3)) * dims[:3]).astype(np.float32)
     p2 = (rng.random((n2, 3)) * dims[:3]).astype(np.float32)
     want = _oracle().radial_histogram(p1, p2, 47, (0.0, 3.7), dims)
-    for hist in HISTS:
-        got = _structure().radial_histogram(p1, p2, 47, (0.0, 3.7), dims, hist=hist)
+    for hist, arith in VARIANTS:
+        got = _structure().radial_histogram(p1, p2, 47, (0.0, 3.7), dims, hist=hist,
+                                            arith=arith)
         assert np.array_equal(got, want)
 
 
@@ -88,6 +96,89 @@ def test_many_bins_falls_back_to_warp_atomics():
     want = _oracle().radial_histogram(p, p, 3000, (0.0, 6.0), dims)
     got = _structure().radial_histogram(p, p, 3000, (0.0, 6.0), dims)
     assert np.array_equal(got, want)
+
+
+# ---- the fp32 filter (rdf_filter.cu): audited against the exact arithmetic ----------
+
+def _audit(p1, p2, n_bins, rng_, dims, exclusion=None):
+    """Runs the filter kernel with the audit on; returns (counts, stats)."""
+    st = {}
+    got = _structure().radial_histogram(p1, p2, n_bins, rng_, dims, exclusion=exclusion,
+                                        arith="audit", stats=st)
+    assert st["eligible"] == 1
+    assert st["audit_violations"] == 0, st
+    return got, st
+
+
+@pytest.mark.parametrize("n_bins,rng_", [(201, (0.0, 5.0)), (64, (0.0, 5.4)),
+                                         (100, (1.0, 4.5)), (1000, (0.0, 2.5)),
+                                         (3000, (0.0, 5.0)), (37, (2.25, 2.75))])
+def test_filter_audit_random(n_bins, rng_):
+    """Every pair the filter calls certain agrees with the fp64 arithmetic; counts are
+    the oracle's (uniform random coordinates, non-cubic box, ranges with r_lo > 0)."""
+    rng = np.random.default_rng(n_bins)
+    dims = np.array([10.75, 11.5, 12.25, 90, 90, 90], np.float32)
+    p1 = (rng.random((1500, 3)) * dims[:3]).astype(np.float32)
+    p2 = (rng.random((2100, 3)) * dims[:3]).astype(np.float32)
+    want = _oracle().radial_histogram(p1, p2, n_bins, rng_, dims)
+    got, st = _audit(p1, p2, n_bins, rng_, dims)
+    assert np.array_equal(got, want)
+    # the uncertainty window is a small part of a bin
+    assert st["audit_uncertain_pairs"] < 0.02 * len(p1) * len(p2)
+    off = _structure().radial_histogram(p1, p2, n_bins, rng_, dims, arith="off")
+    assert np.array_equal(off, want)
+
+
+def test_filter_audit_exclusions_and_unwrapped():
+    rng = np.random.default_rng(77)
+    dims = np.array([9.5, 9.5, 9.5, 90, 90, 90], np.float32)
+    # coordinates up to three boxes outside the cell
+    p = ((rng.random((1800, 3)) * 7 - 3) * dims[:3]).astype(np.float32)
+    want = _oracle().radial_histogram(p, p, 120, (0.0, 4.75), dims, exclusion=(3, 3))
+    got, _ = _audit(p, p, 120, (0.0, 4.75), dims, exclusion=(3, 3))
+    assert np.array_equal(got, want)
+
+
+def test_filter_adversarial_lattice_overflows_deferred_list():
+    """Simple-cubic lattice whose neighbour distances sit exactly on bin edges: most
+    pairs are uncertain, the deferred lists overflow into the inline path, and the
+    counts still equal the oracle's."""
+    n = 16
+    a = 0.5
+    g = np.arange(n, dtype=np.float32) * a
+    p = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    dims = np.array([n * a, n * a, n * a, 90, 90, 90], np.float32)
+    want = _oracle().radial_histogram(p, p, 16, (0.0, 4.0), dims)
+    st = {}
+    got = _structure().radial_histogram(p, p, 16, (0.0, 4.0), dims, stats=st)
+    assert np.array_equal(got, want)
+    assert st["eligible"] == 1 and st["deferred_entries"] > 0
+    assert st["inline_entries"] > 0
+    got, _ = _audit(p, p, 16, (0.0, 4.0), dims)
+    assert np.array_equal(got, want)
+
+
+def test_filter_declines_frames_far_outside_the_box():
+    """Coordinates millions of boxes away: the error bound is useless, the filter
+    kernel hands the frame to the exact kernel, counts stay the oracle's."""
+    rng = np.random.default_rng(3)
+    dims = np.array([6.0, 6.0, 6.0, 90, 90, 90], np.float32)
+    p = (rng.random((700, 3)) * 6).astype(np.float32)
+    q = p.copy()
+    q[::2, 0] += np.float32(6.0 * 2 ** 21)
+    want = _oracle().radial_histogram(q, q, 50, (0.0, 3.0), dims)
+    st = {}
+    got = _structure().radial_histogram(q, q, 50, (0.0, 3.0), dims, stats=st)
+    assert np.array_equal(got, want)
+    assert st["declined_frames"] == 1
+    # non-finite coordinates are declined as well (and never counted)
+    q = p.copy()
+    q[5] = np.nan
+    want = _oracle().radial_histogram(q, q, 50, (0.0, 3.0), dims)
+    st = {}
+    got = _structure().radial_histogram(q, q, 50, (0.0, 3.0), dims, stats=st)
+    assert np.array_equal(got, want)
+    assert st["declined_frames"] == 1
 
 
 def test_same_group_symmetry_and_self_pairs():
@@ -156,6 +247,13 @@ def test_config2_sized_frame_against_oracle():
     r = S.RadialDistributionFunction(cat, an, verbose=False, **kw).run()
     want = rp.rdf_run(u, cat, an, method="bruteforce", **kw)
     assert np.array_equal(r.results.counts, want["counts"])
+    assert r._filter_stats["eligible"] == 1 and r._filter_stats["declined_frames"] == 0
+    for arith in ("off", "audit"):
+        x = S.RadialDistributionFunction(cat, an, verbose=False, arith=arith, **kw).run()
+        assert np.array_equal(x.results.counts, want["counts"])
+        assert x._filter_stats["audit_violations"] == 0
+        if arith == "audit":      # about one pair in a thousand needs the fp64 path
+            assert 0 < x._filter_stats["audit_uncertain_pairs"] < 4e5
     np.testing.assert_allclose(r.results.rdf, want["rdf"], rtol=1e-6)
     # pair conservation at full range: every ordered pair is within L*sqrt(3)/2
     L = float(u.dimensions[0])
