@@ -580,10 +580,17 @@ class StructureFactor(GpuAnalysisBase):
         self.results.ssf /= self.n_frames * self._N
 
         if self._unique:
+            # same columns, same order and same mean as the reference's
+            # np.isclose(q, wavenumbers) loop; the memberships depend only on the
+            # wavevectors, so they are found once per instance, not once per run
+            if getattr(self, "_unique_members", None) is None:
+                self._unique_members = [
+                    np.flatnonzero(np.isclose(q, self._wavenumbers))
+                    for q in self.results.wavenumbers
+                ]
             self.results.ssf = np.hstack(
-                [self.results.ssf[:, np.isclose(q, self._wavenumbers)]
-                 .mean(axis=1, keepdims=True)
-                 for q in self.results.wavenumbers]
+                [self.results.ssf[:, cols].mean(axis=1, keepdims=True)
+                 for cols in self._unique_members]
             )
         if self._sort:
             order = np.argsort(self.results.wavenumbers)

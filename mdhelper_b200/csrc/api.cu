@@ -97,6 +97,51 @@ int KernelTimer::collect(cudaStream_t s, bool reset, double *ms, int64_t *n)
     return MDH_OK;
 }
 
+int HostStager::init()
+{
+    if (copy) return MDH_OK;
+    MDH_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        MDH_CUDA(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+        MDH_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    return MDH_OK;
+}
+
+int HostStager::acquire(int *slot)
+{
+    if (int rc = init()) return rc;
+    *slot = turn++ & 1;
+    if (used[*slot]) MDH_CUDA(cudaStreamWaitEvent(copy, done[*slot], 0));
+    return MDH_OK;
+}
+
+int HostStager::publish(cudaStream_t compute, int slot)
+{
+    MDH_CUDA(cudaEventRecord(ready[slot], copy));
+    MDH_CUDA(cudaStreamWaitEvent(compute, ready[slot], 0));
+    return MDH_OK;
+}
+
+int HostStager::retire(cudaStream_t compute, int slot)
+{
+    MDH_CUDA(cudaEventRecord(done[slot], compute));
+    used[slot] = true;
+    return MDH_OK;
+}
+
+void HostStager::destroy()
+{
+    for (int i = 0; i < 2; ++i) {
+        if (ready[i]) cudaEventDestroy(ready[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+        ready[i] = done[i] = nullptr;
+        used[i] = false;
+    }
+    if (copy) cudaStreamDestroy(copy);
+    copy = nullptr;
+}
+
 void KernelTimer::destroy()
 {
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
@@ -155,7 +200,10 @@ int mdh_ctx_destroy(mdh_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     RdfState &R = c->rdf;
-    R.thr.release(); R.counts.release(); R.raw1.release(); R.raw2.release();
+    if (c->stager.copy) cudaStreamSynchronize(c->stager.copy);
+    c->stager.destroy();
+    R.thr.release(); R.counts.release();
+    for (int i = 0; i < 2; ++i) { R.raw1[i].release(); R.raw2[i].release(); c->sq.raw[i].release(); }
     R.pk1.release(); R.pk2.release(); R.boxes.release();
     R.ext1.release(); R.ext2.release(); R.filt.release(); R.fstats.release();
     for (auto &b : R.cell) b.release();
@@ -163,7 +211,7 @@ int mdh_ctx_destroy(mdh_ctx *c)
     if (R.ev_boxes) cudaEventDestroy(R.ev_boxes);
     SqState &S = c->sq;
     S.qv.release(); S.items.release(); S.qidx.release(); S.d_pairs.release();
-    S.chunks.release(); S.raw.release(); S.tab.release(); S.rho.release(); S.ssf.release();
+    S.chunks.release(); S.tab.release(); S.rho.release(); S.ssf.release();
     c->t_rdf.destroy();
     c->t_sq.destroy();
     if (c->own_stream) cudaStreamDestroy(c->stream);

@@ -51,14 +51,16 @@ struct FrameBox {          // per frame, device side
 struct FrameFilter {
     float nbox[3];         // -box_k
     float inv[3];          // (float)(1.0 / box_k), the reference's float32 inverse box
-    unsigned madd;         // m << (32 - k): centres the uncertainty window on a bin edge
-    unsigned wthr;         // pair is uncertain iff (bits << (32 - k)) + madd < wthr;
+    float offm;            // 1.5 * 2^(23-k) + off + m * 2^-k: the bin coordinate is
+                           // shifted up by the window half-width m (units of 2^-k), so
+                           // the uncertainty window is [0, 2m] in its fraction bits
+    unsigned wlim;         // pair is uncertain iff (bits & (2^k - 1)) < wlim = 2m + 1;
                            // 0 = frame not eligible (the exact kernel handles it)
 };
 
 struct FilterConst {       // per configuration (host)
     float scale;           // (float)(n_bins / (r_hi - r_lo))
-    float offm;            // 1.5 * 2^(23-k) + off, off a multiple of 2^-k
+    double offbase;        // 1.5 * 2^(23-k) + off, off a multiple of 2^-k
     unsigned cbits;        // bits of the float (1.5 * 2^(23-k)): slot 0 ("below range")
     unsigned span;         // (n_bins + 2) << k: slots 0 .. n_bins + 1
     int k;                 // fraction bits of the fixed-point bin coordinate
@@ -74,7 +76,7 @@ struct RdfState {
     double r_lo = 0, r_hi = 0, thr_hi = 0;
     DevBuf thr;            // double[n_bins + 2]: thresholds, then +inf
     DevBuf counts;         // unsigned long long[n_bins]
-    DevBuf raw1, raw2;     // float[F][n][3] staging for host input
+    DevBuf raw1[2], raw2[2];  // float[F][n][3] staging for host input, one per stager slot
     DevBuf pk1, pk2;       // float4[F][npad]
     DevBuf boxes;          // FrameBox[F]
     DevBuf cell[10];       // cell-list scratch (grids, counts, starts, ranks, sorted, evals)
@@ -121,7 +123,7 @@ struct SqState {
     DevBuf d_pairs;        // int[n_pairs][2]
     DevBuf chunks;         // int4[n_chunks]: {start, end, rho_row, 0}
     int n_chunks = 0, chunk_len = 0;
-    DevBuf raw;            // float[F][n][3]
+    DevBuf raw[2];         // float[F][n][3] staging for host input, one per stager slot
     DevBuf tab;            // phase-factor tables of one group of frames
     DevBuf rho;            // double[F][n_rho][n_q][2]
     DevBuf ssf;            // double[n_pairs][n_q]
@@ -142,10 +144,30 @@ struct KernelTimer {
     void destroy();
 };
 
+// Host -> device staging of coordinate batches on a separate copy stream, two slots:
+// the copy of piece k + 1 runs while the kernels of piece k do (accumulate calls with
+// host pointers are cut into pieces for exactly this).
+struct HostStager {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr};   // slot filled (recorded on the copy stream)
+    cudaEvent_t done[2] = {nullptr, nullptr};    // slot consumed (recorded on the compute stream)
+    bool used[2] = {false, false};
+    int turn = 0;
+    int init();
+    // next slot; the copy stream waits until the kernels that read it last are done
+    int acquire(int *slot);
+    // compute stream waits for the copies queued into `slot` since acquire()
+    int publish(cudaStream_t compute, int slot);
+    // to be called after the kernels reading `slot` have been launched
+    int retire(cudaStream_t compute, int slot);
+    void destroy();
+};
+
 struct mdh_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    HostStager stager;
     int sm_count = 148;
     int64_t launches = 0;
     KernelTimer t_rdf, t_sq;
@@ -162,7 +184,7 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
 // rdf_filter.cu
 int rdf_filter_sqrt_error(mdh_ctx *c, double *err);
 bool rdf_filter_configure(RdfState &R, const double *thr, double sqrt_err);
-int rdf_filter_prepare(mdh_ctx *c, int n_frames, double sqrt_err);
+int rdf_filter_prepare(mdh_ctx *c, int f0, int n_frames, double sqrt_err);
 // sq.cu
 int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *goff,
                       int n_q, const double *wv, const int32_t *lat_n, const double *lat_b,

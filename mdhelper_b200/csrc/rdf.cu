@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_allpairs_kernel(const PairPar
     if (P.same) jt0 = max(jt0, it);       // upper triangle of tile pairs
     if (jt0 >= jt1) return;
     // frames the fp32-filter kernel (rdf_filter.cu) has taken are not done again
-    if (P.filt != nullptr && P.filt[frame].wthr != 0u) return;
+    if (P.filt != nullptr && P.filt[frame].wlim != 0u) return;
 
     const int n_bins = P.n_bins;
     const int n_words = priv_words(n_bins);
@@ -222,7 +222,9 @@ int launch_allpairs_dyn(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl, b
 
 // ---- host side ------------------------------------------------------------------
 
-int rdf_cells_accumulate(mdh_ctx *c, int n_frames);   // rdf_cells.cu
+int rdf_cells_accumulate(mdh_ctx *c, int f0, int n_frames);   // rdf_cells.cu
+static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const float *pos2,
+                                int64_t s2, int location, int f0, int n_frames, int mode);
 int rdf_filter_launch(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl,
                       bool audit);                     // rdf_filter.cu
 
@@ -269,7 +271,7 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
         if (const char *p = strstr(t, "ipt=")) ipt = atoi(p + 4) == 4 ? 4 : 2;
         if (const char *p = strstr(t, "fast=")) allow_fast = atoi(p + 5) != 0;
         if (const char *p = strstr(t, "filter=")) allow_filter = atoi(p + 7) != 0;
-        if (const char *p = strstr(t, "occ=")) R.filter_occ = atoi(p + 4) == 3 ? 3 : 2;
+        if (const char *p = strstr(t, "occ=")) R.filter_occ = std::min(4, std::max(2, atoi(p + 4)));
     }
     // measured on B200 (profiles/): per-warp shared-memory atomics beat the
     // lane-private byte counters at every bin count tried, and need less memory
@@ -316,7 +318,7 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
     // fp32 filter: needs the 4-particle tile, the shared-atomic histogram layout and
     // uniform edges; the approximation error of MUFU.SQRT is measured, not assumed
     R.filter_ok = false;
-    if (allow_filter && ipt == 4 && hist == MDH_HIST_WARP_ATOMIC) {
+    if (allow_filter && hist == MDH_HIST_WARP_ATOMIC) {
         if (int rc = rdf_filter_sqrt_error(c, &g_sqrt_err_cached)) return rc;
         rdf_filter_configure(R, thr, g_sqrt_err_cached);
     }
@@ -324,25 +326,30 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
     return MDH_OK;
 }
 
+// host input: the copy into `raw` is queued on the stager's copy stream (the caller
+// brackets the group copies of a piece with stager.acquire / publish)
 static int rdf_upload_group(mdh_ctx *c, const float *pos, int64_t stride, int location,
                             int64_t n, int64_t npad, int64_t excl, int n_frames,
-                            DevBuf &raw, DevBuf &pk, DevBuf *ext)
+                            DevBuf &raw, DevBuf &pk, DevBuf *ext, bool copy_only)
 {
     RdfState &R = c->rdf;
     MDH_REQUIRE(pos != nullptr, MDH_EINVAL, "rdf: coordinate pointer is NULL");
     MDH_REQUIRE(stride >= 3 * n, MDH_EINVAL, "rdf: frame_stride (%lld) < 3*n (%lld)",
                 (long long)stride, (long long)(3 * n));
-    if (int rc = pk.reserve(sizeof(float4) * npad * n_frames)) return rc;
     const float *dsrc = pos;
     int64_t dstride = stride;
     if (location == MDH_HOST) {
-        if (int rc = raw.reserve(sizeof(float) * 3 * n * n_frames)) return rc;
-        MDH_CUDA(cudaMemcpy2DAsync(raw.p, sizeof(float) * 3 * n, pos, sizeof(float) * stride,
-                                   sizeof(float) * 3 * n, n_frames, cudaMemcpyHostToDevice,
-                                   c->stream));
+        if (copy_only) {
+            if (int rc = raw.reserve(sizeof(float) * 3 * n * n_frames)) return rc;
+            MDH_CUDA(cudaMemcpy2DAsync(raw.p, sizeof(float) * 3 * n, pos,
+                                       sizeof(float) * stride, sizeof(float) * 3 * n, n_frames,
+                                       cudaMemcpyHostToDevice, c->stager.copy));
+            return MDH_OK;
+        }
         dsrc = raw.as<float>();
         dstride = 3 * n;
     }
+    if (int rc = pk.reserve(sizeof(float4) * npad * n_frames)) return rc;
     unsigned *d_ext = nullptr;
     if (ext) {
         // per frame {min x, y, z, max x, y, z} as order-preserving keys
@@ -403,9 +410,6 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
                              cudaMemcpyHostToDevice, c->stream));
     MDH_CUDA(cudaEventRecord(R.ev_boxes, c->stream));
 
-    const int tile = kThreads * R.ipt;
-    const int64_t pad1 = (R.n1 + tile - 1) / tile * tile;
-    const int64_t pad2 = (R.n2 + tile - 1) / tile * tile;
     int mode = R.mode;
     if (mode == MDH_RDF_AUTO) {
         // cells pay off when the cut-off sphere is a small part of the box
@@ -414,28 +418,71 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
                               (double)R.n1 * (double)R.n2 >= 4e6 && R.drop_axis < 0;
         mode = cells_ok ? MDH_RDF_CELLS : MDH_RDF_ALLPAIRS;
     }
+    // Host input is cut into up to four pieces so that the copy of one piece (copy
+    // stream) overlaps the kernels of the previous one (compute stream).
+    int piece = n_frames;
+    if (location == MDH_HOST) {
+        // pieces of at least ~12 MB: shorter ones cost more in kernel tails than the
+        // hidden copy time is worth
+        const double bytes = 12.0 * (double)(R.n1 + (R.same ? 0 : R.n2)) * n_frames;
+        const int n_pieces = (int)std::min(4.0, std::max(1.0, floor(bytes / 12e6)));
+        piece = (n_frames + n_pieces - 1) / n_pieces;
+    }
+    for (int f0 = 0; f0 < n_frames; f0 += piece) {
+        const int nf = std::min(piece, n_frames - f0);
+        if (int rc = rdf_accumulate_piece(c, pos1 + (int64_t)f0 * s1, s1,
+                                          pos2 ? pos2 + (int64_t)f0 * s2 : nullptr, s2,
+                                          location, f0, nf, mode)) return rc;
+    }
+    return MDH_OK;
+}
+
+// One piece of an accumulate call: frames [f0, f0 + n_frames) of the batch whose boxes
+// are already on the device (R.boxes / R.h_boxes).
+static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const float *pos2,
+                                int64_t s2, int location, int f0, int n_frames, int mode)
+{
+    RdfState &R = c->rdf;
+    const int tile = kThreads * R.ipt;
+    const int64_t pad1 = (R.n1 + tile - 1) / tile * tile;
+    const int64_t pad2 = (R.n2 + tile - 1) / tile * tile;
     const bool use_filter = mode == MDH_RDF_ALLPAIRS && R.filter_ok &&
                             R.filter_mode != MDH_FILTER_OFF;
 
+    int slot = 0;
+    if (location == MDH_HOST) {
+        if (int rc = c->stager.acquire(&slot)) return rc;
+        if (int rc = rdf_upload_group(c, pos1, s1, location, R.n1, pad1, R.excl1, n_frames,
+                                      R.raw1[slot], R.pk1, nullptr, true)) return rc;
+        if (!R.same)
+            if (int rc = rdf_upload_group(c, pos2, s2, location, R.n2, pad2, R.excl2, n_frames,
+                                          R.raw2[slot], R.pk2, nullptr, true)) return rc;
+        if (int rc = c->stager.publish(c->stream, slot)) return rc;
+    }
     if (int rc = rdf_upload_group(c, pos1, s1, location, R.n1, pad1, R.excl1, n_frames,
-                                  R.raw1, R.pk1, use_filter ? &R.ext1 : nullptr)) return rc;
+                                  R.raw1[slot], R.pk1, use_filter ? &R.ext1 : nullptr, false))
+        return rc;
     if (!R.same)
         if (int rc = rdf_upload_group(c, pos2, s2, location, R.n2, pad2, R.excl2, n_frames,
-                                      R.raw2, R.pk2, use_filter ? &R.ext2 : nullptr)) return rc;
+                                      R.raw2[slot], R.pk2, use_filter ? &R.ext2 : nullptr,
+                                      false)) return rc;
+    // the raw staging slot has been consumed by the pack kernels
+    if (location == MDH_HOST)
+        if (int rc = c->stager.retire(c->stream, slot)) return rc;
     if (use_filter)
-        if (int rc = rdf_filter_prepare(c, n_frames, g_sqrt_err_cached)) return rc;
+        if (int rc = rdf_filter_prepare(c, f0, n_frames, g_sqrt_err_cached)) return rc;
 
     if (int rc = c->t_rdf.begin(c->stream)) return rc;
 
     if (mode == MDH_RDF_CELLS) {
-        if (int rc = rdf_cells_accumulate(c, n_frames)) return rc;
+        if (int rc = rdf_cells_accumulate(c, f0, n_frames)) return rc;
     } else {
         PairParams P;
         P.p1 = R.pk1.as<float4>();
         P.p2 = R.same ? P.p1 : R.pk2.as<float4>();
         P.pad1 = pad1; P.pad2 = R.same ? pad1 : pad2;
         P.n1 = (int)R.n1; P.n2 = (int)R.n2;
-        P.boxes = R.boxes.as<FrameBox>();
+        P.boxes = R.boxes.as<FrameBox>() + f0;
         P.thr = R.thr.as<double>();
         P.n_bins = R.n_bins;
         P.guess = rdf_bin_guess(R);

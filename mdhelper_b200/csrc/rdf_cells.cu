@@ -311,7 +311,7 @@ int sort_group(mdh_ctx *c, const float4 *pk, int64_t npad, int n, int n_frames,
 
 // Called from rdf_accumulate_impl after the packed float4 arrays and the FrameBox
 // array of the batch are on the device.
-int rdf_cells_accumulate(mdh_ctx *c, int n_frames)
+int rdf_cells_accumulate(mdh_ctx *c, int f0, int n_frames)
 {
     RdfState &R = c->rdf;
     MDH_REQUIRE(R.drop_axis < 0, MDH_EINVAL, "rdf: cell-list mode does not support drop_axis");
@@ -322,7 +322,7 @@ int rdf_cells_accumulate(mdh_ctx *c, int n_frames)
         CellGrid &g = grids[f];
         double ncell = 1;
         for (int k = 0; k < 3; ++k) {
-            g.box[k] = R.h_boxes[f].box[k];
+            g.box[k] = R.h_boxes[f0 + f].box[k];
             int nc = (int)floor(g.box[k] / r_cut);
             MDH_REQUIRE(nc >= 3, MDH_EINVAL,
                         "rdf: cell-list mode needs box edge >= 3*r_max (frame %d axis %d)", f, k);
@@ -345,9 +345,10 @@ int rdf_cells_accumulate(mdh_ctx *c, int n_frames)
     const int cstride = ncell_max + 1;
     DevBuf &d_grids = R.cell[0];
     if (int rc = d_grids.reserve(sizeof(CellGrid) * n_frames)) return rc;
+    // pageable source: the runtime stages it before returning, so the local vector
+    // may go out of scope while the copy is still queued
     MDH_CUDA(cudaMemcpyAsync(d_grids.p, grids.data(), sizeof(CellGrid) * n_frames,
                              cudaMemcpyHostToDevice, c->stream));
-    MDH_CUDA(cudaStreamSynchronize(c->stream));      // grids is a local
 
     const int tile = kThreads * R.ipt;
     const int64_t pad1 = (R.n1 + tile - 1) / tile * tile;
@@ -367,7 +368,7 @@ int rdf_cells_accumulate(mdh_ctx *c, int n_frames)
     P.start2 = R.same ? R.cell[2].as<int>() : R.cell[6].as<int>();
     P.cstride = cstride;
     P.grids = d_grids.as<CellGrid>();
-    P.boxes = R.boxes.as<FrameBox>();
+    P.boxes = R.boxes.as<FrameBox>() + f0;
     P.thr = R.thr.as<double>();
     P.n_bins = R.n_bins;
     P.guess = rdf_bin_guess(R);

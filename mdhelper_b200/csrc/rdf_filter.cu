@@ -17,7 +17,9 @@
 // then d2 = mx*mx + my*my + mz*mz (fma chain), s = sqrt.approx(d2), and the bin
 // coordinate as a fixed-point number in the mantissa of one more fma:
 //     bits(fma(s, scale, 1.5*2^(23-k) + off)) - bits(1.5*2^(23-k)) = slot * 2^k + frac
-// slot = bin + 1 (slot 0: below the range, slot n_bins + 1: above).
+// slot = bin + 1 (slot 0: below the range, slot n_bins + 1: above).  The coordinate is
+// additionally shifted up by the window half-width m, so that "within m of a bin
+// edge" reads "fraction bits <= 2m" (one AND + one MIN per pair on the ALU pipe).
 //
 // Error bound (rdf_filter_prepare_kernel, per frame, in bin units) -- see DESIGN.md
 // section 4.1b for the derivation.  With eps_b = |box*inv - 1| (the reference's
@@ -149,14 +151,14 @@ __device__ __noinline__ void filter_fix(const PairParams &P, int frame, int it, 
         const float4 a0 = f1[min(i0, P.n1 - 1)], a1 = f1[min(i1, P.n1 - 1)];
         unsigned uu[2];
         filter_eval2<LOWER>(pk2(-a0.x, -a1.x), pk2(-a0.y, -a1.y), pk2(-a0.z, -a1.z), pj, ff,
-                            fc.scale, fc.offm, fc.cbits, uu[0], uu[1]);
+                            fc.scale, ff.offm, fc.cbits, uu[0], uu[1]);
         for (int h = 0; h < 2; ++h) {
             const int i = h ? i1 : i0;
             const float4 a = h ? a1 : a0;
             const unsigned u = uu[h];
             if (i >= P.n1) continue;
             if (!(u < span_l)) continue;
-            if (!((u << (32 - fc.k)) + ff.madd < ff.wthr)) continue;
+            if (!((u & ((1u << fc.k) - 1u)) < ff.wlim)) continue;
             if (EXCL && __float_as_int(a.w) == __float_as_int(pj.w)) continue;
             const unsigned word = (LOWER ? u : u - fc.cbits) >> (fc.k - fc.sb);
             const double d2 = pair_d2(a.x, a.y, a.z, pj, fb);
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, OCC)
     constexpr int TILE = kThreads * IPT;
     const int frame = blockIdx.y;
     const FrameFilter ff = P.filt[frame];
-    if (ff.wthr == 0u) {                  // left to the exact kernel (whole block)
+    if (ff.wlim == 0u) {                  // left to the exact kernel (whole block)
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.fstats[4], 1ull);
         return;
     }
@@ -238,10 +240,8 @@ __global__ void __launch_bounds__(kThreads, OCC)
     // every pair issues one unconditional RED; pairs outside the range -- about half
     // of them when the range ends at L/2 -- land here and never contend
     const unsigned trash_w = (span_l >> shift) + (unsigned)lane;
-    // opaque to the compiler so that the window test is one IMAD, not shift + add
-    unsigned fmul;
-    asm volatile("mov.u32 %0, %1;" : "=r"(fmul) : "r"(1u << (32 - fc.k)));
-    const float scale = fc.scale, offm = fc.offm;
+    const unsigned fmask = (1u << fc.k) - 1u;      // fraction bits of the bin coordinate
+    const float scale = fc.scale, offm = ff.offm;
 
     auto stage_tile = [&](int jt, int buf) {
         const float4 *src = f2 + (int64_t)jt * TILE;
@@ -272,18 +272,21 @@ __global__ void __launch_bounds__(kThreads, OCC)
         const int jn = min(TILE, P.n2 - jt * TILE);
         const float4 *tile = sJ + buf * TILE;
 
-        // NR tile rows against the IPT particles of this thread: all the arithmetic
-        // and the REDs first (NR * IPT independent chains for the scheduler), then one
-        // rarely taken branch for the uncertain pairs of the whole group
-        auto rows = [&](const float4 *pj, int jj, auto nr_tag) {
+        // Stage A: the packed fp32 arithmetic of NR tile rows against the IPT particles
+        // of this thread -> fixed-point bin coordinates (FMA pipe).
+        auto stage_a = [&](const float4 *pj, unsigned (*uu)[IPT], auto nr_tag) {
             constexpr int NR = decltype(nr_tag)::value;
-            unsigned uu[NR][IPT];
 #pragma unroll
             for (int r = 0; r < NR; ++r)
 #pragma unroll
                 for (int ip = 0; ip < IPT / 2; ++ip)
                     filter_eval2<LOWER>(nx[ip], ny[ip], nz[ip], pj[r], ff, scale, offm, fc.cbits,
                                         uu[r][2 * ip], uu[r][2 * ip + 1]);
+        };
+        // Stage B: histogram updates and the uncertainty test of NR rows (ALU pipe,
+        // LSU), then one rarely taken branch for the uncertain pairs of the group.
+        auto stage_b = [&](const float4 *pj, const unsigned (*uu)[IPT], int jj, auto nr_tag) {
+            constexpr int NR = decltype(nr_tag)::value;
             unsigned vmin[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
@@ -291,13 +294,13 @@ __global__ void __launch_bounds__(kThreads, OCC)
 #pragma unroll
                 for (int ii = 0; ii < IPT; ++ii) {
                     const unsigned u = uu[r][ii];
-                    // uncertain iff u * fmul + madd < wthr; keep the smallest per row
-                    vmin[r] = min(vmin[r], u * fmul + ff.madd);
+                    // uncertain iff the fraction bits are below wlim; keep the smallest
+                    vmin[r] = min(vmin[r], u & fmask);
                     unsigned w = min(u >> shift, trash_w);
                     if (EXCL && gi[ii] == __float_as_int(pj[r].w)) w = trash_w;
                     red_shared_hot(hbase + (w << 2), wi[ii]);
                     if (AUDIT) {
-                        const bool unc = u * fmul + ff.madd < ff.wthr;
+                        const bool unc = (u & fmask) < ff.wlim;
                         const bool in = u < span_l;
                         const double d2 =
                             pair_d2(xi[ii], yi[ii], zi[ii], pj[r], P.boxes[frame]);
@@ -317,10 +320,10 @@ __global__ void __launch_bounds__(kThreads, OCC)
             unsigned vall = vmin[0];
 #pragma unroll
             for (int r = 1; r < NR; ++r) vall = min(vall, vmin[r]);
-            if (vall < ff.wthr) {
+            if (vall < ff.wlim) {
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
-                    if (vmin[r] < ff.wthr) {
+                    if (vmin[r] < ff.wlim) {
                         const unsigned entry = ((unsigned)tid << 16) | (unsigned)(jj + r);
                         const unsigned idx = atomicAdd(sCount, 1u);
                         if (idx < (unsigned)kListCap) sList[idx] = entry;
@@ -331,18 +334,37 @@ __global__ void __launch_bounds__(kThreads, OCC)
                 }
             }
         };
-        // two rows per iteration, the next two fetched before the arithmetic of the
-        // current ones (rows up to TILE - 1 always exist: the packed arrays are padded)
+        // Software pipeline over pairs of rows: stage B of rows (jj, jj+1) is issued
+        // together with stage A of rows (jj+2, jj+3), so that every warp offers the
+        // scheduler FMA-pipe and ALU-pipe work at the same time; the rows after those
+        // are fetched from shared memory one more iteration ahead.  Rows up to
+        // TILE - 1 always exist (the packed arrays are padded), so the last iteration
+        // may evaluate two rows nobody uses.
+        using two = std::integral_constant<int, 2>;
         const int jn2 = jn & ~1;
-        float4 nxt[2] = {tile[0], tile[1]};
+        unsigned ua[2][IPT];
+        float4 cur[2] = {tile[0], tile[1]};
+        float4 nxt[2] = {tile[2], tile[3]};
+        if (jn2 > 0) stage_a(cur, ua, two());
         for (int jj = 0; jj < jn2; jj += 2) {
-            const float4 cur[2] = {nxt[0], nxt[1]};
-            const int jnext = min(jj + 2, TILE - 2);
-            nxt[0] = tile[jnext];
-            nxt[1] = tile[jnext + 1];
-            rows(cur, jj, std::integral_constant<int, 2>());
+            unsigned ub[2][IPT];
+            const float4 nn[2] = {nxt[0], nxt[1]};
+            const int jfetch = min(jj + 4, TILE - 2);
+            nxt[0] = tile[jfetch];
+            nxt[1] = tile[jfetch + 1];
+            stage_a(nn, ub, two());
+            stage_b(cur, ua, jj, two());
+            cur[0] = nn[0]; cur[1] = nn[1];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int ii = 0; ii < IPT; ++ii) ua[r][ii] = ub[r][ii];
         }
-        if (jn2 < jn) rows(tile + jn2, jn2, std::integral_constant<int, 1>());
+        if (jn2 < jn) {
+            unsigned u1[1][IPT];
+            stage_a(tile + jn2, u1, std::integral_constant<int, 1>());
+            stage_b(tile + jn2, u1, jn2, std::integral_constant<int, 1>());
+        }
         __syncthreads();
 
         // drain the deferred entries of this tile while it is still in shared memory
@@ -399,6 +421,7 @@ struct PrepareParams {
     double scale;                    // n_bins / (r_hi - r_lo)
     double d_max;                    // largest distance that can still be binned
     double sqrt_err;
+    double offbase;                  // FilterConst::offbase
 };
 
 __global__ void rdf_filter_prepare_kernel(const PrepareParams Q)
@@ -435,21 +458,21 @@ __global__ void rdf_filter_prepare_kernel(const PrepareParams Q)
     const double m = ceil(1.25 * mu * two_k) + 1.0;
     if (!(m >= 1.0) || !(2.0 * m + 1.0 < two_k / 8.0)) ok = false;
     if (ok) {
-        const unsigned mk = (unsigned)m;
-        ff.madd = mk << (32 - Q.k);
-        ff.wthr = (2u * mk + 1u) << (32 - Q.k);
+        // shifted coordinate: exactly representable (a multiple of 2^-k in the binade)
+        ff.offm = (float)(Q.offbase + m / two_k);
+        ff.wlim = 2u * (unsigned)m + 1u;
     } else {
-        ff.madd = 0u;
-        ff.wthr = 0u;
+        ff.offm = 0.f;
+        ff.wlim = 0u;
     }
     Q.out[f] = ff;
 }
 
-template <bool EXCL, bool LOWER, bool AUDIT, int OCC>
+template <bool EXCL, bool LOWER, bool AUDIT, int IPT, int OCC>
 int launch_filter_o(mdh_ctx *c, const PairParams &P, dim3 grid)
 {
-    const size_t smem = filter_smem_bytes<4>(P.n_bins, P.fc.sb);
-    auto kern = rdf_filter_kernel<EXCL, LOWER, AUDIT, 4, OCC>;
+    const size_t smem = filter_smem_bytes<IPT>(P.n_bins, P.fc.sb);
+    auto kern = rdf_filter_kernel<EXCL, LOWER, AUDIT, IPT, OCC>;
     MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     kern<<<grid, kThreads, smem, c->stream>>>(P);
@@ -461,9 +484,16 @@ int launch_filter_o(mdh_ctx *c, const PairParams &P, dim3 grid)
 template <bool EXCL, bool LOWER>
 int launch_filter_a(mdh_ctx *c, const PairParams &P, dim3 grid, bool audit)
 {
-    if (audit) return launch_filter_o<EXCL, LOWER, true, 2>(c, P, grid);
-    return c->rdf.filter_occ == 3 ? launch_filter_o<EXCL, LOWER, false, 3>(c, P, grid)
-                                  : launch_filter_o<EXCL, LOWER, false, 2>(c, P, grid);
+    const int occ = c->rdf.filter_occ;
+    if (c->rdf.ipt == 2) {
+        if (audit) return launch_filter_o<EXCL, LOWER, true, 2, 2>(c, P, grid);
+        return occ == 4   ? launch_filter_o<EXCL, LOWER, false, 2, 4>(c, P, grid)
+               : occ == 3 ? launch_filter_o<EXCL, LOWER, false, 2, 3>(c, P, grid)
+                          : launch_filter_o<EXCL, LOWER, false, 2, 2>(c, P, grid);
+    }
+    if (audit) return launch_filter_o<EXCL, LOWER, true, 4, 2>(c, P, grid);
+    return occ == 3 ? launch_filter_o<EXCL, LOWER, false, 4, 3>(c, P, grid)
+                    : launch_filter_o<EXCL, LOWER, false, 4, 2>(c, P, grid);
 }
 
 }  // namespace
@@ -514,29 +544,35 @@ bool rdf_filter_configure(RdfState &R, const double *thr, double sqrt_err)
     const double magic = 1.5 * (double)(1 << (23 - k));
     // slot = bin + 1: one scratch slot below the range
     const double off = nearbyint((1.0 - R.r_lo * scale) * two_k) / two_k;
-    fc.offm = (float)(magic + off);
-    if ((double)fc.offm != magic + off) return false;
+    fc.offbase = magic + off;
+    // representable with the largest shift added, and still below the next binade
+    if ((double)(float)fc.offbase != fc.offbase ||
+        (double)(float)(fc.offbase + 0.125) != fc.offbase + 0.125) return false;
     const float mf = (float)magic;
     memcpy(&fc.cbits, &mf, 4);
     fc.span = (unsigned)(n_bins + 2) << k;
     fc.lower = R.r_lo > 0.0;
+    // sub-bins: as many as the shared memory of R.filter_occ resident blocks allows
+    const size_t budget = (size_t)(224 * 1024) / R.filter_occ - 1024;
+    auto need = [&](int sb) {
+        return R.ipt == 2 ? filter_smem_bytes<2>(n_bins, sb) : filter_smem_bytes<4>(n_bins, sb);
+    };
     int sb = 2;
-    while (sb > 0 && sizeof(unsigned) * kWarps * (((size_t)(n_bins + 2) << sb) + 32) > 36864)
-        --sb;
+    while (sb > 0 && need(sb) > budget) --sb;
     fc.sb = std::min(sb, k);
-    if (filter_smem_bytes<4>(n_bins, fc.sb) > 200 * 1024) return false;
+    if (need(fc.sb) > 200 * 1024) return false;
     R.fc = fc;
     R.filter_ok = true;
     return true;
 }
 
 // Builds the per-frame filter parameters of a batch (device side, asynchronous).
-int rdf_filter_prepare(mdh_ctx *c, int n_frames, double sqrt_err)
+int rdf_filter_prepare(mdh_ctx *c, int f0, int n_frames, double sqrt_err)
 {
     RdfState &R = c->rdf;
     if (int rc = R.filt.reserve(sizeof(FrameFilter) * n_frames)) return rc;
     PrepareParams Q;
-    Q.boxes = R.boxes.as<FrameBox>();
+    Q.boxes = R.boxes.as<FrameBox>() + f0;
     Q.ext1 = R.ext1.as<unsigned>();
     Q.ext2 = R.same ? Q.ext1 : R.ext2.as<unsigned>();
     Q.out = R.filt.as<FrameFilter>();
@@ -545,6 +581,7 @@ int rdf_filter_prepare(mdh_ctx *c, int n_frames, double sqrt_err)
     Q.scale = R.n_bins / (R.r_hi - R.r_lo);
     Q.d_max = R.r_hi + 2.0 / Q.scale;
     Q.sqrt_err = sqrt_err;
+    Q.offbase = R.fc.offbase;
     rdf_filter_prepare_kernel<<<(n_frames + 127) / 128, 128, 0, c->stream>>>(Q);
     MDH_CUDA(cudaGetLastError());
     c->launches++;
@@ -560,7 +597,7 @@ int rdf_filter_prepare(mdh_ctx *c, int n_frames, double sqrt_err)
             for (int i = 0; i < 6; ++i) fprintf(stderr, " %08x(%g)", e1[6 * f + i], ext_unkey(e1[6 * f + i]));
             fprintf(stderr, "\n  ext2:");
             for (int i = 0; i < 6; ++i) fprintf(stderr, " %08x(%g)", e2[6 * f + i], ext_unkey(e2[6 * f + i]));
-            fprintf(stderr, "\n  madd %08x wthr %08x\n", ff[f].madd, ff[f].wthr);
+            fprintf(stderr, "\n  offm %.9g wlim %u\n", ff[f].offm, ff[f].wlim);
         }
     }
     return MDH_OK;

@@ -39,6 +39,7 @@ constexpr int kSqThreads = 256;
 #define MDH_SQ_KPS 32
 #endif
 constexpr int kPS = MDH_SQ_KPS;    // particles per shared-memory sub-chunk
+constexpr int kSqProducers = 64;   // table-building threads at the end of every block
 
 template <typename T> struct C2;
 template <> struct C2<double> { using type = double2; };
@@ -54,35 +55,44 @@ struct LatticeParams {
     int n_rho, n_q;
     double b[3];
     int nmax[3];                   // largest n per axis
-    int offy, offz, nt;            // table layout per particle
+    int offy, offz, nt;            // table layout per particle (in table elements)
 };
 
 // One sub-chunk of particles into the register accumulators.  The per-thread
 // tile is kSqTM columns x R z-terms (R even, warp-uniform), i.e. per particle
-// 2*kSqTM + R shared-memory loads feed 4*kSqTM*(R + 1) FP64 FMAs -- the kernel
-// is bounded by the FP64 pipe and the shared-memory pipe together, and the 2 x 8
-// tile is what balances them.
+// 2*kSqTM complex loads of E_x / E_y and R of E_z feed 4*kSqTM*(R + 1) FP64 FMAs.
+//
+// Table row of one particle (elements of T): E_x real parts, E_x imaginary parts,
+// E_y real, E_y imaginary -- split because every lane reads a different n: 8-byte
+// loads of 17 distinct entries are bank-conflict free per half-warp, whereas 16-byte
+// (re, im) entries put n and n + 8 in the same banks and cost ~3x the wavefronts --
+// then E_z as interleaved (re, im) pairs, which are warp-uniform (one broadcast
+// LDS.128 each).
 template <typename T, int R>
-__device__ __forceinline__ void sq_accumulate_subchunk(const typename C2<T>::type *tab, int nt,
-                                                       const int (&ix)[kSqTM],
-                                                       const int (&iy)[kSqTM], int iz,
+__device__ __forceinline__ void sq_accumulate_subchunk(const T *tab, int nt,
+                                                       const int (&ixr)[kSqTM],
+                                                       const int (&ixi)[kSqTM],
+                                                       const int (&iyr)[kSqTM],
+                                                       const int (&iyi)[kSqTM], int iz,
                                                        T (&acc_re)[kSqTM][kSqTN],
                                                        T (&acc_im)[kSqTM][kSqTN])
 {
     using T2 = typename C2<T>::type;
 #pragma unroll 1
     for (int p = 0; p < kPS; ++p) {
-        const T2 *row = tab + p * nt;
+        const T *row = tab + p * nt;
         T ar[kSqTM], ai[kSqTM];
 #pragma unroll
         for (int m = 0; m < kSqTM; ++m) {
-            const T2 ex = row[ix[m]], ey = row[iy[m]];
-            ar[m] = ex.x * ey.x - ex.y * ey.y;
-            ai[m] = ex.x * ey.y + ex.y * ey.x;
+            const T exr = row[ixr[m]], exi = row[ixi[m]];
+            const T eyr = row[iyr[m]], eyi = row[iyi[m]];
+            ar[m] = exr * eyr - exi * eyi;
+            ai[m] = exr * eyi + exi * eyr;
         }
+        const T2 *zrow = reinterpret_cast<const T2 *>(row + iz);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const T2 ez = row[iz + r];
+            const T2 ez = zrow[r];
 #pragma unroll
             for (int m = 0; m < kSqTM; ++m) {
                 acc_re[m][r] += ar[m] * ez.x;
@@ -94,17 +104,59 @@ __device__ __forceinline__ void sq_accumulate_subchunk(const typename C2<T>::typ
     }
 }
 
+// Block = S.block consumer threads (one work item each) followed by kSqProducers
+// producer threads.  The producers build the phase-factor tables of sub-chunk s + 1
+// in the second table buffer while the consumers accumulate sub-chunk s: one barrier
+// per sub-chunk, and nobody waits for the sincos / recurrence chains (the single-buffer
+// version spent 2 of 3 stall cycles at its barriers).
 template <typename T>
 __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const LatticeParams P)
 {
     using T2 = typename C2<T>::type;
     extern __shared__ __align__(16) unsigned char smem[];
-    T2 *sTab = reinterpret_cast<T2 *>(smem);         // [kPS][nt]
+    const int nt = P.nt;                             // elements of T per particle
+    T *sTab = reinterpret_cast<T *>(smem);           // [2][kPS][nt]
 
     const int tid = threadIdx.x;
+    const int n_cons = (int)blockDim.x - kSqProducers;
+    const bool producer = tid >= n_cons;
     const int frame = blockIdx.z;
     const int4 chunk = P.chunks[blockIdx.y];
-    const int item_index = blockIdx.x * blockDim.x + tid;
+    const float *pos = P.raw + (int64_t)frame * P.stride;
+
+    // tables of particles [p0, p0 + np): task <-> (particle, axis); one fp64 sincos,
+    // then E(n+1) = E(n) E(1); rows past np are zero so that the consumers never test
+    auto build = [&](T *tab, int p0) {
+        const int np = min(kPS, chunk.y - p0);
+        for (int task = tid - n_cons; task < kPS * 3; task += kSqProducers) {
+            const int p = task / 3, a = task - 3 * p;
+            const int nm = P.nmax[a];
+            // real parts at re[n * st], imaginary parts at im[n * st]; npad entries
+            T *re, *im;
+            int st, npad;
+            if (a == 2) {
+                re = tab + p * nt + P.offz; im = re + 1; st = 2; npad = (nt - P.offz) / 2;
+            } else {
+                re = tab + p * nt + (a == 0 ? 0 : P.offy); im = re + nm + 1; st = 1;
+                npad = nm + 1;
+            }
+            double s1 = 0.0, c1 = 0.0, er = 0.0, ei = 0.0;
+            if (p < np) {
+                sincos(P.b[a] * (double)pos[3 * (int64_t)(p0 + p) + a], &s1, &c1);
+                er = 1.0;
+            }
+            for (int n = 0; n < npad; ++n) {
+                const bool live = n <= nm;
+                re[n * st] = live ? (T)er : T(0);
+                im[n * st] = live ? (T)ei : T(0);
+                const double nr = er * c1 - ei * s1;
+                ei = er * s1 + ei * c1;
+                er = nr;
+            }
+        }
+    };
+
+    const int item_index = blockIdx.x * n_cons + min(tid, n_cons - 1);
     const SqWorkItem item = P.items[item_index];
     // warp-uniform number of z-terms, rounded up to an even count
     const int wlen =
@@ -116,50 +168,36 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
 #pragma unroll
         for (int r = 0; r < kSqTN; ++r) acc_re[m][r] = acc_im[m][r] = T(0);
 
-    const int nt = P.nt;
-    int ix[kSqTM], iy[kSqTM];
+    int ixr[kSqTM], ixi[kSqTM], iyr[kSqTM], iyi[kSqTM];
 #pragma unroll
-    for (int m = 0; m < kSqTM; ++m) { ix[m] = item.nx[m]; iy[m] = P.offy + item.ny[m]; }
-    const int iz = P.offz + item.nz0;
+    for (int m = 0; m < kSqTM; ++m) {
+        ixr[m] = item.nx[m];
+        ixi[m] = P.nmax[0] + 1 + item.nx[m];
+        iyr[m] = P.offy + item.ny[m];
+        iyi[m] = P.offy + P.nmax[1] + 1 + item.ny[m];
+    }
+    const int iz = P.offz + 2 * item.nz0;
 
-    const float *pos = P.raw + (int64_t)frame * P.stride;
+    if (producer) build(sTab, chunk.x);
+    __syncthreads();
+    int buf = 0;
     for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS) {
-        const int np = min(kPS, chunk.y - p0);
-        // ---- phase-factor tables for particles [p0, p0 + np): thread <-> (particle,
-        // axis); one fp64 sincos, then E(n+1) = E(n) E(1) ----
-        if (tid < kPS * 3) {
-            const int p = tid / 3, a = tid - 3 * p;
-            T2 *row = sTab + p * nt + (a == 0 ? 0 : (a == 1 ? P.offy : P.offz));
-            const int nm = P.nmax[a];
-            const int npad = (a == 2) ? (nt - P.offz) : nm + 1;
-            if (p < np) {
-                const double x = (double)pos[3 * (int64_t)(p0 + p) + a];
-                double s1, c1;
-                sincos(P.b[a] * x, &s1, &c1);
-                double er = 1.0, ei = 0.0;
-                for (int n = 0; n <= nm; ++n) {
-                    T2 v; v.x = (T)er; v.y = (T)ei;
-                    row[n] = v;
-                    const double nr = er * c1 - ei * s1;
-                    ei = er * s1 + ei * c1;
-                    er = nr;
-                }
-                for (int n = nm + 1; n < npad; ++n) { T2 v; v.x = T(0); v.y = T(0); row[n] = v; }
-            } else {
-                for (int n = 0; n < npad; ++n) { T2 v; v.x = T(0); v.y = T(0); row[n] = v; }
+        const T *tab = sTab + (size_t)buf * kPS * nt;
+        if (producer) {
+            if (p0 + kPS < chunk.y) build(sTab + (size_t)(buf ^ 1) * kPS * nt, p0 + kPS);
+        } else {
+            switch (wlen) {
+                case 2: sq_accumulate_subchunk<T, 2>(tab, nt, ixr, ixi, iyr, iyi, iz, acc_re, acc_im); break;
+                case 4: sq_accumulate_subchunk<T, 4>(tab, nt, ixr, ixi, iyr, iyi, iz, acc_re, acc_im); break;
+                case 6: sq_accumulate_subchunk<T, 6>(tab, nt, ixr, ixi, iyr, iyi, iz, acc_re, acc_im); break;
+                case 8: sq_accumulate_subchunk<T, 8>(tab, nt, ixr, ixi, iyr, iyi, iz, acc_re, acc_im); break;
+                default: break;
             }
         }
         __syncthreads();
-        // ---- accumulate: particles beyond np have all-zero tables ----
-        switch (wlen) {
-            case 2: sq_accumulate_subchunk<T, 2>(sTab, nt, ix, iy, iz, acc_re, acc_im); break;
-            case 4: sq_accumulate_subchunk<T, 4>(sTab, nt, ix, iy, iz, acc_re, acc_im); break;
-            case 6: sq_accumulate_subchunk<T, 6>(sTab, nt, ix, iy, iz, acc_re, acc_im); break;
-            case 8: sq_accumulate_subchunk<T, 8>(sTab, nt, ix, iy, iz, acc_re, acc_im); break;
-            default: break;
-        }
-        __syncthreads();
+        buf ^= 1;
     }
+    if (producer) return;
 
     double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
     const int *qi = P.qidx + (int64_t)item_index * (kSqTM * kSqTN);
@@ -250,11 +288,11 @@ template <typename T>
 int launch_lattice(mdh_ctx *c, const LatticeParams &P, dim3 grid, int block)
 {
     using T2 = typename C2<T>::type;
-    const size_t smem = sizeof(T2) * kPS * P.nt;
+    const size_t smem = 2 * sizeof(T) * kPS * P.nt;           // double-buffered tables
     auto kern = sq_lattice_kernel<T>;
     MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    kern<<<grid, block, smem, c->stream>>>(P);
+    kern<<<grid, block + kSqProducers, smem, c->stream>>>(P);
     MDH_CUDA(cudaGetLastError());
     c->launches++;
     return MDH_OK;
@@ -369,12 +407,13 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                     items.push_back(it);
                     qidx.insert(qidx.end(), qi.begin(), qi.end());
                 }
-            // block size: whole warps, at most kSqThreads, at least the 96 threads
-            // the table build needs; items padded to whole blocks
+            // consumer threads per block: whole warps, at most kSqThreads minus the
+            // producer warps; items padded to whole blocks
+            const int max_cons = kSqThreads - kSqProducers;
             const int n_warps = (int)((items.size() + 31) / 32);
-            const int n_blocks = (n_warps * 32 + kSqThreads - 1) / kSqThreads;
+            const int n_blocks = (n_warps * 32 + max_cons - 1) / max_cons;
             int block = ((n_warps + n_blocks - 1) / n_blocks) * 32;
-            block = std::max(block, 96);
+            block = std::max(block, 32);
             S.block = block;
             while (items.size() % block) {
                 items.push_back(SqWorkItem{});
@@ -446,6 +485,9 @@ static int sq_build_chunks(mdh_ctx *c, int n_frames)
     return MDH_OK;
 }
 
+static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int location,
+                               int n_frames, int nominal_frames);
+
 int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
                        int n_frames)
 {
@@ -457,24 +499,48 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
     MDH_REQUIRE(stride >= 3 * S.n_total, MDH_EINVAL, "sq: frame_stride < 3*n_total");
     MDH_REQUIRE(location == MDH_HOST || location == MDH_DEVICE, MDH_EINVAL,
                 "sq: invalid location");
+    // host input in up to four pieces: the copy of one piece (copy stream) overlaps the
+    // kernels of the previous one (compute stream)
+    int piece = n_frames;
+    if (location == MDH_HOST) {
+        const double bytes = 12.0 * (double)S.n_total * n_frames;      // >= ~12 MB a piece
+        const int n_pieces = (int)std::min(4.0, std::max(1.0, floor(bytes / 12e6)));
+        piece = (n_frames + n_pieces - 1) / n_pieces;
+    }
+    for (int f0 = 0; f0 < n_frames; f0 += piece)
+        if (int rc = sq_accumulate_piece(c, pos + (int64_t)f0 * stride, stride, location,
+                                         std::min(piece, n_frames - f0), piece)) return rc;
+    return MDH_OK;
+}
 
+// nominal_frames: the piece size the particle chunks are laid out for (the last piece
+// of a call may be shorter; it reuses the layout instead of rebuilding it)
+static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int location,
+                               int n_frames, int nominal_frames)
+{
+    SqState &S = c->sq;
     const float *dsrc = pos;
     int64_t dstride = stride;
+    int slot = 0;
     if (location == MDH_HOST) {
-        if (int rc = S.raw.reserve(sizeof(float) * 3 * S.n_total * n_frames)) return rc;
-        MDH_CUDA(cudaMemcpy2DAsync(S.raw.p, sizeof(float) * 3 * S.n_total, pos,
+        if (int rc = c->stager.acquire(&slot)) return rc;
+        DevBuf &raw = S.raw[slot];
+        if (int rc = raw.reserve(sizeof(float) * 3 * S.n_total * n_frames)) return rc;
+        MDH_CUDA(cudaMemcpy2DAsync(raw.p, sizeof(float) * 3 * S.n_total, pos,
                                    sizeof(float) * stride, sizeof(float) * 3 * S.n_total,
-                                   n_frames, cudaMemcpyHostToDevice, c->stream));
-        dsrc = S.raw.as<float>();
+                                   n_frames, cudaMemcpyHostToDevice, c->stager.copy));
+        if (int rc = c->stager.publish(c->stream, slot)) return rc;
+        dsrc = raw.as<float>();
         dstride = 3 * S.n_total;
     }
     LatticeParams LP;
     if (S.lattice) {
-        LP.offy = S.nmax[0] + 1;
-        LP.offz = LP.offy + S.nmax[1] + 1;
-        LP.nt = LP.offz + (S.nmax[2] + kSqTN) / kSqTN * kSqTN;
+        // row layout in table elements: E_x re | E_x im | E_y re | E_y im | E_z (re, im)
+        LP.offy = 2 * (S.nmax[0] + 1);
+        LP.offz = (LP.offy + 2 * (S.nmax[1] + 1) + 3) / 4 * 4;     // 16-byte aligned
+        LP.nt = LP.offz + 2 * ((S.nmax[2] + kSqTN) / kSqTN * kSqTN);
     }
-    if (int rc = sq_build_chunks(c, n_frames)) return rc;
+    if (int rc = sq_build_chunks(c, nominal_frames)) return rc;
     const size_t rho_bytes = sizeof(double) * 2 * (size_t)n_frames * S.n_rho * S.n_q;
     if (int rc = S.rho.reserve(rho_bytes)) return rc;
 
@@ -514,5 +580,7 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
     MDH_CUDA(cudaGetLastError());
     c->launches++;
     S.rho_frames = n_frames;
+    if (location == MDH_HOST)
+        if (int rc = c->stager.retire(c->stream, slot)) return rc;
     return c->t_sq.end(c->stream);
 }

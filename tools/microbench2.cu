@@ -56,6 +56,35 @@ KERNEL(k_mix, float, a + i + threadIdx.x,
        v[i] = fmaf(v[i], a, b); v[i] = fmaf(v[i], a, b);
        v[i] = __uint_as_float(min(__float_as_uint(v[i]), 0x4f000000u + it)))
 
+// DFMA with three distinct vector-register operands, the S(q) inner loop's shape:
+// 32 accumulators, acc[m][r] += a[m] * z[r] (re/im mixes), operands refreshed from
+// registers only.  Counts DFMAs.
+__global__ void k_dfma3(unsigned long long *out, double a0, double b0)
+{
+    double acc_re[2][8], acc_im[2][8], ar[2], ai[2], zr[8], zi[8];
+    for (int m = 0; m < 2; ++m) { ar[m] = a0 + m + threadIdx.x; ai[m] = b0 + m; }
+    for (int r = 0; r < 8; ++r) { zr[r] = a0 * r + 1; zi[r] = b0 * r + threadIdx.x; }
+    for (int m = 0; m < 2; ++m)
+        for (int r = 0; r < 8; ++r) acc_re[m][r] = acc_im[m][r] = 0;
+    for (int it = 0; it < ITERS / 8; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                acc_re[m][r] = fma(ar[m], zr[r], acc_re[m][r]);
+                acc_re[m][r] = fma(-ai[m], zi[r], acc_re[m][r]);
+                acc_im[m][r] = fma(ar[m], zi[r], acc_im[m][r]);
+                acc_im[m][r] = fma(ai[m], zr[r], acc_im[m][r]);
+            }
+        // keep the compiler from hoisting: rotate the operands through the accumulators
+        ar[0] += acc_im[1][7] * 1e-300; zr[0] += acc_re[0][0] * 1e-300;
+    }
+    double s = 0;
+    for (int m = 0; m < 2; ++m)
+        for (int r = 0; r < 8; ++r) s += acc_re[m][r] + acc_im[m][r];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (unsigned long long)s;
+}
+
 // RED.shared with per-thread precomputed word indices (ILP addresses in registers)
 template <int MODE>   // 0: every lane its own bank, 1: random words of a 201*4-word histogram
 __global__ void k_red(unsigned long long *out, int n_words)
@@ -117,6 +146,8 @@ int main()
     run("fadd", [&] { k_fadd<<<blocks, threads>>>(out, 1.0000001f, 1e-9f); }, n, sms, khz);
     run("ffma2", [&] { k_ffma2<<<blocks, threads>>>(out, 1.0000001f, 1e-9f); }, n, sms, khz);
     run("fadd2", [&] { k_fadd2<<<blocks, threads>>>(out, 1.0000001f, 1e-9f); }, n, sms, khz);
+    run("dfma_3reg_operands", [&] { k_dfma3<<<blocks, 256>>>(out, 1.0000001, 1e-9); },
+        (double)(ITERS / 8) * 64 * 256 * blocks, sms, khz);
     run("imad", [&] { k_imad<<<blocks, threads>>>(out, 3.f, 7.f); }, n, sms, khz);
     run("vimnmx", [&] { k_vimnmx<<<blocks, threads>>>(out, 3.f, 7.f); }, n, sms, khz);
     run("shf_iadd", [&] { k_shf<<<blocks, threads>>>(out, 3.f, 7.f); }, 2 * n, sms, khz);
