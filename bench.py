@@ -365,6 +365,12 @@ def run_ours(args):
     prewarm(step, ctx, 1.5)                   # bring the clocks up (untimed, on top of W)
     for s in range(W):
         step(s)
+    # the tail of the timed region once, untimed: the first fetch -> device copy ->
+    # all-reduce of a process pays one-off initialisation (tens of ms on a fresh box)
+    warm = torch.from_numpy(ctx.rdf_fetch()).cuda()
+    if world > 1:
+        dist.all_reduce(warm)
+    torch.cuda.synchronize()
     ctx.sync()
     ctx.rdf_reset()
     ctx.kernel_time(reset=True)
@@ -376,14 +382,27 @@ def run_ours(args):
     wall0 = time.time()
     ev0.record()
     frames_done, kernel_ms = 0, 0.0
+    dbg = os.environ.get("MDH_BENCH_DEBUG")
+    dbg_ev, dbg_host = [], []
     for s in range(W, W + K):
+        if dbg:
+            e = torch.cuda.Event(enable_timing=True); e.record(); dbg_ev.append(e)
+            dbg_host.append(time.perf_counter())
         frames_done += step(s)
+    if dbg:
+        e = torch.cuda.Event(enable_timing=True); e.record(); dbg_ev.append(e)
+        dbg_host.append(time.perf_counter())
     counts = torch.from_numpy(ctx.rdf_fetch()).cuda()
     if world > 1:
         dist.all_reduce(counts)
     ev1.record()
     torch.cuda.synchronize()
     wall1 = time.time()
+    if dbg:
+        print("per-step GPU ms:", [round(a.elapsed_time(b), 2) for a, b in
+                                   zip(dbg_ev[:-1], dbg_ev[1:])], file=sys.stderr)
+        print("per-step host enqueue ms:", [round(1e3 * (b - a), 2) for a, b in
+                                            zip(dbg_host[:-1], dbg_host[1:])], file=sys.stderr)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -542,6 +561,10 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
     prewarm(step, ctx, 0.4)
     for s in range(W):
         step(s)
+    warm = torch.from_numpy(ctx.sq_fetch()).cuda()
+    if world > 1:
+        dist.all_reduce(warm)
+    torch.cuda.synchronize()
     ctx.sync()
     ctx.sq_reset()
     ctx.kernel_time(reset=True)

@@ -122,7 +122,8 @@ def radial_histogram(
     ctx = Context(dev)
     try:
         ctx.rdf_set_filter(arith)
-        ctx.rdf_configure(len(p1), len(p2), False,
+        # the same array twice: the kernels may use the pair symmetry (same counts)
+        ctx.rdf_configure(len(p1), len(p2), pos2 is pos1,
                           squared_thresholds(n_bins, range), range[0], range[1],
                           exclusion=exclusion, mode=mode, hist=hist)
         ctx.rdf_accumulate(p1, 3 * len(p1), p2, 3 * len(p2),

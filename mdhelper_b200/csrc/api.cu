@@ -207,6 +207,7 @@ int mdh_ctx_destroy(mdh_ctx *c)
     R.pk1.release(); R.pk2.release(); R.boxes.release();
     R.ext1.release(); R.ext2.release(); R.filt.release(); R.fstats.release();
     for (auto &b : R.cell) b.release();
+    R.cell_pairs.release();
     if (R.h_boxes_pinned) cudaFreeHost(R.h_boxes_pinned);
     if (R.ev_boxes) cudaEventDestroy(R.ev_boxes);
     SqState &S = c->sq;

@@ -80,6 +80,7 @@ struct RdfState {
     DevBuf pk1, pk2;       // float4[F][npad]
     DevBuf boxes;          // FrameBox[F]
     DevBuf cell[10];       // cell-list scratch (grids, counts, starts, ranks, sorted, evals)
+    DevBuf cell_pairs;     // pair-interleaved copy of the sorted group-2 particles
     bool evals_dev_init = false;
     std::vector<FrameBox> h_boxes;
     FrameBox *h_boxes_pinned = nullptr;   // staging for the async box upload

@@ -222,7 +222,7 @@ int launch_allpairs_dyn(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl, b
 
 // ---- host side ------------------------------------------------------------------
 
-int rdf_cells_accumulate(mdh_ctx *c, int f0, int n_frames);   // rdf_cells.cu
+int rdf_cells_accumulate(mdh_ctx *c, int f0, int n_frames, bool use_filter);   // rdf_cells.cu
 static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const float *pos2,
                                 int64_t s2, int location, int f0, int n_frames, int mode);
 int rdf_filter_launch(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl,
@@ -360,7 +360,7 @@ static int rdf_upload_group(mdh_ctx *c, const float *pos, int64_t stride, int lo
         MDH_CUDA(cudaGetLastError());
         c->launches++;
     }
-    dim3 grid((unsigned)std::min<int64_t>((npad + 255) / 256, 1024), n_frames);
+    dim3 grid((unsigned)std::min<int64_t>((npad + 255) / 256, 2048), n_frames);
     rdf_pack_kernel<<<grid, 256, 0, c->stream>>>(dsrc, dstride, pk.as<float4>(), n, npad, excl,
                                                  R.drop_axis, d_ext);
     MDH_CUDA(cudaGetLastError());
@@ -446,8 +446,7 @@ static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const
     const int tile = kThreads * R.ipt;
     const int64_t pad1 = (R.n1 + tile - 1) / tile * tile;
     const int64_t pad2 = (R.n2 + tile - 1) / tile * tile;
-    const bool use_filter = mode == MDH_RDF_ALLPAIRS && R.filter_ok &&
-                            R.filter_mode != MDH_FILTER_OFF;
+    const bool use_filter = R.filter_ok && R.filter_mode != MDH_FILTER_OFF;
 
     int slot = 0;
     if (location == MDH_HOST) {
@@ -475,7 +474,7 @@ static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const
     if (int rc = c->t_rdf.begin(c->stream)) return rc;
 
     if (mode == MDH_RDF_CELLS) {
-        if (int rc = rdf_cells_accumulate(c, f0, n_frames)) return rc;
+        if (int rc = rdf_cells_accumulate(c, f0, n_frames, use_filter)) return rc;
     } else {
         PairParams P;
         P.p1 = R.pk1.as<float4>();

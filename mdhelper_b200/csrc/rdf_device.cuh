@@ -47,21 +47,35 @@ static __global__ void rdf_ext_init_kernel(unsigned *ext, int n)
 
 // ext: unsigned[F][6] = {min x, y, z, max x, y, z} keys, initialised by
 // rdf_ext_init_kernel (or nullptr)
-static __global__ void rdf_pack_kernel(const float *__restrict__ raw, int64_t frame_stride,
-                                       float4 *__restrict__ out, int64_t n, int64_t npad,
-                                       int64_t excl, int drop_axis, unsigned *__restrict__ ext)
+static __global__ void __launch_bounds__(256)
+    rdf_pack_kernel(const float *__restrict__ raw, int64_t frame_stride,
+                    float4 *__restrict__ out, int64_t n, int64_t npad, int64_t excl,
+                    int drop_axis, unsigned *__restrict__ ext)
 {
+    __shared__ float stage[3 * 256];
+    __shared__ unsigned red[8][6];
     const int frame = blockIdx.y;
+    const int tid = threadIdx.x;
     const float *src = raw + (int64_t)frame * frame_stride;
     float4 *dst = out + (int64_t)frame * npad;
     unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npad;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    // 256 particles per step: their 768 floats are read as one contiguous run
+    // (coalesced, unlike three stride-3 loads per thread) and regrouped through
+    // shared memory
+    for (int64_t i0 = (int64_t)blockIdx.x * 256; i0 < npad; i0 += (int64_t)gridDim.x * 256) {
+        const int64_t f0 = 3 * i0, fend = 3 * n;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int64_t f = f0 + k * 256 + tid;
+            stage[k * 256 + tid] = f < fend ? src[f] : 0.f;
+        }
+        __syncthreads();
+        const int64_t i = i0 + tid;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n) {
-            v.x = src[3 * i];
-            v.y = src[3 * i + 1];
-            v.z = src[3 * i + 2];
+            v.x = stage[3 * tid];
+            v.y = stage[3 * tid + 1];
+            v.z = stage[3 * tid + 2];
             if (drop_axis == 0) v.x = 0.f;
             if (drop_axis == 1) v.y = 0.f;
             if (drop_axis == 2) v.z = 0.f;
@@ -71,17 +85,23 @@ static __global__ void rdf_pack_kernel(const float *__restrict__ raw, int64_t fr
             lo[1] = min(lo[1], ky); hi[1] = max(hi[1], ky);
             lo[2] = min(lo[2], kz); hi[2] = max(hi[2], kz);
         }
-        dst[i] = v;
+        if (i < npad) dst[i] = v;
+        __syncthreads();
     }
     if (ext) {
+        // block-level extents first: six global atomics per block, not per warp
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const unsigned l = __reduce_min_sync(0xffffffffu, lo[k]);
             const unsigned h = __reduce_max_sync(0xffffffffu, hi[k]);
-            if ((threadIdx.x & 31) == 0) {
-                if (l != 0xffffffffu) atomicMin(&ext[frame * 6 + k], l);
-                if (h != 0u) atomicMax(&ext[frame * 6 + 3 + k], h);
-            }
+            if ((tid & 31) == 0) { red[tid >> 5][k] = l; red[tid >> 5][3 + k] = h; }
+        }
+        __syncthreads();
+        if (tid < 6) {
+            unsigned v = red[0][tid];
+            for (int w = 1; w < 8; ++w) v = tid < 3 ? min(v, red[w][tid]) : max(v, red[w][tid]);
+            if (tid < 3) { if (v != 0xffffffffu) atomicMin(&ext[frame * 6 + tid], v); }
+            else if (v != 0u) atomicMax(&ext[frame * 6 + tid], v);
         }
     }
 }
@@ -265,6 +285,81 @@ __device__ __forceinline__ void priv_flush(unsigned *priv_w, unsigned *bhist, in
         }
     }
     __syncwarp();
+}
+
+// ---- packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE round-to-nearest
+// operations per issue slot; a scalar operand is broadcast by the hardware) -----------
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// The fp32 evaluation of TWO pairs at once: coordinate differences d = b + a per axis
+// with a = the NEGATED coordinates of the group-1 particle(s) and b = the group-2
+// particle(s) -- the all-pairs kernel packs two group-1 particles against one tile row
+// (b broadcast), the cell-list kernel one group-1 particle (a broadcast) against two
+// neighbours.  Returns the fixed-point bin coordinates u0, u1 (relative to slot 0 when
+// LOWER, else with the bits of 1.5*2^(23-k) still added).  Main loops and exact
+// re-evaluations go through this one function, so they see identical bits.
+template <bool LOWER>
+__device__ __forceinline__ void filter_eval2(f32x2 ax, f32x2 ay, f32x2 az, f32x2 bx, f32x2 by,
+                                             f32x2 bz, const FrameFilter &ff, float scale,
+                                             float offm, unsigned cbits, unsigned &u0,
+                                             unsigned &u1)
+{
+    const f32x2 magic = pk2(kMagicF, kMagicF), nmagic = pk2(-kMagicF, -kMagicF);
+    const f32x2 dx = add2(bx, ax);
+    const f32x2 dy = add2(by, ay);
+    const f32x2 dz = add2(bz, az);
+    const f32x2 rx = add2(fma2(dx, pk2(ff.inv[0], ff.inv[0]), magic), nmagic);
+    const f32x2 ry = add2(fma2(dy, pk2(ff.inv[1], ff.inv[1]), magic), nmagic);
+    const f32x2 rz = add2(fma2(dz, pk2(ff.inv[2], ff.inv[2]), magic), nmagic);
+    const f32x2 mx = fma2(pk2(ff.nbox[0], ff.nbox[0]), rx, dx);
+    const f32x2 my = fma2(pk2(ff.nbox[1], ff.nbox[1]), ry, dy);
+    const f32x2 mz = fma2(pk2(ff.nbox[2], ff.nbox[2]), rz, dz);
+    const f32x2 d2 = fma2(mz, mz, fma2(my, my, mul2(mx, mx)));
+    float a, b, s0, s1;
+    upk2(d2, a, b);
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(a));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(b));
+    const f32x2 e = fma2(pk2(s0, s1), pk2(scale, scale), pk2(offm, offm));
+    upk2(e, a, b);
+    u0 = __float_as_uint(a) - (LOWER ? cbits : 0u);
+    u1 = __float_as_uint(b) - (LOWER ? cbits : 0u);
+}
+
+// RED without the "memory" clobber: the compiler may move the tile loads of the next
+// iteration across it (they never alias the histogram); __syncthreads() orders the
+// histogram against its final read.
+__device__ __forceinline__ void red_shared_hot(unsigned smem_addr, unsigned v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(smem_addr), "r"(v));
 }
 
 // ---- parameters of the all-pairs kernels (rdf.cu, rdf_filter.cu) -------------------

@@ -56,78 +56,6 @@ __host__ __device__ inline size_t filter_smem_bytes(int n_bins, int sb)
            sizeof(unsigned) * (kListCap + 4);
 }
 
-// ---- packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE round-to-nearest
-// operations per issue slot; a scalar operand is broadcast by the hardware) -----------
-typedef unsigned long long f32x2;
-
-__device__ __forceinline__ f32x2 pk2(float lo, float hi)
-{
-    f32x2 d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
-    return d;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
-{
-    f32x2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
-{
-    f32x2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
-{
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
-// The fp32 evaluation of one tile row against TWO particles of group 1 (their
-// negated coordinates packed in nx, ny, nz): the fixed-point bin coordinates u0, u1
-// (relative to slot 0 when LOWER, else with the bits of 1.5*2^(23-k) still added).
-// The main loop and the re-evaluation in filter_fix both go through this function,
-// so they see identical bits.
-template <bool LOWER>
-__device__ __forceinline__ void filter_eval2(f32x2 nx, f32x2 ny, f32x2 nz, const float4 &pj,
-                                             const FrameFilter &ff, float scale, float offm,
-                                             unsigned cbits, unsigned &u0, unsigned &u1)
-{
-    const f32x2 magic = pk2(kMagicF, kMagicF), nmagic = pk2(-kMagicF, -kMagicF);
-    const f32x2 dx = add2(nx, pk2(pj.x, pj.x));
-    const f32x2 dy = add2(ny, pk2(pj.y, pj.y));
-    const f32x2 dz = add2(nz, pk2(pj.z, pj.z));
-    const f32x2 rx = add2(fma2(dx, pk2(ff.inv[0], ff.inv[0]), magic), nmagic);
-    const f32x2 ry = add2(fma2(dy, pk2(ff.inv[1], ff.inv[1]), magic), nmagic);
-    const f32x2 rz = add2(fma2(dz, pk2(ff.inv[2], ff.inv[2]), magic), nmagic);
-    const f32x2 mx = fma2(pk2(ff.nbox[0], ff.nbox[0]), rx, dx);
-    const f32x2 my = fma2(pk2(ff.nbox[1], ff.nbox[1]), ry, dy);
-    const f32x2 mz = fma2(pk2(ff.nbox[2], ff.nbox[2]), rz, dz);
-    const f32x2 d2 = fma2(mz, mz, fma2(my, my, mul2(mx, mx)));
-    float a, b, s0, s1;
-    upk2(d2, a, b);
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(a));
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(b));
-    const f32x2 e = fma2(pk2(s0, s1), pk2(scale, scale), pk2(offm, offm));
-    upk2(e, a, b);
-    u0 = __float_as_uint(a) - (LOWER ? cbits : 0u);
-    u1 = __float_as_uint(b) - (LOWER ? cbits : 0u);
-}
-
-// RED without the "memory" clobber: the compiler may move the tile loads of the next
-// iteration across it (they never alias the histogram); __syncthreads() orders the
-// histogram against its final read.
-__device__ __forceinline__ void red_shared_hot(unsigned smem_addr, unsigned v)
-{
-    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(smem_addr), "r"(v));
-}
-
 // Exact re-evaluation of the IPT pairs behind one deferred entry (thread te of the
 // block, tile row jj): every pair the main loop saw as uncertain has been added to
 // the slot the fp32 arithmetic suggested; move it if the fp64 arithmetic disagrees.
@@ -150,8 +78,9 @@ __device__ __noinline__ void filter_fix(const PairParams &P, int frame, int it, 
         const int i0 = it * TILE + ip * kThreads + te, i1 = i0 + kThreads;
         const float4 a0 = f1[min(i0, P.n1 - 1)], a1 = f1[min(i1, P.n1 - 1)];
         unsigned uu[2];
-        filter_eval2<LOWER>(pk2(-a0.x, -a1.x), pk2(-a0.y, -a1.y), pk2(-a0.z, -a1.z), pj, ff,
-                            fc.scale, ff.offm, fc.cbits, uu[0], uu[1]);
+        filter_eval2<LOWER>(pk2(-a0.x, -a1.x), pk2(-a0.y, -a1.y), pk2(-a0.z, -a1.z),
+                            pk2(pj.x, pj.x), pk2(pj.y, pj.y), pk2(pj.z, pj.z), ff, fc.scale,
+                            ff.offm, fc.cbits, uu[0], uu[1]);
         for (int h = 0; h < 2; ++h) {
             const int i = h ? i1 : i0;
             const float4 a = h ? a1 : a0;
@@ -280,8 +209,9 @@ __global__ void __launch_bounds__(kThreads, OCC)
             for (int r = 0; r < NR; ++r)
 #pragma unroll
                 for (int ip = 0; ip < IPT / 2; ++ip)
-                    filter_eval2<LOWER>(nx[ip], ny[ip], nz[ip], pj[r], ff, scale, offm, fc.cbits,
-                                        uu[r][2 * ip], uu[r][2 * ip + 1]);
+                    filter_eval2<LOWER>(nx[ip], ny[ip], nz[ip], pk2(pj[r].x, pj[r].x),
+                                        pk2(pj[r].y, pj[r].y), pk2(pj[r].z, pj[r].z), ff, scale,
+                                        offm, fc.cbits, uu[r][2 * ip], uu[r][2 * ip + 1]);
         };
         // Stage B: histogram updates and the uncertainty test of NR rows (ALU pipe,
         // LSU), then one rarely taken branch for the uncertain pairs of the group.

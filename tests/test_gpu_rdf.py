@@ -55,10 +55,10 @@ def test_class_matches_golden(golden, name, hist, arith):
     np.testing.assert_allclose(r.results.rdf, g["rdf"], rtol=1e-6)
 
 
-@pytest.mark.parametrize("hist", HISTS)
+@pytest.mark.parametrize("hist,arith", VARIANTS)
 @pytest.mark.parametrize("name", ["lj1000", "twogroup", "excl11", "excl410",
                                   "noncubic_npt", "unwrapped"])
-def test_cells_mode_matches_golden(golden, name, hist):
+def test_cells_mode_matches_golden(golden, name, hist, arith):
     g = golden(f"rdf_{name}")
     u = universe_from(g)
     ag1, ag2 = rdf_groups(u, g)
@@ -72,8 +72,10 @@ def test_cells_mode_matches_golden(golden, name, hist):
     else:
         want = g["counts"]
     r = _structure().RadialDistributionFunction(
-        ag1, ag2, verbose=False, mode="cells", hist=hist, **kw).run()
+        ag1, ag2, verbose=False, mode="cells", hist=hist, arith=arith, **kw).run()
     assert np.array_equal(r.results.counts, want)
+    if arith == "auto":
+        assert r._filter_stats["eligible"] == 1
 
 
 @pytest.mark.parametrize("n1,n2", [(1, 1), (1, 700), (513, 511), (512, 1024), (33, 1537)])
@@ -181,6 +183,31 @@ def test_filter_declines_frames_far_outside_the_box():
     assert st["declined_frames"] == 1
 
 
+@pytest.mark.parametrize("same", [True, False])
+@pytest.mark.parametrize("exclusion", [None, (2, 2)])
+def test_cells_filter_audit(same, exclusion):
+    """The cell-list kernel with the fp32 filter, audited pair by pair against the fp64
+    arithmetic: half stencil (same group) and full stencil (two groups), odd particle
+    counts (the pair layout's filler slot), exclusions, r_lo > 0."""
+    rng = np.random.default_rng(41 + same)
+    dims = np.array([21.0, 23.5, 22.25, 90, 90, 90], np.float32)
+    p1 = (rng.random((6001, 3)) * dims[:3]).astype(np.float32)
+    p2 = p1 if same else (rng.random((7003, 3)) * dims[:3]).astype(np.float32)
+    S = _structure()
+    for n_bins, rng_ in [(100, (0.0, 2.5)), (75, (0.5, 2.75))]:
+        want = _oracle().radial_histogram(p1, p2, n_bins, rng_, dims, exclusion=exclusion)
+        st = {}
+        got = S.radial_histogram(p1, p2, n_bins, rng_, dims, exclusion=exclusion,
+                                 mode="cells", arith="audit", stats=st)
+        assert st["eligible"] == 1 and st["audit_violations"] == 0, st
+        assert st["deferred_entries"] > 0
+        assert np.array_equal(got, want)
+        for arith in ("auto", "off"):
+            got = S.radial_histogram(p1, p2, n_bins, rng_, dims, exclusion=exclusion,
+                                     mode="cells", arith=arith)
+            assert np.array_equal(got, want)
+
+
 def test_same_group_symmetry_and_self_pairs():
     """ag1 is ag2: ordered pairs, N self pairs in bin 0."""
     from mdhelper_b200 import synthetic
@@ -276,6 +303,10 @@ def test_large_cutoff_run_modes_agree():
         assert np.array_equal(c, ref)
     auto = S.RadialDistributionFunction(u.atoms, **kw).run().results.counts
     assert np.array_equal(auto, ref)
+    for arith in ("off", "audit"):
+        x = S.RadialDistributionFunction(u.atoms, mode="cells", arith=arith, **kw).run()
+        assert np.array_equal(x.results.counts, ref)
+        assert x._filter_stats["audit_violations"] == 0
     # one frame against the oracle's grid search
     want = _oracle().rdf_run(u, u.atoms, n_bins=100, range=(0.0, 2.5), norm=None,
                              frames=[0], method="nsgrid")["counts"]
