@@ -423,17 +423,21 @@ def run_ours(args):
     rdf = RadialDistributionFunction(cat, an, n_bins=CFG2["n_bins"], range=CFG2["range"],
                                      verbose=False, batch_frames=fps, hist=args.hist,
                                      arith=args.arith)
+    # weak scaling like `value`: run() shards the frames it is given over the ranks
+    # (np.array_split), so a step hands it world * fps frames -- fps per GPU, each rank
+    # reading its own trajectory -- and the counts come back summed over the ranks
+    span = fps * world
     for s in range(W):
-        f0 = (s * fps) % n_frames
-        rdf.run(start=f0, stop=min(n_frames, f0 + fps))
+        f0 = (s * span) % n_frames
+        rdf.run(start=f0, stop=min(n_frames, f0 + span))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_binned = 0
     for s in range(W, W + K):
-        f0 = (s * fps) % n_frames
-        rdf.run(start=f0, stop=min(n_frames, f0 + fps))
+        f0 = (s * span) % n_frames
+        rdf.run(start=f0, stop=min(n_frames, f0 + span))
         e2e_binned += int(rdf.results.counts.sum())       # already summed over ranks
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
@@ -508,8 +512,8 @@ def run_ours(args):
         "frames_per_s": frames_done * world / (ms * 1e-3),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pairs/s",
-                "h2d_bytes_per_step": fps * (n1 + n2) * 12 + fps * 48,
-                "d2h_bytes_per_step": CFG2["n_bins"] * 8,
+                "h2d_bytes_per_step": world * (fps * (n1 + n2) * 12 + fps * 48),
+                "d2h_bytes_per_step": world * CFG2["n_bins"] * 8,
                 "api": "RadialDistributionFunction(cations, anions, n_bins=201, "
                        "range=(0, 14.5)).run(start, stop) per step"},
         "gpu_launches": launches,
@@ -527,7 +531,7 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
     from mdhelper_b200 import _lib, synthetic
     from mdhelper_b200.analysis.structure import StructureFactor
     K, W, fps = args.steps, args.warmup, args.sq_frames_per_step
-    ring = 256                                    # distinct frames (154 MB > L2)
+    ring = max(256, fps * world)                  # distinct frames (>= 154 MB > L2)
     u = synthetic.lj_fluid(CFG4["n"], ring, seed=CFG4["seed"] + 1000 * rank)
     L = float(u.trajectory.unitcells[0, 0])
     q_max = 2 * np.pi * CFG4["n_max"] / L
@@ -590,16 +594,19 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
     _, _, kern_total_ms, kern_calls = ctx.kernel_time(reset=True)
     kern_ms = kern_total_ms / max(kern_calls, 1) * (fps * K / max(frames, 1))
 
+    span = fps * world                            # fps frames per GPU and step
     for s in range(W):
-        f0 = (s * fps) % ring
-        sf.run(start=f0, stop=min(ring, f0 + fps))
+        f0 = (s * span) % ring
+        sf.run(start=f0, stop=min(ring, f0 + span))
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_frames = 0
     for s in range(W, W + K):
-        f0 = (s * fps) % ring
-        sf.run(start=f0, stop=min(ring, f0 + fps))
-        e2e_frames += sf.n_frames * world
+        f0 = (s * span) % ring
+        sf.run(start=f0, stop=min(ring, f0 + span))
+        e2e_frames += sf.n_frames                 # all ranks together
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
@@ -615,10 +622,11 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
         "config": {"workload": f"cfg4: direct-sum S(q), N=50,000, n_points=32, "
                                f"q_max=2*pi*16/L -> N_q={n_q}, mode=None, form=exp, fp64",
                    "frames_per_step": fps, "terms_per_frame": N * n_q,
-                   "cache": f"ring of {ring} distinct frames (154 MB > L2)"},
+                   "cache": f"ring of {ring} distinct frames ({ring * N * 12 / 1e6:.0f} MB > L2)"},
         "ms_per_step": ms / K, "gpu_launches": launches,
         "e2e": {"value": e2e_frames / float(e2e_s.item()), "unit": "frames/s",
-                "h2d_bytes_per_step": fps * N * 12, "d2h_bytes_per_step": n_q * 8,
+                "h2d_bytes_per_step": world * fps * N * 12,
+                "d2h_bytes_per_step": world * n_q * 8,
                 "api": "StructureFactor([atoms], n_points=32, q_max=...).run(start, stop)"},
         "roofline": {"kernel": "sq_lattice_kernel<double,16>", "bound": "fp64_pipe",
                      "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Ginstr/s",
