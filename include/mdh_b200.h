@@ -201,6 +201,29 @@ int mdh_sq_accum_device(mdh_ctx *ctx, void **dptr);
  * n_groups (or 1 for the (-1,-1) pair).  Debug / parity aid for seam #2. */
 int mdh_sq_fetch_rho(mdh_ctx *ctx, double *rho);
 
+/* ---- intermediate scattering function F(q, t), F_s(q, t) ------------------------
+ *
+ * Replaces the per-frame work of IntermediateScatteringFunction._single_frame
+ * (src/mdhelper/analysis/structure.py:1959-2085), which calls seam #2 once per frame
+ * for rho(q, t) and, with incoherent=True, once per (frame, time lag) on the
+ * displacements r(t) - r(t - lag) (:1991-1996).
+ *
+ * Call mdh_sq_configure first (wavevectors, groups, pairs), then mdh_isf_configure;
+ * frames must be passed in time order.  n_lags time lags (0 .. n_lags-1); max_frames
+ * is the total number of frames that will be passed (sizes the rho(q, t) store).
+ *   cisf[lag][pair][q] = sum over t >= lag of Re(rho_j(t-lag) conj(rho_k(t)))
+ *                        (+ the j <-> k term when j != k)
+ *   iisf[lag][row][q]  = sum over t >= lag of Re sum_particles exp(i q.(r(t) - r(t-lag))),
+ *                        row = group (or 0 for the (-1, -1) pair)
+ * Un-normalised sums, as the reference accumulates them before _conclude.
+ */
+int mdh_isf_configure(mdh_ctx *ctx, int n_lags, int incoherent, int64_t max_frames);
+int mdh_isf_accumulate(mdh_ctx *ctx, const float *pos, int64_t frame_stride, int location,
+                       int n_frames);
+/* iisf may be NULL.  Synchronises. */
+int mdh_isf_fetch(mdh_ctx *ctx, double *cisf /* [n_lags][n_pairs][n_q] */,
+                  double *iisf /* [n_lags][n_rho][n_q] or NULL */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,9 @@ SIGNATURES = {
     "mdh_sq_reset": (_i32, [_p]),
     "mdh_sq_accum_device": (_i32, [_p, ctypes.POINTER(_p)]),
     "mdh_sq_fetch_rho": (_i32, [_p, _p]),
+    "mdh_isf_configure": (_i32, [_p, _i32, _i32, _i64]),
+    "mdh_isf_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
+    "mdh_isf_fetch": (_i32, [_p, _p, _p]),
 }
 
 _LIB = None
@@ -238,6 +241,29 @@ class Context:
 
     def sq_reset(self):
         check(self._lib.mdh_sq_reset(self._h))
+
+    # ---- intermediate scattering function (after sq_configure) ----
+    def isf_configure(self, n_lags: int, incoherent: bool, max_frames: int):
+        check(self._lib.mdh_isf_configure(self._h, int(n_lags), int(bool(incoherent)),
+                                          int(max_frames)))
+        self._isf = (int(n_lags), bool(incoherent))
+
+    def isf_accumulate(self, pos, stride, n_frames, *, device=False, keepalive=None):
+        check(self._lib.mdh_isf_accumulate(
+            self._h, _ptr(pos), int(stride),
+            MDH_DEVICE if device else MDH_HOST, int(n_frames)))
+        if keepalive is not None:
+            self._keep.append(keepalive)
+
+    def isf_fetch(self):
+        """``(cisf[n_lags, n_pairs, n_q], iisf[n_lags, n_rho, n_q] or None)``, raw sums."""
+        n_lags, inc = self._isf
+        n_pairs, n_q = self._sq_shape
+        cisf = np.empty((n_lags, n_pairs, n_q), dtype=np.float64)
+        iisf = np.empty((n_lags, self._sq_nrho, n_q), dtype=np.float64) if inc else None
+        check(self._lib.mdh_isf_fetch(self._h, cisf.ctypes.data, _ptr(iisf)))
+        self._keep.clear()
+        return cisf, iisf
 
     def sq_fetch_rho(self) -> np.ndarray:
         out = np.empty((self._sq_nrho, self._sq_shape[1]), dtype=np.complex128)

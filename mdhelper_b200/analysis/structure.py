@@ -9,6 +9,9 @@ structure.py``):
 * :func:`radial_histogram` -- seam #1, ``structure.py:32-104``.
 * :class:`RadialDistributionFunction` -- ``structure.py:444-1032``.
 * :class:`StructureFactor` -- ``structure.py:1034-1550``.
+* :class:`IntermediateScatteringFunction` -- ``structure.py:1552-2127`` (the first
+  "next" row of the scope table: it reuses the S(q) kernels for ``rho(q, t)`` and
+  for the displacement sums of the incoherent part).
 
 Constructors, ``run(start, stop, step, frames)`` and ``results.*`` follow the
 reference.  The distance / binning loop and the Fourier sums run in
@@ -597,6 +600,192 @@ class StructureFactor(GpuAnalysisBase):
             order = np.argsort(self.results.wavenumbers)
             self.results.wavenumbers = self.results.wavenumbers[order]
             self.results.ssf = self.results.ssf[:, order]
+
+
+class IntermediateScatteringFunction(StructureFactor):
+    r"""
+    Coherent and incoherent (self) intermediate scattering functions
+    :math:`F(q,\,t)`, :math:`F_\mathrm{s}(q,\,t)` and their partial variants,
+    computed on the GPU (reference class: ``structure.py:1552-2127``).
+
+    Same constructor as :class:`StructureFactor` plus
+
+    dt : `float`, keyword-only, optional
+        Time between frames (default: the trajectory's ``dt``).
+    n_lags : `int`, keyword-only, optional
+        Number of time lags (default: the number of analysed frames).
+    incoherent : `bool`, keyword-only, default: :code:`False`
+        Also compute the incoherent part (one direct sum per frame and lag over
+        the particle displacements, as the reference does).
+
+    Attributes
+    ----------
+    results.times, results.wavenumbers, results.pairs, results.cisf, results.iisf
+        As in the reference: ``cisf`` has shape :math:`(N_t,\,N_\mathrm{pairs},
+        \,N_q)`, ``iisf`` :math:`(N_t,\,N_\mathrm{groups},\,N_q)`.
+
+    Notes
+    -----
+    * Time order matters, so under ``torch.distributed`` the *wavevectors* are
+      sharded over the ranks (every rank streams all frames) and the columns are
+      combined with one all-reduce.
+    * ``rho(q, t)`` of every frame stays on the device (16 bytes per frame, group
+      and wavevector), which is what the reference's comment at
+      ``structure.py:1971-1977`` rules out for host memory; the incoherent part
+      keeps a coordinate window of ``n_lags - 1`` frames.
+    """
+
+    def __init__(self, groups, groupings: Union[str, tuple] = "atoms", *,
+                 mode: str = None, form: str = "exp", dimensions=None,
+                 dt: float = None, n_points: int = 32, n_surfaces: int = None,
+                 n_surface_points: int = 8, q_max: float = None,
+                 wavevectors: np.ndarray = None, sort: bool = True,
+                 unique: bool = True, n_lags: int = None,
+                 incoherent: bool = False, parallel: bool = False,
+                 verbose: bool = True, **kwargs) -> None:
+        super().__init__(
+            groups, groupings, mode=mode, form=form, dimensions=dimensions,
+            n_points=n_points, n_surfaces=n_surfaces,
+            n_surface_points=n_surface_points, q_max=q_max,
+            wavevectors=wavevectors, sort=sort, unique=unique,
+            parallel=parallel, verbose=verbose, **kwargs
+        )
+        self._dt = float(dt if dt is not None
+                         else getattr(self._trajectory, "dt", 1.0))
+        self._n_lags_arg = n_lags
+        self._incoherent = incoherent
+
+    def _prepare(self) -> None:
+        # reference: structure.py:1899-1957
+        self._n_lags = self._n_lags_arg or self.n_frames
+        if self._n_lags > self.n_frames:
+            raise ValueError("There are fewer frames than time lags.")
+        df = 1
+        if self.n_frames > 1:
+            d = np.diff(self._frame_list)
+            if d[0] <= 0 or not np.allclose(d, d[0]):
+                emsg = ("The selected frames must be evenly spaced and "
+                        "proceed forward in time.")
+                raise ValueError(emsg)
+            df = d[0]
+        self.results.pairs = (
+            tuple(combinations_with_replacement(range(self._n_groups), 2))
+            if self._mode == "partial"
+            else ((0, self._n_groups - 1),) if self._mode == "pair"
+            else ((None, None),)
+        )
+        n_q = len(self._wavenumbers)
+        self.results.cisf = np.zeros((
+            self._n_lags,
+            1 if self._mode is None else len(self.results.pairs), n_q))
+        if self._incoherent:
+            self.results.iisf = np.zeros((
+                self._n_lags,
+                1 if self._mode is None else self._n_groups, n_q))
+        self.results.times = df * self._dt * np.arange(self._n_lags)
+        self.results.wavenumbers = (np.unique(self._wavenumbers.round(11))
+                                    if self._unique else self._wavenumbers)
+        self.results.units = {"results.times": "picosecond",
+                              "results.wavenumbers": "angstrom^-1"}
+
+    def run(self, start: int = None, stop: int = None, step: int = None,
+            frames=None, verbose: bool = None, **kwargs):
+        """Performs the calculation (all ranks stream all frames; the wavevectors
+        are sharded instead, see *Notes*)."""
+        self._setup_frames(self._trajectory, start=start, stop=stop, step=step,
+                           frames=frames)
+        self._prepare()
+        self.n_local_frames = self.n_frames
+        self._process(self._frame_list)
+        self._conclude()
+        return self
+
+    def _process(self, frames: np.ndarray) -> None:
+        ctx = self._context()
+        rank, size = world()
+        n_q = len(self._wavenumbers)
+        cols = np.array_split(np.arange(n_q), size)[rank]
+        self._local_cols = cols
+        offsets = np.concatenate(([0], np.cumsum(self._Ns)))
+        pairs = np.array([(-1, -1) if p[0] is None else p
+                          for p in self.results.pairs], dtype=np.int32)
+        self._local = (np.zeros_like(self.results.cisf),
+                       np.zeros_like(self.results.iisf)
+                       if self._incoherent else None)
+        if len(cols) == 0 or len(frames) == 0:
+            return
+        if self._kernel is not None:
+            mode = self._kernel
+        elif self._lattice_n is None:
+            mode = "general_fp64"
+        else:
+            mode = "lattice_fp32" if self._precision == "fp32" else "lattice_fp64"
+        ctx.sq_configure(
+            int(self._N), offsets, self._wavevectors[cols], pairs,
+            lattice_n=None if self._lattice_n is None else self._lattice_n[cols],
+            lattice_b=self._lattice_b, mode=mode)
+        ctx.isf_configure(self._n_lags, self._incoherent, len(frames))
+
+        atoms_only = all(g == "atoms" for g in self._groupings)
+        if atoms_only:
+            sets = [np.concatenate([g.ix for g in self._groups])]
+            positions_fn = None
+        else:
+            sets = [np.arange(self._N)]
+
+            def positions_fn(ts):
+                return [np.concatenate([
+                    ts.positions[g.ix] if gr == "atoms"
+                    else _centers_of_mass(g, gr, ts.positions[g.ix])
+                    for g, gr in zip(self._groups, self._groupings)
+                ])]
+
+        feeder = FrameFeeder(self._trajectory, sets, frames,
+                             self._default_batch(12 * int(self._N)),
+                             positions_fn)
+        for batch in feeder:
+            ctx.isf_accumulate(batch.ptrs[0], batch.strides[0], batch.n_frames,
+                               keepalive=batch.keepalive)
+            _record(batch)
+        cisf, iisf = ctx.isf_fetch()
+        self._local[0][:, :, cols] = cisf
+        if self._incoherent:
+            # the reference only fills the groups that form a (j, j) pair
+            # (structure.py:2013-2027); with mode=None there is one row
+            if self._mode is None:
+                self._local[1][:, :, cols] = iisf
+            else:
+                for j in {j for j, k in self.results.pairs if j == k}:
+                    self._local[1][:, j, cols] = iisf[:, j]
+
+    def _conclude(self) -> None:
+        # reference: structure.py:2087-2127
+        self.results.cisf = all_reduce_sum(self._local[0], self._device)
+        if self._incoherent:
+            self.results.iisf = all_reduce_sum(self._local[1], self._device)
+        normalization = (
+            self._N * np.arange(self.n_frames,
+                                self.n_frames - self._n_lags, -1)[:, None, None]
+        )
+        self.results.cisf = self.results.cisf / normalization
+        if self._incoherent:
+            self.results.iisf = self.results.iisf / normalization
+        if self._unique:
+            members = [np.isclose(q, self._wavenumbers)
+                       for q in self.results.wavenumbers]
+            self.results.cisf = np.stack(
+                [self.results.cisf[:, :, m].mean(axis=2) for m in members],
+                axis=-1)
+            if self._incoherent:
+                self.results.iisf = np.stack(
+                    [self.results.iisf[:, :, m].mean(axis=2) for m in members],
+                    axis=-1)
+        if self._sort:
+            order = np.argsort(self.results.wavenumbers)
+            self.results.wavenumbers = self.results.wavenumbers[order]
+            self.results.cisf = self.results.cisf[:, :, order]
+            if self._incoherent:
+                self.results.iisf = self.results.iisf[:, :, order]
 
 
 def _closest_factor_pair(value: int) -> tuple:

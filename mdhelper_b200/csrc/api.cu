@@ -213,6 +213,9 @@ int mdh_ctx_destroy(mdh_ctx *c)
     SqState &S = c->sq;
     S.qv.release(); S.items.release(); S.qidx.release(); S.d_pairs.release();
     S.chunks.release(); S.tab.release(); S.rho.release(); S.ssf.release();
+    IsfState &I = c->isf;
+    I.rho_all.release(); I.window[0].release(); I.window[1].release(); I.vmap.release();
+    I.cisf.release(); I.iisf.release();
     c->t_rdf.destroy();
     c->t_sq.destroy();
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -396,6 +399,27 @@ int mdh_sq_fetch_rho(mdh_ctx *c, double *rho)
                              sizeof(double) * per_frame, cudaMemcpyDeviceToHost, c->stream));
     MDH_CUDA(cudaStreamSynchronize(c->stream));
     return MDH_OK;
+}
+
+/* ---- intermediate scattering function (on top of seam #2) ---- */
+
+int mdh_isf_configure(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frames)
+{
+    CTX_GUARD(c);
+    return isf_configure_impl(c, n_lags, incoherent, max_frames);
+}
+
+int mdh_isf_accumulate(mdh_ctx *c, const float *pos, int64_t frame_stride, int location,
+                       int n_frames)
+{
+    CTX_GUARD(c);
+    return isf_accumulate_impl(c, pos, frame_stride, location, n_frames);
+}
+
+int mdh_isf_fetch(mdh_ctx *c, double *cisf, double *iisf)
+{
+    CTX_GUARD(c);
+    return isf_fetch_impl(c, cisf, iisf);
 }
 
 }  // extern "C"

@@ -131,6 +131,19 @@ struct SqState {
     int rho_frames = 0;    // frames held in rho from the last batch
 };
 
+struct IsfState {           // intermediate scattering function on top of SqState
+    bool on = false;
+    int n_lags = 0;
+    bool incoherent = false;
+    int64_t max_frames = 0, n_done = 0;
+    DevBuf rho_all;        // double2[max_frames][n_rho][n_q]: rho(q, t) of every frame
+    DevBuf window[2];      // float[kept + batch][n_total][3], ping-pong
+    int window_frames = 0, which = 0;
+    DevBuf vmap;           // int4 per virtual frame: {frame, reference frame, lag, 0}
+    DevBuf cisf;           // double[n_lags][n_pairs][n_q]
+    DevBuf iisf;           // double[n_lags][n_rho][n_q]
+};
+
 // CUDA-event stopwatch around the hot kernels of every accumulate call, on the
 // context's stream.  Pairs are recorded without synchronising; collect() sums them.
 struct KernelTimer {
@@ -174,6 +187,7 @@ struct mdh_ctx {
     KernelTimer t_rdf, t_sq;
     RdfState rdf;
     SqState sq;
+    IsfState isf;
 };
 
 // rdf.cu
@@ -192,3 +206,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                       int n_pairs, const int32_t *pairs, int mode);
 int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
                        int n_frames);
+int isf_configure_impl(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frames);
+int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
+                        int n_frames);
+int isf_fetch_impl(mdh_ctx *c, double *cisf, double *iisf);

@@ -48,6 +48,10 @@ template <> struct C2<float> { using type = float2; };
 struct LatticeParams {
     const float *raw;              // [F][stride]
     int64_t stride;
+    // optional: virtual frame z -> {frame index of r, frame index of r0 or -1, ., .}:
+    // the sums run over the displacements r - r0 (intermediate scattering function,
+    // structure.py:1991-1996); nullptr: frame z, no reference frame
+    const int4 *vmap;
     const int4 *chunks;            // {start, end, rho_row, 0}
     const SqWorkItem *items;
     const int *qidx;               // [n_items][kSqTM][kSqTN]
@@ -122,7 +126,9 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
     const bool producer = tid >= n_cons;
     const int frame = blockIdx.z;
     const int4 chunk = P.chunks[blockIdx.y];
-    const float *pos = P.raw + (int64_t)frame * P.stride;
+    const int4 vm = P.vmap ? P.vmap[frame] : make_int4(frame, -1, 0, 0);
+    const float *pos = P.raw + (int64_t)vm.x * P.stride;
+    const float *pos0 = vm.y >= 0 ? P.raw + (int64_t)vm.y * P.stride : nullptr;
 
     // tables of particles [p0, p0 + np): task <-> (particle, axis); one fp64 sincos,
     // then E(n+1) = E(n) E(1); rows past np are zero so that the consumers never test
@@ -142,7 +148,11 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
             }
             double s1 = 0.0, c1 = 0.0, er = 0.0, ei = 0.0;
             if (p < np) {
-                sincos(P.b[a] * (double)pos[3 * (int64_t)(p0 + p) + a], &s1, &c1);
+                double x = (double)pos[3 * (int64_t)(p0 + p) + a];
+                // displacement in fp64 of the float32 coordinates: exact, as the
+                // reference's float64 position buffer makes it
+                if (pos0) x -= (double)pos0[3 * (int64_t)(p0 + p) + a];
+                sincos(P.b[a] * x, &s1, &c1);
                 er = 1.0;
             }
             for (int n = 0; n < npad; ++n) {
@@ -218,6 +228,7 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
 struct GeneralParams {
     const float *raw;
     int64_t stride;
+    const int4 *vmap;              // as in LatticeParams
     const int4 *chunks;
     const double *qv;              // [n_q][3]
     double *rho;
@@ -235,7 +246,9 @@ __global__ void __launch_bounds__(128) sq_general_kernel(const GeneralParams P)
     const double qx = qvalid ? P.qv[3 * q] : 0.0;
     const double qy = qvalid ? P.qv[3 * q + 1] : 0.0;
     const double qz = qvalid ? P.qv[3 * q + 2] : 0.0;
-    const float *pos = P.raw + (int64_t)frame * P.stride;
+    const int4 vm = P.vmap ? P.vmap[frame] : make_int4(frame, -1, 0, 0);
+    const float *pos = P.raw + (int64_t)vm.x * P.stride;
+    const float *pos0 = vm.y >= 0 ? P.raw + (int64_t)vm.y * P.stride : nullptr;
     double re = 0.0, im = 0.0;
     for (int p0 = chunk.x; p0 < chunk.y; p0 += 256) {
         const int np = min(256, chunk.y - p0);
@@ -243,6 +256,11 @@ __global__ void __launch_bounds__(128) sq_general_kernel(const GeneralParams P)
             sx[p] = (double)pos[3 * (int64_t)(p0 + p)];
             sy[p] = (double)pos[3 * (int64_t)(p0 + p) + 1];
             sz[p] = (double)pos[3 * (int64_t)(p0 + p) + 2];
+            if (pos0) {
+                sx[p] -= (double)pos0[3 * (int64_t)(p0 + p)];
+                sy[p] -= (double)pos0[3 * (int64_t)(p0 + p) + 1];
+                sz[p] -= (double)pos0[3 * (int64_t)(p0 + p) + 2];
+            }
         }
         __syncthreads();
         if (qvalid) {
@@ -485,6 +503,45 @@ static int sq_build_chunks(mdh_ctx *c, int n_frames)
     return MDH_OK;
 }
 
+// rho[v][row][q] = sum over the particles of row's group of exp(i q . r) for the
+// n_vframes (virtual) frames of `raw`; vmap as in LatticeParams.  Zeroes rho first.
+static int sq_compute_rho(mdh_ctx *c, const float *raw, int64_t stride, const int4 *vmap,
+                          int n_vframes, double *rho, int nominal_frames)
+{
+    SqState &S = c->sq;
+    if (int rc = sq_build_chunks(c, nominal_frames)) return rc;
+    const size_t rho_bytes = sizeof(double) * 2 * (size_t)n_vframes * S.n_rho * S.n_q;
+    MDH_CUDA(cudaMemsetAsync(rho, 0, rho_bytes, c->stream));
+    if (S.lattice) {
+        LatticeParams P;
+        // row layout in table elements: E_x re | E_x im | E_y re | E_y im | E_z (re, im)
+        P.offy = 2 * (S.nmax[0] + 1);
+        P.offz = (P.offy + 2 * (S.nmax[1] + 1) + 3) / 4 * 4;     // 16-byte aligned
+        P.nt = P.offz + 2 * ((S.nmax[2] + kSqTN) / kSqTN * kSqTN);
+        P.raw = raw; P.stride = stride; P.vmap = vmap;
+        P.chunks = S.chunks.as<int4>();
+        P.items = S.items.as<SqWorkItem>();
+        P.qidx = S.qidx.as<int>();
+        P.rho = rho;
+        P.n_rho = S.n_rho; P.n_q = S.n_q;
+        for (int k = 0; k < 3; ++k) { P.b[k] = S.b[k]; P.nmax[k] = S.nmax[k]; }
+        dim3 grid(S.n_items / S.block, S.n_chunks, n_vframes);
+        return S.mode == MDH_SQ_LATTICE_FP32 ? launch_lattice<float>(c, P, grid, S.block)
+                                             : launch_lattice<double>(c, P, grid, S.block);
+    }
+    GeneralParams P;
+    P.raw = raw; P.stride = stride; P.vmap = vmap;
+    P.chunks = S.chunks.as<int4>();
+    P.qv = S.qv.as<double>();
+    P.rho = rho;
+    P.n_rho = S.n_rho; P.n_q = S.n_q;
+    dim3 grid((S.n_q + 127) / 128, S.n_chunks, n_vframes);
+    sq_general_kernel<<<grid, 128, 0, c->stream>>>(P);
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    return MDH_OK;
+}
+
 static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int location,
                                int n_frames, int nominal_frames);
 
@@ -533,46 +590,12 @@ static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int
         dsrc = raw.as<float>();
         dstride = 3 * S.n_total;
     }
-    LatticeParams LP;
-    if (S.lattice) {
-        // row layout in table elements: E_x re | E_x im | E_y re | E_y im | E_z (re, im)
-        LP.offy = 2 * (S.nmax[0] + 1);
-        LP.offz = (LP.offy + 2 * (S.nmax[1] + 1) + 3) / 4 * 4;     // 16-byte aligned
-        LP.nt = LP.offz + 2 * ((S.nmax[2] + kSqTN) / kSqTN * kSqTN);
-    }
-    if (int rc = sq_build_chunks(c, nominal_frames)) return rc;
     const size_t rho_bytes = sizeof(double) * 2 * (size_t)n_frames * S.n_rho * S.n_q;
     if (int rc = S.rho.reserve(rho_bytes)) return rc;
 
     if (int rc = c->t_sq.begin(c->stream)) return rc;
-    MDH_CUDA(cudaMemsetAsync(S.rho.p, 0, rho_bytes, c->stream));
-
-    if (S.lattice) {
-        LatticeParams P = LP;
-        P.raw = dsrc; P.stride = dstride;
-        P.chunks = S.chunks.as<int4>();
-        P.items = S.items.as<SqWorkItem>();
-        P.qidx = S.qidx.as<int>();
-        P.rho = S.rho.as<double>();
-        P.n_rho = S.n_rho; P.n_q = S.n_q;
-        for (int k = 0; k < 3; ++k) { P.b[k] = S.b[k]; P.nmax[k] = S.nmax[k]; }
-        dim3 grid(S.n_items / S.block, S.n_chunks, n_frames);
-        int rc;
-        if (S.mode == MDH_SQ_LATTICE_FP32) rc = launch_lattice<float>(c, P, grid, S.block);
-        else rc = launch_lattice<double>(c, P, grid, S.block);
-        if (rc) return rc;
-    } else {
-        GeneralParams P;
-        P.raw = dsrc; P.stride = dstride;
-        P.chunks = S.chunks.as<int4>();
-        P.qv = S.qv.as<double>();
-        P.rho = S.rho.as<double>();
-        P.n_rho = S.n_rho; P.n_q = S.n_q;
-        dim3 grid((S.n_q + 127) / 128, S.n_chunks, n_frames);
-        sq_general_kernel<<<grid, 128, 0, c->stream>>>(P);
-        MDH_CUDA(cudaGetLastError());
-        c->launches++;
-    }
+    if (int rc = sq_compute_rho(c, dsrc, dstride, nullptr, n_frames, S.rho.as<double>(),
+                                nominal_frames)) return rc;
     dim3 fgrid((S.n_q + 127) / 128, S.n_pairs);
     sq_finalize_kernel<<<fgrid, 128, 0, c->stream>>>(S.rho.as<double2>(), n_frames, S.n_rho,
                                                      S.n_q, S.d_pairs.as<int>(), S.n_pairs,
@@ -583,4 +606,193 @@ static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int
     if (location == MDH_HOST)
         if (int rc = c->stager.retire(c->stream, slot)) return rc;
     return c->t_sq.end(c->stream);
+}
+
+// ---- intermediate scattering function ---------------
+// Replaces the per-frame work of IntermediateScatteringFunction._single_frame
+// (/root/reference/src/mdhelper/analysis/structure.py:1959-2085):
+//   coherent:    rho(q, t) of every frame is kept on the device; at fetch time
+//                cisf[lag][pair] = sum_t Re(rho_j(t - lag) conj(rho_k(t))) (+ j <-> k)
+//   incoherent:  iisf[lag][group] += Re sum_particles exp(i q . (r(t) - r(t - lag)))
+//                -- the S(q) kernels on displacement vectors of a coordinate window
+//                that holds the last n_lags - 1 frames.
+// Normalisation, unique-|q| grouping and sorting stay on the host.
+
+namespace {
+
+__global__ void isf_coherent_kernel(const double2 *__restrict__ rho, int n_frames, int n_rho,
+                                    int n_q, const int *__restrict__ pairs, int n_pairs,
+                                    double *__restrict__ cisf)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y, lag = blockIdx.z;
+    if (q >= n_q) return;
+    int j = pairs[2 * p], k = pairs[2 * p + 1];
+    if (j < 0) j = k = 0;
+    double acc = 0.0;
+    for (int t = lag; t < n_frames; ++t) {
+        const double2 aj = rho[((int64_t)(t - lag) * n_rho + j) * n_q + q];
+        const double2 bk = rho[((int64_t)t * n_rho + k) * n_q + q];
+        acc += aj.x * bk.x + aj.y * bk.y;              // Re(rho_j(t0) conj(rho_k(t)))
+        if (j != k) {
+            const double2 ak = rho[((int64_t)(t - lag) * n_rho + k) * n_q + q];
+            const double2 bj = rho[((int64_t)t * n_rho + j) * n_q + q];
+            acc += ak.x * bj.x + ak.y * bj.y;
+        }
+    }
+    cisf[((int64_t)lag * n_pairs + p) * n_q + q] = acc;
+}
+
+// iisf[lag(v)][row][q] += Re rho_tmp[v][row][q]; one thread per (row, q) walks the
+// virtual frames of the batch in order (deterministic, no atomics)
+__global__ void isf_incoherent_kernel(const double2 *__restrict__ rho_tmp,
+                                      const int4 *__restrict__ vmap, int n_v, int n_rho,
+                                      int n_q, double *__restrict__ iisf)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (q >= n_q) return;
+    for (int v = 0; v < n_v; ++v) {
+        const int lag = vmap[v].z;
+        iisf[((int64_t)lag * n_rho + row) * n_q + q] +=
+            rho_tmp[((int64_t)v * n_rho + row) * n_q + q].x;
+    }
+}
+
+}  // namespace
+
+int isf_configure_impl(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frames)
+{
+    SqState &S = c->sq;
+    IsfState &I = c->isf;
+    MDH_REQUIRE(S.configured, MDH_ESTATE, "isf: the wavevectors are not configured");
+    MDH_REQUIRE(n_lags >= 1 && n_lags <= 65535, MDH_EINVAL, "isf: n_lags must be in [1, 65535]");
+    MDH_REQUIRE(max_frames >= n_lags, MDH_EINVAL, "isf: fewer frames than time lags");
+    I.on = false;
+    I.n_lags = n_lags; I.incoherent = incoherent != 0; I.max_frames = max_frames;
+    I.n_done = 0; I.window_frames = 0; I.which = 0;
+    const size_t row = sizeof(double) * 2 * (size_t)S.n_rho * S.n_q;
+    if (int rc = I.rho_all.reserve(row * (size_t)max_frames)) return rc;
+    if (int rc = I.cisf.reserve(sizeof(double) * (size_t)n_lags * S.n_pairs * S.n_q)) return rc;
+    if (I.incoherent) {
+        const size_t bytes = sizeof(double) * (size_t)n_lags * S.n_rho * S.n_q;
+        if (int rc = I.iisf.reserve(bytes)) return rc;
+        MDH_CUDA(cudaMemsetAsync(I.iisf.p, 0, bytes, c->stream));
+    }
+    I.on = true;
+    return MDH_OK;
+}
+
+int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
+                        int n_frames)
+{
+    SqState &S = c->sq;
+    IsfState &I = c->isf;
+    MDH_REQUIRE(S.configured && I.on, MDH_ESTATE, "isf: accumulate before configure");
+    MDH_REQUIRE(n_frames >= 1 && n_frames <= 65535, MDH_EINVAL,
+                "isf: n_frames per call must be in [1, 65535]");
+    MDH_REQUIRE(pos != nullptr, MDH_EINVAL, "isf: coordinate pointer is NULL");
+    MDH_REQUIRE(stride >= 3 * S.n_total, MDH_EINVAL, "isf: frame_stride < 3*n_total");
+    MDH_REQUIRE(location == MDH_HOST || location == MDH_DEVICE, MDH_EINVAL,
+                "isf: invalid location");
+    MDH_REQUIRE(I.n_done + n_frames <= I.max_frames, MDH_EINVAL,
+                "isf: more frames than announced at configure (%lld)", (long long)I.max_frames);
+
+    // coordinate window: [frames kept from earlier calls][the frames of this call]
+    const int64_t fsz = 3 * S.n_total;                     // floats per frame
+    const int keep = I.window_frames;
+    DevBuf &win = I.window[I.which];
+    const size_t need = sizeof(float) * fsz * (size_t)(keep + n_frames);
+    if (win.cap < need) {
+        // grow WITHOUT losing the frames kept from earlier calls (DevBuf::reserve frees)
+        DevBuf bigger;
+        if (int rc = bigger.reserve(need)) return rc;
+        if (keep > 0)
+            MDH_CUDA(cudaMemcpyAsync(bigger.p, win.p, sizeof(float) * fsz * (size_t)keep,
+                                     cudaMemcpyDeviceToDevice, c->stream));
+        MDH_CUDA(cudaStreamSynchronize(c->stream));
+        win.release();
+        win = bigger;
+    }
+    MDH_CUDA(cudaMemcpy2DAsync(win.as<float>() + fsz * keep, sizeof(float) * fsz, pos,
+                               sizeof(float) * stride, sizeof(float) * fsz, n_frames,
+                               location == MDH_HOST ? cudaMemcpyHostToDevice
+                                                    : cudaMemcpyDeviceToDevice, c->stream));
+    if (int rc = c->t_sq.begin(c->stream)) return rc;
+
+    // rho(q, t) of the new frames, straight into the per-frame store
+    const size_t row = (size_t)2 * S.n_rho * S.n_q;        // doubles per frame
+    if (int rc = sq_compute_rho(c, win.as<float>() + fsz * keep, fsz, nullptr, n_frames,
+                                I.rho_all.as<double>() + row * I.n_done, n_frames)) return rc;
+
+    if (I.incoherent) {
+        // virtual frames (t, lag): displacement r(t) - r(t - lag), lag = 0 included
+        // (the reference evaluates it too: sum of exp(0) = N)
+        std::vector<int4> vm;
+        for (int t = 0; t < n_frames; ++t) {
+            const int64_t tg = I.n_done + t;                // global frame index
+            const int lags = (int)std::min<int64_t>(I.n_lags, tg + 1);
+            for (int lag = 0; lag < lags; ++lag)
+                vm.push_back(make_int4(keep + t, keep + t - lag, lag, 0));
+        }
+        // batches sized to ~256 MB of temporary rho
+        const int vmax = (int)std::max<size_t>(1, std::min<size_t>(
+            8192, ((size_t)256 << 20) / (sizeof(double) * row)));
+        if (int rc = I.vmap.reserve(sizeof(int4) * (size_t)vmax)) return rc;
+        if (int rc = S.rho.reserve(sizeof(double) * row * (size_t)vmax)) return rc;
+        for (size_t v0 = 0; v0 < vm.size(); v0 += vmax) {
+            const int nv = (int)std::min<size_t>(vmax, vm.size() - v0);
+            // pageable source: staged by the runtime before the call returns
+            MDH_CUDA(cudaMemcpyAsync(I.vmap.p, vm.data() + v0, sizeof(int4) * nv,
+                                     cudaMemcpyHostToDevice, c->stream));
+            if (int rc = sq_compute_rho(c, win.as<float>(), fsz, I.vmap.as<int4>(), nv,
+                                        S.rho.as<double>(), std::max(nv, 64))) return rc;
+            dim3 grid((S.n_q + 127) / 128, S.n_rho);
+            isf_incoherent_kernel<<<grid, 128, 0, c->stream>>>(
+                S.rho.as<double2>(), I.vmap.as<int4>(), nv, S.n_rho, S.n_q,
+                I.iisf.as<double>());
+            MDH_CUDA(cudaGetLastError());
+            c->launches++;
+        }
+        // keep the last n_lags - 1 frames for the next call (other window buffer)
+        const int total = keep + n_frames;
+        const int next_keep = std::min(total, I.n_lags - 1);
+        DevBuf &nxt = I.window[I.which ^ 1];
+        if (next_keep > 0) {
+            if (int rc = nxt.reserve(sizeof(float) * fsz * (size_t)next_keep)) return rc;
+            MDH_CUDA(cudaMemcpyAsync(nxt.p, win.as<float>() + fsz * (total - next_keep),
+                                     sizeof(float) * fsz * next_keep,
+                                     cudaMemcpyDeviceToDevice, c->stream));
+        }
+        I.window_frames = next_keep;
+        I.which ^= 1;
+    }
+    I.n_done += n_frames;
+    S.rho_frames = 0;
+    return c->t_sq.end(c->stream);
+}
+
+int isf_fetch_impl(mdh_ctx *c, double *cisf, double *iisf)
+{
+    SqState &S = c->sq;
+    IsfState &I = c->isf;
+    MDH_REQUIRE(S.configured && I.on, MDH_ESTATE, "isf: fetch before configure");
+    MDH_REQUIRE(cisf != nullptr, MDH_EINVAL, "isf: cisf is NULL");
+    MDH_REQUIRE(!iisf || I.incoherent, MDH_EINVAL,
+                "isf: the incoherent part was not requested at configure");
+    MDH_REQUIRE(I.n_done >= 1, MDH_ESTATE, "isf: no frame has been processed");
+    dim3 grid((S.n_q + 127) / 128, S.n_pairs, I.n_lags);
+    isf_coherent_kernel<<<grid, 128, 0, c->stream>>>(I.rho_all.as<double2>(), (int)I.n_done,
+                                                     S.n_rho, S.n_q, S.d_pairs.as<int>(),
+                                                     S.n_pairs, I.cisf.as<double>());
+    MDH_CUDA(cudaGetLastError());
+    c->launches++;
+    MDH_CUDA(cudaMemcpyAsync(cisf, I.cisf.p, sizeof(double) * (size_t)I.n_lags * S.n_pairs * S.n_q,
+                             cudaMemcpyDeviceToHost, c->stream));
+    if (iisf)
+        MDH_CUDA(cudaMemcpyAsync(iisf, I.iisf.p,
+                                 sizeof(double) * (size_t)I.n_lags * S.n_rho * S.n_q,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    MDH_CUDA(cudaStreamSynchronize(c->stream));
+    return MDH_OK;
 }

@@ -64,9 +64,18 @@ class Timestep:
 
 
 class _SlicedTrajectory:
-    def __init__(self, trajectory, frames):
+    """``trajectory[slice]`` / ``trajectory[indices]``.  Like MDAnalysis'
+    ``FrameIteratorSliced`` / ``FrameIteratorIndices`` it carries ``step`` (slices)
+    or ``frames`` (index arrays), which the reference's
+    ``IntermediateScatteringFunction._prepare`` reads (``structure.py:1907-1917``)."""
+
+    def __init__(self, trajectory, frames, step=None):
         self._trajectory = trajectory
         self._frames = frames
+        if step is not None:
+            self.step = step
+        else:
+            self.frames = np.asarray(frames)
 
     def __len__(self):
         return len(self._frames)
@@ -136,9 +145,8 @@ class MemoryTrajectory:
             self._frame = item
             return self._ts(item)
         if isinstance(item, slice):
-            return _SlicedTrajectory(
-                self, np.arange(*item.indices(self.n_frames))
-            )
+            start, stop, step = item.indices(self.n_frames)
+            return _SlicedTrajectory(self, np.arange(start, stop, step), step=step)
         item = np.asarray(item)
         if item.dtype == bool:
             item = np.nonzero(item)[0]

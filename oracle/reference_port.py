@@ -232,3 +232,89 @@ def ssf_run(universe, groups, *, mode=None, wavevectors=None, n_points=32,
         wn_out, ssf = wn_out[order], ssf[:, order]
     return {"pairs": pairs, "wavenumbers": wn_out, "ssf": ssf,
             "wavevectors": wavevectors}
+
+
+def isf_run(universe, groups, *, mode=None, wavevectors=None, n_points=32,
+            q_max=None, sort=True, unique=True, n_lags=None, incoherent=False,
+            dt=None, start=None, stop=None, step=None, n_threads=1):
+    """
+    Restates ``IntermediateScatteringFunction`` with ``form="exp"``,
+    ``groupings="atoms"``: ``_prepare`` (``structure.py:1899-1957``), the sliding
+    window of ``_single_frame`` (``:1959-2033``) and ``_conclude`` (``:2087-2127``).
+    """
+    traj = universe.trajectory
+    sl = slice(start, stop, step).indices(len(traj))
+    frames = np.arange(*sl)
+    n_frames = len(frames)
+    df = sl[2]
+    dt = traj.dt if dt is None else dt
+    if wavevectors is None:
+        wavevectors, wavenumbers = lattice_wavevectors(
+            universe.dimensions[:3].copy(), n_points, q_max)
+    else:
+        wavevectors = np.asarray(wavevectors, dtype=np.float64)
+        wavenumbers = np.linalg.norm(wavevectors, axis=1)
+        if q_max is not None:
+            keep = wavenumbers <= q_max
+            wavevectors, wavenumbers = wavevectors[keep], wavenumbers[keep]
+    n_groups = len(groups)
+    n_lags = n_lags or n_frames
+    pairs = (tuple(combinations_with_replacement(np.arange(n_groups).tolist(), 2))
+             if mode == "partial"
+             else ((0, n_groups - 1),) if mode == "pair" else ((None, None),))
+    Ns = [g.n_atoms for g in groups]
+    N = sum(Ns)
+    slices, idx = [], 0
+    for n in Ns:
+        slices.append(slice(idx, idx + n))
+        idx += n
+    n_q = len(wavenumbers)
+    positions = np.zeros((n_lags, N, 3))
+    exp_sum = np.empty((n_lags, 1 if mode is None else n_groups, n_q), dtype=complex)
+    cisf = np.zeros((n_lags, 1 if mode is None else len(pairs), n_q))
+    iisf = np.zeros((n_lags, 1 if mode is None else n_groups, n_q)) if incoherent else None
+    dfts = lambda r: delta_fourier_transform_sum(wavevectors, r, n_threads)  # noqa: E731
+    for fi, f in enumerate(frames):
+        traj[int(f)]
+        rcfi = fi % n_lags
+        for g, s in zip(groups, slices):
+            positions[rcfi, s] = g.positions
+        if mode is None:
+            exp_sum[rcfi] = dfts(positions[rcfi])
+            for lag in range(min(n_lags, fi + 1)):
+                rifi = (fi - lag) % n_lags
+                cisf[lag] += (exp_sum[rifi] * exp_sum[rcfi].conj()).real
+                if incoherent:
+                    iisf[lag] += dfts(positions[rcfi] - positions[rifi]).real
+        else:
+            for i in range(n_groups):
+                exp_sum[rcfi, i] = dfts(positions[rcfi, slices[i]])
+            for lag in range(min(n_lags, fi + 1)):
+                rifi = (fi - lag) % n_lags
+                for i, (j, k) in enumerate(pairs):
+                    if j == k:
+                        cisf[lag, i] += (exp_sum[rifi, j] * exp_sum[rcfi, j].conj()).real
+                        if incoherent:
+                            iisf[lag, j] += dfts(positions[rcfi, slices[j]]
+                                                 - positions[rifi, slices[j]]).real
+                    else:
+                        cisf[lag, i] += ((exp_sum[rifi, j] * exp_sum[rcfi, k].conj()).real
+                                         + (exp_sum[rifi, k] * exp_sum[rcfi, j].conj()).real)
+    normalization = N * np.arange(n_frames, n_frames - n_lags, -1)[:, None, None]
+    cisf /= normalization
+    if incoherent:
+        iisf /= normalization
+    wn_out = np.unique(wavenumbers.round(11)) if unique else wavenumbers
+    if unique:
+        cisf = np.stack([cisf[:, :, np.isclose(q, wavenumbers)].mean(axis=2)
+                         for q in wn_out], axis=-1)
+        if incoherent:
+            iisf = np.stack([iisf[:, :, np.isclose(q, wavenumbers)].mean(axis=2)
+                             for q in wn_out], axis=-1)
+    if sort:
+        order = np.argsort(wn_out)
+        wn_out, cisf = wn_out[order], cisf[:, :, order]
+        if incoherent:
+            iisf = iisf[:, :, order]
+    return {"pairs": pairs, "wavenumbers": wn_out, "cisf": cisf, "iisf": iisf,
+            "times": df * dt * np.arange(n_lags), "wavevectors": wavevectors}

@@ -44,3 +44,42 @@ class FakeSSF(structure.StructureFactor):
                     rk = rp.delta_fourier_transform_sum(self._wavevectors,
                                                         pos[offs[k]:offs[k + 1]])
                     self._local_ssf[i] += 2 * (rj * rk.conj()).real
+
+
+class FakeISF(structure.IntermediateScatteringFunction):
+    """rho(q, t) and the displacement sums from the CPU oracle for this rank's
+    wavevector columns; the window logic is the reference's (structure.py:1959-2033)."""
+
+    def _process(self, frames):
+        from mdhelper_b200.analysis.base import world
+        rank, size = world()
+        n_q = len(self._wavenumbers)
+        cols = np.array_split(np.arange(n_q), size)[rank]
+        self._local_cols = cols
+        offs = np.concatenate(([0], np.cumsum(self._Ns)))
+        n_rho = 1 if self._mode is None else self._n_groups
+        cisf = np.zeros_like(self.results.cisf)
+        iisf = np.zeros_like(self.results.iisf) if self._incoherent else None
+        self._local = (cisf, iisf)
+        if len(cols) == 0:
+            return
+        wv = self._wavevectors[cols]
+        rows = [slice(0, int(self._N))] if self._mode is None else \
+            [slice(offs[i], offs[i + 1]) for i in range(self._n_groups)]
+        pos, rho = [], []
+        for f in frames:
+            self._trajectory[int(f)]
+            p = np.concatenate([g.positions for g in self._groups]).astype(np.float64)
+            pos.append(p)
+            rho.append([rp.delta_fourier_transform_sum(wv, p[r]) for r in rows])
+        for t in range(len(frames)):
+            for lag in range(min(self._n_lags, t + 1)):
+                for i, (j, k) in enumerate(self.results.pairs):
+                    if j is None:
+                        j = k = 0
+                    cisf[lag, i, cols] += (rho[t - lag][j] * rho[t][k].conj()).real
+                    if j != k:
+                        cisf[lag, i, cols] += (rho[t - lag][k] * rho[t][j].conj()).real
+                    elif self._incoherent:
+                        iisf[lag, j, cols] += rp.delta_fourier_transform_sum(
+                            wv, pos[t][rows[j]] - pos[t - lag][rows[j]]).real

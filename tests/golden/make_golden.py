@@ -226,12 +226,56 @@ def sq_cases(S):
     print("sq cfg4", s.results.ssf.shape, su.results.ssf.shape)
 
 
+def isf_cases(S):
+    """IntermediateScatteringFunction (structure.py:1552-2127), the real class: the
+    coherent and incoherent parts, all modes, a strided frame selection, both forms,
+    user wavevectors (off the lattice)."""
+    u, cat, an = synthetic.electrolyte(600, 14, seed=20260009)
+    pos = u.trajectory.coordinates.copy()
+    dims = u.trajectory.unitcells[0].copy()
+    L = float(dims[0])
+    out = dict(positions=pos, dims=dims, n_cat=cat.n_atoms, n_points=8,
+               q_max=2 * np.pi * 5 / L, n_lags=5, dt=0.25)
+    common = dict(n_points=8, q_max=out["q_max"], n_lags=5, incoherent=True, dt=0.25,
+                  verbose=False)
+    for mode, groups in ((None, [cat, an]), ("pair", [cat, an]), ("partial", [cat, an])):
+        for form in ("exp", "trig"):
+            r = S.IntermediateScatteringFunction(groups, mode=mode, form=form,
+                                                 **common).run()
+            key = f"{mode}_{form}"
+            out[f"cisf_{key}"] = r.results.cisf
+            out[f"iisf_{key}"] = r.results.iisf
+            out[f"wavenumbers_{key}"] = r.results.wavenumbers
+            out[f"times_{key}"] = r.results.times
+    # strided frames, default n_lags (= number of frames), raw ordering
+    r = S.IntermediateScatteringFunction([u.atoms], n_points=8, q_max=out["q_max"],
+                                         incoherent=True, sort=False, unique=False,
+                                         dt=0.25, verbose=False).run(start=2, stop=14,
+                                                                     step=3)
+    out["cisf_strided"] = r.results.cisf
+    out["iisf_strided"] = r.results.iisf
+    out["times_strided"] = r.results.times
+    rng = np.random.default_rng(20260010)
+    wv = rng.normal(size=(23, 3)) * 1.5
+    r = S.IntermediateScatteringFunction([cat, an], mode="partial", wavevectors=wv,
+                                         n_lags=4, incoherent=True, sort=False,
+                                         unique=False, dt=0.25, verbose=False).run()
+    out["wavevectors_user"] = wv
+    out["cisf_user"] = r.results.cisf
+    out["iisf_user"] = r.results.iisf
+    np.savez_compressed(OUT / "isf_small.npz", **out)
+    print("isf small", out["cisf_None_exp"].shape, out["cisf_partial_exp"].shape,
+          "exp vs trig", np.abs(out["cisf_partial_exp"] - out["cisf_partial_trig"]).max())
+
+
 if __name__ == "__main__":
     S = ref_harness.load()
-    which = sys.argv[1:] or ["kat", "rdf", "sq"]
+    which = sys.argv[1:] or ["kat", "rdf", "sq", "isf"]
     if "kat" in which:
         kat_radial_histogram(S)
     if "rdf" in which:
         rdf_cases(S)
     if "sq" in which:
         sq_cases(S)
+    if "isf" in which:
+        isf_cases(S)

@@ -21,7 +21,7 @@ def _worker(rank, world_size, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
     try:
-        from _fake import FakeRDF, FakeSSF
+        from _fake import FakeISF, FakeRDF, FakeSSF
         from mdhelper_b200.universe import SyntheticUniverse
         g = dict(np.load(GOLDEN / "rdf_lj1000.npz"))
         u = SyntheticUniverse(g["positions"], g["dims"])
@@ -46,6 +46,22 @@ def _worker(rank, world_size, port, out_dir):
         assert s.n_local_frames == 1
         np.testing.assert_allclose(s.results.ssf, g["ssf_partial_exp"], rtol=1e-9,
                                    atol=1e-12)
+        # intermediate scattering function: wavevector columns are sharded, every
+        # rank streams all frames, one all-reduce assembles the columns
+        g = dict(np.load(GOLDEN / "isf_small.npz"))
+        u = SyntheticUniverse(g["positions"], g["dims"])
+        n = int(g["n_cat"])
+        cat, an = u.select(slice(0, n)), u.select(slice(n, u.atoms.n_atoms))
+        f = FakeISF([cat, an], mode="partial", n_points=int(g["n_points"]),
+                    q_max=float(g["q_max"]), n_lags=int(g["n_lags"]), incoherent=True,
+                    dt=float(g["dt"]), verbose=False).run()
+        n_q = len(f._wavenumbers)
+        assert len(f._local_cols) == len(np.array_split(np.arange(n_q), 2)[rank])
+        assert 0 < len(f._local_cols) < n_q and f.n_local_frames == 14
+        np.testing.assert_allclose(f.results.cisf, g["cisf_partial_exp"], rtol=1e-9,
+                                   atol=1e-10)
+        np.testing.assert_allclose(f.results.iisf, g["iisf_partial_exp"], rtol=1e-9,
+                                   atol=1e-10)
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), r.results.counts)
     finally:
         dist.destroy_process_group()

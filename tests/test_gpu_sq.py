@@ -133,6 +133,79 @@ def test_frame_additivity_and_selection():
     assert s.results.ssf.shape[0] == 1 and np.isfinite(s.results.ssf).all()
 
 
+# ---- intermediate scattering function ------------------
+
+@pytest.mark.parametrize("kernel", [None, "general_fp64"])
+@pytest.mark.parametrize("mode", [None, "pair", "partial"])
+def test_isf_matches_golden(golden, mode, kernel):
+    """GPU IntermediateScatteringFunction vs the fixtures of the reference's real class:
+    coherent and incoherent parts, all modes, lattice and general kernels, a batch size
+    that cuts the run into several accumulate calls (window hand-over)."""
+    g = golden("isf_small")
+    u = universe_from(g)
+    cat, an = _groups(u, g)
+    for form, bf in (("exp", 3), ("trig", None)):
+        r = _S().IntermediateScatteringFunction(
+            [cat, an], mode=mode, form=form, n_points=int(g["n_points"]),
+            q_max=float(g["q_max"]), n_lags=int(g["n_lags"]), incoherent=True,
+            dt=float(g["dt"]), kernel=kernel, batch_frames=bf, verbose=False).run()
+        np.testing.assert_allclose(r.results.cisf, g[f"cisf_{mode}_{form}"], rtol=1e-9,
+                                   atol=1e-10)
+        np.testing.assert_allclose(r.results.iisf, g[f"iisf_{mode}_{form}"], rtol=1e-9,
+                                   atol=1e-10)
+        np.testing.assert_allclose(r.results.times, g[f"times_{mode}_{form}"])
+        np.testing.assert_allclose(r.results.wavenumbers,
+                                   g[f"wavenumbers_{mode}_{form}"], rtol=1e-13)
+
+
+def test_isf_strided_frames_user_wavevectors_and_properties(golden):
+    g = golden("isf_small")
+    u = universe_from(g)
+    cat, an = _groups(u, g)
+    S = _S()
+    r = S.IntermediateScatteringFunction(
+        [u.atoms], n_points=int(g["n_points"]), q_max=float(g["q_max"]), incoherent=True,
+        sort=False, unique=False, dt=float(g["dt"]), verbose=False,
+        batch_frames=2).run(start=2, stop=14, step=3)
+    np.testing.assert_allclose(r.results.cisf, g["cisf_strided"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(r.results.iisf, g["iisf_strided"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(r.results.times, g["times_strided"])
+    # F_s(q, 0) = 1;  F(q, 0) = S(q) of the same frames
+    np.testing.assert_allclose(r.results.iisf[0], 1.0, rtol=1e-12)
+    s = S.StructureFactor([u.atoms], n_points=int(g["n_points"]), q_max=float(g["q_max"]),
+                          sort=False, unique=False, verbose=False).run(start=2, stop=14,
+                                                                       step=3)
+    np.testing.assert_allclose(r.results.cisf[0], s.results.ssf, rtol=1e-9, atol=1e-12)
+    # without the incoherent part; user wavevectors off the lattice
+    r = S.IntermediateScatteringFunction(
+        [cat, an], mode="partial", wavevectors=g["wavevectors_user"], n_lags=4,
+        incoherent=True, sort=False, unique=False, dt=float(g["dt"]), verbose=False).run()
+    np.testing.assert_allclose(r.results.cisf, g["cisf_user"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(r.results.iisf, g["iisf_user"], rtol=1e-9, atol=1e-10)
+    r2 = S.IntermediateScatteringFunction(
+        [cat, an], mode="partial", wavevectors=g["wavevectors_user"], n_lags=4,
+        sort=False, unique=False, dt=float(g["dt"]), verbose=False).run()
+    assert r2.results.iisf is None
+    np.testing.assert_allclose(r2.results.cisf, r.results.cisf, rtol=1e-13)
+    with pytest.raises(ValueError):        # frames must be evenly spaced
+        S.IntermediateScatteringFunction([u.atoms], n_points=4, verbose=False).run(
+            frames=[0, 1, 3])
+
+
+def test_isf_larger_system_against_oracle():
+    """5,000 particles, 12 frames, 6 lags, lattice kernel vs the CPU oracle."""
+    from mdhelper_b200 import synthetic
+    from oracle import reference_port as rp
+    u = synthetic.lj_fluid(5000, 12, seed=77)
+    L = float(u.dimensions[0])
+    kw = dict(n_points=10, q_max=2 * np.pi * 6 / L, n_lags=6, incoherent=True, dt=2.0)
+    r = _S().IntermediateScatteringFunction([u.atoms], verbose=False, batch_frames=5,
+                                            **kw).run()
+    o = rp.isf_run(u, [u.atoms], n_threads=8, **kw)
+    np.testing.assert_allclose(r.results.cisf, o["cisf"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(r.results.iisf, o["iisf"], rtol=1e-9, atol=1e-10)
+
+
 def test_argument_errors():
     from mdhelper_b200 import _lib
     ctx = _lib.Context(0)

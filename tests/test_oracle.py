@@ -96,6 +96,33 @@ def test_sq_port_noncubic(golden):
 
 
 @pytest.mark.skipif(not ref_harness.available(), reason="/root/reference not present")
+@pytest.mark.parametrize("mode", [None, "pair", "partial"])
+def test_isf_port_matches_golden(golden, mode):
+    """oracle isf_run vs fixtures produced by the reference's real
+    IntermediateScatteringFunction (both forms are stored; the port restates form=exp)."""
+    g = golden("isf_small")
+    u = universe_from(g)
+    n = int(g["n_cat"])
+    cat, an = u.select(slice(0, n)), u.select(slice(n, u.atoms.n_atoms))
+    o = rp.isf_run(u, [cat, an], mode=mode, n_points=int(g["n_points"]),
+                   q_max=float(g["q_max"]), n_lags=int(g["n_lags"]), incoherent=True,
+                   dt=float(g["dt"]))
+    for form in ("exp", "trig"):
+        np.testing.assert_allclose(o["cisf"], g[f"cisf_{mode}_{form}"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(o["iisf"], g[f"iisf_{mode}_{form}"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(o["times"], g[f"times_{mode}_exp"])
+    np.testing.assert_allclose(o["wavenumbers"], g[f"wavenumbers_{mode}_exp"], rtol=1e-13)
+    if mode is None:
+        o = rp.isf_run(u, [u.atoms], n_points=int(g["n_points"]), q_max=float(g["q_max"]),
+                       incoherent=True, sort=False, unique=False, dt=float(g["dt"]),
+                       start=2, stop=14, step=3)
+        np.testing.assert_allclose(o["cisf"], g["cisf_strided"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(o["iisf"], g["iisf_strided"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(o["times"], g["times_strided"])
+        # F_s(q, 0) = 1 and F(q, 0) = S(q)
+        np.testing.assert_allclose(o["iisf"][0], 1.0, rtol=1e-12)
+
+
 def test_port_matches_live_reference():
     """Where the reference tree exists, the port is checked against the real classes."""
     from mdhelper_b200 import synthetic
