@@ -18,7 +18,8 @@ sys.path.insert(0, str(ROOT))
 import torch  # noqa: E402
 
 from mdhelper_b200 import synthetic  # noqa: E402
-from mdhelper_b200.analysis.structure import (RadialDistributionFunction,  # noqa: E402
+from mdhelper_b200.analysis.structure import (IntermediateScatteringFunction,  # noqa: E402
+                                              RadialDistributionFunction,
                                               StructureFactor)
 
 
@@ -100,5 +101,28 @@ def main():
                           / 18529.6e9}), flush=True)
 
 
+def isf():
+    """Scope table 8(f) rank 1: F(q, t) and F_s(q, t) of the cfg4 system, 96 frames, 32
+    lags -- 96 rho(q, t) sums and 2,576 displacement sums of 50,000 x 2,446 terms."""
+    u = synthetic.lj_fluid(50_000, 96, seed=20260011)
+    L = float(u.dimensions[0])
+    kw = dict(n_points=32, q_max=2 * np.pi * 16 / L, n_lags=32, verbose=False,
+              batch_frames=32)
+    for inc in (False, True):
+        f = IntermediateScatteringFunction([u.atoms], incoherent=inc, **kw)
+        dt, _, sms = timed(f)
+        nq = len(f._wavenumbers)
+        sums = 96 + (sum(min(32, t + 1) for t in range(96)) if inc else 0)
+        print(json.dumps({"config": f"isf: 50k particles, 96 frames, 32 lags, "
+                                    f"incoherent={inc}", "n_q": nq, "direct_sums": sums,
+                          "e2e_s": dt, "kernel_ms": sms,
+                          "sums_per_s_kernel": sums / (sms * 1e-3),
+                          "fp64_pipe_frac": 50_000 * nq * sums * 4 / (sms * 1e-3)
+                          / 18529.6e9}), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "isf" in sys.argv[1:]:
+        isf()
+    else:
+        main()
