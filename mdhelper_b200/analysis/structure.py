@@ -27,7 +27,12 @@ from typing import Union
 
 import numpy as np
 
+from . import _postprocess
 from ._binning import squared_thresholds
+from ._postprocess import (calculate_coordination_numbers,  # noqa: F401  (re-exported,
+                           calculate_structure_factor,       # as in the reference module)
+                           radial_fourier_transform,
+                           zeroth_order_hankel_transform)
 from .base import FrameFeeder, GpuAnalysisBase, all_reduce_sum, world
 
 _GROUPINGS_RDF = {"atoms", "residues", "segments"}
@@ -347,6 +352,54 @@ class RadialDistributionFunction(GpuAnalysisBase):
             np.pi * self.n_frames ** 2 * _N2 * norm
             * _n_entities(self.ag1, self._groupings[0])
         )
+
+    def calculate_coordination_numbers(self, rho: float, *, n_coord_nums: int = 2,
+                                       threshold: float = 0.1) -> None:
+        """
+        Coordination numbers from the minima of :math:`g(r)` into
+        ``results.coordination_numbers`` (reference: ``structure.py:893-923``).
+
+        Parameters
+        ----------
+        rho : `float`
+            Number density of the surrounding species.
+        n_coord_nums : `int`, keyword-only, default: :code:`2`
+            Number of coordination numbers to calculate.
+        threshold : `float`, keyword-only, default: :code:`0.1`
+            Minimum :math:`g(r)` a local minimum must have to count.
+        """
+        self.results.coordination_numbers = \
+            _postprocess.calculate_coordination_numbers(
+                self.results.bins, self._get_rdf(), rho, n_coord_nums=n_coord_nums,
+                n_dims=2 + (self._drop_axis is None), threshold=threshold)
+
+    def calculate_pmf(self, temperature: float) -> None:
+        """
+        Potential of mean force :math:`-k_\\mathrm{B}T\\ln g(r)` into ``results.pmf``
+        (kJ/mol, or reduced units when ``reduced=True``; reference:
+        ``structure.py:925-959``).  ``temperature`` is a plain number (kelvin).
+        """
+        self.results.units["results.pmf"] = "kilojoule / mole"
+        kBT = _postprocess.thermal_energy(temperature, self._reduced)
+        with np.errstate(divide="ignore"):
+            self.results.pmf = -kBT * np.log(self._get_rdf())
+
+    def calculate_structure_factor(self, rho: float, x_i: float = None,
+                                   x_j: float = None, q: np.ndarray = None, *,
+                                   q_lower: float = None, q_upper: float = None,
+                                   n_q: int = 1_000, formalism: str = "FZ") -> None:
+        """
+        (Partial) static structure factor from :math:`g(r)` by a radial Fourier
+        (3-D) or Hankel (2-D) transform into ``results.wavenumbers`` and
+        ``results.ssf`` (reference: ``structure.py:961-1031``).
+        """
+        equal = (self.ag1 is self.ag2
+                 or np.array_equal(self.ag1.ix, self.ag2.ix))
+        self.results.wavenumbers, self.results.ssf = \
+            _postprocess.calculate_structure_factor(
+                self.results.bins, self._get_rdf(), equal, rho, x_i, x_j, q=q,
+                q_lower=q_lower, q_upper=q_upper, n_q=n_q,
+                n_dims=2 + (self._drop_axis is None), formalism=formalism)
 
 
 def _lattice_indices(wavevectors: np.ndarray, dimensions) -> tuple:

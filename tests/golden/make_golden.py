@@ -226,6 +226,25 @@ def sq_cases(S):
     print("sq cfg4", s.results.ssf.shape, su.results.ssf.shape)
 
 
+def rdf_post(S):
+    """The reference's g(r) post-processing functions (structure.py:106-442) on the
+    g(r) of the lj1000 fixture.  (Its Hankel transform only accepts a one-element
+    wavenumber array: ``jv(0, q * r)`` does not broadcast otherwise.)"""
+    g = dict(np.load(OUT / "rdf_lj1000.npz"))
+    bins, rdf = g["bins"], g["rdf"]
+    qa, sa = S.calculate_structure_factor(bins, rdf, True, 0.8, n_q=64)
+    qb, sb = S.calculate_structure_factor(bins, rdf, False, 0.8, 0.3, 0.7, n_q=32,
+                                          formalism="AL")
+    np.savez_compressed(
+        OUT / "rdf_post.npz", bins=bins, rdf=rdf, rho=0.8,
+        coordination_numbers=S.calculate_coordination_numbers(bins, rdf, 0.8,
+                                                              n_coord_nums=3),
+        q_fz=qa, ssf_fz=sa, q_al=qb, ssf_al=sb,
+        hankel_07=S.zeroth_order_hankel_transform(bins, rdf - 1, np.array([0.7])),
+        rft=S.radial_fourier_transform(bins, rdf - 1, np.array([0.0, 0.5, 1.0])))
+    print("rdf post-processing saved")
+
+
 def isf_cases(S):
     """IntermediateScatteringFunction (structure.py:1552-2127), the real class: the
     coherent and incoherent parts, all modes, a strided frame selection, both forms,
@@ -270,11 +289,13 @@ def isf_cases(S):
 
 if __name__ == "__main__":
     S = ref_harness.load()
-    which = sys.argv[1:] or ["kat", "rdf", "sq", "isf"]
+    which = sys.argv[1:] or ["kat", "rdf", "post", "sq", "isf"]
     if "kat" in which:
         kat_radial_histogram(S)
     if "rdf" in which:
         rdf_cases(S)
+    if "post" in which:
+        rdf_post(S)
     if "sq" in which:
         sq_cases(S)
     if "isf" in which:

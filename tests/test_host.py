@@ -191,3 +191,56 @@ def test_ssf_host_logic_matches_golden(golden):
     np.testing.assert_allclose(s.results.ssf, g["ssf_surfaces"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(s.results.wavenumbers, g["wavenumbers_surfaces"],
                                rtol=1e-13)
+
+
+def test_rdf_postprocessing_matches_reference_functions(golden):
+    """calculate_coordination_numbers / calculate_structure_factor /
+    radial_fourier_transform: same numbers as the reference's own functions
+    (tests/golden/rdf_post.npz, produced by them)."""
+    from mdhelper_b200.analysis import structure as S
+    g = golden("rdf_post")
+    bins, rdf, rho = g["bins"], g["rdf"], float(g["rho"])
+    cn = S.calculate_coordination_numbers(bins, rdf, rho, n_coord_nums=3)
+    np.testing.assert_allclose(cn, g["coordination_numbers"], rtol=1e-13)
+    q, s = S.calculate_structure_factor(bins, rdf, True, rho, n_q=64)
+    np.testing.assert_allclose(q, g["q_fz"], rtol=1e-14)
+    np.testing.assert_allclose(s, g["ssf_fz"], rtol=1e-12, atol=1e-12)
+    q, s = S.calculate_structure_factor(bins, rdf, False, rho, 0.3, 0.7, n_q=32,
+                                        formalism="AL")
+    np.testing.assert_allclose(s, g["ssf_al"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(
+        S.radial_fourier_transform(bins, rdf - 1, np.array([0.0, 0.5, 1.0])), g["rft"],
+        rtol=1e-12)
+    np.testing.assert_allclose(
+        np.ravel(S.zeroth_order_hankel_transform(bins, rdf - 1, np.array([0.7])))[0],
+        float(g["hankel_07"]), rtol=1e-12)
+    # the 2-D transform also takes wavenumber arrays here (it raises in the reference)
+    h = S.zeroth_order_hankel_transform(bins, rdf - 1, np.array([0.0, 0.7]))
+    np.testing.assert_allclose(h[1], float(g["hankel_07"]), rtol=1e-12)
+    with pytest.raises(ValueError):
+        S.calculate_structure_factor(bins, rdf, False, rho, 0.3, 0.7, formalism="xyz")
+    with pytest.raises(ValueError):
+        S.calculate_coordination_numbers(bins, rdf, rho, n_dims=4)
+
+
+def test_rdf_class_postprocessing_methods(golden):
+    """results.coordination_numbers / pmf / wavenumbers / ssf of the class, driven on
+    the host with the counts of the lj1000 fixture in place of the GPU pass."""
+    from _fake import FakeRDF
+    from mdhelper_b200.analysis import _postprocess as P
+    g = golden("rdf_lj1000")
+    p = golden("rdf_post")
+    u = universe_from(g)
+    r = FakeRDF(u.atoms, n_bins=int(g["n_bins"]), range=tuple(g["range"]),
+                verbose=False).run()
+    r.calculate_coordination_numbers(0.8, n_coord_nums=3)
+    np.testing.assert_allclose(r.results.coordination_numbers, p["coordination_numbers"],
+                               rtol=1e-12)
+    r.calculate_structure_factor(0.8, n_q=64)
+    np.testing.assert_allclose(r.results.ssf, p["ssf_fz"], rtol=1e-10, atol=1e-10)
+    r.calculate_pmf(300.0)
+    ok = r.results.rdf > 0
+    np.testing.assert_allclose(r.results.pmf[ok],
+                               -8.31446261815324e-3 * 300.0 * np.log(r.results.rdf[ok]),
+                               rtol=1e-12)
+    assert P.thermal_energy(1.5, True) == 1.5
