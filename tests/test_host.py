@@ -227,6 +227,7 @@ def test_rdf_class_postprocessing_methods(golden):
     """results.coordination_numbers / pmf / wavenumbers / ssf of the class, driven on
     the host with the counts of the lj1000 fixture in place of the GPU pass."""
     from _fake import FakeRDF
+    from conftest import universe_from
     from mdhelper_b200.analysis import _postprocess as P
     g = golden("rdf_lj1000")
     p = golden("rdf_post")
