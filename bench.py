@@ -10,7 +10,7 @@ bench.py -- hot-path benchmark (contract: one JSON line on stdout from rank 0).
 Workload (BASELINE.json configs[1], SURVEY.md section 8(d) "cfg2"): two-group
 cation-anion partial RDF of a 20,000-ion electrolyte, n_bins=201, range (0, 14.5),
 2,000 synthetic frames per GPU.  One "step" = one batch of ``--frames-per-step``
-frames (default 100) through the pair-histogram hot path.
+frames (default 200) through the pair-histogram hot path.
 
 * ``value``      pairs binned / s, coordinates already resident in HBM, device time
                  (CUDA events on the launching stream), max over ranks.
@@ -18,11 +18,15 @@ frames (default 100) through the pair-histogram hot path.
                  ``RadialDistributionFunction(cations, anions).run(start, stop)``
                  from pinned HOST memory (H2D of every frame and D2H of the
                  counts inside the timed region).
-* ``roofline``   pair kernel vs the FP64 pipe: pair evaluations/s x 21 FP64-pipe
-                 instructions per evaluation over the measured
-                 per-SM FP64 issue rate x SM count x the SM clock sampled during
-                 the run.  (Neither HBM- nor tensor-bound; the HBM figure is
-                 reported beside it for the record.)
+* ``roofline``   the kernel that runs by default is the fp32-filter pair kernel
+                 (rdf_filter.cu: counts identical to the reference's fp64 arithmetic,
+                 uncertain pairs re-evaluated in fp64): pair evaluations/s x 16 FP32
+                 operations per evaluation over the measured packed-FP32 rate x SM
+                 count x the SM clock sampled during the run; beside it
+                 ``fp64_pipe_equivalent_frac``, the same rate against the bound of a
+                 kernel that executes the reference's 21 FP64 instructions per pair.
+                 ``--arith off`` benches that kernel (FP64-pipe roofline).  (Neither
+                 HBM- nor tensor-bound; the HBM figure is reported for the record.)
 * ``cpu_baseline`` the restated reference CPU path (oracle/: C distances + real
                  numpy.histogram), serial and frame-parallel over all host cores,
                  on a bounded sample of the same frames.
@@ -63,7 +67,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=100)
+    ap.add_argument("--frames-per-step", type=int, default=200)
     ap.add_argument("--sq-frames-per-step", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
@@ -141,6 +145,26 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
                 "power_w_max": float(max(pw)), "samples": len(sm),
                 "reasons": sorted(reasons)}
+
+
+def profiled_traffic(kernel_tag, frames_in_capture, frames_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full
+    capture (profiles/r01_<tag>_metrics.csv), scaled from the capture's frame count to
+    this run's (the kernel streams every coordinate once, so traffic is linear in
+    frames).  None if the profile is missing."""
+    p = ROOT / "profiles" / f"r01_{kernel_tag}_metrics.csv"
+    if not p.exists():
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    try:
+        for line in p.read_text().splitlines():
+            f = line.split(",")
+            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[2]) * unit[f[1]]
+    except (ValueError, KeyError, IndexError):
+        return None
+    return tot * frames_per_launch / frames_in_capture
 
 
 def measured_peaks():
@@ -473,7 +497,10 @@ def run_ours(args):
         roofline = {
             "kernel": "rdf_filter_kernel", "bound": "fp32_pipe",
             "achieved": achieved / 1e9, "peak": fp32_peak / 1e9, "unit": "Ginstr/s",
-            "frac": achieved / fp32_peak, "traffic": None,
+            "frac": achieved / fp32_peak,
+            "traffic": profiled_traffic("filter", 20, fps),
+            "traffic_note": "dram__bytes_read+write of profiles/r01_filter_metrics.csv (a "
+                            "20-frame launch) scaled to this launch's frames; bytes",
             "per_unit": f"{FP32_OPS_PER_PAIR} FP32 operations per pair evaluation "
                         "(minimum image, squared distance, bin coordinate; issued as "
                         "packed f32x2 instructions)",
@@ -494,7 +521,10 @@ def run_ours(args):
         roofline = {
             "kernel": "rdf_allpairs_kernel", "bound": "fp64_pipe",
             "achieved": fp64_equiv / 1e9, "peak": fp64_peak / 1e9, "unit": "Ginstr/s",
-            "frac": fp64_equiv / fp64_peak, "traffic": None,
+            "frac": fp64_equiv / fp64_peak,
+            "traffic": profiled_traffic("pair", 20, fps),
+            "traffic_note": "dram__bytes_read+write of profiles/r01_pair_metrics.csv (a "
+                            "20-frame launch) scaled to this launch's frames; bytes",
             "per_unit": f"{FP64_OPS_PER_PAIR} FP64-pipe instructions per pair evaluation "
                         "(no FMA fusion allowed)",
             "units_per_launch": evals_per_launch, "launch_ms": kern_ms,
@@ -630,7 +660,14 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
                 "api": "StructureFactor([atoms], n_points=32, q_max=...).run(start, stop)"},
         "roofline": {"kernel": "sq_lattice_kernel<double,16>", "bound": "fp64_pipe",
                      "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Ginstr/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak,
+                     "traffic": profiled_traffic("sq", 16, fps),
+                     "traffic_note": "dram__bytes_read+write of profiles/r01_sq_metrics.csv "
+                                     "(a 16-frame launch) scaled to this launch's frames; "
+                                     "bytes",
+                     "nominal_vs_reachable": "a DFMA with three register operands sustains "
+                                             "42.6/clk/SM (profiles/microbench2_r01.json), "
+                                             "0.67 of the nominal rate used as peak",
                      "per_unit": f"{FP64_OPS_PER_TERM} DFMA per (q, r) term",
                      "units_per_launch": terms, "launch_ms": kern_ms,
                      "peak_source": f"{peaks['pipe_source']}; {peaks['fp64_per_clk_sm']:.1f} "

@@ -314,6 +314,30 @@ def test_large_cutoff_run_modes_agree():
     assert np.array_equal(one, want)
 
 
+def test_host_batches_in_overlapped_pieces():
+    """A host batch of more than ~24 MB is cut into pieces whose copies overlap the
+    kernels of the previous piece (HostStager): same counts as small batches, for an
+    uneven split (103 frames -> 2 pieces of 52 + 51) and the device-resident path."""
+    import torch
+    from mdhelper_b200 import _lib, synthetic
+    from mdhelper_b200.analysis._binning import squared_thresholds
+    u, cat, an = synthetic.electrolyte(20_000, 103, seed=99)
+    S = _structure()
+    kw = dict(n_bins=64, range=(0.0, 7.0), norm=None, verbose=False)
+    big = S.RadialDistributionFunction(cat, an, batch_frames=103, **kw).run()
+    small = S.RadialDistributionFunction(cat, an, batch_frames=10, **kw).run()
+    assert np.array_equal(big.results.counts, small.results.counts)
+    ctx = _lib.Context(0)
+    n1, N = cat.n_atoms, 20_000
+    ctx.rdf_configure(n1, N - n1, False, squared_thresholds(64, (0.0, 7.0)), 0.0, 7.0)
+    dev = torch.from_numpy(u.trajectory.coordinates).cuda()
+    boxes = np.ascontiguousarray(u.trajectory.unitcells[:, :3])
+    ctx.rdf_accumulate(dev.data_ptr(), 3 * N, dev.data_ptr() + 12 * n1, 3 * N, boxes, 103,
+                       device=True)
+    assert np.array_equal(ctx.rdf_fetch(), big.results.counts)
+    ctx.close()
+
+
 def test_argument_errors():
     from mdhelper_b200 import _lib
     ctx = _lib.Context(0)

@@ -206,6 +206,18 @@ def test_isf_larger_system_against_oracle():
     np.testing.assert_allclose(r.results.iisf, o["iisf"], rtol=1e-9, atol=1e-10)
 
 
+def test_host_batches_in_overlapped_pieces():
+    """S(q) host batches above ~24 MB go through the copy stream in pieces (uneven
+    split: 45 frames of 600 kB -> 2 pieces of 23 + 22); same sums as small batches."""
+    from mdhelper_b200 import synthetic
+    u = synthetic.lj_fluid(50_000, 45, seed=3)
+    L = float(u.dimensions[0])
+    kw = dict(n_points=8, q_max=2 * np.pi * 4 / L, sort=False, unique=False, verbose=False)
+    a = _S().StructureFactor([u.atoms], batch_frames=45, **kw).run()
+    b = _S().StructureFactor([u.atoms], batch_frames=7, **kw).run()
+    np.testing.assert_allclose(a.results.ssf, b.results.ssf, rtol=1e-12)
+
+
 def test_argument_errors():
     from mdhelper_b200 import _lib
     ctx = _lib.Context(0)
