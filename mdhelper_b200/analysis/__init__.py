@@ -5,5 +5,6 @@ Mirrors ``mdhelper.analysis`` for the two classes on the accelerated path.
 """
 
 from . import base, structure
+from .base import CombinedAnalysis
 
-__all__ = ["base", "structure"]
+__all__ = ["base", "structure", "CombinedAnalysis"]

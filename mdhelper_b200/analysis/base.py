@@ -261,8 +261,30 @@ class GpuAnalysisBase:
     def _prepare(self):
         pass
 
-    def _process(self, frames: np.ndarray):
+    # ---- per-run protocol of the GPU classes: _begin -> _consume* -> _finish ----
+    def _begin(self, frames: np.ndarray):
         raise NotImplementedError
+
+    def _consume(self, batch, device: bool = False) -> None:
+        raise NotImplementedError
+
+    def _finish(self) -> None:
+        raise NotImplementedError
+
+    def _empty(self) -> None:
+        """Accumulators of a rank that received no frames."""
+        self._finish()
+
+    def _process(self, frames: np.ndarray) -> None:
+        sets, positions_fn, bytes_per_frame = self._begin(frames)
+        if len(frames) == 0:
+            self._empty()
+            return
+        feeder = FrameFeeder(self._trajectory, sets, frames,
+                             self._default_batch(bytes_per_frame), positions_fn)
+        for batch in feeder:
+            self._consume(batch)
+        self._finish()
 
     def _conclude(self):
         pass
@@ -313,3 +335,93 @@ class GpuAnalysisBase:
         else:
             for k, v in data.items():
                 np.save(f"{file}_{k}", v, **kwargs)
+
+
+class CombinedAnalysis:
+    """
+    Several GPU analyses over the same frames with ONE host->device upload per batch
+    (BASELINE.json's "combined RDF + S(q) pass": in the reference every analysis
+    re-reads the trajectory).
+
+    Each frame batch is copied to the device once (pinned source, asynchronous) and
+    every analysis consumes it through device pointers.  This needs the trajectory in
+    memory as one float32 ``[F, N, 3]`` array (``trajectory.coordinates``), evenly
+    spaced frames, ``groupings="atoms"`` and contiguous index ranges; anything else
+    falls back to one pass per analysis.  Results are those of the separate runs.
+
+    Parameters
+    ----------
+    *analyses : GpuAnalysisBase
+        Configured analysis objects sharing one trajectory.
+    batch_frames : `int`, keyword-only, optional
+        Frames per upload (default: ~128 MB of coordinates).
+    """
+
+    def __init__(self, *analyses, batch_frames: int = None):
+        if not analyses:
+            raise ValueError("No analyses given.")
+        traj = analyses[0]._trajectory
+        if any(a._trajectory is not traj for a in analyses):
+            raise ValueError("The analyses must share one trajectory.")
+        self.analyses = analyses
+        self._trajectory = traj
+        self._batch_frames = batch_frames
+
+    def run(self, start: int = None, stop: int = None, step: int = None,
+            frames=None, **kwargs) -> "CombinedAnalysis":
+        for a in self.analyses:
+            a._setup_frames(self._trajectory, start=start, stop=stop, step=step,
+                            frames=frames)
+            a._prepare()
+        rank, size = world()
+        local = np.array_split(self.analyses[0]._frame_list, size)[rank]
+        for a in self.analyses:
+            a.n_local_frames = len(local)
+        plans = [a._begin(local) for a in self.analyses]
+        coords = getattr(self._trajectory, "coordinates", None)
+        d = np.diff(local)
+        shared = (
+            len(local) > 0 and isinstance(coords, np.ndarray)
+            and coords.dtype == np.float32 and coords.ndim == 3
+            and coords.flags.c_contiguous
+            and (len(local) == 1 or (d[0] > 0 and bool(np.all(d == d[0]))))
+            and all(fn is None and all(
+                ix.size > 0 and ix[-1] - ix[0] + 1 == ix.size for ix in sets)
+                for sets, fn, _ in plans)
+        )
+        if not shared:
+            for a, (sets, fn, bpf) in zip(self.analyses, plans):
+                if len(local) == 0:
+                    a._empty()
+                    continue
+                for batch in FrameFeeder(self._trajectory, sets, local,
+                                         a._default_batch(bpf), fn):
+                    a._consume(batch)
+                a._finish()
+        else:
+            import torch
+            n = coords.shape[1]
+            df = int(d[0]) if len(local) > 1 else 1
+            bf = self._batch_frames or int(min(512, max(1, (128 << 20) // (12 * n))))
+            cells = getattr(self._trajectory, "unitcells", None)
+            for b0 in range(0, len(local), bf):
+                fr = local[b0:b0 + bf]
+                host = torch.from_numpy(coords[int(fr[0]):int(fr[-1]) + 1:df])
+                dev = host.cuda(non_blocking=True)           # one upload for everyone
+                if isinstance(cells, np.ndarray):
+                    dims = np.ascontiguousarray(cells[fr], dtype=np.float32)
+                else:
+                    dims = np.stack([self._trajectory[int(f)].dimensions for f in fr]
+                                    ).astype(np.float32)
+                for a, (sets, _, _) in zip(self.analyses, plans):
+                    ptrs = [dev.data_ptr() + 12 * int(ix[0]) for ix in sets]
+                    # no keep-alive needed: the kernels are queued on torch's current
+                    # stream, so the caching allocator cannot hand `dev` out again
+                    # before they have run
+                    a._consume(Batch(len(fr), ptrs, [3 * n] * len(sets), dims, None),
+                               device=True)
+            for a in self.analyses:
+                a._finish()
+        for a in self.analyses:
+            a._conclude()
+        return self

@@ -255,13 +255,16 @@ class RadialDistributionFunction(GpuAnalysisBase):
                               "results.edges": "angstrom"}
         self._area_or_volume = 0.0
 
-    def _process(self, frames: np.ndarray) -> None:
+    def _begin(self, frames: np.ndarray):
+        """Configures the context; returns ``(index_sets, positions_fn,
+        bytes_per_frame)`` for the frame feeder."""
         ctx = self._context()
         n1 = _n_entities(self.ag1, self._groupings[0])
         n2 = _n_entities(self.ag2, self._groupings[1])
         same = (self.ag1 is self.ag2
                 or np.array_equal(self.ag1.ix, self.ag2.ix)) \
             and self._groupings[0] == self._groupings[1]
+        self._same = same
         ctx.rdf_set_filter(self._arith)
         ctx.rdf_configure(
             n1, n2, same, squared_thresholds(self._n_bins, self._range),
@@ -269,10 +272,6 @@ class RadialDistributionFunction(GpuAnalysisBase):
             drop_axis=self._drop_axis, mode=self._mode, hist=self._hist
         )
         self._kernel_ms = 0.0
-        if len(frames) == 0:
-            self._local_counts = np.zeros(self._n_bins, dtype=np.int64)
-            return
-
         atoms_only = self._groupings[0] == self._groupings[1] == "atoms"
         sets = [self.ag1.ix] if same else [self.ag1.ix, self.ag2.ix]
         positions_fn = None
@@ -285,29 +284,33 @@ class RadialDistributionFunction(GpuAnalysisBase):
                         else _centers_of_mass(g, gr, ts.positions[g.ix])
                         for g, gr in zip(groups, grps)]
             sets = [np.arange(n1)] if same else [np.arange(n1), np.arange(n2)]
+        return sets, positions_fn, 12 * (n1 + n2)
 
-        feeder = FrameFeeder(self._trajectory, sets, frames,
-                             self._default_batch(12 * (n1 + n2)), positions_fn)
-        for batch in feeder:
-            _check_orthorhombic(batch.dims)
-            box = batch.dims[:, :3].copy()
-            if self._drop_axis is None:
-                # ts.volume: float64 product of the float32 edges
-                for v in box.astype(np.float64).prod(axis=1):
-                    self._area_or_volume += v
-            else:
-                # reference: structure.py:764-770
-                box[:, self._drop_axis] = box.max(axis=1)
-                keep = [k for k in (0, 1, 2) if k != self._drop_axis]
-                for v in box[:, keep].astype(np.float64).prod(axis=1):
-                    self._area_or_volume += v
-            ctx.rdf_accumulate(
-                batch.ptrs[0], batch.strides[0],
-                None if same else batch.ptrs[1],
-                0 if same else batch.strides[1],
-                box, batch.n_frames, keepalive=batch.keepalive
-            )
-            _record(batch)
+    def _consume(self, batch, device: bool = False) -> None:
+        """One batch of frames (host or device pointers) into the accumulators."""
+        _check_orthorhombic(batch.dims)
+        box = batch.dims[:, :3].copy()
+        if self._drop_axis is None:
+            # ts.volume: float64 product of the float32 edges
+            for v in box.astype(np.float64).prod(axis=1):
+                self._area_or_volume += v
+        else:
+            # reference: structure.py:764-770
+            box[:, self._drop_axis] = box.max(axis=1)
+            keep = [k for k in (0, 1, 2) if k != self._drop_axis]
+            for v in box[:, keep].astype(np.float64).prod(axis=1):
+                self._area_or_volume += v
+        same = self._same
+        self._ctx.rdf_accumulate(
+            batch.ptrs[0], batch.strides[0],
+            None if same else batch.ptrs[1],
+            0 if same else batch.strides[1],
+            box, batch.n_frames, device=device, keepalive=batch.keepalive
+        )
+        _record(batch)
+
+    def _finish(self) -> None:
+        ctx = self._ctx
         self._local_counts = ctx.rdf_fetch()
         self._pair_evaluations = ctx.rdf_pair_evaluations()
         self._filter_stats = ctx.rdf_filter_stats()
@@ -590,7 +593,7 @@ class StructureFactor(GpuAnalysisBase):
                                     if self._unique else self._wavenumbers)
         self.results.units = {"results.wavenumbers": "angstrom^-1"}
 
-    def _process(self, frames: np.ndarray) -> None:
+    def _begin(self, frames: np.ndarray):
         ctx = self._context()
         offsets = np.concatenate(([0], np.cumsum(self._Ns)))
         pairs = np.array([(-1, -1) if p[0] is None else p
@@ -604,10 +607,6 @@ class StructureFactor(GpuAnalysisBase):
         ctx.sq_configure(int(self._N), offsets, self._wavevectors, pairs,
                          lattice_n=self._lattice_n, lattice_b=self._lattice_b,
                          mode=mode)
-        if len(frames) == 0:
-            self._local_ssf = np.zeros_like(self.results.ssf)
-            return
-
         atoms_only = all(g == "atoms" for g in self._groupings)
         if atoms_only:
             sets = [np.concatenate([g.ix for g in self._groups])]
@@ -621,15 +620,15 @@ class StructureFactor(GpuAnalysisBase):
                     else _centers_of_mass(g, gr, ts.positions[g.ix])
                     for g, gr in zip(self._groups, self._groupings)
                 ])]
+        return sets, positions_fn, 12 * int(self._N)
 
-        feeder = FrameFeeder(self._trajectory, sets, frames,
-                             self._default_batch(12 * int(self._N)),
-                             positions_fn)
-        for batch in feeder:
-            ctx.sq_accumulate(batch.ptrs[0], batch.strides[0], batch.n_frames,
-                              keepalive=batch.keepalive)
-            _record(batch)
-        self._local_ssf = ctx.sq_fetch()
+    def _consume(self, batch, device: bool = False) -> None:
+        self._ctx.sq_accumulate(batch.ptrs[0], batch.strides[0], batch.n_frames,
+                                device=device, keepalive=batch.keepalive)
+        _record(batch)
+
+    def _finish(self) -> None:
+        self._local_ssf = self._ctx.sq_fetch()
 
     def _conclude(self) -> None:
         # reference: structure.py:1529-1550

@@ -206,6 +206,34 @@ def test_isf_larger_system_against_oracle():
     np.testing.assert_allclose(r.results.iisf, o["iisf"], rtol=1e-9, atol=1e-10)
 
 
+def test_combined_pass_equals_separate_runs():
+    """CombinedAnalysis (one upload per batch shared by RDF and S(q), BASELINE cfg5):
+    identical counts, S(q) to rounding; strided frames; fallback for scattered groups."""
+    from mdhelper_b200 import synthetic
+    from mdhelper_b200.analysis import CombinedAnalysis
+    u, cat, an = synthetic.electrolyte(6000, 11, seed=8)
+    L = float(u.dimensions[0])
+    S = _S()
+    mk_r = lambda a, b: S.RadialDistributionFunction(a, b, n_bins=50, range=(0.0, 4.0),  # noqa
+                                                     verbose=False)
+    mk_s = lambda g: S.StructureFactor(g, mode="partial" if len(g) > 1 else None,  # noqa
+                                       n_points=8, q_max=2 * np.pi * 4 / L, verbose=False)
+    for run_kw in (dict(), dict(start=1, stop=11, step=3)):
+        r0, s0 = mk_r(cat, an).run(**run_kw), mk_s([cat, an]).run(**run_kw)
+        r1, s1 = mk_r(cat, an), mk_s([cat, an])
+        CombinedAnalysis(r1, s1, batch_frames=4).run(**run_kw)
+        assert np.array_equal(r1.results.counts, r0.results.counts)
+        np.testing.assert_allclose(r1.results.rdf, r0.results.rdf, rtol=1e-13)
+        np.testing.assert_allclose(s1.results.ssf, s0.results.ssf, rtol=1e-12)
+    # scattered selection -> per-analysis fallback, same results
+    g = u.select(np.random.default_rng(0).permutation(6000)[:2000])
+    r0 = mk_r(g, None).run()
+    r1, s1 = mk_r(g, None), mk_s([u.atoms])
+    CombinedAnalysis(r1, s1).run()
+    assert np.array_equal(r1.results.counts, r0.results.counts)
+    np.testing.assert_allclose(s1.results.ssf, mk_s([u.atoms]).run().results.ssf, rtol=1e-12)
+
+
 def test_host_batches_in_overlapped_pieces():
     """S(q) host batches above ~24 MB go through the copy stream in pieces (uneven
     split: 45 frames of 600 kB -> 2 pieces of 23 + 22); same sums as small batches."""

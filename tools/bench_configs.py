@@ -99,6 +99,18 @@ def main():
                           "kernel_frames_per_s": sf.n_frames / (sms * 1e-3),
                           "fp64_pipe_frac": 1e6 * nq * sf.n_frames * 4 / (sms * 1e-3)
                           / 18529.6e9}), flush=True)
+        # the configuration as BASELINE.json names it: RDF + S(q) in ONE pass over each
+        # uploaded frame
+        from mdhelper_b200.analysis import CombinedAnalysis
+        both = CombinedAnalysis(rdf, sf, batch_frames=4)
+        both.run()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        both.run()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"config": "cfg5: combined RDF + S(q) pass, 1M beads, 4 frames",
+                          "e2e_frames_per_s": rdf.n_frames / dt, "e2e_s": dt}), flush=True)
 
 
 def isf():
