@@ -34,8 +34,6 @@
 // bound is not small against a bin (coordinates many boxes away, non-finite values)
 // are left to the exact kernel of rdf.cu.
 
-#include <stdio.h>
-#include <stdlib.h>
 
 #include <algorithm>
 #include <type_traits>
@@ -515,21 +513,6 @@ int rdf_filter_prepare(mdh_ctx *c, int f0, int n_frames, double sqrt_err)
     rdf_filter_prepare_kernel<<<(n_frames + 127) / 128, 128, 0, c->stream>>>(Q);
     MDH_CUDA(cudaGetLastError());
     c->launches++;
-    if (getenv("MDH_DEBUG_EXT")) {
-        MDH_CUDA(cudaStreamSynchronize(c->stream));
-        std::vector<unsigned> e1(6 * n_frames), e2(6 * n_frames);
-        std::vector<FrameFilter> ff(n_frames);
-        cudaMemcpy(e1.data(), Q.ext1, 24 * n_frames, cudaMemcpyDeviceToHost);
-        cudaMemcpy(e2.data(), Q.ext2, 24 * n_frames, cudaMemcpyDeviceToHost);
-        cudaMemcpy(ff.data(), Q.out, sizeof(FrameFilter) * n_frames, cudaMemcpyDeviceToHost);
-        for (int f = 0; f < std::min(n_frames, 2); ++f) {
-            fprintf(stderr, "frame %d ext1:", f);
-            for (int i = 0; i < 6; ++i) fprintf(stderr, " %08x(%g)", e1[6 * f + i], ext_unkey(e1[6 * f + i]));
-            fprintf(stderr, "\n  ext2:");
-            for (int i = 0; i < 6; ++i) fprintf(stderr, " %08x(%g)", e2[6 * f + i], ext_unkey(e2[6 * f + i]));
-            fprintf(stderr, "\n  offm %.9g wlim %u\n", ff[f].offm, ff[f].wlim);
-        }
-    }
     return MDH_OK;
 }
 
