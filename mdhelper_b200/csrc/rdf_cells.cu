@@ -309,12 +309,17 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
 // packed f32x2 arithmetic; uncertain pairs go to a per-block list that is re-evaluated
 // with the fp64 arithmetic when the block has finished its sweeps. -------------------
 
-constexpr int kCellListCap = 2048;
+constexpr int kCellListCap = 1024;
+// 128-thread blocks, four per SM: a block ends with its slowest warp, and with the same
+// registers per SM smaller blocks lose less to that (barrier stalls were 13 % of the
+// samples with 256 threads)
+constexpr int kCfThreads = 128;
+constexpr int kCfWarps = kCfThreads / 32;
 
 __host__ __device__ inline size_t cells_filter_smem_bytes(int n_bins, int sb)
 {
     return align16(sizeof(double) * (n_bins + 1)) +
-           sizeof(unsigned) * ((size_t)kWarps * (((size_t)(n_bins + 2) << sb) + 32)) +
+           sizeof(unsigned) * ((size_t)kCfWarps * (((size_t)(n_bins + 2) << sb) + 32)) +
            sizeof(unsigned) * (kCellListCap + 4);
 }
 
@@ -326,7 +331,7 @@ __device__ __noinline__ void cells_filter_fix(const CellParams &P, int frame, un
     const FrameFilter ff = P.filt[frame];
     const FrameBox fb = P.boxes[frame];
     const FilterConst fc = P.fc;
-    const int i = blockIdx.x * kThreads + (int)(entry >> 24);
+    const int i = blockIdx.x * kCfThreads + (int)(entry >> 24);
     const unsigned vbits = (entry >> 22) & 3u;
     const int q = (int)(entry & 0x3fffffu);
     const float4 pi = P.s1[(int64_t)frame * P.n1 + i];
@@ -355,7 +360,7 @@ __device__ __noinline__ void cells_filter_fix(const CellParams &P, int frame, un
 }
 
 template <bool EXCL, bool LOWER, bool AUDIT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kCfThreads, 4)
     rdf_cells_filter_kernel(const __grid_constant__ CellParams P)
 {
     const int frame = blockIdx.y;
@@ -370,12 +375,12 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int hwords = ((n_bins + 2) << fc.sb) + 32;
     double *sT = reinterpret_cast<double *>(smem);
     unsigned *sH = reinterpret_cast<unsigned *>(smem + align16(sizeof(double) * (n_bins + 1)));
-    unsigned *sList = sH + kWarps * hwords;
+    unsigned *sList = sH + kCfWarps * hwords;
     unsigned *sCount = sList + kCellListCap;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k <= n_bins; k += kThreads) sT[k] = P.thr[k];
-    for (int k = tid; k < kWarps * hwords; k += kThreads) sH[k] = 0;
+    for (int k = tid; k <= n_bins; k += kCfThreads) sT[k] = P.thr[k];
+    for (int k = tid; k < kCfWarps * hwords; k += kCfThreads) sH[k] = 0;
     if (tid == 0) *sCount = 0;
     __syncthreads();
 
@@ -393,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     const float4 *pairs = P.pairs2 + (int64_t)frame * P.npair2 * 2;
     const int *start = P.start2 + (int64_t)frame * P.cstride;
 
-    const int i = blockIdx.x * kThreads + tid;
+    const int i = blockIdx.x * kCfThreads + tid;
     const bool valid = i < P.n1;
     const float4 pi = s1[min(i, P.n1 - 1)];
     const int gi = __float_as_int(pi.w);
@@ -498,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     // exact re-evaluation of the uncertain pairs of this block
     const unsigned n_push = *sCount;
     const unsigned n_list = min(n_push, (unsigned)kCellListCap);
-    for (unsigned e = tid; e < n_list; e += kThreads)
+    for (unsigned e = tid; e < n_list; e += kCfThreads)
         cells_filter_fix<EXCL, LOWER>(P, frame, sList[e], sT, hist32, weight);
     if (tid == 0 && n_push) {
         atomicAdd(&P.fstats[0], (unsigned long long)n_list);
@@ -506,9 +511,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
     __syncthreads();
 
-    for (int k = tid; k < n_bins; k += kThreads) {
+    for (int k = tid; k < n_bins; k += kCfThreads) {
         unsigned sum = 0;                 // modulo 2^32 across warps, see rdf_filter.cu
-        for (int w = 0; w < kWarps; ++w)
+        for (int w = 0; w < kCfWarps; ++w)
             for (int q = 0; q < (1 << fc.sb); ++q)
                 sum += sH[w * hwords + ((k + 1) << fc.sb) + q];
         if (sum) atomicAdd(&P.counts[k], (unsigned long long)sum);
@@ -528,7 +533,8 @@ int launch_cells_filter_t(mdh_ctx *c, const CellParams &P, dim3 grid)
     auto kern = rdf_cells_filter_kernel<EXCL, LOWER, AUDIT>;
     MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    kern<<<grid, kThreads, smem, c->stream>>>(P);
+    kern<<<dim3((unsigned)((P.n1 + kCfThreads - 1) / kCfThreads), grid.y), kCfThreads, smem,
+         c->stream>>>(P);
     MDH_CUDA(cudaGetLastError());
     c->launches++;
     return MDH_OK;
