@@ -374,8 +374,11 @@ __global__ void rdf_filter_prepare_kernel(const PrepareParams Q)
         // the magic-number rounding needs |df * inv| well inside 2^22
         if (!(D * inv < 1048576.0)) ok = false;
         const double eps_b = fabs(box * inv - 1.0);       // exact: 24-bit x 24-bit
+        // last term: the fp64 product inv*df of the reference may round across a
+        // half-integer that the exact product does not cross (|m| changes by at most
+        // box * 2^-52 * |inv*df| <= 2^-51 D)
         const double a = e24 * (0.5 * box + eps_b * D + e24 * D) * (1.0 + 1e-6) + eps_b * D +
-                         1e-30;
+                         D / 2251799813685248.0 + 1e-30;
         a2 += a * a;
         ff.nbox[k] = -(float)box;                          // box is a float32 value
         ff.inv[k] = (float)inv;

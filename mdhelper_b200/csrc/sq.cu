@@ -63,7 +63,7 @@ struct LatticeParams {
 };
 
 // One sub-chunk of particles into the register accumulators.  The per-thread
-// tile is kSqTM columns x R z-terms (R even, warp-uniform), i.e. per particle
+// tile is kSqTM columns x R z-terms (R warp-uniform, 1..8), i.e. per particle
 // 2*kSqTM complex loads of E_x / E_y and R of E_z feed 4*kSqTM*(R + 1) FP64 FMAs.
 //
 // Table row of one particle (elements of T): E_x real parts, E_x imaginary parts,
@@ -168,9 +168,8 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
 
     const int item_index = blockIdx.x * n_cons + min(tid, n_cons - 1);
     const SqWorkItem item = P.items[item_index];
-    // warp-uniform number of z-terms, rounded up to an even count
-    const int wlen =
-        (__reduce_max_sync(0xffffffffu, max(item.len[0], item.len[1])) + 1) & ~1;
+    // warp-uniform number of z-terms
+    const int wlen = __reduce_max_sync(0xffffffffu, max(item.len[0], item.len[1]));
 
     T acc_re[kSqTM][kSqTN], acc_im[kSqTM][kSqTN];
 #pragma unroll
@@ -196,13 +195,14 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
         if (producer) {
             if (p0 + kPS < chunk.y) build(sTab + (size_t)(buf ^ 1) * kPS * nt, p0 + kPS);
         } else {
+#define MDH_SQ_CASE(R) \
+    case R: sq_accumulate_subchunk<T, R>(tab, nt, ixr, ixi, iyr, iyi, iz, acc_re, acc_im); break;
             switch (wlen) {
-                case 2: sq_accumulate_subchunk<T, 2>(tab, nt, ixr, ixi, iyr, iyi, iz, acc_re, acc_im); break;
-                case 4: sq_accumulate_subchunk<T, 4>(tab, nt, ixr, ixi, iyr, iyi, iz, acc_re, acc_im); break;
-                case 6: sq_accumulate_subchunk<T, 6>(tab, nt, ixr, ixi, iyr, iyi, iz, acc_re, acc_im); break;
-                case 8: sq_accumulate_subchunk<T, 8>(tab, nt, ixr, ixi, iyr, iyi, iz, acc_re, acc_im); break;
+                MDH_SQ_CASE(1) MDH_SQ_CASE(2) MDH_SQ_CASE(3) MDH_SQ_CASE(4)
+                MDH_SQ_CASE(5) MDH_SQ_CASE(6) MDH_SQ_CASE(7) MDH_SQ_CASE(8)
                 default: break;
             }
+#undef MDH_SQ_CASE
         }
         __syncthreads();
         buf ^= 1;
@@ -728,6 +728,9 @@ int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locati
     if (I.incoherent) {
         // virtual frames (t, lag): displacement r(t) - r(t - lag), lag = 0 included
         // (the reference evaluates it too: sum of exp(0) = N)
+        MDH_REQUIRE((int64_t)n_frames * I.n_lags <= (1ll << 26), MDH_EINVAL,
+                    "isf: n_frames * n_lags per call must not exceed 2^26 (pass fewer frames "
+                    "per call)");
         std::vector<int4> vm;
         for (int t = 0; t < n_frames; ++t) {
             const int64_t tg = I.n_done + t;                // global frame index
