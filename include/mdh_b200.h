@@ -201,6 +201,16 @@ int mdh_sq_accum_device(mdh_ctx *ctx, void **dptr);
  * n_groups (or 1 for the (-1,-1) pair).  Debug / parity aid for seam #2. */
 int mdh_sq_fetch_rho(mdh_ctx *ctx, double *rho);
 
+/*
+ * Single-chain structure factor (SingleChainStructureFactor._single_frame,
+ * src/mdhelper/analysis/polymer.py:1076-1099): after mdh_sq_configure with lattice
+ * wavevectors, one group and the pair (-1, -1), declare the particles to be n_chains
+ * consecutive chains of n_monomers.  mdh_sq_accumulate then adds, per frame,
+ *   ssf[0][q] += sum over chains | sum over the chain's monomers exp(i q . r) |^2
+ * and mdh_sq_fetch returns that sum (normalise by n_chains * n_monomers * n_frames).
+ */
+int mdh_sq_configure_chains(mdh_ctx *ctx, int64_t n_chains, int64_t n_monomers);
+
 /* ---- intermediate scattering function F(q, t), F_s(q, t) ------------------------
  *
  * Replaces the per-frame work of IntermediateScatteringFunction._single_frame

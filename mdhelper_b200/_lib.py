@@ -57,6 +57,7 @@ SIGNATURES = {
     "mdh_sq_reset": (_i32, [_p]),
     "mdh_sq_accum_device": (_i32, [_p, ctypes.POINTER(_p)]),
     "mdh_sq_fetch_rho": (_i32, [_p, _p]),
+    "mdh_sq_configure_chains": (_i32, [_p, _i64, _i64]),
     "mdh_isf_configure": (_i32, [_p, _i32, _i32, _i64]),
     "mdh_isf_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
     "mdh_isf_fetch": (_i32, [_p, _p, _p]),
@@ -241,6 +242,10 @@ class Context:
 
     def sq_reset(self):
         check(self._lib.mdh_sq_reset(self._h))
+
+    def sq_configure_chains(self, n_chains: int, n_monomers: int):
+        """Single-chain mode: ``sq_accumulate`` adds sum over chains of |rho_chain|^2."""
+        check(self._lib.mdh_sq_configure_chains(self._h, int(n_chains), int(n_monomers)))
 
     # ---- intermediate scattering function (after sq_configure) ----
     def isf_configure(self, n_lags: int, incoherent: bool, max_frames: int):

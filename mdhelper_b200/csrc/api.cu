@@ -401,6 +401,12 @@ int mdh_sq_fetch_rho(mdh_ctx *c, double *rho)
     return MDH_OK;
 }
 
+int mdh_sq_configure_chains(mdh_ctx *c, int64_t n_chains, int64_t n_monomers)
+{
+    CTX_GUARD(c);
+    return sq_configure_chains_impl(c, n_chains, n_monomers);
+}
+
 /* ---- intermediate scattering function (on top of seam #2) ---- */
 
 int mdh_isf_configure(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frames)

@@ -129,6 +129,9 @@ struct SqState {
     DevBuf rho;            // double[F][n_rho][n_q][2]
     DevBuf ssf;            // double[n_pairs][n_q]
     int rho_frames = 0;    // frames held in rho from the last batch
+    // single-chain mode (mdh_sq_configure_chains): chunks are chains, ssf[0][q]
+    // accumulates sum over chains of |rho_chain(q)|^2
+    int64_t n_chains = 0, n_monomers = 0;
 };
 
 struct IsfState {           // intermediate scattering function on top of SqState
@@ -206,6 +209,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                       int n_pairs, const int32_t *pairs, int mode);
 int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
                        int n_frames);
+int sq_configure_chains_impl(mdh_ctx *c, int64_t n_chains, int64_t n_monomers);
 int isf_configure_impl(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frames);
 int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
                         int n_frames);

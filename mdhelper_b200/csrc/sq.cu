@@ -57,6 +57,11 @@ struct LatticeParams {
     const int *qidx;               // [n_items][kSqTM][kSqTN]
     double *rho;                   // [F][n_rho][n_q][2]
     int n_rho, n_q;
+    // single-chain mode (SingleChainStructureFactor): every chunk is one chain and
+    // |rho_chain(q)|^2 is added to chain_out[q]; a block walks the chunks
+    // blockIdx.y, blockIdx.y + gridDim.y, ...
+    double *chain_out;             // nullptr: normal mode
+    int n_chunks;
     double b[3];
     int nmax[3];                   // largest n per axis
     int offy, offz, nt;            // table layout per particle (in table elements)
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
     const int n_cons = (int)blockDim.x - kSqProducers;
     const bool producer = tid >= n_cons;
     const int frame = blockIdx.z;
-    const int4 chunk = P.chunks[blockIdx.y];
+    int4 chunk = P.chunks[blockIdx.y];
     const int4 vm = P.vmap ? P.vmap[frame] : make_int4(frame, -1, 0, 0);
     const float *pos = P.raw + (int64_t)vm.x * P.stride;
     const float *pos0 = vm.y >= 0 ? P.raw + (int64_t)vm.y * P.stride : nullptr;
@@ -187,6 +192,11 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
     }
     const int iz = P.offz + 2 * item.nz0;
 
+    const int *qi = P.qidx + (int64_t)item_index * (kSqTM * kSqTN);
+    // normal mode: one chunk per block (gridDim.y == n_chunks); chain mode: a stride
+    // loop over the chains with the accumulators squared and cleared in between
+    for (int ci = blockIdx.y; ci < P.n_chunks; ci += gridDim.y) {
+    chunk = P.chunks[ci];
     if (producer) build(sTab, chunk.x);
     __syncthreads();
     int buf = 0;
@@ -207,10 +217,9 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
         __syncthreads();
         buf ^= 1;
     }
-    if (producer) return;
+    if (producer) continue;
 
     double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
-    const int *qi = P.qidx + (int64_t)item_index * (kSqTM * kSqTN);
 #pragma unroll
     for (int m = 0; m < kSqTM; ++m)
 #pragma unroll
@@ -218,11 +227,18 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
             if (r < item.len[m]) {
                 const int q = qi[m * kSqTN + r];
                 if (q >= 0) {
-                    atomicAdd(out + 2 * q, (double)acc_re[m][r]);
-                    atomicAdd(out + 2 * q + 1, (double)acc_im[m][r]);
+                    if (P.chain_out) {
+                        const double re = (double)acc_re[m][r], im = (double)acc_im[m][r];
+                        atomicAdd(P.chain_out + q, re * re + im * im);
+                    } else {
+                        atomicAdd(out + 2 * q, (double)acc_re[m][r]);
+                        atomicAdd(out + 2 * q + 1, (double)acc_im[m][r]);
+                    }
                 }
             }
+            acc_re[m][r] = acc_im[m][r] = T(0);
         }
+    }
 }
 
 struct GeneralParams {
@@ -361,6 +377,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
     S.group_offsets.assign(goff, goff + n_groups + 1);
     S.pairs.assign(pairs, pairs + 2 * n_pairs);
     S.rho_frames = 0;
+    S.n_chains = S.n_monomers = 0;
 
     // ---- lattice work items ----
     // Columns (nx, ny) sorted by their number of wavevectors; thread tiles take two
@@ -481,9 +498,13 @@ static int sq_build_chunks(mdh_ctx *c, int n_frames)
     int64_t len = (S.n_total + want - 1) / std::max<int64_t>(want, 1);
     len = std::max<int64_t>(256, std::min<int64_t>(len, 4096));
     len = (len + kPS - 1) / kPS * kPS;
+    if (S.n_chains > 0) len = -S.n_monomers;   // single-chain layout: its own cache key
     if (S.n_chunks > 0 && S.chunk_len == (int)len) return MDH_OK;
     std::vector<int4> ch;
-    if (S.n_rho == 1) {
+    if (S.n_chains > 0) {
+        for (int64_t k = 0; k < S.n_chains; ++k)
+            ch.push_back(make_int4((int)(k * S.n_monomers), (int)((k + 1) * S.n_monomers), 0, 0));
+    } else if (S.n_rho == 1) {
         for (int64_t s = 0; s < S.n_total; s += len)
             ch.push_back(make_int4((int)s, (int)std::min<int64_t>(S.n_total, s + len), 0, 0));
     } else {
@@ -493,7 +514,8 @@ static int sq_build_chunks(mdh_ctx *c, int n_frames)
                                        (int)std::min<int64_t>(S.group_offsets[g + 1], s + len),
                                        g, 0));
     }
-    MDH_REQUIRE(ch.size() <= 65535, MDH_EINVAL, "sq: too many particle chunks");
+    MDH_REQUIRE(S.n_chains > 0 || ch.size() <= 65535, MDH_EINVAL,
+                "sq: too many particle chunks");
     if (int rc = S.chunks.reserve(sizeof(int4) * ch.size())) return rc;
     MDH_CUDA(cudaMemcpyAsync(S.chunks.p, ch.data(), sizeof(int4) * ch.size(),
                              cudaMemcpyHostToDevice, c->stream));
@@ -511,7 +533,9 @@ static int sq_compute_rho(mdh_ctx *c, const float *raw, int64_t stride, const in
     SqState &S = c->sq;
     if (int rc = sq_build_chunks(c, nominal_frames)) return rc;
     const size_t rho_bytes = sizeof(double) * 2 * (size_t)n_vframes * S.n_rho * S.n_q;
-    MDH_CUDA(cudaMemsetAsync(rho, 0, rho_bytes, c->stream));
+    if (S.n_chains == 0) MDH_CUDA(cudaMemsetAsync(rho, 0, rho_bytes, c->stream));
+    MDH_REQUIRE(S.n_chains == 0 || S.lattice, MDH_ESTATE,
+                "sq: single-chain mode needs lattice wavevectors");
     if (S.lattice) {
         LatticeParams P;
         // row layout in table elements: E_x re | E_x im | E_y re | E_y im | E_z (re, im)
@@ -524,8 +548,10 @@ static int sq_compute_rho(mdh_ctx *c, const float *raw, int64_t stride, const in
         P.qidx = S.qidx.as<int>();
         P.rho = rho;
         P.n_rho = S.n_rho; P.n_q = S.n_q;
+        P.chain_out = S.n_chains > 0 ? S.ssf.as<double>() : nullptr;
+        P.n_chunks = S.n_chunks;
         for (int k = 0; k < 3; ++k) { P.b[k] = S.b[k]; P.nmax[k] = S.nmax[k]; }
-        dim3 grid(S.n_items / S.block, S.n_chunks, n_vframes);
+        dim3 grid(S.n_items / S.block, std::min(S.n_chunks, 65535), n_vframes);
         return S.mode == MDH_SQ_LATTICE_FP32 ? launch_lattice<float>(c, P, grid, S.block)
                                              : launch_lattice<double>(c, P, grid, S.block);
     }
@@ -591,11 +617,19 @@ static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int
         dstride = 3 * S.n_total;
     }
     const size_t rho_bytes = sizeof(double) * 2 * (size_t)n_frames * S.n_rho * S.n_q;
-    if (int rc = S.rho.reserve(rho_bytes)) return rc;
+    if (S.n_chains == 0)
+        if (int rc = S.rho.reserve(rho_bytes)) return rc;
 
     if (int rc = c->t_sq.begin(c->stream)) return rc;
     if (int rc = sq_compute_rho(c, dsrc, dstride, nullptr, n_frames, S.rho.as<double>(),
                                 nominal_frames)) return rc;
+    if (S.n_chains > 0) {
+        // the kernel has added |rho_chain|^2 to the accumulator itself
+        S.rho_frames = 0;
+        if (location == MDH_HOST)
+            if (int rc = c->stager.retire(c->stream, slot)) return rc;
+        return c->t_sq.end(c->stream);
+    }
     dim3 fgrid((S.n_q + 127) / 128, S.n_pairs);
     sq_finalize_kernel<<<fgrid, 128, 0, c->stream>>>(S.rho.as<double2>(), n_frames, S.n_rho,
                                                      S.n_q, S.d_pairs.as<int>(), S.n_pairs,
@@ -661,11 +695,32 @@ __global__ void isf_incoherent_kernel(const double2 *__restrict__ rho_tmp,
 
 }  // namespace
 
+// Single-chain structure factor (SURVEY.md section 8(f) rank 3;
+// /root/reference/src/mdhelper/analysis/polymer.py:1096-1099): the particles are
+// n_chains consecutive runs of n_monomers; every accumulate call adds
+// sum over frames and chains of |sum over the chain's monomers of exp(i q . r)|^2.
+int sq_configure_chains_impl(mdh_ctx *c, int64_t n_chains, int64_t n_monomers)
+{
+    SqState &S = c->sq;
+    MDH_REQUIRE(S.configured, MDH_ESTATE, "sq: configure the wavevectors first");
+    MDH_REQUIRE(S.lattice, MDH_EINVAL,
+                "sq: single-chain mode needs lattice wavevectors (lattice_n / lattice_b)");
+    MDH_REQUIRE(S.n_pairs == 1 && S.n_rho == 1, MDH_EINVAL,
+                "sq: single-chain mode needs the single pair (-1, -1)");
+    MDH_REQUIRE(n_chains >= 1 && n_monomers >= 1 && n_chains * n_monomers == S.n_total,
+                MDH_EINVAL, "sq: n_chains * n_monomers must equal n_total");
+    S.n_chains = n_chains;
+    S.n_monomers = n_monomers;
+    S.n_chunks = 0;                    // rebuild the chunk list
+    return MDH_OK;
+}
+
 int isf_configure_impl(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frames)
 {
     SqState &S = c->sq;
     IsfState &I = c->isf;
     MDH_REQUIRE(S.configured, MDH_ESTATE, "isf: the wavevectors are not configured");
+    MDH_REQUIRE(S.n_chains == 0, MDH_ESTATE, "isf: not available in single-chain mode");
     MDH_REQUIRE(n_lags >= 1 && n_lags <= 65535, MDH_EINVAL, "isf: n_lags must be in [1, 65535]");
     MDH_REQUIRE(max_frames >= n_lags, MDH_EINVAL, "isf: fewer frames than time lags");
     I.on = false;

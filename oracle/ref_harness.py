@@ -175,3 +175,15 @@ def accelerated():
     """Returns the reference's ``mdhelper.algorithm.accelerated`` module."""
     load()
     return _load_state["accelerated"]
+
+
+def polymer():
+    """Returns the reference's ``mdhelper.analysis.polymer`` module (same stubs)."""
+    load()
+    if "polymer" not in _load_state:
+        sys.path.insert(0, str(REFERENCE_SRC))
+        try:
+            _load_state["polymer"] = importlib.import_module("mdhelper.analysis.polymer")
+        finally:
+            sys.path.remove(str(REFERENCE_SRC))
+    return _load_state["polymer"]

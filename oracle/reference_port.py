@@ -318,3 +318,42 @@ def isf_run(universe, groups, *, mode=None, wavevectors=None, n_points=32,
             iisf = iisf[:, :, order]
     return {"pairs": pairs, "wavenumbers": wn_out, "cisf": cisf, "iisf": iisf,
             "times": df * dt * np.arange(n_lags), "wavevectors": wavevectors}
+
+
+def scsf_run(universe, group, *, n_points=32, n_chains, n_monomers, unwrap=False,
+             start=None, stop=None, step=None):
+    """
+    Restates ``SingleChainStructureFactor`` (``analysis/polymer.py:805-1129``) for
+    ``grouping="atoms"`` with explicit ``n_chains`` / ``n_monomers``: wavevector grid
+    (``:977-984``), per-frame unwrapping (``algorithm/topology.py:294-383``), the
+    per-chain trigonometric sums (``:1096-1099``) and ``_conclude`` (``:1101-1129``).
+    """
+    traj = universe.trajectory
+    frames = np.arange(*slice(start, stop, step).indices(len(traj)))
+    dims = universe.dimensions[:3].copy()
+    wavevectors = np.stack(
+        np.meshgrid(*[2 * np.pi * np.arange(n_points) / L for L in dims]), -1
+    ).reshape(-1, 3)
+    wavenumbers = np.linalg.norm(wavevectors, axis=1)
+    wn_out = np.unique(wavenumbers.round(11))
+    scsf = np.zeros(len(wavevectors))
+    old = images = None
+    for f in frames:
+        traj[int(f)]
+        positions = group.positions.astype(np.float32)
+        if unwrap:
+            if old is None:
+                old = positions.copy()
+                images = np.zeros(positions.shape, dtype=int)
+            dpos = positions - old
+            mask = np.abs(dpos) >= dims / 2
+            images[mask] -= np.sign(dpos[mask]).astype(int)
+            old[:] = positions[:]
+            positions += images * dims          # in place: stays float32, as in the reference
+        for chain in positions.reshape((n_chains, n_monomers, 3)):
+            arg = np.einsum("ij,kj->ki", wavevectors, chain)
+            scsf += np.sin(arg).sum(axis=0) ** 2 + np.cos(arg).sum(axis=0) ** 2
+    scsf /= n_chains * n_monomers * len(frames)
+    out = np.fromiter((scsf[np.isclose(q, wavenumbers)].mean() for q in wn_out),
+                      dtype=float, count=len(wn_out))
+    return {"wavenumbers": wn_out, "scsf": out, "wavevectors": wavevectors}

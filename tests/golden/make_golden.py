@@ -287,9 +287,30 @@ def isf_cases(S):
           "exp vs trig", np.abs(out["cisf_partial_exp"] - out["cisf_partial_trig"]).max())
 
 
+def scsf_cases(S):
+    """SingleChainStructureFactor (analysis/polymer.py:805-1129), the real class, on a
+    small bead-spring melt: wrapped coordinates as stored, and unwrap=True."""
+    P = ref_harness.polymer()
+    u = synthetic.polymer_melt(12, 20, 6, seed=20260012)
+    out = dict(positions=u.trajectory.coordinates.copy(),
+               dims=u.trajectory.unitcells[0].copy(), n_chains=12, n_monomers=20,
+               n_points=6)
+    for unwrap in (False, True):
+        r = P.SingleChainStructureFactor(u.atoms, n_points=6, n_chains=12, n_monomers=20,
+                                         unwrap=unwrap, verbose=False).run()
+        out[f"scsf_unwrap{int(unwrap)}"] = r.results.scsf
+        out["wavenumbers"] = r.results.wavenumbers
+    r = P.SingleChainStructureFactor(u.atoms, n_points=6, n_chains=12, n_monomers=20,
+                                     verbose=False).run(start=1, stop=6, step=2)
+    out["scsf_strided"] = r.results.scsf
+    np.savez_compressed(OUT / "scsf_small.npz", **out)
+    print("scsf small", out["scsf_unwrap0"].shape,
+          "wrapped vs unwrapped", np.abs(out["scsf_unwrap0"] - out["scsf_unwrap1"]).max())
+
+
 if __name__ == "__main__":
     S = ref_harness.load()
-    which = sys.argv[1:] or ["kat", "rdf", "post", "sq", "isf"]
+    which = sys.argv[1:] or ["kat", "rdf", "post", "sq", "isf", "scsf"]
     if "kat" in which:
         kat_radial_histogram(S)
     if "rdf" in which:
@@ -300,3 +321,5 @@ if __name__ == "__main__":
         sq_cases(S)
     if "isf" in which:
         isf_cases(S)
+    if "scsf" in which:
+        scsf_cases(S)

@@ -206,6 +206,51 @@ def test_isf_larger_system_against_oracle():
     np.testing.assert_allclose(r.results.iisf, o["iisf"], rtol=1e-9, atol=1e-10)
 
 
+# ---- single-chain structure factor ---------------------
+
+def test_scsf_matches_golden(golden):
+    """GPU SingleChainStructureFactor vs the fixtures of the reference's real class:
+    wrapped coordinates, host unwrapping, a strided frame selection, chains taken from
+    the segment information."""
+    from mdhelper_b200.analysis.polymer import SingleChainStructureFactor
+    from mdhelper_b200 import synthetic
+    g = golden("scsf_small")
+    u = universe_from(g)
+    kw = dict(n_points=int(g["n_points"]), n_chains=int(g["n_chains"]),
+              n_monomers=int(g["n_monomers"]), verbose=False)
+    for unwrap in (False, True):
+        r = SingleChainStructureFactor(u.atoms, unwrap=unwrap, batch_frames=4, **kw).run()
+        np.testing.assert_allclose(r.results.scsf, g[f"scsf_unwrap{int(unwrap)}"],
+                                   rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(r.results.wavenumbers, g["wavenumbers"], rtol=1e-13)
+    r = SingleChainStructureFactor(u.atoms, **kw).run(start=1, stop=6, step=2)
+    np.testing.assert_allclose(r.results.scsf, g["scsf_strided"], rtol=1e-9, atol=1e-10)
+    # chain bookkeeping from the universe's segments (polymer_melt sets them)
+    u2 = synthetic.polymer_melt(12, 20, 6, seed=20260012)
+    r2 = SingleChainStructureFactor(u2.atoms, n_points=int(g["n_points"]),
+                                    verbose=False).run()
+    np.testing.assert_allclose(r2.results.scsf, g["scsf_unwrap0"], rtol=1e-9, atol=1e-10)
+    with pytest.raises(ValueError):
+        SingleChainStructureFactor(u.atoms, grouping="segments", **kw)
+
+
+def test_scsf_many_chains_against_oracle():
+    """More chains than one grid dimension takes at once is not needed here, but chain
+    lengths that are not a multiple of the 32-particle sub-chunk and a non-cubic box
+    are: 300 chains x 37 monomers vs the CPU oracle."""
+    from mdhelper_b200.analysis.polymer import SingleChainStructureFactor
+    from mdhelper_b200.universe import SyntheticUniverse
+    from oracle import reference_port as rp
+    rng = np.random.default_rng(12)
+    dims = np.array([21.0, 24.0, 27.0, 90, 90, 90], np.float32)
+    pos = (rng.random((2, 300 * 37, 3)) * dims[:3]).astype(np.float32)
+    u = SyntheticUniverse(pos, dims)
+    r = SingleChainStructureFactor(u.atoms, n_points=7, n_chains=300, n_monomers=37,
+                                   verbose=False).run()
+    o = rp.scsf_run(u, u.atoms, n_points=7, n_chains=300, n_monomers=37)
+    np.testing.assert_allclose(r.results.scsf, o["scsf"], rtol=1e-9, atol=1e-10)
+
+
 def test_combined_pass_equals_separate_runs():
     """CombinedAnalysis (one upload per batch shared by RDF and S(q), BASELINE cfg5):
     identical counts, S(q) to rounding; strided frames; fallback for scattered groups."""

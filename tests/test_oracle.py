@@ -123,6 +123,21 @@ def test_isf_port_matches_golden(golden, mode):
         np.testing.assert_allclose(o["iisf"][0], 1.0, rtol=1e-12)
 
 
+def test_scsf_port_matches_golden(golden):
+    """oracle scsf_run vs fixtures of the reference's real SingleChainStructureFactor."""
+    g = golden("scsf_small")
+    u = universe_from(g)
+    kw = dict(n_points=int(g["n_points"]), n_chains=int(g["n_chains"]),
+              n_monomers=int(g["n_monomers"]))
+    for unwrap in (False, True):
+        o = rp.scsf_run(u, u.atoms, unwrap=unwrap, **kw)
+        np.testing.assert_allclose(o["scsf"], g[f"scsf_unwrap{int(unwrap)}"], rtol=1e-12)
+        np.testing.assert_allclose(o["wavenumbers"], g["wavenumbers"], rtol=1e-13)
+    o = rp.scsf_run(u, u.atoms, start=1, stop=6, step=2, **kw)
+    np.testing.assert_allclose(o["scsf"], g["scsf_strided"], rtol=1e-12)
+    assert abs(o["scsf"][0] - 20.0) < 1e-12          # S_sc(0) = chain length
+
+
 def test_port_matches_live_reference():
     """Where the reference tree exists, the port is checked against the real classes."""
     from mdhelper_b200 import synthetic
