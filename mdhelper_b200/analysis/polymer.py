@@ -14,7 +14,8 @@ from __future__ import annotations
 import numpy as np
 
 from .base import GpuAnalysisBase, all_reduce_sum
-from .structure import _centers_of_mass, _lattice_indices, _record
+from .structure import (_centers_of_mass, _isclose_members, _lattice_indices,
+                        _record)
 
 
 def unwrap(positions: np.ndarray, positions_old: np.ndarray, dimensions: np.ndarray,
@@ -202,7 +203,9 @@ class SingleChainStructureFactor(GpuAnalysisBase):
         # reference: polymer.py:1101-1129
         scsf = all_reduce_sum(self._local, self._device)
         scsf = scsf / (self._n_chains * self._n_monomers * self.n_frames)
+        # same index sets as the reference's np.isclose(q, wavenumbers) scan
+        if getattr(self, "_members", None) is None:
+            self._members = _isclose_members(self.results.wavenumbers, self._wavenumbers)
         self.results.scsf = np.fromiter(
-            (scsf[np.isclose(q, self._wavenumbers)].mean()
-             for q in self.results.wavenumbers),
+            (scsf[m].mean() for m in self._members),
             dtype=float, count=len(self.results.wavenumbers))

@@ -640,10 +640,8 @@ class StructureFactor(GpuAnalysisBase):
             # np.isclose(q, wavenumbers) loop; the memberships depend only on the
             # wavevectors, so they are found once per instance, not once per run
             if getattr(self, "_unique_members", None) is None:
-                self._unique_members = [
-                    np.flatnonzero(np.isclose(q, self._wavenumbers))
-                    for q in self.results.wavenumbers
-                ]
+                self._unique_members = _isclose_members(self.results.wavenumbers,
+                                                        self._wavenumbers)
             self.results.ssf = np.hstack(
                 [self.results.ssf[:, cols].mean(axis=1, keepdims=True)
                  for cols in self._unique_members]
@@ -823,8 +821,7 @@ class IntermediateScatteringFunction(StructureFactor):
         if self._incoherent:
             self.results.iisf = self.results.iisf / normalization
         if self._unique:
-            members = [np.isclose(q, self._wavenumbers)
-                       for q in self.results.wavenumbers]
+            members = _isclose_members(self.results.wavenumbers, self._wavenumbers)
             self.results.cisf = np.stack(
                 [self.results.cisf[:, :, m].mean(axis=2) for m in members],
                 axis=-1)
@@ -838,6 +835,26 @@ class IntermediateScatteringFunction(StructureFactor):
             self.results.cisf = self.results.cisf[:, :, order]
             if self._incoherent:
                 self.results.iisf = self.results.iisf[:, :, order]
+
+
+def _isclose_members(unique_q: np.ndarray, wavenumbers: np.ndarray) -> list:
+    """
+    ``[np.flatnonzero(np.isclose(q, wavenumbers)) for q in unique_q]`` -- the groups
+    the reference averages over in its ``_conclude`` methods (``structure.py:1538-1543``,
+    ``polymer.py:1121-1128``) -- without the O(n_unique x n_q) scan: candidates come from
+    a sorted copy (a window slightly wider than ``isclose``'s tolerance) and are then
+    filtered with ``np.isclose`` itself, so the index sets are identical and ascending.
+    """
+    order = np.argsort(wavenumbers, kind="stable")
+    w_sorted = wavenumbers[order]
+    out = []
+    for q in unique_q:
+        tol = 1e-8 + 1.1e-5 * (abs(q) + 1e-8)          # isclose: atol + rtol * |w|
+        lo = np.searchsorted(w_sorted, q - 2 * tol, side="left")
+        hi = np.searchsorted(w_sorted, q + 2 * tol, side="right")
+        cand = np.sort(order[lo:hi])
+        out.append(cand[np.isclose(q, wavenumbers[cand])])
+    return out
 
 
 def _closest_factor_pair(value: int) -> tuple:

@@ -245,3 +245,18 @@ def test_rdf_class_postprocessing_methods(golden):
                                -8.31446261815324e-3 * 300.0 * np.log(r.results.rdf[ok]),
                                rtol=1e-12)
     assert P.thermal_energy(1.5, True) == 1.5
+
+
+def test_isclose_members_equals_the_reference_scan():
+    """The sorted-window grouping gives exactly np.isclose's index sets (also where
+    neighbouring unique wavenumbers are closer than isclose's relative tolerance)."""
+    rng = np.random.default_rng(0)
+    g = 2 * np.pi * np.arange(12) / np.float32(17.3)
+    wv = np.stack(np.meshgrid(g, g * 1.000004, g), -1).reshape(-1, 3)
+    wn = np.linalg.norm(wv, axis=1)
+    uq = np.unique(wn.round(11))
+    got = structure._isclose_members(uq, wn)
+    assert len(got) == len(uq)
+    for q, m in zip(uq, got):
+        assert np.array_equal(m, np.flatnonzero(np.isclose(q, wn)))
+    assert any(len(m) > 1 for m in got)
