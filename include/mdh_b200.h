@@ -201,6 +201,23 @@ int mdh_sq_accum_device(mdh_ctx *ctx, void **dptr);
  * n_groups (or 1 for the (-1,-1) pair).  Debug / parity aid for seam #2. */
 int mdh_sq_fetch_rho(mdh_ctx *ctx, double *rho);
 
+/* ---- centres of mass (groupings="residues"/"segments") ----------------------------
+ *
+ * Replaces center_of_mass(group, grouping) (src/mdhelper/algorithm/molecule.py:15-310)
+ * as used at structure.py:753-756 / 1485-1486 for entities that are consecutive runs of
+ * atoms: entity e covers atoms starts[e] .. starts[e+1]-1 of the group.
+ *   out[f][e][k] = (float)(sum_a masses[a] * pos[f][a][k] / sum_a masses[a])   (fp64,
+ * atoms in index order).  out_device is a DEVICE buffer with out_frame_stride floats per
+ * frame (>= 3 * n_entities; several groups can be written side by side) that can be
+ * handed to mdh_rdf_accumulate / mdh_sq_accumulate with MDH_DEVICE.  Slots 0..7 hold one
+ * group description each.
+ */
+int mdh_com_configure(mdh_ctx *ctx, int slot, int64_t n_atoms, int64_t n_entities,
+                      const int64_t *starts /* [n_entities+1] host */,
+                      const double *masses /* [n_atoms] host */);
+int mdh_com_reduce(mdh_ctx *ctx, int slot, const float *pos, int64_t frame_stride,
+                   int location, int n_frames, float *out_device, int64_t out_frame_stride);
+
 /*
  * Single-chain structure factor (SingleChainStructureFactor._single_frame,
  * src/mdhelper/analysis/polymer.py:1076-1099): after mdh_sq_configure with lattice

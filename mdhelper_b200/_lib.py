@@ -57,6 +57,8 @@ SIGNATURES = {
     "mdh_sq_reset": (_i32, [_p]),
     "mdh_sq_accum_device": (_i32, [_p, ctypes.POINTER(_p)]),
     "mdh_sq_fetch_rho": (_i32, [_p, _p]),
+    "mdh_com_configure": (_i32, [_p, _i32, _i64, _i64, _p, _p]),
+    "mdh_com_reduce": (_i32, [_p, _i32, _p, _i64, _i32, _i32, _p, _i64]),
     "mdh_sq_configure_chains": (_i32, [_p, _i64, _i64]),
     "mdh_isf_configure": (_i32, [_p, _i32, _i32, _i64]),
     "mdh_isf_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
@@ -242,6 +244,19 @@ class Context:
 
     def sq_reset(self):
         check(self._lib.mdh_sq_reset(self._h))
+
+    # ---- centres of mass of consecutive atom runs ----
+    def com_configure(self, slot: int, starts, masses):
+        st = np.ascontiguousarray(starts, dtype=np.int64)
+        m = np.ascontiguousarray(masses, dtype=np.float64)
+        check(self._lib.mdh_com_configure(self._h, int(slot), len(m), len(st) - 1,
+                                          st.ctypes.data, m.ctypes.data))
+
+    def com_reduce(self, slot: int, pos, stride, n_frames, out_device, out_stride, *,
+                   device=False):
+        check(self._lib.mdh_com_reduce(self._h, int(slot), _ptr(pos), int(stride),
+                                       MDH_DEVICE if device else MDH_HOST, int(n_frames),
+                                       _ptr(out_device), int(out_stride)))
 
     def sq_configure_chains(self, n_chains: int, n_monomers: int):
         """Single-chain mode: ``sq_accumulate`` adds sum over chains of |rho_chain|^2."""

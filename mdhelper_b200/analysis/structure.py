@@ -74,6 +74,26 @@ def _centers_of_mass(group, grouping: str, positions: np.ndarray) -> np.ndarray:
     return com
 
 
+def _com_plan(group, grouping: str):
+    """
+    ``(starts, masses)`` for the device centre-of-mass kernel if the entities of
+    ``group`` are consecutive runs of a contiguous atom range (the usual topology
+    order), else ``None`` (the host helper is used).  ``grouping="atoms"`` gives the
+    identity plan (one atom per entity, unit masses: ``(1 * x) / 1`` is exact).
+    """
+    ix = np.asarray(group.ix)
+    if ix.size == 0 or ix[-1] - ix[0] + 1 != ix.size or np.any(np.diff(ix) != 1):
+        return None
+    if grouping == "atoms":
+        return np.arange(ix.size + 1, dtype=np.int64), np.ones(ix.size)
+    key = np.asarray(group.resindices if grouping == "residues" else group.segindices)
+    change = np.flatnonzero(np.diff(key) != 0) + 1
+    starts = np.concatenate(([0], change, [key.size])).astype(np.int64)
+    if len(np.unique(key)) != len(starts) - 1:      # an entity split into several runs
+        return None
+    return starts, np.asarray(group.masses, dtype=np.float64)
+
+
 def _n_entities(group, grouping: str) -> int:
     return int(getattr(group, f"n_{grouping}"))
 
@@ -181,6 +201,9 @@ class RadialDistributionFunction(GpuAnalysisBase):
         Determines whether progress is logged.
     mode, hist, arith : `str`, keyword-only
         Kernel selectors, see :func:`radial_histogram`.
+    host_com : `bool`, keyword-only, default: :code:`False`
+        Compute centres of mass on the host even where the device kernel applies
+        (entities that are consecutive atom runs); the results are identical.
 
     Attributes
     ----------
@@ -202,7 +225,7 @@ class RadialDistributionFunction(GpuAnalysisBase):
             groupings: Union[str, tuple] = "atoms", reduced: bool = False,
             n_batches: int = None, parallel: bool = False,
             verbose: bool = True, mode: str = "auto", hist: str = "auto",
-            arith: str = "auto", **kwargs) -> None:
+            arith: str = "auto", host_com: bool = False, **kwargs) -> None:
 
         self.ag1 = ag1
         self.ag2 = ag1 if ag2 is None else ag2
@@ -244,6 +267,8 @@ class RadialDistributionFunction(GpuAnalysisBase):
         self._mode = mode
         self._hist = hist
         self._arith = arith
+        self._host_com = bool(host_com)
+        self._com = None
 
     def _prepare(self) -> None:
         # reference: structure.py:734-748
@@ -275,9 +300,17 @@ class RadialDistributionFunction(GpuAnalysisBase):
         atoms_only = self._groupings[0] == self._groupings[1] == "atoms"
         sets = [self.ag1.ix] if same else [self.ag1.ix, self.ag2.ix]
         positions_fn = None
+        self._com = None
         if not atoms_only:
             groups = [self.ag1] if same else [self.ag1, self.ag2]
             grps = self._groupings[:len(groups)]
+            plans = [_com_plan(g, gr) for g, gr in zip(groups, grps)]
+            if all(p is not None for p in plans) and not self._host_com:
+                # centres of mass on the device: the feeder hands over the raw atoms
+                for slot, (starts, masses) in enumerate(plans):
+                    ctx.com_configure(slot, starts, masses)
+                self._com = [len(p[0]) - 1 for p in plans]
+                return [g.ix for g in groups], None, 12 * sum(g.n_atoms for g in groups)
 
             def positions_fn(ts, groups=groups, grps=grps):
                 return [ts.positions[g.ix] if gr == "atoms"
@@ -301,10 +334,24 @@ class RadialDistributionFunction(GpuAnalysisBase):
             for v in box[:, keep].astype(np.float64).prod(axis=1):
                 self._area_or_volume += v
         same = self._same
+        ptrs, strides = batch.ptrs, batch.strides
+        if self._com is not None:
+            # raw atoms -> centres of mass on the device (com.cu); the kernels that
+            # read `outs` are queued on torch's current stream, so the allocator cannot
+            # recycle them early
+            import torch
+            outs = [torch.empty((batch.n_frames, n, 3), dtype=torch.float32,
+                                device=f"cuda:{self._device}") for n in self._com]
+            for slot, out in enumerate(outs):
+                self._ctx.com_reduce(slot, ptrs[slot], strides[slot], batch.n_frames,
+                                     out, 3 * self._com[slot], device=device)
+            ptrs = [o.data_ptr() for o in outs]
+            strides = [3 * n for n in self._com]
+            device = True
         self._ctx.rdf_accumulate(
-            batch.ptrs[0], batch.strides[0],
-            None if same else batch.ptrs[1],
-            0 if same else batch.strides[1],
+            ptrs[0], strides[0],
+            None if same else ptrs[1],
+            0 if same else strides[1],
             box, batch.n_frames, device=device, keepalive=batch.keepalive
         )
         _record(batch)
@@ -470,8 +517,10 @@ class StructureFactor(GpuAnalysisBase):
             n_surface_points: int = 8, q_max: float = None,
             wavevectors: np.ndarray = None, sort: bool = True,
             unique: bool = True, parallel: bool = False, verbose: bool = True,
-            precision: str = "fp64", kernel: str = None, **kwargs) -> None:
+            precision: str = "fp64", kernel: str = None, host_com: bool = False,
+            **kwargs) -> None:
 
+        self._host_com = bool(host_com)
         self._groups = ([groups] if hasattr(groups, "universe")
                         and hasattr(groups, "positions") else list(groups))
         self.universe = self._groups[0].universe
@@ -608,10 +657,21 @@ class StructureFactor(GpuAnalysisBase):
                          lattice_n=self._lattice_n, lattice_b=self._lattice_b,
                          mode=mode)
         atoms_only = all(g == "atoms" for g in self._groupings)
+        self._com = None
         if atoms_only:
             sets = [np.concatenate([g.ix for g in self._groups])]
             positions_fn = None
         else:
+            plans = [_com_plan(g, gr) for g, gr in zip(self._groups, self._groupings)]
+            if all(p is not None for p in plans) and len(plans) <= 8 \
+                    and not getattr(self, "_host_com", False):
+                # centres of mass on the device (com.cu), the groups written side by
+                # side into one [frames, N, 3] buffer
+                for slot, (starts, masses) in enumerate(plans):
+                    ctx.com_configure(slot, starts, masses)
+                self._com = [len(p[0]) - 1 for p in plans]
+                return ([g.ix for g in self._groups], None,
+                        12 * sum(g.n_atoms for g in self._groups))
             sets = [np.arange(self._N)]
 
             def positions_fn(ts):
@@ -623,8 +683,21 @@ class StructureFactor(GpuAnalysisBase):
         return sets, positions_fn, 12 * int(self._N)
 
     def _consume(self, batch, device: bool = False) -> None:
-        self._ctx.sq_accumulate(batch.ptrs[0], batch.strides[0], batch.n_frames,
-                                device=device, keepalive=batch.keepalive)
+        ptr, stride = batch.ptrs[0], batch.strides[0]
+        if self._com is not None:
+            import torch
+            N = int(self._N)
+            out = torch.empty((batch.n_frames, N, 3), dtype=torch.float32,
+                              device=f"cuda:{self._device}")
+            off = 0
+            for slot, n in enumerate(self._com):
+                self._ctx.com_reduce(slot, batch.ptrs[slot], batch.strides[slot],
+                                     batch.n_frames, out.data_ptr() + 12 * off, 3 * N,
+                                     device=device)
+                off += n
+            ptr, stride, device = out.data_ptr(), 3 * N, True
+        self._ctx.sq_accumulate(ptr, stride, batch.n_frames, device=device,
+                                keepalive=batch.keepalive)
         _record(batch)
 
     def _finish(self) -> None:

@@ -213,6 +213,7 @@ int mdh_ctx_destroy(mdh_ctx *c)
     SqState &S = c->sq;
     S.qv.release(); S.items.release(); S.qidx.release(); S.d_pairs.release();
     S.chunks.release(); S.tab.release(); S.rho.release(); S.ssf.release();
+    for (auto &k : c->com) { k.starts.release(); k.masses.release(); k.raw.release(); }
     IsfState &I = c->isf;
     I.rho_all.release(); I.window[0].release(); I.window[1].release(); I.vmap.release();
     I.cisf.release(); I.iisf.release();
@@ -399,6 +400,21 @@ int mdh_sq_fetch_rho(mdh_ctx *c, double *rho)
                              sizeof(double) * per_frame, cudaMemcpyDeviceToHost, c->stream));
     MDH_CUDA(cudaStreamSynchronize(c->stream));
     return MDH_OK;
+}
+
+int mdh_com_configure(mdh_ctx *c, int slot, int64_t n_atoms, int64_t n_entities,
+                      const int64_t *starts, const double *masses)
+{
+    CTX_GUARD(c);
+    return com_configure_impl(c, slot, n_atoms, n_entities, starts, masses);
+}
+
+int mdh_com_reduce(mdh_ctx *c, int slot, const float *pos, int64_t frame_stride, int location,
+                   int n_frames, float *out_device, int64_t out_frame_stride)
+{
+    CTX_GUARD(c);
+    return com_reduce_impl(c, slot, pos, frame_stride, location, n_frames, out_device,
+                           out_frame_stride);
 }
 
 int mdh_sq_configure_chains(mdh_ctx *c, int64_t n_chains, int64_t n_monomers)

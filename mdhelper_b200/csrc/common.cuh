@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -134,6 +135,15 @@ struct SqState {
     int64_t n_chains = 0, n_monomers = 0;
 };
 
+constexpr int kComSlots = 8;
+struct ComState {           // centres of mass of consecutive atom runs (com.cu)
+    bool configured = false;
+    int64_t n_atoms = 0, n_entities = 0;
+    DevBuf starts;         // int64[n_entities + 1]
+    DevBuf masses;         // double[n_atoms]
+    DevBuf raw;            // float[F][n_atoms][3] staging for host input
+};
+
 struct IsfState {           // intermediate scattering function on top of SqState
     bool on = false;
     int n_lags = 0;
@@ -191,6 +201,7 @@ struct mdh_ctx {
     RdfState rdf;
     SqState sq;
     IsfState isf;
+    ComState com[kComSlots];
 };
 
 // rdf.cu
@@ -209,6 +220,11 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                       int n_pairs, const int32_t *pairs, int mode);
 int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
                        int n_frames);
+// com.cu
+int com_configure_impl(mdh_ctx *c, int slot, int64_t n_atoms, int64_t n_entities,
+                       const int64_t *starts, const double *masses);
+int com_reduce_impl(mdh_ctx *c, int slot, const float *pos, int64_t stride, int location,
+                    int n_frames, float *out_device, int64_t out_stride);
 int sq_configure_chains_impl(mdh_ctx *c, int64_t n_chains, int64_t n_monomers);
 int isf_configure_impl(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frames);
 int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,

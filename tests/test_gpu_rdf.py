@@ -265,6 +265,40 @@ def test_centre_of_mass_groupings():
     assert np.array_equal(r.results.counts, counts)
 
 
+def test_device_centres_of_mass_equal_host():
+    """groupings on the device (com.cu) vs the host helper: identical float32 centres,
+    hence identical counts -- residues x residues, residues x atoms (identity plan for
+    the atoms side), unequal residue sizes, staged (strided frames) input."""
+    from mdhelper_b200.universe import SyntheticUniverse
+    rng = np.random.default_rng(21)
+    n_res = 900
+    sizes = rng.integers(1, 7, n_res)
+    res = np.repeat(np.arange(n_res), sizes)
+    n = res.size
+    dims = np.array([14.0, 15.0, 16.0, 90, 90, 90], np.float32)
+    pos = (rng.random((5, n, 3)) * dims[:3]).astype(np.float32)
+    u = SyntheticUniverse(pos, dims, resindices=res, segindices=res // 3,
+                          masses=rng.uniform(1.0, 40.0, n))
+    S = _structure()
+    half = int(np.searchsorted(res, n_res // 2))
+    g1, g2 = u.select(slice(0, half)), u.select(slice(half, n))
+    cases = [(u.atoms, None, "residues"), (u.atoms, None, "segments"),
+             (g1, g2, ("residues", "atoms")), (g1, g2, ("residues", "residues"))]
+    for a, b, grp in cases:
+        kw = dict(n_bins=60, range=(0.0, 6.0), groupings=grp, norm=None, verbose=False)
+        dev = S.RadialDistributionFunction(a, b, batch_frames=2, **kw).run()
+        assert dev._com is not None                         # the device path was taken
+        host = S.RadialDistributionFunction(a, b, host_com=True, **kw).run()
+        assert host._com is None
+        assert np.array_equal(dev.results.counts, host.results.counts)
+        assert dev.results.counts.sum() > 0
+    # scattered atoms: no device plan, host helper
+    sc = u.select(rng.permutation(n)[: n // 2])
+    r = S.RadialDistributionFunction(sc, groupings="residues", n_bins=20,
+                                     range=(0.0, 5.0), verbose=False).run()
+    assert r._com is None
+
+
 def test_config2_sized_frame_against_oracle():
     """One frame of the bench workload (10k x 10k two-group) vs the CPU oracle."""
     from mdhelper_b200 import synthetic

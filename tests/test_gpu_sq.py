@@ -206,6 +206,27 @@ def test_isf_larger_system_against_oracle():
     np.testing.assert_allclose(r.results.iisf, o["iisf"], rtol=1e-9, atol=1e-10)
 
 
+def test_device_centres_of_mass_equal_host():
+    """groupings="residues" with the centres of mass built on the device vs the host
+    helper (identical float32 centres -> S(q) to rounding), mixed with an atoms group."""
+    from mdhelper_b200.universe import SyntheticUniverse
+    rng = np.random.default_rng(5)
+    sizes = rng.integers(1, 6, 500)
+    res = np.repeat(np.arange(500), sizes)
+    n = res.size
+    dims = np.array([12.0, 12.0, 12.0, 90, 90, 90], np.float32)
+    pos = (rng.random((3, n, 3)) * 12).astype(np.float32)
+    u = SyntheticUniverse(pos, dims, resindices=res, masses=rng.uniform(1, 30, n))
+    half = int(np.searchsorted(res, 250))
+    g1, g2 = u.select(slice(0, half)), u.select(slice(half, n))
+    kw = dict(mode="partial", n_points=6, verbose=False)
+    for grp in (("residues", "residues"), ("residues", "atoms")):
+        d = _S().StructureFactor([g1, g2], grp, **kw).run()
+        h = _S().StructureFactor([g1, g2], grp, host_com=True, **kw).run()
+        assert d._com is not None and h._com is None
+        np.testing.assert_allclose(d.results.ssf, h.results.ssf, rtol=1e-12, atol=1e-13)
+
+
 # ---- single-chain structure factor (SURVEY.md section 8(f) rank 3) ---------------------
 
 def test_scsf_matches_golden(golden):
