@@ -5,11 +5,12 @@
 // only when a rigorous error bound proves that the reference's fp64 distance falls in
 // the same bin; every other pair ("uncertain": within the bound of a bin edge, about
 // 1 in 1,500 for the benchmark configurations) is re-evaluated with the exact
-// arithmetic of rdf_device.cuh::pair_d2 and corrected.  The fp32 path costs ~24
-// instructions per pair on the FP32/ALU pipes instead of 21 FP64-pipe instructions
-// plus conversions (46 in total) -- it removes the FP64 pipe as the bound.
+// arithmetic of rdf_device.cuh::pair_d2 and corrected.  The fp32 path costs ~17
+// issue slots per pair (8 packed f32x2 instructions on the FMA pipe, ~6 on the ALU
+// pipe, one MUFU, one RED) instead of 21 FP64-pipe instructions plus conversions (46
+// in total) -- it removes the FP64 pipe as the bound.
 //
-// fp32 evaluation (filter_eval), per axis:
+// fp32 evaluation (rdf_device.cuh::filter_eval2, two pairs per instruction), per axis:
 //     df = xj - xi                      the reference's own float32 difference (exact copy)
 //     t  = fma(df, inv, 1.5*2^23)       -> 1.5*2^23 + rint(df * inv), one rounding
 //     r  = t - 1.5*2^23                 exact
@@ -33,7 +34,6 @@
 // The window half-width is ceil(1.25 * bound * 2^k) + 1 units of 2^-k.  Frames whose
 // bound is not small against a bin (coordinates many boxes away, non-finite values)
 // are left to the exact kernel of rdf.cu.
-
 
 #include <algorithm>
 #include <type_traits>
