@@ -6,7 +6,11 @@ path of bbye98/mdhelper: the minimum-image pair-distance histogram behind
 ``RadialDistributionFunction`` and the direct-sum static structure factor.
 
 * :mod:`mdhelper_b200.analysis.structure` -- drop-in analysis classes
-  (constructor, ``.run(start, stop, step)`` and ``results.*`` as in the reference).
+  (constructor, ``.run(start, stop, step)`` and ``results.*`` as in the reference):
+  ``RadialDistributionFunction``, ``StructureFactor``,
+  ``IntermediateScatteringFunction``; :mod:`mdhelper_b200.analysis.polymer` --
+  ``SingleChainStructureFactor``; ``mdhelper_b200.analysis.CombinedAnalysis`` -- several
+  analyses over one upload of every frame.
 * :mod:`mdhelper_b200.universe` -- in-memory trajectory carrier (duck-types the
   slice of ``MDAnalysis.Universe`` the classes touch).
 * :mod:`mdhelper_b200._lib` -- ctypes binding of ``libmdh_b200.so``

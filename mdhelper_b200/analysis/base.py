@@ -74,6 +74,24 @@ def all_reduce_sum(array: np.ndarray, device=None) -> np.ndarray:
     return t.cpu().numpy()
 
 
+def _memory_coordinates(trajectory):
+    """
+    The whole trajectory as one float32 ``[F, N, 3]`` array if the reader keeps it in
+    memory: ``trajectory.coordinates`` (:class:`mdhelper_b200.universe.MemoryTrajectory`)
+    or MDAnalysis' ``MemoryReader.coordinate_array`` in its default frame-atom-coordinate
+    order; else ``None`` (frames are then read one by one through ``trajectory[i]``).
+    """
+    coords = getattr(trajectory, "coordinates", None)
+    if not isinstance(coords, np.ndarray):
+        coords = getattr(trajectory, "coordinate_array", None)
+        if getattr(trajectory, "stored_order", "fac") != "fac":
+            coords = None
+    if isinstance(coords, np.ndarray) and coords.ndim == 3 and coords.shape[2] == 3 \
+            and coords.shape[0] == len(trajectory):
+        return coords
+    return None
+
+
 class Batch:
     """A run of frames ready for the C ABI."""
 
@@ -110,7 +128,7 @@ class FrameFeeder:
         self.frames = np.asarray(frames, dtype=np.intp)
         self.batch_frames = max(1, int(batch_frames))
         self.positions_fn = positions_fn
-        coords = getattr(trajectory, "coordinates", None)
+        coords = _memory_coordinates(trajectory)
         steps = np.diff(self.frames)
         uniform = (len(self.frames) <= 1
                    or (steps[0] > 0 and bool(np.all(steps == steps[0]))))
@@ -130,7 +148,9 @@ class FrameFeeder:
 
     def _dims(self, frames):
         cells = getattr(self.trajectory, "unitcells", None)
-        if isinstance(cells, np.ndarray):
+        if not isinstance(cells, np.ndarray):          # MDAnalysis MemoryReader
+            cells = getattr(self.trajectory, "dimensions_array", None)
+        if isinstance(cells, np.ndarray) and cells.shape == (len(self.trajectory), 6):
             return np.ascontiguousarray(cells[frames], dtype=np.float32)
         out = np.empty((len(frames), 6), dtype=np.float32)
         for b, f in enumerate(frames):
@@ -378,7 +398,7 @@ class CombinedAnalysis:
         for a in self.analyses:
             a.n_local_frames = len(local)
         plans = [a._begin(local) for a in self.analyses]
-        coords = getattr(self._trajectory, "coordinates", None)
+        coords = _memory_coordinates(self._trajectory)
         d = np.diff(local)
         shared = (
             len(local) > 0 and isinstance(coords, np.ndarray)

@@ -260,3 +260,26 @@ def test_isclose_members_equals_the_reference_scan():
     for q, m in zip(uq, got):
         assert np.array_equal(m, np.flatnonzero(np.isclose(q, wn)))
     assert any(len(m) > 1 for m in got)
+
+
+def test_feeder_accepts_mdanalysis_memoryreader_layout():
+    """A reader that keeps the trajectory in memory under MDAnalysis' MemoryReader names
+    (coordinate_array / dimensions_array / stored_order) is fed without copies."""
+    class MemoryReaderLike:
+        def __init__(self, arr, dims):
+            self.coordinate_array, self.dimensions_array = arr, dims
+            self.stored_order = "fac"
+
+        def __len__(self):
+            return len(self.coordinate_array)
+
+    arr = np.random.default_rng(0).random((6, 40, 3)).astype(np.float32)
+    dims = np.tile(np.array([5, 5, 5, 90, 90, 90], np.float32), (6, 1))
+    t = MemoryReaderLike(arr, dims)
+    f = base.FrameFeeder(t, [np.arange(10, 30)], np.arange(0, 6, 2), 2)
+    assert f.zero_copy
+    b = next(iter(f))
+    assert b.ptrs[0] == arr.ctypes.data + 12 * 10 and b.strides[0] == 2 * 40 * 3
+    assert np.array_equal(b.dims, dims[[0, 2]])
+    t.stored_order = "afc"
+    assert not base.FrameFeeder(t, [np.arange(10, 30)], np.arange(6), 2).zero_copy
