@@ -72,6 +72,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--hist", default="auto")
+    ap.add_argument("--sq-kernel", default="lattice_dmma",
+                    choices=["lattice_dmma", "lattice_fp64"],
+                    help="lattice_dmma: FP64 matrix unit (default); lattice_fp64: scalar DFMA")
     ap.add_argument("--arith", default="auto", choices=["auto", "off"],
                     help="auto: fp32 filter + exact fp64 re-evaluation; off: fp64 for "
                          "every pair (the round-1 kernel)")
@@ -566,7 +569,8 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
     L = float(u.trajectory.unitcells[0, 0])
     q_max = 2 * np.pi * CFG4["n_max"] / L
     sf = StructureFactor([u.atoms], n_points=CFG4["n_points"], q_max=q_max, verbose=False,
-                         batch_frames=fps)
+                         batch_frames=fps, kernel=args.sq_kernel)
+    dmma = args.sq_kernel == "lattice_dmma"
     n_q = len(sf._wavenumbers)
     N = CFG4["n"]
 
@@ -583,7 +587,8 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
     dev = torch.from_numpy(u.trajectory.coordinates).cuda()
     ctx = _lib.Context(local)
     ctx.sq_configure(N, [0, N], sf._wavevectors, [(-1, -1)], lattice_n=sf._lattice_n,
-                     lattice_b=sf._lattice_b, mode="lattice_fp64")
+                     lattice_b=sf._lattice_b, mode=args.sq_kernel)
+    assert ctx.sq_kernel() == args.sq_kernel, ctx.sq_kernel()
     base = dev.data_ptr()
 
     def step(s):
@@ -658,17 +663,25 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
                 "h2d_bytes_per_step": world * fps * N * 12,
                 "d2h_bytes_per_step": world * n_q * 8,
                 "api": "StructureFactor([atoms], n_points=32, q_max=...).run(start, stop)"},
-        "roofline": {"kernel": "sq_lattice_kernel<double,16>", "bound": "fp64_pipe",
+        "roofline": {"kernel": "sq_lattice_mma_kernel" if dmma else "sq_lattice_kernel<double>",
+                     "bound": "fp64_pipe",
                      "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Ginstr/s",
                      "frac": achieved / peak,
                      "traffic": profiled_traffic("sq", 16, fps),
                      "traffic_note": "dram__bytes_read+write of profiles/r01_sq_metrics.csv "
                                      "(a 16-frame launch) scaled to this launch's frames; "
                                      "bytes",
-                     "nominal_vs_reachable": "a DFMA with three register operands sustains "
-                                             "42.6/clk/SM (profiles/microbench2_r01.json), "
-                                             "0.67 of the nominal rate used as peak",
-                     "per_unit": f"{FP64_OPS_PER_TERM} DFMA per (q, r) term",
+                     "nominal_vs_reachable":
+                         ("DMMA.8x8x4 sustains the nominal 63.6 FMA/clk/SM "
+                          "(profiles/microbench3_r01.json); the (column group x nz tile) "
+                          "tiling of the |q| <= q_max sphere carries padding slots that "
+                          "are executed but not counted as algorithmic work") if dmma else
+                         ("a DFMA with three register operands sustains 42.6/clk/SM "
+                          "(profiles/microbench2_r01.json), 0.67 of the nominal rate used "
+                          "as peak"),
+                     "per_unit": f"{FP64_OPS_PER_TERM} fp64 FMA per (q, r) term (complex "
+                                 "multiply-accumulate)" + (", issued as DMMA m8n8k4 "
+                                 "(256 FMA per warp instruction)" if dmma else ""),
                      "units_per_launch": terms, "launch_ms": kern_ms,
                      "peak_source": f"{peaks['pipe_source']}; {peaks['fp64_per_clk_sm']:.1f} "
                                     f"instr/clk/SM x {n_sm} SMs x 1965 MHz (max clock)",

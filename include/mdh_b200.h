@@ -88,8 +88,13 @@ enum {
     MDH_SQ_LATTICE_SFU = 2,   /* q = n*b: 32-bit fixed-point phase, MUFU sin/cos,
                                  fp64 accumulation (approximate: ~1e-6 abs/term) */
     MDH_SQ_GENERAL_FP64 = 3,  /* arbitrary q: fp64 dot product + fp64 sincos     */
-    MDH_SQ_LATTICE_FP32 = 4   /* q = n*b: the FP64 scheme on the FP32 pipe
+    MDH_SQ_LATTICE_FP32 = 4,  /* q = n*b: the FP64 scheme on the FP32 pipe
                                  (approximate: ~1e-7 relative per term)          */
+    MDH_SQ_LATTICE_DMMA = 5   /* q = n*b: per-axis phase factors, the complex rank-N
+                                 update on the FP64 matrix unit (mma.m8n8k4.f64);
+                                 what MDH_SQ_AUTO picks for lattice wavevectors; falls
+                                 back to MDH_SQ_LATTICE_FP64 when the phase-factor
+                                 tables do not fit in shared memory                */
 };
 
 typedef struct mdh_ctx mdh_ctx;
@@ -195,6 +200,8 @@ int mdh_sq_accumulate(mdh_ctx *ctx, const float *pos, int64_t frame_stride, int 
                       int n_frames);
 
 int mdh_sq_fetch(mdh_ctx *ctx, double *ssf /* [n_pairs][n_q] host */);
+/* The MDH_SQ_* kernel the current configuration runs (after AUTO / fallback). */
+int mdh_sq_kernel(mdh_ctx *ctx, int *mode);
 int mdh_sq_reset(mdh_ctx *ctx);
 int mdh_sq_accum_device(mdh_ctx *ctx, void **dptr);
 /* rho(q) of the LAST frame of the last batch: [n_rho][n_q][2] (re, im), n_rho =

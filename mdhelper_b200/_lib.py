@@ -25,7 +25,7 @@ RDF_MODES = {"auto": 0, "allpairs": 1, "cells": 2}
 HIST_MODES = {"auto": 0, "warp_atomic": 1, "lane_private": 2}
 FILTER_MODES = {"auto": 0, "off": 1, "on": 2, "audit": 3}
 SQ_MODES = {"auto": 0, "lattice_fp64": 1, "lattice_sfu": 2, "general_fp64": 3,
-            "lattice_fp32": 4}
+            "lattice_fp32": 4, "lattice_dmma": 5}
 
 _i32, _i64, _f64 = ctypes.c_int, ctypes.c_int64, ctypes.c_double
 _p = ctypes.c_void_p
@@ -54,6 +54,7 @@ SIGNATURES = {
     "mdh_sq_configure": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i32, _p, _i32]),
     "mdh_sq_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
     "mdh_sq_fetch": (_i32, [_p, _p]),
+    "mdh_sq_kernel": (_i32, [_p, _p]),
     "mdh_sq_reset": (_i32, [_p]),
     "mdh_sq_accum_device": (_i32, [_p, ctypes.POINTER(_p)]),
     "mdh_sq_fetch_rho": (_i32, [_p, _p]),
@@ -241,6 +242,12 @@ class Context:
         check(self._lib.mdh_sq_fetch(self._h, out.ctypes.data))
         self._keep.clear()
         return out
+
+    def sq_kernel(self) -> str:
+        """Name of the kernel strategy the current configuration runs."""
+        m = ctypes.c_int(0)
+        check(self._lib.mdh_sq_kernel(self._h, ctypes.byref(m)))
+        return {v: k for k, v in SQ_MODES.items()}[m.value]
 
     def sq_reset(self):
         check(self._lib.mdh_sq_reset(self._h))

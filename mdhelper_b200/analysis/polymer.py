@@ -68,6 +68,8 @@ class SingleChainStructureFactor(GpuAnalysisBase):
         periodic image, so this only matters when the box fluctuates.
     parallel, verbose
         As in the reference (``parallel`` is accepted and ignored).
+    kernel : `str`, keyword-only, optional
+        GPU kernel strategy (``"lattice_dmma"`` (default) or ``"lattice_fp64"``).
 
     Attributes
     ----------
@@ -78,8 +80,9 @@ class SingleChainStructureFactor(GpuAnalysisBase):
     def __init__(self, group, grouping: str = "atoms", n_points: int = 32, *,
                  n_chains: int = None, n_monomers: int = None, dimensions=None,
                  unwrap: bool = False, parallel: bool = False, verbose: bool = True,
-                 **kwargs) -> None:
+                 kernel: str = None, **kwargs) -> None:
         self._group = group
+        self._kernel = kernel
         self.universe = group.universe
         super().__init__(self.universe.trajectory, verbose, **kwargs)
         self._parallel = parallel
@@ -142,7 +145,7 @@ class SingleChainStructureFactor(GpuAnalysisBase):
         n = self._n_chains * self._n_monomers
         ctx.sq_configure(n, [0, n], self._wavevectors, [(-1, -1)],
                          lattice_n=self._lattice_n, lattice_b=self._lattice_b,
-                         mode="lattice_fp64")
+                         mode=self._kernel or "lattice_dmma")
         ctx.sq_configure_chains(self._n_chains, self._n_monomers)
         g = self._group
         if self._grouping == "atoms" and not self._unwrap:

@@ -372,6 +372,14 @@ int mdh_sq_fetch(mdh_ctx *c, double *ssf)
     return MDH_OK;
 }
 
+int mdh_sq_kernel(mdh_ctx *c, int *mode)
+{
+    MDH_REQUIRE(c && mode, MDH_EINVAL, "NULL argument");
+    MDH_REQUIRE(c->sq.configured, MDH_ESTATE, "sq: not configured");
+    *mode = c->sq.mode;
+    return MDH_OK;
+}
+
 int mdh_sq_reset(mdh_ctx *c)
 {
     CTX_GUARD(c);

@@ -122,6 +122,11 @@ struct SqState {
     DevBuf qv;             // double[n_q][3]
     DevBuf items;          // SqWorkItem[n_items]
     DevBuf qidx;           // int[n_items][kSqTM][kSqTN]
+    // DMMA lattice kernel (MDH_SQ_LATTICE_DMMA): one SqMmaItem per consumer warp
+    bool mma = false;      // built and selected for this configuration
+    int mma_items = 0, mma_warps = 0;   // items (padded to whole blocks), warps per block
+    DevBuf mitems;         // SqMmaItem[mma_items]
+    DevBuf mqidx;          // int[mma_items][groups][tiles][8][8]
     DevBuf d_pairs;        // int[n_pairs][2]
     DevBuf chunks;         // int4[n_chunks]: {start, end, rho_row, 0}
     int n_chunks = 0, chunk_len = 0;

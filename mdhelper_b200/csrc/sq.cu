@@ -241,6 +241,201 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
     }
 }
 
+// ---- lattice sum on the FP64 matrix unit (DMMA m8n8k4) ---------------------------------
+//
+// With A[c][j] = E_x(nx_c)[j] E_y(ny_c)[j] (c = (nx, ny) column, j = particle) and
+// B[j][nz] = E_z(nz)[j] the lattice sum is the complex rank-N update
+//     rho[c][nz] = sum_j A[c][j] B[j][nz]
+// i.e. four real matrix products (re re, im im, re im, im re).  mma.sync.m8n8k4.f64
+// (SASS DMMA.8x8x4) sustains the full 64 FMA/clk/SM with two 64-bit register operands
+// per 8 FMAs of a thread, where the scalar DFMA of sq_lattice_kernel is limited by
+// register-operand bandwidth to 42.6 (tools/microbench3.cu, profiles/microbench3_r01.json).
+//
+// A warp owns up to kMmaG groups of 8 columns x up to kMmaTZ tiles of 8 consecutive nz.
+// Fragment layout of m8n8k4 (lane = 4 g + k): A[g][k], B[k][g], C[g][2k], C[g][2k + 1].
+// Per step of 4 particles lane (g, k) loads E_x(nx_g), E_y(ny_g) of particle k (two
+// LDS.128), multiplies them (the A element), loads E_z(8 t + g) of particle k per tile
+// (one LDS.128 = the B elements re / im) and issues 4 DMMAs per (group, tile).
+//
+// Table row of one particle: double2 (re, im) entries  E_x(0..nmax_x) | E_y(0..nmax_y) |
+// E_z(0..8 * tiles - 1, zero past nmax_z), R entries with R = 2 (mod 8): the four
+// particles of a step start 8 banks apart, so the 16-byte loads of a quarter-warp (two
+// columns x four particles) are conflict-free whenever the two columns' nx (ny) are equal
+// or differ by an odd number -- the host pairs the columns that way.
+constexpr int kMmaG = 2;
+constexpr int kMmaTZ = 4;
+constexpr int kMmaMaxWarps = 16;   // consumer warps per block
+
+struct SqMmaItem {                 // one warp's work
+    int16_t nx[kMmaG][8], ny[kMmaG][8];
+    int ng, nt, t0, pad;           // groups, nz tiles, first tile
+};
+
+struct MmaParams {
+    const float *raw;
+    int64_t stride;
+    const int4 *vmap;              // as in LatticeParams
+    const int4 *chunks;
+    const SqMmaItem *items;
+    const int *qidx;               // [n_items][kMmaG][kMmaTZ][8][8]
+    double *rho;
+    int n_rho, n_q;
+    double *chain_out;
+    int n_chunks;
+    double b[3];
+    int nmax[3];
+    int offy, offz, nzpad, R;      // table layout in double2 entries
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int NG, int NT>
+__device__ __forceinline__ void sq_mma_subchunk(const double2 *row, int R4,
+                                                const int (&ox)[kMmaG], const int (&oy)[kMmaG],
+                                                int oz, double (&cre)[kMmaG][kMmaTZ][2],
+                                                double (&cim)[kMmaG][kMmaTZ][2])
+{
+#pragma unroll 2
+    for (int ks = 0; ks < kPS / 4; ++ks, row += R4) {
+        double ar[NG], ai[NG], nai[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            const double2 ex = row[ox[i]], ey = row[oy[i]];
+            ar[i] = ex.x * ey.x - ex.y * ey.y;
+            ai[i] = ex.x * ey.y + ex.y * ey.x;
+            nai[i] = __hiloint2double(__double2hiint(ai[i]) ^ (int)0x80000000,
+                                      __double2loint(ai[i]));
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const double2 ez = row[oz + 8 * t];
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+                dmma884(cre[i][t], ar[i], ez.x);
+                dmma884(cim[i][t], ar[i], ez.y);
+                dmma884(cre[i][t], nai[i], ez.y);
+                dmma884(cim[i][t], ai[i], ez.x);
+            }
+        }
+    }
+}
+
+// Block = n_cons consumer warps (one SqMmaItem each) followed by kSqProducers producer
+// threads that build the tables of sub-chunk s + 1 while the consumers work on s.
+__global__ void __launch_bounds__(kMmaMaxWarps * 32 + kSqProducers, 1)
+    sq_lattice_mma_kernel(const MmaParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    double2 *sTab = reinterpret_cast<double2 *>(smem);      // [2][kPS][R]
+    const int R = P.R;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n_cons = (int)blockDim.x - kSqProducers;
+    const bool producer = tid >= n_cons;
+    const int frame = blockIdx.z;
+    const int4 vm = P.vmap ? P.vmap[frame] : make_int4(frame, -1, 0, 0);
+    const float *pos = P.raw + (int64_t)vm.x * P.stride;
+    const float *pos0 = vm.y >= 0 ? P.raw + (int64_t)vm.y * P.stride : nullptr;
+    int4 chunk = make_int4(0, 0, 0, 0);
+
+    // task <-> (axis, particle): lanes of a warp write the same entry of consecutive rows
+    auto build = [&](double2 *tab, int p0) {
+        const int np = min(kPS, chunk.y - p0);
+        for (int task = tid - n_cons; task < kPS * 3; task += kSqProducers) {
+            const int a = task / kPS, p = task - a * kPS;
+            const int nm = P.nmax[a];
+            const int npad = a == 2 ? P.nzpad : nm + 1;
+            double2 *e = tab + p * R + (a == 0 ? 0 : a == 1 ? P.offy : P.offz);
+            double s1 = 0.0, c1 = 0.0, er = 0.0, ei = 0.0;
+            if (p < np) {
+                double x = (double)pos[3 * (int64_t)(p0 + p) + a];
+                if (pos0) x -= (double)pos0[3 * (int64_t)(p0 + p) + a];
+                sincos(P.b[a] * x, &s1, &c1);
+                er = 1.0;
+            }
+            for (int n = 0; n < npad; ++n) {
+                e[n] = n <= nm ? make_double2(er, ei) : make_double2(0.0, 0.0);
+                const double nr = er * c1 - ei * s1;
+                ei = er * s1 + ei * c1;
+                er = nr;
+            }
+        }
+    };
+
+    const int item_index = blockIdx.x * (n_cons >> 5) + min(tid >> 5, (n_cons >> 5) - 1);
+    const SqMmaItem *item = P.items + item_index;
+    const int ng = producer ? 0 : item->ng, nt = item->nt;
+    const int g = lane >> 2, k = lane & 3;
+    int ox[kMmaG], oy[kMmaG];
+#pragma unroll
+    for (int i = 0; i < kMmaG; ++i) {
+        ox[i] = item->nx[i][g];
+        oy[i] = P.offy + item->ny[i][g];
+    }
+    const int oz = P.offz + 8 * item->t0 + g;
+
+    double cre[kMmaG][kMmaTZ][2], cim[kMmaG][kMmaTZ][2];
+#pragma unroll
+    for (int i = 0; i < kMmaG; ++i)
+#pragma unroll
+        for (int t = 0; t < kMmaTZ; ++t)
+            cre[i][t][0] = cre[i][t][1] = cim[i][t][0] = cim[i][t][1] = 0.0;
+
+    const int *qi = P.qidx + (int64_t)item_index * (kMmaG * kMmaTZ * 64);
+    for (int ci = blockIdx.y; ci < P.n_chunks; ci += gridDim.y) {
+        chunk = P.chunks[ci];
+        if (producer) build(sTab, chunk.x);
+        __syncthreads();
+        int buf = 0;
+        for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS) {
+            const double2 *row = sTab + (size_t)buf * kPS * R + k * R;
+            if (producer) {
+                if (p0 + kPS < chunk.y) build(sTab + (size_t)(buf ^ 1) * kPS * R, p0 + kPS);
+            } else {
+#define MDH_MMA_CASE(G, T) \
+    case G * 8 + T: sq_mma_subchunk<G, T>(row, 4 * R, ox, oy, oz, cre, cim); break;
+                switch (ng * 8 + nt) {
+                    MDH_MMA_CASE(1, 1) MDH_MMA_CASE(1, 2) MDH_MMA_CASE(1, 3) MDH_MMA_CASE(1, 4)
+                    MDH_MMA_CASE(2, 1) MDH_MMA_CASE(2, 2) MDH_MMA_CASE(2, 3) MDH_MMA_CASE(2, 4)
+                    default: break;
+                }
+#undef MDH_MMA_CASE
+            }
+            __syncthreads();
+            buf ^= 1;
+        }
+        if (producer) continue;
+
+        double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
+#pragma unroll
+        for (int i = 0; i < kMmaG; ++i)
+#pragma unroll
+            for (int t = 0; t < kMmaTZ; ++t) {
+                if (i < ng && t < nt) {
+                    // this lane holds C[g][2k], C[g][2k + 1]
+                    const int2 q2 = *reinterpret_cast<const int2 *>(
+                        qi + ((i * kMmaTZ + t) * 8 + g) * 8 + 2 * k);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int q = j ? q2.y : q2.x;
+                        if (q < 0) continue;
+                        const double re = cre[i][t][j], im = cim[i][t][j];
+                        if (P.chain_out) {
+                            atomicAdd(P.chain_out + q, re * re + im * im);
+                        } else {
+                            atomicAdd(out + 2 * q, re);
+                            atomicAdd(out + 2 * q + 1, im);
+                        }
+                    }
+                }
+                cre[i][t][0] = cre[i][t][1] = cim[i][t][0] = cim[i][t][1] = 0.0;
+            }
+    }
+}
+
 struct GeneralParams {
     const float *raw;
     int64_t stride;
@@ -332,6 +527,129 @@ int launch_lattice(mdh_ctx *c, const LatticeParams &P, dim3 grid, int block)
     return MDH_OK;
 }
 
+
+// ---- host side: work items of the DMMA kernel ---------------------------------------
+
+struct Column { int nx, ny; std::vector<int> q; };   // q[nz] = wavevector index or -1
+
+static int column_top(const Column &c)                // 1 + largest nz present
+{
+    int t = 0;
+    for (int z = 0; z < (int)c.q.size(); ++z) if (c.q[z] >= 0) t = z + 1;
+    return t;
+}
+
+// table layout of sq_lattice_mma_kernel (double2 entries per particle)
+static void mma_layout(const int (&nmax)[3], int *offy, int *offz, int *nzpad, int *R)
+{
+    *offy = nmax[0] + 1;
+    *offz = *offy + nmax[1] + 1;
+    *nzpad = (nmax[2] + 8) / 8 * 8;
+    int r = *offz + *nzpad;
+    while (r % 8 != 2) ++r;
+    *R = r;
+}
+static size_t mma_smem_bytes(const int (&nmax)[3])
+{
+    int offy, offz, nzpad, R;
+    mma_layout(nmax, &offy, &offz, &nzpad, &R);
+    return (size_t)2 * kPS * R * sizeof(double2);
+}
+constexpr size_t kMmaSmemLimit = 200 * 1024;
+
+// cols: sorted by decreasing column_top.  Columns are paired so that the two columns a
+// quarter-warp loads together have nx (and ny) equal or an odd distance apart (see the
+// bank analysis at the kernel), four pairs make a group of 8, kMmaG consecutive groups x
+// <= kMmaTZ nz tiles make a warp item; items are dealt to blocks and, inside a block, to
+// the four warp schedulers (warp w runs on scheduler w % 4) by decreasing cost so that
+// every scheduler's FP64 unit gets the same number of DMMAs between two barriers.
+static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
+                            std::vector<SqMmaItem> &out_items, std::vector<int> &out_qidx,
+                            int &warps_per_block)
+{
+    const int n = (int)cols.size();
+    auto compatible = [&](int a, int b) {
+        const int dx = std::abs(cols[a].nx - cols[b].nx), dy = std::abs(cols[a].ny - cols[b].ny);
+        return (dx == 0 || (dx & 1)) && (dy == 0 || (dy & 1));
+    };
+    std::vector<int> slot;                            // column index or -1 (dummy), pairs
+    std::vector<char> used(n, 0);
+    for (int a = 0; a < n; ++a) {
+        if (used[a]) continue;
+        used[a] = 1;
+        int partner = -1;
+        for (int b = a + 1; b < n && b < a + 96; ++b)
+            if (!used[b] && compatible(a, b)) { partner = b; break; }
+        if (partner >= 0) used[partner] = 1;
+        slot.push_back(a);
+        slot.push_back(partner);
+    }
+    while (slot.size() % 8) slot.push_back(-1);
+    const int n_groups = (int)slot.size() / 8;
+    auto group_tiles = [&](int gi) {
+        int t = 0;
+        for (int m = 0; m < 8; ++m)
+            if (slot[gi * 8 + m] >= 0) t = std::max(t, (column_top(cols[slot[gi * 8 + m]]) + 7) / 8);
+        return t;
+    };
+    struct Proto { int g0, ng, t0, nt; };
+    std::vector<Proto> protos;
+    for (int g0 = 0; g0 < n_groups; g0 += kMmaG) {
+        const int ng = std::min(kMmaG, n_groups - g0);
+        int tiles = 0;
+        for (int i = 0; i < ng; ++i) tiles = std::max(tiles, group_tiles(g0 + i));
+        for (int t0 = 0; t0 < tiles; t0 += kMmaTZ)
+            protos.push_back(Proto{g0, ng, t0, std::min(kMmaTZ, tiles - t0)});
+    }
+    std::stable_sort(protos.begin(), protos.end(), [](const Proto &a, const Proto &b) {
+        return a.ng * a.nt > b.ng * b.nt;
+    });
+    const int n_items = (int)protos.size();
+    const int n_blocks = (n_items + kMmaMaxWarps - 1) / kMmaMaxWarps;
+    const int W = (n_items + n_blocks - 1) / n_blocks;
+    warps_per_block = W;
+    // bins = (block, scheduler); capacity = warps of the block on that scheduler
+    std::vector<int> load(n_blocks * 4, 0), fill(n_blocks * 4, 0);
+    std::vector<int> place(n_blocks * W, -1);         // slot -> proto
+    for (int p = 0; p < n_items; ++p) {
+        int best = -1;
+        for (int bin = 0; bin < n_blocks * 4; ++bin) {
+            const int s = bin & 3, cap = (W - s + 3) / 4;
+            if (fill[bin] >= cap) continue;
+            if (best < 0 || load[bin] < load[best]) best = bin;
+        }
+        place[(best >> 2) * W + (best & 3) + 4 * fill[best]] = p;
+        fill[best]++;
+        load[best] += protos[p].ng * protos[p].nt;
+    }
+    out_items.assign((size_t)n_blocks * W, SqMmaItem{});
+    out_qidx.assign((size_t)n_blocks * W * kMmaG * kMmaTZ * 64, -1);
+    for (int s = 0; s < n_blocks * W; ++s) {
+        if (place[s] < 0) continue;
+        const Proto &pr = protos[place[s]];
+        SqMmaItem &it = out_items[s];
+        it.ng = pr.ng; it.nt = pr.nt; it.t0 = pr.t0;
+        for (int i = 0; i < pr.ng; ++i)
+            for (int m = 0; m < 8; ++m) {
+                int ci = slot[(pr.g0 + i) * 8 + m];
+                const bool dummy = ci < 0;
+                if (dummy) ci = slot[(pr.g0 + i) * 8 + (m ^ 1)];   // partner's entries
+                if (ci < 0) ci = 0;                                  // an all-dummy pair
+                it.nx[i][m] = (int16_t)cols[ci].nx;
+                it.ny[i][m] = (int16_t)cols[ci].ny;
+                if (dummy) continue;
+                for (int t = 0; t < pr.nt; ++t)
+                    for (int z = 0; z < 8; ++z) {
+                        const int nz = 8 * (pr.t0 + t) + z;
+                        if (nz < (int)cols[ci].q.size())
+                            out_qidx[(((size_t)s * kMmaG + i) * kMmaTZ + t) * 64 + m * 8 + z] =
+                                cols[ci].q[nz];
+                    }
+            }
+    }
+    (void)nm;
+}
+
 }  // namespace
 
 // ---- host side ------------------------------------------------------------------
@@ -350,7 +668,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
         MDH_REQUIRE(goff[g] < goff[g + 1], MDH_EINVAL, "sq: group %d is empty", g);
     MDH_REQUIRE(n_q >= 1 && wv != nullptr, MDH_EINVAL, "sq: wavevectors missing");
     MDH_REQUIRE(n_pairs >= 1 && pairs != nullptr, MDH_EINVAL, "sq: pairs missing");
-    MDH_REQUIRE(mode >= MDH_SQ_AUTO && mode <= MDH_SQ_LATTICE_FP32, MDH_EINVAL,
+    MDH_REQUIRE(mode >= MDH_SQ_AUTO && mode <= MDH_SQ_LATTICE_DMMA, MDH_EINVAL,
                 "sq: invalid mode");
     bool all = false;
     for (int p = 0; p < n_pairs; ++p) {
@@ -365,7 +683,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
         }
     }
     const bool want_lattice = mode == MDH_SQ_LATTICE_FP64 || mode == MDH_SQ_LATTICE_FP32 ||
-                              mode == MDH_SQ_LATTICE_SFU;
+                              mode == MDH_SQ_LATTICE_SFU || mode == MDH_SQ_LATTICE_DMMA;
     MDH_REQUIRE(!want_lattice || (lat_n && lat_b), MDH_EINVAL,
                 "sq: a lattice kernel was requested without lattice_n / lattice_b");
     MDH_REQUIRE(mode != MDH_SQ_LATTICE_SFU, MDH_EINVAL,
@@ -385,6 +703,9 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
     bool lattice = lat_n && lat_b && mode != MDH_SQ_GENERAL_FP64;
     std::vector<SqWorkItem> items;
     std::vector<int> qidx;
+    std::vector<SqMmaItem> mitems;
+    std::vector<int> mqidx;
+    int mma_warps = 0;
     if (lattice) {
         int nm[3] = {0, 0, 0};
         for (int i = 0; i < n_q && lattice; ++i)
@@ -393,7 +714,6 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                 if (n < 0 || n > 1023) lattice = false;
                 else nm[k] = std::max(nm[k], n);
             }
-        struct Column { int nx, ny; std::vector<int> q; };   // q[nz] = wavevector index
         std::vector<Column> cols;
         if (lattice) {
             std::map<std::pair<int, int>, int> where;
@@ -411,11 +731,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
             }
         }
         if (lattice) {
-            auto top = [](const Column &c) {                 // 1 + largest nz present
-                int t = 0;
-                for (int z = 0; z < (int)c.q.size(); ++z) if (c.q[z] >= 0) t = z + 1;
-                return t;
-            };
+            auto top = column_top;
             std::stable_sort(cols.begin(), cols.end(),
                              [&](const Column &a, const Column &b) { return top(a) > top(b); });
             const int n_seg = (nm[2] + kSqTN) / kSqTN;
@@ -455,15 +771,23 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                 qidx.insert(qidx.end(), kSqTM * kSqTN, -1);
             }
             for (int k = 0; k < 3; ++k) { S.nmax[k] = nm[k]; S.b[k] = lat_b[k]; }
+
+            // ---- DMMA work items (sq_lattice_mma_kernel) ----
+            if (mode == MDH_SQ_AUTO || mode == MDH_SQ_LATTICE_DMMA)
+                mma_build_items(cols, nm, mitems, mqidx, mma_warps);
         }
     }
     MDH_REQUIRE(lattice || !want_lattice, MDH_EINVAL,
                 "sq: wavevectors are not usable by the lattice kernels "
                 "(need 0 <= n <= 1023 and no duplicates)");
     S.lattice = lattice;
-    S.mode = lattice ? (mode == MDH_SQ_LATTICE_FP32 ? MDH_SQ_LATTICE_FP32 : MDH_SQ_LATTICE_FP64)
-                     : MDH_SQ_GENERAL_FP64;
+    S.mma = lattice && !mitems.empty() && mma_smem_bytes(S.nmax) <= kMmaSmemLimit;
+    S.mode = !lattice ? MDH_SQ_GENERAL_FP64
+             : mode == MDH_SQ_LATTICE_FP32 ? MDH_SQ_LATTICE_FP32
+             : S.mma ? MDH_SQ_LATTICE_DMMA : MDH_SQ_LATTICE_FP64;
     S.n_items = (int)items.size();
+    S.mma_items = S.mma ? (int)mitems.size() : 0;
+    S.mma_warps = mma_warps;
 
     if (int rc = S.qv.reserve(sizeof(double) * 3 * n_q)) return rc;
     if (int rc = S.d_pairs.reserve(sizeof(int) * 2 * n_pairs)) return rc;
@@ -481,6 +805,14 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
         MDH_CUDA(cudaMemcpyAsync(S.qidx.p, qidx.data(), sizeof(int) * qidx.size(),
                                  cudaMemcpyHostToDevice, c->stream));
     }
+    if (S.mma) {
+        if (int rc = S.mitems.reserve(sizeof(SqMmaItem) * mitems.size())) return rc;
+        if (int rc = S.mqidx.reserve(sizeof(int) * mqidx.size())) return rc;
+        MDH_CUDA(cudaMemcpyAsync(S.mitems.p, mitems.data(), sizeof(SqMmaItem) * mitems.size(),
+                                 cudaMemcpyHostToDevice, c->stream));
+        MDH_CUDA(cudaMemcpyAsync(S.mqidx.p, mqidx.data(), sizeof(int) * mqidx.size(),
+                                 cudaMemcpyHostToDevice, c->stream));
+    }
     MDH_CUDA(cudaStreamSynchronize(c->stream));   // host sources are caller/local memory
     S.n_chunks = 0;
     S.configured = true;
@@ -491,12 +823,16 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
 static int sq_build_chunks(mdh_ctx *c, int n_frames)
 {
     SqState &S = c->sq;
-    const int item_blocks = S.lattice ? S.n_items / S.block : (S.n_q + 127) / 128;
+    const int item_blocks = S.mode == MDH_SQ_LATTICE_DMMA ? S.mma_items / S.mma_warps
+                            : S.lattice ? S.n_items / S.block : (S.n_q + 127) / 128;
     // enough blocks for ~6 waves, chunks a multiple of the sub-chunk length
     int64_t want = ((int64_t)c->sm_count * 2 * 6 + (int64_t)item_blocks * n_frames - 1) /
                    ((int64_t)item_blocks * n_frames);
     int64_t len = (S.n_total + want - 1) / std::max<int64_t>(want, 1);
     len = std::max<int64_t>(256, std::min<int64_t>(len, 4096));
+    // equal chunks (a short last chunk is a short last block of every frame)
+    const int64_t span = S.n_rho == 1 ? S.n_total : S.n_total / S.n_groups;
+    len = (span + (span + len - 1) / len - 1) / ((span + len - 1) / len);
     len = (len + kPS - 1) / kPS * kPS;
     if (S.n_chains > 0) len = -S.n_monomers;   // single-chain layout: its own cache key
     if (S.n_chunks > 0 && S.chunk_len == (int)len) return MDH_OK;
@@ -536,6 +872,27 @@ static int sq_compute_rho(mdh_ctx *c, const float *raw, int64_t stride, const in
     if (S.n_chains == 0) MDH_CUDA(cudaMemsetAsync(rho, 0, rho_bytes, c->stream));
     MDH_REQUIRE(S.n_chains == 0 || S.lattice, MDH_ESTATE,
                 "sq: single-chain mode needs lattice wavevectors");
+    if (S.mode == MDH_SQ_LATTICE_DMMA) {
+        MmaParams P;
+        mma_layout(S.nmax, &P.offy, &P.offz, &P.nzpad, &P.R);
+        P.raw = raw; P.stride = stride; P.vmap = vmap;
+        P.chunks = S.chunks.as<int4>();
+        P.items = S.mitems.as<SqMmaItem>();
+        P.qidx = S.mqidx.as<int>();
+        P.rho = rho;
+        P.n_rho = S.n_rho; P.n_q = S.n_q;
+        P.chain_out = S.n_chains > 0 ? S.ssf.as<double>() : nullptr;
+        P.n_chunks = S.n_chunks;
+        for (int k = 0; k < 3; ++k) { P.b[k] = S.b[k]; P.nmax[k] = S.nmax[k]; }
+        const size_t smem = mma_smem_bytes(S.nmax);
+        MDH_CUDA(cudaFuncSetAttribute(sq_lattice_mma_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(S.mma_items / S.mma_warps, std::min(S.n_chunks, 65535), n_vframes);
+        sq_lattice_mma_kernel<<<grid, S.mma_warps * 32 + kSqProducers, smem, c->stream>>>(P);
+        MDH_CUDA(cudaGetLastError());
+        c->launches++;
+        return MDH_OK;
+    }
     if (S.lattice) {
         LatticeParams P;
         // row layout in table elements: E_x re | E_x im | E_y re | E_y im | E_z (re, im)

@@ -20,7 +20,7 @@ def _groups(u, g):
     return u.select(slice(0, n)), u.select(slice(n, u.atoms.n_atoms))
 
 
-@pytest.mark.parametrize("kernel", [None, "general_fp64"])
+@pytest.mark.parametrize("kernel", [None, "lattice_fp64", "general_fp64"])
 @pytest.mark.parametrize("mode", [None, "pair", "partial"])
 def test_class_matches_golden(golden, mode, kernel):
     g = golden("sq_small")
@@ -35,6 +35,8 @@ def test_class_matches_golden(golden, mode, kernel):
         np.testing.assert_allclose(s.results.wavenumbers,
                                    g[f"wavenumbers_{mode}_{form}"], rtol=1e-13)
     assert len(s.results.pairs) == (3 if mode == "partial" else 1)
+    # the default for lattice wavevectors is the FP64 matrix-unit kernel
+    assert s._ctx.sq_kernel() == (kernel or "lattice_dmma")
 
 
 def test_raw_grid_order_and_rho(golden):
@@ -71,7 +73,7 @@ def test_off_lattice_wavevectors(golden):
 def test_noncubic(golden):
     g = golden("sq_noncubic")
     u = universe_from(g)
-    for kernel in (None, "general_fp64"):
+    for kernel in (None, "lattice_fp64", "general_fp64"):
         s = _S().StructureFactor([u.atoms], n_points=int(g["n_points"]),
                                  q_max=float(g["q_max"]), kernel=kernel,
                                  verbose=False).run()
@@ -90,8 +92,14 @@ def test_config4_frame(golden):
     s = _S().StructureFactor([u.atoms], n_points=32, q_max=float(g["q_max"]),
                              sort=False, unique=False, verbose=False).run()
     assert s.results.ssf.shape == (1, 2446)
+    assert s._ctx.sq_kernel() == "lattice_dmma"
     np.testing.assert_allclose(s.results.ssf, g["ssf_raw"], rtol=1e-6, atol=0)
     np.testing.assert_allclose(s.results.ssf, g["ssf_raw"], rtol=1e-9, atol=1e-12)
+    sd = _S().StructureFactor([u.atoms], n_points=32, q_max=float(g["q_max"]),
+                              sort=False, unique=False, kernel="lattice_fp64",
+                              verbose=False).run()
+    assert sd._ctx.sq_kernel() == "lattice_fp64"
+    np.testing.assert_allclose(sd.results.ssf, g["ssf_raw"], rtol=1e-9, atol=1e-12)
     su = _S().StructureFactor([u.atoms], n_points=32, q_max=float(g["q_max"]),
                               verbose=False).run()
     np.testing.assert_allclose(su.results.ssf, g["ssf_unique"], rtol=1e-9, atol=1e-12)
@@ -111,10 +119,41 @@ def test_default_grid_n_points_32_no_qmax():
     from mdhelper_b200 import synthetic
     from oracle import reference_port as rp
     u = synthetic.lj_fluid(300, 2, seed=21)
-    s = _S().StructureFactor([u.atoms], sort=False, unique=False, verbose=False).run()
-    assert s.results.ssf.shape == (1, 32768)
     want = rp.ssf_run(u, [u.atoms], sort=False, unique=False, n_threads=8)
-    np.testing.assert_allclose(s.results.ssf, want["ssf"], rtol=1e-9, atol=1e-11)
+    for kernel in (None, "lattice_fp64"):
+        s = _S().StructureFactor([u.atoms], sort=False, unique=False, kernel=kernel,
+                                 verbose=False).run()
+        assert s.results.ssf.shape == (1, 32768)
+        np.testing.assert_allclose(s.results.ssf, want["ssf"], rtol=1e-9, atol=1e-11)
+
+
+def test_mma_tiling_odd_shapes():
+    """DMMA kernel: grids whose column count is not a multiple of 8, a single column,
+    nz ranges that need a partial last tile and more than four tiles, anisotropic
+    n_max, two groups with a cross term -- against the general (sincos) kernel."""
+    from mdhelper_b200 import synthetic
+    u = synthetic.lj_fluid(777, 3, seed=31)
+    L = float(u.dimensions[0])
+    cases = [dict(n_points=3), dict(n_points=5, q_max=2 * np.pi * 3.3 / L),
+             dict(n_points=40, q_max=2 * np.pi * 5.01 / L), dict(n_points=37, q_max=None)]
+    for kw in cases:
+        kw = {k: v for k, v in kw.items() if v is not None}
+        a = _S().StructureFactor([u.atoms], sort=False, unique=False, verbose=False,
+                                 **kw).run()
+        assert a._ctx.sq_kernel() == "lattice_dmma"
+        b = _S().StructureFactor([u.atoms], sort=False, unique=False, verbose=False,
+                                 kernel="general_fp64", **kw).run()
+        np.testing.assert_allclose(a.results.ssf, b.results.ssf, rtol=1e-9, atol=1e-10)
+    # user wavevectors on the lattice: one column (0, 0, nz) and a sparse set
+    b3 = 2 * np.pi / np.asarray(u.dimensions[:3], dtype=np.float64)
+    n = np.array([[0, 0, z] for z in range(0, 45, 3)] + [[7, 2, 1], [1, 30, 0], [9, 9, 9]])
+    wv = n * b3
+    g1, g2 = u.select(slice(0, 300)), u.select(slice(300, 777))
+    a = _S().StructureFactor([g1, g2], mode="partial", wavevectors=wv, sort=False,
+                             unique=False, verbose=False).run()
+    b = _S().StructureFactor([g1, g2], mode="partial", wavevectors=wv, sort=False,
+                             unique=False, kernel="general_fp64", verbose=False).run()
+    np.testing.assert_allclose(a.results.ssf, b.results.ssf, rtol=1e-9, atol=1e-10)
 
 
 def test_frame_additivity_and_selection():
@@ -135,7 +174,7 @@ def test_frame_additivity_and_selection():
 
 # ---- intermediate scattering function ------------------
 
-@pytest.mark.parametrize("kernel", [None, "general_fp64"])
+@pytest.mark.parametrize("kernel", [None, "lattice_fp64", "general_fp64"])
 @pytest.mark.parametrize("mode", [None, "pair", "partial"])
 def test_isf_matches_golden(golden, mode, kernel):
     """GPU IntermediateScatteringFunction vs the fixtures of the reference's real class:
@@ -239,8 +278,10 @@ def test_scsf_matches_golden(golden):
     u = universe_from(g)
     kw = dict(n_points=int(g["n_points"]), n_chains=int(g["n_chains"]),
               n_monomers=int(g["n_monomers"]), verbose=False)
-    for unwrap in (False, True):
-        r = SingleChainStructureFactor(u.atoms, unwrap=unwrap, batch_frames=4, **kw).run()
+    for unwrap, kernel in ((False, None), (True, None), (False, "lattice_fp64")):
+        r = SingleChainStructureFactor(u.atoms, unwrap=unwrap, batch_frames=4,
+                                       kernel=kernel, **kw).run()
+        assert r._ctx.sq_kernel() == (kernel or "lattice_dmma")
         np.testing.assert_allclose(r.results.scsf, g[f"scsf_unwrap{int(unwrap)}"],
                                    rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(r.results.wavenumbers, g["wavenumbers"], rtol=1e-13)
