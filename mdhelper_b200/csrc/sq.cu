@@ -264,11 +264,12 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
 // or differ by an odd number -- the host pairs the columns that way.
 constexpr int kMmaG = 2;
 constexpr int kMmaTZ = 4;
-constexpr int kMmaMaxWarps = 16;   // consumer warps per block
+constexpr int kMmaMaxWarps = 14;   // consumer warps per block (+ 2 producer warps = 512 threads)
 
 struct SqMmaItem {                 // one warp's work
     int16_t nx[kMmaG][8], ny[kMmaG][8];
-    int ng, nt, t0, pad;           // groups, nz tiles, first tile
+    int nt[kMmaG];                 // nz tiles of each group, nt[0] >= nt[1]; 0: unused
+    int t0, pad;                   // first tile
 };
 
 struct MmaParams {
@@ -281,7 +282,7 @@ struct MmaParams {
     double *rho;
     int n_rho, n_q;
     double *chain_out;
-    int n_chunks;
+    int n_chunks, n_units;         // work units = (frame, chunk), frame-major
     double b[3];
     int nmax[3];
     int offy, offz, nzpad, R;      // table layout in double2 entries
@@ -293,81 +294,151 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-template <int NG, int NT>
-__device__ __forceinline__ void sq_mma_subchunk(const double2 *row, int R4,
+// One sub-chunk (kPS particles, 4 per step) into the accumulators.  nt0 / nt1: nz tiles
+// of the item's first / second column group (warp-uniform; nt1 = 0: no second group).
+__device__ __forceinline__ void sq_mma_subchunk(const double2 *row, int R4, int nt0, int nt1,
                                                 const int (&ox)[kMmaG], const int (&oy)[kMmaG],
                                                 int oz, double (&cre)[kMmaG][kMmaTZ][2],
                                                 double (&cim)[kMmaG][kMmaTZ][2])
 {
 #pragma unroll 2
     for (int ks = 0; ks < kPS / 4; ++ks, row += R4) {
-        double ar[NG], ai[NG], nai[NG];
+        double ar[kMmaG], ai[kMmaG], nai[kMmaG];
 #pragma unroll
-        for (int i = 0; i < NG; ++i) {
-            const double2 ex = row[ox[i]], ey = row[oy[i]];
-            ar[i] = ex.x * ey.x - ex.y * ey.y;
-            ai[i] = ex.x * ey.y + ex.y * ey.x;
-            nai[i] = __hiloint2double(__double2hiint(ai[i]) ^ (int)0x80000000,
-                                      __double2loint(ai[i]));
+        for (int i = 0; i < kMmaG; ++i) {
+            if (i == 0 || nt1 > 0) {
+                const double2 ex = row[ox[i]], ey = row[oy[i]];
+                ar[i] = ex.x * ey.x - ex.y * ey.y;
+                ai[i] = ex.x * ey.y + ex.y * ey.x;
+                nai[i] = __hiloint2double(__double2hiint(ai[i]) ^ (int)0x80000000,
+                                          __double2loint(ai[i]));
+            }
         }
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const double2 ez = row[oz + 8 * t];
+        for (int t = 0; t < kMmaTZ; ++t) {
+            if (t < nt0) {
+                const double2 ez = row[oz + 8 * t];
 #pragma unroll
-            for (int i = 0; i < NG; ++i) {
-                dmma884(cre[i][t], ar[i], ez.x);
-                dmma884(cim[i][t], ar[i], ez.y);
-                dmma884(cre[i][t], nai[i], ez.y);
-                dmma884(cim[i][t], ai[i], ez.x);
+                for (int i = 0; i < kMmaG; ++i) {
+                    if (i == 0 || t < nt1) {
+                        dmma884(cre[i][t], ar[i], ez.x);
+                        dmma884(cim[i][t], ar[i], ez.y);
+                        dmma884(cre[i][t], nai[i], ez.y);
+                        dmma884(cim[i][t], ai[i], ez.x);
+                    }
+                }
             }
         }
     }
 }
 
-// Block = n_cons consumer warps (one SqMmaItem each) followed by kSqProducers producer
-// threads that build the tables of sub-chunk s + 1 while the consumers work on s.
-__global__ void __launch_bounds__(kMmaMaxWarps * 32 + kSqProducers, 1)
+// mbarrier helpers (CTA scope): producers -> consumers "stage full", consumers ->
+// producers "stage empty"; arrive has release, try_wait acquire semantics
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+                 :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}"
+                 :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}"
+        :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+constexpr int kMmaStages = 3;      // table buffers in flight
+constexpr int kMmaProducers = 64;  // threads building the 3 * kPS (particle, axis) tables
+
+// Persistent block = n_cons consumer warps (one SqMmaItem each) followed by kMmaProducers
+// producer threads.  The block walks the work units (frame, particle chunk) blockIdx.y,
+// blockIdx.y + gridDim.y, ...; the producers build the phase-factor tables of the
+// sub-chunks (32 particles) into a ring of kMmaStages buffers, running ahead of the
+// consumers across unit boundaries; "full" / "empty" mbarriers per stage -- a consumer
+// warp waits only for the producers, never for the other consumer warps.
+__global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
     sq_lattice_mma_kernel(const MmaParams P)
 {
+    static_assert(kMmaMaxWarps * 32 + kMmaProducers == 512, "128 registers per thread");
     extern __shared__ __align__(16) unsigned char smem[];
-    double2 *sTab = reinterpret_cast<double2 *>(smem);      // [2][kPS][R]
+    __shared__ uint64_t bar_full[kMmaStages], bar_empty[kMmaStages];
+    double2 *sTab = reinterpret_cast<double2 *>(smem);      // [kMmaStages][kPS][R]
     const int R = P.R;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int n_cons = (int)blockDim.x - kSqProducers;
+    const int n_cons = (int)blockDim.x - kMmaProducers;
     const bool producer = tid >= n_cons;
-    const int frame = blockIdx.z;
-    const int4 vm = P.vmap ? P.vmap[frame] : make_int4(frame, -1, 0, 0);
-    const float *pos = P.raw + (int64_t)vm.x * P.stride;
-    const float *pos0 = vm.y >= 0 ? P.raw + (int64_t)vm.y * P.stride : nullptr;
-    int4 chunk = make_int4(0, 0, 0, 0);
+    if (tid == 0)
+        for (int s = 0; s < kMmaStages; ++s) {
+            mbar_init(bar_full + s, kMmaProducers);
+            mbar_init(bar_empty + s, n_cons >> 5);
+        }
+    __syncthreads();
 
-    // task <-> (axis, particle): lanes of a warp write the same entry of consecutive rows
-    auto build = [&](double2 *tab, int p0) {
-        const int np = min(kPS, chunk.y - p0);
-        for (int task = tid - n_cons; task < kPS * 3; task += kSqProducers) {
-            const int a = task / kPS, p = task - a * kPS;
-            const int nm = P.nmax[a];
-            const int npad = a == 2 ? P.nzpad : nm + 1;
-            double2 *e = tab + p * R + (a == 0 ? 0 : a == 1 ? P.offy : P.offz);
-            double s1 = 0.0, c1 = 0.0, er = 0.0, ei = 0.0;
-            if (p < np) {
-                double x = (double)pos[3 * (int64_t)(p0 + p) + a];
-                if (pos0) x -= (double)pos0[3 * (int64_t)(p0 + p) + a];
-                sincos(P.b[a] * x, &s1, &c1);
-                er = 1.0;
-            }
-            for (int n = 0; n < npad; ++n) {
-                e[n] = n <= nm ? make_double2(er, ei) : make_double2(0.0, 0.0);
-                const double nr = er * c1 - ei * s1;
-                ei = er * s1 + ei * c1;
-                er = nr;
+    if (producer) {
+        // task <-> (axis, particle): the lanes of a warp write the same entry of
+        // consecutive rows.  Four interleaved recurrences E(n) = E(n - 4) E(4) keep the
+        // dependent chains short (the FP64 pipe is shared with the consumers' DMMAs).
+        // A partial last sub-chunk gets zero rows, so the consumers never test.
+        int it = 0;
+        for (int u = blockIdx.y; u < P.n_units; u += gridDim.y) {
+            const int frame = u / P.n_chunks;
+            const int4 chunk = P.chunks[u - frame * P.n_chunks];
+            const int4 vm = P.vmap ? P.vmap[frame] : make_int4(frame, -1, 0, 0);
+            const float *pos = P.raw + (int64_t)vm.x * P.stride;
+            const float *pos0 = vm.y >= 0 ? P.raw + (int64_t)vm.y * P.stride : nullptr;
+            for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS, ++it) {
+                const int stage = it % kMmaStages, use = it / kMmaStages;
+                if (use > 0) mbar_wait(bar_empty + stage, (use - 1) & 1);
+                for (int task = tid - n_cons; task < 3 * kPS; task += kMmaProducers) {
+                    const int a = task / kPS, p = task - a * kPS;
+                    const int nm = P.nmax[a];
+                    const int npad = a == 2 ? P.nzpad : nm + 1;
+                    double er[4], ei[4], c4 = 0.0, s4 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) er[j] = ei[j] = 0.0;
+                    if (p0 + p < chunk.y) {
+                        double x = (double)pos[3 * (int64_t)(p0 + p) + a];
+                        // displacement in fp64 of the float32 coordinates: exact, as the
+                        // reference's float64 position buffer makes it
+                        if (pos0) x -= (double)pos0[3 * (int64_t)(p0 + p) + a];
+                        double s1, c1;
+                        sincos(P.b[a] * x, &s1, &c1);
+                        er[0] = 1.0;
+                        er[1] = c1; ei[1] = s1;
+                        er[2] = c1 * c1 - s1 * s1; ei[2] = 2.0 * (c1 * s1);
+                        er[3] = er[2] * c1 - ei[2] * s1; ei[3] = er[2] * s1 + ei[2] * c1;
+                        c4 = er[2] * er[2] - ei[2] * ei[2]; s4 = 2.0 * (er[2] * ei[2]);
+                    }
+                    double2 *e = sTab + ((size_t)stage * kPS + p) * R +
+                                 (a == 0 ? 0 : a == 1 ? P.offy : P.offz);
+                    for (int n = 0; n < npad; n += 4) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (n + j < npad)
+                                e[n + j] = n + j <= nm ? make_double2(er[j], ei[j])
+                                                       : make_double2(0.0, 0.0);
+                            const double nr = er[j] * c4 - ei[j] * s4;
+                            ei[j] = er[j] * s4 + ei[j] * c4;
+                            er[j] = nr;
+                        }
+                    }
+                }
+                mbar_arrive(bar_full + stage);
             }
         }
-    };
+        return;
+    }
 
-    const int item_index = blockIdx.x * (n_cons >> 5) + min(tid >> 5, (n_cons >> 5) - 1);
+    const int item_index = blockIdx.x * (n_cons >> 5) + (tid >> 5);
     const SqMmaItem *item = P.items + item_index;
-    const int ng = producer ? 0 : item->ng, nt = item->nt;
+    const int nt0 = item->nt[0], nt1 = item->nt[1];
     const int g = lane >> 2, k = lane & 3;
     int ox[kMmaG], oy[kMmaG];
 #pragma unroll
@@ -385,36 +456,25 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kSqProducers, 1)
             cre[i][t][0] = cre[i][t][1] = cim[i][t][0] = cim[i][t][1] = 0.0;
 
     const int *qi = P.qidx + (int64_t)item_index * (kMmaG * kMmaTZ * 64);
-    for (int ci = blockIdx.y; ci < P.n_chunks; ci += gridDim.y) {
-        chunk = P.chunks[ci];
-        if (producer) build(sTab, chunk.x);
-        __syncthreads();
-        int buf = 0;
-        for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS) {
-            const double2 *row = sTab + (size_t)buf * kPS * R + k * R;
-            if (producer) {
-                if (p0 + kPS < chunk.y) build(sTab + (size_t)(buf ^ 1) * kPS * R, p0 + kPS);
-            } else {
-#define MDH_MMA_CASE(G, T) \
-    case G * 8 + T: sq_mma_subchunk<G, T>(row, 4 * R, ox, oy, oz, cre, cim); break;
-                switch (ng * 8 + nt) {
-                    MDH_MMA_CASE(1, 1) MDH_MMA_CASE(1, 2) MDH_MMA_CASE(1, 3) MDH_MMA_CASE(1, 4)
-                    MDH_MMA_CASE(2, 1) MDH_MMA_CASE(2, 2) MDH_MMA_CASE(2, 3) MDH_MMA_CASE(2, 4)
-                    default: break;
-                }
-#undef MDH_MMA_CASE
-            }
-            __syncthreads();
-            buf ^= 1;
+    int it = 0;
+    for (int u = blockIdx.y; u < P.n_units; u += gridDim.y) {
+        const int frame = u / P.n_chunks;
+        const int4 chunk = P.chunks[u - frame * P.n_chunks];
+        for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS, ++it) {
+            const int stage = it % kMmaStages, use = it / kMmaStages;
+            mbar_wait(bar_full + stage, use & 1);
+            const double2 *row = sTab + ((size_t)stage * kPS + k) * R;
+            sq_mma_subchunk(row, 4 * R, nt0, nt1, ox, oy, oz, cre, cim);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + stage);
         }
-        if (producer) continue;
 
         double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
 #pragma unroll
         for (int i = 0; i < kMmaG; ++i)
 #pragma unroll
             for (int t = 0; t < kMmaTZ; ++t) {
-                if (i < ng && t < nt) {
+                if (t < (i == 0 ? nt0 : nt1)) {
                     // this lane holds C[g][2k], C[g][2k + 1]
                     const int2 q2 = *reinterpret_cast<const int2 *>(
                         qi + ((i * kMmaTZ + t) * 8 + g) * 8 + 2 * k);
@@ -553,7 +613,7 @@ static size_t mma_smem_bytes(const int (&nmax)[3])
 {
     int offy, offz, nzpad, R;
     mma_layout(nmax, &offy, &offz, &nzpad, &R);
-    return (size_t)2 * kPS * R * sizeof(double2);
+    return (size_t)kMmaStages * kPS * R * sizeof(double2);
 }
 constexpr size_t kMmaSmemLimit = 200 * 1024;
 
@@ -592,18 +652,22 @@ static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
             if (slot[gi * 8 + m] >= 0) t = std::max(t, (column_top(cols[slot[gi * 8 + m]]) + 7) / 8);
         return t;
     };
-    struct Proto { int g0, ng, t0, nt; };
+    // groups are sorted by decreasing tile count; kMmaG consecutive groups x one segment
+    // of <= kMmaTZ tiles make an item (the second group may need fewer tiles)
+    struct Proto { int g0, t0, nt[kMmaG]; int cost() const { return nt[0] + nt[1]; } };
+    static_assert(kMmaG == 2, "items are built for two groups");
     std::vector<Proto> protos;
     for (int g0 = 0; g0 < n_groups; g0 += kMmaG) {
-        const int ng = std::min(kMmaG, n_groups - g0);
-        int tiles = 0;
-        for (int i = 0; i < ng; ++i) tiles = std::max(tiles, group_tiles(g0 + i));
-        for (int t0 = 0; t0 < tiles; t0 += kMmaTZ)
-            protos.push_back(Proto{g0, ng, t0, std::min(kMmaTZ, tiles - t0)});
+        const int ta = group_tiles(g0), tb = g0 + 1 < n_groups ? group_tiles(g0 + 1) : 0;
+        for (int t0 = 0; t0 < std::max(ta, tb); t0 += kMmaTZ) {
+            Proto pr{g0, t0, {std::min(kMmaTZ, std::max(0, ta - t0)),
+                              std::min(kMmaTZ, std::max(0, tb - t0))}};
+            if (pr.nt[0] < pr.nt[1]) { std::swap(pr.nt[0], pr.nt[1]); pr.g0 = -g0 - 1; }
+            protos.push_back(pr);
+        }
     }
-    std::stable_sort(protos.begin(), protos.end(), [](const Proto &a, const Proto &b) {
-        return a.ng * a.nt > b.ng * b.nt;
-    });
+    std::stable_sort(protos.begin(), protos.end(),
+                     [](const Proto &a, const Proto &b) { return a.cost() > b.cost(); });
     const int n_items = (int)protos.size();
     const int n_blocks = (n_items + kMmaMaxWarps - 1) / kMmaMaxWarps;
     const int W = (n_items + n_blocks - 1) / n_blocks;
@@ -620,7 +684,7 @@ static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
         }
         place[(best >> 2) * W + (best & 3) + 4 * fill[best]] = p;
         fill[best]++;
-        load[best] += protos[p].ng * protos[p].nt;
+        load[best] += protos[p].cost();
     }
     out_items.assign((size_t)n_blocks * W, SqMmaItem{});
     out_qidx.assign((size_t)n_blocks * W * kMmaG * kMmaTZ * 64, -1);
@@ -628,17 +692,22 @@ static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
         if (place[s] < 0) continue;
         const Proto &pr = protos[place[s]];
         SqMmaItem &it = out_items[s];
-        it.ng = pr.ng; it.nt = pr.nt; it.t0 = pr.t0;
-        for (int i = 0; i < pr.ng; ++i)
+        it.t0 = pr.t0;
+        // g0 < 0: the two groups swapped so that nt[0] >= nt[1]
+        const int gbase = pr.g0 >= 0 ? pr.g0 : -pr.g0 - 1;
+        for (int i = 0; i < kMmaG; ++i) {
+            it.nt[i] = pr.nt[i];
+            const int gi = gbase + (pr.g0 >= 0 ? i : 1 - i);
             for (int m = 0; m < 8; ++m) {
-                int ci = slot[(pr.g0 + i) * 8 + m];
+                if (pr.nt[i] == 0) { it.nx[i][m] = it.ny[i][m] = 0; continue; }
+                int ci = slot[gi * 8 + m];
                 const bool dummy = ci < 0;
-                if (dummy) ci = slot[(pr.g0 + i) * 8 + (m ^ 1)];   // partner's entries
+                if (dummy) ci = slot[gi * 8 + (m ^ 1)];             // partner's entries
                 if (ci < 0) ci = 0;                                  // an all-dummy pair
                 it.nx[i][m] = (int16_t)cols[ci].nx;
                 it.ny[i][m] = (int16_t)cols[ci].ny;
                 if (dummy) continue;
-                for (int t = 0; t < pr.nt; ++t)
+                for (int t = 0; t < pr.nt[i]; ++t)
                     for (int z = 0; z < 8; ++z) {
                         const int nz = 8 * (pr.t0 + t) + z;
                         if (nz < (int)cols[ci].q.size())
@@ -646,6 +715,7 @@ static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
                                 cols[ci].q[nz];
                     }
             }
+        }
     }
     (void)nm;
 }
@@ -825,8 +895,12 @@ static int sq_build_chunks(mdh_ctx *c, int n_frames)
     SqState &S = c->sq;
     const int item_blocks = S.mode == MDH_SQ_LATTICE_DMMA ? S.mma_items / S.mma_warps
                             : S.lattice ? S.n_items / S.block : (S.n_q + 127) / 128;
-    // enough blocks for ~6 waves, chunks a multiple of the sub-chunk length
-    int64_t want = ((int64_t)c->sm_count * 2 * 6 + (int64_t)item_blocks * n_frames - 1) /
+    // enough blocks for ~6 waves (two blocks per SM), chunks a multiple of the sub-chunk
+    // length; the persistent DMMA kernel strides over ~40 small units per block instead
+    // (its table pipeline runs across unit boundaries, so small units cost nothing and
+    // the last, partial round is 1/40 of the launch)
+    const int64_t rounds = S.mode == MDH_SQ_LATTICE_DMMA ? 40 : 12;
+    int64_t want = ((int64_t)c->sm_count * rounds + (int64_t)item_blocks * n_frames - 1) /
                    ((int64_t)item_blocks * n_frames);
     int64_t len = (S.n_total + want - 1) / std::max<int64_t>(want, 1);
     len = std::max<int64_t>(256, std::min<int64_t>(len, 4096));
@@ -883,12 +957,17 @@ static int sq_compute_rho(mdh_ctx *c, const float *raw, int64_t stride, const in
         P.n_rho = S.n_rho; P.n_q = S.n_q;
         P.chain_out = S.n_chains > 0 ? S.ssf.as<double>() : nullptr;
         P.n_chunks = S.n_chunks;
+        MDH_REQUIRE((int64_t)S.n_chunks * n_vframes < (1ll << 31), MDH_EINVAL,
+                    "sq: too many (frame, chunk) work units in one call");
+        P.n_units = S.n_chunks * n_vframes;
         for (int k = 0; k < 3; ++k) { P.b[k] = S.b[k]; P.nmax[k] = S.nmax[k]; }
         const size_t smem = mma_smem_bytes(S.nmax);
         MDH_CUDA(cudaFuncSetAttribute(sq_lattice_mma_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(S.mma_items / S.mma_warps, std::min(S.n_chunks, 65535), n_vframes);
-        sq_lattice_mma_kernel<<<grid, S.mma_warps * 32 + kSqProducers, smem, c->stream>>>(P);
+        // persistent: one block per SM (and item block), striding over the work units
+        const int item_blocks = S.mma_items / S.mma_warps;
+        dim3 grid(item_blocks, std::min(P.n_units, std::max(1, c->sm_count / item_blocks)));
+        sq_lattice_mma_kernel<<<grid, S.mma_warps * 32 + kMmaProducers, smem, c->stream>>>(P);
         MDH_CUDA(cudaGetLastError());
         c->launches++;
         return MDH_OK;
