@@ -202,6 +202,11 @@ int mdh_sq_accumulate(mdh_ctx *ctx, const float *pos, int64_t frame_stride, int 
 int mdh_sq_fetch(mdh_ctx *ctx, double *ssf /* [n_pairs][n_q] host */);
 /* The MDH_SQ_* kernel the current configuration runs (after AUTO / fallback). */
 int mdh_sq_kernel(mdh_ctx *ctx, int *mode);
+/* Tiling of the MDH_SQ_LATTICE_DMMA kernel (zeros for the other kernels): stats[0] warp
+ * items, stats[1] (column group, nz tile) pairs -- 64 accumulator slots each, n_q of
+ * which are wavevectors --, stats[2] largest number of pairs on one warp scheduler,
+ * stats[3] warp schedulers (4 per block of items). */
+int mdh_sq_tiling(mdh_ctx *ctx, int64_t *stats /* [4] host */);
 int mdh_sq_reset(mdh_ctx *ctx);
 int mdh_sq_accum_device(mdh_ctx *ctx, void **dptr);
 /* rho(q) of the LAST frame of the last batch: [n_rho][n_q][2] (re, im), n_rho =

@@ -55,6 +55,7 @@ SIGNATURES = {
     "mdh_sq_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
     "mdh_sq_fetch": (_i32, [_p, _p]),
     "mdh_sq_kernel": (_i32, [_p, _p]),
+    "mdh_sq_tiling": (_i32, [_p, _p]),
     "mdh_sq_reset": (_i32, [_p]),
     "mdh_sq_accum_device": (_i32, [_p, ctypes.POINTER(_p)]),
     "mdh_sq_fetch_rho": (_i32, [_p, _p]),
@@ -248,6 +249,13 @@ class Context:
         m = ctypes.c_int(0)
         check(self._lib.mdh_sq_kernel(self._h, ctypes.byref(m)))
         return {v: k for k, v in SQ_MODES.items()}[m.value]
+
+    def sq_tiling(self) -> dict:
+        """Tiling statistics of the DMMA lattice kernel (zeros for the other kernels)."""
+        st = (ctypes.c_int64 * 4)()
+        check(self._lib.mdh_sq_tiling(self._h, st))
+        return {"items": st[0], "tiles": st[1], "max_scheduler_tiles": st[2],
+                "schedulers": st[3]}
 
     def sq_reset(self):
         check(self._lib.mdh_sq_reset(self._h))

@@ -380,6 +380,14 @@ int mdh_sq_kernel(mdh_ctx *c, int *mode)
     return MDH_OK;
 }
 
+int mdh_sq_tiling(mdh_ctx *c, int64_t *stats)
+{
+    MDH_REQUIRE(c && stats, MDH_EINVAL, "NULL argument");
+    MDH_REQUIRE(c->sq.configured, MDH_ESTATE, "sq: not configured");
+    for (int i = 0; i < 4; ++i) stats[i] = c->sq.mma ? c->sq.mma_stats[i] : 0;
+    return MDH_OK;
+}
+
 int mdh_sq_reset(mdh_ctx *c)
 {
     CTX_GUARD(c);

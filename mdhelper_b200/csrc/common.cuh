@@ -125,6 +125,7 @@ struct SqState {
     // DMMA lattice kernel (MDH_SQ_LATTICE_DMMA): one SqMmaItem per consumer warp
     bool mma = false;      // built and selected for this configuration
     int mma_items = 0, mma_warps = 0;   // items (padded to whole blocks), warps per block
+    int mma_stats[4] = {0, 0, 0, 0};    // items, (group, tile) pairs, max scheduler load, schedulers
     DevBuf mitems;         // SqMmaItem[mma_items]
     DevBuf mqidx;          // int[mma_items][groups][tiles][8][8]
     DevBuf d_pairs;        // int[n_pairs][2]

@@ -26,6 +26,8 @@
 
 #include <cuda_pipeline.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -257,14 +259,34 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
 // LDS.128), multiplies them (the A element), loads E_z(8 t + g) of particle k per tile
 // (one LDS.128 = the B elements re / im) and issues 4 DMMAs per (group, tile).
 //
-// Table row of one particle: double2 (re, im) entries  E_x(0..nmax_x) | E_y(0..nmax_y) |
-// E_z(0..8 * tiles - 1, zero past nmax_z), R entries with R = 2 (mod 8): the four
-// particles of a step start 8 banks apart, so the 16-byte loads of a quarter-warp (two
-// columns x four particles) are conflict-free whenever the two columns' nx (ny) are equal
-// or differ by an odd number -- the host pairs the columns that way.
-constexpr int kMmaG = 2;
+// Issue slots are the scarce resource: on sm_100 a DMMA.8x8x4 occupies its scheduler for
+// the 16 cycles it occupies the pipe, and every other instruction of any warp on that
+// scheduler adds its own issue cycles on top (tools/microbench3.cu: 2 IMADs per DMMA cost
+// 11 %, one LDS.128 + DADD per DMMA 27 %).  The consumer loop therefore carries nothing but
+// loads with immediate offsets, the complex product and the DMMAs: the 8 steps of a
+// sub-chunk are unrolled, the tile counts are template parameters, and the table layout
+// makes every address a per-lane base plus a compile-time constant.
+//
+// Table of one sub-chunk (32 particles): rows of kRowSlots = 36 double2 (re, im) entries --
+// 32 particles + 4 pad --, one row per table entry: E_x(0..nmax_x) | E_y(0..nmax_y) |
+// E_z(0..8 * tiles - 1, zero past nmax_z).  A step reads 4 consecutive particles of a row
+// (64 bytes); the row stride of 576 bytes puts neighbouring rows 16 banks apart, so the
+// 16-byte loads of a quarter-warp (two columns x four particles) are conflict-free whenever
+// the two columns' nx (ny) are equal or differ by an odd number -- the host pairs the
+// columns that way (E_z rows of a quarter-warp are always neighbours).
+#ifndef MDH_SQ_MMA_G
+#define MDH_SQ_MMA_G 2
+#endif
+constexpr int kMmaG = MDH_SQ_MMA_G;     // column groups per warp item (1 or 2)
 constexpr int kMmaTZ = 4;
-constexpr int kMmaMaxWarps = 14;   // consumer warps per block (+ 2 producer warps = 512 threads)
+constexpr int kRowSlots = kPS + 4;   // double2 entries per table row
+#ifndef MDH_SQ_MMA_WARPS
+#define MDH_SQ_MMA_WARPS 14
+#endif
+#ifndef MDH_SQ_MMA_PRODUCERS
+#define MDH_SQ_MMA_PRODUCERS 64
+#endif
+constexpr int kMmaMaxWarps = MDH_SQ_MMA_WARPS;   // consumer warps per block
 
 struct SqMmaItem {                 // one warp's work
     int16_t nx[kMmaG][8], ny[kMmaG][8];
@@ -285,50 +307,59 @@ struct MmaParams {
     int n_chunks, n_units;         // work units = (frame, chunk), frame-major
     double b[3];
     int nmax[3];
-    int offy, offz, nzpad, R;      // table layout in double2 entries
+    int offy, offz, nzpad, R;      // table rows: first E_y / E_z row, E_z rows, all rows
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+    // volatile: keeps the issue order chosen in the loops below
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
 // One sub-chunk (kPS particles, 4 per step) into the accumulators.  nt0 / nt1: nz tiles
-// of the item's first / second column group (warp-uniform; nt1 = 0: no second group).
-__device__ __forceinline__ void sq_mma_subchunk(const double2 *row, int R4, int nt0, int nt1,
-                                                const int (&ox)[kMmaG], const int (&oy)[kMmaG],
-                                                int oz, double (&cre)[kMmaG][kMmaTZ][2],
+// of the item's first / second column group (nt0 >= nt1; nt1 = 0: no second group) --
+// compile-time.  bx / by / bz: this lane's E_x / E_y / E_z entries of the sub-chunk's first
+// step (row * kRowSlots + k); step ks is 4 * ks entries further, tile t 8 rows further.
+template <int nt0, int nt1>
+__device__ __forceinline__ void sq_mma_subchunk(const double2 *tab, const int (&bx)[kMmaG],
+                                                const int (&by)[kMmaG], int bz,
+                                                double (&cre)[kMmaG][kMmaTZ][2],
                                                 double (&cim)[kMmaG][kMmaTZ][2])
 {
-#pragma unroll 2
-    for (int ks = 0; ks < kPS / 4; ++ks, row += R4) {
-        double ar[kMmaG], ai[kMmaG], nai[kMmaG];
+    constexpr int NG = nt1 > 0 ? 2 : 1;
 #pragma unroll
-        for (int i = 0; i < kMmaG; ++i) {
-            if (i == 0 || nt1 > 0) {
-                const double2 ex = row[ox[i]], ey = row[oy[i]];
-                ar[i] = ex.x * ey.x - ex.y * ey.y;
-                ai[i] = ex.x * ey.y + ex.y * ey.x;
-                nai[i] = __hiloint2double(__double2hiint(ai[i]) ^ (int)0x80000000,
-                                          __double2loint(ai[i]));
-            }
+    for (int ks = 0; ks < kPS / 4; ++ks) {
+        double ar[NG], ai[NG], nai[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            const double2 ex = tab[bx[i] + 4 * ks], ey = tab[by[i] + 4 * ks];
+            ar[i] = ex.x * ey.x - ex.y * ey.y;
+            ai[i] = ex.x * ey.y + ex.y * ey.x;
+            nai[i] = __hiloint2double(__double2hiint(ai[i]) ^ (int)0x80000000,
+                                      __double2loint(ai[i]));
         }
+        // all E_z tiles first, then two passes over the (group, tile) pairs so that the two
+        // DMMAs into the same accumulator are far apart
+        double2 ez[nt0];
 #pragma unroll
-        for (int t = 0; t < kMmaTZ; ++t) {
-            if (t < nt0) {
-                const double2 ez = row[oz + 8 * t];
+        for (int t = 0; t < nt0; ++t) ez[t] = tab[bz + 4 * ks + 8 * kRowSlots * t];
 #pragma unroll
-                for (int i = 0; i < kMmaG; ++i) {
-                    if (i == 0 || t < nt1) {
-                        dmma884(cre[i][t], ar[i], ez.x);
-                        dmma884(cim[i][t], ar[i], ez.y);
-                        dmma884(cre[i][t], nai[i], ez.y);
-                        dmma884(cim[i][t], ai[i], ez.x);
-                    }
+        for (int t = 0; t < nt0; ++t)
+#pragma unroll
+            for (int i = 0; i < NG; ++i)
+                if (i == 0 || t < nt1) {
+                    dmma884(cre[i][t], ar[i], ez[t].x);
+                    dmma884(cim[i][t], ar[i], ez[t].y);
                 }
-            }
-        }
+#pragma unroll
+        for (int t = 0; t < nt0; ++t)
+#pragma unroll
+            for (int i = 0; i < NG; ++i)
+                if (i == 0 || t < nt1) {
+                    dmma884(cre[i][t], nai[i], ez[t].y);
+                    dmma884(cim[i][t], ai[i], ez[t].x);
+                }
     }
 }
 
@@ -355,7 +386,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 }
 
 constexpr int kMmaStages = 3;      // table buffers in flight
-constexpr int kMmaProducers = 64;  // threads building the 3 * kPS (particle, axis) tables
+// producer threads; the 4 * kPS tasks of a sub-chunk are (particle, table part) with the
+// parts E_x, E_y and the two halves of E_z
+constexpr int kMmaProducers = MDH_SQ_MMA_PRODUCERS;
+constexpr int kMmaRounds = 4 * kPS / kMmaProducers;
+static_assert(kMmaRounds * kMmaProducers == 4 * kPS, "producer threads must divide the tasks");
 
 // Persistent block = n_cons consumer warps (one SqMmaItem each) followed by kMmaProducers
 // producer threads.  The block walks the work units (frame, particle chunk) blockIdx.y,
@@ -366,10 +401,9 @@ constexpr int kMmaProducers = 64;  // threads building the 3 * kPS (particle, ax
 __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
     sq_lattice_mma_kernel(const MmaParams P)
 {
-    static_assert(kMmaMaxWarps * 32 + kMmaProducers == 512, "128 registers per thread");
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t bar_full[kMmaStages], bar_empty[kMmaStages];
-    double2 *sTab = reinterpret_cast<double2 *>(smem);      // [kMmaStages][kPS][R]
+    double2 *sTab = reinterpret_cast<double2 *>(smem);      // [kMmaStages][R][kRowSlots]
     const int R = P.R;
     const int tid = threadIdx.x, lane = tid & 31;
     const int n_cons = (int)blockDim.x - kMmaProducers;
@@ -382,71 +416,113 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
     __syncthreads();
 
     if (producer) {
-        // task <-> (axis, particle): the lanes of a warp write the same entry of
-        // consecutive rows.  Four interleaved recurrences E(n) = E(n - 4) E(4) keep the
-        // dependent chains short (the FP64 pipe is shared with the consumers' DMMAs).
-        // A partial last sub-chunk gets zero rows, so the consumers never test.
-        int it = 0;
-        for (int u = blockIdx.y; u < P.n_units; u += gridDim.y) {
+        // task r of this thread: particle p of the sub-chunk, part 0 = E_x, 1 = E_y, 2 / 3 =
+        // first / second half of E_z (entries n0 .. n0 + cnt - 1 of the axis, zero past nmax);
+        // the lanes of a warp write the same entry of 32 consecutive particles (one row).
+        // Four interleaved recurrences E(n) = E(n - 4) E(4) keep the dependent chains short:
+        // every scalar FP64 instruction queues behind the consumers' DMMAs.  A partial last
+        // sub-chunk gets zero columns, so the consumers never test.
+        const int zhalf = (P.nzpad / 2 + 3) / 4 * 4;
+        // coordinate for task r of the sub-chunk at p0 of unit u; fetched one sub-chunk
+        // ahead so that the global-memory latency is off the critical path
+        auto fetch = [&](int r, int u, int p0) -> double {
+            const int task = tid - n_cons + r * kMmaProducers;
+            const int part = task / kPS, p = task - part * kPS, a = min(part, 2);
+            if (u >= P.n_units) return 0.0;
             const int frame = u / P.n_chunks;
-            const int4 chunk = P.chunks[u - frame * P.n_chunks];
+            const int4 ch = P.chunks[u - frame * P.n_chunks];
+            if (p0 + p >= ch.y) return nan("");
             const int4 vm = P.vmap ? P.vmap[frame] : make_int4(frame, -1, 0, 0);
-            const float *pos = P.raw + (int64_t)vm.x * P.stride;
-            const float *pos0 = vm.y >= 0 ? P.raw + (int64_t)vm.y * P.stride : nullptr;
-            for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS, ++it) {
-                const int stage = it % kMmaStages, use = it / kMmaStages;
-                if (use > 0) mbar_wait(bar_empty + stage, (use - 1) & 1);
-                for (int task = tid - n_cons; task < 3 * kPS; task += kMmaProducers) {
-                    const int a = task / kPS, p = task - a * kPS;
-                    const int nm = P.nmax[a];
-                    const int npad = a == 2 ? P.nzpad : nm + 1;
-                    double er[4], ei[4], c4 = 0.0, s4 = 0.0;
+            const int64_t idx = 3 * (int64_t)(p0 + p) + a;
+            double x = (double)P.raw[(int64_t)vm.x * P.stride + idx];
+            // displacement in fp64 of the float32 coordinates: exact, as the reference's
+            // float64 position buffer makes it
+            if (vm.y >= 0) x -= (double)P.raw[(int64_t)vm.y * P.stride + idx];
+            return x;
+        };
+        int it = 0;
+        int u = blockIdx.y;
+        int4 chunk = u < P.n_units ? P.chunks[u % P.n_chunks] : make_int4(0, 0, 0, 0);
+        int p0 = chunk.x;
+        double x[kMmaRounds], xn[kMmaRounds];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) er[j] = ei[j] = 0.0;
-                    if (p0 + p < chunk.y) {
-                        double x = (double)pos[3 * (int64_t)(p0 + p) + a];
-                        // displacement in fp64 of the float32 coordinates: exact, as the
-                        // reference's float64 position buffer makes it
-                        if (pos0) x -= (double)pos0[3 * (int64_t)(p0 + p) + a];
-                        double s1, c1;
-                        sincos(P.b[a] * x, &s1, &c1);
-                        er[0] = 1.0;
-                        er[1] = c1; ei[1] = s1;
-                        er[2] = c1 * c1 - s1 * s1; ei[2] = 2.0 * (c1 * s1);
-                        er[3] = er[2] * c1 - ei[2] * s1; ei[3] = er[2] * s1 + ei[2] * c1;
-                        c4 = er[2] * er[2] - ei[2] * ei[2]; s4 = 2.0 * (er[2] * ei[2]);
+        for (int r = 0; r < kMmaRounds; ++r) x[r] = fetch(r, u, p0);
+        while (u < P.n_units) {
+            // next (unit, sub-chunk)
+            int un = u, pn = p0 + kPS;
+            int4 chn = chunk;
+            if (pn >= chunk.y) {
+                un = u + gridDim.y;
+                if (un < P.n_units) chn = P.chunks[un % P.n_chunks];
+                pn = chn.x;
+            }
+#pragma unroll
+            for (int r = 0; r < kMmaRounds; ++r) xn[r] = fetch(r, un, pn);
+
+            const int stage = it % kMmaStages, use = it / kMmaStages;
+            if (use > 0) mbar_wait(bar_empty + stage, (use - 1) & 1);
+#pragma unroll
+            for (int r = 0; r < kMmaRounds; ++r) {
+                const int task = tid - n_cons + r * kMmaProducers;
+                const int part = task / kPS, p = task - part * kPS, a = min(part, 2);
+                const int nm = P.nmax[a];
+                const int n0 = part == 3 ? zhalf : 0;
+                const int cnt = part < 2 ? nm + 1 : part == 2 ? zhalf : P.nzpad - zhalf;
+                double er[4], ei[4], c4 = 0.0, s4 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) er[j] = ei[j] = 0.0;
+                if (x[r] == x[r]) {               // NaN: past the end of the chunk -> zero row
+                    const double th = P.b[a] * x[r];
+                    double s1, c1;
+                    sincos(th, &s1, &c1);
+                    const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * (c1 * s1);
+                    c4 = c2 * c2 - s2 * s2; s4 = 2.0 * (c2 * s2);
+                    er[0] = 1.0;
+                    // second half of E_z: start at E(n0) = E(4)^(n0 / 4) (n0 is a multiple of 4)
+                    for (int m = 0; m < n0; m += 4) {
+                        const double nr = er[0] * c4 - ei[0] * s4;
+                        ei[0] = er[0] * s4 + ei[0] * c4;
+                        er[0] = nr;
                     }
-                    double2 *e = sTab + ((size_t)stage * kPS + p) * R +
-                                 (a == 0 ? 0 : a == 1 ? P.offy : P.offz);
-                    for (int n = 0; n < npad; n += 4) {
+                    er[1] = er[0] * c1 - ei[0] * s1; ei[1] = er[0] * s1 + ei[0] * c1;
+                    er[2] = er[0] * c2 - ei[0] * s2; ei[2] = er[0] * s2 + ei[0] * c2;
+                    er[3] = er[1] * c2 - ei[1] * s2; ei[3] = er[1] * s2 + ei[1] * c2;
+                }
+                // entry n of this part: row (offset + n0 + n), slot p
+                double2 *e = sTab + ((size_t)stage * R +
+                                     (a == 0 ? 0 : a == 1 ? P.offy : P.offz) + n0) * kRowSlots + p;
+                for (int n = 0; n < cnt; n += 4) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (n + j < npad)
-                                e[n + j] = n + j <= nm ? make_double2(er[j], ei[j])
-                                                       : make_double2(0.0, 0.0);
-                            const double nr = er[j] * c4 - ei[j] * s4;
-                            ei[j] = er[j] * s4 + ei[j] * c4;
-                            er[j] = nr;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        if (n + j < cnt)
+                            e[(n + j) * kRowSlots] = n0 + n + j <= nm ? make_double2(er[j], ei[j])
+                                                                      : make_double2(0.0, 0.0);
+                        const double nr = er[j] * c4 - ei[j] * s4;
+                        ei[j] = er[j] * s4 + ei[j] * c4;
+                        er[j] = nr;
                     }
                 }
-                mbar_arrive(bar_full + stage);
             }
+            mbar_arrive(bar_full + stage);
+            ++it;
+            u = un; p0 = pn; chunk = chn;
+#pragma unroll
+            for (int r = 0; r < kMmaRounds; ++r) x[r] = xn[r];
         }
         return;
     }
 
     const int item_index = blockIdx.x * (n_cons >> 5) + (tid >> 5);
     const SqMmaItem *item = P.items + item_index;
-    const int nt0 = item->nt[0], nt1 = item->nt[1];
+    const int nt0 = item->nt[0], nt1 = kMmaG > 1 ? item->nt[kMmaG - 1] : 0;
     const int g = lane >> 2, k = lane & 3;
-    int ox[kMmaG], oy[kMmaG];
+    int bx[kMmaG], by[kMmaG];
 #pragma unroll
     for (int i = 0; i < kMmaG; ++i) {
-        ox[i] = item->nx[i][g];
-        oy[i] = P.offy + item->ny[i][g];
+        bx[i] = item->nx[i][g] * kRowSlots + k;
+        by[i] = (P.offy + item->ny[i][g]) * kRowSlots + k;
     }
-    const int oz = P.offz + 8 * item->t0 + g;
+    const int bz = (P.offz + 8 * item->t0 + g) * kRowSlots + k;
 
     double cre[kMmaG][kMmaTZ][2], cim[kMmaG][kMmaTZ][2];
 #pragma unroll
@@ -463,8 +539,19 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
         for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS, ++it) {
             const int stage = it % kMmaStages, use = it / kMmaStages;
             mbar_wait(bar_full + stage, use & 1);
-            const double2 *row = sTab + ((size_t)stage * kPS + k) * R;
-            sq_mma_subchunk(row, 4 * R, nt0, nt1, ox, oy, oz, cre, cim);
+            const double2 *tab = sTab + (size_t)stage * R * kRowSlots;
+#define MDH_MMA_CASE(A, B) \
+    case A * 8 + B: sq_mma_subchunk<A, B>(tab, bx, by, bz, cre, cim); break;
+            switch (nt0 * 8 + nt1) {
+                MDH_MMA_CASE(1, 0) MDH_MMA_CASE(2, 0) MDH_MMA_CASE(3, 0) MDH_MMA_CASE(4, 0)
+#if MDH_SQ_MMA_G > 1
+                MDH_MMA_CASE(1, 1) MDH_MMA_CASE(2, 1) MDH_MMA_CASE(2, 2) MDH_MMA_CASE(3, 1)
+                MDH_MMA_CASE(3, 2) MDH_MMA_CASE(3, 3) MDH_MMA_CASE(4, 1) MDH_MMA_CASE(4, 2)
+                MDH_MMA_CASE(4, 3) MDH_MMA_CASE(4, 4)
+#endif
+                default: break;
+            }
+#undef MDH_MMA_CASE
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + stage);
         }
@@ -605,28 +692,34 @@ static void mma_layout(const int (&nmax)[3], int *offy, int *offz, int *nzpad, i
     *offy = nmax[0] + 1;
     *offz = *offy + nmax[1] + 1;
     *nzpad = (nmax[2] + 8) / 8 * 8;
-    int r = *offz + *nzpad;
-    while (r % 8 != 2) ++r;
-    *R = r;
+    *R = *offz + *nzpad;                  // rows of a sub-chunk table
 }
 static size_t mma_smem_bytes(const int (&nmax)[3])
 {
     int offy, offz, nzpad, R;
     mma_layout(nmax, &offy, &offz, &nzpad, &R);
-    return (size_t)kMmaStages * kPS * R * sizeof(double2);
+    return (size_t)kMmaStages * R * kRowSlots * sizeof(double2);
 }
 constexpr size_t kMmaSmemLimit = 200 * 1024;
 
-// cols: sorted by decreasing column_top.  Columns are paired so that the two columns a
+// Columns are paired so that the two columns a
 // quarter-warp loads together have nx (and ny) equal or an odd distance apart (see the
 // bank analysis at the kernel), four pairs make a group of 8, kMmaG consecutive groups x
 // <= kMmaTZ nz tiles make a warp item; items are dealt to blocks and, inside a block, to
 // the four warp schedulers (warp w runs on scheduler w % 4) by decreasing cost so that
 // every scheduler's FP64 unit gets the same number of DMMAs between two barriers.
-static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
+static void mma_build_items(std::vector<Column> cols, const int (&nm)[3],
                             std::vector<SqMmaItem> &out_items, std::vector<int> &out_qidx,
-                            int &warps_per_block)
+                            int &warps_per_block, int (&stats)[4])
 {
+    // by decreasing number of nz tiles, then row by row: neighbours (nx, ny), (nx + 1, ny)
+    // are compatible, and a group of 8 never mixes tile counts except at one boundary
+    std::sort(cols.begin(), cols.end(), [](const Column &a, const Column &b) {
+        const int ta = (column_top(a) + 7) / 8, tb = (column_top(b) + 7) / 8;
+        if (ta != tb) return ta > tb;
+        if (a.ny != b.ny) return a.ny < b.ny;
+        return a.nx < b.nx;
+    });
     const int n = (int)cols.size();
     auto compatible = [&](int a, int b) {
         const int dx = std::abs(cols[a].nx - cols[b].nx), dy = std::abs(cols[a].ny - cols[b].ny);
@@ -654,17 +747,42 @@ static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
     };
     // groups are sorted by decreasing tile count; kMmaG consecutive groups x one segment
     // of <= kMmaTZ tiles make an item (the second group may need fewer tiles)
-    struct Proto { int g0, t0, nt[kMmaG]; int cost() const { return nt[0] + nt[1]; } };
-    static_assert(kMmaG == 2, "items are built for two groups");
+    // pieces = (group, segment of <= kMmaTZ tiles); an item pairs two pieces of the same
+    // segment, the largest with the smallest, so that all warps carry about the same number
+    // of tiles: the block advances at the pace of its slowest warp (a warp releases a table
+    // stage only when it is done with it), and one warp alone cannot keep the DMMA pipe busy
+    // cost() in 1/8 of the scheduler time of one (group, tile) pair per sub-chunk (32 DMMAs):
+    // the complex products of a group cost about 3/8 of that, a producer warp about 30/8
+    // (scalar FP64 instructions share the DMMA pipe at ~5 cycles each)
+    struct Proto {
+        int ga, gb, t0, nt[2];
+        int tiles() const { return nt[0] + nt[1]; }
+        int cost() const { return 8 * tiles() + 3 * ((nt[0] > 0) + (nt[1] > 0)); }
+    };
+    constexpr int kProducerCost = 30;
+    static_assert(kMmaG == 1 || kMmaG == 2, "items are built for one or two groups");
     std::vector<Proto> protos;
-    for (int g0 = 0; g0 < n_groups; g0 += kMmaG) {
-        const int ta = group_tiles(g0), tb = g0 + 1 < n_groups ? group_tiles(g0 + 1) : 0;
-        for (int t0 = 0; t0 < std::max(ta, tb); t0 += kMmaTZ) {
-            Proto pr{g0, t0, {std::min(kMmaTZ, std::max(0, ta - t0)),
-                              std::min(kMmaTZ, std::max(0, tb - t0))}};
-            if (pr.nt[0] < pr.nt[1]) { std::swap(pr.nt[0], pr.nt[1]); pr.g0 = -g0 - 1; }
-            protos.push_back(pr);
+    int max_tiles = 0;
+    for (int gi = 0; gi < n_groups; ++gi) max_tiles = std::max(max_tiles, group_tiles(gi));
+    for (int t0 = 0; t0 < max_tiles; t0 += kMmaTZ) {
+        std::vector<std::pair<int, int>> pieces;         // (tiles, group)
+        for (int gi = 0; gi < n_groups; ++gi) {
+            const int nt = std::min(kMmaTZ, group_tiles(gi) - t0);
+            if (nt > 0) pieces.push_back({nt, gi});
         }
+        std::sort(pieces.begin(), pieces.end(), [](const std::pair<int, int> &x,
+                                                   const std::pair<int, int> &y) {
+            return x.first != y.first ? x.first > y.first : x.second < y.second;
+        });
+        size_t lo = 0, hi = pieces.size();
+        if (kMmaG == 1 || (hi - lo) % 2) {               // odd: the largest piece stays alone
+            const size_t solo = kMmaG == 1 ? hi : 1;
+            for (; lo < solo; ++lo)
+                protos.push_back(Proto{pieces[lo].second, -1, t0, {pieces[lo].first, 0}});
+        }
+        for (; lo + 1 < hi; ++lo, --hi)
+            protos.push_back(Proto{pieces[lo].second, pieces[hi - 1].second, t0,
+                                   {pieces[lo].first, pieces[hi - 1].first}});
     }
     std::stable_sort(protos.begin(), protos.end(),
                      [](const Proto &a, const Proto &b) { return a.cost() > b.cost(); });
@@ -675,6 +793,8 @@ static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
     // bins = (block, scheduler); capacity = warps of the block on that scheduler
     std::vector<int> load(n_blocks * 4, 0), fill(n_blocks * 4, 0);
     std::vector<int> place(n_blocks * W, -1);         // slot -> proto
+    for (int b = 0; b < n_blocks; ++b)                // the producer warps follow the consumers
+        for (int j = 0; j < kMmaProducers / 32; ++j) load[b * 4 + ((W + j) & 3)] += kProducerCost;
     for (int p = 0; p < n_items; ++p) {
         int best = -1;
         for (int bin = 0; bin < n_blocks * 4; ++bin) {
@@ -686,6 +806,36 @@ static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
         fill[best]++;
         load[best] += protos[p].cost();
     }
+    // local search: swap items between schedulers of a block while that lowers the larger
+    // of the two loads (LPT with unequal capacities leaves easy gains)
+    for (bool improved = true; improved;) {
+        improved = false;
+        for (int b = 0; b < n_blocks && !improved; ++b)
+            for (int s1 = 0; s1 < W && !improved; ++s1)
+                for (int s2 = 0; s2 < W && !improved; ++s2) {
+                    const int b1 = b * 4 + (s1 & 3), b2 = b * 4 + (s2 & 3);
+                    if (b1 == b2 || load[b1] <= load[b2]) continue;
+                    const int p1 = place[b * W + s1], p2 = place[b * W + s2];
+                    const int c1 = p1 < 0 ? 0 : protos[p1].cost(), c2 = p2 < 0 ? 0 : protos[p2].cost();
+                    if (c1 > c2 && std::max(load[b1] - c1 + c2, load[b2] - c2 + c1) < load[b1]) {
+                        std::swap(place[b * W + s1], place[b * W + s2]);
+                        load[b1] += c2 - c1; load[b2] += c1 - c2;
+                        improved = true;
+                    }
+                }
+    }
+    // {items, (group, tile) pairs = 64 accumulator slots each, largest scheduler load,
+    //  schedulers}
+    stats[0] = n_items; stats[1] = 0; stats[2] = 0; stats[3] = n_blocks * 4;
+    for (const Proto &pr : protos) stats[1] += pr.tiles();
+    for (int l : load) stats[2] = std::max(stats[2], (l + 7) / 8);
+    if (getenv("MDH_SQ_DEBUG")) {
+        fprintf(stderr, "mdh sq dmma: %d columns, %d groups, %d items in %d block(s) of %d warps, "
+                "%d tiles; scheduler loads (1/8 tile, producers included):", n, n_groups, n_items,
+                n_blocks, W, stats[1]);
+        for (int l : load) fprintf(stderr, " %d", l);
+        fprintf(stderr, "\n");
+    }
     out_items.assign((size_t)n_blocks * W, SqMmaItem{});
     out_qidx.assign((size_t)n_blocks * W * kMmaG * kMmaTZ * 64, -1);
     for (int s = 0; s < n_blocks * W; ++s) {
@@ -693,11 +843,9 @@ static void mma_build_items(const std::vector<Column> &cols, const int (&nm)[3],
         const Proto &pr = protos[place[s]];
         SqMmaItem &it = out_items[s];
         it.t0 = pr.t0;
-        // g0 < 0: the two groups swapped so that nt[0] >= nt[1]
-        const int gbase = pr.g0 >= 0 ? pr.g0 : -pr.g0 - 1;
         for (int i = 0; i < kMmaG; ++i) {
             it.nt[i] = pr.nt[i];
-            const int gi = gbase + (pr.g0 >= 0 ? i : 1 - i);
+            const int gi = i == 0 ? pr.ga : pr.gb;
             for (int m = 0; m < 8; ++m) {
                 if (pr.nt[i] == 0) { it.nx[i][m] = it.ny[i][m] = 0; continue; }
                 int ci = slot[gi * 8 + m];
@@ -844,7 +992,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
 
             // ---- DMMA work items (sq_lattice_mma_kernel) ----
             if (mode == MDH_SQ_AUTO || mode == MDH_SQ_LATTICE_DMMA)
-                mma_build_items(cols, nm, mitems, mqidx, mma_warps);
+                mma_build_items(cols, nm, mitems, mqidx, mma_warps, S.mma_stats);
         }
     }
     MDH_REQUIRE(lattice || !want_lattice, MDH_EINVAL,
