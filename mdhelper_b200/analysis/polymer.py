@@ -69,7 +69,8 @@ class SingleChainStructureFactor(GpuAnalysisBase):
     parallel, verbose
         As in the reference (``parallel`` is accepted and ignored).
     kernel : `str`, keyword-only, optional
-        GPU kernel strategy (``"lattice_dmma"`` (default) or ``"lattice_fp64"``).
+        GPU kernel strategy: ``"lattice_dmma"`` (FP64 matrix unit; what the default
+        ``"auto"`` picks for all but tiny grids) or ``"lattice_fp64"`` (scalar DFMA).
 
     Attributes
     ----------
@@ -145,7 +146,7 @@ class SingleChainStructureFactor(GpuAnalysisBase):
         n = self._n_chains * self._n_monomers
         ctx.sq_configure(n, [0, n], self._wavevectors, [(-1, -1)],
                          lattice_n=self._lattice_n, lattice_b=self._lattice_b,
-                         mode=self._kernel or "lattice_dmma")
+                         mode=self._kernel or "auto")
         ctx.sq_configure_chains(self._n_chains, self._n_monomers)
         g = self._group
         if self._grouping == "atoms" and not self._unwrap:

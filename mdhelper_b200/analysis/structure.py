@@ -652,7 +652,7 @@ class StructureFactor(GpuAnalysisBase):
         elif self._lattice_n is None:
             mode = "general_fp64"
         else:
-            mode = "lattice_fp32" if self._precision == "fp32" else "lattice_dmma"
+            mode = "lattice_fp32" if self._precision == "fp32" else "auto"
         ctx.sq_configure(int(self._N), offsets, self._wavevectors, pairs,
                          lattice_n=self._lattice_n, lattice_b=self._lattice_b,
                          mode=mode)
@@ -842,7 +842,7 @@ class IntermediateScatteringFunction(StructureFactor):
         elif self._lattice_n is None:
             mode = "general_fp64"
         else:
-            mode = "lattice_fp32" if self._precision == "fp32" else "lattice_dmma"
+            mode = "lattice_fp32" if self._precision == "fp32" else "auto"
         ctx.sq_configure(
             int(self._N), offsets, self._wavevectors[cols], pairs,
             lattice_n=None if self._lattice_n is None else self._lattice_n[cols],

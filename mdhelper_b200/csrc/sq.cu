@@ -385,7 +385,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-constexpr int kMmaStages = 3;      // table buffers in flight
+#ifndef MDH_SQ_MMA_STAGES
+#define MDH_SQ_MMA_STAGES 2
+#endif
+constexpr int kMmaStages = MDH_SQ_MMA_STAGES;      // table buffers in flight
 // producer threads; the 4 * kPS tasks of a sub-chunk are (particle, table part) with the
 // parts E_x, E_y and the two halves of E_z
 constexpr int kMmaProducers = MDH_SQ_MMA_PRODUCERS;
@@ -701,6 +704,7 @@ static size_t mma_smem_bytes(const int (&nmax)[3])
     return (size_t)kMmaStages * R * kRowSlots * sizeof(double2);
 }
 constexpr size_t kMmaSmemLimit = 200 * 1024;
+constexpr int kMmaAutoTiles = 28;
 
 // Columns are paired so that the two columns a
 // quarter-warp loads together have nx (and ny) equal or an odd distance apart (see the
@@ -759,7 +763,7 @@ static void mma_build_items(std::vector<Column> cols, const int (&nm)[3],
         int tiles() const { return nt[0] + nt[1]; }
         int cost() const { return 8 * tiles() + 3 * ((nt[0] > 0) + (nt[1] > 0)); }
     };
-    constexpr int kProducerCost = 30;
+    constexpr int kProducerCost = 60 * 32 / kMmaProducers;   // per producer warp
     static_assert(kMmaG == 1 || kMmaG == 2, "items are built for one or two groups");
     std::vector<Proto> protos;
     int max_tiles = 0;
@@ -999,7 +1003,10 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                 "sq: wavevectors are not usable by the lattice kernels "
                 "(need 0 <= n <= 1023 and no duplicates)");
     S.lattice = lattice;
-    S.mma = lattice && !mitems.empty() && mma_smem_bytes(S.nmax) <= kMmaSmemLimit;
+    // AUTO: the DMMA kernel needs enough (group, tile) pairs to load all four schedulers
+    // of an SM (measured: 9 pairs lose to the scalar kernel, 49 win by 1.5x)
+    S.mma = lattice && !mitems.empty() && mma_smem_bytes(S.nmax) <= kMmaSmemLimit &&
+            (mode == MDH_SQ_LATTICE_DMMA || S.mma_stats[1] >= kMmaAutoTiles);
     S.mode = !lattice ? MDH_SQ_GENERAL_FP64
              : mode == MDH_SQ_LATTICE_FP32 ? MDH_SQ_LATTICE_FP32
              : S.mma ? MDH_SQ_LATTICE_DMMA : MDH_SQ_LATTICE_FP64;

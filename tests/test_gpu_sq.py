@@ -20,7 +20,7 @@ def _groups(u, g):
     return u.select(slice(0, n)), u.select(slice(n, u.atoms.n_atoms))
 
 
-@pytest.mark.parametrize("kernel", [None, "lattice_fp64", "general_fp64"])
+@pytest.mark.parametrize("kernel", [None, "lattice_dmma", "lattice_fp64", "general_fp64"])
 @pytest.mark.parametrize("mode", [None, "pair", "partial"])
 def test_class_matches_golden(golden, mode, kernel):
     g = golden("sq_small")
@@ -35,8 +35,9 @@ def test_class_matches_golden(golden, mode, kernel):
         np.testing.assert_allclose(s.results.wavenumbers,
                                    g[f"wavenumbers_{mode}_{form}"], rtol=1e-13)
     assert len(s.results.pairs) == (3 if mode == "partial" else 1)
-    # the default for lattice wavevectors is the FP64 matrix-unit kernel
-    assert s._ctx.sq_kernel() == (kernel or "lattice_dmma")
+    # default: a lattice kernel (the matrix-unit one for all but tiny wavevector sets)
+    assert s._ctx.sq_kernel() == kernel or (kernel is None and s._ctx.sq_kernel() in
+                                            ("lattice_dmma", "lattice_fp64"))
 
 
 def test_raw_grid_order_and_rho(golden):
@@ -73,7 +74,7 @@ def test_off_lattice_wavevectors(golden):
 def test_noncubic(golden):
     g = golden("sq_noncubic")
     u = universe_from(g)
-    for kernel in (None, "lattice_fp64", "general_fp64"):
+    for kernel in (None, "lattice_dmma", "lattice_fp64", "general_fp64"):
         s = _S().StructureFactor([u.atoms], n_points=int(g["n_points"]),
                                  q_max=float(g["q_max"]), kernel=kernel,
                                  verbose=False).run()
@@ -139,7 +140,7 @@ def test_mma_tiling_odd_shapes():
     for kw in cases:
         kw = {k: v for k, v in kw.items() if v is not None}
         a = _S().StructureFactor([u.atoms], sort=False, unique=False, verbose=False,
-                                 **kw).run()
+                                 kernel="lattice_dmma", **kw).run()
         assert a._ctx.sq_kernel() == "lattice_dmma"
         b = _S().StructureFactor([u.atoms], sort=False, unique=False, verbose=False,
                                  kernel="general_fp64", **kw).run()
@@ -150,7 +151,8 @@ def test_mma_tiling_odd_shapes():
     wv = n * b3
     g1, g2 = u.select(slice(0, 300)), u.select(slice(300, 777))
     a = _S().StructureFactor([g1, g2], mode="partial", wavevectors=wv, sort=False,
-                             unique=False, verbose=False).run()
+                             unique=False, kernel="lattice_dmma", verbose=False).run()
+    assert a._ctx.sq_kernel() == "lattice_dmma"
     b = _S().StructureFactor([g1, g2], mode="partial", wavevectors=wv, sort=False,
                              unique=False, kernel="general_fp64", verbose=False).run()
     np.testing.assert_allclose(a.results.ssf, b.results.ssf, rtol=1e-9, atol=1e-10)
@@ -174,7 +176,7 @@ def test_frame_additivity_and_selection():
 
 # ---- intermediate scattering function ------------------
 
-@pytest.mark.parametrize("kernel", [None, "lattice_fp64", "general_fp64"])
+@pytest.mark.parametrize("kernel", [None, "lattice_dmma", "lattice_fp64", "general_fp64"])
 @pytest.mark.parametrize("mode", [None, "pair", "partial"])
 def test_isf_matches_golden(golden, mode, kernel):
     """GPU IntermediateScatteringFunction vs the fixtures of the reference's real class:
@@ -278,10 +280,11 @@ def test_scsf_matches_golden(golden):
     u = universe_from(g)
     kw = dict(n_points=int(g["n_points"]), n_chains=int(g["n_chains"]),
               n_monomers=int(g["n_monomers"]), verbose=False)
-    for unwrap, kernel in ((False, None), (True, None), (False, "lattice_fp64")):
+    for unwrap, kernel in ((False, None), (True, "lattice_dmma"), (False, "lattice_dmma"),
+                           (False, "lattice_fp64")):
         r = SingleChainStructureFactor(u.atoms, unwrap=unwrap, batch_frames=4,
                                        kernel=kernel, **kw).run()
-        assert r._ctx.sq_kernel() == (kernel or "lattice_dmma")
+        assert kernel is None or r._ctx.sq_kernel() == kernel
         np.testing.assert_allclose(r.results.scsf, g[f"scsf_unwrap{int(unwrap)}"],
                                    rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(r.results.wavenumbers, g["wavenumbers"], rtol=1e-13)
@@ -307,10 +310,12 @@ def test_scsf_many_chains_against_oracle():
     dims = np.array([21.0, 24.0, 27.0, 90, 90, 90], np.float32)
     pos = (rng.random((2, 300 * 37, 3)) * dims[:3]).astype(np.float32)
     u = SyntheticUniverse(pos, dims)
-    r = SingleChainStructureFactor(u.atoms, n_points=7, n_chains=300, n_monomers=37,
-                                   verbose=False).run()
     o = rp.scsf_run(u, u.atoms, n_points=7, n_chains=300, n_monomers=37)
-    np.testing.assert_allclose(r.results.scsf, o["scsf"], rtol=1e-9, atol=1e-10)
+    for kernel in ("lattice_dmma", "lattice_fp64"):
+        r = SingleChainStructureFactor(u.atoms, n_points=7, n_chains=300, n_monomers=37,
+                                       kernel=kernel, verbose=False).run()
+        assert r._ctx.sq_kernel() == kernel
+        np.testing.assert_allclose(r.results.scsf, o["scsf"], rtol=1e-9, atol=1e-10)
 
 
 def test_combined_pass_equals_separate_runs():

@@ -6,6 +6,7 @@ object per configuration: end-to-end rates (pinned host -> results) and the devi
 of the hot kernels (CUDA events, mdh_kernel_time).  Used for profiles/configs_rNN.json.
 """
 import json
+import os
 import pathlib
 import sys
 import time
@@ -119,14 +120,15 @@ def isf():
     u = synthetic.lj_fluid(50_000, 96, seed=20260011)
     L = float(u.dimensions[0])
     kw = dict(n_points=32, q_max=2 * np.pi * 16 / L, n_lags=32, verbose=False,
-              batch_frames=32)
+              batch_frames=32, kernel=os.environ.get("MDH_BENCH_SQ_KERNEL"))
     for inc in (False, True):
         f = IntermediateScatteringFunction([u.atoms], incoherent=inc, **kw)
         dt, _, sms = timed(f)
         nq = len(f._wavenumbers)
         sums = 96 + (sum(min(32, t + 1) for t in range(96)) if inc else 0)
         print(json.dumps({"config": f"isf: 50k particles, 96 frames, 32 lags, "
-                                    f"incoherent={inc}", "n_q": nq, "direct_sums": sums,
+                                    f"incoherent={inc}", "kernel": f._ctx.sq_kernel(),
+                          "n_q": nq, "direct_sums": sums,
                           "e2e_s": dt, "kernel_ms": sms,
                           "sums_per_s_kernel": sums / (sms * 1e-3),
                           "fp64_pipe_frac": 50_000 * nq * sums * 4 / (sms * 1e-3)
@@ -139,11 +141,12 @@ def scsf():
     from mdhelper_b200.analysis.polymer import SingleChainStructureFactor
     u = synthetic.polymer_melt(10_000, 100, 2, seed=20260005)
     s = SingleChainStructureFactor(u.atoms, n_points=32, n_chains=10_000, n_monomers=100,
-                                   verbose=False, batch_frames=2)
+                                   verbose=False, batch_frames=2,
+                                   kernel=os.environ.get("MDH_BENCH_SQ_KERNEL"))
     dt, _, sms = timed(s)
     nq = len(s._wavenumbers)
     print(json.dumps({"config": "scsf: 10,000 chains x 100 beads, 32^3 wavevectors, 2 frames",
-                      "n_q": nq, "e2e_s": dt, "e2e_frames_per_s": s.n_frames / dt,
+                      "kernel": s._ctx.sq_kernel(), "n_q": nq, "e2e_s": dt, "e2e_frames_per_s": s.n_frames / dt,
                       "kernel_ms": sms, "terms_per_s_kernel": 1e6 * nq * s.n_frames
                       / (sms * 1e-3),
                       "fp64_pipe_frac": 1e6 * nq * s.n_frames * 4 / (sms * 1e-3)
