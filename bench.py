@@ -589,6 +589,7 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
     ctx.sq_configure(N, [0, N], sf._wavevectors, [(-1, -1)], lattice_n=sf._lattice_n,
                      lattice_b=sf._lattice_b, mode=args.sq_kernel)
     assert ctx.sq_kernel() == args.sq_kernel, ctx.sq_kernel()
+    tiling = ctx.sq_tiling()
     base = dev.data_ptr()
 
     def step(s):
@@ -667,9 +668,9 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
                      "bound": "fp64_pipe",
                      "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Ginstr/s",
                      "frac": achieved / peak,
-                     "traffic": profiled_traffic("sq", 16, fps),
+                     "traffic": profiled_traffic("sq", 128, fps),
                      "traffic_note": "dram__bytes_read+write of profiles/r01_sq_metrics.csv "
-                                     "(a 16-frame launch) scaled to this launch's frames; "
+                                     "(a 128-frame launch) scaled to this launch's frames; "
                                      "bytes",
                      "nominal_vs_reachable":
                          ("DMMA.8x8x4 sustains the nominal 63.6 FMA/clk/SM "
@@ -683,6 +684,10 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
                                  "multiply-accumulate)" + (", issued as DMMA m8n8k4 "
                                  "(256 FMA per warp instruction)" if dmma else ""),
                      "units_per_launch": terms, "launch_ms": kern_ms,
+                     "tiling": (dict(tiling, executed_over_algorithmic=tiling["tiles"] * 64 / n_q,
+                                     note="(column group x nz tile) pairs of 64 accumulator "
+                                          "slots; the DMMAs of padding slots are executed but "
+                                          "not counted in `achieved`") if dmma else None),
                      "peak_source": f"{peaks['pipe_source']}; {peaks['fp64_per_clk_sm']:.1f} "
                                     f"instr/clk/SM x {n_sm} SMs x 1965 MHz (max clock)",
                      "sfu_equivalent_frac": (terms * 2 / (kern_ms * 1e-3))
