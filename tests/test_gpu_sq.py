@@ -174,6 +174,26 @@ def test_frame_additivity_and_selection():
     assert s.results.ssf.shape[0] == 1 and np.isfinite(s.results.ssf).all()
 
 
+def test_mma_pipeline_long_run():
+    """DMMA kernel: thousands of work units per launch (every persistent block walks many
+    units, the table ring and its mbarrier phases wrap hundreds of times), a particle count
+    that leaves a partial last sub-chunk in every chunk, two groups of unequal size -- the
+    scalar lattice kernel must agree, and so must a second run of the same object."""
+    from mdhelper_b200 import synthetic
+    u = synthetic.lj_fluid(1999, 130, seed=41)
+    L = float(u.dimensions[0])
+    g1, g2 = u.select(slice(0, 777)), u.select(slice(777, 1999))
+    kw = dict(mode="partial", n_points=12, q_max=2 * np.pi * 9.5 / L, sort=False,
+              unique=False, verbose=False, batch_frames=130)
+    a = _S().StructureFactor([g1, g2], kernel="lattice_dmma", **kw).run()
+    assert a._ctx.sq_kernel() == "lattice_dmma"
+    first = a.results.ssf.copy()
+    b = _S().StructureFactor([g1, g2], kernel="lattice_fp64", **kw).run()
+    np.testing.assert_allclose(first, b.results.ssf, rtol=1e-10, atol=1e-9)
+    a.run()
+    np.testing.assert_allclose(a.results.ssf, first, rtol=1e-12, atol=1e-10)
+
+
 # ---- intermediate scattering function (SURVEY.md section 8(f) rank 1) ------------------
 
 @pytest.mark.parametrize("kernel", [None, "lattice_dmma", "lattice_fp64", "general_fp64"])
