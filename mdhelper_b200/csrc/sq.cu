@@ -279,6 +279,16 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
 #endif
 constexpr int kMmaG = MDH_SQ_MMA_G;     // column groups per warp item (1 or 2)
 constexpr int kMmaTZ = 4;
+// 3-multiplication complex product (Gauss / "3M"): with P1 = sum A_r B_r, P2 = sum A_i B_i,
+// P3 = sum (A_r + A_i)(B_r + B_i):  Re = P1 - P2, Im = P3 - P1 - P2 -- three DMMAs per
+// (group, tile) and step instead of four, for one DADD per group and step and a third
+// table value B_r + B_i (written by the producers).  Every accumulator is touched once per
+// step, so no DMMA depends on a recent one.
+#ifndef MDH_SQ_MMA_3M
+#define MDH_SQ_MMA_3M 1
+#endif
+constexpr bool kMma3M = MDH_SQ_MMA_3M != 0;
+constexpr int kMmaAcc = kMma3M ? 3 : 2;   // accumulator pairs per (group, tile)
 constexpr int kRowSlots = kPS + 4;   // double2 entries per table row
 #ifndef MDH_SQ_MMA_WARPS
 #define MDH_SQ_MMA_WARPS 14
@@ -323,43 +333,58 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 // step (row * kRowSlots + k); step ks is 4 * ks entries further, tile t 8 rows further.
 template <int nt0, int nt1>
 __device__ __forceinline__ void sq_mma_subchunk(const double2 *tab, const int (&bx)[kMmaG],
-                                                const int (&by)[kMmaG], int bz,
-                                                double (&cre)[kMmaG][kMmaTZ][2],
-                                                double (&cim)[kMmaG][kMmaTZ][2])
+                                                const int (&by)[kMmaG], int bz, int bs,
+                                                double (&acc)[kMmaAcc][kMmaG][kMmaTZ][2])
 {
     constexpr int NG = nt1 > 0 ? 2 : 1;
 #pragma unroll
     for (int ks = 0; ks < kPS / 4; ++ks) {
-        double ar[NG], ai[NG], nai[NG];
+        double ar[NG], ai[NG], ax[NG];   // ax: A_r + A_i (3M) or -A_i
 #pragma unroll
         for (int i = 0; i < NG; ++i) {
             const double2 ex = tab[bx[i] + 4 * ks], ey = tab[by[i] + 4 * ks];
             ar[i] = ex.x * ey.x - ex.y * ey.y;
             ai[i] = ex.x * ey.y + ex.y * ey.x;
-            nai[i] = __hiloint2double(__double2hiint(ai[i]) ^ (int)0x80000000,
-                                      __double2loint(ai[i]));
+            ax[i] = kMma3M ? ar[i] + ai[i]
+                           : __hiloint2double(__double2hiint(ai[i]) ^ (int)0x80000000,
+                                              __double2loint(ai[i]));
         }
-        // all E_z tiles first, then two passes over the (group, tile) pairs so that the two
-        // DMMAs into the same accumulator are far apart
-        double2 ez[nt0];
+        if (kMma3M) {
 #pragma unroll
-        for (int t = 0; t < nt0; ++t) ez[t] = tab[bz + 4 * ks + 8 * kRowSlots * t];
+            for (int t = 0; t < nt0; ++t) {
+                const double2 ez = tab[bz + 4 * ks + 8 * kRowSlots * t];
+                const double es = tab[bs + 4 * ks + 8 * kRowSlots * t].x;
 #pragma unroll
-        for (int t = 0; t < nt0; ++t)
+                for (int i = 0; i < NG; ++i)
+                    if (i == 0 || t < nt1) {
+                        dmma884(acc[0][i][t], ar[i], ez.x);
+                        dmma884(acc[1][i][t], ai[i], ez.y);
+                        dmma884(acc[kMmaAcc - 1][i][t], ax[i], es);
+                    }
+            }
+        } else {
+            // all E_z tiles first, then two passes over the (group, tile) pairs so that the
+            // two DMMAs into the same accumulator are far apart
+            double2 ez[nt0];
 #pragma unroll
-            for (int i = 0; i < NG; ++i)
-                if (i == 0 || t < nt1) {
-                    dmma884(cre[i][t], ar[i], ez[t].x);
-                    dmma884(cim[i][t], ar[i], ez[t].y);
-                }
+            for (int t = 0; t < nt0; ++t) ez[t] = tab[bz + 4 * ks + 8 * kRowSlots * t];
 #pragma unroll
-        for (int t = 0; t < nt0; ++t)
+            for (int t = 0; t < nt0; ++t)
 #pragma unroll
-            for (int i = 0; i < NG; ++i)
-                if (i == 0 || t < nt1) {
-                    dmma884(cre[i][t], nai[i], ez[t].y);
-                    dmma884(cim[i][t], ai[i], ez[t].x);
-                }
+                for (int i = 0; i < NG; ++i)
+                    if (i == 0 || t < nt1) {
+                        dmma884(acc[0][i][t], ar[i], ez[t].x);
+                        dmma884(acc[1][i][t], ar[i], ez[t].y);
+                    }
+#pragma unroll
+            for (int t = 0; t < nt0; ++t)
+#pragma unroll
+                for (int i = 0; i < NG; ++i)
+                    if (i == 0 || t < nt1) {
+                        dmma884(acc[0][i][t], ax[i], ez[t].y);
+                        dmma884(acc[1][i][t], ai[i], ez[t].x);
+                    }
+        }
     }
 }
 
@@ -497,9 +522,13 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
                 for (int n = 0; n < cnt; n += 4) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        if (n + j < cnt)
-                            e[(n + j) * kRowSlots] = n0 + n + j <= nm ? make_double2(er[j], ei[j])
-                                                                      : make_double2(0.0, 0.0);
+                        if (n + j < cnt) {
+                            const bool live = n0 + n + j <= nm;
+                            e[(n + j) * kRowSlots] = live ? make_double2(er[j], ei[j])
+                                                          : make_double2(0.0, 0.0);
+                            if (kMma3M && a == 2)     // B_r + B_i, nzpad rows further
+                                e[(P.nzpad + n + j) * kRowSlots].x = live ? er[j] + ei[j] : 0.0;
+                        }
                         const double nr = er[j] * c4 - ei[j] * s4;
                         ei[j] = er[j] * s4 + ei[j] * c4;
                         er[j] = nr;
@@ -526,13 +555,15 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
         by[i] = (P.offy + item->ny[i][g]) * kRowSlots + k;
     }
     const int bz = (P.offz + 8 * item->t0 + g) * kRowSlots + k;
+    const int bs = bz + P.nzpad * kRowSlots;
 
-    double cre[kMmaG][kMmaTZ][2], cim[kMmaG][kMmaTZ][2];
+    double acc[kMmaAcc][kMmaG][kMmaTZ][2];
 #pragma unroll
-    for (int i = 0; i < kMmaG; ++i)
+    for (int c = 0; c < kMmaAcc; ++c)
 #pragma unroll
-        for (int t = 0; t < kMmaTZ; ++t)
-            cre[i][t][0] = cre[i][t][1] = cim[i][t][0] = cim[i][t][1] = 0.0;
+        for (int i = 0; i < kMmaG; ++i)
+#pragma unroll
+            for (int t = 0; t < kMmaTZ; ++t) acc[c][i][t][0] = acc[c][i][t][1] = 0.0;
 
     const int *qi = P.qidx + (int64_t)item_index * (kMmaG * kMmaTZ * 64);
     int it = 0;
@@ -544,7 +575,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
             mbar_wait(bar_full + stage, use & 1);
             const double2 *tab = sTab + (size_t)stage * R * kRowSlots;
 #define MDH_MMA_CASE(A, B) \
-    case A * 8 + B: sq_mma_subchunk<A, B>(tab, bx, by, bz, cre, cim); break;
+    case A * 8 + B: sq_mma_subchunk<A, B>(tab, bx, by, bz, bs, acc); break;
             switch (nt0 * 8 + nt1) {
                 MDH_MMA_CASE(1, 0) MDH_MMA_CASE(2, 0) MDH_MMA_CASE(3, 0) MDH_MMA_CASE(4, 0)
 #if MDH_SQ_MMA_G > 1
@@ -572,7 +603,9 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
                     for (int j = 0; j < 2; ++j) {
                         const int q = j ? q2.y : q2.x;
                         if (q < 0) continue;
-                        const double re = cre[i][t][j], im = cim[i][t][j];
+                        const double p1 = acc[0][i][t][j], p2 = acc[1][i][t][j];
+                        const double re = kMma3M ? p1 - p2 : p1;
+                        const double im = kMma3M ? acc[kMmaAcc - 1][i][t][j] - p1 - p2 : p2;
                         if (P.chain_out) {
                             atomicAdd(P.chain_out + q, re * re + im * im);
                         } else {
@@ -581,7 +614,8 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
                         }
                     }
                 }
-                cre[i][t][0] = cre[i][t][1] = cim[i][t][0] = cim[i][t][1] = 0.0;
+#pragma unroll
+                for (int c = 0; c < kMmaAcc; ++c) acc[c][i][t][0] = acc[c][i][t][1] = 0.0;
             }
     }
 }
@@ -695,7 +729,7 @@ static void mma_layout(const int (&nmax)[3], int *offy, int *offz, int *nzpad, i
     *offy = nmax[0] + 1;
     *offz = *offy + nmax[1] + 1;
     *nzpad = (nmax[2] + 8) / 8 * 8;
-    *R = *offz + *nzpad;                  // rows of a sub-chunk table
+    *R = *offz + (kMma3M ? 2 : 1) * *nzpad;   // rows of a sub-chunk table (3M: + B_r + B_i)
 }
 static size_t mma_smem_bytes(const int (&nmax)[3])
 {
@@ -704,7 +738,7 @@ static size_t mma_smem_bytes(const int (&nmax)[3])
     return (size_t)kMmaStages * R * kRowSlots * sizeof(double2);
 }
 constexpr size_t kMmaSmemLimit = 200 * 1024;
-constexpr int kMmaAutoTiles = 28;
+constexpr int kMmaAutoTiles = 22;
 
 // Columns are paired so that the two columns a
 // quarter-warp loads together have nx (and ny) equal or an odd distance apart (see the
@@ -755,15 +789,16 @@ static void mma_build_items(std::vector<Column> cols, const int (&nm)[3],
     // segment, the largest with the smallest, so that all warps carry about the same number
     // of tiles: the block advances at the pace of its slowest warp (a warp releases a table
     // stage only when it is done with it), and one warp alone cannot keep the DMMA pipe busy
-    // cost() in 1/8 of the scheduler time of one (group, tile) pair per sub-chunk (32 DMMAs):
-    // the complex products of a group cost about 3/8 of that, a producer warp about 30/8
-    // (scalar FP64 instructions share the DMMA pipe at ~5 cycles each)
+    // cost() in 1/8 of the scheduler time of one (group, tile) pair per sub-chunk (8 steps x
+    // 3 or 4 DMMAs x 16 cycles): the complex products of a group cost about 5/8 (3/8 with 4
+    // DMMAs per pair) of that, a producer warp about 40/8 (30/8) -- scalar FP64
+    // instructions share the DMMA pipe at ~5 cycles each
     struct Proto {
         int ga, gb, t0, nt[2];
         int tiles() const { return nt[0] + nt[1]; }
-        int cost() const { return 8 * tiles() + 3 * ((nt[0] > 0) + (nt[1] > 0)); }
+        int cost() const { return 8 * tiles() + (kMma3M ? 5 : 3) * ((nt[0] > 0) + (nt[1] > 0)); }
     };
-    constexpr int kProducerCost = 60 * 32 / kMmaProducers;   // per producer warp
+    constexpr int kProducerCost = (kMma3M ? 80 : 60) * 32 / kMmaProducers;   // per producer warp
     static_assert(kMmaG == 1 || kMmaG == 2, "items are built for one or two groups");
     std::vector<Proto> protos;
     int max_tiles = 0;
@@ -1004,7 +1039,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                 "(need 0 <= n <= 1023 and no duplicates)");
     S.lattice = lattice;
     // AUTO: the DMMA kernel needs enough (group, tile) pairs to load all four schedulers
-    // of an SM (measured: 9 pairs lose to the scalar kernel, 49 win by 1.5x)
+    // of an SM (measured: 17 pairs lose to the scalar kernel by 6 %, 26 win by 11 %, 49 by 1.5x)
     S.mma = lattice && !mitems.empty() && mma_smem_bytes(S.nmax) <= kMmaSmemLimit &&
             (mode == MDH_SQ_LATTICE_DMMA || S.mma_stats[1] >= kMmaAutoTiles);
     S.mode = !lattice ? MDH_SQ_GENERAL_FP64
