@@ -207,6 +207,14 @@ int mdh_sq_kernel(mdh_ctx *ctx, int *mode);
  * which are wavevectors --, stats[2] largest number of pairs on one warp scheduler,
  * stats[3] warp schedulers (4 per block of items). */
 int mdh_sq_tiling(mdh_ctx *ctx, int64_t *stats /* [4] host */);
+/* The same planning without a device or a context (host only; used by the CPU test suite):
+ * stats[0..3] as mdh_sq_tiling, stats[4] consumer warps per block, stats[5] dynamic shared
+ * memory per block in bytes.  coverage[q] (optional) = how many accumulator slots are
+ * mapped to wavevector q -- must be 1 everywhere --, pair_rule_violations (optional) =
+ * column pairs that break the bank-conflict rule of the table layout (0 unless the
+ * wavevector set has columns without a compatible partner). */
+int mdh_sq_plan(int n_q, const int32_t *lattice_n /* [n_q][3] */, int64_t *stats /* [6] */,
+                int32_t *coverage /* [n_q] or NULL */, int32_t *pair_rule_violations);
 int mdh_sq_reset(mdh_ctx *ctx);
 int mdh_sq_accum_device(mdh_ctx *ctx, void **dptr);
 /* rho(q) of the LAST frame of the last batch: [n_rho][n_q][2] (re, im), n_rho =

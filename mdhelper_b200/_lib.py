@@ -56,6 +56,7 @@ SIGNATURES = {
     "mdh_sq_fetch": (_i32, [_p, _p]),
     "mdh_sq_kernel": (_i32, [_p, _p]),
     "mdh_sq_tiling": (_i32, [_p, _p]),
+    "mdh_sq_plan": (_i32, [_i32, _p, _p, _p, _p]),
     "mdh_sq_reset": (_i32, [_p]),
     "mdh_sq_accum_device": (_i32, [_p, ctypes.POINTER(_p)]),
     "mdh_sq_fetch_rho": (_i32, [_p, _p]),
@@ -112,6 +113,22 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     return a.data_ptr()          # torch.Tensor
+
+
+def sq_plan(lattice_n) -> dict:
+    """Work decomposition of the DMMA structure-factor kernel for the lattice indices
+    ``lattice_n`` (``[n_q, 3]``), computed on the host without a device: tiling statistics,
+    how often every wavevector is covered (must be once) and violations of the table
+    layout's column-pairing rule (must be none)."""
+    ln = np.ascontiguousarray(lattice_n, dtype=np.int32).reshape(-1, 3)
+    stats = (ctypes.c_int64 * 6)()
+    cover = np.zeros(len(ln), dtype=np.int32)
+    bad = ctypes.c_int32(0)
+    check(lib().mdh_sq_plan(len(ln), ln.ctypes.data, stats, cover.ctypes.data,
+                            ctypes.byref(bad)))
+    return {"items": stats[0], "tiles": stats[1], "max_scheduler_tiles": stats[2],
+            "schedulers": stats[3], "warps_per_block": stats[4], "smem_bytes": stats[5],
+            "coverage": cover, "pair_rule_violations": bad.value}
 
 
 class Context:

@@ -503,6 +503,11 @@ class StructureFactor(GpuAnalysisBase):
         ``"fp64"`` (default, ~1e-13 relative to the reference), or ``"fp32"``
         (lattice wavevectors only: phase factors and accumulation on the FP32
         pipe, ~1e-6 relative).
+    kernel : `str`, keyword-only, optional
+        GPU kernel strategy.  Default: chosen by the library -- for lattice
+        wavevectors ``"lattice_dmma"`` (complex rank-N update on the FP64 matrix
+        unit) from 22 (column group x nz tile) pairs up and ``"lattice_fp64"``
+        (scalar DFMA) below, ``"general_fp64"`` (dot product + sincos) otherwise.
 
     Attributes
     ----------

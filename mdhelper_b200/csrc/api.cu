@@ -380,6 +380,12 @@ int mdh_sq_kernel(mdh_ctx *c, int *mode)
     return MDH_OK;
 }
 
+int mdh_sq_plan(int n_q, const int32_t *lattice_n, int64_t *stats, int32_t *coverage,
+                int32_t *pair_rule_violations)
+{
+    return sq_plan_impl(n_q, lattice_n, stats, coverage, pair_rule_violations);
+}
+
 int mdh_sq_tiling(mdh_ctx *c, int64_t *stats)
 {
     MDH_REQUIRE(c && stats, MDH_EINVAL, "NULL argument");

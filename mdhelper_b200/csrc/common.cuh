@@ -232,6 +232,8 @@ int com_configure_impl(mdh_ctx *c, int slot, int64_t n_atoms, int64_t n_entities
 int com_reduce_impl(mdh_ctx *c, int slot, const float *pos, int64_t stride, int location,
                     int n_frames, float *out_device, int64_t out_stride);
 int sq_configure_chains_impl(mdh_ctx *c, int64_t n_chains, int64_t n_monomers);
+int sq_plan_impl(int n_q, const int32_t *lat_n, int64_t *stats, int32_t *coverage,
+                 int32_t *pair_rule_violations);
 int isf_configure_impl(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frames);
 int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
                         int n_frames);

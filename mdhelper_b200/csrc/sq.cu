@@ -740,6 +740,32 @@ static size_t mma_smem_bytes(const int (&nmax)[3])
 constexpr size_t kMmaSmemLimit = 200 * 1024;
 constexpr int kMmaAutoTiles = 22;
 
+// wavevector list -> columns (nx, ny) with their nz entries; false if the indices are not
+// usable by the lattice kernels (negative, > 1023 or duplicated)
+static bool build_columns(int n_q, const int32_t *lat_n, int (&nm)[3], std::vector<Column> &cols)
+{
+    nm[0] = nm[1] = nm[2] = 0;
+    for (int i = 0; i < n_q; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const int n = lat_n[3 * i + k];
+            if (n < 0 || n > 1023) return false;
+            nm[k] = std::max(nm[k], n);
+        }
+    std::map<std::pair<int, int>, int> where;
+    for (int i = 0; i < n_q; ++i) {
+        const std::pair<int, int> key{lat_n[3 * i], lat_n[3 * i + 1]};
+        auto it = where.find(key);
+        if (it == where.end()) {
+            it = where.emplace(key, (int)cols.size()).first;
+            cols.push_back(Column{key.first, key.second, std::vector<int>(nm[2] + 1, -1)});
+        }
+        int &slot = cols[it->second].q[lat_n[3 * i + 2]];
+        if (slot >= 0) return false;                          // duplicate wavevector
+        slot = i;
+    }
+    return true;
+}
+
 // Columns are paired so that the two columns a
 // quarter-warp loads together have nx (and ny) equal or an odd distance apart (see the
 // bank analysis at the kernel), four pairs make a group of 8, kMmaG consecutive groups x
@@ -909,6 +935,45 @@ static void mma_build_items(std::vector<Column> cols, const int (&nm)[3],
 
 }  // namespace
 
+// Device-free planning of the DMMA kernel's work items (what mdh_sq_configure builds for
+// MDH_SQ_LATTICE_DMMA); see mdh_sq_plan in the header.
+int sq_plan_impl(int n_q, const int32_t *lat_n, int64_t *stats, int32_t *coverage,
+                 int32_t *pair_rule_violations)
+{
+    MDH_REQUIRE(n_q >= 1 && lat_n && stats, MDH_EINVAL, "sq plan: missing argument");
+    int nm[3];
+    std::vector<Column> cols;
+    MDH_REQUIRE(build_columns(n_q, lat_n, nm, cols), MDH_EINVAL,
+                "sq plan: wavevector indices are not usable by the lattice kernels");
+    std::vector<SqMmaItem> items;
+    std::vector<int> qidx;
+    int warps = 0, st[4] = {0, 0, 0, 0};
+    mma_build_items(cols, nm, items, qidx, warps, st);
+    for (int i = 0; i < 4; ++i) stats[i] = st[i];
+    stats[4] = warps;
+    stats[5] = (int64_t)mma_smem_bytes(nm);
+    if (coverage) {
+        for (int i = 0; i < n_q; ++i) coverage[i] = 0;
+        for (int q : qidx) if (q >= 0 && q < n_q) coverage[q]++;
+    }
+    if (pair_rule_violations) {
+        // the two columns a quarter-warp loads together (m = 2j, 2j + 1) must have equal or
+        // odd-distance nx and ny, or their shared-memory loads conflict
+        int bad = 0;
+        for (const SqMmaItem &it : items)
+            for (int i = 0; i < kMmaG; ++i) {
+                if (it.nt[i] == 0) continue;
+                for (int m = 0; m < 8; m += 2) {
+                    const int dx = std::abs(it.nx[i][m] - it.nx[i][m + 1]);
+                    const int dy = std::abs(it.ny[i][m] - it.ny[i][m + 1]);
+                    if ((dx != 0 && !(dx & 1)) || (dy != 0 && !(dy & 1))) ++bad;
+                }
+            }
+        *pair_rule_violations = bad;
+    }
+    return MDH_OK;
+}
+
 // ---- host side ------------------------------------------------------------------
 
 int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *goff,
@@ -965,28 +1030,8 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
     int mma_warps = 0;
     if (lattice) {
         int nm[3] = {0, 0, 0};
-        for (int i = 0; i < n_q && lattice; ++i)
-            for (int k = 0; k < 3; ++k) {
-                const int n = lat_n[3 * i + k];
-                if (n < 0 || n > 1023) lattice = false;
-                else nm[k] = std::max(nm[k], n);
-            }
         std::vector<Column> cols;
-        if (lattice) {
-            std::map<std::pair<int, int>, int> where;
-            for (int i = 0; i < n_q && lattice; ++i) {
-                const std::pair<int, int> key{lat_n[3 * i], lat_n[3 * i + 1]};
-                auto it = where.find(key);
-                if (it == where.end()) {
-                    it = where.emplace(key, (int)cols.size()).first;
-                    cols.push_back(Column{key.first, key.second,
-                                          std::vector<int>(nm[2] + 1, -1)});
-                }
-                int &slot = cols[it->second].q[lat_n[3 * i + 2]];
-                if (slot >= 0) lattice = false;               // duplicate wavevector
-                slot = i;
-            }
-        }
+        lattice = build_columns(n_q, lat_n, nm, cols);
         if (lattice) {
             auto top = column_top;
             std::stable_sort(cols.begin(), cols.end(),

@@ -283,3 +283,48 @@ def test_feeder_accepts_mdanalysis_memoryreader_layout():
     assert np.array_equal(b.dims, dims[[0, 2]])
     t.stored_order = "afc"
     assert not base.FrameFeeder(t, [np.arange(10, 30)], np.arange(6), 2).zero_copy
+
+
+# ---- work decomposition of the DMMA S(q) kernel (host-side planning, no device) ---------
+
+def _sphere(n_max, n_points=None):
+    r = range((n_points or n_max + 1))
+    return np.array([(x, y, z) for x in r for y in r for z in r
+                     if x * x + y * y + z * z <= n_max * n_max], dtype=np.int32)
+
+
+@pytest.mark.parametrize("case", ["cfg4", "n20", "full32", "tiny", "column", "sparse",
+                                  "anisotropic", "tall"])
+def test_sq_dmma_plan_covers_every_wavevector_once(case):
+    """mdh_sq_plan: every wavevector is mapped to exactly one accumulator slot, the paired
+    columns obey the bank rule of the table layout, the tables fit in shared memory and the
+    schedulers' loads are level (include/mdh_b200.h; kernel: csrc/sq.cu)."""
+    from mdhelper_b200 import _lib
+    rng = np.random.default_rng(3)
+    n = {"cfg4": _sphere(16), "n20": _sphere(20), "tiny": _sphere(2),
+         "full32": np.stack(np.meshgrid(*[np.arange(32)] * 3), -1).reshape(-1, 3),
+         "column": np.array([(0, 0, z) for z in range(0, 45, 3)]),
+         "sparse": rng.permutation(_sphere(12))[:97],
+         "anisotropic": np.array([(x, y, z) for x in range(3) for y in range(11)
+                                  for z in range(37)]),
+         "tall": np.array([(x, 0, z) for x in range(5) for z in range(70)])}[case]
+    n = rng.permutation(np.asarray(n, dtype=np.int32))          # order must not matter
+    plan = _lib.sq_plan(n)
+    assert np.array_equal(plan["coverage"], np.ones(len(n), np.int32))
+    assert plan["pair_rule_violations"] == 0
+    assert plan["tiles"] * 64 >= len(n)
+    assert 1 <= plan["warps_per_block"] <= 14
+    assert plan["items"] <= plan["warps_per_block"] * plan["schedulers"] // 4
+    if case == "cfg4":      # the bench workload: 216 columns -> 27 groups, 49 tiles, one block
+        assert (plan["tiles"], plan["items"], plan["schedulers"]) == (49, 14, 4)
+        assert plan["smem_bytes"] <= 200 * 1024
+    if case == "full32":    # perfect tiling: 1,024 columns x 4 tiles
+        assert plan["tiles"] * 64 == 32 ** 3
+
+
+def test_sq_dmma_plan_rejects_bad_indices():
+    from mdhelper_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.sq_plan(np.array([(0, 0, 1), (0, 0, 1)]))           # duplicate
+    with pytest.raises(ValueError):
+        _lib.sq_plan(np.array([(0, -1, 1)]))                     # negative index
