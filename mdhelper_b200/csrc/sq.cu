@@ -453,26 +453,27 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
         const int zhalf = (P.nzpad / 2 + 3) / 4 * 4;
         // coordinate for task r of the sub-chunk at p0 of unit u; fetched one sub-chunk
         // ahead so that the global-memory latency is off the critical path
-        auto fetch = [&](int r, int u, int p0) -> double {
+        // (raw floats: converted only when used, or the conversion would wait for the load
+        // right here; second value: the reference frame of a displacement, else 0; NaN: a
+        // particle past the end of the chunk)
+        auto fetch = [&](int r, int u, int p0) -> float2 {
             const int task = tid - n_cons + r * kMmaProducers;
             const int part = task / kPS, p = task - part * kPS, a = min(part, 2);
-            if (u >= P.n_units) return 0.0;
+            if (u >= P.n_units) return make_float2(0.f, 0.f);
             const int frame = u / P.n_chunks;
             const int4 ch = P.chunks[u - frame * P.n_chunks];
-            if (p0 + p >= ch.y) return nan("");
+            if (p0 + p >= ch.y) return make_float2(nanf(""), 0.f);
             const int4 vm = P.vmap ? P.vmap[frame] : make_int4(frame, -1, 0, 0);
             const int64_t idx = 3 * (int64_t)(p0 + p) + a;
-            double x = (double)P.raw[(int64_t)vm.x * P.stride + idx];
-            // displacement in fp64 of the float32 coordinates: exact, as the reference's
-            // float64 position buffer makes it
-            if (vm.y >= 0) x -= (double)P.raw[(int64_t)vm.y * P.stride + idx];
-            return x;
+            float2 v = make_float2(P.raw[(int64_t)vm.x * P.stride + idx], 0.f);
+            if (vm.y >= 0) v.y = P.raw[(int64_t)vm.y * P.stride + idx];
+            return v;
         };
         int it = 0;
         int u = blockIdx.y;
         int4 chunk = u < P.n_units ? P.chunks[u % P.n_chunks] : make_int4(0, 0, 0, 0);
         int p0 = chunk.x;
-        double x[kMmaRounds], xn[kMmaRounds];
+        float2 x[kMmaRounds], xn[kMmaRounds];
 #pragma unroll
         for (int r = 0; r < kMmaRounds; ++r) x[r] = fetch(r, u, p0);
         while (u < P.n_units) {
@@ -499,8 +500,10 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
                 double er[4], ei[4], c4 = 0.0, s4 = 0.0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) er[j] = ei[j] = 0.0;
-                if (x[r] == x[r]) {               // NaN: past the end of the chunk -> zero row
-                    const double th = P.b[a] * x[r];
+                if (x[r].x == x[r].x) {           // NaN: past the end of the chunk -> zero row
+                    // displacement in fp64 of the float32 coordinates: exact, as the
+                    // reference's float64 position buffer makes it
+                    const double th = P.b[a] * ((double)x[r].x - (double)x[r].y);
                     double s1, c1;
                     sincos(th, &s1, &c1);
                     const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * (c1 * s1);
@@ -817,14 +820,19 @@ static void mma_build_items(std::vector<Column> cols, const int (&nm)[3],
     // stage only when it is done with it), and one warp alone cannot keep the DMMA pipe busy
     // cost() in 1/8 of the scheduler time of one (group, tile) pair per sub-chunk (8 steps x
     // 3 or 4 DMMAs x 16 cycles): the complex products of a group cost about 5/8 (3/8 with 4
-    // DMMAs per pair) of that, a producer warp about 40/8 (30/8) -- scalar FP64
-    // instructions share the DMMA pipe at ~5 cycles each
+    // DMMAs per pair) of that -- scalar FP64 instructions share the DMMA pipe at ~5 cycles
+    // each -- and a producer warp is charged 80/8 (60/8): measured optimum (cfg4: 21.7k
+    // frames/s at 40/8, 22.6k at 60/8, 23.0k at 80/8, 22.9k at 100/8); its FP64 chains lose
+    // the arbitration against the DMMAs of its scheduler, so the consumers there must be few
     struct Proto {
         int ga, gb, t0, nt[2];
         int tiles() const { return nt[0] + nt[1]; }
         int cost() const { return 8 * tiles() + (kMma3M ? 5 : 3) * ((nt[0] > 0) + (nt[1] > 0)); }
     };
-    constexpr int kProducerCost = (kMma3M ? 80 : 60) * 32 / kMmaProducers;   // per producer warp
+#ifndef MDH_SQ_MMA_PCOST
+#define MDH_SQ_MMA_PCOST (kMma3M ? 160 : 120)
+#endif
+    constexpr int kProducerCost = MDH_SQ_MMA_PCOST * 32 / kMmaProducers;   // per producer warp
     static_assert(kMmaG == 1 || kMmaG == 2, "items are built for one or two groups");
     std::vector<Proto> protos;
     int max_tiles = 0;
