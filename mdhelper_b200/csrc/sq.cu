@@ -503,9 +503,11 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
                 if (x[r].x == x[r].x) {           // NaN: past the end of the chunk -> zero row
                     // displacement in fp64 of the float32 coordinates: exact, as the
                     // reference's float64 position buffer makes it
-                    const double th = P.b[a] * ((double)x[r].x - (double)x[r].y);
+                    // phase = pi * (b / pi) * x: sincospi needs no Cody-Waite reduction
+                    const double th = (P.b[a] * 0.31830988618379067154) *
+                                      ((double)x[r].x - (double)x[r].y);
                     double s1, c1;
-                    sincos(th, &s1, &c1);
+                    sincospi(th, &s1, &c1);
                     const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * (c1 * s1);
                     c4 = c2 * c2 - s2 * s2; s4 = 2.0 * (c2 * s2);
                     er[0] = 1.0;
