@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(kSqThreads, 2) sq_lattice_kernel(const Lattice
 #endif
 constexpr int kMmaG = MDH_SQ_MMA_G;     // column groups per warp item (1 or 2)
 constexpr int kMmaTZ = 4;
+constexpr int kRowSlots = kPS + 4;   // entries per table row
 // 3-multiplication complex product (Gauss / "3M"): with P1 = sum A_r B_r, P2 = sum A_i B_i,
 // P3 = sum (A_r + A_i)(B_r + B_i):  Re = P1 - P2, Im = P3 - P1 - P2 -- three DMMAs per
 // (group, tile) and step instead of four, for one DADD per group and step and a third
@@ -289,7 +290,13 @@ constexpr int kMmaTZ = 4;
 #endif
 constexpr bool kMma3M = MDH_SQ_MMA_3M != 0;
 constexpr int kMmaAcc = kMma3M ? 3 : 2;   // accumulator pairs per (group, tile)
-constexpr int kRowSlots = kPS + 4;   // double2 entries per table row
+// double2 entries of one table stage: R rows of kRowSlots (re, im) entries, then (3M) nzpad
+// rows of kRowSlots doubles B_r + B_i -- 288-byte rows, 8 banks apart, so that the 8-byte
+// loads of a half-warp (four neighbouring rows x four particles) are conflict-free
+__host__ __device__ inline int mma_stage_entries(int R, int nzpad)
+{
+    return R * kRowSlots + (kMma3M ? nzpad * kRowSlots / 2 : 0);
+}
 #ifndef MDH_SQ_MMA_WARPS
 #define MDH_SQ_MMA_WARPS 14
 #endif
@@ -333,7 +340,8 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
 // step (row * kRowSlots + k); step ks is 4 * ks entries further, tile t 8 rows further.
 template <int nt0, int nt1>
 __device__ __forceinline__ void sq_mma_subchunk(const double2 *tab, const int (&bx)[kMmaG],
-                                                const int (&by)[kMmaG], int bz, int bs,
+                                                const int (&by)[kMmaG], int bz,
+                                                const double *sums, int bs,
                                                 double (&acc)[kMmaAcc][kMmaG][kMmaTZ][2])
 {
     constexpr int NG = nt1 > 0 ? 2 : 1;
@@ -353,7 +361,7 @@ __device__ __forceinline__ void sq_mma_subchunk(const double2 *tab, const int (&
 #pragma unroll
             for (int t = 0; t < nt0; ++t) {
                 const double2 ez = tab[bz + 4 * ks + 8 * kRowSlots * t];
-                const double es = tab[bs + 4 * ks + 8 * kRowSlots * t].x;
+                const double es = sums[bs + 4 * ks + 8 * kRowSlots * t];
 #pragma unroll
                 for (int i = 0; i < NG; ++i)
                     if (i == 0 || t < nt1) {
@@ -522,8 +530,10 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
                     er[3] = er[1] * c2 - ei[1] * s2; ei[3] = er[1] * s2 + ei[1] * c2;
                 }
                 // entry n of this part: row (offset + n0 + n), slot p
-                double2 *e = sTab + ((size_t)stage * R +
-                                     (a == 0 ? 0 : a == 1 ? P.offy : P.offz) + n0) * kRowSlots + p;
+                double2 *stab = sTab + (size_t)stage * mma_stage_entries(R, P.nzpad);
+                double2 *e = stab + ((a == 0 ? 0 : a == 1 ? P.offy : P.offz) + n0) * kRowSlots + p;
+                // B_r + B_i of E_z entry n0 + n: row n0 + n of the doubles behind the table
+                double *es = reinterpret_cast<double *>(stab + R * kRowSlots) + n0 * kRowSlots + p;
                 for (int n = 0; n < cnt; n += 4) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -531,8 +541,8 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
                             const bool live = n0 + n + j <= nm;
                             e[(n + j) * kRowSlots] = live ? make_double2(er[j], ei[j])
                                                           : make_double2(0.0, 0.0);
-                            if (kMma3M && a == 2)     // B_r + B_i, nzpad rows further
-                                e[(P.nzpad + n + j) * kRowSlots].x = live ? er[j] + ei[j] : 0.0;
+                            if (kMma3M && a == 2)
+                                es[(n + j) * kRowSlots] = live ? er[j] + ei[j] : 0.0;
                         }
                         const double nr = er[j] * c4 - ei[j] * s4;
                         ei[j] = er[j] * s4 + ei[j] * c4;
@@ -560,7 +570,8 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
         by[i] = (P.offy + item->ny[i][g]) * kRowSlots + k;
     }
     const int bz = (P.offz + 8 * item->t0 + g) * kRowSlots + k;
-    const int bs = bz + P.nzpad * kRowSlots;
+    // this lane's B_r + B_i entry (doubles, behind the R double2 rows of the stage)
+    const int bs = (8 * item->t0 + g) * kRowSlots + k;
 
     double acc[kMmaAcc][kMmaG][kMmaTZ][2];
 #pragma unroll
@@ -578,9 +589,10 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
         for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS, ++it) {
             const int stage = it % kMmaStages, use = it / kMmaStages;
             mbar_wait(bar_full + stage, use & 1);
-            const double2 *tab = sTab + (size_t)stage * R * kRowSlots;
+            const double2 *tab = sTab + (size_t)stage * mma_stage_entries(R, P.nzpad);
+            const double *sums = reinterpret_cast<const double *>(tab + R * kRowSlots);
 #define MDH_MMA_CASE(A, B) \
-    case A * 8 + B: sq_mma_subchunk<A, B>(tab, bx, by, bz, bs, acc); break;
+    case A * 8 + B: sq_mma_subchunk<A, B>(tab, bx, by, bz, sums, bs, acc); break;
             switch (nt0 * 8 + nt1) {
                 MDH_MMA_CASE(1, 0) MDH_MMA_CASE(2, 0) MDH_MMA_CASE(3, 0) MDH_MMA_CASE(4, 0)
 #if MDH_SQ_MMA_G > 1
@@ -734,13 +746,13 @@ static void mma_layout(const int (&nmax)[3], int *offy, int *offz, int *nzpad, i
     *offy = nmax[0] + 1;
     *offz = *offy + nmax[1] + 1;
     *nzpad = (nmax[2] + 8) / 8 * 8;
-    *R = *offz + (kMma3M ? 2 : 1) * *nzpad;   // rows of a sub-chunk table (3M: + B_r + B_i)
+    *R = *offz + *nzpad;                  // double2 rows of a sub-chunk table
 }
 static size_t mma_smem_bytes(const int (&nmax)[3])
 {
     int offy, offz, nzpad, R;
     mma_layout(nmax, &offy, &offz, &nzpad, &R);
-    return (size_t)kMmaStages * R * kRowSlots * sizeof(double2);
+    return (size_t)kMmaStages * mma_stage_entries(R, nzpad) * sizeof(double2);
 }
 constexpr size_t kMmaSmemLimit = 200 * 1024;
 constexpr int kMmaAutoTiles = 22;
