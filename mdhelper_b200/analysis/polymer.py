@@ -14,7 +14,8 @@ from __future__ import annotations
 import numpy as np
 
 from .base import GpuAnalysisBase, all_reduce_sum
-from .structure import (_centers_of_mass, _isclose_members, _lattice_indices,
+from .structure import (_centers_of_mass, _grouped_mean, _isclose_members,
+                        _lattice_indices,
                         _record)
 
 
@@ -210,6 +211,4 @@ class SingleChainStructureFactor(GpuAnalysisBase):
         # same index sets as the reference's np.isclose(q, wavenumbers) scan
         if getattr(self, "_members", None) is None:
             self._members = _isclose_members(self.results.wavenumbers, self._wavenumbers)
-        self.results.scsf = np.fromiter(
-            (scsf[m].mean() for m in self._members),
-            dtype=float, count=len(self.results.wavenumbers))
+        self.results.scsf = _grouped_mean(scsf, self._members)

@@ -328,3 +328,22 @@ def test_sq_dmma_plan_rejects_bad_indices():
         _lib.sq_plan(np.array([(0, 0, 1), (0, 0, 1)]))           # duplicate
     with pytest.raises(ValueError):
         _lib.sq_plan(np.array([(0, -1, 1)]))                     # negative index
+
+
+def test_grouped_mean_is_bit_identical_to_the_per_group_loop():
+    """structure._grouped_mean (one numpy call per group size) == the reference's loop of
+    values[..., members].mean(axis=-1) (structure.py:1538-1543), bit for bit, for the
+    unique-|q| groups of a real wavevector grid and for 1-, 2- and 3-dimensional values."""
+    rng = np.random.default_rng(11)
+    grid = 2 * np.pi * np.arange(18) / 39.685
+    wv = np.stack(np.meshgrid(grid, grid, grid), -1).reshape(-1, 3)
+    w = np.linalg.norm(wv, axis=1)
+    w = w[w <= grid[16] + 1e-9]
+    uq = np.unique(w.round(11))
+    members = structure._isclose_members(uq, w)
+    assert sorted(len(m) for m in members)[-1] > 24       # long groups: pairwise summation
+    for shape in ((len(w),), (3, len(w)), (5, 2, len(w))):
+        v = rng.standard_normal(shape) * 10.0 ** rng.integers(-3, 4, size=shape)
+        want = np.stack([v[..., m].mean(axis=-1) for m in members], axis=-1)
+        got = structure._grouped_mean(v, members)
+        assert got.shape == want.shape and np.array_equal(got, want)

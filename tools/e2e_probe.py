@@ -23,7 +23,7 @@ print("sq run(128 frames) ms:", t(lambda: sf.run(start=0, stop=128)))
 ctx = _lib.Context(0)
 N = 50_000
 cfg = lambda: ctx.sq_configure(N, [0, N], sf._wavevectors, [(-1, -1)], lattice_n=sf._lattice_n,
-                               lattice_b=sf._lattice_b, mode="lattice_fp64")
+                               lattice_b=sf._lattice_b, mode="auto")
 print("sq configure ms:", t(cfg))
 c = u.trajectory.coordinates
 print("pinned:", torch.from_numpy(c).is_pinned() if hasattr(torch.from_numpy(c), "is_pinned") else None)
