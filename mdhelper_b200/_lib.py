@@ -241,10 +241,19 @@ class Context:
             lb = np.ascontiguousarray(lattice_b, dtype=np.float64)
             if ln.shape != wv.shape or lb.shape != (3,):
                 raise ValueError("lattice_n must match wavevectors; lattice_b is (3,)")
+        # an unchanged configuration (run() after run() on the same object) only needs its
+        # accumulator cleared, not the work items rebuilt and uploaded
+        key = (int(n_total), goff.tobytes(), wv.tobytes(), pr.tobytes(),
+               None if ln is None else ln.tobytes(), None if lb is None else lb.tobytes(), mode)
+        if key == getattr(self, "_sq_key", None):
+            check(self._lib.mdh_sq_reset(self._h))
+            return
+        self._sq_key = None
         check(self._lib.mdh_sq_configure(
             self._h, int(n_total), len(goff) - 1, goff.ctypes.data, len(wv),
             wv.ctypes.data, _ptr(ln), _ptr(lb), len(pr), pr.ctypes.data,
             SQ_MODES[mode]))
+        self._sq_key = key
         self._sq_shape = (len(pr), len(wv))
         self._sq_nrho = 1 if (pr < 0).any() else len(goff) - 1
 
@@ -292,6 +301,7 @@ class Context:
 
     def sq_configure_chains(self, n_chains: int, n_monomers: int):
         """Single-chain mode: ``sq_accumulate`` adds sum over chains of |rho_chain|^2."""
+        self._sq_key = None                      # C-side state now differs from a plain configure
         check(self._lib.mdh_sq_configure_chains(self._h, int(n_chains), int(n_monomers)))
 
     # ---- intermediate scattering function (after sq_configure) ----
