@@ -291,8 +291,10 @@ class RadialDistributionFunction(GpuAnalysisBase):
             and self._groupings[0] == self._groupings[1]
         self._same = same
         ctx.rdf_set_filter(self._arith)
+        if getattr(self, "_thresholds", None) is None:   # fixed per instance
+            self._thresholds = squared_thresholds(self._n_bins, self._range)
         ctx.rdf_configure(
-            n1, n2, same, squared_thresholds(self._n_bins, self._range),
+            n1, n2, same, self._thresholds,
             self._range[0], self._range[1], exclusion=self._exclusion,
             drop_axis=self._drop_axis, mode=self._mode, hist=self._hist
         )
