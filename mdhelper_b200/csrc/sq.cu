@@ -428,8 +428,27 @@ constexpr int kMmaProducers = MDH_SQ_MMA_PRODUCERS;
 constexpr int kMmaRounds = 4 * kPS / kMmaProducers;
 static_assert(kMmaRounds * kMmaProducers == 4 * kPS, "producer threads must divide the tasks");
 
-// Persistent block = n_cons consumer warps (one SqMmaItem each) followed by kMmaProducers
-// producer threads.  The block walks the work units (frame, particle chunk) blockIdx.y,
+// Position of producer warp j in a block of W consumer warps: with at least 6 consumers the
+// (two) producers sit at warps 3 and 7, i.e. on the same scheduler (warp w runs on
+// scheduler w mod 4), which then carries few consumer warps -- the producers' scalar FP64
+// chains lose the arbitration against DMMAs, so they should meet as few as possible;
+// smaller blocks keep the producers behind the consumers.
+__host__ __device__ inline int mma_producer_warp(int W, int j)
+{
+    return (kMmaProducers == 64 && W >= 6) ? 3 + 4 * j : W + j;
+}
+// warp index of consumer slot c
+__host__ __device__ inline int mma_consumer_warp(int W, int c)
+{
+    int w = c;
+    for (int j = 0; j < kMmaProducers / 32; ++j)
+        if (w >= mma_producer_warp(W, j)) ++w;
+    return w;
+}
+
+
+// Persistent block = n_cons consumer warps (one SqMmaItem each) and kMmaProducers producer
+// threads (warp roles: mma_producer_warp).  The block walks the work units (frame, particle chunk) blockIdx.y,
 // blockIdx.y + gridDim.y, ...; the producers build the phase-factor tables of the
 // sub-chunks (32 particles) into a ring of kMmaStages buffers, running ahead of the
 // consumers across unit boundaries; "full" / "empty" mbarriers per stage -- a consumer
@@ -443,7 +462,18 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
     const int R = P.R;
     const int tid = threadIdx.x, lane = tid & 31;
     const int n_cons = (int)blockDim.x - kMmaProducers;
-    const bool producer = tid >= n_cons;
+    // warp roles: the producer warps sit at the positions mma_producer_warp() says (on ONE
+    // scheduler when the block is large enough), the consumers fill the rest in order
+    const int warp = tid >> 5;
+    int prod_index = -1, cons_index = warp;
+#pragma unroll
+    for (int j = 0; j < kMmaProducers / 32; ++j) {
+        const int pw = mma_producer_warp(n_cons >> 5, j);
+        if (warp == pw) prod_index = j;
+        if (warp > pw) --cons_index;
+    }
+    const bool producer = prod_index >= 0;
+    const int ptid = prod_index * 32 + lane;       // thread index among the producers
     if (tid == 0)
         for (int s = 0; s < kMmaStages; ++s) {
             mbar_init(bar_full + s, kMmaProducers);
@@ -465,7 +495,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
         // right here; second value: the reference frame of a displacement, else 0; NaN: a
         // particle past the end of the chunk)
         auto fetch = [&](int r, int u, int p0) -> float2 {
-            const int task = tid - n_cons + r * kMmaProducers;
+            const int task = ptid + r * kMmaProducers;
             const int part = task / kPS, p = task - part * kPS, a = min(part, 2);
             if (u >= P.n_units) return make_float2(0.f, 0.f);
             const int frame = u / P.n_chunks;
@@ -500,7 +530,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
             if (use > 0) mbar_wait(bar_empty + stage, (use - 1) & 1);
 #pragma unroll
             for (int r = 0; r < kMmaRounds; ++r) {
-                const int task = tid - n_cons + r * kMmaProducers;
+                const int task = ptid + r * kMmaProducers;
                 const int part = task / kPS, p = task - part * kPS, a = min(part, 2);
                 const int nm = P.nmax[a];
                 const int n0 = part == 3 ? zhalf : 0;
@@ -559,7 +589,7 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
         return;
     }
 
-    const int item_index = blockIdx.x * (n_cons >> 5) + (tid >> 5);
+    const int item_index = blockIdx.x * (n_cons >> 5) + cons_index;
     const SqMmaItem *item = P.items + item_index;
     const int nt0 = item->nt[0], nt1 = kMmaG > 1 ? item->nt[kMmaG - 1] : 0;
     const int g = lane >> 2, k = lane & 3;
@@ -881,15 +911,19 @@ static void mma_build_items(std::vector<Column> cols, const int (&nm)[3],
     std::vector<int> load(n_blocks * 4, 0), fill(n_blocks * 4, 0);
     std::vector<int> place(n_blocks * W, -1);         // slot -> proto
     for (int b = 0; b < n_blocks; ++b)                // the producer warps follow the consumers
-        for (int j = 0; j < kMmaProducers / 32; ++j) load[b * 4 + ((W + j) & 3)] += kProducerCost;
+        for (int j = 0; j < kMmaProducers / 32; ++j)
+            load[b * 4 + (mma_producer_warp(W, j) & 3)] += kProducerCost;
+    // consumer slots of a block by scheduler
+    std::vector<int> slots_of[4];
+    for (int c = 0; c < W; ++c) slots_of[mma_consumer_warp(W, c) & 3].push_back(c);
+    auto sched_of = [&](int c) { return mma_consumer_warp(W, c) & 3; };
     for (int p = 0; p < n_items; ++p) {
         int best = -1;
         for (int bin = 0; bin < n_blocks * 4; ++bin) {
-            const int s = bin & 3, cap = (W - s + 3) / 4;
-            if (fill[bin] >= cap) continue;
+            if (fill[bin] >= (int)slots_of[bin & 3].size()) continue;
             if (best < 0 || load[bin] < load[best]) best = bin;
         }
-        place[(best >> 2) * W + (best & 3) + 4 * fill[best]] = p;
+        place[(best >> 2) * W + slots_of[best & 3][fill[best]]] = p;
         fill[best]++;
         load[best] += protos[p].cost();
     }
@@ -900,7 +934,7 @@ static void mma_build_items(std::vector<Column> cols, const int (&nm)[3],
         for (int b = 0; b < n_blocks && !improved; ++b)
             for (int s1 = 0; s1 < W && !improved; ++s1)
                 for (int s2 = 0; s2 < W && !improved; ++s2) {
-                    const int b1 = b * 4 + (s1 & 3), b2 = b * 4 + (s2 & 3);
+                    const int b1 = b * 4 + sched_of(s1), b2 = b * 4 + sched_of(s2);
                     if (b1 == b2 || load[b1] <= load[b2]) continue;
                     const int p1 = place[b * W + s1], p2 = place[b * W + s2];
                     const int c1 = p1 < 0 ? 0 : protos[p1].cost(), c2 = p2 < 0 ? 0 : protos[p2].cost();
