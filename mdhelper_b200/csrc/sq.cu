@@ -11,16 +11,18 @@
 // Normalisation, unique-|q| grouping and sorting stay on the host (numpy).
 //
 // Kernels
-//   sq_lattice_kernel<T, RZ>  wavevectors on the reciprocal lattice, q = n * b
-//       (the reference's default grid, structure.py:1376-1416).  exp(i q.r)
-//       factorises into per-axis phase factors E_a(n) = exp(i n b_a r_a): each
-//       block builds E_a(0..nmax_a) for a sub-chunk of 32 particles in shared
-//       memory (one fp64 sincos per particle and axis, then the recurrence
-//       E(n+1) = E(n) E(1)), and each thread owns two (nx, ny) columns x 8
-//       consecutive nz with register accumulators:
+//   sq_lattice_mma_kernel    wavevectors on the reciprocal lattice, q = n * b (the
+//       reference's default grid, structure.py:1376-1416).  exp(i q.r) factorises into
+//       per-axis phase factors E_a(n) = exp(i n b_a r_a), which turns the sum into the
+//       complex rank-N update rho[(nx, ny)][nz] = sum_j (E_x E_y)[j] E_z[j]: warp-
+//       specialised, producer warps build the E_a tables (fp64 sincospi + recurrence) into
+//       an mbarrier-guarded shared-memory ring, consumer warps run the update on the FP64
+//       matrix unit (mma.m8n8k4.f64, 3-multiplication complex product).  Default for all
+//       but small wavevector sets (~1e-13 relative to the reference).
+//   sq_lattice_kernel<T>     the same factorisation with scalar FMAs: each thread owns two
+//       (nx, ny) columns x 8 consecutive nz in registers,
 //           A = E_x(nx) E_y(ny);   acc[r] += A * E_z(nz0 + r)     (4 FMA per term)
-//       T = double: fp64 throughout (default; ~1e-13 relative to the reference).
-//       T = float : same scheme on the FP32 pipe (approximate mode).
+//       T = double: small wavevector sets;  T = float: approximate mode on the FP32 pipe.
 //   sq_general_kernel        arbitrary wavevectors: fp64 dot product + fp64 sincos.
 //   sq_finalize_kernel       ssf += per-frame |rho|^2 / cross terms.
 
