@@ -508,7 +508,7 @@ class StructureFactor(GpuAnalysisBase):
     kernel : `str`, keyword-only, optional
         GPU kernel strategy.  Default: chosen by the library -- for lattice
         wavevectors ``"lattice_dmma"`` (complex rank-N update on the FP64 matrix
-        unit) from 22 (column group x nz tile) pairs up and ``"lattice_fp64"``
+        unit) from 16 (column group x nz tile) pairs up and ``"lattice_fp64"``
         (scalar DFMA) below, ``"general_fp64"`` (dot product + sincos) otherwise.
 
     Attributes

@@ -787,7 +787,7 @@ static size_t mma_smem_bytes(const int (&nmax)[3])
     return (size_t)kMmaStages * mma_stage_entries(R, nzpad) * sizeof(double2);
 }
 constexpr size_t kMmaSmemLimit = 200 * 1024;
-constexpr int kMmaAutoTiles = 22;
+constexpr int kMmaAutoTiles = 16;
 
 // wavevector list -> columns (nx, ny) with their nz entries; false if the indices are not
 // usable by the lattice kernels (negative, > 1023 or duplicated)
@@ -1142,7 +1142,7 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                 "(need 0 <= n <= 1023 and no duplicates)");
     S.lattice = lattice;
     // AUTO: the DMMA kernel needs enough (group, tile) pairs to load all four schedulers
-    // of an SM (measured: 17 pairs lose to the scalar kernel by 6 %, 26 win by 11 %, 49 by 1.5x)
+    // of an SM (measured: 9 pairs lose to the scalar kernel by 27 %, 17 win by 4 %, 26 by 11 %, 49 by 1.8x)
     S.mma = lattice && !mitems.empty() && mma_smem_bytes(S.nmax) <= kMmaSmemLimit &&
             (mode == MDH_SQ_LATTICE_DMMA || S.mma_stats[1] >= kMmaAutoTiles);
     S.mode = !lattice ? MDH_SQ_GENERAL_FP64
