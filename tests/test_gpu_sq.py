@@ -174,6 +174,25 @@ def test_frame_additivity_and_selection():
     assert s.results.ssf.shape[0] == 1 and np.isfinite(s.results.ssf).all()
 
 
+def test_auto_kernel_choice_and_tiling_report():
+    """MDH_SQ_AUTO: small lattice sets run on the scalar kernel, larger ones on the matrix
+    unit, off-lattice wavevectors on the general kernel; mdh_sq_tiling agrees with the
+    device-free mdh_sq_plan."""
+    from mdhelper_b200 import _lib, synthetic
+    u = synthetic.lj_fluid(400, 1, seed=2)
+    small = _S().StructureFactor([u.atoms], n_points=8, verbose=False).run()       # 8 pairs
+    assert small._ctx.sq_kernel() == "lattice_fp64"
+    assert small._ctx.sq_tiling()["tiles"] == 0
+    big = _S().StructureFactor([u.atoms], n_points=12, verbose=False).run()        # 36 pairs
+    assert big._ctx.sq_kernel() == "lattice_dmma"
+    plan = _lib.sq_plan(big._lattice_n)
+    tiling = big._ctx.sq_tiling()
+    assert {k: plan[k] for k in tiling} == tiling and tiling["tiles"] == 36
+    off = _S().StructureFactor([u.atoms], n_points=6, n_surfaces=2, n_surface_points=8,
+                               verbose=False).run()
+    assert off._ctx.sq_kernel() == "general_fp64"
+
+
 def test_mma_pipeline_long_run():
     """DMMA kernel: thousands of work units per launch (every persistent block walks many
     units, the table ring and its mbarrier phases wrap hundreds of times), a particle count
