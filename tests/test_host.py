@@ -387,3 +387,26 @@ def test_lattice_factorisation_and_3m_product_accuracy():
     ssf, ssf_want = np.abs(rho) ** 2, np.abs(want) ** 2
     assert np.abs(rho - want).max() < 1e-10                        # |rho| is O(sqrt(N)) ~ 60
     np.testing.assert_allclose(ssf[ssf_want > 1.0], ssf_want[ssf_want > 1.0], rtol=1e-10)
+
+
+def test_sq_dmma_plan_fuzz():
+    """mdh_sq_plan on 80 random wavevector sets (boxes, spheres, random subsets, nz ranges of
+    up to 25 tiles): every wavevector exactly once, pairing rule kept, block shape legal."""
+    from mdhelper_b200 import _lib
+    rng = np.random.default_rng(123)
+    for _ in range(80):
+        nx, ny, nz = (int(v) for v in rng.integers(1, 30, 3))
+        if rng.random() < 0.3:
+            nz = int(rng.integers(1, 200))
+        pts = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz),
+                                   indexing="ij"), -1).reshape(-1, 3)
+        mode = rng.integers(0, 3)
+        if mode == 0:
+            pts = pts[rng.choice(len(pts), int(rng.integers(1, len(pts) + 1)), replace=False)]
+        elif mode == 1:
+            radius = rng.uniform(1, max(nx, ny, nz))
+            pts = pts[(pts ** 2).sum(1) <= radius * radius]
+        plan = _lib.sq_plan(pts)
+        assert (plan["coverage"] == 1).all()
+        assert plan["pair_rule_violations"] == 0
+        assert 1 <= plan["warps_per_block"] <= 14 and plan["tiles"] * 64 >= len(pts)
