@@ -7,36 +7,43 @@ bench.py -- hot-path benchmark (contract: one JSON line on stdout from rank 0).
            --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference --steps K --warmup W      # CPU reference arm
 
-Workload (BASELINE.json configs[1], SURVEY.md section 8(d) "cfg2"): two-group
-cation-anion partial RDF of a 20,000-ion electrolyte, n_bins=201, range (0, 14.5),
-2,000 synthetic frames per GPU.  One "step" = one batch of ``--frames-per-step``
-frames (default 200) through the pair-histogram hot path.
+Headline workload (BASELINE.json configs[1], SURVEY.md section 8(d) "cfg2"): two-group
+cation-anion partial RDF of a 20,000-ion electrolyte, n_bins=201, range (0, 14.5), 2,000
+synthetic frames.  One "step" = one pass of the pair-histogram hot path over the whole
+2,000-frame trajectory (ten C-ABI calls of 200 frames); under torchrun every rank brings
+its own trajectory (weak scaling).
 
-* ``value``      pairs binned / s, coordinates already resident in HBM, device time
-                 (CUDA events on the launching stream), max over ranks.
+* ``value``      pairs binned / s, coordinates already resident in HBM, device time (CUDA
+                 events on the launching stream), max over ranks.
 * ``e2e``        the same metric through the public class
-                 ``RadialDistributionFunction(cations, anions).run(start, stop)``
-                 from pinned HOST memory (H2D of every frame and D2H of the
-                 counts inside the timed region).
+                 ``RadialDistributionFunction(cations, anions).run()`` from pinned HOST
+                 memory (H2D of every frame and D2H of the counts inside the timed region).
 * ``roofline``   the kernel that runs by default is the fp32-filter pair kernel
                  (rdf_filter.cu: counts identical to the reference's fp64 arithmetic,
                  uncertain pairs re-evaluated in fp64): pair evaluations/s x 16 FP32
-                 operations per evaluation over the measured packed-FP32 rate x SM
-                 count x the SM clock sampled during the run; beside it
-                 ``fp64_pipe_equivalent_frac``, the same rate against the bound of a
-                 kernel that executes the reference's 21 FP64 instructions per pair.
-                 ``--arith off`` benches that kernel (FP64-pipe roofline).  (Neither
-                 HBM- nor tensor-bound; the HBM figure is reported for the record.)
+                 operations per evaluation over the measured packed-FP32 rate x SM count x
+                 the SM clock sampled during the run; beside it
+                 ``fp64_pipe_equivalent_frac``, the same rate against the bound of a kernel
+                 that executes the reference's 21 FP64 instructions per pair.  ``--arith
+                 off`` benches that kernel (FP64-pipe roofline).
 * ``cpu_baseline`` the restated reference CPU path (oracle/: C distances + real
-                 numpy.histogram), serial and frame-parallel over all host cores,
-                 on a bounded sample of the same frames.
-* ``secondary``  the S(q) half of the metric: frames/s of the direct-sum structure
-                 factor for N=50,000, N_q=2,446 (configs[3]) with its own roofline
-                 and CPU baseline.
+                 numpy.histogram), serial and frame-parallel over all host cores, on a
+                 bounded sample of the same frames.
+* ``secondary``  the S(q) half of BASELINE's metric: frames/s of the direct-sum structure
+                 factor for N=50,000, N_q=2,446 (configs[3]; step = its 1,000 frames) with
+                 its own roofline, e2e and CPU baseline.  ``--impl reference`` carries the
+                 CPU S(q) rate in the same place.
+* ``strong``     the named configurations at their named scale, STRONG scaling: a fixed
+                 frame list -- cfg4: 1,000 frames of S(q); cfg3: 1,000 frames of the cut-off
+                 RDF of 500,000 particles; cfg5: 500 frames of the combined RDF + S(q) pass
+                 over 1,000,000 beads -- through ``run()`` / ``CombinedAnalysis.run()``,
+                 split over the ranks as the reference splits its frame list
+                 (base.py:433-441), host memory -> results.  Under torchrun rank 0 then
+                 recomputes the whole span alone and compares (``multi_gpu_parity``:
+                 integer counts identical, S(q) within 1e-12 relative).
 
-Multi-GPU: frames shard over ranks (weak scaling: every rank processes its own
-2,000-frame trajectory), no data-path collective; one NCCL all-reduce of the
-int64 counts at the end, inside the timed region.
+Multi-GPU: frames shard over ranks, no data-path collective; one NCCL all-reduce of the
+accumulators at the end, inside the timed region.
 """
 
 import argparse
@@ -53,8 +60,12 @@ import numpy as np
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-CFG2 = dict(n_ions=20_000, n_frames=2_000, n_bins=201, range=(0.0, 14.5), seed=20260002)
-CFG4 = dict(n=50_000, n_frames=1_000, n_points=32, n_max=16, seed=20260004)
+CFG2 = dict(n_ions=20_000, n_frames=2_000, n_bins=201, range=(0.0, 14.5), seed=20260002,
+            call_frames=200)
+CFG3 = dict(n=500_000, n_frames=1_000, n_bins=100, range=(0.0, 2.5), seed=20260003, ring=32)
+CFG4 = dict(n=50_000, n_frames=1_000, n_points=32, n_max=16, seed=20260004, call_frames=125)
+CFG5 = dict(n_chains=10_000, chain=100, n_frames=500, n_bins=100, range=(0.0, 2.5),
+            n_points=32, n_max=16, seed=20260005, ring=16)
 FP64_OPS_PER_PAIR = 21       # FP64-pipe instructions per pair evaluation
 FP32_OPS_PER_PAIR = 16       # FP32 instructions per pair of the filter
                              # kernel (3 sub, 3 fma, 3 sub, 3 fma, mul + 2 fma, 1 fma)
@@ -67,17 +78,21 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=200)
-    ap.add_argument("--sq-frames-per-step", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--strong", default="cfg4,cfg3,cfg5",
+                    help="comma-separated strong-scaling workloads to run")
+    ap.add_argument("--strong-reps", type=int, default=3)
+    ap.add_argument("--strong-only", action="store_true",
+                    help="skip the headline and the secondary; only the strong passes")
     ap.add_argument("--hist", default="auto")
     ap.add_argument("--sq-kernel", default="lattice_dmma",
                     choices=["lattice_dmma", "lattice_fp64"],
                     help="lattice_dmma: FP64 matrix unit (default); lattice_fp64: scalar DFMA")
     ap.add_argument("--arith", default="auto", choices=["auto", "off"],
                     help="auto: fp32 filter + exact fp64 re-evaluation; off: fp64 for "
-                         "every pair (the round-1 kernel)")
+                         "every pair")
     return ap.parse_args()
 
 
@@ -150,24 +165,33 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def profiled_traffic(kernel_tag, frames_in_capture, frames_per_launch):
+def profiled_traffic(kernel_tag, frames_per_launch):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full
-    capture (profiles/r01_<tag>_metrics.csv), scaled from the capture's frame count to
-    this run's (the kernel streams every coordinate once, so traffic is linear in
-    frames).  None if the profile is missing."""
-    p = ROOT / "profiles" / f"r01_{kernel_tag}_metrics.csv"
-    if not p.exists():
-        return None
+    capture (profiles/rNN_<tag>_metrics.csv, newest round first; the capture's frame count
+    is in profiles/captures.json, default 20 / 128), scaled to this run's frames per
+    launch (the kernel streams every coordinate once, so traffic is linear in frames).
+    None if no profile is committed."""
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = 0.0
+    frames_in = {"filter": 20, "pair": 20, "sq": 128}
     try:
-        for line in p.read_text().splitlines():
-            f = line.split(",")
-            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(f[2]) * unit[f[1]]
-    except (ValueError, KeyError, IndexError):
-        return None
-    return tot * frames_per_launch / frames_in_capture
+        frames_in.update(json.loads((ROOT / "profiles" / "captures.json").read_text()))
+    except (OSError, ValueError):
+        pass
+    for rnd in ("r02", "r01"):
+        p = ROOT / "profiles" / f"{rnd}_{kernel_tag}_metrics.csv"
+        if not p.exists():
+            continue
+        tot = 0.0
+        try:
+            for line in p.read_text().splitlines():
+                f = line.split(",")
+                if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(f[2]) * unit[f[1]]
+        except (ValueError, KeyError, IndexError):
+            continue
+        key = f"{rnd}_{kernel_tag}" if f"{rnd}_{kernel_tag}" in frames_in else kernel_tag
+        return tot * frames_per_launch / frames_in[key], p.name
+    return None, None
 
 
 def measured_peaks():
@@ -219,9 +243,13 @@ def _cpu_rdf_frame(f):
     from oracle import reference_port as rp
     u, cat, an = _CPU_STATE["u"]
     ts = u.trajectory[int(f)]
-    # mirrors _single_frame_parallel (structure.py:793-835): counts || volume
+    # mirrors _single_frame_parallel (structure.py:793-835): counts || volume.  method=None:
+    # the port chooses brute force / grid search by MDAnalysis' own rule (SURVEY.md
+    # Appendix A item 2: grid search from 1e8 pairs up); with r_max = 14.5 in a 29.24 box a
+    # grid has two cells per axis, which the restated grid search does not cover -- it then
+    # evaluates all pairs, like a two-cell grid would.
     c = rp.radial_histogram(cat.positions, an.positions, CFG2["n_bins"], CFG2["range"],
-                            ts.dimensions, method="bruteforce")
+                            ts.dimensions, method=None)
     return np.concatenate((c, [ts.volume]))
 
 
@@ -239,9 +267,9 @@ def cpu_rdf(frames, n_jobs):
     return float(tot[:-1].sum()) / dt, dt, tot[:-1].astype(np.int64)
 
 
-def cpu_sq(u, wavevectors, n_frames, n_threads):
+def cpu_sq(coords, wavevectors, n_frames, n_threads):
     from oracle import reference_port as rp
-    pos = [u.trajectory.coordinates[f].astype(np.float64) for f in range(n_frames)]
+    pos = [coords[f].astype(np.float64) for f in range(n_frames)]
     rp.delta_fourier_transform_sum(wavevectors[:64], pos[0][:1000], n_threads)   # warm-up
     t0 = time.perf_counter()
     for p in pos:
@@ -257,6 +285,18 @@ def make_cpu_sample(n_frames):
                                             pinned=False)
 
 
+def cfg4_wavevectors():
+    """The cfg4 wavevector set (first-octant lattice, |q| <= 2 pi 16 / L) without a GPU."""
+    from mdhelper_b200 import synthetic
+    L = float(synthetic.box_edge(CFG4["n"], 0.8))
+    idx = np.arange(CFG4["n_points"])
+    g = 2 * np.pi * idx / np.float32(L)
+    ii, jj, kk = np.meshgrid(idx, idx, idx, indexing="ij")
+    n = np.stack((jj, ii, kk), axis=-1).reshape(-1, 3)
+    wv = np.stack((g[n[:, 0]], g[n[:, 1]], g[n[:, 2]]), axis=-1)
+    return wv[np.linalg.norm(wv, axis=1) <= 2 * np.pi * CFG4["n_max"] / L]
+
+
 # ---------------------------------------------------------------------------------
 # reference arm
 # ---------------------------------------------------------------------------------
@@ -266,6 +306,7 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle
+    from mdhelper_b200 import synthetic
     oracle.build()
     cores = len(os.sched_getaffinity(0))
     fps = cores                                     # one frame per core per step
@@ -281,20 +322,34 @@ def run_reference(args):
         binned += int(c.sum())
     dt = time.perf_counter() - t0
     value = binned / dt
-    sample = (f"{fps} frames per step ({fps * args.steps} of the workload's 2,000), "
-              f"multiprocessing fork pool of {cores} processes over frames "
+    sample = (f"each step = {fps} frames of the workload's 2,000 ({fps * args.steps} in "
+              f"all), multiprocessing fork pool of {cores} processes over frames "
               "(mirrors base.py:477-501)")
+    # the S(q) half of the metric on the same cores: the restated numba kernel
+    # (accelerated.py:124-165, prange over wavevectors) on 3 cfg4 frames
+    secondary = None
+    if not args.no_secondary:
+        pos, _, _ = synthetic.fluid_positions(CFG4["n"], 3, seed=CFG4["seed"], pinned=False)
+        wv = cfg4_wavevectors()
+        v, dts = cpu_sq(pos, wv, 3, cores)
+        secondary = {"metric": "sq_frames_per_s", "value": v, "unit": "frames/s",
+                     "config": sq_config(len(wv)),
+                     "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores,
+                                      "kind": "port",
+                                      "sample": f"3 of the workload's 1,000 frames in {dts:.1f} s, "
+                                                f"{cores} OpenMP threads over wavevectors"}}
     line = {
         "impl": "reference", "metric": "rdf_pairs_binned_per_s", "value": value,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(fps),
+        "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "secondary": secondary,
         "note": "restated reference CPU path: MDAnalysis is not installable here, so "
                 "capped_distance is the C restatement in oracle/ feeding the real "
                 "numpy.histogram",
@@ -302,26 +357,33 @@ def run_reference(args):
     emit(line)
 
 
-def prewarm(step, ctx, seconds=0.75):
+def prewarm(step, sync, seconds=0.75):
     """Untimed: run steps until `seconds` of wall time have passed, so the timed
     region starts with the SM clocks already raised."""
     t0 = time.perf_counter()
     s = 0
     while time.perf_counter() - t0 < seconds:
         step(s)
-        ctx.sync()
+        sync()
         s += 1
 
 
-def workload_config(frames_per_step):
+def workload_config():
+    """Identical in both arms (how a step is batched or sampled is not part of it)."""
     return {"workload": "cfg2: two-group cation-anion partial RDF, 20,000-ion electrolyte "
                         "(10,000 x 10,000 ordered pairs per frame), n_bins=201, "
                         "range=(0, 14.5), L=29.2402, 2,000 synthetic frames per GPU",
-            "frames_per_step": frames_per_step,
             "pairs_per_frame": 100_000_000,
-            "cache": "inputs larger than L2: 480 MB of coordinates cycle through HBM, "
-                     "each step reads a different 24 MB batch",
+            "cache": "inputs larger than L2: every step streams the 480 MB trajectory "
+                     "through the kernels once",
             "parallelism": "frames sharded over GPUs, one all-reduce at the end"}
+
+
+def sq_config(n_q):
+    return {"workload": f"cfg4: direct-sum S(q), N=50,000, n_points=32, q_max=2*pi*16/L -> "
+                        f"N_q={n_q}, mode=None, form=exp, fp64, 1,000 synthetic frames per GPU",
+            "terms_per_frame": CFG4["n"] * n_q,
+            "cache": "inputs larger than L2: every step streams the 600 MB trajectory once"}
 
 
 # ---------------------------------------------------------------------------------
@@ -336,8 +398,7 @@ def run_ours(args):
 
     # ---- CPU baselines first (fork pool before any CUDA context exists) ----
     cpu = None
-    cpu_sq_res = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.strong_only:
         import oracle
         oracle.build()
         make_cpu_sample(2 * cores)
@@ -354,11 +415,42 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mdhelper_b200 import affinity
+    # each rank next to its GPU before any trajectory buffer is allocated
+    bound = affinity.bind_to_device(local, world, local) if world > 1 else None
+
+    line = {}
+    if not args.strong_only:
+        line = bench_rdf(args, rank, world, local, cpu, dist, torch)
+        if not args.no_secondary:
+            sec = bench_sq(args, rank, world, local, cores, dist, torch)
+            if rank == 0:
+                line["secondary"] = sec
+    if not args.no_strong:
+        strong = {}
+        for which in [w for w in args.strong.split(",") if w]:
+            res = bench_strong(which, args, rank, world, local, dist, torch)
+            if rank == 0:
+                strong[which] = res
+        if rank == 0:
+            line["strong"] = strong
+    if rank == 0:
+        if args.strong_only:
+            line = dict({"metric": "strong_scaling_passes", "n_gpus": world}, **line)
+        if bound is not None:
+            line["affinity"] = bound
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_rdf(args, rank, world, local, cpu, dist, torch):
     from mdhelper_b200 import _lib, synthetic
     from mdhelper_b200.analysis._binning import squared_thresholds
-    from mdhelper_b200.analysis.structure import RadialDistributionFunction, StructureFactor
+    from mdhelper_b200.analysis.structure import RadialDistributionFunction
+    from mdhelper_b200.universe import SyntheticUniverse
 
-    K, W, fps = args.steps, args.warmup, args.frames_per_step
+    K, W, cf = args.steps, args.warmup, CFG2["call_frames"]
     n_frames = CFG2["n_frames"]
     u, cat, an = synthetic.electrolyte(CFG2["n_ions"], n_frames, seed=CFG2["seed"] + 1000 * rank)
     n1, n2, N = cat.n_atoms, an.n_atoms, CFG2["n_ions"]
@@ -374,12 +466,14 @@ def run_ours(args):
     ctx.rdf_configure(n1, n2, False, thr, *CFG2["range"], hist=args.hist)
     base = dev.data_ptr()
 
-    def step(s):
-        f0 = (s * fps) % n_frames
-        nf = min(fps, n_frames - f0)
+    def call(f0):
+        nf = min(cf, n_frames - f0)
         ctx.rdf_accumulate(base + 4 * 3 * N * f0, 3 * N, base + 4 * 3 * (N * f0 + n1), 3 * N,
                            boxes[f0:f0 + nf], nf, device=True)
         return nf
+
+    def step(_s):
+        return sum(call(f0) for f0 in range(0, n_frames, cf))
 
     # the clock sampler starts first: nvidia-smi's own start-up (NVML init) must be
     # over before the timed region; only samples inside [wall0, wall1] are used
@@ -389,7 +483,7 @@ def run_ours(args):
         sampler.wait_ready()
     if world > 1:
         dist.barrier()
-    prewarm(step, ctx, 1.5)                   # bring the clocks up (untimed, on top of W)
+    prewarm(lambda s: call((s * cf) % n_frames), ctx.sync, 1.5)   # clocks up (untimed)
     for s in range(W):
         step(s)
     # the tail of the timed region once, untimed: the first fetch -> device copy ->
@@ -408,28 +502,15 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
     ev0.record()
-    frames_done, kernel_ms = 0, 0.0
-    dbg = os.environ.get("MDH_BENCH_DEBUG")
-    dbg_ev, dbg_host = [], []
+    frames_done = 0
     for s in range(W, W + K):
-        if dbg:
-            e = torch.cuda.Event(enable_timing=True); e.record(); dbg_ev.append(e)
-            dbg_host.append(time.perf_counter())
         frames_done += step(s)
-    if dbg:
-        e = torch.cuda.Event(enable_timing=True); e.record(); dbg_ev.append(e)
-        dbg_host.append(time.perf_counter())
     counts = torch.from_numpy(ctx.rdf_fetch()).cuda()
     if world > 1:
         dist.all_reduce(counts)
     ev1.record()
     torch.cuda.synchronize()
     wall1 = time.time()
-    if dbg:
-        print("per-step GPU ms:", [round(a.elapsed_time(b), 2) for a, b in
-                                   zip(dbg_ev[:-1], dbg_ev[1:])], file=sys.stderr)
-        print("per-step host enqueue ms:", [round(1e3 * (b - a), 2) for a, b in
-                                            zip(dbg_host[:-1], dbg_host[1:])], file=sys.stderr)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -445,50 +526,43 @@ def run_ours(args):
     kern_ms = kern_total_ms / max(kern_calls, 1)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     value = binned_total / (ms * 1e-3)
+    del dev
+    ctx.close()
 
     # ---- e2e: public class, pinned host memory, H2D + D2H inside the timed region ----
-    rdf = RadialDistributionFunction(cat, an, n_bins=CFG2["n_bins"], range=CFG2["range"],
-                                     verbose=False, batch_frames=fps, hist=args.hist,
-                                     arith=args.arith)
     # weak scaling like `value`: run() shards the frames it is given over the ranks
-    # (np.array_split), so a step hands it world * fps frames -- fps per GPU, each rank
-    # reading its own trajectory -- and the counts come back summed over the ranks
-    span = fps * world
-    for s in range(W):
-        f0 = (s * span) % n_frames
-        rdf.run(start=f0, stop=min(n_frames, f0 + span))
+    # (np.array_split), so every rank exposes a trajectory of world * 2,000 frames whose
+    # own share is its 2,000 local frames, and the counts come back summed over the ranks
+    ue = SyntheticUniverse(coords, u.trajectory.unitcells[0], n_frames=world * n_frames)
+    cat_e, an_e = ue.select(slice(0, n1)), ue.select(slice(n1, N))
+    rdf = RadialDistributionFunction(cat_e, an_e, n_bins=CFG2["n_bins"], range=CFG2["range"],
+                                     verbose=False, batch_frames=cf, hist=args.hist,
+                                     arith=args.arith)
+    for s in range(max(1, min(W, 2))):
+        rdf.run()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_binned = 0
-    for s in range(W, W + K):
-        f0 = (s * span) % n_frames
-        rdf.run(start=f0, stop=min(n_frames, f0 + span))
+    for s in range(K):
+        rdf.run()
         e2e_binned += int(rdf.results.counts.sum())       # already summed over ranks
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = e2e_binned / float(e2e_s.item())
-
-    # ---- secondary: S(q), cfg4 ----
-    secondary = None
-    if not args.no_secondary:
-        secondary = bench_sq(args, rank, world, local, cores, dist, torch)
-
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peaks = measured_peaks()
     sm_mhz = clocks["sm_mhz"] or clocks.get("sm_max_mhz") or 1965.0
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
     fp64_peak = peaks["fp64_per_clk_sm"] * n_sm * sm_mhz * 1e6        # instr/s
     fp32_peak = peaks["fp32_per_clk_sm"] * n_sm * sm_mhz * 1e6        # FP32 lanes/s
-    evals_per_launch = fps * n1 * n2
-    alg_bytes = fps * (n1 + n2) * 16 + CFG2["n_bins"] * 8            # float4 in, counts out
+    evals_per_launch = cf * n1 * n2
+    alg_bytes = cf * (n1 + n2) * 16 + CFG2["n_bins"] * 8            # float4 in, counts out
     hbm = {"achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9,
            "peak_gbs": peaks["hbm_gbs"], "source": peaks["hbm_source"],
            "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
@@ -497,13 +571,14 @@ def run_ours(args):
         # the kernel that runs: fp32 filter (packed FFMA2/FADD2 on the FP32 pipe);
         # about 1 pair in 1,500 is re-evaluated in fp64 (counted in fstats)
         achieved = evals_per_launch * FP32_OPS_PER_PAIR / (kern_ms * 1e-3)
+        traffic, tfile = profiled_traffic("filter", cf)
         roofline = {
             "kernel": "rdf_filter_kernel", "bound": "fp32_pipe",
             "achieved": achieved / 1e9, "peak": fp32_peak / 1e9, "unit": "Ginstr/s",
             "frac": achieved / fp32_peak,
-            "traffic": profiled_traffic("filter", 20, fps),
-            "traffic_note": "dram__bytes_read+write of profiles/r01_filter_metrics.csv (a "
-                            "20-frame launch) scaled to this launch's frames; bytes",
+            "traffic": traffic,
+            "traffic_note": f"dram__bytes_read+write of profiles/{tfile} scaled to this "
+                            "launch's frames; bytes",
             "per_unit": f"{FP32_OPS_PER_PAIR} FP32 operations per pair evaluation "
                         "(minimum image, squared distance, bin coordinate; issued as "
                         "packed f32x2 instructions)",
@@ -521,13 +596,14 @@ def run_ours(args):
             "hbm": hbm,
         }
     else:
+        traffic, tfile = profiled_traffic("pair", cf)
         roofline = {
             "kernel": "rdf_allpairs_kernel", "bound": "fp64_pipe",
             "achieved": fp64_equiv / 1e9, "peak": fp64_peak / 1e9, "unit": "Ginstr/s",
             "frac": fp64_equiv / fp64_peak,
-            "traffic": profiled_traffic("pair", 20, fps),
-            "traffic_note": "dram__bytes_read+write of profiles/r01_pair_metrics.csv (a "
-                            "20-frame launch) scaled to this launch's frames; bytes",
+            "traffic": traffic,
+            "traffic_note": f"dram__bytes_read+write of profiles/{tfile} scaled to this "
+                            "launch's frames; bytes",
             "per_unit": f"{FP64_OPS_PER_PAIR} FP64-pipe instructions per pair evaluation "
                         "(no FMA fusion allowed)",
             "units_per_launch": evals_per_launch, "launch_ms": kern_ms,
@@ -535,56 +611,57 @@ def run_ours(args):
                            f"instr/clk/SM x {n_sm} SMs x {sm_mhz:.0f} MHz (sampled)",
             "hbm": hbm,
         }
-    line = {
+    return {
         "metric": "rdf_pairs_binned_per_s", "value": value, "unit": "pairs/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(fps),
-        "pairs_evaluated_per_s": evals_local * world / (ms * 1e-3) * (K / (K + 0.0)),
+        "config": workload_config(),
+        "step": f"one pass over the 2,000 frames: {n_frames // cf} C-ABI calls of {cf} frames",
+        "pairs_evaluated_per_s": evals_local * world / (ms * 1e-3),
         "frames_per_s": frames_done * world / (ms * 1e-3),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pairs/s",
-                "h2d_bytes_per_step": world * (fps * (n1 + n2) * 12 + fps * 48),
+                "h2d_bytes_per_step": world * (n_frames * (n1 + n2) * 12 + n_frames * 48),
                 "d2h_bytes_per_step": world * CFG2["n_bins"] * 8,
                 "api": "RadialDistributionFunction(cations, anions, n_bins=201, "
-                       "range=(0, 14.5)).run(start, stop) per step"},
+                       "range=(0, 14.5)).run() over the 2,000 frames per step"},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "secondary": secondary,
     }
-    emit(line)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def bench_sq(args, rank, world, local, cores, dist, torch):
-    """S(q) frames/s for cfg4 (N=50,000, N_q=2,446), device-resident and end to end."""
+    """S(q) frames/s for cfg4 (N=50,000, N_q=2,446, 1,000 frames per GPU), device-resident
+    and end to end; step = one pass over the 1,000 frames."""
     from mdhelper_b200 import _lib, synthetic
     from mdhelper_b200.analysis.structure import StructureFactor
-    K, W, fps = args.steps, args.warmup, args.sq_frames_per_step
-    ring = max(256, fps * world)                  # distinct frames (>= 154 MB > L2)
-    u = synthetic.lj_fluid(CFG4["n"], ring, seed=CFG4["seed"] + 1000 * rank)
+    from mdhelper_b200.universe import SyntheticUniverse
+    K, W, cf = args.steps, args.warmup, CFG4["call_frames"]
+    n_frames = CFG4["n_frames"]
+    u = synthetic.lj_fluid(CFG4["n"], n_frames, seed=CFG4["seed"] + 1000 * rank)
+    coords = u.trajectory.coordinates
     L = float(u.trajectory.unitcells[0, 0])
     q_max = 2 * np.pi * CFG4["n_max"] / L
-    sf = StructureFactor([u.atoms], n_points=CFG4["n_points"], q_max=q_max, verbose=False,
-                         batch_frames=fps, kernel=args.sq_kernel)
+    ue = SyntheticUniverse(coords, u.trajectory.unitcells[0], n_frames=world * n_frames)
+    sf = StructureFactor([ue.atoms], n_points=CFG4["n_points"], q_max=q_max, verbose=False,
+                         batch_frames=cf, kernel=args.sq_kernel)
     dmma = args.sq_kernel == "lattice_dmma"
     n_q = len(sf._wavenumbers)
     N = CFG4["n"]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v1, dt1 = cpu_sq(u, sf._wavevectors, 1, 1)
-        vp, dtp = cpu_sq(u, sf._wavevectors, 3, cores)
+        v1, dt1 = cpu_sq(coords, sf._wavevectors, 1, 1)
+        vp, dtp = cpu_sq(coords, sf._wavevectors, 3, cores)
         cpu = {"value": vp, "unit": "frames/s", "cores": cores, "kind": "port",
                "serial_value": v1,
                "sample": f"serial: 1 frame in {dt1:.1f} s; {cores} OpenMP threads over "
                          f"wavevectors: 3 frames in {dtp:.1f} s (C restatement of "
                          "accelerated.py:81-165)"}
 
-    dev = torch.from_numpy(u.trajectory.coordinates).cuda()
+    dev = torch.from_numpy(coords).cuda()
     ctx = _lib.Context(local)
     ctx.sq_configure(N, [0, N], sf._wavevectors, [(-1, -1)], lattice_n=sf._lattice_n,
                      lattice_b=sf._lattice_b, mode=args.sq_kernel)
@@ -592,13 +669,15 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
     tiling = ctx.sq_tiling()
     base = dev.data_ptr()
 
-    def step(s):
-        f0 = (s * fps) % ring
-        nf = min(fps, ring - f0)
+    def call(f0):
+        nf = min(cf, n_frames - f0)
         ctx.sq_accumulate(base + 4 * 3 * N * f0, 3 * N, nf, device=True)
         return nf
 
-    prewarm(step, ctx, 0.4)
+    def step(_s):
+        return sum(call(f0) for f0 in range(0, n_frames, cf))
+
+    prewarm(lambda s: call((s * cf) % n_frames), ctx.sync, 0.4)
     for s in range(W):
         step(s)
     warm = torch.from_numpy(ctx.sq_fetch()).cuda()
@@ -628,42 +707,43 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
     ms = float(ms.item())
     launches = ctx.launch_count() - l0
     _, _, kern_total_ms, kern_calls = ctx.kernel_time(reset=True)
-    kern_ms = kern_total_ms / max(kern_calls, 1) * (fps * K / max(frames, 1))
+    kern_ms = kern_total_ms / max(kern_calls, 1)
+    del dev
+    ctx.close()
 
-    span = fps * world                            # fps frames per GPU and step
-    for s in range(W):
-        f0 = (s * span) % ring
-        sf.run(start=f0, stop=min(ring, f0 + span))
+    for s in range(max(1, min(W, 2))):
+        sf.run()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_frames = 0
-    for s in range(W, W + K):
-        f0 = (s * span) % ring
-        sf.run(start=f0, stop=min(ring, f0 + span))
+    for s in range(K):
+        sf.run()
         e2e_frames += sf.n_frames                 # all ranks together
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
 
     peaks = measured_peaks()
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-    terms = fps * N * n_q
+    terms = cf * N * n_q
     achieved = terms * FP64_OPS_PER_TERM / (kern_ms * 1e-3)
     peak = peaks["fp64_per_clk_sm"] * n_sm * 1965e6
+    traffic, tfile = profiled_traffic("sq", cf)
     return {
         "metric": "sq_frames_per_s", "value": frames * world / (ms * 1e-3), "unit": "frames/s",
-        "config": {"workload": f"cfg4: direct-sum S(q), N=50,000, n_points=32, "
-                               f"q_max=2*pi*16/L -> N_q={n_q}, mode=None, form=exp, fp64",
-                   "frames_per_step": fps, "terms_per_frame": N * n_q,
-                   "cache": f"ring of {ring} distinct frames ({ring * N * 12 / 1e6:.0f} MB > L2)"},
+        "config": sq_config(n_q),
+        "step": f"one pass over the 1,000 frames: {n_frames // cf} C-ABI calls of {cf} frames",
         "ms_per_step": ms / K, "gpu_launches": launches,
         "e2e": {"value": e2e_frames / float(e2e_s.item()), "unit": "frames/s",
-                "h2d_bytes_per_step": world * fps * N * 12,
+                "h2d_bytes_per_step": world * n_frames * N * 12,
                 "d2h_bytes_per_step": world * n_q * 8,
-                "api": "StructureFactor([atoms], n_points=32, q_max=...).run(start, stop)"},
+                "api": "StructureFactor([atoms], n_points=32, q_max=...).run() over the "
+                       "1,000 frames per step"},
         # the DMMA kernel runs on the FP64 matrix unit: the contract's "tensor" bound, in
         # TFLOP/s (2 flop per FMA); the scalar kernel is bound by the FP64 FMA pipe
         "roofline": {"kernel": "sq_lattice_mma_kernel" if dmma else "sq_lattice_kernel<double>",
@@ -675,10 +755,9 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
                      "bound_note": ("fp64 matrix unit (mma.m8n8k4.f64 = SASS DMMA.8x8x4); "
                                     "algorithmic work = 4 fp64 FMA = 8 flop per (q, r) term")
                      if dmma else None,
-                     "traffic": profiled_traffic("sq", 128, fps),
-                     "traffic_note": "dram__bytes_read+write of profiles/r01_sq_metrics.csv "
-                                     "(a 128-frame launch) scaled to this launch's frames; "
-                                     "bytes",
+                     "traffic": traffic,
+                     "traffic_note": f"dram__bytes_read+write of profiles/{tfile} scaled to "
+                                     "this launch's frames; bytes",
                      "nominal_vs_reachable":
                          ("DMMA.8x8x4 sustains the nominal 63.6 FMA/clk/SM "
                           "(profiles/microbench3_r01.json); the (column group x nz tile) "
@@ -701,6 +780,131 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
                      / (peaks["sfu_per_clk_sm"] * n_sm * 1965e6)},
         "cpu_baseline": cpu,
     }
+
+
+# ---------------------------------------------------------------------------------
+# strong scaling: the named configurations at their named scale
+# ---------------------------------------------------------------------------------
+
+def bench_strong(which, args, rank, world, local, dist, torch):
+    """One named configuration, a FIXED frame list split over the ranks, through the public
+    classes from host memory.  Every rank builds the same seeded ring of distinct frames
+    (a ring may be cycled to bound host memory) and analyses its
+    block of the frame list (np.array_split, as base.py:433-441); afterwards rank 0
+    recomputes the whole list alone and compares."""
+    from mdhelper_b200 import synthetic
+    from mdhelper_b200.analysis import CombinedAnalysis
+    from mdhelper_b200.analysis.base import single_rank
+    from mdhelper_b200.analysis.structure import RadialDistributionFunction, StructureFactor
+    from mdhelper_b200.universe import SyntheticUniverse
+
+    def ring_universe(pos, L, n_frames, **kw):
+        return SyntheticUniverse(pos, np.array([L, L, L, 90, 90, 90], np.float32),
+                                 n_frames=n_frames, **kw)
+
+    rdf = sf = None
+    if which == "cfg4":
+        ring = 250
+        pos, L, keep = synthetic.fluid_positions(CFG4["n"], ring, seed=CFG4["seed"])
+        n_frames, n_part = CFG4["n_frames"], CFG4["n"]
+        u = ring_universe(pos, L, n_frames)
+        sf = StructureFactor([u.atoms], n_points=CFG4["n_points"],
+                             q_max=2 * np.pi * CFG4["n_max"] / float(L), verbose=False,
+                             kernel=args.sq_kernel)
+        name = ("cfg4: direct-sum S(q), 50,000 particles, N_q=2,446, 1,000 frames "
+                f"(ring of {ring} distinct frames)")
+    elif which == "cfg3":
+        ring = CFG3["ring"]
+        pos, L, keep = synthetic.fluid_positions(CFG3["n"], ring, seed=CFG3["seed"])
+        n_frames, n_part = CFG3["n_frames"], CFG3["n"]
+        u = ring_universe(pos, L, n_frames)
+        rdf = RadialDistributionFunction(u.atoms, n_bins=CFG3["n_bins"], range=CFG3["range"],
+                                         verbose=False, arith=args.arith)
+        name = ("cfg3: RDF with cut-off 2.5 (cell list), 500,000-particle LJ fluid, 1,000 "
+                f"frames (ring of {ring} distinct frames)")
+    elif which == "cfg5":
+        ring = CFG5["ring"]
+        um = synthetic.polymer_melt(CFG5["n_chains"], CFG5["chain"], ring, seed=CFG5["seed"])
+        pos, L = um.trajectory.coordinates, um.trajectory.unitcells[0, 0]
+        keep = um
+        n_frames, n_part = CFG5["n_frames"], CFG5["n_chains"] * CFG5["chain"]
+        chain = np.repeat(np.arange(CFG5["n_chains"]), CFG5["chain"])
+        u = ring_universe(pos, L, n_frames, resindices=chain, segindices=chain)
+        rdf = RadialDistributionFunction(u.atoms, n_bins=CFG5["n_bins"], range=CFG5["range"],
+                                         verbose=False, arith=args.arith)
+        sf = StructureFactor([u.atoms], n_points=CFG5["n_points"],
+                             q_max=2 * np.pi * CFG5["n_max"] / float(L), verbose=False,
+                             kernel=args.sq_kernel)
+        name = ("cfg5: combined RDF (cut-off 2.5) + S(q) (N_q=2,446) pass, 1,000,000-bead "
+                f"polymer melt, 500 frames (ring of {ring} distinct frames)")
+    else:
+        raise SystemExit(f"unknown strong workload {which}")
+
+    job = CombinedAnalysis(rdf, sf) if (rdf is not None and sf is not None) else (rdf or sf)
+
+    def one_pass():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        job.run()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+
+    one_pass()                                     # allocations, configuration, clocks
+    for a in (rdf, sf):
+        if a is not None:
+            a._ctx.kernel_time(reset=True)
+    times = [one_pass() for _ in range(max(1, args.strong_reps))]
+    best, mean = min(times), float(np.mean(times))
+    kern = {}
+    if rdf is not None:
+        kern["rdf_kernel_ms_rank0"] = rdf._ctx.kernel_time()[0] / len(times)
+        kern["rdf_pair_evaluations_rank0"] = rdf._pair_evaluations
+    if sf is not None:
+        kern["sq_kernel_ms_rank0"] = sf._ctx.kernel_time()[2] / len(times)
+    out = {"workload": name, "n_gpus": world, "frames": n_frames, "scaling": "strong",
+           "passes_timed": len(times), "e2e_s_mean": mean, "e2e_s_best": best,
+           "frames_per_s": n_frames / mean,
+           "h2d_bytes_per_pass": n_frames * n_part * 12,
+           "api": ("CombinedAnalysis(rdf, ssf).run()" if isinstance(job, CombinedAnalysis)
+                   else type(job).__name__ + "(...).run()") + " over the whole frame list, "
+                  "host memory -> results"}
+    if rdf is not None:
+        counts = rdf.results.counts.copy()
+        out["pairs_binned_per_s"] = float(counts.sum()) / mean
+        out["counts_sum"] = int(counts.sum())
+    if sf is not None:
+        ssf = sf.results.ssf.copy()
+    # ---- multi-GPU parity: rank 0 alone over the whole frame list ----
+    if world > 1:
+        ok = torch.ones(1, device="cuda")
+        if rank == 0:
+            with single_rank():
+                job.run()
+            good = True
+            if rdf is not None:
+                good = good and bool(np.array_equal(rdf.results.counts, counts))
+                out["parity_counts_equal"] = bool(np.array_equal(rdf.results.counts, counts))
+            if sf is not None:
+                rel = float(np.max(np.abs(sf.results.ssf - ssf)
+                                   / np.maximum(np.abs(sf.results.ssf), 1e-300)))
+                out["parity_ssf_max_rel"] = rel
+                good = good and rel <= 1e-12
+            out["multi_gpu_parity"] = good
+            ok[0] = 1.0 if good else 0.0
+        dist.broadcast(ok, 0)
+        if float(ok.item()) != 1.0:
+            raise SystemExit(f"multi-GPU parity FAILED for {which}: {out}")
+    else:
+        out["multi_gpu_parity"] = None           # one rank: nothing to compare
+    out.update(kern)
+    del job, rdf, sf, u, keep
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
 
 
 def emit(line: dict) -> None:

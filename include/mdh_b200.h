@@ -85,8 +85,7 @@ enum {
 enum {
     MDH_SQ_AUTO = 0,
     MDH_SQ_LATTICE_FP64 = 1,  /* q = n*b: per-axis phase factors, fp64 complex FMA */
-    MDH_SQ_LATTICE_SFU = 2,   /* q = n*b: 32-bit fixed-point phase, MUFU sin/cos,
-                                 fp64 accumulation (approximate: ~1e-6 abs/term) */
+    /* 2 is retired (a MUFU sin/cos variant that was never built) and is rejected */
     MDH_SQ_GENERAL_FP64 = 3,  /* arbitrary q: fp64 dot product + fp64 sincos     */
     MDH_SQ_LATTICE_FP32 = 4,  /* q = n*b: the FP64 scheme on the FP32 pipe
                                  (approximate: ~1e-7 relative per term)          */

@@ -24,8 +24,8 @@ MDH_HOST, MDH_DEVICE = 0, 1
 RDF_MODES = {"auto": 0, "allpairs": 1, "cells": 2}
 HIST_MODES = {"auto": 0, "warp_atomic": 1, "lane_private": 2}
 FILTER_MODES = {"auto": 0, "off": 1, "on": 2, "audit": 3}
-SQ_MODES = {"auto": 0, "lattice_fp64": 1, "lattice_sfu": 2, "general_fp64": 3,
-            "lattice_fp32": 4, "lattice_dmma": 5}
+SQ_MODES = {"auto": 0, "lattice_fp64": 1, "general_fp64": 3, "lattice_fp32": 4,
+            "lattice_dmma": 5}
 
 _i32, _i64, _f64 = ctypes.c_int, ctypes.c_int64, ctypes.c_double
 _p = ctypes.c_void_p

@@ -45,8 +45,34 @@ class Hash(dict):
             raise AttributeError(name) from None
 
 
+_SINGLE_RANK = False
+
+
+class single_rank:
+    """
+    Context manager: inside it the analyses ignore ``torch.distributed`` -- the calling
+    rank analyses every frame itself and no collective is issued.  Used to recompute a
+    multi-GPU result on one GPU for comparison (``bench.py``'s ``multi_gpu_parity``)::
+
+        with single_rank():
+            alone = RadialDistributionFunction(...).run()
+    """
+
+    def __enter__(self):
+        global _SINGLE_RANK
+        self._old, _SINGLE_RANK = _SINGLE_RANK, True
+        return self
+
+    def __exit__(self, *exc):
+        global _SINGLE_RANK
+        _SINGLE_RANK = self._old
+        return False
+
+
 def world():
     """``(rank, world_size)`` of the running job (``(0, 1)`` when not distributed)."""
+    if _SINGLE_RANK:
+        return 0, 1
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
@@ -82,6 +108,8 @@ def _memory_coordinates(trajectory):
     order; else ``None`` (frames are then read one by one through ``trajectory[i]``).
     """
     coords = getattr(trajectory, "coordinates", None)
+    if not isinstance(coords, np.ndarray) and hasattr(trajectory, "ring_coordinates"):
+        return None                           # addressed through _ring_coordinates
     if not isinstance(coords, np.ndarray):
         coords = getattr(trajectory, "coordinate_array", None)
         if getattr(trajectory, "stored_order", "fac") != "fac":
@@ -90,6 +118,33 @@ def _memory_coordinates(trajectory):
             and coords.shape[0] == len(trajectory):
         return coords
     return None
+
+
+def _is_contiguous(ix) -> bool:
+    """``ix`` is a non-empty run ``a, a+1, ..., b`` (permutations and duplicates are not)."""
+    ix = np.asarray(ix)
+    return bool(ix.size > 0 and ix[-1] - ix[0] + 1 == ix.size
+                and (ix.size == 1 or np.all(np.diff(ix) == 1)))
+
+
+def _ring_coordinates(trajectory):
+    """``(ring, period)`` of a :class:`mdhelper_b200.universe.RingTrajectory` (frame ``f``
+    is ``ring[f % period]``), else ``(None, 0)``."""
+    ring = getattr(trajectory, "ring_coordinates", None)
+    if isinstance(ring, np.ndarray) and ring.ndim == 3 and ring.shape[2] == 3:
+        return ring, int(trajectory.ring_period)
+    return None, 0
+
+
+def _runs_in_ring(frames: np.ndarray, step: int, period: int, max_frames: int):
+    """Cuts evenly spaced ``frames`` into runs of at most ``max_frames`` whose ring slots
+    ``f % period`` are evenly spaced too (no wrap inside a run): ``(first, count)`` pairs."""
+    i, n = 0, len(frames)
+    while i < n:
+        fit = (period - 1 - int(frames[i]) % period) // step + 1 if period else n
+        cnt = max(1, min(max_frames, n - i, fit))
+        yield i, cnt
+        i += cnt
 
 
 class Batch:
@@ -129,13 +184,14 @@ class FrameFeeder:
         self.batch_frames = max(1, int(batch_frames))
         self.positions_fn = positions_fn
         coords = _memory_coordinates(trajectory)
+        self._period = 0
+        if coords is None:
+            coords, self._period = _ring_coordinates(trajectory)
         steps = np.diff(self.frames)
         uniform = (len(self.frames) <= 1
                    or (steps[0] > 0 and bool(np.all(steps == steps[0]))))
         contiguous = all(
-            ix.size > 0 and ix[-1] - ix[0] + 1 == ix.size
-            and (ix.size == 1 or bool(np.all(np.diff(ix) == 1)))
-            for ix in self.index_sets
+            _is_contiguous(ix) for ix in self.index_sets
         )
         self.zero_copy = (
             positions_fn is None and uniform and contiguous
@@ -166,9 +222,11 @@ class FrameFeeder:
     def _iter_zero_copy(self):
         c = self._coords
         n = c.shape[1]
-        for b0 in range(0, len(self.frames), self.batch_frames):
-            fr = self.frames[b0:b0 + self.batch_frames]
-            ptrs = [c.ctypes.data + 4 * 3 * (int(fr[0]) * n + int(ix[0]))
+        for b0, cnt in _runs_in_ring(self.frames, self._step, self._period,
+                                     self.batch_frames):
+            fr = self.frames[b0:b0 + cnt]
+            first = int(fr[0]) % self._period if self._period else int(fr[0])
+            ptrs = [c.ctypes.data + 4 * 3 * (first * n + int(ix[0]))
                     for ix in self.index_sets]
             strides = [self._step * n * 3] * len(self.index_sets)
             yield Batch(len(fr), ptrs, strides, self._dims(fr), c)
@@ -383,6 +441,13 @@ class CombinedAnalysis:
         traj = analyses[0]._trajectory
         if any(a._trajectory is not traj for a in analyses):
             raise ValueError("The analyses must share one trajectory.")
+        for a in analyses:
+            # classes with their own frame loop (time-ordered ISF, chain unwrapping) cannot
+            # be fed through the frame-sharded _begin / _consume / _finish protocol
+            if (type(a).run is not GpuAnalysisBase.run
+                    or type(a)._process is not GpuAnalysisBase._process):
+                raise TypeError(f"{type(a).__name__} overrides run()/_process() and cannot "
+                                "be part of a CombinedAnalysis.")
         self.analyses = analyses
         self._trajectory = traj
         self._batch_frames = batch_frames
@@ -399,15 +464,17 @@ class CombinedAnalysis:
             a.n_local_frames = len(local)
         plans = [a._begin(local) for a in self.analyses]
         coords = _memory_coordinates(self._trajectory)
+        period = 0
+        if coords is None:
+            coords, period = _ring_coordinates(self._trajectory)
         d = np.diff(local)
         shared = (
             len(local) > 0 and isinstance(coords, np.ndarray)
             and coords.dtype == np.float32 and coords.ndim == 3
             and coords.flags.c_contiguous
             and (len(local) == 1 or (d[0] > 0 and bool(np.all(d == d[0]))))
-            and all(fn is None and all(
-                ix.size > 0 and ix[-1] - ix[0] + 1 == ix.size for ix in sets)
-                for sets, fn, _ in plans)
+            and all(fn is None and all(_is_contiguous(ix) for ix in sets)
+                    for sets, fn, _ in plans)
         )
         if not shared:
             for a, (sets, fn, bpf) in zip(self.analyses, plans):
@@ -424,10 +491,27 @@ class CombinedAnalysis:
             df = int(d[0]) if len(local) > 1 else 1
             bf = self._batch_frames or int(min(512, max(1, (128 << 20) // (12 * n))))
             cells = getattr(self._trajectory, "unitcells", None)
-            for b0 in range(0, len(local), bf):
-                fr = local[b0:b0 + bf]
-                host = torch.from_numpy(coords[int(fr[0]):int(fr[-1]) + 1:df])
-                dev = host.cuda(non_blocking=True)           # one upload for everyone
+            # uploads run on their own stream, one batch ahead of the kernels
+            compute = torch.cuda.current_stream()
+            copy = torch.cuda.Stream()
+
+            def upload(b0, cnt):
+                fr = local[b0:b0 + cnt]
+                first = int(fr[0]) % period if period else int(fr[0])
+                host = torch.from_numpy(coords[first:first + (cnt - 1) * df + 1:df])
+                with torch.cuda.stream(copy):
+                    dev = host.cuda(non_blocking=True)       # one upload for everyone
+                    ready = torch.cuda.Event()
+                    ready.record(copy)
+                return fr, dev, ready
+
+            runs = list(_runs_in_ring(local, df, period, bf))
+            nxt = upload(*runs[0])
+            for k in range(len(runs)):
+                fr, dev, ready = nxt
+                if k + 1 < len(runs):
+                    nxt = upload(*runs[k + 1])
+                compute.wait_event(ready)
                 if isinstance(cells, np.ndarray):
                     dims = np.ascontiguousarray(cells[fr], dtype=np.float32)
                 else:
@@ -435,11 +519,11 @@ class CombinedAnalysis:
                                     ).astype(np.float32)
                 for a, (sets, _, _) in zip(self.analyses, plans):
                     ptrs = [dev.data_ptr() + 12 * int(ix[0]) for ix in sets]
-                    # no keep-alive needed: the kernels are queued on torch's current
-                    # stream, so the caching allocator cannot hand `dev` out again
-                    # before they have run
                     a._consume(Batch(len(fr), ptrs, [3 * n] * len(sets), dims, None),
                                device=True)
+                # the kernels reading `dev` are queued on the compute stream: the caching
+                # allocator must not hand the block out again before they have run
+                dev.record_stream(compute)
             for a in self.analyses:
                 a._finish()
         for a in self.analyses:

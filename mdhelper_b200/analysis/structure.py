@@ -150,8 +150,10 @@ def radial_histogram(
     ctx = Context(dev)
     try:
         ctx.rdf_set_filter(arith)
-        # the same array twice: the kernels may use the pair symmetry (same counts)
-        ctx.rdf_configure(len(p1), len(p2), pos2 is pos1,
+        # the same array twice: the kernels may use the pair symmetry (same counts) --
+        # unless the exclusion blocks differ, i // e0 == j // e1 is not symmetric then
+        same = pos2 is pos1 and (exclusion is None or exclusion[0] == exclusion[1])
+        ctx.rdf_configure(len(p1), len(p2), same,
                           squared_thresholds(n_bins, range), range[0], range[1],
                           exclusion=exclusion, mode=mode, hist=hist)
         ctx.rdf_accumulate(p1, 3 * len(p1), p2, 3 * len(p2),
@@ -286,9 +288,12 @@ class RadialDistributionFunction(GpuAnalysisBase):
         ctx = self._context()
         n1 = _n_entities(self.ag1, self._groupings[0])
         n2 = _n_entities(self.ag2, self._groupings[1])
+        # one packed copy and the pair symmetry are only valid when the exclusion test
+        # i // e0 == j // e1 (structure.py:100-102) is symmetric as well
         same = (self.ag1 is self.ag2
                 or np.array_equal(self.ag1.ix, self.ag2.ix)) \
-            and self._groupings[0] == self._groupings[1]
+            and self._groupings[0] == self._groupings[1] \
+            and (not self._exclusion or self._exclusion[0] == self._exclusion[1])
         self._same = same
         ctx.rdf_set_filter(self._arith)
         if getattr(self, "_thresholds", None) is None:   # fixed per instance

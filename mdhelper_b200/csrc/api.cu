@@ -50,6 +50,23 @@ void DevBuf::release()
     cap = 0;
 }
 
+std::vector<int> mdh_plan_pieces(int n_frames, double bytes_per_frame)
+{
+    std::vector<int> out;
+    const double bpf = std::max(1.0, bytes_per_frame);
+    double want = 2e6;
+    int done = 0;
+    while (done < n_frames) {
+        int nf = (int)std::max(1.0, std::floor(want / bpf));
+        const int left = n_frames - done;
+        if (left < nf + nf / 2) nf = left;         // no short tail piece
+        out.push_back(nf);
+        done += nf;
+        want = std::min(32e6, want * 2.0);
+    }
+    return out;
+}
+
 int KernelTimer::begin(cudaStream_t s)
 {
     if (used == 512) {                       // ring full: fold what has been recorded
@@ -202,21 +219,9 @@ int mdh_ctx_destroy(mdh_ctx *c)
     RdfState &R = c->rdf;
     if (c->stager.copy) cudaStreamSynchronize(c->stager.copy);
     c->stager.destroy();
-    R.thr.release(); R.counts.release();
-    for (int i = 0; i < 2; ++i) { R.raw1[i].release(); R.raw2[i].release(); c->sq.raw[i].release(); }
-    R.pk1.release(); R.pk2.release(); R.boxes.release();
-    R.ext1.release(); R.ext2.release(); R.filt.release(); R.fstats.release();
-    for (auto &b : R.cell) b.release();
-    R.cell_pairs.release();
     if (R.h_boxes_pinned) cudaFreeHost(R.h_boxes_pinned);
     if (R.ev_boxes) cudaEventDestroy(R.ev_boxes);
-    SqState &S = c->sq;
-    S.qv.release(); S.items.release(); S.qidx.release(); S.d_pairs.release();
-    S.chunks.release(); S.tab.release(); S.rho.release(); S.ssf.release();
-    for (auto &k : c->com) { k.starts.release(); k.masses.release(); k.raw.release(); }
-    IsfState &I = c->isf;
-    I.rho_all.release(); I.window[0].release(); I.window[1].release(); I.vmap.release();
-    I.cisf.release(); I.iisf.release();
+    // every DevBuf of the state structs releases its memory in its destructor (delete c)
     c->t_rdf.destroy();
     c->t_sq.destroy();
     if (c->own_stream) cudaStreamDestroy(c->stream);

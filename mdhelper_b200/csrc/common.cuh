@@ -34,12 +34,19 @@ void mdh_set_error(const char *fmt, ...);
         }                                                                       \
     } while (0)
 
-// Device buffer that only ever grows; owned by the context.
+// Device buffer that only ever grows; owned by the context (freed with it: a buffer
+// added to a state struct cannot be forgotten in mdh_ctx_destroy).
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
     int reserve(size_t bytes);
     void release();
+    // take over another buffer's memory (this one must have been released)
+    void adopt(DevBuf &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -80,8 +87,10 @@ struct RdfState {
     DevBuf raw1[2], raw2[2];  // float[F][n][3] staging for host input, one per stager slot
     DevBuf pk1, pk2;       // float4[F][npad]
     DevBuf boxes;          // FrameBox[F]
-    DevBuf cell[10];       // cell-list scratch (grids, counts, starts, ranks, sorted, evals)
-    DevBuf cell_pairs;     // pair-interleaved copy of the sorted group-2 particles
+    DevBuf cell[10];       // cell-list scratch, layout in rdf_cells.cu
+    double cells_ws_mb = 48.0;   // working set of one group of frames (sort + pair kernel)
+    int cells_chunk = 8;         // cells per work item of the cell-pair kernel
+    int cells_ipt = 4;           // particles per lane of the cell-pair kernel (2 or 4)
     bool evals_dev_init = false;
     std::vector<FrameBox> h_boxes;
     FrameBox *h_boxes_pinned = nullptr;   // staging for the async box upload
@@ -195,6 +204,12 @@ struct HostStager {
     int retire(cudaStream_t compute, int slot);
     void destroy();
 };
+
+// Host batches are cut into pieces so that the copy of one piece (copy stream) overlaps the
+// kernels of the previous one.  The pieces grow geometrically: the first copy -- the only
+// one nothing can hide -- is short (~2 MB), later ones are long enough (up to ~32 MB) for
+// their kernels to run at full efficiency.
+std::vector<int> mdh_plan_pieces(int n_frames, double bytes_per_frame);
 
 struct mdh_ctx {
     int device = 0;

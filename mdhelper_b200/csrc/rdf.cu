@@ -222,7 +222,9 @@ int launch_allpairs_dyn(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl, b
 
 // ---- host side ------------------------------------------------------------------
 
-int rdf_cells_accumulate(mdh_ctx *c, int f0, int n_frames, bool use_filter);   // rdf_cells.cu
+int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const float *raw2,
+                         int64_t stride2, int f0, int n_frames, bool use_filter,
+                         double sqrt_err);                        // rdf_cells.cu
 static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const float *pos2,
                                 int64_t s2, int location, int f0, int n_frames, int mode);
 int rdf_filter_launch(mdh_ctx *c, const PairParams &P, dim3 grid, bool excl,
@@ -258,6 +260,9 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
     MDH_REQUIRE(thr[0] >= 0.0, MDH_EINVAL, "rdf: thresholds_sq[0] must be >= 0");
     MDH_REQUIRE((e1 > 0) == (e2 > 0) && e1 >= 0, MDH_EINVAL,
                 "rdf: exclusion sizes must both be positive or both zero");
+    MDH_REQUIRE(!same || e1 == e2, MDH_EINVAL,
+                "rdf: same_group needs equal exclusion block sizes (i/excl1 == j/excl2 is not "
+                "symmetric otherwise); pass the group twice with same_group = 0");
     MDH_REQUIRE(drop_axis >= -1 && drop_axis <= 2, MDH_EINVAL, "rdf: invalid drop_axis");
     MDH_REQUIRE(mode >= MDH_RDF_AUTO && mode <= MDH_RDF_CELLS, MDH_EINVAL,
                 "rdf: invalid mode");
@@ -272,6 +277,9 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
         if (const char *p = strstr(t, "fast=")) allow_fast = atoi(p + 5) != 0;
         if (const char *p = strstr(t, "filter=")) allow_filter = atoi(p + 7) != 0;
         if (const char *p = strstr(t, "occ=")) R.filter_occ = std::min(4, std::max(2, atoi(p + 4)));
+        if (const char *p = strstr(t, "cws=")) R.cells_ws_mb = std::max(1.0, atof(p + 4));
+        if (const char *p = strstr(t, "cchunk=")) R.cells_chunk = std::max(1, atoi(p + 7));
+        if (const char *p = strstr(t, "cipt=")) R.cells_ipt = atoi(p + 5) == 2 ? 2 : 4;
     }
     // measured on B200 (profiles/): per-warp shared-memory atomics beat the
     // lane-private byte counters at every bin count tried, and need less memory
@@ -378,6 +386,12 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
     MDH_REQUIRE(box != nullptr, MDH_EINVAL, "rdf: box is NULL");
     MDH_REQUIRE(location == MDH_HOST || location == MDH_DEVICE, MDH_EINVAL,
                 "rdf: invalid location");
+    MDH_REQUIRE(pos1 != nullptr && (R.same || pos2 != nullptr), MDH_EINVAL,
+                "rdf: coordinate pointer is NULL");
+    MDH_REQUIRE(s1 >= 3 * R.n1, MDH_EINVAL, "rdf: frame_stride (%lld) < 3*n (%lld)",
+                (long long)s1, (long long)(3 * R.n1));
+    MDH_REQUIRE(R.same || s2 >= 3 * R.n2, MDH_EINVAL, "rdf: frame_stride (%lld) < 3*n (%lld)",
+                (long long)s2, (long long)(3 * R.n2));
 
     // per-frame box: box_k and inv_k = (float)(1.0 / (double)box_k)  (Appendix A item 3)
     R.h_boxes.resize(n_frames);
@@ -418,23 +432,19 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
                               (double)R.n1 * (double)R.n2 >= 4e6 && R.drop_axis < 0;
         mode = cells_ok ? MDH_RDF_CELLS : MDH_RDF_ALLPAIRS;
     }
-    // Host input is cut into up to four pieces so that the copy of one piece (copy
-    // stream) overlaps the kernels of the previous one (compute stream).
-    int piece = n_frames;
+    // Host input is cut into pieces so that the copy of one piece (copy stream) overlaps
+    // the kernels of the previous one (compute stream).
     if (location == MDH_HOST) {
-        // pieces of at least ~12 MB: shorter ones cost more in kernel tails than the
-        // hidden copy time is worth
-        const double bytes = 12.0 * (double)(R.n1 + (R.same ? 0 : R.n2)) * n_frames;
-        const int n_pieces = (int)std::min(4.0, std::max(1.0, floor(bytes / 12e6)));
-        piece = (n_frames + n_pieces - 1) / n_pieces;
+        int f0 = 0;
+        for (int nf : mdh_plan_pieces(n_frames, 12.0 * (double)(R.n1 + (R.same ? 0 : R.n2)))) {
+            if (int rc = rdf_accumulate_piece(c, pos1 + (int64_t)f0 * s1, s1,
+                                              pos2 ? pos2 + (int64_t)f0 * s2 : nullptr, s2,
+                                              location, f0, nf, mode)) return rc;
+            f0 += nf;
+        }
+        return MDH_OK;
     }
-    for (int f0 = 0; f0 < n_frames; f0 += piece) {
-        const int nf = std::min(piece, n_frames - f0);
-        if (int rc = rdf_accumulate_piece(c, pos1 + (int64_t)f0 * s1, s1,
-                                          pos2 ? pos2 + (int64_t)f0 * s2 : nullptr, s2,
-                                          location, f0, nf, mode)) return rc;
-    }
-    return MDH_OK;
+    return rdf_accumulate_piece(c, pos1, s1, pos2, s2, location, 0, n_frames, mode);
 }
 
 // One piece of an accumulate call: frames [f0, f0 + n_frames) of the batch whose boxes
@@ -458,6 +468,19 @@ static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const
                                           R.raw2[slot], R.pk2, nullptr, true)) return rc;
         if (int rc = c->stager.publish(c->stream, slot)) return rc;
     }
+    if (mode == MDH_RDF_CELLS) {
+        // the cell-list pipeline sorts straight from the raw coordinates (rdf_cells.cu)
+        const bool host = location == MDH_HOST;
+        if (int rc = c->t_rdf.begin(c->stream)) return rc;
+        if (int rc = rdf_cells_accumulate(
+                c, host ? R.raw1[slot].as<float>() : pos1, host ? 3 * R.n1 : s1,
+                R.same ? nullptr : (host ? R.raw2[slot].as<float>() : pos2),
+                host ? 3 * R.n2 : s2, f0, n_frames, use_filter, g_sqrt_err_cached)) return rc;
+        if (int rc = c->t_rdf.end(c->stream)) return rc;
+        if (host)
+            if (int rc = c->stager.retire(c->stream, slot)) return rc;
+        return MDH_OK;
+    }
     if (int rc = rdf_upload_group(c, pos1, s1, location, R.n1, pad1, R.excl1, n_frames,
                                   R.raw1[slot], R.pk1, use_filter ? &R.ext1 : nullptr, false))
         return rc;
@@ -473,9 +496,7 @@ static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const
 
     if (int rc = c->t_rdf.begin(c->stream)) return rc;
 
-    if (mode == MDH_RDF_CELLS) {
-        if (int rc = rdf_cells_accumulate(c, f0, n_frames, use_filter)) return rc;
-    } else {
+    {
         PairParams P;
         P.p1 = R.pk1.as<float4>();
         P.p2 = R.same ? P.p1 : R.pk2.as<float4>();

@@ -1,19 +1,47 @@
 // rdf_cells.cu -- cell-list variant of the pair histogram (cut-off runs).
 //
-// Same per-pair arithmetic and binning as rdf.cu (rdf_device.cuh); only the set
-// of candidate pairs shrinks: each frame's particles are counting-sorted into
-// cells of edge >= r_cut*(1+1e-5) and every i visits the 27 surrounding cells
-// of the j group.  This is the role MDAnalysis' grid search ("nsgrid") plays
-// behind capped_distance for the reference (call site
-// /root/reference/src/mdhelper/analysis/structure.py:93-96; SURVEY.md Appendix A
-// items 2 and 4).  Counts are identical to the all-pairs kernel by construction:
-// a pair closer than r_cut always lies in adjacent cells, and every other
-// candidate falls above the last threshold and is not counted.
+// Same per-pair arithmetic and binning as rdf.cu / rdf_filter.cu (rdf_device.cuh); only
+// the set of candidate pairs shrinks: each frame's particles are counting-sorted into
+// cells of edge >= r_cut*(1+1e-5) and every cell meets the 27 surrounding cells of the j
+// group.  This is the role MDAnalysis' grid search ("nsgrid") plays behind
+// capped_distance for the reference (call site
+// /root/reference/src/mdhelper/analysis/structure.py:93-96; SURVEY.md Appendix A items 2
+// and 4).  Counts are identical to the all-pairs kernels by construction: a pair closer
+// than r_cut always lies in adjacent cells, and every other candidate falls above the
+// last threshold and is not counted.
 //
-// Ordered pairs are enumerated directly (i over group 1, j over group 2, both
-// orders and the self pair when the groups coincide), as the reference counts them.
+// Pipeline per group of frames (sized so that its working set stays in L2):
+//   cells_bin_kernel      raw float[n][3] -> (cell, rank-in-cell) + per-cell counts +
+//                         coordinate extents (for the fp32 filter's error bound)
+//   cells_scan_kernel     exclusive scan of the counts, one block per (frame, group);
+//                         also builds the frame's FrameFilter (no extra launch)
+//   cells_scatter_kernel  raw -> cell-sorted float4 (x, y, z, exclusion block id)
+//   rdf_cellpair_kernel   the pair kernel (below); frames it declines go to
+//   rdf_cells_kernel      the fp64 kernel (every pair through the reference arithmetic)
+// No packed or pair-interleaved copy of the coordinates is made any more: the raw
+// floats are read twice (second time from L2) and the sorted float4 array is the only
+// intermediate.
+//
+// rdf_cellpair_kernel.  One WARP per cell, persistent warps fetching chunks of cells
+// from a global counter.  The cell's particles and the particles of its stencil cells
+// (half stencil of 13 cells + itself when the two groups coincide, 27 cells otherwise) are
+// contiguous runs of the sorted array -- three x-adjacent cells are one run -- and are
+// copied into a per-warp shared-memory buffer with one bulk copy (cp.async.bulk, the TMA
+// unit's 1-D mode) per run, completion on a per-warp mbarrier; the copy of the next cell
+// is in flight while the current one is computed.  The cell's n_i particles are then
+// dealt to the lanes IPT at a time (ni = ceil(n_i / IPT) lanes hold them all) and the 32
+// lanes split into ways = 32 / ni groups that walk the candidate list with stride `ways`:
+// every lane-step evaluates IPT pairs (two per packed f32x2 instruction) against ONE
+// candidate read as a 16-byte shared-memory load (lanes of a way read the same address:
+// broadcast; the ways read consecutive 16-byte words: one wavefront).  The arithmetic,
+// the fixed-point bin coordinate, the uncertainty window and the histogram update are
+// those of rdf_filter.cu (same device functions -> same bits); uncertain pairs go to a
+// per-warp list that is re-evaluated with the fp64 arithmetic as soon as the cell is done,
+// from the same shared-memory buffer.  Cells whose candidate list does not fit the buffer
+// (dense clusters) take a slower path that reads the runs from global memory.
 
 #include <algorithm>
+#include <type_traits>
 
 #include "rdf_device.cuh"
 
@@ -36,111 +64,156 @@ __device__ __forceinline__ int cell_coord(float x, double box, double inv_w, int
     return min(max(c, 0), nc - 1);
 }
 
-__device__ __forceinline__ int cell_id(const float4 &p, const CellGrid &g, int &cx, int &cy,
-                                       int &cz)
+__device__ __forceinline__ int cell_id(float x, float y, float z, const CellGrid &g, int &cx,
+                                       int &cy, int &cz)
 {
-    cx = cell_coord(p.x, g.box[0], g.inv_w[0], g.nc[0]);
-    cy = cell_coord(p.y, g.box[1], g.inv_w[1], g.nc[1]);
-    cz = cell_coord(p.z, g.box[2], g.inv_w[2], g.nc[2]);
+    cx = cell_coord(x, g.box[0], g.inv_w[0], g.nc[0]);
+    cy = cell_coord(y, g.box[1], g.inv_w[1], g.nc[1]);
+    cz = cell_coord(z, g.box[2], g.inv_w[2], g.nc[2]);
     return (cz * g.nc[1] + cy) * g.nc[0] + cx;
 }
 
-// count particles per cell; the old counter value is the particle's rank in its cell
-__global__ void cells_count_kernel(const float4 *__restrict__ p, int64_t npad, int n,
-                                   const CellGrid *__restrict__ grids, int *__restrict__ cnt,
-                                   int cstride, int *__restrict__ rank)
+// ---- counting sort, straight from the raw coordinates ------------------------------
+
+// 256 particles per step: their 768 floats are read as one contiguous run (coalesced,
+// unlike three stride-3 loads per thread) and regrouped through shared memory.
+__device__ __forceinline__ void load_xyz_256(const float *__restrict__ src, int64_t i0, int64_t n,
+                                             float *stage, int tid)
 {
-    const int frame = blockIdx.y;
-    const CellGrid g = grids[frame];
-    const float4 *pf = p + (int64_t)frame * npad;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int cx, cy, cz;
-        const int c = cell_id(pf[i], g, cx, cy, cz);
-        rank[(int64_t)frame * n + i] = atomicAdd(&cnt[(int64_t)frame * cstride + c], 1);
+    const int64_t f0 = 3 * i0, fend = 3 * n;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int64_t f = f0 + k * 256 + tid;
+        stage[k * 256 + tid] = f < fend ? src[f] : 0.f;
     }
 }
 
-// exclusive scan of the per-cell counts, one block per frame: tiles of 4096 counters
-// (one int4 per thread, coalesced), block scan by warp shuffles, running carry
-__global__ void __launch_bounds__(1024) cells_scan_kernel(const int *__restrict__ cnt,
-                                                          int *__restrict__ start, int cstride,
-                                                          const CellGrid *__restrict__ grids)
+// pass 1: cell of every particle, rank inside its cell (old value of the cell counter),
+// coordinate extents of the frame (order-preserving keys; ext == nullptr: not wanted)
+__global__ void __launch_bounds__(256)
+    cells_bin_kernel(const float *__restrict__ raw, int64_t frame_stride, int n,
+                     const CellGrid *__restrict__ grids, int *__restrict__ cnt, int cstride,
+                     int2 *__restrict__ keyrank, unsigned *__restrict__ ext)
+{
+    __shared__ float stage[3 * 256];
+    __shared__ unsigned red[8][6];
+    const int frame = blockIdx.y, tid = threadIdx.x;
+    const CellGrid g = grids[frame];
+    const float *src = raw + (int64_t)frame * frame_stride;
+    unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+    for (int64_t i0 = (int64_t)blockIdx.x * 256; i0 < n; i0 += (int64_t)gridDim.x * 256) {
+        load_xyz_256(src, i0, n, stage, tid);
+        __syncthreads();
+        const int64_t i = i0 + tid;
+        if (i < n) {
+            const float x = stage[3 * tid], y = stage[3 * tid + 1], z = stage[3 * tid + 2];
+            int cx, cy, cz;
+            const int cell = cell_id(x, y, z, g, cx, cy, cz);
+            const int r = atomicAdd(&cnt[(int64_t)frame * cstride + cell], 1);
+            keyrank[(int64_t)frame * n + i] = make_int2(cell, r);
+            const unsigned kx = ext_key(x), ky = ext_key(y), kz = ext_key(z);
+            lo[0] = min(lo[0], kx); hi[0] = max(hi[0], kx);
+            lo[1] = min(lo[1], ky); hi[1] = max(hi[1], ky);
+            lo[2] = min(lo[2], kz); hi[2] = max(hi[2], kz);
+        }
+        __syncthreads();
+    }
+    if (ext) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned l = __reduce_min_sync(0xffffffffu, lo[k]);
+            const unsigned h = __reduce_max_sync(0xffffffffu, hi[k]);
+            if ((tid & 31) == 0) { red[tid >> 5][k] = l; red[tid >> 5][3 + k] = h; }
+        }
+        __syncthreads();
+        if (tid < 6) {
+            unsigned v = red[0][tid];
+            for (int w = 1; w < 8; ++w) v = tid < 3 ? min(v, red[w][tid]) : max(v, red[w][tid]);
+            if (tid < 3) { if (v != 0xffffffffu) atomicMin(&ext[frame * 6 + tid], v); }
+            else if (v != 0u) atomicMax(&ext[frame * 6 + tid], v);
+        }
+    }
+}
+
+struct ScanFilter {            // optional: build the frames' FrameFilter in the scan kernel
+    const FrameBox *boxes;     // [F] (already offset to the group of frames)
+    const unsigned *ext1, *ext2;
+    FrameFilter *out;
+    FilterPrep prep;
+};
+
+// pass 2: exclusive scan of the per-cell counts; grid = (frames, groups), one block each.
+// Every thread owns a contiguous run of counters (sum, block scan of the sums, write).
+__global__ void __launch_bounds__(1024)
+    cells_scan_kernel(const int *__restrict__ cnt, int *__restrict__ start, int cstride,
+                      int n_frames, const CellGrid *__restrict__ grids, const ScanFilter F)
 {
     __shared__ int warp_sums[32];
-    __shared__ int carry_s;
-    const int frame = blockIdx.x;
+    const int frame = blockIdx.x, group = blockIdx.y;
     const int ncell = grids[frame].ncell;
-    const int *c = cnt + (int64_t)frame * cstride;
-    int *s = start + (int64_t)frame * cstride;
+    const int64_t base = ((int64_t)group * n_frames + frame) * cstride;
+    const int *c = cnt + base;
+    int *s = start + base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < ncell; base += 4096) {
-        const int k0 = base + 4 * tid;
-        int v[4];
+    const int per = (ncell + 1023) / 1024;
+    const int k0 = tid * per, k1 = min(ncell, k0 + per);
+    int local = 0;
+    for (int k = k0; k < k1; ++k) local += c[k];
+    int incl = local;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = k0 + j < ncell ? c[k0 + j] : 0;
-        const int local = v[0] + v[1] + v[2] + v[3];
-        int incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sums[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
         }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        const int carry = carry_s;
-        int run = carry + incl - local + (warp ? warp_sums[warp - 1] : 0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (k0 + j < ncell) s[k0 + j] = run;
-            run += v[j];
-        }
-        __syncthreads();
-        if (tid == 1023) carry_s = carry + warp_sums[31];
-        __syncthreads();
+        warp_sums[lane] = w;
     }
-    if (tid == 0) s[ncell] = carry_s;
+    __syncthreads();
+    int run = incl - local + (warp ? warp_sums[warp - 1] : 0);
+    for (int k = k0; k < k1; ++k) {
+        s[k] = run;
+        run += c[k];
+    }
+    if (tid == 1023) s[ncell] = warp_sums[31];
+    if (F.out != nullptr && group == 0 && tid == 0)
+        F.out[frame] = filter_prepare_frame(F.boxes[frame], F.ext1 + frame * 6,
+                                            F.ext2 + frame * 6, F.prep);
 }
 
-// sorted: float4[F][n] cell-sorted particles.  pairs (optional): the same order in the
-// layout the fp32-filter kernel reads, float4[F][2 * npair] with entry 2q = (x0, x1, y0,
-// y1) and entry 2q + 1 = (z0, z1, id0, id1) of the sorted particles 2q and 2q + 1, so
-// that one 16-byte load yields operands already packed for f32x2 arithmetic.
-__global__ void cells_scatter_kernel(const float4 *__restrict__ p, int64_t npad, int n,
-                                     const CellGrid *__restrict__ grids,
-                                     const int *__restrict__ start, int cstride,
-                                     const int *__restrict__ rank, float4 *__restrict__ sorted,
-                                     float *__restrict__ pairs, int npair)
+// pass 3: raw -> cell-sorted float4 (x, y, z, exclusion block id)
+__global__ void __launch_bounds__(256)
+    cells_scatter_kernel(const float *__restrict__ raw, int64_t frame_stride, int n, int64_t excl,
+                         const int *__restrict__ start, int cstride,
+                         const int2 *__restrict__ keyrank, float4 *__restrict__ sorted)
 {
-    const int frame = blockIdx.y;
-    const CellGrid g = grids[frame];
-    const float4 *pf = p + (int64_t)frame * npad;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 v = pf[i];
-        int cx, cy, cz;
-        const int c = cell_id(v, g, cx, cy, cz);
-        const int dst = start[(int64_t)frame * cstride + c] + rank[(int64_t)frame * n + i];
-        sorted[(int64_t)frame * n + dst] = v;
-        if (pairs) {
-            float *q = pairs + ((int64_t)frame * npair + (dst >> 1)) * 8 + (dst & 1);
-            q[0] = v.x; q[2] = v.y; q[4] = v.z; q[6] = v.w;
-            if (dst == n - 1 && (n & 1)) {       // odd count: finite filler in the last slot
-                q[1] = v.x; q[3] = v.y; q[5] = v.z; q[7] = v.w;
-            }
+    __shared__ float stage[3 * 256];
+    const int frame = blockIdx.y, tid = threadIdx.x;
+    const float *src = raw + (int64_t)frame * frame_stride;
+    const int *st = start + (int64_t)frame * cstride;
+    for (int64_t i0 = (int64_t)blockIdx.x * 256; i0 < n; i0 += (int64_t)gridDim.x * 256) {
+        load_xyz_256(src, i0, n, stage, tid);
+        __syncthreads();
+        const int64_t i = i0 + tid;
+        if (i < n) {
+            const int2 kr = keyrank[(int64_t)frame * n + i];
+            float4 v;
+            v.x = stage[3 * tid]; v.y = stage[3 * tid + 1]; v.z = stage[3 * tid + 2];
+            v.w = __int_as_float((int)(excl > 0 ? i / excl : i));
+            sorted[(int64_t)frame * n + st[kr.x] + kr.y] = v;
         }
+        __syncthreads();
     }
 }
+
+// ---- fp64 kernel: every candidate pair through the reference arithmetic ----------------
 
 struct CellParams {
     const float4 *s1, *s2;        // cell-sorted particles, [F][n]
@@ -155,13 +228,8 @@ struct CellParams {
     unsigned long long *counts;
     unsigned long long *evals;
     int half;                     // same group: half stencil, weight 2
-    // fp32 filter (rdf_cells_filter_kernel); filt == nullptr: exact kernel does it all
-    const float4 *pairs2;         // pair-interleaved copy of s2, [F][2 * npair2]
-    int npair2;
-    const FrameFilter *filt;
-    FilterConst fc;
-    int fast_bins;
-    unsigned long long *fstats;
+    const FrameFilter *filt;      // != nullptr: frames with wlim != 0 were done by the
+                                  // fp32-filter kernel and are skipped here
 };
 
 template <int HIST>
@@ -209,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
     const float4 pi = s1[min(i, P.n1 - 1)];
     const int gi = __float_as_int(pi.w);
     int cx, cy, cz;
-    cell_id(pi, g, cx, cy, cz);
+    cell_id(pi.x, pi.y, pi.z, g, cx, cy, cz);
 
     int steps = 0;                       // warp-uniform: increments since the last flush
     unsigned long long my_evals = 0;
@@ -303,253 +371,6 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
     if (lane == 0 && my_evals) atomicAdd(P.evals, my_evals);
 }
 
-
-// ---- fp32 filter in front of the exact arithmetic (see rdf_filter.cu for the scheme and
-// its error bound): same traversal as rdf_cells_kernel, two neighbours per step with
-// packed f32x2 arithmetic; uncertain pairs go to a per-block list that is re-evaluated
-// with the fp64 arithmetic when the block has finished its sweeps. -------------------
-
-constexpr int kCellListCap = 1024;
-// 128-thread blocks, four per SM: a block ends with its slowest warp, and with the same
-// registers per SM smaller blocks lose less to that (barrier stalls were 13 % of the
-// samples with 256 threads)
-constexpr int kCfThreads = 128;
-constexpr int kCfWarps = kCfThreads / 32;
-
-__host__ __device__ inline size_t cells_filter_smem_bytes(int n_bins, int sb)
-{
-    return align16(sizeof(double) * (n_bins + 1)) +
-           sizeof(unsigned) * ((size_t)kCfWarps * (((size_t)(n_bins + 2) << sb) + 32)) +
-           sizeof(unsigned) * (kCellListCap + 4);
-}
-
-// entry = thread << 24 | valid bits << 22 | pair index q
-template <bool EXCL, bool LOWER>
-__device__ __noinline__ void cells_filter_fix(const CellParams &P, int frame, unsigned entry,
-                                              const double *sT, unsigned hist32, unsigned weight)
-{
-    const FrameFilter ff = P.filt[frame];
-    const FrameBox fb = P.boxes[frame];
-    const FilterConst fc = P.fc;
-    const int i = blockIdx.x * kCfThreads + (int)(entry >> 24);
-    const unsigned vbits = (entry >> 22) & 3u;
-    const int q = (int)(entry & 0x3fffffu);
-    const float4 pi = P.s1[(int64_t)frame * P.n1 + i];
-    const float4 *pp = P.pairs2 + ((int64_t)frame * P.npair2 + q) * 2;
-    const float4 A = pp[0], B = pp[1];
-    unsigned uu[2];
-    filter_eval2<LOWER>(pk2(-pi.x, -pi.x), pk2(-pi.y, -pi.y), pk2(-pi.z, -pi.z), pk2(A.x, A.y),
-                        pk2(A.z, A.w), pk2(B.x, B.y), ff, fc.scale, ff.offm, fc.cbits, uu[0],
-                        uu[1]);
-    const unsigned span_l = LOWER ? fc.span : fc.cbits + fc.span;
-    for (int h = 0; h < 2; ++h) {
-        if (!((vbits >> h) & 1u)) continue;
-        const unsigned u = uu[h];
-        if (!(u < span_l)) continue;
-        if (!((u & ((1u << fc.k) - 1u)) < ff.wlim)) continue;
-        const float4 pj = h ? make_float4(A.y, A.w, B.y, B.w) : make_float4(A.x, A.z, B.x, B.z);
-        if (EXCL && __float_as_int(pi.w) == __float_as_int(pj.w)) continue;
-        const unsigned word = (LOWER ? u : u - fc.cbits) >> (fc.k - fc.sb);
-        const double d2 = pair_d2(pi.x, pi.y, pi.z, pj, fb);
-        const int slot = P.fast_bins ? slot_fast(d2, sT, P.n_bins, P.guess)
-                                     : slot_search(d2, sT, P.n_bins);
-        if ((word >> fc.sb) == (unsigned)slot) continue;
-        red_shared(hist32 + 4u * word, 0u - weight);
-        red_shared(hist32 + 4u * ((unsigned)slot << fc.sb), weight);
-    }
-}
-
-template <bool EXCL, bool LOWER, bool AUDIT>
-__global__ void __launch_bounds__(kCfThreads, 4)
-    rdf_cells_filter_kernel(const __grid_constant__ CellParams P)
-{
-    const int frame = blockIdx.y;
-    const FrameFilter ff = P.filt[frame];
-    if (ff.wlim == 0u) {                  // left to the exact kernel (whole block)
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.fstats[4], 1ull);
-        return;
-    }
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int n_bins = P.n_bins;
-    const FilterConst fc = P.fc;
-    const int hwords = ((n_bins + 2) << fc.sb) + 32;
-    double *sT = reinterpret_cast<double *>(smem);
-    unsigned *sH = reinterpret_cast<unsigned *>(smem + align16(sizeof(double) * (n_bins + 1)));
-    unsigned *sList = sH + kCfWarps * hwords;
-    unsigned *sCount = sList + kCellListCap;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k <= n_bins; k += kCfThreads) sT[k] = P.thr[k];
-    for (int k = tid; k < kCfWarps * hwords; k += kCfThreads) sH[k] = 0;
-    if (tid == 0) *sCount = 0;
-    __syncthreads();
-
-    const unsigned hist32 = (unsigned)__cvta_generic_to_shared(sH + warp * hwords);
-    const int shift = fc.k - fc.sb;
-    const unsigned hbase = hist32 - (LOWER ? 0u : ((fc.cbits >> shift) << 2));
-    const unsigned span_l = LOWER ? fc.span : fc.cbits + fc.span;
-    const unsigned trash_w = (span_l >> shift) + (unsigned)lane;
-    const unsigned fmask = (1u << fc.k) - 1u;
-    const float scale = fc.scale, offm = ff.offm;
-    const unsigned weight = P.half ? 2u : 1u;     // every sweep of a run has one weight
-
-    const CellGrid g = P.grids[frame];
-    const float4 *s1 = P.s1 + (int64_t)frame * P.n1;
-    const float4 *pairs = P.pairs2 + (int64_t)frame * P.npair2 * 2;
-    const int *start = P.start2 + (int64_t)frame * P.cstride;
-
-    const int i = blockIdx.x * kCfThreads + tid;
-    const bool valid = i < P.n1;
-    const float4 pi = s1[min(i, P.n1 - 1)];
-    const int gi = __float_as_int(pi.w);
-    const f32x2 ax = pk2(-pi.x, -pi.x), ay = pk2(-pi.y, -pi.y), az = pk2(-pi.z, -pi.z);
-    int cx, cy, cz;
-    cell_id(pi, g, cx, cy, cz);
-
-    unsigned long long my_evals = 0, audit_bad = 0, audit_unc = 0;
-    const int last_pair = P.npair2 - 1;
-
-    // partners [b, b + len) of this lane, two per step (pair q holds sorted particles 2q
-    // and 2q + 1; the ones outside the range get weight 0); warp-uniform trip count
-    auto sweep = [&](int b, int len) {
-        const int q0 = b >> 1;
-        const int nq = len > 0 ? ((b + len + 1) >> 1) - q0 : 0;
-        const int maxq = __reduce_max_sync(0xffffffffu, nq);
-        my_evals += len;
-        const float4 *pp = pairs + 2 * (int64_t)min(q0, last_pair);
-        float4 nA = __ldg(pp), nB = __ldg(pp + 1);
-        for (int t = 0; t < maxq; ++t) {
-            const float4 A = nA, B = nB;
-            const int q = q0 + t;
-            pp = pairs + 2 * (int64_t)min(q + 1, last_pair);
-            nA = __ldg(pp); nB = __ldg(pp + 1);
-            // in range?  (lanes past their own nq fall out here as well)
-            const bool v0 = (unsigned)(2 * q - b) < (unsigned)len;
-            const bool v1 = (unsigned)(2 * q + 1 - b) < (unsigned)len;
-            unsigned u0, u1;
-            filter_eval2<LOWER>(ax, ay, az, pk2(A.x, A.y), pk2(A.z, A.w), pk2(B.x, B.y), ff, scale,
-                                offm, fc.cbits, u0, u1);
-            unsigned w0 = min(u0 >> shift, trash_w), w1 = min(u1 >> shift, trash_w);
-            if (EXCL && gi == __float_as_int(B.z)) w0 = trash_w;
-            if (EXCL && gi == __float_as_int(B.w)) w1 = trash_w;
-            red_shared_hot(hbase + (w0 << 2), v0 ? weight : 0u);
-            red_shared_hot(hbase + (w1 << 2), v1 ? weight : 0u);
-            if (AUDIT) {
-                const unsigned uu[2] = {u0, u1};
-                const bool vv[2] = {v0, v1};
-                for (int h = 0; h < 2; ++h) {
-                    if (!vv[h]) continue;
-                    const float4 pj = h ? make_float4(A.y, A.w, B.y, B.w)
-                                        : make_float4(A.x, A.z, B.x, B.z);
-                    const unsigned u = uu[h];
-                    const bool unc = (u & fmask) < ff.wlim, in = u < span_l;
-                    const double d2 = pair_d2(pi.x, pi.y, pi.z, pj, P.boxes[frame]);
-                    const int slot = slot_search(d2, sT, n_bins);
-                    const unsigned fs = in ? ((LOWER ? u : u - fc.cbits) >> fc.k)
-                                           : (unsigned)(n_bins + 1);
-                    const bool counted = slot >= 1 && slot <= n_bins;
-                    if (in && unc) ++audit_unc;
-                    if (!(in && unc) && (unsigned)slot != fs &&
-                        (counted || (fs >= 1u && fs <= (unsigned)n_bins)))
-                        ++audit_bad;
-                }
-            }
-            if (min(u0 & fmask, u1 & fmask) < ff.wlim) {
-                const unsigned vb = (v0 ? 1u : 0u) | (v1 ? 2u : 0u);
-                if (vb) {
-                    const unsigned entry = ((unsigned)tid << 24) | (vb << 22) | (unsigned)q;
-                    const unsigned idx = atomicAdd(sCount, 1u);
-                    if (idx < (unsigned)kCellListCap) sList[idx] = entry;
-                    else cells_filter_fix<EXCL, LOWER>(P, frame, entry, sT, hist32, weight);
-                }
-            }
-        }
-    };
-    auto wrap = [](int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); };
-    auto sweep_row = [&](int y, int z) {
-        const int row = (z * g.nc[1] + y) * g.nc[0];
-        const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nc[0] - 1);
-        const int b0 = start[row + xa];
-        sweep(b0, valid ? start[row + xb + 1] - b0 : 0);
-        const int xw = (cx == 0) ? g.nc[0] - 1 : (cx == g.nc[0] - 1 ? 0 : -1);
-        const int bw = xw >= 0 ? start[row + xw] : 0;
-        sweep(bw, (valid && xw >= 0) ? start[row + xw + 1] - bw : 0);
-    };
-
-    if (!P.half) {
-        for (int dz = -1; dz <= 1; ++dz)
-            for (int dy = -1; dy <= 1; ++dy)
-                sweep_row(wrap(cy + dy, g.nc[1]), wrap(cz + dz, g.nc[2]));
-    } else {
-        // half stencil (see rdf_cells_kernel); the own cell contributes j > i with
-        // weight 2 and the self pair (distance 0) once
-        for (int dy = -1; dy <= 1; ++dy)
-            sweep_row(wrap(cy + dy, g.nc[1]), wrap(cz + 1, g.nc[2]));
-        sweep_row(wrap(cy + 1, g.nc[1]), cz);
-        const int row = (cz * g.nc[1] + cy) * g.nc[0];
-        const int xr = wrap(cx + 1, g.nc[0]);
-        const int br = start[row + xr];
-        sweep(br, valid ? start[row + xr + 1] - br : 0);
-        sweep(i + 1, valid ? start[row + cx + 1] - (i + 1) : 0);
-        if (valid) {
-            my_evals += 1;
-            const int slot = slot_search(0.0, sT, n_bins);
-            if (!(EXCL) && slot >= 1 && slot <= n_bins)
-                red_shared(hist32 + 4u * ((unsigned)slot << fc.sb), 1u);
-        }
-    }
-    __syncthreads();
-
-    // exact re-evaluation of the uncertain pairs of this block
-    const unsigned n_push = *sCount;
-    const unsigned n_list = min(n_push, (unsigned)kCellListCap);
-    for (unsigned e = tid; e < n_list; e += kCfThreads)
-        cells_filter_fix<EXCL, LOWER>(P, frame, sList[e], sT, hist32, weight);
-    if (tid == 0 && n_push) {
-        atomicAdd(&P.fstats[0], (unsigned long long)n_list);
-        if (n_push > n_list) atomicAdd(&P.fstats[1], (unsigned long long)(n_push - n_list));
-    }
-    __syncthreads();
-
-    for (int k = tid; k < n_bins; k += kCfThreads) {
-        unsigned sum = 0;                 // modulo 2^32 across warps, see rdf_filter.cu
-        for (int w = 0; w < kCfWarps; ++w)
-            for (int q = 0; q < (1 << fc.sb); ++q)
-                sum += sH[w * hwords + ((k + 1) << fc.sb) + q];
-        if (sum) atomicAdd(&P.counts[k], (unsigned long long)sum);
-    }
-    for (int o = 16; o; o >>= 1) my_evals += __shfl_xor_sync(0xffffffffu, my_evals, o);
-    if (lane == 0 && my_evals) atomicAdd(P.evals, my_evals);
-    if (AUDIT) {
-        if (audit_bad) atomicAdd(&P.fstats[2], audit_bad);
-        if (audit_unc) atomicAdd(&P.fstats[3], audit_unc);
-    }
-}
-
-template <bool EXCL, bool LOWER, bool AUDIT>
-int launch_cells_filter_t(mdh_ctx *c, const CellParams &P, dim3 grid)
-{
-    const size_t smem = cells_filter_smem_bytes(P.n_bins, P.fc.sb);
-    auto kern = rdf_cells_filter_kernel<EXCL, LOWER, AUDIT>;
-    MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    kern<<<dim3((unsigned)((P.n1 + kCfThreads - 1) / kCfThreads), grid.y), kCfThreads, smem,
-         c->stream>>>(P);
-    MDH_CUDA(cudaGetLastError());
-    c->launches++;
-    return MDH_OK;
-}
-
-template <bool EXCL>
-int launch_cells_filter(mdh_ctx *c, const CellParams &P, dim3 grid, bool audit)
-{
-    if (P.fc.lower)
-        return audit ? launch_cells_filter_t<EXCL, true, true>(c, P, grid)
-                     : launch_cells_filter_t<EXCL, true, false>(c, P, grid);
-    return audit ? launch_cells_filter_t<EXCL, false, true>(c, P, grid)
-                 : launch_cells_filter_t<EXCL, false, false>(c, P, grid);
-}
-
 template <int HIST, bool EXCL, bool FAST>
 int launch_cells(mdh_ctx *c, const CellParams &P, dim3 grid)
 {
@@ -563,45 +384,577 @@ int launch_cells(mdh_ctx *c, const CellParams &P, dim3 grid)
     return MDH_OK;
 }
 
-int sort_group(mdh_ctx *c, const float4 *pk, int64_t npad, int n, int n_frames,
-               const CellGrid *grids, int cstride, DevBuf &cnt, DevBuf &start, DevBuf &rank,
-               DevBuf &sorted, DevBuf *pairs)
+// ---- fp32-filter pair kernel: one warp per cell ------------------------------------------
+
+constexpr int kCpThreads = 256;
+constexpr int kCpWarps = kCpThreads / 32;
+constexpr int kCpRanges = 19;            // own cell + 9 rows x (main run, wrapped cell)
+constexpr int kCpListCap = 64;           // deferred entries per warp and cell pass
+constexpr int kCpSlack = 32;             // buffer words a strided walk may read past the list
+
+struct CellPairParams {
+    const float4 *s1, *s2;        // cell-sorted particles, [F][n1], [F][n2]
+    int n1, n2;
+    const int *start1, *start2;   // [F][cstride]
+    int cstride;
+    const CellGrid *grids;
+    const FrameBox *boxes;
+    const FrameFilter *filt;
+    const double *thr;
+    int n_bins;
+    BinGuess guess;
+    FilterConst fc;               // fc.sb: sub-bins of THIS kernel's histograms
+    int fast_bins;
+    unsigned long long *counts, *evals, *fstats;
+    unsigned *work;               // work-item counter (zero at launch)
+    int n_frames;
+    int max_ncell;                // largest cell count of the frames of this launch
+    int chunk_cells;              // cells per work item
+    int cap;                      // buffer capacity in particles (multiple of 32)
+};
+
+__host__ __device__ inline size_t cp_smem_bytes(int n_bins, int sb, int cap)
 {
-    const int npair = (n + 1) / 2;
-    if (pairs)
-        if (int rc = pairs->reserve(sizeof(float) * 8 * (size_t)npair * n_frames)) return rc;
-    if (int rc = cnt.reserve(sizeof(int) * (size_t)cstride * n_frames)) return rc;
-    if (int rc = start.reserve(sizeof(int) * (size_t)cstride * n_frames)) return rc;
-    if (int rc = rank.reserve(sizeof(int) * (size_t)n * n_frames)) return rc;
-    if (int rc = sorted.reserve(sizeof(float4) * (size_t)n * n_frames)) return rc;
-    MDH_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int) * (size_t)cstride * n_frames, c->stream));
-    dim3 grid((unsigned)std::min((n + 255) / 256, 2048), n_frames);
-    cells_count_kernel<<<grid, 256, 0, c->stream>>>(pk, npad, n, grids, cnt.as<int>(), cstride,
-                                                    rank.as<int>());
+    return 256 + align16(sizeof(double) * (n_bins + 1)) +
+           (size_t)kCpWarps * 2 * (cap + kCpSlack) * sizeof(float4) +
+           sizeof(unsigned) * (size_t)kCpWarps * ((((size_t)n_bins + 2) << sb) + 32) +
+           sizeof(unsigned) * kCpWarps * kCpListCap + sizeof(int2) * kCpWarps * 2 * 32;
+}
+
+__device__ __forceinline__ void cp_mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cp_mbar_expect(unsigned bar, unsigned bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\t"
+                 "mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+                 :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA unit), completion counted in bytes on `bar`
+__device__ __forceinline__ void cp_bulk_g2s(unsigned dst, const void *src, unsigned bytes,
+                                            unsigned bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <bool HALF, bool EXCL, bool LOWER, bool AUDIT, int IPT>
+__global__ void __launch_bounds__(kCpThreads, 2)
+    rdf_cellpair_kernel(const __grid_constant__ CellPairParams P)
+{
+    static_assert(IPT == 2 || IPT == 4, "particles are processed in packed pairs");
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int n_bins = P.n_bins;
+    const FilterConst fc = P.fc;
+    const int cap = P.cap, bufw = cap + kCpSlack;
+    const int hwords = ((n_bins + 2) << fc.sb) + 32;
+    // layout: mbarriers | thresholds | candidate buffers | histograms | lists | ranges
+    unsigned long long *sBar = reinterpret_cast<unsigned long long *>(smem);
+    double *sT = reinterpret_cast<double *>(smem + 256);
+    float4 *sBuf =
+        reinterpret_cast<float4 *>(smem + 256 + align16(sizeof(double) * (n_bins + 1)));
+    unsigned *sH = reinterpret_cast<unsigned *>(sBuf + (size_t)kCpWarps * 2 * bufw);
+    unsigned *sList = sH + kCpWarps * hwords;
+    int2 *sRng = reinterpret_cast<int2 *>(sList + kCpWarps * kCpListCap);
+    unsigned *sCount = reinterpret_cast<unsigned *>(smem + 128);      // [kCpWarps]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k <= n_bins; k += kCpThreads) sT[k] = P.thr[k];
+    for (int k = tid; k < kCpWarps * hwords; k += kCpThreads) sH[k] = 0;
+    if (tid < kCpWarps) sCount[tid] = 0;
+    const unsigned bar32 = (unsigned)__cvta_generic_to_shared(sBar + 2 * warp);
+    if (lane == 0) {
+        cp_mbar_init(bar32, 1);
+        cp_mbar_init(bar32 + 8, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    float4 *wbuf = sBuf + (size_t)warp * 2 * bufw;            // two buffers of this warp
+    const unsigned wbuf32 = (unsigned)__cvta_generic_to_shared(wbuf);
+    int2 *wrng = sRng + warp * 2 * 32;
+    unsigned *wlist = sList + warp * kCpListCap;
+    unsigned *wcount = sCount + warp;
+    const unsigned hist32 = (unsigned)__cvta_generic_to_shared(sH + warp * hwords);
+    const int shift = fc.k - fc.sb;
+    const unsigned hbase = hist32 - (LOWER ? 0u : ((fc.cbits >> shift) << 2));
+    const unsigned span_l = LOWER ? fc.span : fc.cbits + fc.span;
+    const unsigned trash_w = (span_l >> shift) + (unsigned)lane;
+    const unsigned fmask = (1u << fc.k) - 1u;
+    const float scale = fc.scale;
+    // self pairs of a same-group run (distance 0) are not evaluated: their bin is known
+    const int slot_zero = slot_search(0.0, sT, n_bins);
+    const bool count_self = HALF && !EXCL && slot_zero >= 1 && slot_zero <= n_bins;
+
+    unsigned phase = 0;                       // bit s: parity the next wait on buffer s uses
+    unsigned long long my_evals = 0;          // lane 0 only
+    unsigned acc_w = 0, n_deferred = 0, n_inline = 0;
+    unsigned long long audit_bad = 0, audit_unc = 0;
+
+    const int items_per_frame = (P.max_ncell + P.chunk_cells - 1) / P.chunk_cells;
+    const int n_items = items_per_frame * P.n_frames;
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(P.work, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int frame = item / items_per_frame;
+        const int c0 = (item - frame * items_per_frame) * P.chunk_cells;
+        const FrameFilter ff = P.filt[frame];
+        if (ff.wlim == 0u) {                  // left to the fp64 kernel
+            if (c0 == 0 && lane == 0) atomicAdd(&P.fstats[4], 1ull);
+            continue;
+        }
+        const float offm = ff.offm;
+        const int ncx = P.grids[frame].nc[0], ncy = P.grids[frame].nc[1],
+                  ncz = P.grids[frame].nc[2];
+        const int c1 = min(c0 + P.chunk_cells, ncx * ncy * ncz);
+
+        // Plans the candidate list of `cell` into buffer `slot` and starts its copy.
+        // Lane r describes run r: r = 0 the cell's own particles (group 1), r >= 1 the
+        // stencil runs of group 2.  Returns (warp-uniform) n_i, total and the mode:
+        // 0 empty cell, 1 buffered (copy in flight), 2 too long for the buffer.
+        auto issue = [&](int cell, int slot, int &n_i, int &total) -> int {
+            const float4 *s1 = P.s1 + (int64_t)frame * P.n1;
+            const float4 *s2 = P.s2 + (int64_t)frame * P.n2;
+            const int *st1 = P.start1 + (int64_t)frame * P.cstride;
+            const int *st2 = P.start2 + (int64_t)frame * P.cstride;
+            const int cx = cell % ncx, t = cell / ncx;
+            const int cy = t % ncy, cz = t / ncy;
+            auto wrap = [](int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); };
+            int b = 0, len = 0;
+            if (lane == 0) {
+                b = st1[cell];
+                len = st1[cell + 1] - b;
+            } else if (lane < kCpRanges) {
+                const int r = lane - 1;              // 0..17: row r / 2, run r & 1
+                int row_i = r >> 1;                  // 0..8 = (dz + 1) * 3 + (dy + 1)
+                int dz = row_i / 3 - 1, dy = row_i % 3 - 1;
+                bool use = true;
+                int xa, xb;                          // cells [xa, xb] of the row
+                if (HALF) {
+                    // forward half: rows at z + 1 (all dy), row (y + 1, z), and the cell
+                    // (x + 1, y, z) of the own row
+                    use = dz == 1 || (dz == 0 && dy >= 0);
+                }
+                const int y = wrap(cy + dy, ncy), z = wrap(cz + dz, ncz);
+                const int row = (z * ncy + y) * ncx;
+                if (HALF && dz == 0 && dy == 0) {
+                    // own row: only x + 1 (the own cell is run 0)
+                    const int xr = wrap(cx + 1, ncx);
+                    xa = xb = xr;
+                    use = (r & 1) == 0;
+                } else if ((r & 1) == 0) {
+                    xa = max(cx - 1, 0); xb = min(cx + 1, ncx - 1);
+                } else {
+                    const int xw = (cx == 0) ? ncx - 1 : (cx == ncx - 1 ? 0 : -1);
+                    use = use && xw >= 0;
+                    xa = xb = max(xw, 0);
+                }
+                if (use) {
+                    b = st2[row + xa];
+                    len = st2[row + xb + 1] - b;
+                }
+            }
+            // exclusive prefix of the run lengths
+            int pre = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += v;
+            }
+            total = __shfl_sync(0xffffffffu, pre, 31);
+            pre -= len;
+            n_i = __shfl_sync(0xffffffffu, len, 0);
+            wrng[slot * 32 + lane] = make_int2(b, len);
+            if (n_i == 0 || (!HALF && total == n_i)) return 0;
+            if (total > cap) return 2;
+            const unsigned bar = bar32 + 8u * slot;
+            if (lane == 0) cp_mbar_expect(bar, (unsigned)total * 16u);
+            __syncwarp();
+            if (len > 0)
+                cp_bulk_g2s(wbuf32 + 16u * (unsigned)(slot * bufw + pre),
+                            (lane == 0 ? s1 : s2) + b, (unsigned)len * 16u, bar);
+            return 1;
+        };
+
+        // All pairs of the cell's particles [off, off + cn) with the candidates.
+        // SLOW: candidates come from global memory (list too long for the buffer),
+        // uncertain pairs are then re-evaluated on the spot.
+        auto compute = [&](int cell, int slot, int n_i, int total, auto slow_tag) {
+            constexpr bool SLOW = decltype(slow_tag)::value;
+            const float4 *buf = wbuf + slot * bufw;
+            const float4 *s2 = P.s2 + (int64_t)frame * P.n2;
+            const float4 *own =
+                SLOW ? P.s1 + (int64_t)frame * P.n1 + wrng[slot * 32].x : buf;
+            const int n_chunks = (n_i + 8 * IPT - 1) / (8 * IPT);
+            const int cs = (n_i + n_chunks - 1) / n_chunks;
+            for (int off = 0; off < n_i; off += cs) {
+                const int cn = min(cs, n_i - off);
+                const int ni = (cn + IPT - 1) / IPT, ways = 32 / ni;
+                const int way = lane / ni, il = lane - way * ni;
+                const bool lane_ok = way < ways;
+                const int ipos0 = off + il * IPT;
+                // the lane's particles: negated coordinates packed in pairs (the operands of
+                // the f32x2 arithmetic), exclusion ids, validity
+                f32x2 nx[IPT / 2], ny[IPT / 2], nz[IPT / 2];
+                int gi[IPT];
+                unsigned vmask = 0;                   // bit k: particle k exists
+                {
+                    float4 a[IPT];
+#pragma unroll
+                    for (int k = 0; k < IPT; ++k) {
+                        if (lane_ok && ipos0 + k < off + cn) vmask |= 1u << k;
+                        a[k] = own[min(ipos0 + k, n_i - 1)];
+                        gi[k] = __float_as_int(a[k].w);
+                    }
+#pragma unroll
+                    for (int ip = 0; ip < IPT / 2; ++ip) {
+                        // negated by an (exact) packed multiplication: its result is a fresh
+                        // aligned register pair -- packed from the halves of two LDS.128
+                        // quads, ptxas re-assembles the pair with two moves at every use
+                        const f32x2 m1 = pk2(-1.f, -1.f);
+                        nx[ip] = mul2(pk2(a[2 * ip].x, a[2 * ip + 1].x), m1);
+                        ny[ip] = mul2(pk2(a[2 * ip].y, a[2 * ip + 1].y), m1);
+                        nz[ip] = mul2(pk2(a[2 * ip].z, a[2 * ip + 1].z), m1);
+                    }
+                }
+                auto coords_of = [&](int k, float &x, float &y, float &z) {
+                    float lo, hi;
+                    upk2(nx[k >> 1], lo, hi); x = -((k & 1) ? hi : lo);
+                    upk2(ny[k >> 1], lo, hi); y = -((k & 1) ? hi : lo);
+                    upk2(nz[k >> 1], lo, hi); z = -((k & 1) ? hi : lo);
+                };
+
+                // the packed fp32 arithmetic of one candidate against the lane's particles
+                auto eval_row = [&](const float4 &pj, unsigned *uu) {
+#pragma unroll
+                    for (int ip = 0; ip < IPT / 2; ++ip)
+                        filter_eval2<LOWER>(nx[ip], ny[ip], nz[ip], pk2(pj.x, pj.x),
+                                            pk2(pj.y, pj.y), pk2(pj.z, pj.z), ff, scale, offm,
+                                            fc.cbits, uu[2 * ip], uu[2 * ip + 1]);
+                };
+                // fp64 re-evaluation of the uncertain pairs among uu[0..IPT): move the
+                // count if the reference arithmetic puts the pair into another slot
+                auto fix = [&](const float *fx, const float *fy, const float *fz, const int *fg,
+                               unsigned fmask_v, int fi0, const float4 &pj, const unsigned *uu,
+                               int jpos, bool self, unsigned weight) {
+                    const FrameBox fb = P.boxes[frame];
+#pragma unroll
+                    for (int k = 0; k < IPT; ++k) {
+                        const unsigned u = uu[k];
+                        if (!((fmask_v >> k) & 1u) || !(u < span_l) || !((u & fmask) < ff.wlim))
+                            continue;
+                        if (EXCL && fg[k] == __float_as_int(pj.w)) continue;
+                        if (self && jpos == fi0 + k) continue;
+                        const unsigned word = (LOWER ? u : u - fc.cbits) >> shift;
+                        const double d2 = pair_d2(fx[k], fy[k], fz[k], pj, fb);
+                        const int slot_e = P.fast_bins ? slot_fast(d2, sT, n_bins, P.guess)
+                                                       : slot_search(d2, sT, n_bins);
+                        if ((word >> fc.sb) == (unsigned)slot_e) continue;
+                        red_shared(hist32 + 4u * word, 0u - weight);
+                        red_shared(hist32 + 4u * ((unsigned)slot_e << fc.sb), weight);
+                    }
+                };
+                // histogram updates of one row (wk: weight per particle, 0 = absent);
+                // returns the smallest fraction of the row's bin coordinates
+                auto hist_row = [&](const float4 &pj, const unsigned *uu, int jpos,
+                                    const unsigned *wk, auto self_tag) -> unsigned {
+                    constexpr bool SELF = decltype(self_tag)::value;
+                    unsigned vmin = 0xffffffffu;
+#pragma unroll
+                    for (int k = 0; k < IPT; ++k) {
+                        const unsigned u = uu[k];
+                        vmin = min(vmin, u & fmask);
+                        unsigned w = min(u >> shift, trash_w);
+                        if (EXCL && gi[k] == __float_as_int(pj.w)) w = trash_w;
+                        if (SELF && jpos == ipos0 + k) w = trash_w;
+                        red_shared_hot(hbase + (w << 2), wk[k]);
+                        if (AUDIT && wk[k] != 0u && !(SELF && jpos == ipos0 + k)) {
+                            const bool unc = (u & fmask) < ff.wlim, in = u < span_l;
+                            float x, y, z;
+                            coords_of(k, x, y, z);
+                            const double d2 = pair_d2(x, y, z, pj, P.boxes[frame]);
+                            const int slot_e = slot_search(d2, sT, n_bins);
+                            const unsigned fs = in ? ((LOWER ? u : u - fc.cbits) >> fc.k)
+                                                   : (unsigned)(n_bins + 1);
+                            const bool counted = slot_e >= 1 && slot_e <= n_bins;
+                            if (in && unc) ++audit_unc;
+                            if (!(in && unc) && (unsigned)slot_e != fs &&
+                                (counted || (fs >= 1u && fs <= (unsigned)n_bins)))
+                                ++audit_bad;
+                        }
+                    }
+                    return vmin;
+                };
+                // a row with an uncertain pair: remember it (re-evaluated after the pass),
+                // or re-evaluate on the spot (list full / candidates not in the buffer)
+                auto push_row = [&](const float4 &pj, const unsigned *uu, int jpos,
+                                    unsigned weight, bool self) {
+                    bool inl = SLOW;
+                    if (!SLOW) {
+                        const unsigned idx = atomicAdd(wcount, 1u);
+                        if (idx < (unsigned)kCpListCap)
+                            wlist[idx] = (self ? 0x80000000u : 0u) | ((unsigned)lane << 16) |
+                                         (unsigned)jpos;
+                        else
+                            inl = true;
+                    }
+                    if (inl) {
+                        float fx[IPT], fy[IPT], fz[IPT];
+#pragma unroll
+                        for (int k = 0; k < IPT; ++k) coords_of(k, fx[k], fy[k], fz[k]);
+                        fix(fx, fy, fz, gi, vmask, ipos0, pj, uu, jpos, self, weight);
+                        ++n_inline;
+                    }
+                };
+                // candidates list[0 .. cnt): lane (way, il) takes list[way], list[way + ways],
+                // ...; two rows per iteration, the next two fetched ahead.  jpos0: position
+                // of list[0] in the own-cell numbering (self test) / in the buffer.
+                auto run_list = [&](const float4 *list, int jpos0, int cnt, unsigned weight,
+                                    auto self_tag) {
+                    constexpr bool SELF = decltype(self_tag)::value;
+                    if (cnt <= 0) return;
+                    const int full = cnt / ways, rem = cnt - full * ways;
+                    const int omax = cnt - 1;
+                    auto ld = [&](int o) -> float4 {
+                        const float4 *q = list + min(o, omax);
+                        return SLOW ? __ldg(q) : *q;
+                    };
+                    unsigned wi[IPT];
+#pragma unroll
+                    for (int k = 0; k < IPT; ++k) {
+                        wi[k] = ((vmask >> k) & 1u) ? weight : 0u;
+                        // keep the weights in registers (as predicates they cost a SEL per pair)
+                        asm volatile("" : "+r"(wi[k]));
+                    }
+                    int o = lane_ok ? way : 0;
+                    float4 r0 = ld(o), r1 = ld(o + ways);
+                    int t = 0;
+#pragma unroll 2
+                    for (; t + 2 <= full; t += 2) {
+                        const float4 a0 = r0, a1 = r1;
+                        r0 = ld(o + 2 * ways);
+                        r1 = ld(o + 3 * ways);
+                        unsigned u0[IPT], u1[IPT];
+                        eval_row(a0, u0);
+                        eval_row(a1, u1);
+                        const unsigned v0 = hist_row(a0, u0, jpos0 + o, wi, self_tag);
+                        const unsigned v1 = hist_row(a1, u1, jpos0 + o + ways, wi, self_tag);
+                        if (min(v0, v1) < ff.wlim && lane_ok) {
+                            if (v0 < ff.wlim) push_row(a0, u0, jpos0 + o, weight, SELF);
+                            if (v1 < ff.wlim) push_row(a1, u1, jpos0 + o + ways, weight, SELF);
+                        }
+                        o += 2 * ways;
+                    }
+                    // at most one more full row, then the partial row
+                    if (t < full) {
+                        unsigned u0[IPT];
+                        eval_row(r0, u0);
+                        const unsigned v0 = hist_row(r0, u0, jpos0 + o, wi, self_tag);
+                        if (v0 < ff.wlim && lane_ok) push_row(r0, u0, jpos0 + o, weight, SELF);
+                        o += ways;
+                        r0 = r1;
+                    }
+                    if (rem) {
+                        unsigned u0[IPT], wm[IPT];
+#pragma unroll
+                        for (int k = 0; k < IPT; ++k) wm[k] = way < rem ? wi[k] : 0u;
+                        eval_row(r0, u0);
+                        const unsigned v0 = hist_row(r0, u0, jpos0 + o, wm, self_tag);
+                        if (v0 < ff.wlim && lane_ok && way < rem)
+                            push_row(r0, u0, jpos0 + o, weight, SELF);
+                    }
+                };
+
+                using yes = std::integral_constant<bool, true>;
+                using no = std::integral_constant<bool, false>;
+                const unsigned w_fwd = HALF ? 2u : 1u;
+                if (!SLOW) {
+                    if (HALF) run_list(buf, 0, n_i, 1u, yes());
+                    run_list(buf + n_i, n_i, total - n_i, w_fwd, no());
+                } else {
+                    if (HALF) run_list(own, 0, n_i, 1u, yes());
+                    for (int r = 1; r < kCpRanges; ++r) {
+                        const int2 rg = wrng[slot * 32 + r];
+                        run_list(s2 + rg.x, n_i, rg.y, w_fwd, no());
+                    }
+                }
+                __syncwarp();
+
+                // drain: the uncertain pairs of this pass, re-evaluated from the buffer
+                if (!SLOW) {
+                    const unsigned n_push = *wcount;
+                    const unsigned n_list = min(n_push, (unsigned)kCpListCap);
+                    for (unsigned e = lane; e < n_list; e += 32) {
+                        const unsigned entry = wlist[e];
+                        const bool self = (entry >> 31) != 0u;
+                        const int src = (int)((entry >> 16) & 0x7fffu), jpos = (int)(entry & 0xffffu);
+                        const int e_il = src - (src / ni) * ni, e_i0 = off + e_il * IPT;
+                        const float4 pj = buf[jpos];
+                        float fx[IPT], fy[IPT], fz[IPT];
+                        int fg[IPT];
+                        unsigned fv = 0;
+#pragma unroll
+                        for (int k = 0; k < IPT; ++k) {
+                            const float4 a = buf[min(e_i0 + k, n_i - 1)];
+                            fx[k] = a.x; fy[k] = a.y; fz[k] = a.z; fg[k] = __float_as_int(a.w);
+                            if (e_i0 + k < off + cn) fv |= 1u << k;
+                        }
+                        unsigned uu[IPT];
+#pragma unroll
+                        for (int ip = 0; ip < IPT / 2; ++ip)
+                            filter_eval2<LOWER>(pk2(-fx[2 * ip], -fx[2 * ip + 1]),
+                                                pk2(-fy[2 * ip], -fy[2 * ip + 1]),
+                                                pk2(-fz[2 * ip], -fz[2 * ip + 1]), pk2(pj.x, pj.x),
+                                                pk2(pj.y, pj.y), pk2(pj.z, pj.z), ff, scale, offm,
+                                                fc.cbits, uu[2 * ip], uu[2 * ip + 1]);
+                        fix(fx, fy, fz, fg, fv, e_i0, pj, uu, jpos, self, self ? 1u : w_fwd);
+                    }
+                    n_deferred += n_list;
+                    __syncwarp();
+                    if (lane == 0) *wcount = 0;
+                    __syncwarp();
+                }
+                // the per-warp u32 words must not wrap: hand them over in time
+                acc_w += (unsigned)cn * (unsigned)total * 2u;      // each term < 2^31
+                if (acc_w >= (1u << 31)) {
+                    for (int k = lane; k < n_bins; k += 32) {
+                        unsigned sum = 0;
+                        for (int q = 0; q < (1 << fc.sb); ++q) {
+                            unsigned *w = sH + warp * hwords + ((k + 1) << fc.sb) + q;
+                            sum += *w;
+                            *w = 0;
+                        }
+                        if (sum) atomicAdd(&P.counts[k], (unsigned long long)sum);
+                    }
+                    acc_w = 0;
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) {
+                my_evals += (unsigned long long)n_i *
+                            (unsigned long long)(HALF ? total : total - n_i);
+                if (count_self) red_shared(hist32 + 4u * ((unsigned)slot_zero << fc.sb), (unsigned)n_i);
+            }
+        };
+
+        int ni_c = 0, tot_c = 0;
+        int mode_c = issue(c0, 0, ni_c, tot_c);
+        int slot = 0;
+        for (int cell = c0; cell < c1; ++cell) {
+            int ni_n = 0, tot_n = 0, mode_n = 0;
+            if (cell + 1 < c1) mode_n = issue(cell + 1, slot ^ 1, ni_n, tot_n);
+            if (mode_c == 1) {
+                cp_mbar_wait(bar32 + 8u * slot, (phase >> slot) & 1u);
+                phase ^= 1u << slot;
+                compute(cell, slot, ni_c, tot_c, std::integral_constant<bool, false>());
+            } else if (mode_c == 2) {
+                compute(cell, slot, ni_c, tot_c, std::integral_constant<bool, true>());
+            }
+            ni_c = ni_n; tot_c = tot_n; mode_c = mode_n;
+            slot ^= 1;
+        }
+    }
+    __syncthreads();
+
+    // merge into the global int64 histogram (sum of the warps' words modulo 2^32 first)
+    for (int k = tid; k < n_bins; k += kCpThreads) {
+        unsigned sum = 0;
+        for (int w = 0; w < kCpWarps; ++w)
+            for (int q = 0; q < (1 << fc.sb); ++q)
+                sum += sH[w * hwords + ((k + 1) << fc.sb) + q];
+        if (sum) atomicAdd(&P.counts[k], (unsigned long long)sum);
+    }
+    if (lane == 0 && my_evals) atomicAdd(P.evals, my_evals);
+    n_inline = __reduce_add_sync(0xffffffffu, n_inline);
+    if (lane == 0) {
+        // n_deferred is warp-uniform (every lane added n_list), n_inline is per lane
+        if (n_deferred) atomicAdd(&P.fstats[0], (unsigned long long)n_deferred);
+        if (n_inline) atomicAdd(&P.fstats[1], (unsigned long long)n_inline);
+    }
+    if (AUDIT) {
+        if (audit_bad) atomicAdd(&P.fstats[2], audit_bad);
+        if (audit_unc) atomicAdd(&P.fstats[3], audit_unc);
+    }
+}
+
+template <bool HALF, bool EXCL, bool LOWER, bool AUDIT, int IPT>
+int launch_cellpair_t(mdh_ctx *c, const CellPairParams &P)
+{
+    const size_t smem = cp_smem_bytes(P.n_bins, P.fc.sb, P.cap);
+    auto kern = rdf_cellpair_kernel<HALF, EXCL, LOWER, AUDIT, IPT>;
+    MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    int per_sm = 0;
+    MDH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCpThreads, smem));
+    MDH_REQUIRE(per_sm >= 1, MDH_EINVAL, "rdf: cell-pair kernel does not fit on an SM");
+    const int items = (P.max_ncell + P.chunk_cells - 1) / P.chunk_cells * P.n_frames;
+    const int blocks = std::max(1, std::min(c->sm_count * per_sm, (items + kCpWarps - 1) / kCpWarps));
+    kern<<<blocks, kCpThreads, smem, c->stream>>>(P);
     MDH_CUDA(cudaGetLastError());
-    cells_scan_kernel<<<n_frames, 1024, 0, c->stream>>>(cnt.as<int>(), start.as<int>(), cstride,
-                                                        grids);
-    MDH_CUDA(cudaGetLastError());
-    cells_scatter_kernel<<<grid, 256, 0, c->stream>>>(pk, npad, n, grids, start.as<int>(),
-                                                      cstride, rank.as<int>(),
-                                                      sorted.as<float4>(),
-                                                      pairs ? pairs->as<float>() : nullptr, npair);
-    MDH_CUDA(cudaGetLastError());
-    c->launches += 3;
+    c->launches++;
     return MDH_OK;
+}
+
+template <bool HALF, bool EXCL>
+int launch_cellpair_he(mdh_ctx *c, const CellPairParams &P, bool audit, int ipt)
+{
+    if (audit)
+        return P.fc.lower ? launch_cellpair_t<HALF, EXCL, true, true, 4>(c, P)
+                          : launch_cellpair_t<HALF, EXCL, false, true, 4>(c, P);
+    if (ipt == 2)
+        return P.fc.lower ? launch_cellpair_t<HALF, EXCL, true, false, 2>(c, P)
+                          : launch_cellpair_t<HALF, EXCL, false, false, 2>(c, P);
+    return P.fc.lower ? launch_cellpair_t<HALF, EXCL, true, false, 4>(c, P)
+                      : launch_cellpair_t<HALF, EXCL, false, false, 4>(c, P);
+}
+
+int launch_cellpair(mdh_ctx *c, const CellPairParams &P, bool half, bool excl, bool audit,
+                    int ipt)
+{
+    if (half)
+        return excl ? launch_cellpair_he<true, true>(c, P, audit, ipt)
+                    : launch_cellpair_he<true, false>(c, P, audit, ipt);
+    return excl ? launch_cellpair_he<false, true>(c, P, audit, ipt)
+                : launch_cellpair_he<false, false>(c, P, audit, ipt);
+}
+
+// Largest number of sub-bins (log2) <= sb_max whose histograms leave room for two
+// resident blocks; -1 if not even sb = 0 fits a single block.
+int cellpair_sub_bins(int n_bins, int sb_max, int cap)
+{
+    for (int sb = sb_max; sb >= 0; --sb)
+        if (cp_smem_bytes(n_bins, sb, cap) <= 112 * 1024) return sb;
+    return cp_smem_bytes(n_bins, 0, cap) <= 224 * 1024 ? 0 : -1;
 }
 
 }  // namespace
 
-// Called from rdf_accumulate_impl after the packed float4 arrays and the FrameBox
-// array of the batch are on the device.
-int rdf_cells_accumulate(mdh_ctx *c, int f0, int n_frames, bool use_filter)
+// Device layout of the cell-list scratch (RdfState::cell):
+//   cell[0] CellGrid[F]            cell[1] int cnt[2][G][cstride] | unsigned ext[2][G][6] | work
+//   cell[2] int start[2][G][cstride]   cell[3] int2 keyrank[G][n1]   cell[4] float4 sorted1[G][n1]
+//   cell[7] int2 keyrank[G][n2]    cell[8] float4 sorted2[G][n2]     cell[9] evals (+ selfcheck word)
+// G = frames per group.
+int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const float *raw2,
+                         int64_t stride2, int f0, int n_frames, bool use_filter, double sqrt_err)
 {
     RdfState &R = c->rdf;
-    // the filter kernel addresses neighbour pairs with 22 bits
-    use_filter = use_filter && (R.n2 + 1) / 2 <= (1 << 22) &&
-                 cells_filter_smem_bytes(R.n_bins, R.fc.sb) <= 100 * 1024;
     MDH_REQUIRE(R.drop_axis < 0, MDH_EINVAL, "rdf: cell-list mode does not support drop_axis");
+    MDH_REQUIRE(R.n1 <= (1ll << 25) && R.n2 <= (1ll << 25), MDH_EINVAL,
+                "rdf: cell-list mode takes at most 2^25 particles per group");
     const double r_cut = sqrt(R.thr_hi) * 1.00001;
     std::vector<CellGrid> grids(n_frames);
     int ncell_max = 0;
@@ -637,59 +990,152 @@ int rdf_cells_accumulate(mdh_ctx *c, int f0, int n_frames, bool use_filter)
     MDH_CUDA(cudaMemcpyAsync(d_grids.p, grids.data(), sizeof(CellGrid) * n_frames,
                              cudaMemcpyHostToDevice, c->stream));
 
-    const int tile = kThreads * R.ipt;
-    const int64_t pad1 = (R.n1 + tile - 1) / tile * tile;
-    const int64_t pad2 = (R.n2 + tile - 1) / tile * tile;
-    if (int rc = sort_group(c, R.pk1.as<float4>(), pad1, (int)R.n1, n_frames,
-                            d_grids.as<CellGrid>(), cstride, R.cell[1], R.cell[2], R.cell[3],
-                            R.cell[4], (R.same && use_filter) ? &R.cell_pairs : nullptr))
-        return rc;
-    if (!R.same)
-        if (int rc = sort_group(c, R.pk2.as<float4>(), pad2, (int)R.n2, n_frames,
-                                d_grids.as<CellGrid>(), cstride, R.cell[5], R.cell[6],
-                                R.cell[7], R.cell[8], use_filter ? &R.cell_pairs : nullptr))
-            return rc;
+    // frames per group: the sorted copies, the (cell, rank) words and the raw floats of a
+    // group should stay in L2 between the passes (R.cells_ws_mb, default 48 MB)
+    const int n_groups = R.same ? 1 : 2;
+    const double per_frame = 36.0 * (double)(R.n1 + (R.same ? 0 : R.n2)) + 8.0 * cstride * n_groups;
+    int G = (int)std::max(1.0, std::min(64.0, floor(R.cells_ws_mb * 1048576.0 / per_frame)));
+    G = std::min(G, n_frames);
 
-    CellParams P;
-    P.s1 = R.cell[4].as<float4>();
-    P.s2 = R.same ? P.s1 : R.cell[8].as<float4>();
-    P.n1 = (int)R.n1; P.n2 = (int)R.n2;
-    P.start2 = R.same ? R.cell[2].as<int>() : R.cell[6].as<int>();
-    P.cstride = cstride;
-    P.grids = d_grids.as<CellGrid>();
-    P.boxes = R.boxes.as<FrameBox>() + f0;
-    P.thr = R.thr.as<double>();
-    P.n_bins = R.n_bins;
-    P.guess = rdf_bin_guess(R);
-    P.counts = R.counts.as<unsigned long long>();
-    P.evals = R.cell[9].as<unsigned long long>();
-    P.half = R.same;
-    P.pairs2 = nullptr; P.npair2 = (int)((R.n2 + 1) / 2);
-    P.filt = nullptr;
-    P.fc = R.fc;
-    P.fast_bins = R.fast_bins ? 1 : 0;
-    P.fstats = R.fstats.as<unsigned long long>();
-    dim3 grid((unsigned)((R.n1 + kThreads - 1) / kThreads), (unsigned)n_frames);
+    const size_t cnt_words = (size_t)2 * G * cstride;
+    const size_t ext_off = cnt_words, work_off = ext_off + (size_t)2 * G * 6;
+    if (int rc = R.cell[1].reserve(sizeof(int) * (work_off + 4))) return rc;
+    if (int rc = R.cell[2].reserve(sizeof(int) * cnt_words)) return rc;
+    if (int rc = R.cell[3].reserve(sizeof(int2) * (size_t)R.n1 * G)) return rc;
+    if (int rc = R.cell[4].reserve(sizeof(float4) * (size_t)R.n1 * G)) return rc;
+    if (!R.same) {
+        if (int rc = R.cell[7].reserve(sizeof(int2) * (size_t)R.n2 * G)) return rc;
+        if (int rc = R.cell[8].reserve(sizeof(float4) * (size_t)R.n2 * G)) return rc;
+    }
+    if (use_filter)
+        if (int rc = R.filt.reserve(sizeof(FrameFilter) * G)) return rc;
+
+    int *d_cnt = R.cell[1].as<int>();
+    unsigned *d_ext = R.cell[1].as<unsigned>() + ext_off;
+    unsigned *d_work = R.cell[1].as<unsigned>() + work_off;
+    int *d_start = R.cell[2].as<int>();
+
+    // candidates per cell the buffers are sized for: mean + 6 sigma (Poisson) + slack
+    const double per_cell1 = (double)R.n1 / ncell_max, per_cell2 = (double)R.n2 / ncell_max;
+    const double expect = per_cell1 + (R.same ? 13.0 : 27.0) * per_cell2;
+    int cap = (int)(expect + 6.0 * sqrt(expect) + 24.0);
+    cap = std::min(1024, std::max(96, (cap + 31) / 32 * 32));
+    int sb_c = use_filter ? cellpair_sub_bins(R.n_bins, R.fc.sb, cap) : -1;
+    while (use_filter && sb_c < 0 && cap > 96) {      // many bins: smaller buffers
+        cap = std::max(96, cap / 2 / 32 * 32);
+        sb_c = cellpair_sub_bins(R.n_bins, R.fc.sb, cap);
+    }
+    use_filter = use_filter && sb_c >= 0;
+
     const bool excl = R.excl1 > 0, fast = R.fast_bins;
-    if (use_filter) {
-        // the filter kernel takes the frames whose error bound is small against a bin;
-        // the exact kernel below only runs the ones it declined
-        P.pairs2 = R.cell_pairs.as<float4>();
-        P.filt = R.filt.as<FrameFilter>();
-        const bool audit = R.filter_mode == MDH_FILTER_AUDIT;
-        if (int rc = excl ? launch_cells_filter<true>(c, P, grid, audit)
-                          : launch_cells_filter<false>(c, P, grid, audit)) return rc;
+    for (int g0 = 0; g0 < n_frames; g0 += G) {
+        const int ng = std::min(G, n_frames - g0);
+        // counters, extents (min keys start at all-ones, max keys at 0) and the work
+        // counter: one contiguous region, two memsets
+        MDH_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (work_off + 4), c->stream));
+        if (use_filter) {
+            rdf_ext_init_kernel<<<(12 * G + 255) / 256, 256, 0, c->stream>>>(d_ext, 12 * G);
+            MDH_CUDA(cudaGetLastError());
+            c->launches++;
+        }
+        const CellGrid *gg = d_grids.as<CellGrid>() + g0;
+        for (int grp = 0; grp < n_groups; ++grp) {
+            const float *raw = (grp ? raw2 : raw1) + (int64_t)g0 * (grp ? stride2 : stride1);
+            const int n = (int)(grp ? R.n2 : R.n1);
+            dim3 grid((unsigned)std::min((n + 255) / 256, 4096), ng);
+            cells_bin_kernel<<<grid, 256, 0, c->stream>>>(
+                raw, grp ? stride2 : stride1, n, gg, d_cnt + (size_t)grp * G * cstride, cstride,
+                R.cell[grp ? 7 : 3].as<int2>(), use_filter ? d_ext + (size_t)grp * G * 6 : nullptr);
+            MDH_CUDA(cudaGetLastError());
+            c->launches++;
+        }
+        ScanFilter F{};
+        F.out = nullptr;
+        if (use_filter) {
+            F.boxes = R.boxes.as<FrameBox>() + f0 + g0;
+            F.ext1 = d_ext;
+            F.ext2 = R.same ? d_ext : d_ext + (size_t)G * 6;
+            F.out = R.filt.as<FrameFilter>();
+            F.prep = rdf_filter_prep(R, sqrt_err);
+        }
+        cells_scan_kernel<<<dim3(ng, n_groups), 1024, 0, c->stream>>>(d_cnt, d_start, cstride, G,
+                                                                     gg, F);
+        MDH_CUDA(cudaGetLastError());
+        c->launches++;
+        for (int grp = 0; grp < n_groups; ++grp) {
+            const float *raw = (grp ? raw2 : raw1) + (int64_t)g0 * (grp ? stride2 : stride1);
+            const int n = (int)(grp ? R.n2 : R.n1);
+            dim3 grid((unsigned)std::min((n + 255) / 256, 4096), ng);
+            cells_scatter_kernel<<<grid, 256, 0, c->stream>>>(
+                raw, grp ? stride2 : stride1, n, grp ? R.excl2 : R.excl1,
+                d_start + (size_t)grp * G * cstride, cstride, R.cell[grp ? 7 : 3].as<int2>(),
+                R.cell[grp ? 8 : 4].as<float4>());
+            MDH_CUDA(cudaGetLastError());
+            c->launches++;
+        }
+
+        const float4 *s1 = R.cell[4].as<float4>();
+        const float4 *s2 = R.same ? s1 : R.cell[8].as<float4>();
+        const int *start1 = d_start, *start2 = R.same ? d_start : d_start + (size_t)G * cstride;
+        if (use_filter) {
+            CellPairParams Q;
+            Q.s1 = s1; Q.s2 = s2;
+            Q.n1 = (int)R.n1; Q.n2 = (int)R.n2;
+            Q.start1 = start1; Q.start2 = start2;
+            Q.cstride = cstride;
+            Q.grids = gg;
+            Q.boxes = R.boxes.as<FrameBox>() + f0 + g0;
+            Q.filt = R.filt.as<FrameFilter>();
+            Q.thr = R.thr.as<double>();
+            Q.n_bins = R.n_bins;
+            Q.guess = rdf_bin_guess(R);
+            Q.fc = R.fc;
+            Q.fc.sb = sb_c;
+            Q.fast_bins = R.fast_bins ? 1 : 0;
+            Q.counts = R.counts.as<unsigned long long>();
+            Q.evals = R.cell[9].as<unsigned long long>();
+            Q.fstats = R.fstats.as<unsigned long long>();
+            Q.work = d_work;
+            Q.n_frames = ng;
+            Q.max_ncell = ncell_max;
+            Q.chunk_cells = R.cells_chunk;
+            Q.cap = cap;
+            if (int rc = launch_cellpair(c, Q, R.same != 0, excl,
+                                         R.filter_mode == MDH_FILTER_AUDIT, R.cells_ipt))
+                return rc;
+        }
+        // the fp64 kernel: every frame without the filter, else the frames it declined
+        CellParams P;
+        P.s1 = s1; P.s2 = s2;
+        P.n1 = (int)R.n1; P.n2 = (int)R.n2;
+        P.start2 = start2;
+        P.cstride = cstride;
+        P.grids = gg;
+        P.boxes = R.boxes.as<FrameBox>() + f0 + g0;
+        P.thr = R.thr.as<double>();
+        P.n_bins = R.n_bins;
+        P.guess = rdf_bin_guess(R);
+        P.counts = R.counts.as<unsigned long long>();
+        P.evals = R.cell[9].as<unsigned long long>();
+        P.half = R.same;
+        P.filt = use_filter ? R.filt.as<FrameFilter>() : nullptr;
+        dim3 grid((unsigned)((R.n1 + kThreads - 1) / kThreads), (unsigned)ng);
+        int rc;
+        if (R.hist == MDH_HIST_LANE_PRIVATE) {
+            if (excl)
+                rc = fast ? launch_cells<MDH_HIST_LANE_PRIVATE, true, true>(c, P, grid)
+                          : launch_cells<MDH_HIST_LANE_PRIVATE, true, false>(c, P, grid);
+            else
+                rc = fast ? launch_cells<MDH_HIST_LANE_PRIVATE, false, true>(c, P, grid)
+                          : launch_cells<MDH_HIST_LANE_PRIVATE, false, false>(c, P, grid);
+        } else if (excl) {
+            rc = fast ? launch_cells<MDH_HIST_WARP_ATOMIC, true, true>(c, P, grid)
+                      : launch_cells<MDH_HIST_WARP_ATOMIC, true, false>(c, P, grid);
+        } else {
+            rc = fast ? launch_cells<MDH_HIST_WARP_ATOMIC, false, true>(c, P, grid)
+                      : launch_cells<MDH_HIST_WARP_ATOMIC, false, false>(c, P, grid);
+        }
+        if (rc) return rc;
     }
-    if (R.hist == MDH_HIST_LANE_PRIVATE) {
-        if (excl)
-            return fast ? launch_cells<MDH_HIST_LANE_PRIVATE, true, true>(c, P, grid)
-                        : launch_cells<MDH_HIST_LANE_PRIVATE, true, false>(c, P, grid);
-        return fast ? launch_cells<MDH_HIST_LANE_PRIVATE, false, true>(c, P, grid)
-                    : launch_cells<MDH_HIST_LANE_PRIVATE, false, false>(c, P, grid);
-    }
-    if (excl)
-        return fast ? launch_cells<MDH_HIST_WARP_ATOMIC, true, true>(c, P, grid)
-                    : launch_cells<MDH_HIST_WARP_ATOMIC, true, false>(c, P, grid);
-    return fast ? launch_cells<MDH_HIST_WARP_ATOMIC, false, true>(c, P, grid)
-                : launch_cells<MDH_HIST_WARP_ATOMIC, false, false>(c, P, grid);
+    return MDH_OK;
 }

@@ -354,6 +354,62 @@ __device__ __forceinline__ void filter_eval2(f32x2 ax, f32x2 ay, f32x2 az, f32x2
     u1 = __float_as_uint(b) - (LOWER ? cbits : 0u);
 }
 
+// Per-frame parameters of the fp32 filter from the frame's box and coordinate extents
+// (error bound: rdf_filter.cu header and DESIGN.md 4.1b).  e1 / e2: the six extent keys
+// {min x, y, z, max x, y, z} of the two groups.
+struct FilterPrep {            // per configuration (host)
+    int k;
+    double scale;              // n_bins / (r_hi - r_lo)
+    double d_max;              // largest distance that can still be binned
+    double sqrt_err;           // measured relative error of sqrt.approx.ftz.f32
+    double offbase;            // FilterConst::offbase
+};
+
+__device__ inline FrameFilter filter_prepare_frame(const FrameBox &fb, const unsigned *e1,
+                                                   const unsigned *e2, const FilterPrep &Q)
+{
+    const double e24 = 1.0 / 16777216.0;
+    bool ok = true;
+    double a2 = 0.0;
+    FrameFilter ff;
+    for (int k = 0; k < 3; ++k) {
+        const float e4[4] = {ext_unkey(e1[k]), ext_unkey(e1[3 + k]), ext_unkey(e2[k]),
+                             ext_unkey(e2[3 + k])};
+        // inf / NaN coordinates (all-ones exponent) make the bound meaningless
+        for (int q = 0; q < 4; ++q)
+            if ((__float_as_uint(e4[q]) & 0x7f800000u) == 0x7f800000u) ok = false;
+        const double lo1 = (double)e4[0], hi1 = (double)e4[1];
+        const double lo2 = (double)e4[2], hi2 = (double)e4[3];
+        const double D = fmax(fmax(hi2 - lo1, hi1 - lo2), 0.0) * (1.0 + 2.0 * e24);
+        const double box = fb.box[k], inv = fb.inv[k];
+        // the magic-number rounding needs |df * inv| well inside 2^22
+        if (!(D * inv < 1048576.0)) ok = false;
+        const double eps_b = fabs(box * inv - 1.0);       // exact: 24-bit x 24-bit
+        // last term: the fp64 product inv*df of the reference may round across a
+        // half-integer that the exact product does not cross (|m| changes by at most
+        // box * 2^-52 * |inv*df| <= 2^-51 D)
+        const double a = e24 * (0.5 * box + eps_b * D + e24 * D) * (1.0 + 1e-6) + eps_b * D +
+                         D / 2251799813685248.0 + 1e-30;
+        a2 += a * a;
+        ff.nbox[k] = -(float)box;                          // box is a float32 value
+        ff.inv[k] = (float)inv;
+    }
+    const double two_k = (double)(1u << Q.k);
+    const double mu = Q.scale * (sqrt(a2) + Q.d_max * (1.5 * e24 * 1.001 + Q.sqrt_err)) +
+                      e24 * Q.scale * Q.d_max * 1.001 + 1.0 / two_k + 1e-9;
+    const double m = ceil(1.25 * mu * two_k) + 1.0;
+    if (!(m >= 1.0) || !(2.0 * m + 1.0 < two_k / 8.0)) ok = false;
+    if (ok) {
+        // shifted coordinate: exactly representable (a multiple of 2^-k in the binade)
+        ff.offm = (float)(Q.offbase + m / two_k);
+        ff.wlim = 2u * (unsigned)m + 1u;
+    } else {
+        ff.offm = 0.f;
+        ff.wlim = 0u;
+    }
+    return ff;
+}
+
 // RED without the "memory" clobber: the compiler may move the tile loads of the next
 // iteration across it (they never alias the histogram); __syncthreads() orders the
 // histogram against its final read.
@@ -387,3 +443,4 @@ struct PairParams {
 }  // namespace rdfdev
 
 rdfdev::BinGuess rdf_bin_guess(const RdfState &R);   // rdf.cu
+rdfdev::FilterPrep rdf_filter_prep(const RdfState &R, double sqrt_err);   // rdf_filter.cu

@@ -345,58 +345,14 @@ struct PrepareParams {
     const unsigned *ext1, *ext2;     // [F][6] keys
     FrameFilter *out;
     int n_frames;
-    int k;
-    double scale;                    // n_bins / (r_hi - r_lo)
-    double d_max;                    // largest distance that can still be binned
-    double sqrt_err;
-    double offbase;                  // FilterConst::offbase
+    FilterPrep prep;
 };
 
 __global__ void rdf_filter_prepare_kernel(const PrepareParams Q)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= Q.n_frames) return;
-    const FrameBox fb = Q.boxes[f];
-    const double e24 = 1.0 / 16777216.0;
-    bool ok = true;
-    double a2 = 0.0;
-    FrameFilter ff;
-    for (int k = 0; k < 3; ++k) {
-        const float e4[4] = {ext_unkey(Q.ext1[f * 6 + k]), ext_unkey(Q.ext1[f * 6 + 3 + k]),
-                             ext_unkey(Q.ext2[f * 6 + k]), ext_unkey(Q.ext2[f * 6 + 3 + k])};
-        // inf / NaN coordinates (all-ones exponent) make the bound meaningless
-        for (int q = 0; q < 4; ++q)
-            if ((__float_as_uint(e4[q]) & 0x7f800000u) == 0x7f800000u) ok = false;
-        const double lo1 = (double)e4[0], hi1 = (double)e4[1];
-        const double lo2 = (double)e4[2], hi2 = (double)e4[3];
-        const double D = fmax(fmax(hi2 - lo1, hi1 - lo2), 0.0) * (1.0 + 2.0 * e24);
-        const double box = fb.box[k], inv = fb.inv[k];
-        // the magic-number rounding needs |df * inv| well inside 2^22
-        if (!(D * inv < 1048576.0)) ok = false;
-        const double eps_b = fabs(box * inv - 1.0);       // exact: 24-bit x 24-bit
-        // last term: the fp64 product inv*df of the reference may round across a
-        // half-integer that the exact product does not cross (|m| changes by at most
-        // box * 2^-52 * |inv*df| <= 2^-51 D)
-        const double a = e24 * (0.5 * box + eps_b * D + e24 * D) * (1.0 + 1e-6) + eps_b * D +
-                         D / 2251799813685248.0 + 1e-30;
-        a2 += a * a;
-        ff.nbox[k] = -(float)box;                          // box is a float32 value
-        ff.inv[k] = (float)inv;
-    }
-    const double two_k = (double)(1u << Q.k);
-    const double mu = Q.scale * (sqrt(a2) + Q.d_max * (1.5 * e24 * 1.001 + Q.sqrt_err)) +
-                      e24 * Q.scale * Q.d_max * 1.001 + 1.0 / two_k + 1e-9;
-    const double m = ceil(1.25 * mu * two_k) + 1.0;
-    if (!(m >= 1.0) || !(2.0 * m + 1.0 < two_k / 8.0)) ok = false;
-    if (ok) {
-        // shifted coordinate: exactly representable (a multiple of 2^-k in the binade)
-        ff.offm = (float)(Q.offbase + m / two_k);
-        ff.wlim = 2u * (unsigned)m + 1u;
-    } else {
-        ff.offm = 0.f;
-        ff.wlim = 0u;
-    }
-    Q.out[f] = ff;
+    Q.out[f] = filter_prepare_frame(Q.boxes[f], Q.ext1 + f * 6, Q.ext2 + f * 6, Q.prep);
 }
 
 template <bool EXCL, bool LOWER, bool AUDIT, int IPT, int OCC>
@@ -497,6 +453,17 @@ bool rdf_filter_configure(RdfState &R, const double *thr, double sqrt_err)
     return true;
 }
 
+FilterPrep rdf_filter_prep(const RdfState &R, double sqrt_err)
+{
+    FilterPrep q;
+    q.k = R.fc.k;
+    q.scale = R.n_bins / (R.r_hi - R.r_lo);
+    q.d_max = R.r_hi + 2.0 / q.scale;
+    q.sqrt_err = sqrt_err;
+    q.offbase = R.fc.offbase;
+    return q;
+}
+
 // Builds the per-frame filter parameters of a batch (device side, asynchronous).
 int rdf_filter_prepare(mdh_ctx *c, int f0, int n_frames, double sqrt_err)
 {
@@ -508,11 +475,7 @@ int rdf_filter_prepare(mdh_ctx *c, int f0, int n_frames, double sqrt_err)
     Q.ext2 = R.same ? Q.ext1 : R.ext2.as<unsigned>();
     Q.out = R.filt.as<FrameFilter>();
     Q.n_frames = n_frames;
-    Q.k = R.fc.k;
-    Q.scale = R.n_bins / (R.r_hi - R.r_lo);
-    Q.d_max = R.r_hi + 2.0 / Q.scale;
-    Q.sqrt_err = sqrt_err;
-    Q.offbase = R.fc.offbase;
+    Q.prep = rdf_filter_prep(R, sqrt_err);
     rdf_filter_prepare_kernel<<<(n_frames + 127) / 128, 128, 0, c->stream>>>(Q);
     MDH_CUDA(cudaGetLastError());
     c->launches++;

@@ -746,6 +746,18 @@ __global__ void sq_finalize_kernel(const double2 *__restrict__ rho, int n_frames
     ssf[(int64_t)p * n_q + q] += acc;
 }
 
+// Row layout of the scalar lattice kernel's tables, in elements per particle:
+// E_x re | E_x im | E_y re | E_y im | E_z (re, im) pairs padded to whole kSqTN tiles.
+static int lattice_row_elems(const int (&nmax)[3], int *offy, int *offz)
+{
+    const int oy = 2 * (nmax[0] + 1);
+    const int oz = (oy + 2 * (nmax[1] + 1) + 3) / 4 * 4;     // 16-byte aligned
+    if (offy) *offy = oy;
+    if (offz) *offz = oz;
+    return oz + 2 * ((nmax[2] + kSqTN) / kSqTN * kSqTN);
+}
+constexpr size_t kSqMaxSmem = 227 * 1024;
+
 template <typename T>
 int launch_lattice(mdh_ctx *c, const LatticeParams &P, dim3 grid, int block)
 {
@@ -1062,12 +1074,11 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                         "sq: pair %d refers to a missing group", p);
         }
     }
+    MDH_REQUIRE(mode != 2, MDH_EINVAL, "sq: invalid mode");   // retired selector value
     const bool want_lattice = mode == MDH_SQ_LATTICE_FP64 || mode == MDH_SQ_LATTICE_FP32 ||
-                              mode == MDH_SQ_LATTICE_SFU || mode == MDH_SQ_LATTICE_DMMA;
+                              mode == MDH_SQ_LATTICE_DMMA;
     MDH_REQUIRE(!want_lattice || (lat_n && lat_b), MDH_EINVAL,
                 "sq: a lattice kernel was requested without lattice_n / lattice_b");
-    MDH_REQUIRE(mode != MDH_SQ_LATTICE_SFU, MDH_EINVAL,
-                "sq: MDH_SQ_LATTICE_SFU is not available in this build");
 
     S.configured = false;
     S.n_total = n_total; S.n_groups = n_groups; S.n_q = n_q; S.n_pairs = n_pairs;
@@ -1140,6 +1151,21 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
     MDH_REQUIRE(lattice || !want_lattice, MDH_EINVAL,
                 "sq: wavevectors are not usable by the lattice kernels "
                 "(need 0 <= n <= 1023 and no duplicates)");
+    // The scalar lattice kernel keeps two phase-factor tables of (nx + ny + nz + 3) entries
+    // x kPS particles in shared memory (launch_lattice): grids beyond ~75 points per axis
+    // (fp64) do not fit, and the general kernel -- no tables -- takes them.
+    if (lattice) {
+        const size_t nt = (size_t)lattice_row_elems(S.nmax, nullptr, nullptr);
+        const size_t elem = mode == MDH_SQ_LATTICE_FP32 ? sizeof(float) : sizeof(double);
+        if (2 * elem * kPS * nt > kSqMaxSmem) {
+            MDH_REQUIRE(mode == MDH_SQ_AUTO, MDH_EINVAL,
+                        "sq: the phase-factor tables of this wavevector grid (%d x %d x %d) "
+                        "do not fit in shared memory; use MDH_SQ_AUTO or MDH_SQ_GENERAL_FP64",
+                        S.nmax[0] + 1, S.nmax[1] + 1, S.nmax[2] + 1);
+            lattice = false;
+            mitems.clear();
+        }
+    }
     S.lattice = lattice;
     // AUTO: the DMMA kernel needs enough (group, tile) pairs to load all four schedulers
     // of an SM (measured: 9 pairs lose to the scalar kernel by 27 %, 17 win by 4 %, 26 by 11 %, 49 by 1.8x)
@@ -1268,9 +1294,7 @@ static int sq_compute_rho(mdh_ctx *c, const float *raw, int64_t stride, const in
     if (S.lattice) {
         LatticeParams P;
         // row layout in table elements: E_x re | E_x im | E_y re | E_y im | E_z (re, im)
-        P.offy = 2 * (S.nmax[0] + 1);
-        P.offz = (P.offy + 2 * (S.nmax[1] + 1) + 3) / 4 * 4;     // 16-byte aligned
-        P.nt = P.offz + 2 * ((S.nmax[2] + kSqTN) / kSqTN * kSqTN);
+        P.nt = lattice_row_elems(S.nmax, &P.offy, &P.offz);
         P.raw = raw; P.stride = stride; P.vmap = vmap;
         P.chunks = S.chunks.as<int4>();
         P.items = S.items.as<SqWorkItem>();
@@ -1311,22 +1335,23 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
     MDH_REQUIRE(stride >= 3 * S.n_total, MDH_EINVAL, "sq: frame_stride < 3*n_total");
     MDH_REQUIRE(location == MDH_HOST || location == MDH_DEVICE, MDH_EINVAL,
                 "sq: invalid location");
-    // host input in up to four pieces: the copy of one piece (copy stream) overlaps the
-    // kernels of the previous one (compute stream)
-    int piece = n_frames;
+    // host input in pieces: the copy of one piece (copy stream) overlaps the kernels of
+    // the previous one (compute stream); the particle chunks are laid out once, for the
+    // whole call
     if (location == MDH_HOST) {
-        const double bytes = 12.0 * (double)S.n_total * n_frames;      // >= ~12 MB a piece
-        const int n_pieces = (int)std::min(4.0, std::max(1.0, floor(bytes / 12e6)));
-        piece = (n_frames + n_pieces - 1) / n_pieces;
+        int f0 = 0;
+        for (int nf : mdh_plan_pieces(n_frames, 12.0 * (double)S.n_total)) {
+            if (int rc = sq_accumulate_piece(c, pos + (int64_t)f0 * stride, stride, location, nf,
+                                             n_frames)) return rc;
+            f0 += nf;
+        }
+        return MDH_OK;
     }
-    for (int f0 = 0; f0 < n_frames; f0 += piece)
-        if (int rc = sq_accumulate_piece(c, pos + (int64_t)f0 * stride, stride, location,
-                                         std::min(piece, n_frames - f0), piece)) return rc;
-    return MDH_OK;
+    return sq_accumulate_piece(c, pos, stride, location, n_frames, n_frames);
 }
 
-// nominal_frames: the piece size the particle chunks are laid out for (the last piece
-// of a call may be shorter; it reuses the layout instead of rebuilding it)
+// nominal_frames: the frame count the particle chunks are laid out for (the whole call;
+// its pieces reuse the layout instead of rebuilding it)
 static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int location,
                                int n_frames, int nominal_frames)
 {
@@ -1495,8 +1520,7 @@ int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locati
             MDH_CUDA(cudaMemcpyAsync(bigger.p, win.p, sizeof(float) * fsz * (size_t)keep,
                                      cudaMemcpyDeviceToDevice, c->stream));
         MDH_CUDA(cudaStreamSynchronize(c->stream));
-        win.release();
-        win = bigger;
+        win.adopt(bigger);
     }
     MDH_CUDA(cudaMemcpy2DAsync(win.as<float>() + fsz * keep, sizeof(float) * fsz, pos,
                                sizeof(float) * stride, sizeof(float) * fsz, n_frames,

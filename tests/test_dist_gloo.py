@@ -32,6 +32,28 @@ def _worker(rank, world_size, port, out_dir):
         assert r.n_frames == 5
         assert np.array_equal(r.results.counts, g["counts"])
         np.testing.assert_allclose(r.results.rdf, g["rdf"], rtol=1e-6)
+        # the in-run parity check of bench.py: a rank recomputes the whole frame list alone
+        # (no sharding, no collective) and must find the all-reduced result
+        from mdhelper_b200.analysis.base import single_rank, world
+        if rank == 0:
+            with single_rank():
+                assert world() == (0, 1)
+                alone = FakeRDF(u.atoms, n_bins=int(g["n_bins"]), range=tuple(g["range"]),
+                                verbose=False).run()
+                assert alone.n_local_frames == 5
+            assert np.array_equal(alone.results.counts, r.results.counts)
+        assert world() == (rank, 2)
+        # a ring trajectory: 12 frames cycling through the 5 in memory, split 6 + 6
+        ur = SyntheticUniverse(g["positions"], g["dims"], n_frames=12)
+        rr = FakeRDF(ur.atoms, n_bins=int(g["n_bins"]), range=tuple(g["range"]),
+                     verbose=False).run()
+        assert rr.n_local_frames == 6 and rr.n_frames == 12
+        per_frame = [FakeRDF(u.atoms, n_bins=int(g["n_bins"]), range=tuple(g["range"]),
+                             verbose=False) for _ in range(1)][0]
+        with single_rank():
+            want = sum(per_frame.run(start=f % 5, stop=f % 5 + 1).results.counts
+                       for f in range(12))
+        assert np.array_equal(rr.results.counts, want)
         # a strided selection and more ranks than frames on one side
         r2 = FakeRDF(u.atoms, n_bins=int(g["n_bins"]), range=tuple(g["range"]),
                      verbose=False).run(start=4)

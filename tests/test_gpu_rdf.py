@@ -208,6 +208,100 @@ def test_cells_filter_audit(same, exclusion):
             assert np.array_equal(got, want)
 
 
+def test_cells_dense_clusters_take_the_long_list_path():
+    """Clusters far denser than the average: cells with more particles than one pass deals
+    to the lanes (several particle chunks) and candidate lists longer than the per-warp
+    buffer (read from global memory instead); same group, two groups, exclusions, audit."""
+    rng = np.random.default_rng(2026)
+    dims = np.array([30.0, 27.0, 33.0, 90, 90, 90], np.float32)
+    p = (rng.random((5000, 3)) * dims[:3]).astype(np.float32)
+    p[:1400] = (np.array([7.0, 8.0, 9.0]) + 0.8 * rng.standard_normal((1400, 3))).astype(np.float32)
+    p[1400:1500] = (np.array([29.9, 0.1, 16.0])
+                    + 0.2 * rng.standard_normal((100, 3))).astype(np.float32)   # across a face
+    q = (rng.random((3100, 3)) * dims[:3]).astype(np.float32)
+    q[:600] = (np.array([7.5, 8.5, 9.5]) + 0.5 * rng.standard_normal((600, 3))).astype(np.float32)
+    S = _structure()
+    for p2, exclusion in [(p, None), (p, (4, 4)), (q, None), (q, (2, 3))]:
+        want = _oracle().radial_histogram(p, p2, 90, (0.0, 3.0), dims, exclusion=exclusion,
+                                          method="bruteforce")
+        for arith in ("auto", "audit", "off"):
+            st = {}
+            got = S.radial_histogram(p, p2, 90, (0.0, 3.0), dims, exclusion=exclusion,
+                                     mode="cells", arith=arith, stats=st)
+            assert np.array_equal(got, want), (exclusion, arith)
+            assert st["audit_violations"] == 0
+            if arith != "off":
+                assert st["eligible"] == 1 and st["declined_frames"] == 0
+
+
+@pytest.mark.parametrize("tune", ["cipt=2", "cchunk=1", "cchunk=64,cws=1"])
+def test_cells_kernel_tunables_do_not_change_counts(tune, monkeypatch):
+    """Two particles per lane instead of four, one cell or 64 cells per work item, one
+    frame per sort group: identical counts."""
+    from mdhelper_b200 import synthetic
+    u = synthetic.lj_fluid(20_000, 3, seed=5)
+    S = _structure()
+    kw = dict(n_bins=100, range=(0.0, 2.5), norm=None, verbose=False, mode="cells")
+    ref = S.RadialDistributionFunction(u.atoms, **kw).run().results.counts
+    monkeypatch.setenv("MDH_TUNE", tune)
+    got = S.RadialDistributionFunction(u.atoms, **kw).run().results.counts
+    assert np.array_equal(got, ref)
+    want = _oracle().rdf_run(u, u.atoms, n_bins=100, range=(0.0, 2.5), norm=None)["counts"]
+    assert np.array_equal(ref, want)
+
+
+def test_cells_minimal_grid_and_changing_boxes():
+    """Three cells per axis (every stencil offset wraps) and a box that changes from
+    frame to frame (the grid is rebuilt per frame)."""
+    from mdhelper_b200.universe import SyntheticUniverse
+    rng = np.random.default_rng(12)
+    F, n = 5, 2500
+    edges = np.array([[9.1, 9.4, 9.7], [9.3, 9.2, 10.4], [12.9, 9.05, 9.6], [9.0, 9.0, 9.0],
+                      [15.5, 12.5, 9.9]], np.float32)
+    pos = (rng.random((F, n, 3)) * edges[:, None, :]).astype(np.float32)
+    dims = np.concatenate([edges, np.full((F, 3), 90, np.float32)], axis=1)
+    u = SyntheticUniverse(pos, dims)
+    S = _structure()
+    for sel, excl in [((u.atoms, None), None), ((u.select(slice(0, 900)),
+                                                 u.select(slice(900, n))), None),
+                      ((u.atoms, None), (5, 5))]:
+        kw = dict(n_bins=60, range=(0.0, 3.0), norm=None, exclusion=excl)
+        want = _oracle().rdf_run(u, sel[0], sel[1], method="bruteforce", **kw)["counts"]
+        for arith in ("auto", "off", "audit"):
+            r = S.RadialDistributionFunction(sel[0], sel[1], verbose=False, mode="cells",
+                                             arith=arith, **kw).run()
+            assert np.array_equal(r.results.counts, want)
+            assert r._filter_stats["audit_violations"] == 0
+
+
+@pytest.mark.parametrize("exclusion", [(2, 3), (3, 1)])
+def test_same_group_with_unequal_exclusion_blocks(exclusion):
+    """ag1 is ag2 with exclusion[0] != exclusion[1]: i // e0 == j // e1 is not symmetric,
+    so the pair symmetry must not be used (structure.py:100-102)."""
+    from mdhelper_b200 import synthetic
+    u = synthetic.lj_fluid(1200, 2, seed=17)
+    L = float(u.dimensions[0])
+    S = _structure()
+    kw = dict(n_bins=50, range=(0.0, L / 2), norm=None, exclusion=exclusion)
+    want = _oracle().rdf_run(u, u.atoms, **kw)["counts"]
+    for mode, rng_ in [("allpairs", (0.0, L / 2)), ("cells", (0.0, L / 3.3))]:
+        kw["range"] = rng_
+        want = _oracle().rdf_run(u, u.atoms, **kw)["counts"]
+        for arith in ("auto", "off", "audit"):
+            r = S.RadialDistributionFunction(u.atoms, verbose=False, mode=mode, arith=arith,
+                                             **kw).run()
+            assert np.array_equal(r.results.counts, want), (mode, arith)
+    p = u.trajectory.coordinates[0]
+    got = S.radial_histogram(p, p, 50, (0.0, L / 2), u.dimensions, exclusion=exclusion)
+    assert np.array_equal(got, _oracle().radial_histogram(p, p, 50, (0.0, L / 2), u.dimensions,
+                                                          exclusion=exclusion))
+    from mdhelper_b200 import _lib
+    ctx = _lib.Context(0)
+    with pytest.raises(ValueError):        # the C ABI refuses the unsound combination
+        ctx.rdf_configure(8, 8, True, np.array([0.0, 1.0, 4.0]), 0.0, 2.0, exclusion=(2, 3))
+    ctx.close()
+
+
 def test_same_group_symmetry_and_self_pairs():
     """ag1 is ag2: ordered pairs, N self pairs in bin 0."""
     from mdhelper_b200 import synthetic
@@ -346,6 +440,28 @@ def test_large_cutoff_run_modes_agree():
                              frames=[0], method="nsgrid")["counts"]
     one = S.RadialDistributionFunction(u.atoms, **kw).run(stop=1).results.counts
     assert np.array_equal(one, want)
+
+
+@pytest.mark.parametrize("which", ["cfg3", "cfg5"])
+def test_full_size_cutoff_frames_against_oracle(which):
+    """One frame at the size of BASELINE configs 3 and 5 (500,000-particle LJ fluid,
+    1,000,000-bead melt; cut-off 2.5) against the oracle's grid search, plus the fp64
+    kernel and the audited filter on the same frame."""
+    from mdhelper_b200 import synthetic
+    if which == "cfg3":
+        u = synthetic.lj_fluid(500_000, 1, seed=20260003)
+    else:
+        u = synthetic.polymer_melt(10_000, 100, 1, seed=20260005)
+    S = _structure()
+    kw = dict(n_bins=100, range=(0.0, 2.5), norm=None)
+    want = _oracle().rdf_run(u, u.atoms, method="nsgrid", **kw)["counts"]
+    r = S.RadialDistributionFunction(u.atoms, verbose=False, **kw).run()
+    assert np.array_equal(r.results.counts, want)
+    assert r._filter_stats["eligible"] == 1 and r._filter_stats["declined_frames"] == 0
+    for arith in ("off", "audit"):
+        x = S.RadialDistributionFunction(u.atoms, verbose=False, arith=arith, **kw).run()
+        assert np.array_equal(x.results.counts, want)
+        assert x._filter_stats["audit_violations"] == 0
 
 
 def test_host_batches_in_overlapped_pieces():

@@ -410,3 +410,49 @@ def test_sq_dmma_plan_fuzz():
         assert (plan["coverage"] == 1).all()
         assert plan["pair_rule_violations"] == 0
         assert 1 <= plan["warps_per_block"] <= 14 and plan["tiles"] * 64 >= len(pts)
+
+
+def test_ring_trajectory_and_feeder_runs():
+    """A RingTrajectory (frame f = ring[f % period]) is fed without copies: runs never
+    straddle the wrap, pointers and strides address the right ring slots."""
+    import ctypes
+    from mdhelper_b200.analysis.base import FrameFeeder, _is_contiguous, _runs_in_ring
+    from mdhelper_b200.universe import SyntheticUniverse
+    assert list(_runs_in_ring(np.arange(20), 1, 8, 5)) == [(0, 5), (5, 3), (8, 5), (13, 3),
+                                                            (16, 4)]
+    assert list(_runs_in_ring(np.arange(20), 1, 0, 6)) == [(0, 6), (6, 6), (12, 6), (18, 2)]
+    for first, cnt in _runs_in_ring(np.arange(3, 40, 3), 3, 8, 4):
+        slots = (np.arange(3, 40, 3)[first:first + cnt]) % 8
+        assert np.all(np.diff(slots) == 3)
+    pos = np.arange(4 * 5 * 3, dtype=np.float32).reshape(4, 5, 3)
+    u = SyntheticUniverse(pos, np.array([9, 9, 9, 90, 90, 90], np.float32), n_frames=11)
+    traj = u.trajectory
+    assert len(traj) == 11 and traj.unitcells.shape == (11, 6)
+    assert np.array_equal(traj[9].positions, pos[1]) and traj[9].frame == 9
+    feeder = FrameFeeder(traj, [np.arange(1, 4)], np.arange(2, 11), 3)
+    assert feeder.zero_copy
+    seen = []
+    for b in feeder:
+        assert b.strides == [15] and b.dims.shape == (b.n_frames, 6)
+        for k in range(b.n_frames):
+            a = np.ctypeslib.as_array(
+                (ctypes.c_float * 9).from_address(b.ptrs[0] + 4 * 15 * k)).reshape(3, 3)
+            seen.append(a.copy())
+    want = [pos[f % 4, 1:4] for f in range(2, 11)]
+    assert len(seen) == 9 and all(np.array_equal(a, w) for a, w in zip(seen, want))
+    assert _is_contiguous([3, 4, 5]) and not _is_contiguous([0, 2, 1, 3])
+    assert not _is_contiguous([1, 1, 2]) and not _is_contiguous([])
+
+
+def test_combined_analysis_rejects_classes_with_their_own_frame_loop():
+    from mdhelper_b200.analysis import CombinedAnalysis
+    from mdhelper_b200.analysis.structure import (IntermediateScatteringFunction,
+                                                  RadialDistributionFunction)
+    from mdhelper_b200.universe import SyntheticUniverse
+    pos = np.random.default_rng(0).random((3, 40, 3)).astype(np.float32) * 5
+    u = SyntheticUniverse(pos, np.array([5, 5, 5, 90, 90, 90], np.float32))
+    rdf = RadialDistributionFunction(u.atoms, n_bins=10, range=(0.0, 2.0), verbose=False)
+    isf = IntermediateScatteringFunction([u.atoms], n_points=3, verbose=False)
+    with pytest.raises(TypeError):
+        CombinedAnalysis(rdf, isf)
+    CombinedAnalysis(rdf)                      # the plain classes are accepted

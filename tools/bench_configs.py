@@ -49,6 +49,8 @@ def rdf_report(name, rdf, n_pairs_frame, **run_kw):
         "ordered_pairs_considered_per_s_kernel":
             n_pairs_frame * rdf.n_frames / (kms * 1e-3) if kms else None,
         "fp64_pipe_frac": (ev0 * 21 / (kms * 1e-3)) / 18529.6e9 if kms else None,
+        "kernel_us_per_frame": 1e3 * kms / rdf.n_frames if kms else None,
+        "filter_stats": rdf._filter_stats,
         "counts_sum": int(rdf.results.counts.sum()),
     }
     print(json.dumps(out), flush=True)
@@ -67,11 +69,11 @@ def main():
                                          verbose=False, batch_frames=100)
         rdf_report("cfg2: cation-anion RDF, 20k ions, 400 of 2,000 frames", rdf, 10 ** 8)
     if "cfg3" in which:
-        u = synthetic.lj_fluid(500_000, 16, seed=20260003)
+        u = synthetic.lj_fluid(500_000, 64, seed=20260003)
         for mode in ("cells",):
             rdf = RadialDistributionFunction(u.atoms, n_bins=100, range=(0.0, 2.5),
-                                             verbose=False, mode=mode, batch_frames=8)
-            rdf_report(f"cfg3: RDF cut-off 2.5, 500k LJ, 16 frames, mode={mode}", rdf,
+                                             verbose=False, mode=mode, batch_frames=32)
+            rdf_report(f"cfg3: RDF cut-off 2.5, 500k LJ, 64 frames, mode={mode}", rdf,
                        500_000 ** 2)
     if "cfg4" in which:
         u = synthetic.lj_fluid(50_000, 256, seed=20260004)
@@ -86,16 +88,16 @@ def main():
                           "fp64_pipe_frac": 50_000 * nq * sf.n_frames * 4 / (sms * 1e-3)
                           / 18529.6e9}), flush=True)
     if "cfg5" in which:
-        u = synthetic.polymer_melt(10_000, 100, 4, seed=20260005)
+        u = synthetic.polymer_melt(10_000, 100, 16, seed=20260005)
         rdf = RadialDistributionFunction(u.atoms, n_bins=100, range=(0.0, 2.5),
-                                         verbose=False, batch_frames=4)
-        rdf_report("cfg5a: RDF cut-off 2.5, 1M-bead melt, 4 frames", rdf, 10 ** 12)
+                                         verbose=False, batch_frames=8)
+        rdf_report("cfg5a: RDF cut-off 2.5, 1M-bead melt, 16 frames", rdf, 10 ** 12)
         L = float(u.dimensions[0])
         sf = StructureFactor([u.atoms], n_points=32, q_max=2 * np.pi * 16 / L,
-                             verbose=False, batch_frames=4)
+                             verbose=False, batch_frames=8)
         dt, _, sms = timed(sf)
         nq = len(sf._wavenumbers)
-        print(json.dumps({"config": "cfg5b: S(q) 1M beads, n_max=16, 4 frames", "n_q": nq,
+        print(json.dumps({"config": "cfg5b: S(q) 1M beads, n_max=16, 16 frames", "n_q": nq,
                           "e2e_frames_per_s": sf.n_frames / dt, "kernel_ms": sms,
                           "kernel_frames_per_s": sf.n_frames / (sms * 1e-3),
                           "fp64_pipe_frac": 1e6 * nq * sf.n_frames * 4 / (sms * 1e-3)
@@ -103,14 +105,14 @@ def main():
         # the configuration as BASELINE.json names it: RDF + S(q) in ONE pass over each
         # uploaded frame
         from mdhelper_b200.analysis import CombinedAnalysis
-        both = CombinedAnalysis(rdf, sf, batch_frames=4)
+        both = CombinedAnalysis(rdf, sf, batch_frames=8)
         both.run()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         both.run()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        print(json.dumps({"config": "cfg5: combined RDF + S(q) pass, 1M beads, 4 frames",
+        print(json.dumps({"config": "cfg5: combined RDF + S(q) pass, 1M beads, 16 frames",
                           "e2e_frames_per_s": rdf.n_frames / dt, "e2e_s": dt}), flush=True)
 
 
