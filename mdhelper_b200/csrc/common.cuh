@@ -88,7 +88,7 @@ struct RdfState {
     DevBuf pk1, pk2;       // float4[F][npad]
     DevBuf boxes;          // FrameBox[F]
     DevBuf cell[10];       // cell-list scratch, layout in rdf_cells.cu
-    double cells_ws_mb = 48.0;   // working set of one group of frames (sort + pair kernel)
+    double cells_ws_mb = 96.0;   // working set of one group of frames (sort + pair kernel)
     int cells_chunk = 8;         // cells per work item of the cell-pair kernel
     int cells_ipt = 4;           // particles per lane of the cell-pair kernel (2 or 4)
     bool evals_dev_init = false;

@@ -59,7 +59,8 @@ struct CellGrid {          // per frame
 __device__ __forceinline__ int cell_coord(float x, double box, double inv_w, int nc)
 {
     double w = (double)x;
-    w -= floor(w / box) * box;               // into [0, box) for cell assignment only
+    if (!(w >= 0.0 && w < box))              // into [0, box) for cell assignment only
+        w -= floor(w / box) * box;
     int c = (int)(w * inv_w);
     return min(max(c, 0), nc - 1);
 }
@@ -89,7 +90,9 @@ __device__ __forceinline__ void load_xyz_256(const float *__restrict__ src, int6
 }
 
 // pass 1: cell of every particle, rank inside its cell (old value of the cell counter),
-// coordinate extents of the frame (order-preserving keys; ext == nullptr: not wanted)
+// coordinate extents of the frame (ext == nullptr: not wanted) as order-preserving keys:
+// ext[frame][0..2] = ~(smallest key) per axis, ext[frame][3..5] = largest key, both kept
+// with atomicMax so that one zero fill initialises them
 __global__ void __launch_bounds__(256)
     cells_bin_kernel(const float *__restrict__ raw, int64_t frame_stride, int n,
                      const CellGrid *__restrict__ grids, int *__restrict__ cnt, int cstride,
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(256)
         if (tid < 6) {
             unsigned v = red[0][tid];
             for (int w = 1; w < 8; ++w) v = tid < 3 ? min(v, red[w][tid]) : max(v, red[w][tid]);
-            if (tid < 3) { if (v != 0xffffffffu) atomicMin(&ext[frame * 6 + tid], v); }
+            if (tid < 3) { if (v != 0xffffffffu) atomicMax(&ext[frame * 6 + tid], ~v); }
             else if (v != 0u) atomicMax(&ext[frame * 6 + tid], v);
         }
     }
@@ -143,11 +146,17 @@ struct ScanFilter {            // optional: build the frames' FrameFilter in the
 };
 
 // pass 2: exclusive scan of the per-cell counts; grid = (frames, groups), one block each.
-// Every thread owns a contiguous run of counters (sum, block scan of the sums, write).
+// Tiles of kScanTile counters go through shared memory: coalesced load, every thread scans
+// its own 32 consecutive counters (rows padded by one word per 32: conflict-free), block
+// scan of the row sums by warp shuffles, coalesced store.
+constexpr int kScanTile = 32768;
+constexpr int kScanPer = kScanTile / 1024;
+
 __global__ void __launch_bounds__(1024)
     cells_scan_kernel(const int *__restrict__ cnt, int *__restrict__ start, int cstride,
                       int n_frames, const CellGrid *__restrict__ grids, const ScanFilter F)
 {
+    extern __shared__ int tile[];                      // kScanTile + kScanTile / 32 words
     __shared__ int warp_sums[32];
     const int frame = blockIdx.x, group = blockIdx.y;
     const int ncell = grids[frame].ncell;
@@ -155,37 +164,57 @@ __global__ void __launch_bounds__(1024)
     const int *c = cnt + base;
     int *s = start + base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (ncell + 1023) / 1024;
-    const int k0 = tid * per, k1 = min(ncell, k0 + per);
-    int local = 0;
-    for (int k = k0; k < k1; ++k) local += c[k];
-    int incl = local;
+    int carry = 0;
+    for (int t0 = 0; t0 < ncell; t0 += kScanTile) {
+        const int n = min(kScanTile, ncell - t0);
+        for (int k = tid; k < kScanTile; k += 1024) tile[k + (k >> 5)] = k < n ? c[t0 + k] : 0;
+        __syncthreads();
+        const int k0 = tid * kScanPer;
+        int v[kScanPer], local = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        int w = warp_sums[lane];
+        for (int j = 0; j < kScanPer; ++j) {
+            v[j] = tile[k0 + j + ((k0 + j) >> 5)];
+            local += v[j];
+        }
+        int incl = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += t;
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        warp_sums[lane] = w;
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        int run = carry + incl - local + (warp ? warp_sums[warp - 1] : 0);
+#pragma unroll
+        for (int j = 0; j < kScanPer; ++j) {
+            tile[k0 + j + ((k0 + j) >> 5)] = run;
+            run += v[j];
+        }
+        carry += warp_sums[31];
+        __syncthreads();
+        for (int k = tid; k < n; k += 1024) s[t0 + k] = tile[k + (k >> 5)];
+        __syncthreads();
     }
-    __syncthreads();
-    int run = incl - local + (warp ? warp_sums[warp - 1] : 0);
-    for (int k = k0; k < k1; ++k) {
-        s[k] = run;
-        run += c[k];
+    if (tid == 0) s[ncell] = carry;
+    if (F.out != nullptr && group == 0 && tid == 0) {
+        unsigned e1[6], e2[6];
+        for (int k = 0; k < 6; ++k) {
+            const unsigned a = F.ext1[frame * 6 + k], b = F.ext2[frame * 6 + k];
+            e1[k] = k < 3 ? ~a : a;
+            e2[k] = k < 3 ? ~b : b;
+        }
+        F.out[frame] = filter_prepare_frame(F.boxes[frame], e1, e2, F.prep);
     }
-    if (tid == 1023) s[ncell] = warp_sums[31];
-    if (F.out != nullptr && group == 0 && tid == 0)
-        F.out[frame] = filter_prepare_frame(F.boxes[frame], F.ext1 + frame * 6,
-                                            F.ext2 + frame * 6, F.prep);
 }
 
 // pass 3: raw -> cell-sorted float4 (x, y, z, exclusion block id)
@@ -411,6 +440,7 @@ struct CellPairParams {
     int max_ncell;                // largest cell count of the frames of this launch
     int chunk_cells;              // cells per work item
     int cap;                      // buffer capacity in particles (multiple of 32)
+    unsigned long long sign2;     // 0x8000000080000000: the sign bits of a packed f32x2
 };
 
 __host__ __device__ inline size_t cp_smem_bytes(int n_bins, int sb, int cap)
@@ -447,6 +477,82 @@ __device__ __forceinline__ void cp_bulk_g2s(unsigned dst, const void *src, unsig
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- cold paths, kept out of line so that the hot loops stay small in the instruction
+// cache (the first version inlined them and spent most of its stall cycles waiting for
+// instructions) ---------------------------------------------------------------------------
+
+// fp64 re-evaluation of the uncertain pairs between the lane particles ip[0 .. nv) and the
+// candidate *jp: the main loop has added every one of them to the slot the fp32 arithmetic
+// suggested; move the count if the reference arithmetic disagrees.  A pair with
+// ip + k == jp is a self pair (own-cell pass) and was never counted.
+template <bool EXCL, bool LOWER, int IPT>
+__device__ __noinline__ void cp_fix(const CellPairParams &P, int frame, const float4 *ip, int nv,
+                                    const float4 *jp, unsigned weight, const double *sT,
+                                    unsigned hist32)
+{
+    const FrameFilter ff = P.filt[frame];
+    const FrameBox fb = P.boxes[frame];
+    const FilterConst fc = P.fc;
+    const float4 pj = *jp;
+    const unsigned span_l = LOWER ? fc.span : fc.cbits + fc.span;
+    const int shift = fc.k - fc.sb;
+    for (int k0 = 0; k0 < IPT; k0 += 2) {
+        // the same fp32 function as the main loop (identical bits); which two particles
+        // share a packed instruction does not matter, the halves are independent
+        const float4 a0 = ip[min(k0, nv - 1)], a1 = ip[min(k0 + 1, nv - 1)];
+        unsigned uu[2];
+        filter_eval2<LOWER>(pk2(-a0.x, -a1.x), pk2(-a0.y, -a1.y), pk2(-a0.z, -a1.z),
+                            pk2(pj.x, pj.x), pk2(pj.y, pj.y), pk2(pj.z, pj.z), ff, fc.scale,
+                            ff.offm, fc.cbits, uu[0], uu[1]);
+        for (int h = 0; h < 2; ++h) {
+            const int k = k0 + h;
+            const float4 a = h ? a1 : a0;
+            const unsigned u = uu[h];
+            if (k >= nv || ip + k == jp) continue;
+            if (!(u < span_l) || !((u & ((1u << fc.k) - 1u)) < ff.wlim)) continue;
+            if (EXCL && __float_as_int(a.w) == __float_as_int(pj.w)) continue;
+            const unsigned word = (LOWER ? u : u - fc.cbits) >> shift;
+            const double d2 = pair_d2(a.x, a.y, a.z, pj, fb);
+            const int slot = P.fast_bins ? slot_fast(d2, sT, P.n_bins, P.guess)
+                                         : slot_search(d2, sT, P.n_bins);
+            if ((word >> fc.sb) == (unsigned)slot) continue;
+            red_shared(hist32 + 4u * word, 0u - weight);
+            red_shared(hist32 + 4u * ((unsigned)slot << fc.sb), weight);
+        }
+    }
+}
+
+// A cell whose candidate list does not fit the per-warp buffer (a cluster far denser than
+// the average): every pair through the reference's fp64 arithmetic, straight from global
+// memory, one particle per lane.  wrng: the runs planned by issue().
+template <bool HALF, bool EXCL>
+__device__ __noinline__ void cp_long_cell(const CellPairParams &P, int frame, const int2 *wrng,
+                                          const double *sT, unsigned hist32, int sb, int lane)
+{
+    const FrameBox fb = P.boxes[frame];
+    const float4 *s1 = P.s1 + (int64_t)frame * P.n1;
+    const float4 *s2 = P.s2 + (int64_t)frame * P.n2;
+    const int2 own = wrng[0];
+    for (int i0 = 0; i0 < own.y; i0 += 32) {
+        const int i = i0 + lane;
+        const bool valid = i < own.y;
+        const float4 a = s1[own.x + min(i, own.y - 1)];
+        for (int r = HALF ? 0 : 1; r < kCpRanges; ++r) {
+            const int2 rg = wrng[r];
+            const unsigned w = (HALF && r > 0) ? 2u : 1u;
+            for (int j = 0; j < rg.y; ++j) {
+                const float4 pj = __ldg(s2 + rg.x + j);
+                if (!valid || (HALF && r == 0 && j == i)) continue;
+                if (EXCL && __float_as_int(a.w) == __float_as_int(pj.w)) continue;
+                const double d2 = pair_d2(a.x, a.y, a.z, pj, fb);
+                const int slot = slot_search(d2, sT, P.n_bins);
+                if ((unsigned)(slot - 1) < (unsigned)P.n_bins)
+                    red_shared(hist32 + 4u * ((unsigned)slot << sb), w);
+            }
+        }
+    }
 }
 
 template <bool HALF, bool EXCL, bool LOWER, bool AUDIT, int IPT>
@@ -525,7 +631,7 @@ __global__ void __launch_bounds__(kCpThreads, 2)
         // Plans the candidate list of `cell` into buffer `slot` and starts its copy.
         // Lane r describes run r: r = 0 the cell's own particles (group 1), r >= 1 the
         // stencil runs of group 2.  Returns (warp-uniform) n_i, total and the mode:
-        // 0 empty cell, 1 buffered (copy in flight), 2 too long for the buffer.
+        // 0 nothing to do, 1 buffered (copy in flight), 2 too long for the buffer.
         auto issue = [&](int cell, int slot, int &n_i, int &total) -> int {
             const float4 *s1 = P.s1 + (int64_t)frame * P.n1;
             const float4 *s2 = P.s2 + (int64_t)frame * P.n2;
@@ -540,21 +646,16 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                 len = st1[cell + 1] - b;
             } else if (lane < kCpRanges) {
                 const int r = lane - 1;              // 0..17: row r / 2, run r & 1
-                int row_i = r >> 1;                  // 0..8 = (dz + 1) * 3 + (dy + 1)
-                int dz = row_i / 3 - 1, dy = row_i % 3 - 1;
-                bool use = true;
+                const int row_i = r >> 1;            // 0..8 = (dz + 1) * 3 + (dy + 1)
+                const int dz = row_i / 3 - 1, dy = row_i % 3 - 1;
+                // same group: forward half only -- the rows at z + 1 (all dy), the row
+                // (y + 1, z) and the cell (x + 1, y, z) of the own row
+                bool use = !HALF || dz == 1 || (dz == 0 && dy >= 0);
                 int xa, xb;                          // cells [xa, xb] of the row
-                if (HALF) {
-                    // forward half: rows at z + 1 (all dy), row (y + 1, z), and the cell
-                    // (x + 1, y, z) of the own row
-                    use = dz == 1 || (dz == 0 && dy >= 0);
-                }
                 const int y = wrap(cy + dy, ncy), z = wrap(cz + dz, ncz);
                 const int row = (z * ncy + y) * ncx;
                 if (HALF && dz == 0 && dy == 0) {
-                    // own row: only x + 1 (the own cell is run 0)
-                    const int xr = wrap(cx + 1, ncx);
-                    xa = xb = xr;
+                    xa = xb = wrap(cx + 1, ncx);
                     use = (r & 1) == 0;
                 } else if ((r & 1) == 0) {
                     xa = max(cx - 1, 0); xb = min(cx + 1, ncx - 1);
@@ -590,15 +691,9 @@ __global__ void __launch_bounds__(kCpThreads, 2)
             return 1;
         };
 
-        // All pairs of the cell's particles [off, off + cn) with the candidates.
-        // SLOW: candidates come from global memory (list too long for the buffer),
-        // uncertain pairs are then re-evaluated on the spot.
-        auto compute = [&](int cell, int slot, int n_i, int total, auto slow_tag) {
-            constexpr bool SLOW = decltype(slow_tag)::value;
+        // All pairs of the cell's particles with the candidates in buffer `slot`.
+        auto compute = [&](int slot, int n_i, int total) {
             const float4 *buf = wbuf + slot * bufw;
-            const float4 *s2 = P.s2 + (int64_t)frame * P.n2;
-            const float4 *own =
-                SLOW ? P.s1 + (int64_t)frame * P.n1 + wrng[slot * 32].x : buf;
             const int n_chunks = (n_i + 8 * IPT - 1) / (8 * IPT);
             const int cs = (n_i + n_chunks - 1) / n_chunks;
             for (int off = 0; off < n_i; off += cs) {
@@ -617,26 +712,20 @@ __global__ void __launch_bounds__(kCpThreads, 2)
 #pragma unroll
                     for (int k = 0; k < IPT; ++k) {
                         if (lane_ok && ipos0 + k < off + cn) vmask |= 1u << k;
-                        a[k] = own[min(ipos0 + k, n_i - 1)];
+                        a[k] = buf[min(ipos0 + k, n_i - 1)];
                         gi[k] = __float_as_int(a[k].w);
                     }
 #pragma unroll
                     for (int ip = 0; ip < IPT / 2; ++ip) {
-                        // negated by an (exact) packed multiplication: its result is a fresh
-                        // aligned register pair -- packed from the halves of two LDS.128
-                        // quads, ptxas re-assembles the pair with two moves at every use
-                        const f32x2 m1 = pk2(-1.f, -1.f);
-                        nx[ip] = mul2(pk2(a[2 * ip].x, a[2 * ip + 1].x), m1);
-                        ny[ip] = mul2(pk2(a[2 * ip].y, a[2 * ip + 1].y), m1);
-                        nz[ip] = mul2(pk2(a[2 * ip].z, a[2 * ip + 1].z), m1);
+                        // negated by flipping the sign bits with a mask the compiler cannot
+                        // see through (a kernel parameter): the result is a fresh aligned
+                        // register pair.  Packed from the halves of two LDS.128 quads,
+                        // ptxas would re-assemble the pair with two moves at every use.
+                        nx[ip] = pk2(a[2 * ip].x, a[2 * ip + 1].x) ^ P.sign2;
+                        ny[ip] = pk2(a[2 * ip].y, a[2 * ip + 1].y) ^ P.sign2;
+                        nz[ip] = pk2(a[2 * ip].z, a[2 * ip + 1].z) ^ P.sign2;
                     }
                 }
-                auto coords_of = [&](int k, float &x, float &y, float &z) {
-                    float lo, hi;
-                    upk2(nx[k >> 1], lo, hi); x = -((k & 1) ? hi : lo);
-                    upk2(ny[k >> 1], lo, hi); y = -((k & 1) ? hi : lo);
-                    upk2(nz[k >> 1], lo, hi); z = -((k & 1) ? hi : lo);
-                };
 
                 // the packed fp32 arithmetic of one candidate against the lane's particles
                 auto eval_row = [&](const float4 &pj, unsigned *uu) {
@@ -645,28 +734,6 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                         filter_eval2<LOWER>(nx[ip], ny[ip], nz[ip], pk2(pj.x, pj.x),
                                             pk2(pj.y, pj.y), pk2(pj.z, pj.z), ff, scale, offm,
                                             fc.cbits, uu[2 * ip], uu[2 * ip + 1]);
-                };
-                // fp64 re-evaluation of the uncertain pairs among uu[0..IPT): move the
-                // count if the reference arithmetic puts the pair into another slot
-                auto fix = [&](const float *fx, const float *fy, const float *fz, const int *fg,
-                               unsigned fmask_v, int fi0, const float4 &pj, const unsigned *uu,
-                               int jpos, bool self, unsigned weight) {
-                    const FrameBox fb = P.boxes[frame];
-#pragma unroll
-                    for (int k = 0; k < IPT; ++k) {
-                        const unsigned u = uu[k];
-                        if (!((fmask_v >> k) & 1u) || !(u < span_l) || !((u & fmask) < ff.wlim))
-                            continue;
-                        if (EXCL && fg[k] == __float_as_int(pj.w)) continue;
-                        if (self && jpos == fi0 + k) continue;
-                        const unsigned word = (LOWER ? u : u - fc.cbits) >> shift;
-                        const double d2 = pair_d2(fx[k], fy[k], fz[k], pj, fb);
-                        const int slot_e = P.fast_bins ? slot_fast(d2, sT, n_bins, P.guess)
-                                                       : slot_search(d2, sT, n_bins);
-                        if ((word >> fc.sb) == (unsigned)slot_e) continue;
-                        red_shared(hist32 + 4u * word, 0u - weight);
-                        red_shared(hist32 + 4u * ((unsigned)slot_e << fc.sb), weight);
-                    }
                 };
                 // histogram updates of one row (wk: weight per particle, 0 = absent);
                 // returns the smallest fraction of the row's bin coordinates
@@ -677,16 +744,19 @@ __global__ void __launch_bounds__(kCpThreads, 2)
 #pragma unroll
                     for (int k = 0; k < IPT; ++k) {
                         const unsigned u = uu[k];
-                        vmin = min(vmin, u & fmask);
                         unsigned w = min(u >> shift, trash_w);
                         if (EXCL && gi[k] == __float_as_int(pj.w)) w = trash_w;
-                        if (SELF && jpos == ipos0 + k) w = trash_w;
+                        if (SELF && jpos == ipos0 + k) {
+                            // a particle with itself: never counted here, never uncertain
+                            w = trash_w;
+                        } else {
+                            vmin = min(vmin, u & fmask);
+                        }
                         red_shared_hot(hbase + (w << 2), wk[k]);
                         if (AUDIT && wk[k] != 0u && !(SELF && jpos == ipos0 + k)) {
                             const bool unc = (u & fmask) < ff.wlim, in = u < span_l;
-                            float x, y, z;
-                            coords_of(k, x, y, z);
-                            const double d2 = pair_d2(x, y, z, pj, P.boxes[frame]);
+                            const float4 a = buf[ipos0 + k];
+                            const double d2 = pair_d2(a.x, a.y, a.z, pj, P.boxes[frame]);
                             const int slot_e = slot_search(d2, sT, n_bins);
                             const unsigned fs = in ? ((LOWER ? u : u - fc.cbits) >> fc.k)
                                                    : (unsigned)(n_bins + 1);
@@ -699,40 +769,26 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                     }
                     return vmin;
                 };
-                // a row with an uncertain pair: remember it (re-evaluated after the pass),
-                // or re-evaluate on the spot (list full / candidates not in the buffer)
-                auto push_row = [&](const float4 &pj, const unsigned *uu, int jpos,
-                                    unsigned weight, bool self) {
-                    bool inl = SLOW;
-                    if (!SLOW) {
-                        const unsigned idx = atomicAdd(wcount, 1u);
-                        if (idx < (unsigned)kCpListCap)
-                            wlist[idx] = (self ? 0x80000000u : 0u) | ((unsigned)lane << 16) |
-                                         (unsigned)jpos;
-                        else
-                            inl = true;
-                    }
-                    if (inl) {
-                        float fx[IPT], fy[IPT], fz[IPT];
-#pragma unroll
-                        for (int k = 0; k < IPT; ++k) coords_of(k, fx[k], fy[k], fz[k]);
-                        fix(fx, fy, fz, gi, vmask, ipos0, pj, uu, jpos, self, weight);
+                // a row with an uncertain pair: remember it (re-evaluated after the pass), or
+                // re-evaluate on the spot when the list is full
+                auto push_row = [&](int jpos, unsigned weight) {
+                    const unsigned idx = atomicAdd(wcount, 1u);
+                    if (idx < (unsigned)kCpListCap) {
+                        wlist[idx] = ((unsigned)lane << 16) | (unsigned)jpos;
+                    } else {
+                        cp_fix<EXCL, LOWER, IPT>(P, frame, buf + ipos0,
+                                                 min(IPT, off + cn - ipos0), buf + jpos, weight,
+                                                 sT, hist32);
                         ++n_inline;
                     }
                 };
-                // candidates list[0 .. cnt): lane (way, il) takes list[way], list[way + ways],
-                // ...; two rows per iteration, the next two fetched ahead.  jpos0: position
-                // of list[0] in the own-cell numbering (self test) / in the buffer.
-                auto run_list = [&](const float4 *list, int jpos0, int cnt, unsigned weight,
-                                    auto self_tag) {
-                    constexpr bool SELF = decltype(self_tag)::value;
+                // candidates buf[jb .. jb + cnt): lane (way, il) takes jb + way, jb + way +
+                // ways, ...; two rows per iteration, the next two fetched ahead (rows past
+                // the list are clamped to its last entry and carry weight 0)
+                auto run_list = [&](int jb, int cnt, unsigned weight, auto self_tag) {
                     if (cnt <= 0) return;
                     const int full = cnt / ways, rem = cnt - full * ways;
-                    const int omax = cnt - 1;
-                    auto ld = [&](int o) -> float4 {
-                        const float4 *q = list + min(o, omax);
-                        return SLOW ? __ldg(q) : *q;
-                    };
+                    const int jmax = jb + cnt - 1;
                     unsigned wi[IPT];
 #pragma unroll
                     for (int k = 0; k < IPT; ++k) {
@@ -740,88 +796,62 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                         // keep the weights in registers (as predicates they cost a SEL per pair)
                         asm volatile("" : "+r"(wi[k]));
                     }
-                    int o = lane_ok ? way : 0;
-                    float4 r0 = ld(o), r1 = ld(o + ways);
+                    int j = jb + (lane_ok ? way : 0);
+                    float4 r0 = buf[min(j, jmax)], r1 = buf[min(j + ways, jmax)];
                     int t = 0;
-#pragma unroll 2
+#pragma unroll 1
                     for (; t + 2 <= full; t += 2) {
                         const float4 a0 = r0, a1 = r1;
-                        r0 = ld(o + 2 * ways);
-                        r1 = ld(o + 3 * ways);
+                        r0 = buf[min(j + 2 * ways, jmax)];
+                        r1 = buf[min(j + 3 * ways, jmax)];
                         unsigned u0[IPT], u1[IPT];
                         eval_row(a0, u0);
                         eval_row(a1, u1);
-                        const unsigned v0 = hist_row(a0, u0, jpos0 + o, wi, self_tag);
-                        const unsigned v1 = hist_row(a1, u1, jpos0 + o + ways, wi, self_tag);
+                        const unsigned v0 = hist_row(a0, u0, j, wi, self_tag);
+                        const unsigned v1 = hist_row(a1, u1, j + ways, wi, self_tag);
                         if (min(v0, v1) < ff.wlim && lane_ok) {
-                            if (v0 < ff.wlim) push_row(a0, u0, jpos0 + o, weight, SELF);
-                            if (v1 < ff.wlim) push_row(a1, u1, jpos0 + o + ways, weight, SELF);
+                            if (v0 < ff.wlim) push_row(j, weight);
+                            if (v1 < ff.wlim) push_row(j + ways, weight);
                         }
-                        o += 2 * ways;
+                        j += 2 * ways;
                     }
-                    // at most one more full row, then the partial row
-                    if (t < full) {
-                        unsigned u0[IPT];
-                        eval_row(r0, u0);
-                        const unsigned v0 = hist_row(r0, u0, jpos0 + o, wi, self_tag);
-                        if (v0 < ff.wlim && lane_ok) push_row(r0, u0, jpos0 + o, weight, SELF);
-                        o += ways;
-                        r0 = r1;
-                    }
-                    if (rem) {
-                        unsigned u0[IPT], wm[IPT];
+                    // at most one more full row and the partial row: one more pass of the
+                    // same code, weights of the rows that do not exist set to 0
+                    const int left = (full - t) + (rem ? 1 : 0);      // 0, 1 or 2 rows
+                    if (left > 0) {
+                        unsigned w0[IPT], w1[IPT];
+                        const bool ok0 = lane_ok && (t < full || way < rem);
+                        const bool ok1 = lane_ok && left == 2 && way < rem;
 #pragma unroll
-                        for (int k = 0; k < IPT; ++k) wm[k] = way < rem ? wi[k] : 0u;
+                        for (int k = 0; k < IPT; ++k) {
+                            w0[k] = ok0 ? wi[k] : 0u;
+                            w1[k] = ok1 ? wi[k] : 0u;
+                        }
+                        unsigned u0[IPT], u1[IPT];
                         eval_row(r0, u0);
-                        const unsigned v0 = hist_row(r0, u0, jpos0 + o, wm, self_tag);
-                        if (v0 < ff.wlim && lane_ok && way < rem)
-                            push_row(r0, u0, jpos0 + o, weight, SELF);
+                        eval_row(r1, u1);
+                        const unsigned v0 = hist_row(r0, u0, j, w0, self_tag);
+                        const unsigned v1 = hist_row(r1, u1, j + ways, w1, self_tag);
+                        if (v0 < ff.wlim && ok0) push_row(j, weight);
+                        if (v1 < ff.wlim && ok1) push_row(j + ways, weight);
                     }
                 };
 
-                using yes = std::integral_constant<bool, true>;
-                using no = std::integral_constant<bool, false>;
                 const unsigned w_fwd = HALF ? 2u : 1u;
-                if (!SLOW) {
-                    if (HALF) run_list(buf, 0, n_i, 1u, yes());
-                    run_list(buf + n_i, n_i, total - n_i, w_fwd, no());
-                } else {
-                    if (HALF) run_list(own, 0, n_i, 1u, yes());
-                    for (int r = 1; r < kCpRanges; ++r) {
-                        const int2 rg = wrng[slot * 32 + r];
-                        run_list(s2 + rg.x, n_i, rg.y, w_fwd, no());
-                    }
-                }
+                if (HALF) run_list(0, n_i, 1u, std::integral_constant<bool, true>());
+                run_list(n_i, total - n_i, w_fwd, std::integral_constant<bool, false>());
                 __syncwarp();
 
-                // drain: the uncertain pairs of this pass, re-evaluated from the buffer
-                if (!SLOW) {
-                    const unsigned n_push = *wcount;
+                // drain: the uncertain rows of this pass, re-evaluated from the buffer
+                const unsigned n_push = *wcount;
+                if (n_push) {
                     const unsigned n_list = min(n_push, (unsigned)kCpListCap);
                     for (unsigned e = lane; e < n_list; e += 32) {
                         const unsigned entry = wlist[e];
-                        const bool self = (entry >> 31) != 0u;
-                        const int src = (int)((entry >> 16) & 0x7fffu), jpos = (int)(entry & 0xffffu);
-                        const int e_il = src - (src / ni) * ni, e_i0 = off + e_il * IPT;
-                        const float4 pj = buf[jpos];
-                        float fx[IPT], fy[IPT], fz[IPT];
-                        int fg[IPT];
-                        unsigned fv = 0;
-#pragma unroll
-                        for (int k = 0; k < IPT; ++k) {
-                            const float4 a = buf[min(e_i0 + k, n_i - 1)];
-                            fx[k] = a.x; fy[k] = a.y; fz[k] = a.z; fg[k] = __float_as_int(a.w);
-                            if (e_i0 + k < off + cn) fv |= 1u << k;
-                        }
-                        unsigned uu[IPT];
-#pragma unroll
-                        for (int ip = 0; ip < IPT / 2; ++ip)
-                            filter_eval2<LOWER>(pk2(-fx[2 * ip], -fx[2 * ip + 1]),
-                                                pk2(-fy[2 * ip], -fy[2 * ip + 1]),
-                                                pk2(-fz[2 * ip], -fz[2 * ip + 1]), pk2(pj.x, pj.x),
-                                                pk2(pj.y, pj.y), pk2(pj.z, pj.z), ff, scale, offm,
-                                                fc.cbits, uu[2 * ip], uu[2 * ip + 1]);
-                        fix(fx, fy, fz, fg, fv, e_i0, pj, uu, jpos, self, self ? 1u : w_fwd);
+                        const int src = (int)(entry >> 16), jpos = (int)(entry & 0xffffu);
+                        const int e_i0 = off + (src - (src / ni) * ni) * IPT;
+                        cp_fix<EXCL, LOWER, IPT>(P, frame, buf + e_i0, min(IPT, off + cn - e_i0),
+                                                 buf + jpos, jpos < n_i ? 1u : w_fwd, sT, hist32);
                     }
                     n_deferred += n_list;
                     __syncwarp();
@@ -844,28 +874,29 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                     __syncwarp();
                 }
             }
-            if (lane == 0) {
-                my_evals += (unsigned long long)n_i *
-                            (unsigned long long)(HALF ? total : total - n_i);
-                if (count_self) red_shared(hist32 + 4u * ((unsigned)slot_zero << fc.sb), (unsigned)n_i);
-            }
         };
 
-        int ni_c = 0, tot_c = 0;
-        int mode_c = issue(c0, 0, ni_c, tot_c);
-        int slot = 0;
-        for (int cell = c0; cell < c1; ++cell) {
+        // software pipeline over the cells of the item: plan + copy of cell k + 1, then the
+        // pairs of cell k (one call site each)
+        int ni_c = 0, tot_c = 0, mode_c = 0;
+        for (int cell = c0 - 1; cell < c1; ++cell) {
             int ni_n = 0, tot_n = 0, mode_n = 0;
+            const int slot = (cell - c0) & 1;
             if (cell + 1 < c1) mode_n = issue(cell + 1, slot ^ 1, ni_n, tot_n);
             if (mode_c == 1) {
                 cp_mbar_wait(bar32 + 8u * slot, (phase >> slot) & 1u);
                 phase ^= 1u << slot;
-                compute(cell, slot, ni_c, tot_c, std::integral_constant<bool, false>());
+                compute(slot, ni_c, tot_c);
             } else if (mode_c == 2) {
-                compute(cell, slot, ni_c, tot_c, std::integral_constant<bool, true>());
+                cp_long_cell<HALF, EXCL>(P, frame, wrng + slot * 32, sT, hist32, fc.sb, lane);
+            }
+            if (mode_c != 0 && lane == 0) {
+                my_evals += (unsigned long long)ni_c *
+                            (unsigned long long)(HALF ? tot_c : tot_c - ni_c);
+                if (count_self)
+                    red_shared(hist32 + 4u * ((unsigned)slot_zero << fc.sb), (unsigned)ni_c);
             }
             ni_c = ni_n; tot_c = tot_n; mode_c = mode_n;
-            slot ^= 1;
         }
     }
     __syncthreads();
@@ -1030,14 +1061,8 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
     const bool excl = R.excl1 > 0, fast = R.fast_bins;
     for (int g0 = 0; g0 < n_frames; g0 += G) {
         const int ng = std::min(G, n_frames - g0);
-        // counters, extents (min keys start at all-ones, max keys at 0) and the work
-        // counter: one contiguous region, two memsets
+        // counters, extents and the work counter: one contiguous region, one zero fill
         MDH_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (work_off + 4), c->stream));
-        if (use_filter) {
-            rdf_ext_init_kernel<<<(12 * G + 255) / 256, 256, 0, c->stream>>>(d_ext, 12 * G);
-            MDH_CUDA(cudaGetLastError());
-            c->launches++;
-        }
         const CellGrid *gg = d_grids.as<CellGrid>() + g0;
         for (int grp = 0; grp < n_groups; ++grp) {
             const float *raw = (grp ? raw2 : raw1) + (int64_t)g0 * (grp ? stride2 : stride1);
@@ -1058,8 +1083,12 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
             F.out = R.filt.as<FrameFilter>();
             F.prep = rdf_filter_prep(R, sqrt_err);
         }
-        cells_scan_kernel<<<dim3(ng, n_groups), 1024, 0, c->stream>>>(d_cnt, d_start, cstride, G,
-                                                                     gg, F);
+        const size_t scan_smem = sizeof(int) * (kScanTile + kScanTile / 32);
+        MDH_CUDA(cudaFuncSetAttribute(cells_scan_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)scan_smem));
+        cells_scan_kernel<<<dim3(ng, n_groups), 1024, scan_smem, c->stream>>>(d_cnt, d_start,
+                                                                             cstride, G, gg, F);
         MDH_CUDA(cudaGetLastError());
         c->launches++;
         for (int grp = 0; grp < n_groups; ++grp) {
@@ -1100,6 +1129,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
             Q.max_ncell = ncell_max;
             Q.chunk_cells = R.cells_chunk;
             Q.cap = cap;
+            Q.sign2 = 0x8000000080000000ull;
             if (int rc = launch_cellpair(c, Q, R.same != 0, excl,
                                          R.filter_mode == MDH_FILTER_AUDIT, R.cells_ipt))
                 return rc;

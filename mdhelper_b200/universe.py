@@ -240,6 +240,32 @@ class AtomGroup:
     def atoms(self):
         return self
 
+    @property
+    def dimensions(self):
+        return self.universe.dimensions
+
+    def _entities(self, key):
+        # one group per residue / segment that has atoms in this group, in index order
+        # (what MDAnalysis' ``AtomGroup.residues`` / ``.segments`` iterate over); the
+        # reference's ``center_of_mass`` only uses ``entity.atoms`` of them
+        # (algorithm/molecule.py:232-236, 270-273)
+        return [AtomGroup(self.universe, self.ix[key == k]) for k in np.unique(key)]
+
+    @property
+    def residues(self):
+        return self._entities(self.resindices)
+
+    @property
+    def segments(self):
+        return self._entities(self.segindices)
+
+    def center_of_mass(self):
+        """Restated third-party ``MDAnalysis.core.groups.AtomGroup.center_of_mass`` [recall]:
+        float64 mass-weighted mean of the float32 coordinates.  The reference reaches it for
+        residues / segments of unequal size (algorithm/molecule.py:240-241)."""
+        w = self.masses.astype(np.float64, copy=False)
+        return (self.positions.astype(np.float64) * w[:, None]).sum(axis=0) / w.sum()
+
     def __len__(self):
         return self.ix.size
 

@@ -308,9 +308,60 @@ def scsf_cases(S):
           "wrapped vs unwrapped", np.abs(out["scsf_unwrap0"] - out["scsf_unwrap1"]).max())
 
 
+def com_cases(S):
+    """Centres of mass (groupings="residues"/"segments") from the reference's REAL
+    ``center_of_mass`` (algorithm/molecule.py:15-310, imported by structure.py:25) and the
+    real analysis classes on top of it.  Equal-sized residues go through its einsum
+    (:303-304) -- pure reference code; unequal sizes go through
+    ``g.atoms.center_of_mass()`` (:240-241), third-party MDAnalysis, restated in
+    mdhelper_b200.universe.AtomGroup.center_of_mass."""
+    import importlib
+    mol = importlib.import_module("mdhelper.algorithm.molecule")
+    assert S.center_of_mass is mol.center_of_mass
+    rng = np.random.default_rng(20260013)
+    out = {}
+    for tag, sizes in (("equal", np.full(150, 4)), ("unequal", rng.integers(1, 7, 160))):
+        n = int(sizes.sum())
+        L = np.float32(12.5)
+        pos = (rng.random((4, n, 3)) * float(L)).astype(np.float32)
+        res = np.repeat(np.arange(len(sizes)), sizes)
+        seg = res // 5
+        masses = rng.choice([1.008, 12.011, 14.007, 15.999, 32.06], n)
+        u = SyntheticUniverse(pos, np.array([L, L, L, 90, 90, 90], np.float32),
+                              resindices=res, segindices=seg, masses=masses)
+        out[f"{tag}_positions"] = pos
+        out[f"{tag}_dims"] = u.trajectory.unitcells[0].copy()
+        out[f"{tag}_resindices"], out[f"{tag}_segindices"] = res, seg
+        out[f"{tag}_masses"] = masses
+        n_a = int(np.searchsorted(res, len(sizes) // 3))       # a residue boundary
+        a, b = u.select(slice(0, n_a)), u.select(slice(n_a, n))
+        out[f"{tag}_n_a"] = n_a
+        # the centres themselves, frame by frame
+        for grouping in ("residues", "segments"):
+            com = []
+            for f in range(4):
+                u.trajectory[f]
+                com.append(np.asarray(mol.center_of_mass(u.atoms, grouping), np.float64))
+            out[f"{tag}_com_{grouping}"] = np.stack(com)
+        kw = dict(n_bins=40, range=(0.0, 6.0), verbose=False)
+        r = S.RadialDistributionFunction(a, b, groupings="residues", **kw).run()
+        out[f"{tag}_rdf_res_counts"], out[f"{tag}_rdf_res"] = r.results.counts, r.results.rdf
+        r = S.RadialDistributionFunction(u.atoms, groupings="segments", **kw).run()
+        out[f"{tag}_rdf_seg_counts"], out[f"{tag}_rdf_seg"] = r.results.counts, r.results.rdf
+        r = S.RadialDistributionFunction(a, b, groupings=("residues", "atoms"), **kw).run()
+        out[f"{tag}_rdf_mix_counts"], out[f"{tag}_rdf_mix"] = r.results.counts, r.results.rdf
+        s = S.StructureFactor([a, b], groupings="residues", mode="partial", n_points=5,
+                              verbose=False).run()
+        out[f"{tag}_ssf_res"], out[f"{tag}_ssf_wavenumbers"] = s.results.ssf, s.results.wavenumbers
+        print("com", tag, out[f"{tag}_com_residues"].shape, out[f"{tag}_rdf_res_counts"].sum())
+    np.savez_compressed(OUT / "com_ref.npz", **out)
+
+
 if __name__ == "__main__":
     S = ref_harness.load()
-    which = sys.argv[1:] or ["kat", "rdf", "post", "sq", "isf", "scsf"]
+    which = sys.argv[1:] or ["kat", "rdf", "post", "sq", "isf", "scsf", "com"]
+    if "com" in which:
+        com_cases(S)
     if "kat" in which:
         kat_radial_histogram(S)
     if "rdf" in which:

@@ -256,7 +256,7 @@ def test_cells_minimal_grid_and_changing_boxes():
     from mdhelper_b200.universe import SyntheticUniverse
     rng = np.random.default_rng(12)
     F, n = 5, 2500
-    edges = np.array([[9.1, 9.4, 9.7], [9.3, 9.2, 10.4], [12.9, 9.05, 9.6], [9.0, 9.0, 9.0],
+    edges = np.array([[9.1, 9.4, 9.7], [9.3, 9.2, 10.4], [12.9, 9.05, 9.6], [9.02, 9.01, 9.03],
                       [15.5, 12.5, 9.9]], np.float32)
     pos = (rng.random((F, n, 3)) * edges[:, None, :]).astype(np.float32)
     dims = np.concatenate([edges, np.full((F, 3), 90, np.float32)], axis=1)
@@ -391,6 +391,33 @@ def test_device_centres_of_mass_equal_host():
     r = S.RadialDistributionFunction(sc, groupings="residues", n_bins=20,
                                      range=(0.0, 5.0), verbose=False).run()
     assert r._com is None
+
+
+def _com_universe(g, tag):
+    from mdhelper_b200.universe import SyntheticUniverse
+    return SyntheticUniverse(g[f"{tag}_positions"], g[f"{tag}_dims"],
+                             resindices=g[f"{tag}_resindices"],
+                             segindices=g[f"{tag}_segindices"], masses=g[f"{tag}_masses"])
+
+
+@pytest.mark.parametrize("tag", ["equal", "unequal"])
+@pytest.mark.parametrize("host_com", [False, True])
+def test_groupings_against_the_reference_centres_of_mass(golden, tag, host_com):
+    """groupings="residues"/"segments": counts of the reference's own class running on its
+    own ``center_of_mass`` (algorithm/molecule.py:15-310; tests/golden/com_ref.npz), with
+    the device kernel (com.cu) and with the host helper."""
+    g = golden("com_ref")
+    u = _com_universe(g, tag)
+    n_a, n = int(g[f"{tag}_n_a"]), u.atoms.n_atoms
+    a, b = u.select(slice(0, n_a)), u.select(slice(n_a, n))
+    S = _structure()
+    kw = dict(n_bins=40, range=(0.0, 6.0), verbose=False, host_com=host_com)
+    for sel, grp, key in [((a, b), "residues", "res"), ((u.atoms, None), "segments", "seg"),
+                          ((a, b), ("residues", "atoms"), "mix")]:
+        r = S.RadialDistributionFunction(sel[0], sel[1], groupings=grp, **kw).run()
+        assert (r._com is None) == host_com
+        assert np.array_equal(r.results.counts, g[f"{tag}_rdf_{key}_counts"]), (tag, key)
+        np.testing.assert_allclose(r.results.rdf, g[f"{tag}_rdf_{key}"], rtol=1e-6)
 
 
 def test_config2_sized_frame_against_oracle():

@@ -410,3 +410,24 @@ def test_argument_errors():
     with pytest.raises(ValueError):
         ctx.sq_configure(4, [0, 4], wv, [(-1, -1)], mode="lattice_fp64")  # no lattice
     ctx.close()
+
+
+@pytest.mark.parametrize("tag", ["equal", "unequal"])
+def test_residue_structure_factor_against_the_reference(golden, tag):
+    """StructureFactor(groupings="residues") vs the reference's own class on its own
+    ``center_of_mass`` (tests/golden/com_ref.npz).  The centres are handed to the kernels
+    as float32 (the reference keeps them in a float64 buffer, structure.py:1468): phase
+    errors of q |r| 6e-8 leave ~1e-6 of S(q), hence the looser bound here."""
+    from mdhelper_b200.universe import SyntheticUniverse
+    g = golden("com_ref")
+    u = SyntheticUniverse(g[f"{tag}_positions"], g[f"{tag}_dims"],
+                          resindices=g[f"{tag}_resindices"],
+                          segindices=g[f"{tag}_segindices"], masses=g[f"{tag}_masses"])
+    n_a, n = int(g[f"{tag}_n_a"]), u.atoms.n_atoms
+    a, b = u.select(slice(0, n_a)), u.select(slice(n_a, n))
+    for host_com in (False, True):
+        s = _S().StructureFactor([a, b], groupings="residues", mode="partial", n_points=5,
+                                 verbose=False, host_com=host_com).run()
+        np.testing.assert_allclose(s.results.wavenumbers, g[f"{tag}_ssf_wavenumbers"],
+                                   rtol=1e-12)
+        np.testing.assert_allclose(s.results.ssf, g[f"{tag}_ssf_res"], rtol=2e-5, atol=2e-6)

@@ -152,3 +152,32 @@ def test_port_matches_live_reference():
     s = S.StructureFactor([cat, an], mode="partial", n_points=5, verbose=False).run()
     p = rp.ssf_run(u, [cat, an], mode="partial", n_points=5)
     np.testing.assert_allclose(p["ssf"], s.results.ssf, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["equal", "unequal"])
+def test_centres_of_mass_match_the_reference(golden, tag):
+    """The host centre-of-mass helper (whose operation order the device kernel follows) vs
+    the reference's real ``center_of_mass`` (algorithm/molecule.py:15-310; fixture made by
+    tests/golden/make_golden.py com): within one fp64 ulp, and identical after the
+    rounding to float32 that ``capped_distance`` applies to its inputs."""
+    from mdhelper_b200.analysis.structure import _centers_of_mass
+    from mdhelper_b200.universe import SyntheticUniverse
+    g = golden("com_ref")
+    u = SyntheticUniverse(g[f"{tag}_positions"], g[f"{tag}_dims"],
+                          resindices=g[f"{tag}_resindices"],
+                          segindices=g[f"{tag}_segindices"], masses=g[f"{tag}_masses"])
+    for grouping in ("residues", "segments"):
+        for f in range(4):
+            ts = u.trajectory[f]
+            got = _centers_of_mass(u.atoms, grouping, ts.positions)
+            want = g[f"{tag}_com_{grouping}"][f]
+            np.testing.assert_allclose(got, want, rtol=5e-16)
+            assert np.array_equal(got.astype(np.float32), want.astype(np.float32))
+    if ref_harness.available():
+        # live: the real function on the duck-typed universe gives the stored centres
+        import importlib
+        ref_harness.load()
+        mol = importlib.import_module("mdhelper.algorithm.molecule")
+        u.trajectory[2]
+        np.testing.assert_array_equal(mol.center_of_mass(u.atoms, "residues"),
+                                      g[f"{tag}_com_residues"][2])
