@@ -32,8 +32,8 @@
  *     the distance between consecutive frames in FLOATS (>= 3*n), so a slice of
  *     a larger [F][N][3] trajectory array can be passed without repacking.
  *   - boxes are float32 [frame][3] (orthorhombic edge lengths; this is
- *     ts.dimensions[:3] of the reference).  Triclinic cells are rejected by the
- *     host layer.
+ *     ts.dimensions[:3] of the reference).  Triclinic cells go through
+ *     mdh_rdf_accumulate_triclinic.
  */
 #ifndef MDH_B200_H
 #define MDH_B200_H
@@ -149,6 +149,19 @@ int mdh_rdf_configure(mdh_ctx *ctx, int64_t n1, int64_t n2, int same_group, int 
 int mdh_rdf_accumulate(mdh_ctx *ctx, const float *pos1, int64_t frame_stride1,
                        const float *pos2, int64_t frame_stride2, int location,
                        const float *box, int n_frames);
+
+/*
+ * The same for TRICLINIC cells: cell is a HOST pointer, [n_frames][9], the row-major
+ * lower-triangular cell matrix (a_x 0 0 / b_x b_y 0 / c_x c_y c_z) as float32 -- what
+ * MDAnalysis' triclinic_vectors(ts.dimensions) gives; the reference passes ts.dimensions
+ * with its angles to capped_distance (structure.py:93-96).  Coordinates are wrapped into
+ * the cell, then every pair takes the shortest of its 27 images (fp64).  All-pairs only;
+ * drop_axis is not available.  Restated from MDAnalysis' published algorithm and NOT
+ * pinned against MDAnalysis.
+ */
+int mdh_rdf_accumulate_triclinic(mdh_ctx *ctx, const float *pos1, int64_t frame_stride1,
+                                 const float *pos2, int64_t frame_stride2, int location,
+                                 const float *cell, int n_frames);
 
 int mdh_rdf_fetch(mdh_ctx *ctx, int64_t *counts /* [n_bins] host */);
 int mdh_rdf_reset(mdh_ctx *ctx);

@@ -45,6 +45,7 @@ SIGNATURES = {
     "mdh_rdf_configure": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _f64, _f64, _i64,
                                  _i64, _i32, _i32, _i32]),
     "mdh_rdf_accumulate": (_i32, [_p, _p, _i64, _p, _i64, _i32, _p, _i32]),
+    "mdh_rdf_accumulate_triclinic": (_i32, [_p, _p, _i64, _p, _i64, _i32, _p, _i32]),
     "mdh_rdf_fetch": (_i32, [_p, _p]),
     "mdh_rdf_reset": (_i32, [_p]),
     "mdh_rdf_counts_device": (_i32, [_p, ctypes.POINTER(_p)]),
@@ -201,6 +202,18 @@ class Context:
         check(self._lib.mdh_rdf_accumulate(
             self._h, _ptr(pos1), int(stride1), _ptr(pos2), int(stride2),
             MDH_DEVICE if device else MDH_HOST, box.ctypes.data, int(n_frames)))
+        if keepalive is not None:
+            self._keep.append(keepalive)
+
+    def rdf_accumulate_triclinic(self, pos1, stride1, pos2, stride2, cell, n_frames, *,
+                                 device=False, keepalive=None):
+        """Triclinic cells: ``cell`` is ``[n_frames, 3, 3]`` (lower-triangular matrices)."""
+        cell = np.ascontiguousarray(cell, dtype=np.float32)
+        if cell.shape != (n_frames, 3, 3):
+            raise ValueError("cell must have shape (n_frames, 3, 3)")
+        check(self._lib.mdh_rdf_accumulate_triclinic(
+            self._h, _ptr(pos1), int(stride1), _ptr(pos2), int(stride2),
+            MDH_DEVICE if device else MDH_HOST, cell.ctypes.data, int(n_frames)))
         if keepalive is not None:
             self._keep.append(keepalive)
 

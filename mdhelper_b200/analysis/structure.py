@@ -29,6 +29,7 @@ import numpy as np
 
 from . import _postprocess
 from ._binning import squared_thresholds
+from ._triclinic import box_volume, is_orthorhombic, triclinic_vectors
 from ._postprocess import (calculate_coordination_numbers,  # noqa: F401  (re-exported,
                            calculate_structure_factor,       # as in the reference module)
                            radial_fourier_transform,
@@ -39,16 +40,12 @@ _GROUPINGS_RDF = {"atoms", "residues", "segments"}
 _GROUPINGS_SSF = {"atoms", "residues"}
 
 
-def _check_orthorhombic(dims: np.ndarray) -> None:
-    if dims is None:
-        raise ValueError("Trajectory does not contain system dimension "
-                         "information.")
-    dims = np.atleast_2d(dims)
-    if dims.shape[1] >= 6 and not np.all(dims[:, 3:6] == 90):
-        raise NotImplementedError(
-            "mdhelper_b200 supports orthorhombic cells only (triclinic "
-            "minimum image is not implemented)."
-        )
+def _cell_matrices(dims: np.ndarray) -> np.ndarray:
+    """``[n, 3, 3]`` float32 cell matrices of the triclinic frames ``dims`` (``[n, 6]``)."""
+    cells = np.stack([triclinic_vectors(d) for d in np.atleast_2d(dims)])
+    if not np.all(cells[:, [0, 1, 2], [0, 1, 2]] > 0):
+        raise ValueError("Invalid unit cell dimensions.")
+    return cells
 
 
 def _record(batch):
@@ -143,8 +140,11 @@ def radial_histogram(
     from .._lib import Context
     p1 = np.ascontiguousarray(np.atleast_2d(np.asarray(pos1)), dtype=np.float32)
     p2 = np.ascontiguousarray(np.atleast_2d(np.asarray(pos2)), dtype=np.float32)
+    if dims is None:
+        raise ValueError("Trajectory does not contain system dimension "
+                         "information.")
     dims = np.asarray(dims, dtype=np.float32)
-    _check_orthorhombic(dims)
+    ortho = bool(is_orthorhombic(dims)[0])
     import torch
     dev = torch.cuda.current_device() if device is None else device
     ctx = Context(dev)
@@ -156,8 +156,11 @@ def radial_histogram(
         ctx.rdf_configure(len(p1), len(p2), same,
                           squared_thresholds(n_bins, range), range[0], range[1],
                           exclusion=exclusion, mode=mode, hist=hist)
-        ctx.rdf_accumulate(p1, 3 * len(p1), p2, 3 * len(p2),
-                           dims[None, :3], 1)
+        if ortho:
+            ctx.rdf_accumulate(p1, 3 * len(p1), p2, 3 * len(p2), dims[None, :3], 1)
+        else:
+            ctx.rdf_accumulate_triclinic(p1, 3 * len(p1), p2, 3 * len(p2),
+                                         _cell_matrices(dims[None, :]), 1)
         out = ctx.rdf_fetch()
         if stats is not None:
             stats.update(ctx.rdf_filter_stats())
@@ -217,7 +220,9 @@ class RadialDistributionFunction(GpuAnalysisBase):
     * ``n_batches`` has no effect (the reference documents that its batched
       mode can be off by a few counts, ``structure.py:601-607``; the GPU result
       is the unbatched one).
-    * Orthorhombic cells only.
+    * Triclinic cells run through a separate all-pairs kernel (coordinates wrapped into
+      the cell, shortest of the 27 images per pair); ``drop_axis`` needs an orthorhombic
+      cell.
     """
 
     def __init__(
@@ -328,13 +333,16 @@ class RadialDistributionFunction(GpuAnalysisBase):
 
     def _consume(self, batch, device: bool = False) -> None:
         """One batch of frames (host or device pointers) into the accumulators."""
-        _check_orthorhombic(batch.dims)
+        ortho = is_orthorhombic(batch.dims)
         box = batch.dims[:, :3].copy()
         if self._drop_axis is None:
-            # ts.volume: float64 product of the float32 edges
-            for v in box.astype(np.float64).prod(axis=1):
-                self._area_or_volume += v
+            # ts.volume: float64 product of the float32 edges (times the angular factor
+            # of a triclinic cell)
+            for d, o, v in zip(batch.dims, ortho, box.astype(np.float64).prod(axis=1)):
+                self._area_or_volume += v if o else box_volume(d)
         else:
+            if not ortho.all():
+                raise NotImplementedError("drop_axis needs an orthorhombic cell.")
             # reference: structure.py:764-770
             box[:, self._drop_axis] = box.max(axis=1)
             keep = [k for k in (0, 1, 2) if k != self._drop_axis]
@@ -355,12 +363,25 @@ class RadialDistributionFunction(GpuAnalysisBase):
             ptrs = [o.data_ptr() for o in outs]
             strides = [3 * n for n in self._com]
             device = True
-        self._ctx.rdf_accumulate(
-            ptrs[0], strides[0],
-            None if same else ptrs[1],
-            0 if same else strides[1],
-            box, batch.n_frames, device=device, keepalive=batch.keepalive
-        )
+        # runs of frames with the same kind of cell (a trajectory is normally all of one)
+        f0 = 0
+        while f0 < batch.n_frames:
+            f1 = f0 + 1
+            while f1 < batch.n_frames and ortho[f1] == ortho[f0]:
+                f1 += 1
+            p1 = ptrs[0] + 4 * strides[0] * f0
+            p2 = None if same else ptrs[1] + 4 * strides[1] * f0
+            s2 = 0 if same else strides[1]
+            if ortho[f0]:
+                self._ctx.rdf_accumulate(p1, strides[0], p2, s2, box[f0:f1], f1 - f0,
+                                         device=device, keepalive=batch.keepalive)
+            else:
+                # triclinic: coordinates wrapped into the cell, shortest of 27 images
+                self._ctx.rdf_accumulate_triclinic(
+                    p1, strides[0], p1 if same else p2, strides[0] if same else s2,
+                    _cell_matrices(batch.dims[f0:f1]), f1 - f0, device=device,
+                    keepalive=batch.keepalive)
+            f0 = f1
         _record(batch)
 
     def _finish(self) -> None:

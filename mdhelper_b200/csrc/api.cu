@@ -279,6 +279,15 @@ int mdh_rdf_accumulate(mdh_ctx *c, const float *pos1, int64_t frame_stride1, con
                                n_frames);
 }
 
+int mdh_rdf_accumulate_triclinic(mdh_ctx *c, const float *pos1, int64_t frame_stride1,
+                                 const float *pos2, int64_t frame_stride2, int location,
+                                 const float *cell, int n_frames)
+{
+    CTX_GUARD(c);
+    return rdf_accumulate_triclinic_impl(c, pos1, frame_stride1, pos2, frame_stride2, location,
+                                         cell, n_frames);
+}
+
 int mdh_rdf_fetch(mdh_ctx *c, int64_t *counts)
 {
     CTX_GUARD(c);

@@ -91,6 +91,7 @@ struct RdfState {
     double cells_ws_mb = 96.0;   // working set of one group of frames (sort + pair kernel)
     int cells_chunk = 8;         // cells per work item of the cell-pair kernel
     int cells_ipt = 4;           // particles per lane of the cell-pair kernel (2 or 4)
+    bool cells_debug = false;    // per-stage device times on stderr (MDH_TUNE cdbg=1)
     bool evals_dev_init = false;
     std::vector<FrameBox> h_boxes;
     FrameBox *h_boxes_pinned = nullptr;   // staging for the async box upload
@@ -231,6 +232,9 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
                        int drop_axis, int mode, int hist);
 int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *pos2,
                         int64_t s2, int location, const float *box, int n_frames);
+// rdf_tri.cu
+int rdf_accumulate_triclinic_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *pos2,
+                                  int64_t s2, int location, const float *box9, int n_frames);
 // rdf_filter.cu
 int rdf_filter_sqrt_error(mdh_ctx *c, double *err);
 bool rdf_filter_configure(RdfState &R, const double *thr, double sqrt_err);

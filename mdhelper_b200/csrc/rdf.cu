@@ -280,6 +280,7 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
         if (const char *p = strstr(t, "cws=")) R.cells_ws_mb = std::max(1.0, atof(p + 4));
         if (const char *p = strstr(t, "cchunk=")) R.cells_chunk = std::max(1, atoi(p + 7));
         if (const char *p = strstr(t, "cipt=")) R.cells_ipt = atoi(p + 5) == 2 ? 2 : 4;
+        if (const char *p = strstr(t, "cdbg=")) R.cells_debug = atoi(p + 5) != 0;
     }
     // measured on B200 (profiles/): per-warp shared-memory atomics beat the
     // lane-private byte counters at every bin count tried, and need less memory

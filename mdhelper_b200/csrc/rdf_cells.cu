@@ -40,6 +40,8 @@
 // from the same shared-memory buffer.  Cells whose candidate list does not fit the buffer
 // (dense clusters) take a slower path that reads the runs from global memory.
 
+#include <stdio.h>
+
 #include <algorithm>
 #include <type_traits>
 
@@ -405,8 +407,14 @@ int launch_cells(mdh_ctx *c, const CellParams &P, dim3 grid)
 {
     const size_t smem = cells_smem_bytes<HIST>(P.n_bins);
     auto kern = rdf_cells_kernel<HIST, EXCL, FAST>;
-    MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    static thread_local size_t cached_smem = 0;
+    static thread_local int cached_dev = -1;
+    if (cached_smem < smem || cached_dev != c->device) {
+        MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        cached_smem = smem;
+        cached_dev = c->device;
+    }
     kern<<<grid, kThreads, smem, c->stream>>>(P);
     MDH_CUDA(cudaGetLastError());
     c->launches++;
@@ -628,22 +636,18 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                   ncz = P.grids[frame].nc[2];
         const int c1 = min(c0 + P.chunk_cells, ncx * ncy * ncz);
 
-        // Plans the candidate list of `cell` into buffer `slot` and starts its copy.
-        // Lane r describes run r: r = 0 the cell's own particles (group 1), r >= 1 the
-        // stencil runs of group 2.  Returns (warp-uniform) n_i, total and the mode:
-        // 0 nothing to do, 1 buffered (copy in flight), 2 too long for the buffer.
-        auto issue = [&](int cell, int slot, int &n_i, int &total) -> int {
-            const float4 *s1 = P.s1 + (int64_t)frame * P.n1;
-            const float4 *s2 = P.s2 + (int64_t)frame * P.n2;
+        // Stage 1 of the per-cell pipeline: the runs of the sorted arrays that make up the
+        // candidate list of cell (cx, cy, cz).  Lane r describes run r: r = 0 the cell's own
+        // particles (group 1), r >= 1 the stencil runs of group 2.  Only LOADS the run
+        // bounds; they are consumed one cell later, so their latency is hidden.
+        auto plan = [&](int cell, int cx, int cy, int cz, int &b, int &e) {
             const int *st1 = P.start1 + (int64_t)frame * P.cstride;
             const int *st2 = P.start2 + (int64_t)frame * P.cstride;
-            const int cx = cell % ncx, t = cell / ncx;
-            const int cy = t % ncy, cz = t / ncy;
             auto wrap = [](int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); };
-            int b = 0, len = 0;
+            const int *pb = st1, *pe = st1;          // empty run: b == e
             if (lane == 0) {
-                b = st1[cell];
-                len = st1[cell + 1] - b;
+                pb = st1 + cell;
+                pe = pb + 1;
             } else if (lane < kCpRanges) {
                 const int r = lane - 1;              // 0..17: row r / 2, run r & 1
                 const int row_i = r >> 1;            // 0..8 = (dz + 1) * 3 + (dy + 1)
@@ -652,8 +656,7 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                 // (y + 1, z) and the cell (x + 1, y, z) of the own row
                 bool use = !HALF || dz == 1 || (dz == 0 && dy >= 0);
                 int xa, xb;                          // cells [xa, xb] of the row
-                const int y = wrap(cy + dy, ncy), z = wrap(cz + dz, ncz);
-                const int row = (z * ncy + y) * ncx;
+                const int row = (wrap(cz + dz, ncz) * ncy + wrap(cy + dy, ncy)) * ncx;
                 if (HALF && dz == 0 && dy == 0) {
                     xa = xb = wrap(cx + 1, ncx);
                     use = (r & 1) == 0;
@@ -665,11 +668,19 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                     xa = xb = max(xw, 0);
                 }
                 if (use) {
-                    b = st2[row + xa];
-                    len = st2[row + xb + 1] - b;
+                    pb = st2 + row + xa;
+                    pe = st2 + row + xb + 1;
                 }
             }
-            // exclusive prefix of the run lengths
+            b = __ldg(pb);
+            e = __ldg(pe);
+        };
+        // Stage 2: lays the runs out in buffer `slot` and starts their copy.  Returns
+        // (warp-uniform) n_i, total and the mode: 0 nothing to do, 1 buffered (copy in
+        // flight), 2 list longer than the buffer (copied and computed in segments), 3 cell
+        // too large for that as well (fp64 fallback).
+        auto launch = [&](int slot, int b, int e, int &n_i, int &total) -> int {
+            const int len = e - b;
             int pre = len;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -681,25 +692,69 @@ __global__ void __launch_bounds__(kCpThreads, 2)
             n_i = __shfl_sync(0xffffffffu, len, 0);
             wrng[slot * 32 + lane] = make_int2(b, len);
             if (n_i == 0 || (!HALF && total == n_i)) return 0;
-            if (total > cap) return 2;
+            if (total > cap) return n_i <= cap - 64 ? 2 : 3;
             const unsigned bar = bar32 + 8u * slot;
             if (lane == 0) cp_mbar_expect(bar, (unsigned)total * 16u);
             __syncwarp();
             if (len > 0)
                 cp_bulk_g2s(wbuf32 + 16u * (unsigned)(slot * bufw + pre),
-                            (lane == 0 ? s1 : s2) + b, (unsigned)len * 16u, bar);
+                            (lane == 0 ? P.s1 + (int64_t)frame * P.n1
+                                       : P.s2 + (int64_t)frame * P.n2) + b,
+                            (unsigned)len * 16u, bar);
             return 1;
         };
+        // Mode 2: the next segment of an over-long candidate list into buffer `slot`
+        // (the cell's own particles first), synchronously.  (r, o): run and offset to
+        // continue from.  Returns the number of candidates copied to buf[n_i ..).
+        auto fill_segment = [&](int slot, int n_i, int &r, int &o, bool first) -> int {
+            const unsigned bar = bar32 + 8u * slot;
+            const int room = cap - n_i;
+            int filled = 0, rr = r, oo = o;
+            while (rr < kCpRanges && filled < room) {      // what fits (warp-uniform)
+                const int take = min(wrng[slot * 32 + rr].y - oo, room - filled);
+                filled += take;
+                oo += take;
+                if (oo == wrng[slot * 32 + rr].y) { ++rr; oo = 0; }
+            }
+            if (lane == 0) {
+                cp_mbar_expect(bar, (unsigned)(filled + (first ? n_i : 0)) * 16u);
+                if (first)
+                    cp_bulk_g2s(wbuf32 + 16u * (unsigned)(slot * bufw),
+                                P.s1 + (int64_t)frame * P.n1 + wrng[slot * 32].x,
+                                (unsigned)n_i * 16u, bar);
+                int at = n_i, q = r, qo = o, left = filled;
+                while (left > 0) {
+                    const int2 rg = wrng[slot * 32 + q];
+                    const int take = min(rg.y - qo, left);
+                    if (take > 0)
+                        cp_bulk_g2s(wbuf32 + 16u * (unsigned)(slot * bufw + at),
+                                    P.s2 + (int64_t)frame * P.n2 + rg.x + qo,
+                                    (unsigned)take * 16u, bar);
+                    at += take; left -= take; qo += take;
+                    if (qo == rg.y) { ++q; qo = 0; }
+                }
+            }
+            r = rr; o = oo;
+            __syncwarp();
+            return filled;
+        };
 
-        // All pairs of the cell's particles with the candidates in buffer `slot`.
-        auto compute = [&](int slot, int n_i, int total) {
+        // All pairs of the cell's particles buf[0 .. n_i) with the candidates buf[n_i .. je)
+        // (weight 2 when the groups coincide: the half stencil stands for both orders) and,
+        // if do_self, with each other (ordered pairs, weight 1, a particle never with itself).
+        auto compute = [&](int slot, int n_i, int je, bool do_self) {
             const float4 *buf = wbuf + slot * bufw;
+            const int total = je;
             const int n_chunks = (n_i + 8 * IPT - 1) / (8 * IPT);
             const int cs = (n_i + n_chunks - 1) / n_chunks;
             for (int off = 0; off < n_i; off += cs) {
                 const int cn = min(cs, n_i - off);
-                const int ni = (cn + IPT - 1) / IPT, ways = 32 / ni;
-                const int way = lane / ni, il = lane - way * ni;
+                // ni <= 8 lanes hold the chunk; lane / ni without an integer division
+                // ((lane + 1/2) / ni is at least 1/16 away from every integer)
+                const int ni = (cn + IPT - 1) / IPT;
+                const float rni = __frcp_rn((float)ni);
+                const int ways = (int)(32.5f * rni);
+                const int way = (int)(((float)lane + 0.5f) * rni), il = lane - way * ni;
                 const bool lane_ok = way < ways;
                 const int ipos0 = off + il * IPT;
                 // the lane's particles: negated coordinates packed in pairs (the operands of
@@ -838,7 +893,7 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                 };
 
                 const unsigned w_fwd = HALF ? 2u : 1u;
-                if (HALF) run_list(0, n_i, 1u, std::integral_constant<bool, true>());
+                if (HALF && do_self) run_list(0, n_i, 1u, std::integral_constant<bool, true>());
                 run_list(n_i, total - n_i, w_fwd, std::integral_constant<bool, false>());
                 __syncwarp();
 
@@ -849,7 +904,8 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                     for (unsigned e = lane; e < n_list; e += 32) {
                         const unsigned entry = wlist[e];
                         const int src = (int)(entry >> 16), jpos = (int)(entry & 0xffffu);
-                        const int e_i0 = off + (src - (src / ni) * ni) * IPT;
+                        const int e_i0 =
+                            off + (src - (int)(((float)src + 0.5f) * rni) * ni) * IPT;
                         cp_fix<EXCL, LOWER, IPT>(P, frame, buf + e_i0, min(IPT, off + cn - e_i0),
                                                  buf + jpos, jpos < n_i ? 1u : w_fwd, sT, hist32);
                     }
@@ -876,18 +932,34 @@ __global__ void __launch_bounds__(kCpThreads, 2)
             }
         };
 
-        // software pipeline over the cells of the item: plan + copy of cell k + 1, then the
-        // pairs of cell k (one call site each)
+        // software pipeline over the cells of the item: run bounds of cell k + 2 (loads),
+        // layout + copy of cell k + 1, pairs of cell k (one call site each)
+        int px = c0 % ncx, py = (c0 / ncx) % ncy, pz = c0 / (ncx * ncy);   // cell being planned
+        int pb = 0, pe = 0;                    // planned run of this lane, one cell ahead
         int ni_c = 0, tot_c = 0, mode_c = 0;
-        for (int cell = c0 - 1; cell < c1; ++cell) {
+        for (int cell = c0 - 2; cell < c1; ++cell) {
+            int nb = 0, ne = 0;
+            if (cell + 2 < c1) {
+                plan(cell + 2, px, py, pz, nb, ne);
+                if (++px == ncx) { px = 0; if (++py == ncy) { py = 0; ++pz; } }
+            }
             int ni_n = 0, tot_n = 0, mode_n = 0;
             const int slot = (cell - c0) & 1;
-            if (cell + 1 < c1) mode_n = issue(cell + 1, slot ^ 1, ni_n, tot_n);
-            if (mode_c == 1) {
-                cp_mbar_wait(bar32 + 8u * slot, (phase >> slot) & 1u);
-                phase ^= 1u << slot;
-                compute(slot, ni_c, tot_c);
-            } else if (mode_c == 2) {
+            if (cell + 1 >= c0 && cell + 1 < c1) mode_n = launch(slot ^ 1, pb, pe, ni_n, tot_n);
+            pb = nb; pe = ne;
+            if (mode_c == 1 || mode_c == 2) {
+                int r = HALF ? 1 : 1, o = 0;   // run 0 is the own cell (copied with segment 1)
+                bool first = true;
+                for (;;) {
+                    int je = tot_c;
+                    if (mode_c == 2) je = ni_c + fill_segment(slot, ni_c, r, o, first);
+                    cp_mbar_wait(bar32 + 8u * slot, (phase >> slot) & 1u);
+                    phase ^= 1u << slot;
+                    compute(slot, ni_c, je, first);
+                    first = false;
+                    if (mode_c == 1 || r >= kCpRanges) break;
+                }
+            } else if (mode_c == 3) {
                 cp_long_cell<HALF, EXCL>(P, frame, wrng + slot * 32, sT, hist32, fc.sb, lane);
             }
             if (mode_c != 0 && lane == 0) {
@@ -927,10 +999,19 @@ int launch_cellpair_t(mdh_ctx *c, const CellPairParams &P)
 {
     const size_t smem = cp_smem_bytes(P.n_bins, P.fc.sb, P.cap);
     auto kern = rdf_cellpair_kernel<HALF, EXCL, LOWER, AUDIT, IPT>;
-    MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    int per_sm = 0;
-    MDH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCpThreads, smem));
+    // attribute and occupancy are looked up once per shared-memory size and device (these
+    // calls cost more host time than the launch itself)
+    static thread_local size_t cached_smem = 0;
+    static thread_local int cached_dev = -1, cached_per_sm = 0;
+    if (cached_smem != smem || cached_dev != c->device) {
+        MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        MDH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, kern, kCpThreads,
+                                                               smem));
+        cached_smem = smem;
+        cached_dev = c->device;
+    }
+    const int per_sm = cached_per_sm;
     MDH_REQUIRE(per_sm >= 1, MDH_EINVAL, "rdf: cell-pair kernel does not fit on an SM");
     const int items = (P.max_ncell + P.chunk_cells - 1) / P.chunk_cells * P.n_frames;
     const int blocks = std::max(1, std::min(c->sm_count * per_sm, (items + kCpWarps - 1) / kCpWarps));
@@ -1059,8 +1140,19 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
     use_filter = use_filter && sb_c >= 0;
 
     const bool excl = R.excl1 > 0, fast = R.fast_bins;
+    // MDH_TUNE="cdbg=1": device time of every stage, printed per call (tuning aid;
+    // synchronises)
+    std::vector<cudaEvent_t> dbg;
+    auto mark = [&]() {
+        if (!R.cells_debug) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, c->stream);
+        dbg.push_back(e);
+    };
     for (int g0 = 0; g0 < n_frames; g0 += G) {
         const int ng = std::min(G, n_frames - g0);
+        mark();
         // counters, extents and the work counter: one contiguous region, one zero fill
         MDH_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (work_off + 4), c->stream));
         const CellGrid *gg = d_grids.as<CellGrid>() + g0;
@@ -1074,6 +1166,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
             MDH_CUDA(cudaGetLastError());
             c->launches++;
         }
+        mark();
         ScanFilter F{};
         F.out = nullptr;
         if (use_filter) {
@@ -1084,13 +1177,18 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
             F.prep = rdf_filter_prep(R, sqrt_err);
         }
         const size_t scan_smem = sizeof(int) * (kScanTile + kScanTile / 32);
-        MDH_CUDA(cudaFuncSetAttribute(cells_scan_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)scan_smem));
+        static thread_local int scan_attr_dev = -1;
+        if (scan_attr_dev != c->device) {
+            MDH_CUDA(cudaFuncSetAttribute(cells_scan_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)scan_smem));
+            scan_attr_dev = c->device;
+        }
         cells_scan_kernel<<<dim3(ng, n_groups), 1024, scan_smem, c->stream>>>(d_cnt, d_start,
                                                                              cstride, G, gg, F);
         MDH_CUDA(cudaGetLastError());
         c->launches++;
+        mark();
         for (int grp = 0; grp < n_groups; ++grp) {
             const float *raw = (grp ? raw2 : raw1) + (int64_t)g0 * (grp ? stride2 : stride1);
             const int n = (int)(grp ? R.n2 : R.n1);
@@ -1103,6 +1201,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
             c->launches++;
         }
 
+        mark();
         const float4 *s1 = R.cell[4].as<float4>();
         const float4 *s2 = R.same ? s1 : R.cell[8].as<float4>();
         const int *start1 = d_start, *start2 = R.same ? d_start : d_start + (size_t)G * cstride;
@@ -1134,6 +1233,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
                                          R.filter_mode == MDH_FILTER_AUDIT, R.cells_ipt))
                 return rc;
         }
+        mark();
         // the fp64 kernel: every frame without the filter, else the frames it declined
         CellParams P;
         P.s1 = s1; P.s2 = s2;
@@ -1166,6 +1266,24 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
                       : launch_cells<MDH_HIST_WARP_ATOMIC, false, false>(c, P, grid);
         }
         if (rc) return rc;
+        mark();
+    }
+    if (R.cells_debug && !dbg.empty()) {
+        cudaStreamSynchronize(c->stream);
+        double t[5] = {0, 0, 0, 0, 0};            // six marks, five stages per group
+        for (size_t k = 0; k + 5 < dbg.size(); k += 6)
+            for (int q = 0; q < 5; ++q) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, dbg[k + q], dbg[k + q + 1]);
+                t[q] += ms;
+            }
+        float whole = 0;
+        cudaEventElapsedTime(&whole, dbg.front(), dbg.back());
+        fprintf(stderr, "cells: %d frames (groups of %d): reset+bin %.1f scan %.1f scatter %.1f "
+                        "pair %.1f fp64 %.1f | whole %.1f us per frame\n", n_frames, G,
+                1e3 * t[0] / n_frames, 1e3 * t[1] / n_frames, 1e3 * t[2] / n_frames,
+                1e3 * t[3] / n_frames, 1e3 * t[4] / n_frames, 1e3 * whole / n_frames);
+        for (cudaEvent_t e : dbg) cudaEventDestroy(e);
     }
     return MDH_OK;
 }

@@ -177,6 +177,79 @@ int64_t mdho_capped_distance_cells(const float *pos1, int64_t n1, const float *p
     return m;
 }
 
+/*
+ * Triclinic cells (box9: row-major lower-triangular float32 matrix a_x 0 0 / b_x b_y 0 /
+ * c_x c_y c_z, MDAnalysis' triclinic_vectors).  Restates, from the published algorithm
+ * of MDAnalysis 2.x lib/include/calc_distances.h ("parity unpinned", as above):
+ *   _triclinic_pbc      both coordinate sets are moved into the primary cell first.
+ *                       Restated mathematically (c, then b, then a: s = floor(x_k / h_kk),
+ *                       r -= s h_k in double, rounded to float32); the identity for
+ *                       coordinates that already lie in the cell.
+ *   minimum_image_triclinic   the shortest of the 27 images dx + ix a + iy b + iz c,
+ *                       loop order ix, iy, iz, strict "<", sums in double.
+ */
+static void triclinic_wrap(const float *in, float *out, int64_t n, const float *h)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        double x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+        double s = floor(z / (double)h[8]);
+        if (s != 0.0) { x -= s * (double)h[6]; y -= s * (double)h[7]; z -= s * (double)h[8]; }
+        s = floor(y / (double)h[4]);
+        if (s != 0.0) { x -= s * (double)h[3]; y -= s * (double)h[4]; }
+        s = floor(x / (double)h[0]);
+        if (s != 0.0) x -= s * (double)h[0];
+        out[3 * i] = (float)x; out[3 * i + 1] = (float)y; out[3 * i + 2] = (float)z;
+    }
+}
+
+static inline double triclinic_dist2(const float *a, const float *b, const float *h)
+{
+    double dx[3];
+    for (int k = 0; k < 3; ++k) dx[k] = (double)(float)(b[k] - a[k]);
+    double best = (double)FLT_MAX;
+    for (int ix = -1; ix < 2; ++ix) {
+        double rx = dx[0] + (double)(h[0] * ix);
+        for (int iy = -1; iy < 2; ++iy) {
+            double ry0 = rx + (double)(h[3] * iy);
+            double ry1 = dx[1] + (double)(h[4] * iy);
+            for (int iz = -1; iz < 2; ++iz) {
+                double rz0 = ry0 + (double)(h[6] * iz);
+                double rz1 = ry1 + (double)(h[7] * iz);
+                double rz2 = dx[2] + (double)(h[8] * iz);
+                double dsq = (rz0 * rz0 + rz1 * rz1) + rz2 * rz2;
+                if (dsq < best) best = dsq;
+            }
+        }
+    }
+    return best;
+}
+
+int64_t mdho_capped_distance_triclinic(const float *pos1, int64_t n1, const float *pos2,
+                                       int64_t n2, const float *box9, double max_cutoff,
+                                       double min_cutoff, int64_t *pairs, double *dist,
+                                       int64_t cap)
+{
+    float *w1 = (float *)malloc(sizeof(float) * 3 * (size_t)(n1 > 0 ? n1 : 1));
+    float *w2 = (float *)malloc(sizeof(float) * 3 * (size_t)(n2 > 0 ? n2 : 1));
+    if (!w1 || !w2) { free(w1); free(w2); return -2; }
+    triclinic_wrap(pos1, w1, n1, box9);
+    triclinic_wrap(pos2, w2, n2, box9);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n1; ++i)
+        for (int64_t j = 0; j < n2; ++j) {
+            double d = sqrt(triclinic_dist2(w1 + 3 * i, w2 + 3 * j, box9));
+            if (d > min_cutoff && d <= max_cutoff) {
+                if (m < cap) {
+                    if (pairs) { pairs[2 * m] = i; pairs[2 * m + 1] = j; }
+                    dist[m] = d;
+                }
+                ++m;
+            }
+        }
+    free(w1); free(w2);
+    return m;
+}
+
 /* ---- (2) direct-sum Fourier transform of delta functions --------------------- */
 
 /*

@@ -24,12 +24,60 @@ def _as_coords(x):
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
+def triclinic_vectors(dimensions):
+    """Restated third-party ``MDAnalysis.lib.mdamath.triclinic_vectors`` [recall]: the
+    lower-triangular float32 cell matrix of ``(lx, ly, lz, alpha, beta, gamma)``; float64
+    trigonometry, exact values for right angles, zeros for an invalid cell."""
+    dim = np.asarray(dimensions, dtype=np.float64)
+    lx, ly, lz, alpha, beta, gamma = dim
+    if not (np.all(dim > 0.0) and alpha < 180.0 and beta < 180.0 and gamma < 180.0):
+        return np.zeros((3, 3), dtype=np.float32)
+    if alpha == beta == gamma == 90.0:
+        return np.diag(dim[:3]).astype(np.float32)
+    m = np.zeros((3, 3), dtype=np.float64)
+    m[0, 0] = lx
+    cos_alpha = 0.0 if alpha == 90.0 else np.cos(np.deg2rad(alpha))
+    cos_beta = 0.0 if beta == 90.0 else np.cos(np.deg2rad(beta))
+    cos_gamma = 0.0 if gamma == 90.0 else np.cos(np.deg2rad(gamma))
+    sin_gamma = 1.0 if gamma == 90.0 else np.sin(np.deg2rad(gamma))
+    m[1, 0], m[1, 1] = ly * cos_gamma, ly * sin_gamma
+    m[2, 0] = lz * cos_beta
+    m[2, 1] = lz * (cos_alpha - cos_beta * cos_gamma) / sin_gamma
+    m[2, 2] = np.sqrt(lz * lz - m[2, 0] ** 2 - m[2, 1] ** 2)
+    if not m[2, 2] > 0.0:
+        return np.zeros((3, 3), dtype=np.float32)
+    return m.astype(np.float32)
+
+
+def _capped_distance_triclinic(ref, conf, max_cutoff, lo, box, return_distances):
+    """Triclinic cells: brute force over all pairs (mdh_oracle.c, wrap + 27 images)."""
+    h = np.ascontiguousarray(triclinic_vectors(box), dtype=np.float32)
+    if not np.all(np.diag(h) > 0):
+        raise ValueError("oracle: invalid unit cell")
+    L = lib()
+    n1, n2 = len(ref), len(conf)
+    cap = max(1024, int(1.5 * n1 * n2 * 4.19 * max_cutoff ** 3
+                        / float(np.prod(np.diag(h), dtype=np.float64))))
+    cap = min(cap, n1 * n2)
+    while True:
+        pairs = np.empty((cap, 2), dtype=np.int64)
+        dist = np.empty(cap, dtype=np.float64)
+        m = L.mdho_capped_distance_triclinic(
+            ref.ctypes.data, n1, conf.ctypes.data, n2, h.ctypes.data, float(max_cutoff), lo,
+            pairs.ctypes.data, dist.ctypes.data, cap)
+        if m < 0:
+            raise MemoryError("oracle allocation failed")
+        if m <= cap:
+            return (pairs[:m], dist[:m]) if return_distances else pairs[:m]
+        cap = int(m)
+
+
 def capped_distance(reference, configuration, max_cutoff, min_cutoff=None,
                     box=None, method=None, return_distances=True):
     """
     Restated ``MDAnalysis.lib.distances.capped_distance`` (third-party; call
     site ``src/mdhelper/analysis/structure.py:93-96``; arithmetic: SURVEY.md
-    Appendix A).  Orthorhombic boxes only.
+    Appendix A).  Triclinic boxes: all pairs, wrap + shortest of 27 images.
 
     Returns ``pairs`` (int64 ``[M, 2]``) and ``distances`` (float64 ``[M]``).
     """
@@ -38,9 +86,12 @@ def capped_distance(reference, configuration, max_cutoff, min_cutoff=None,
     if box is None:
         raise NotImplementedError("oracle: a periodic box is required")
     box = np.ascontiguousarray(box, dtype=np.float32)
-    if box.shape != (6,) or not np.all(box[3:] == 90):
-        raise NotImplementedError("oracle: orthorhombic boxes only")
+    if box.shape != (6,):
+        raise NotImplementedError("oracle: box must be (lx, ly, lz, alpha, beta, gamma)")
     lo = -np.inf if min_cutoff is None else float(min_cutoff)
+    if not np.all(box[3:] == 90):
+        return _capped_distance_triclinic(ref, conf, float(max_cutoff), lo, box,
+                                          return_distances)
     n1, n2 = len(ref), len(conf)
     if method is None:                       # Appendix A item 2
         if n1 < 10 or n2 < 10:

@@ -529,7 +529,69 @@ def test_argument_errors():
     with pytest.raises(ValueError):        # non-positive box edge
         ctx.rdf_accumulate(np.zeros((4, 3), np.float32), 12, None, 0,
                            np.zeros((1, 3), np.float32), 1)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):        # angles that do not span a cell
         _structure().radial_histogram(np.zeros((2, 3)), np.zeros((2, 3)), 4, (0, 1),
-                                      (5, 5, 5, 90, 60, 90))
+                                      (5, 5, 5, 30, 40, 120))
     ctx.close()
+
+
+def _triclinic_universe(n=900, F=3, seed=4):
+    from mdhelper_b200.universe import SyntheticUniverse
+    rng = np.random.default_rng(seed)
+    dims = np.array([[10.5, 11.25, 12.0, 75.0, 82.0, 64.0],
+                     [10.0, 11.5, 12.5, 90.0, 90.0, 70.0],
+                     [11.0, 11.0, 11.0, 60.0, 60.0, 60.0]], np.float32)[:F]
+    pos = np.empty((F, n, 3), np.float32)
+    for f in range(F):
+        h = _oracle().triclinic_vectors(dims[f]).astype(np.float64)
+        frac = rng.random((n, 3)) * (1 if f != 1 else 3) - (0 if f != 1 else 1)   # frame 1 unwrapped
+        pos[f] = (frac @ h).astype(np.float32)
+    return SyntheticUniverse(pos, dims)
+
+
+def test_triclinic_cells_against_the_oracle():
+    """Triclinic frames (wrap into the cell + shortest of 27 images in fp64): counts equal
+    the restated triclinic path of capped_distance bit for bit -- same group, two groups,
+    exclusions, coordinates outside the cell, one cell per frame."""
+    u = _triclinic_universe()
+    S = _structure()
+    a, b = u.select(slice(0, 350)), u.select(slice(350, 900))
+    for sel, excl in [((u.atoms, None), None), ((a, b), None), ((u.atoms, None), (3, 3)),
+                      ((a, b), (2, 5))]:
+        kw = dict(n_bins=70, range=(0.0, 4.5), exclusion=excl)
+        want = _oracle().rdf_run(u, sel[0], sel[1], **kw)
+        r = S.RadialDistributionFunction(sel[0], sel[1], verbose=False, **kw).run()
+        assert np.array_equal(r.results.counts, want["counts"])
+        np.testing.assert_allclose(r.results.rdf, want["rdf"], rtol=1e-6)
+    p = u.trajectory.coordinates[0]
+    got = S.radial_histogram(p, p, 40, (0.5, 4.0), u.trajectory.unitcells[0])
+    assert np.array_equal(got, _oracle().radial_histogram(p, p, 40, (0.5, 4.0),
+                                                          u.trajectory.unitcells[0]))
+
+
+def test_triclinic_kernel_with_right_angles_equals_orthorhombic_kernels():
+    """Property: a diagonal cell matrix through the triclinic kernel gives the counts of
+    the orthorhombic kernels; mixed trajectories route every frame to its own kernel."""
+    from mdhelper_b200 import _lib
+    from mdhelper_b200.analysis._binning import squared_thresholds
+    from mdhelper_b200.universe import SyntheticUniverse
+    rng = np.random.default_rng(10)
+    dims = np.array([10.0, 11.0, 12.0, 90, 90, 90], np.float32)
+    p = (rng.random((2, 700, 3)) * dims[:3] * 2 - dims[:3] / 2).astype(np.float32)
+    S = _structure()
+    want = sum(S.radial_histogram(p[f], p[f], 64, (0.0, 5.0), dims) for f in range(2))
+    ctx = _lib.Context(0)
+    ctx.rdf_configure(700, 700, True, squared_thresholds(64, (0.0, 5.0)), 0.0, 5.0)
+    cell = np.tile(np.diag(dims[:3])[None], (2, 1, 1)).astype(np.float32)
+    ctx.rdf_accumulate_triclinic(p, 2100, p, 2100, cell, 2)
+    assert np.array_equal(ctx.rdf_fetch(), want)
+    ctx.close()
+    # frames 0 and 2 orthorhombic, frame 1 triclinic
+    tri = _triclinic_universe(n=700, F=1)
+    pos = np.stack([p[0], tri.trajectory.coordinates[0], p[1]])
+    cells = np.stack([dims, tri.trajectory.unitcells[0], dims])
+    u = SyntheticUniverse(pos, cells)
+    r = S.RadialDistributionFunction(u.atoms, n_bins=64, range=(0.0, 5.0), verbose=False).run()
+    want = _oracle().rdf_run(u, u.atoms, n_bins=64, range=(0.0, 5.0))
+    assert np.array_equal(r.results.counts, want["counts"])
+    np.testing.assert_allclose(r.results.rdf, want["rdf"], rtol=1e-6)

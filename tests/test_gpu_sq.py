@@ -431,3 +431,17 @@ def test_residue_structure_factor_against_the_reference(golden, tag):
         np.testing.assert_allclose(s.results.wavenumbers, g[f"{tag}_ssf_wavenumbers"],
                                    rtol=1e-12)
         np.testing.assert_allclose(s.results.ssf, g[f"{tag}_ssf_res"], rtol=2e-5, atol=2e-6)
+
+
+def test_structure_factor_of_a_triclinic_universe_uses_the_edge_lengths():
+    """The reference builds its wavevectors from ``dimensions[:3]`` alone
+    (structure.py:1366-1381), angles ignored: same result as the orthorhombic cell."""
+    from mdhelper_b200.universe import SyntheticUniverse
+    rng = np.random.default_rng(2)
+    pos = (rng.random((2, 500, 3)) * 9).astype(np.float32)
+    ut = SyntheticUniverse(pos, np.array([9.0, 10.0, 11.0, 80, 70, 60], np.float32))
+    uo = SyntheticUniverse(pos, np.array([9.0, 10.0, 11.0, 90, 90, 90], np.float32))
+    st = _S().StructureFactor([ut.atoms], n_points=6, verbose=False).run()
+    so = _S().StructureFactor([uo.atoms], n_points=6, verbose=False).run()
+    assert np.array_equal(st.results.wavenumbers, so.results.wavenumbers)
+    np.testing.assert_allclose(st.results.ssf, so.results.ssf, rtol=1e-12)

@@ -181,3 +181,74 @@ def test_centres_of_mass_match_the_reference(golden, tag):
         u.trajectory[2]
         np.testing.assert_array_equal(mol.center_of_mass(u.atoms, "residues"),
                                       g[f"{tag}_com_residues"][2])
+
+
+def _triclinic_case(seed=5, n=350):
+    rng = np.random.default_rng(seed)
+    dims = np.array([10.5, 11.25, 12.0, 75.0, 82.0, 64.0], np.float32)
+    h = rp.triclinic_vectors(dims).astype(np.float64)
+    p = (rng.random((n, 3)) @ h).astype(np.float32)
+    return dims, h, p
+
+
+def test_triclinic_minimum_image_is_the_shortest_image():
+    """Restated triclinic path of capped_distance (unpinned against MDAnalysis): the
+    distances are the mathematical minimum over lattice images to float32 rounding."""
+    dims, h, p = _triclinic_case()
+    pairs, d = rp.capped_distance(p, p, 4.0, -1e-16, box=dims)
+    P = p.astype(np.float64)
+    best = np.full((len(p), len(p)), np.inf)
+    for i in range(-2, 3):
+        for j in range(-2, 3):
+            for k in range(-2, 3):
+                D = P[None, :, :] - P[:, None, :] + (i * h[0] + j * h[1] + k * h[2])
+                best = np.minimum(best, (D ** 2).sum(-1))
+    best = np.sqrt(best)
+    assert len(d) == (best <= 4.0).sum()
+    np.testing.assert_allclose(d, best[pairs[:, 0], pairs[:, 1]], atol=2e-6)
+
+
+def test_triclinic_with_right_angles_equals_orthorhombic():
+    """Property: a diagonal cell matrix through the triclinic arithmetic gives the counts
+    of the orthorhombic arithmetic."""
+    import oracle
+    rng = np.random.default_rng(8)
+    dims = np.array([10.0, 11.0, 12.0, 90, 90, 90], np.float32)
+    p = (rng.random((500, 3)) * dims[:3]).astype(np.float32)
+    q = (rng.random((300, 3)) * dims[:3] * 3 - dims[:3]).astype(np.float32)     # unwrapped
+    h = np.ascontiguousarray(np.diag(dims[:3]), np.float32)
+    L = oracle.lib()
+    for a, b in ((p, p), (p, q)):
+        cap = len(a) * len(b)
+        pairs, dist = np.empty((cap, 2), np.int64), np.empty(cap)
+        m = L.mdho_capped_distance_triclinic(a.ctypes.data, len(a), b.ctypes.data, len(b),
+                                             h.ctypes.data, 5.0, -1e-16, pairs.ctypes.data,
+                                             dist.ctypes.data, cap)
+        got = np.histogram(dist[:m], bins=80, range=(0, 5.0))[0]
+        assert np.array_equal(got, rp.radial_histogram(a, b, 80, (0, 5.0), dims))
+
+
+def test_triclinic_lattice_translation_invariance():
+    """Property: moving particles by lattice vectors changes nothing.  Cell and coordinates
+    are dyadic rationals, so the translations are exact in float32."""
+    rng = np.random.default_rng(9)
+    h = np.array([[8, 0, 0], [2, 8, 0], [-1, 3, 8]], np.float32)
+    frac = rng.integers(0, 1024, (260, 3)) / 1024.0
+    p = (frac @ h.astype(np.float64)).astype(np.float32)
+    shift = rng.integers(-2, 3, (260, 3)).astype(np.float64) @ h.astype(np.float64)
+    q = (p.astype(np.float64) + shift).astype(np.float32)
+    assert np.array_equal(q.astype(np.float64), p.astype(np.float64) + shift)   # exact
+    # dims of that matrix: lengths and angles (the port only needs them to be non-90)
+    lx, ly, lz = (np.linalg.norm(h[k].astype(np.float64)) for k in range(3))
+    import oracle
+    L = oracle.lib()
+
+    def counts(a):
+        cap = len(a) ** 2
+        pairs, dist = np.empty((cap, 2), np.int64), np.empty(cap)
+        m = L.mdho_capped_distance_triclinic(a.ctypes.data, len(a), a.ctypes.data, len(a),
+                                             np.ascontiguousarray(h).ctypes.data, 3.9, -1e-16,
+                                             pairs.ctypes.data, dist.ctypes.data, cap)
+        return np.sort(dist[:m])
+    assert np.array_equal(counts(p), counts(q))
+    assert lx > 0 and ly > 0 and lz > 0
