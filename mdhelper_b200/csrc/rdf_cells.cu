@@ -423,7 +423,13 @@ int launch_cells(mdh_ctx *c, const CellParams &P, dim3 grid)
 
 // ---- fp32-filter pair kernel: one warp per cell ------------------------------------------
 
-constexpr int kCpThreads = 256;
+#ifndef MDH_CP_THREADS
+#define MDH_CP_THREADS 256
+#endif
+#ifndef MDH_CP_BLOCKS
+#define MDH_CP_BLOCKS 2
+#endif
+constexpr int kCpThreads = MDH_CP_THREADS;     // warps x 32; tuning: -DMDH_CP_THREADS=192
 constexpr int kCpWarps = kCpThreads / 32;
 constexpr int kCpRanges = 19;            // own cell + 9 rows x (main run, wrapped cell)
 constexpr int kCpListCap = 64;           // deferred entries per warp and cell pass
@@ -564,7 +570,7 @@ __device__ __noinline__ void cp_long_cell(const CellPairParams &P, int frame, co
 }
 
 template <bool HALF, bool EXCL, bool LOWER, bool AUDIT, int IPT>
-__global__ void __launch_bounds__(kCpThreads, 2)
+__global__ void __launch_bounds__(kCpThreads, MDH_CP_BLOCKS)
     rdf_cellpair_kernel(const __grid_constant__ CellPairParams P)
 {
     static_assert(IPT == 2 || IPT == 4, "particles are processed in packed pairs");
@@ -690,9 +696,12 @@ __global__ void __launch_bounds__(kCpThreads, 2)
             total = __shfl_sync(0xffffffffu, pre, 31);
             pre -= len;
             n_i = __shfl_sync(0xffffffffu, len, 0);
-            wrng[slot * 32 + lane] = make_int2(b, len);
             if (n_i == 0 || (!HALF && total == n_i)) return 0;
-            if (total > cap) return n_i <= cap - 64 ? 2 : 3;
+            if (total > cap) {
+                wrng[slot * 32 + lane] = make_int2(b, len);   // the long-list paths walk the runs
+                __syncwarp();
+                return n_i <= cap - 64 ? 2 : 3;
+            }
             const unsigned bar = bar32 + 8u * slot;
             if (lane == 0) cp_mbar_expect(bar, (unsigned)total * 16u);
             __syncwarp();
@@ -745,8 +754,12 @@ __global__ void __launch_bounds__(kCpThreads, 2)
         auto compute = [&](int slot, int n_i, int je, bool do_self) {
             const float4 *buf = wbuf + slot * bufw;
             const int total = je;
-            const int n_chunks = (n_i + 8 * IPT - 1) / (8 * IPT);
-            const int cs = (n_i + n_chunks - 1) / n_chunks;
+            // chunks of at most 8 * IPT particles (nearly always one)
+            int cs = n_i;
+            if (n_i > 8 * IPT) {
+                const int n_chunks = (n_i + 8 * IPT - 1) / (8 * IPT);
+                cs = (n_i + n_chunks - 1) / n_chunks;
+            }
             for (int off = 0; off < n_i; off += cs) {
                 const int cn = min(cs, n_i - off);
                 // ni <= 8 lanes hold the chunk; lane / ni without an integer division
@@ -754,6 +767,7 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                 const int ni = (cn + IPT - 1) / IPT;
                 const float rni = __frcp_rn((float)ni);
                 const int ways = (int)(32.5f * rni);
+                const float rways = __frcp_rn((float)ways);
                 const int way = (int)(((float)lane + 0.5f) * rni), il = lane - way * ni;
                 const bool lane_ok = way < ways;
                 const int ipos0 = off + il * IPT;
@@ -826,7 +840,14 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                 };
                 // a row with an uncertain pair: remember it (re-evaluated after the pass), or
                 // re-evaluate on the spot when the list is full
-                auto push_row = [&](int jpos, unsigned weight) {
+                auto push_row = [&](const unsigned *uu, int jpos, unsigned weight) {
+                    // only pairs inside the histogram range can change a count (5 of 6
+                    // candidates of a cut-off run lie beyond it)
+                    bool any = false;
+#pragma unroll
+                    for (int k = 0; k < IPT; ++k)
+                        any = any || ((uu[k] & fmask) < ff.wlim && uu[k] < span_l);
+                    if (!any) return;
                     const unsigned idx = atomicAdd(wcount, 1u);
                     if (idx < (unsigned)kCpListCap) {
                         wlist[idx] = ((unsigned)lane << 16) | (unsigned)jpos;
@@ -842,7 +863,9 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                 // the list are clamped to its last entry and carry weight 0)
                 auto run_list = [&](int jb, int cnt, unsigned weight, auto self_tag) {
                     if (cnt <= 0) return;
-                    const int full = cnt / ways, rem = cnt - full * ways;
+                    // cnt / ways without an integer division (cnt <= 1024, ways <= 32:
+                    // (cnt + 1/2) / ways stays 1/64 away from every integer)
+                    const int full = (int)(((float)cnt + 0.5f) * rways), rem = cnt - full * ways;
                     const int jmax = jb + cnt - 1;
                     unsigned wi[IPT];
 #pragma unroll
@@ -865,30 +888,33 @@ __global__ void __launch_bounds__(kCpThreads, 2)
                         const unsigned v0 = hist_row(a0, u0, j, wi, self_tag);
                         const unsigned v1 = hist_row(a1, u1, j + ways, wi, self_tag);
                         if (min(v0, v1) < ff.wlim && lane_ok) {
-                            if (v0 < ff.wlim) push_row(j, weight);
-                            if (v1 < ff.wlim) push_row(j + ways, weight);
+                            if (v0 < ff.wlim) push_row(u0, j, weight);
+                            if (v1 < ff.wlim) push_row(u1, j + ways, weight);
                         }
                         j += 2 * ways;
                     }
-                    // at most one more full row and the partial row: one more pass of the
-                    // same code, weights of the rows that do not exist set to 0
+                    // at most one more full row and the partial row (rows that do not exist
+                    // for this lane carry weight 0)
                     const int left = (full - t) + (rem ? 1 : 0);      // 0, 1 or 2 rows
                     if (left > 0) {
-                        unsigned w0[IPT], w1[IPT];
+                        unsigned w0[IPT];
                         const bool ok0 = lane_ok && (t < full || way < rem);
-                        const bool ok1 = lane_ok && left == 2 && way < rem;
 #pragma unroll
-                        for (int k = 0; k < IPT; ++k) {
-                            w0[k] = ok0 ? wi[k] : 0u;
-                            w1[k] = ok1 ? wi[k] : 0u;
-                        }
-                        unsigned u0[IPT], u1[IPT];
+                        for (int k = 0; k < IPT; ++k) w0[k] = ok0 ? wi[k] : 0u;
+                        unsigned u0[IPT];
                         eval_row(r0, u0);
-                        eval_row(r1, u1);
                         const unsigned v0 = hist_row(r0, u0, j, w0, self_tag);
+                        if (v0 < ff.wlim && ok0) push_row(u0, j, weight);
+                    }
+                    if (left > 1) {
+                        unsigned w1[IPT];
+                        const bool ok1 = lane_ok && way < rem;
+#pragma unroll
+                        for (int k = 0; k < IPT; ++k) w1[k] = ok1 ? wi[k] : 0u;
+                        unsigned u1[IPT];
+                        eval_row(r1, u1);
                         const unsigned v1 = hist_row(r1, u1, j + ways, w1, self_tag);
-                        if (v0 < ff.wlim && ok0) push_row(j, weight);
-                        if (v1 < ff.wlim && ok1) push_row(j + ways, weight);
+                        if (v1 < ff.wlim && ok1) push_row(u1, j + ways, weight);
                     }
                 };
 
@@ -1049,7 +1075,7 @@ int launch_cellpair(mdh_ctx *c, const CellPairParams &P, bool half, bool excl, b
 int cellpair_sub_bins(int n_bins, int sb_max, int cap)
 {
     for (int sb = sb_max; sb >= 0; --sb)
-        if (cp_smem_bytes(n_bins, sb, cap) <= 112 * 1024) return sb;
+        if (cp_smem_bytes(n_bins, sb, cap) <= (size_t)(224 * 1024 / MDH_CP_BLOCKS)) return sb;
     return cp_smem_bytes(n_bins, 0, cap) <= 224 * 1024 ? 0 : -1;
 }
 

@@ -595,3 +595,35 @@ def test_triclinic_kernel_with_right_angles_equals_orthorhombic_kernels():
     want = _oracle().rdf_run(u, u.atoms, n_bins=64, range=(0.0, 5.0))
     assert np.array_equal(r.results.counts, want["counts"])
     np.testing.assert_allclose(r.results.rdf, want["rdf"], rtol=1e-6)
+
+
+def test_on_disk_style_reader_gives_the_in_memory_results(tmp_path):
+    """The analyses on a reader that seeks frames from a file (no whole-trajectory array;
+    the staged feeder path) equal the runs on the in-memory trajectory: RDF with strided
+    frames and explicit frame lists, residue groupings, per-frame cells."""
+    from conftest import file_universe
+    from mdhelper_b200.universe import SyntheticUniverse
+    rng = np.random.default_rng(31)
+    F, n = 9, 1200
+    edges = rng.uniform(9.5, 10.5, (F, 3)).astype(np.float32)
+    dims = np.concatenate([edges, np.full((F, 3), 90, np.float32)], 1)
+    pos = (rng.random((F, n, 3)) * edges[:, None, :]).astype(np.float32)
+    mem = SyntheticUniverse(pos, dims)
+    disk = file_universe(tmp_path, pos, dims)
+    S = _structure()
+    kw = dict(n_bins=50, range=(0.0, 4.5), verbose=False, batch_frames=4)
+    for run_kw in (dict(), dict(start=1, stop=8, step=3), dict(frames=[7, 2, 5])):
+        a = S.RadialDistributionFunction(mem.atoms, **kw).run(**run_kw)
+        b = S.RadialDistributionFunction(disk.atoms, **kw).run(**run_kw)
+        assert np.array_equal(a.results.counts, b.results.counts)
+        np.testing.assert_allclose(a.results.rdf, b.results.rdf, rtol=1e-12)
+    g1m, g2m = mem.select(slice(0, 500)), mem.select(slice(500, n))
+    g1d, g2d = disk.select(slice(0, 500)), disk.select(slice(500, n))
+    a = S.RadialDistributionFunction(g1m, g2m, exclusion=(2, 2), **kw).run()
+    b = S.RadialDistributionFunction(g1d, g2d, exclusion=(2, 2), **kw).run()
+    assert np.array_equal(a.results.counts, b.results.counts)
+    sa = S.StructureFactor([g1m, g2m], mode="partial", n_points=6, verbose=False).run()
+    sb = S.StructureFactor([g1d, g2d], mode="partial", n_points=6, verbose=False,
+                           batch_frames=2).run()
+    np.testing.assert_allclose(sa.results.ssf, sb.results.ssf, rtol=1e-12)
+    assert disk.trajectory.reads > 0

@@ -456,3 +456,31 @@ def test_combined_analysis_rejects_classes_with_their_own_frame_loop():
     with pytest.raises(TypeError):
         CombinedAnalysis(rdf, isf)
     CombinedAnalysis(rdf)                      # the plain classes are accepted
+
+
+def test_staged_feeder_reads_an_on_disk_style_reader(tmp_path):
+    """A reader without a whole-trajectory array (frames seeked one by one from a file):
+    the feeder gathers each batch into its staging buffers -- right frames, right atoms,
+    right cells, two alternating buffers."""
+    import ctypes
+    from conftest import file_universe
+    from mdhelper_b200.analysis.base import FrameFeeder
+    rng = np.random.default_rng(3)
+    pos = rng.random((7, 30, 3)).astype(np.float32)
+    dims = np.concatenate([rng.uniform(5, 6, (7, 3)), np.full((7, 3), 90.0)], 1).astype(np.float32)
+    u = file_universe(tmp_path, pos, dims)
+    ix = [np.array([2, 3, 4, 9]), np.arange(10, 30)]
+    feeder = FrameFeeder(u.trajectory, ix, np.array([6, 1, 3, 4, 0]), 2)
+    assert not feeder.zero_copy
+    seen = 0
+    for b, frames in zip(feeder, ([6, 1], [3, 4], [0])):
+        assert b.n_frames == len(frames) and b.strides == [12, 60]
+        np.testing.assert_array_equal(b.dims, dims[frames])
+        for k, f in enumerate(frames):
+            for s, sel in enumerate(ix):
+                n = len(sel)
+                a = np.ctypeslib.as_array((ctypes.c_float * (3 * n)).from_address(
+                    b.ptrs[s] + 4 * b.strides[s] * k)).reshape(n, 3)
+                np.testing.assert_array_equal(a, pos[f][sel])
+        seen += b.n_frames
+    assert seen == 5 and u.trajectory.reads >= 5
