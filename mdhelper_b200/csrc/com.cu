@@ -83,7 +83,7 @@ int com_reduce_impl(mdh_ctx *c, int slot, const float *pos, int64_t stride, int 
     int64_t dstride = stride;
     if (location == MDH_HOST) {
         if (int rc = K.raw.reserve(sizeof(float) * 3 * K.n_atoms * n_frames)) return rc;
-        MDH_CUDA(cudaMemcpy2DAsync(K.raw.p, sizeof(float) * 3 * K.n_atoms, pos,
+        MDH_CUDA(mdh_copy_frames(K.raw.p, sizeof(float) * 3 * K.n_atoms, pos,
                                    sizeof(float) * stride, sizeof(float) * 3 * K.n_atoms,
                                    n_frames, cudaMemcpyHostToDevice, c->stream));
         dsrc = K.raw.as<float>();

@@ -88,8 +88,8 @@ struct RdfState {
     DevBuf pk1, pk2;       // float4[F][npad]
     DevBuf boxes;          // FrameBox[F]
     DevBuf cell[10];       // cell-list scratch, layout in rdf_cells.cu
-    double cells_ws_mb = 96.0;   // working set of one group of frames (sort + pair kernel)
-    int cells_chunk = 8;         // cells per work item of the cell-pair kernel
+    double cells_ws_mb = 192.0;   // working set of one group of frames (sort + pair kernel)
+    int cells_chunk = 4;         // cells per work item of the cell-pair kernel
     int cells_ipt = 4;           // particles per lane of the cell-pair kernel (2 or 4)
     bool cells_debug = false;    // per-stage device times on stderr (MDH_TUNE cdbg=1)
     bool evals_dev_init = false;
@@ -211,6 +211,17 @@ struct HostStager {
 // one nothing can hide -- is short (~2 MB), later ones are long enough (up to ~32 MB) for
 // their kernels to run at full efficiency.
 std::vector<int> mdh_plan_pieces(int n_frames, double bytes_per_frame);
+
+// Frame-strided copy: one contiguous transfer when the frames are adjacent on both sides
+// (a 2-D copy of rows that happen to be contiguous is split by the driver), else a 2-D copy.
+inline cudaError_t mdh_copy_frames(void *dst, size_t dpitch, const void *src, size_t spitch,
+                                   size_t width, size_t n_frames, cudaMemcpyKind kind,
+                                   cudaStream_t stream)
+{
+    if (dpitch == width && spitch == width)
+        return cudaMemcpyAsync(dst, src, width * n_frames, kind, stream);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, n_frames, kind, stream);
+}
 
 struct mdh_ctx {
     int device = 0;

@@ -350,7 +350,7 @@ static int rdf_upload_group(mdh_ctx *c, const float *pos, int64_t stride, int lo
     if (location == MDH_HOST) {
         if (copy_only) {
             if (int rc = raw.reserve(sizeof(float) * 3 * n * n_frames)) return rc;
-            MDH_CUDA(cudaMemcpy2DAsync(raw.p, sizeof(float) * 3 * n, pos,
+            MDH_CUDA(mdh_copy_frames(raw.p, sizeof(float) * 3 * n, pos,
                                        sizeof(float) * stride, sizeof(float) * 3 * n, n_frames,
                                        cudaMemcpyHostToDevice, c->stager.copy));
             return MDH_OK;

@@ -187,7 +187,7 @@ int rdf_accumulate_triclinic_impl(mdh_ctx *c, const float *pos1, int64_t s1, con
         int64_t dstride = stride;
         if (location == MDH_HOST) {
             if (int rc = raw.reserve(sizeof(float) * 3 * n * n_frames)) return rc;
-            MDH_CUDA(cudaMemcpy2DAsync(raw.p, sizeof(float) * 3 * n, pos, sizeof(float) * stride,
+            MDH_CUDA(mdh_copy_frames(raw.p, sizeof(float) * 3 * n, pos, sizeof(float) * stride,
                                        sizeof(float) * 3 * n, n_frames, cudaMemcpyHostToDevice,
                                        c->stream));
             dsrc = raw.as<float>();

@@ -344,7 +344,7 @@ template <int nt0, int nt1>
 __device__ __forceinline__ void sq_mma_subchunk(const double2 *tab, const int (&bx)[kMmaG],
                                                 const int (&by)[kMmaG], int bz,
                                                 const double *sums, int bs,
-                                                double (&acc)[kMmaAcc][kMmaG][kMmaTZ][2])
+                                                double (&acc)[kMmaAcc][kMmaG][nt0][2])
 {
     constexpr int NG = nt1 > 0 ? 2 : 1;
 #pragma unroll
@@ -448,6 +448,68 @@ __host__ __device__ inline int mma_consumer_warp(int W, int c)
     return w;
 }
 
+
+// The consumer loop of one warp item with NT0 / NT1 nz tiles in its two column groups:
+// walks the block's work units, waits for each table stage, runs the sub-chunk update and
+// adds the finished unit to rho (or |rho_chain|^2 to the chain accumulator).
+template <int NT0, int NT1>
+__device__ __forceinline__ void sq_mma_consume(const MmaParams &P, const double2 *sTab, int R,
+                                               uint64_t *bar_full, uint64_t *bar_empty,
+                                               const int (&bx)[kMmaG], const int (&by)[kMmaG],
+                                               int bz, int bs, const int *qi, int g, int k,
+                                               int lane)
+{
+    double acc[kMmaAcc][kMmaG][NT0][2];
+#pragma unroll
+    for (int c = 0; c < kMmaAcc; ++c)
+#pragma unroll
+        for (int i = 0; i < kMmaG; ++i)
+#pragma unroll
+            for (int t = 0; t < NT0; ++t) acc[c][i][t][0] = acc[c][i][t][1] = 0.0;
+
+    int it = 0;
+    for (int u = blockIdx.y; u < P.n_units; u += gridDim.y) {
+        const int frame = u / P.n_chunks;
+        const int4 chunk = P.chunks[u - frame * P.n_chunks];
+        for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS, ++it) {
+            const int stage = it % kMmaStages, use = it / kMmaStages;
+            mbar_wait(bar_full + stage, use & 1);
+            const double2 *tab = sTab + (size_t)stage * mma_stage_entries(R, P.nzpad);
+            const double *sums = reinterpret_cast<const double *>(tab + R * kRowSlots);
+            sq_mma_subchunk<NT0, NT1>(tab, bx, by, bz, sums, bs, acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + stage);
+        }
+
+        double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
+#pragma unroll
+        for (int i = 0; i < kMmaG; ++i)
+#pragma unroll
+            for (int t = 0; t < NT0; ++t) {
+                if (t < (i == 0 ? NT0 : NT1)) {
+                    // this lane holds C[g][2k], C[g][2k + 1]
+                    const int2 q2 = *reinterpret_cast<const int2 *>(
+                        qi + ((i * kMmaTZ + t) * 8 + g) * 8 + 2 * k);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int q = j ? q2.y : q2.x;
+                        if (q < 0) continue;
+                        const double p1 = acc[0][i][t][j], p2 = acc[1][i][t][j];
+                        const double re = kMma3M ? p1 - p2 : p1;
+                        const double im = kMma3M ? acc[kMmaAcc - 1][i][t][j] - p1 - p2 : p2;
+                        if (P.chain_out) {
+                            atomicAdd(P.chain_out + q, re * re + im * im);
+                        } else {
+                            atomicAdd(out + 2 * q, re);
+                            atomicAdd(out + 2 * q + 1, im);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < kMmaAcc; ++c) acc[c][i][t][0] = acc[c][i][t][1] = 0.0;
+                }
+            }
+    }
+}
 
 // Persistent block = n_cons consumer warps (one SqMmaItem each) and kMmaProducers producer
 // threads (warp roles: mma_producer_warp).  The block walks the work units (frame, particle chunk) blockIdx.y,
@@ -605,68 +667,24 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
     // this lane's B_r + B_i entry (doubles, behind the R double2 rows of the stage)
     const int bs = (8 * item->t0 + g) * kRowSlots + k;
 
-    double acc[kMmaAcc][kMmaG][kMmaTZ][2];
-#pragma unroll
-    for (int c = 0; c < kMmaAcc; ++c)
-#pragma unroll
-        for (int i = 0; i < kMmaG; ++i)
-#pragma unroll
-            for (int t = 0; t < kMmaTZ; ++t) acc[c][i][t][0] = acc[c][i][t][1] = 0.0;
-
     const int *qi = P.qidx + (int64_t)item_index * (kMmaG * kMmaTZ * 64);
-    int it = 0;
-    for (int u = blockIdx.y; u < P.n_units; u += gridDim.y) {
-        const int frame = u / P.n_chunks;
-        const int4 chunk = P.chunks[u - frame * P.n_chunks];
-        for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS, ++it) {
-            const int stage = it % kMmaStages, use = it / kMmaStages;
-            mbar_wait(bar_full + stage, use & 1);
-            const double2 *tab = sTab + (size_t)stage * mma_stage_entries(R, P.nzpad);
-            const double *sums = reinterpret_cast<const double *>(tab + R * kRowSlots);
-#define MDH_MMA_CASE(A, B) \
-    case A * 8 + B: sq_mma_subchunk<A, B>(tab, bx, by, bz, sums, bs, acc); break;
-            switch (nt0 * 8 + nt1) {
-                MDH_MMA_CASE(1, 0) MDH_MMA_CASE(2, 0) MDH_MMA_CASE(3, 0) MDH_MMA_CASE(4, 0)
+    // the whole consumer loop is instantiated per (tiles of group 0, tiles of group 1): the
+    // accumulators of an item then are exactly the registers it needs (a runtime tile count
+    // kept all 3 x 2 x 4 pairs -- 96 registers -- alive and spilled in the hot loop)
+#define MDH_MMA_CASE(A, B)                                                                   \
+    case A * 8 + B:                                                                          \
+        sq_mma_consume<A, B>(P, sTab, R, bar_full, bar_empty, bx, by, bz, bs, qi, g, k, lane); \
+        break;
+    switch (nt0 * 8 + nt1) {
+        MDH_MMA_CASE(1, 0) MDH_MMA_CASE(2, 0) MDH_MMA_CASE(3, 0) MDH_MMA_CASE(4, 0)
 #if MDH_SQ_MMA_G > 1
-                MDH_MMA_CASE(1, 1) MDH_MMA_CASE(2, 1) MDH_MMA_CASE(2, 2) MDH_MMA_CASE(3, 1)
-                MDH_MMA_CASE(3, 2) MDH_MMA_CASE(3, 3) MDH_MMA_CASE(4, 1) MDH_MMA_CASE(4, 2)
-                MDH_MMA_CASE(4, 3) MDH_MMA_CASE(4, 4)
+        MDH_MMA_CASE(1, 1) MDH_MMA_CASE(2, 1) MDH_MMA_CASE(2, 2) MDH_MMA_CASE(3, 1)
+        MDH_MMA_CASE(3, 2) MDH_MMA_CASE(3, 3) MDH_MMA_CASE(4, 1) MDH_MMA_CASE(4, 2)
+        MDH_MMA_CASE(4, 3) MDH_MMA_CASE(4, 4)
 #endif
-                default: break;
-            }
-#undef MDH_MMA_CASE
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + stage);
-        }
-
-        double *out = P.rho + ((int64_t)frame * P.n_rho + chunk.z) * P.n_q * 2;
-#pragma unroll
-        for (int i = 0; i < kMmaG; ++i)
-#pragma unroll
-            for (int t = 0; t < kMmaTZ; ++t) {
-                if (t < (i == 0 ? nt0 : nt1)) {
-                    // this lane holds C[g][2k], C[g][2k + 1]
-                    const int2 q2 = *reinterpret_cast<const int2 *>(
-                        qi + ((i * kMmaTZ + t) * 8 + g) * 8 + 2 * k);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int q = j ? q2.y : q2.x;
-                        if (q < 0) continue;
-                        const double p1 = acc[0][i][t][j], p2 = acc[1][i][t][j];
-                        const double re = kMma3M ? p1 - p2 : p1;
-                        const double im = kMma3M ? acc[kMmaAcc - 1][i][t][j] - p1 - p2 : p2;
-                        if (P.chain_out) {
-                            atomicAdd(P.chain_out + q, re * re + im * im);
-                        } else {
-                            atomicAdd(out + 2 * q, re);
-                            atomicAdd(out + 2 * q + 1, im);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < kMmaAcc; ++c) acc[c][i][t][0] = acc[c][i][t][1] = 0.0;
-            }
+        default: break;
     }
+#undef MDH_MMA_CASE
 }
 
 struct GeneralParams {
@@ -1363,7 +1381,7 @@ static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int
         if (int rc = c->stager.acquire(&slot)) return rc;
         DevBuf &raw = S.raw[slot];
         if (int rc = raw.reserve(sizeof(float) * 3 * S.n_total * n_frames)) return rc;
-        MDH_CUDA(cudaMemcpy2DAsync(raw.p, sizeof(float) * 3 * S.n_total, pos,
+        MDH_CUDA(mdh_copy_frames(raw.p, sizeof(float) * 3 * S.n_total, pos,
                                    sizeof(float) * stride, sizeof(float) * 3 * S.n_total,
                                    n_frames, cudaMemcpyHostToDevice, c->stager.copy));
         if (int rc = c->stager.publish(c->stream, slot)) return rc;
@@ -1522,7 +1540,7 @@ int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locati
         MDH_CUDA(cudaStreamSynchronize(c->stream));
         win.adopt(bigger);
     }
-    MDH_CUDA(cudaMemcpy2DAsync(win.as<float>() + fsz * keep, sizeof(float) * fsz, pos,
+    MDH_CUDA(mdh_copy_frames(win.as<float>() + fsz * keep, sizeof(float) * fsz, pos,
                                sizeof(float) * stride, sizeof(float) * fsz, n_frames,
                                location == MDH_HOST ? cudaMemcpyHostToDevice
                                                     : cudaMemcpyDeviceToDevice, c->stream));

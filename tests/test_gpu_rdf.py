@@ -622,6 +622,9 @@ def test_on_disk_style_reader_gives_the_in_memory_results(tmp_path):
     a = S.RadialDistributionFunction(g1m, g2m, exclusion=(2, 2), **kw).run()
     b = S.RadialDistributionFunction(g1d, g2d, exclusion=(2, 2), **kw).run()
     assert np.array_equal(a.results.counts, b.results.counts)
+    # the wavevector grid comes from the cell of the reader's CURRENT frame: same frame
+    mem.trajectory[0]
+    disk.trajectory[0]
     sa = S.StructureFactor([g1m, g2m], mode="partial", n_points=6, verbose=False).run()
     sb = S.StructureFactor([g1d, g2d], mode="partial", n_points=6, verbose=False,
                            batch_frames=2).run()
