@@ -81,6 +81,18 @@ enum {
                               test aid)                                               */
 };
 
+/* coordinates outside the cell (same counts for coordinates inside [0, L)) */
+enum {
+    MDH_WRAP_AUTO = 0,     /* as the reference: MDAnalysis' capped_distance moves both
+                              coordinate sets into the cell IN FLOAT32 before taking
+                              differences whenever it picks its grid search (both groups
+                              >= 10 particles and n1 * n2 >= 1e8 or r_max <= 0.3 * shortest
+                              edge), and takes the differences of the coordinates as given
+                              when it picks brute force                               */
+    MDH_WRAP_NEVER = 1,    /* brute-force semantics for every frame                    */
+    MDH_WRAP_ALWAYS = 2    /* grid-search semantics for every frame                    */
+};
+
 /* S(q) kernel strategy */
 enum {
     MDH_SQ_AUTO = 0,
@@ -177,6 +189,8 @@ int mdh_rdf_pair_evaluations(mdh_ctx *ctx, int64_t *evals);
  * value; it persists across mdh_rdf_configure calls of the context.
  */
 int mdh_rdf_set_filter(mdh_ctx *ctx, int mode);
+/* MDH_WRAP_* selector; persists across mdh_rdf_configure calls of the context. */
+int mdh_rdf_set_prewrap(mdh_ctx *ctx, int mode);
 /* stats[0] pairs-of-IPT entries re-evaluated from the deferred lists, stats[1]
  * entries re-evaluated inline (list overflow), stats[2] audit violations (must be
  * 0), stats[3] uncertain pairs seen by the audit, stats[4] frames the filter

@@ -24,6 +24,7 @@ MDH_HOST, MDH_DEVICE = 0, 1
 RDF_MODES = {"auto": 0, "allpairs": 1, "cells": 2}
 HIST_MODES = {"auto": 0, "warp_atomic": 1, "lane_private": 2}
 FILTER_MODES = {"auto": 0, "off": 1, "on": 2, "audit": 3}
+WRAP_MODES = {"auto": 0, "never": 1, "always": 2}
 SQ_MODES = {"auto": 0, "lattice_fp64": 1, "general_fp64": 3, "lattice_fp32": 4,
             "lattice_dmma": 5}
 
@@ -51,6 +52,7 @@ SIGNATURES = {
     "mdh_rdf_counts_device": (_i32, [_p, ctypes.POINTER(_p)]),
     "mdh_rdf_pair_evaluations": (_i32, [_p, ctypes.POINTER(_i64)]),
     "mdh_rdf_set_filter": (_i32, [_p, _i32]),
+    "mdh_rdf_set_prewrap": (_i32, [_p, _i32]),
     "mdh_rdf_filter_stats": (_i32, [_p, _p]),
     "mdh_sq_configure": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i32, _p, _i32]),
     "mdh_sq_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
@@ -229,6 +231,11 @@ class Context:
     def rdf_set_filter(self, mode: str = "auto"):
         """fp32 filter of the all-pairs kernel: ``auto``, ``off``, ``on``, ``audit``."""
         check(self._lib.mdh_rdf_set_filter(self._h, FILTER_MODES[mode]))
+
+    def rdf_set_prewrap(self, mode: str = "auto"):
+        """Coordinates outside the cell: ``auto`` (as the reference: moved into the cell in
+        float32 whenever MDAnalysis would pick its grid search), ``never``, ``always``."""
+        check(self._lib.mdh_rdf_set_prewrap(self._h, WRAP_MODES[mode]))
 
     def rdf_filter_stats(self) -> dict:
         out = np.zeros(6, dtype=np.int64)

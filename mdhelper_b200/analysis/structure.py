@@ -98,8 +98,8 @@ def _n_entities(group, grouping: str) -> int:
 def radial_histogram(
         pos1: np.ndarray, pos2: np.ndarray, n_bins: int, range: tuple,
         dims: tuple, *, exclusion: tuple = None, mode: str = "auto",
-        hist: str = "auto", arith: str = "auto", device: int = None,
-        stats: dict = None) -> np.ndarray:
+        hist: str = "auto", arith: str = "auto", wrap: str = "auto",
+        device: int = None, stats: dict = None) -> np.ndarray:
     """
     Computes the radial histogram of distances between particles of the same
     type or two different types (GPU version of ``structure.py:32-104``).
@@ -129,6 +129,14 @@ def radial_histogram(
         re-evaluated exactly); ``"off"``: fp64 for every pair; ``"audit"``:
         filter plus a full exact comparison (test aid).  Counts do not depend
         on it either.
+    wrap : `str`, keyword-only
+        Coordinates outside the cell: ``"auto"`` follows the reference --
+        ``capped_distance`` moves both coordinate sets into the cell in float32 before
+        taking differences whenever it picks its grid search (both groups have at least
+        10 particles and ``n1 * n2 >= 1e8`` or ``range[1] <= 0.3 *`` the shortest cell
+        edge) and takes the differences of the coordinates as given otherwise;
+        ``"never"`` / ``"always"`` force one of the two.  No effect on coordinates inside
+        ``[0, L)``.
     stats : `dict`, keyword-only, optional
         If given, receives the filter statistics of the call.
 
@@ -150,6 +158,7 @@ def radial_histogram(
     ctx = Context(dev)
     try:
         ctx.rdf_set_filter(arith)
+        ctx.rdf_set_prewrap(wrap)
         # the same array twice: the kernels may use the pair symmetry (same counts) --
         # unless the exclusion blocks differ, i // e0 == j // e1 is not symmetric then
         same = pos2 is pos1 and (exclusion is None or exclusion[0] == exclusion[1])
@@ -204,8 +213,9 @@ class RadialDistributionFunction(GpuAnalysisBase):
         ``torch.distributed`` is initialised.
     verbose : `bool`, keyword-only, default: :code:`True`
         Determines whether progress is logged.
-    mode, hist, arith : `str`, keyword-only
-        Kernel selectors, see :func:`radial_histogram`.
+    mode, hist, arith, wrap : `str`, keyword-only
+        Kernel selectors and the treatment of coordinates outside the cell, see
+        :func:`radial_histogram`.
     host_com : `bool`, keyword-only, default: :code:`False`
         Compute centres of mass on the host even where the device kernel applies
         (entities that are consecutive atom runs); the results are identical.
@@ -232,7 +242,8 @@ class RadialDistributionFunction(GpuAnalysisBase):
             groupings: Union[str, tuple] = "atoms", reduced: bool = False,
             n_batches: int = None, parallel: bool = False,
             verbose: bool = True, mode: str = "auto", hist: str = "auto",
-            arith: str = "auto", host_com: bool = False, **kwargs) -> None:
+            arith: str = "auto", wrap: str = "auto", host_com: bool = False,
+            **kwargs) -> None:
 
         self.ag1 = ag1
         self.ag2 = ag1 if ag2 is None else ag2
@@ -274,6 +285,7 @@ class RadialDistributionFunction(GpuAnalysisBase):
         self._mode = mode
         self._hist = hist
         self._arith = arith
+        self._wrap = wrap
         self._host_com = bool(host_com)
         self._com = None
 
@@ -301,6 +313,7 @@ class RadialDistributionFunction(GpuAnalysisBase):
             and (not self._exclusion or self._exclusion[0] == self._exclusion[1])
         self._same = same
         ctx.rdf_set_filter(self._arith)
+        ctx.rdf_set_prewrap(self._wrap)
         if getattr(self, "_thresholds", None) is None:   # fixed per instance
             self._thresholds = squared_thresholds(self._n_bins, self._range)
         ctx.rdf_configure(

@@ -343,6 +343,15 @@ int mdh_rdf_set_filter(mdh_ctx *c, int mode)
     return MDH_OK;
 }
 
+int mdh_rdf_set_prewrap(mdh_ctx *c, int mode)
+{
+    MDH_REQUIRE(c != nullptr, MDH_EINVAL, "context is NULL");
+    MDH_REQUIRE(mode >= MDH_WRAP_AUTO && mode <= MDH_WRAP_ALWAYS, MDH_EINVAL,
+                "rdf: invalid wrap mode");
+    c->rdf.prewrap_mode = mode;
+    return MDH_OK;
+}
+
 int mdh_rdf_filter_stats(mdh_ctx *c, int64_t *stats)
 {
     CTX_GUARD(c);

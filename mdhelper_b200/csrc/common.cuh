@@ -53,6 +53,8 @@ struct DevBuf {
 struct FrameBox {          // per frame, device side
     double box[3];         // (double)box_f32
     double inv[3];         // (double)(float)(1.0 / (double)box_f32)
+    int prewrap;           // coordinates are first moved into the cell in float32 (what the
+    int pad;               // reference's grid search does, see rdf_device.cuh::ortho_pbc_f32)
 };
 
 // fp32 filter, per frame (built on the device by rdf_filter_prepare_kernel)
@@ -101,6 +103,7 @@ struct RdfState {
     int ipt = 2;           // i-particles per thread of the all-pairs kernel
     bool fast_bins = false;  // branch-free bin guess certified for this configuration
     // fp32 filter in front of the exact arithmetic (rdf_filter.cu)
+    int prewrap_mode = MDH_WRAP_AUTO;    // survives configure
     int filter_mode = MDH_FILTER_AUTO;   // survives configure
     bool filter_ok = false;  // this configuration is eligible
     int filter_occ = 2;      // blocks per SM the filter kernel is compiled for (2 or 3)

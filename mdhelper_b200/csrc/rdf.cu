@@ -339,7 +339,7 @@ int rdf_configure_impl(mdh_ctx *c, int64_t n1, int64_t n2, int same, int n_bins,
 // brackets the group copies of a piece with stager.acquire / publish)
 static int rdf_upload_group(mdh_ctx *c, const float *pos, int64_t stride, int location,
                             int64_t n, int64_t npad, int64_t excl, int n_frames,
-                            DevBuf &raw, DevBuf &pk, DevBuf *ext, bool copy_only)
+                            DevBuf &raw, DevBuf &pk, DevBuf *ext, bool copy_only, int f0)
 {
     RdfState &R = c->rdf;
     MDH_REQUIRE(pos != nullptr, MDH_EINVAL, "rdf: coordinate pointer is NULL");
@@ -371,7 +371,8 @@ static int rdf_upload_group(mdh_ctx *c, const float *pos, int64_t stride, int lo
     }
     dim3 grid((unsigned)std::min<int64_t>((npad + 255) / 256, 2048), n_frames);
     rdf_pack_kernel<<<grid, 256, 0, c->stream>>>(dsrc, dstride, pk.as<float4>(), n, npad, excl,
-                                                 R.drop_axis, d_ext);
+                                                 R.drop_axis, d_ext,
+                                                 R.boxes.as<FrameBox>() + f0);
     MDH_CUDA(cudaGetLastError());
     c->launches++;
     return MDH_OK;
@@ -406,6 +407,18 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
             R.h_boxes[f].inv[k] = (double)(float)(1.0 / (double)b);
             if (k != R.drop_axis) min_edge = std::min(min_edge, b);
         }
+    // Which arithmetic the reference's capped_distance would use for each frame (SURVEY.md
+    // Appendix A item 2, MDAnalysis' method choice): its grid search moves the coordinates
+    // into the cell in float32 first, its brute force takes them as given.
+    for (int f = 0; f < n_frames; ++f) {
+        bool grid = R.n1 >= 10 && R.n2 >= 10;
+        if (grid && (double)R.n1 * (double)R.n2 < 1e8)
+            for (int k = 0; k < 3; ++k)
+                if (R.r_hi > 0.3 * (double)box[3 * f + k]) grid = false;
+        R.h_boxes[f].prewrap = R.prewrap_mode == MDH_WRAP_ALWAYS ||
+                               (R.prewrap_mode == MDH_WRAP_AUTO && grid);
+        R.h_boxes[f].pad = 0;
+    }
     if (int rc = R.boxes.reserve(sizeof(FrameBox) * n_frames)) return rc;
     // upload through a pinned staging buffer so the call stays asynchronous; the
     // event guards the buffer against being rewritten before the copy has run
@@ -463,10 +476,10 @@ static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const
     if (location == MDH_HOST) {
         if (int rc = c->stager.acquire(&slot)) return rc;
         if (int rc = rdf_upload_group(c, pos1, s1, location, R.n1, pad1, R.excl1, n_frames,
-                                      R.raw1[slot], R.pk1, nullptr, true)) return rc;
+                                      R.raw1[slot], R.pk1, nullptr, true, f0)) return rc;
         if (!R.same)
             if (int rc = rdf_upload_group(c, pos2, s2, location, R.n2, pad2, R.excl2, n_frames,
-                                          R.raw2[slot], R.pk2, nullptr, true)) return rc;
+                                          R.raw2[slot], R.pk2, nullptr, true, f0)) return rc;
         if (int rc = c->stager.publish(c->stream, slot)) return rc;
     }
     if (mode == MDH_RDF_CELLS) {
@@ -483,12 +496,13 @@ static int rdf_accumulate_piece(mdh_ctx *c, const float *pos1, int64_t s1, const
         return MDH_OK;
     }
     if (int rc = rdf_upload_group(c, pos1, s1, location, R.n1, pad1, R.excl1, n_frames,
-                                  R.raw1[slot], R.pk1, use_filter ? &R.ext1 : nullptr, false))
+                                  R.raw1[slot], R.pk1, use_filter ? &R.ext1 : nullptr, false,
+                                  f0))
         return rc;
     if (!R.same)
         if (int rc = rdf_upload_group(c, pos2, s2, location, R.n2, pad2, R.excl2, n_frames,
                                       R.raw2[slot], R.pk2, use_filter ? &R.ext2 : nullptr,
-                                      false)) return rc;
+                                      false, f0)) return rc;
     // the raw staging slot has been consumed by the pack kernels
     if (location == MDH_HOST)
         if (int rc = c->stager.retire(c->stream, slot)) return rc;

@@ -98,13 +98,15 @@ __device__ __forceinline__ void load_xyz_256(const float *__restrict__ src, int6
 __global__ void __launch_bounds__(256)
     cells_bin_kernel(const float *__restrict__ raw, int64_t frame_stride, int n,
                      const CellGrid *__restrict__ grids, int *__restrict__ cnt, int cstride,
-                     int2 *__restrict__ keyrank, unsigned *__restrict__ ext)
+                     int2 *__restrict__ keyrank, unsigned *__restrict__ ext,
+                     const FrameBox *__restrict__ boxes)
 {
     __shared__ float stage[3 * 256];
     __shared__ unsigned red[8][6];
     const int frame = blockIdx.y, tid = threadIdx.x;
     const CellGrid g = grids[frame];
     const float *src = raw + (int64_t)frame * frame_stride;
+    const bool prewrap = boxes[frame].prewrap != 0;
     unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
     for (int64_t i0 = (int64_t)blockIdx.x * 256; i0 < n; i0 += (int64_t)gridDim.x * 256) {
         load_xyz_256(src, i0, n, stage, tid);
@@ -114,7 +116,12 @@ __global__ void __launch_bounds__(256)
         // of a molecule, lattice-ordered fluids), and 32 atomics on a few addresses serialise
         const unsigned active = __ballot_sync(0xffffffffu, i < n);
         if (i < n) {
-            const float x = stage[3 * tid], y = stage[3 * tid + 1], z = stage[3 * tid + 2];
+            float x = stage[3 * tid], y = stage[3 * tid + 1], z = stage[3 * tid + 2];
+            if (prewrap) {
+                x = ortho_pbc_f32(x, g.box[0]);
+                y = ortho_pbc_f32(y, g.box[1]);
+                z = ortho_pbc_f32(z, g.box[2]);
+            }
             int cx, cy, cz;
             const int cell = cell_id(x, y, z, g, cx, cy, cz);
             const unsigned peers = __match_any_sync(active, cell);
@@ -232,7 +239,8 @@ __global__ void __launch_bounds__(1024)
 __global__ void __launch_bounds__(256)
     cells_scatter_kernel(const float *__restrict__ raw, int64_t frame_stride, int n, int64_t excl,
                          const int *__restrict__ start, int cstride,
-                         const int2 *__restrict__ keyrank, float4 *__restrict__ sorted)
+                         const int2 *__restrict__ keyrank, float4 *__restrict__ sorted,
+                         const FrameBox *__restrict__ boxes)
 {
     __shared__ float stage[3 * 256];
     const int frame = blockIdx.y, tid = threadIdx.x;
@@ -246,6 +254,11 @@ __global__ void __launch_bounds__(256)
             const int2 kr = keyrank[(int64_t)frame * n + i];
             float4 v;
             v.x = stage[3 * tid]; v.y = stage[3 * tid + 1]; v.z = stage[3 * tid + 2];
+            if (boxes[frame].prewrap) {          // the same values the binning pass saw
+                v.x = ortho_pbc_f32(v.x, boxes[frame].box[0]);
+                v.y = ortho_pbc_f32(v.y, boxes[frame].box[1]);
+                v.z = ortho_pbc_f32(v.z, boxes[frame].box[2]);
+            }
             v.w = __int_as_float((int)(excl > 0 ? i / excl : i));
             sorted[(int64_t)frame * n + st[kr.x] + kr.y] = v;
         }
@@ -1198,7 +1211,8 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
             dim3 grid((unsigned)std::min((n + 255) / 256, 4096), ng);
             cells_bin_kernel<<<grid, 256, 0, c->stream>>>(
                 raw, grp ? stride2 : stride1, n, gg, d_cnt + (size_t)grp * G * cstride, cstride,
-                R.cell[grp ? 7 : 3].as<int2>(), use_filter ? d_ext + (size_t)grp * G * 6 : nullptr);
+                R.cell[grp ? 7 : 3].as<int2>(), use_filter ? d_ext + (size_t)grp * G * 6 : nullptr,
+                R.boxes.as<FrameBox>() + f0 + g0);
             MDH_CUDA(cudaGetLastError());
             c->launches++;
         }
@@ -1232,7 +1246,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
             cells_scatter_kernel<<<grid, 256, 0, c->stream>>>(
                 raw, grp ? stride2 : stride1, n, grp ? R.excl2 : R.excl1,
                 d_start + (size_t)grp * G * cstride, cstride, R.cell[grp ? 7 : 3].as<int2>(),
-                R.cell[grp ? 8 : 4].as<float4>());
+                R.cell[grp ? 8 : 4].as<float4>(), R.boxes.as<FrameBox>() + f0 + g0);
             MDH_CUDA(cudaGetLastError());
             c->launches++;
         }

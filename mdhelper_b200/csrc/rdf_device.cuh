@@ -39,6 +39,39 @@ __host__ __device__ inline float ext_unkey(unsigned k)
 #endif
 }
 
+// Restated MDAnalysis `_ortho_pbc` (lib/include/calc_distances.h, applied by the grid search
+// FastNS to both coordinate sets; [recall], not pinned against
+// MDAnalysis): one coordinate into the primary cell, IN FLOAT32 STORAGE.  A single box
+// shift is computed in double and stored as float (so -1e-9 becomes exactly box); farther
+// coordinates take floor(c / box) shifts in float arithmetic plus one corrective shift.
+// oracle/mdh_oracle.c::mdho_ortho_pbc is the same code on the CPU.
+__device__ __forceinline__ float ortho_pbc_f32(float c, double boxd)
+{
+    const float box = (float)boxd;                   // boxd is a float32 value
+    double crd = (double)c;
+    if (crd < 0.0) {
+        crd += boxd;
+        if (crd < 0.0) {
+            const int s = (int)floor((double)c * (1.0 / boxd));
+            c = __fsub_rn(c, __fmul_rn((float)s, box));
+            if (c < 0.f) c = __fadd_rn(c, box);
+        } else {
+            c = (float)crd;
+        }
+    }
+    if (crd >= boxd) {
+        crd -= boxd;
+        if (crd >= boxd) {
+            const int s = (int)floor((double)c * (1.0 / boxd));
+            c = __fsub_rn(c, __fmul_rn((float)s, box));
+            if (c >= box) c = __fsub_rn(c, box);
+        } else {
+            c = (float)crd;
+        }
+    }
+    return c;
+}
+
 static __global__ void rdf_ext_init_kernel(unsigned *ext, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,7 +83,8 @@ static __global__ void rdf_ext_init_kernel(unsigned *ext, int n)
 static __global__ void __launch_bounds__(256)
     rdf_pack_kernel(const float *__restrict__ raw, int64_t frame_stride,
                     float4 *__restrict__ out, int64_t n, int64_t npad, int64_t excl,
-                    int drop_axis, unsigned *__restrict__ ext)
+                    int drop_axis, unsigned *__restrict__ ext,
+                    const FrameBox *__restrict__ boxes)
 {
     __shared__ float stage[3 * 256];
     __shared__ unsigned red[8][6];
@@ -58,6 +92,7 @@ static __global__ void __launch_bounds__(256)
     const int tid = threadIdx.x;
     const float *src = raw + (int64_t)frame * frame_stride;
     float4 *dst = out + (int64_t)frame * npad;
+    const bool prewrap = boxes != nullptr && boxes[frame].prewrap != 0;
     unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
     // 256 particles per step: their 768 floats are read as one contiguous run
     // (coalesced, unlike three stride-3 loads per thread) and regrouped through
@@ -79,6 +114,11 @@ static __global__ void __launch_bounds__(256)
             if (drop_axis == 0) v.x = 0.f;
             if (drop_axis == 1) v.y = 0.f;
             if (drop_axis == 2) v.z = 0.f;
+            if (prewrap) {
+                v.x = ortho_pbc_f32(v.x, boxes[frame].box[0]);
+                v.y = ortho_pbc_f32(v.y, boxes[frame].box[1]);
+                v.z = ortho_pbc_f32(v.z, boxes[frame].box[2]);
+            }
             v.w = __int_as_float((int)(excl > 0 ? i / excl : i));
             const unsigned kx = ext_key(v.x), ky = ext_key(v.y), kz = ext_key(v.z);
             lo[0] = min(lo[0], kx); hi[0] = max(hi[0], kx);

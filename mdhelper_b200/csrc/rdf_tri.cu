@@ -196,7 +196,7 @@ int rdf_accumulate_triclinic_impl(mdh_ctx *c, const float *pos1, int64_t s1, con
         if (int rc = pk.reserve(sizeof(float4) * npad * n_frames)) return rc;
         dim3 grid((unsigned)std::min<int64_t>((npad + 255) / 256, 2048), n_frames);
         rdf_pack_kernel<<<grid, 256, 0, c->stream>>>(dsrc, dstride, pk.as<float4>(), n, npad,
-                                                     g ? R.excl2 : R.excl1, -1, nullptr);
+                                                     g ? R.excl2 : R.excl1, -1, nullptr, nullptr);
         MDH_CUDA(cudaGetLastError());
         tri_wrap_kernel<<<grid, 256, 0, c->stream>>>(pk.as<float4>(), npad, (int)n,
                                                      d_box.as<TriBox>());

@@ -449,6 +449,24 @@ __host__ __device__ inline int mma_consumer_warp(int W, int c)
 }
 
 
+// A consumer warp without work (items are padded to whole blocks): waits for every table
+// stage and releases it at once.
+__device__ __forceinline__ void sq_mma_idle(const MmaParams &P, uint64_t *bar_full,
+                                            uint64_t *bar_empty, int lane)
+{
+    int it = 0;
+    for (int u = blockIdx.y; u < P.n_units; u += gridDim.y) {
+        const int frame = u / P.n_chunks;
+        const int4 chunk = P.chunks[u - frame * P.n_chunks];
+        for (int p0 = chunk.x; p0 < chunk.y; p0 += kPS, ++it) {
+            const int stage = it % kMmaStages, use = it / kMmaStages;
+            mbar_wait(bar_full + stage, use & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + stage);
+        }
+    }
+}
+
 // The consumer loop of one warp item with NT0 / NT1 nz tiles in its two column groups:
 // walks the block's work units, waits for each table stage, runs the sub-chunk update and
 // adds the finished unit to rho (or |rho_chain|^2 to the chain accumulator).
@@ -682,7 +700,11 @@ __global__ void __launch_bounds__(kMmaMaxWarps * 32 + kMmaProducers, 1)
         MDH_MMA_CASE(3, 2) MDH_MMA_CASE(3, 3) MDH_MMA_CASE(4, 1) MDH_MMA_CASE(4, 2)
         MDH_MMA_CASE(4, 3) MDH_MMA_CASE(4, 4)
 #endif
-        default: break;
+        default:
+            // a padding item (no tiles): the warp still takes part in the stage hand-over,
+            // or the producers would wait for its "empty" arrival forever
+            sq_mma_idle(P, bar_full, bar_empty, lane);
+            break;
     }
 #undef MDH_MMA_CASE
 }

@@ -37,6 +37,8 @@ def lib() -> ctypes.CDLL:
         L.mdho_capped_distance_cells.restype = i64
         L.mdho_capped_distance_cells.argtypes = [
             p, i64, p, i64, p, f64, f64, p, p, i64]
+        L.mdho_ortho_pbc.restype = None
+        L.mdho_ortho_pbc.argtypes = [p, i64, p]
         L.mdho_capped_distance_triclinic.restype = i64
         L.mdho_capped_distance_triclinic.argtypes = [
             p, i64, p, i64, p, f64, f64, p, p, i64]

@@ -66,6 +66,49 @@ static inline void inverse_box(const float box[3], float inv[3])
 }
 
 /*
+ * Restated MDAnalysis `_ortho_pbc` (lib/include/calc_distances.h, reached through
+ * apply_PBC from the grid search `FastNS`, lib/nsgrid.pyx) [recall; "parity unpinned"]:
+ * moves coordinates into the primary cell IN FLOAT32 STORAGE.  One box shift is tried
+ * first (computed in double, stored as float); only if that is not enough the number of
+ * shifts is estimated with floor() and applied in float, followed by one corrective
+ * single shift.  A coordinate just below 0 can end up exactly on the box edge (the sum
+ * rounds to box_k), as in MDAnalysis.
+ */
+void mdho_ortho_pbc(float *coords, int64_t n, const float *box)
+{
+    if (!box[0] && !box[1] && !box[2]) return;
+    double inverse_box[3];
+    for (int j = 0; j < 3; ++j)
+        inverse_box[j] = box[j] > FLT_EPSILON ? 1.0 / (double)box[j] : 0.0;
+    for (int64_t i = 0; i < n; ++i)
+        for (int j = 0; j < 3; ++j) {
+            float *c = coords + 3 * i + j;
+            double crd = (double)*c;
+            if (crd < 0.0) {
+                crd += box[j];
+                if (crd < 0.0) {                   /* more than one box away */
+                    int s = (int)floor(*c * inverse_box[j]);
+                    *c -= s * box[j];
+                    if (*c < 0.0) *c += box[j];
+                } else {
+                    *c = (float)crd;
+                }
+            }
+            /* no "else": a single shift up may have produced exactly box_k */
+            if (crd >= box[j]) {
+                crd -= box[j];
+                if (crd >= box[j]) {
+                    int s = (int)floor(*c * inverse_box[j]);
+                    *c -= s * box[j];
+                    if (*c >= box[j]) *c -= box[j];
+                } else {
+                    *c = (float)crd;
+                }
+            }
+        }
+}
+
+/*
  * Brute-force capped distances over rows [i0, i1) of pos1 against all of pos2.
  * Writes up to cap results; returns the number of pairs that satisfy the
  * cut-offs (which may exceed cap: call again with a larger buffer).

@@ -104,6 +104,11 @@ def capped_distance(reference, configuration, max_cutoff, min_cutoff=None,
             method = "nsgrid"
     L = lib()
     if method == "nsgrid":
+        # the grid search works on copies moved into the primary cell in float32
+        # (FastNS -> apply_PBC -> _ortho_pbc); the pair arithmetic is the same afterwards
+        ref, conf = ref.copy(), conf.copy()
+        L.mdho_ortho_pbc(ref.ctypes.data, n1, box.ctypes.data)
+        L.mdho_ortho_pbc(conf.ctypes.data, n2, box.ctypes.data)
         cap = max(1024, int(1.3 * n1 * n2 * 4.19 * max_cutoff ** 3
                             / float(np.prod(box[:3], dtype=np.float64))))
         while True:
@@ -112,9 +117,9 @@ def capped_distance(reference, configuration, max_cutoff, min_cutoff=None,
             m = L.mdho_capped_distance_cells(
                 ref.ctypes.data, n1, conf.ctypes.data, n2, box.ctypes.data,
                 float(max_cutoff), lo, pairs.ctypes.data, dist.ctypes.data, cap)
-            if m == -1:                      # box too small for a grid
-                method = "bruteforce"
-                break
+            if m == -1:                      # fewer than 3 cells per axis: the restated
+                method = "bruteforce"        # 27-cell search does not apply; same pairs and
+                break                        # (wrapped) coordinates through all pairs
             if m < 0:
                 raise MemoryError("oracle cell list allocation failed")
             if m <= cap:

@@ -222,8 +222,9 @@ def test_cells_dense_clusters_take_the_long_list_path():
     q[:600] = (np.array([7.5, 8.5, 9.5]) + 0.5 * rng.standard_normal((600, 3))).astype(np.float32)
     S = _structure()
     for p2, exclusion in [(p, None), (p, (4, 4)), (q, None), (q, (2, 3))]:
-        want = _oracle().radial_histogram(p, p2, 90, (0.0, 3.0), dims, exclusion=exclusion,
-                                          method="bruteforce")
+        # a few cluster particles lie outside [0, L): both sides follow the reference's
+        # method choice (grid search here: coordinates moved into the cell in float32)
+        want = _oracle().radial_histogram(p, p2, 90, (0.0, 3.0), dims, exclusion=exclusion)
         for arith in ("auto", "audit", "off"):
             st = {}
             got = S.radial_histogram(p, p2, 90, (0.0, 3.0), dims, exclusion=exclusion,
@@ -630,3 +631,36 @@ def test_on_disk_style_reader_gives_the_in_memory_results(tmp_path):
                            batch_frames=2).run()
     np.testing.assert_allclose(sa.results.ssf, sb.results.ssf, rtol=1e-12)
     assert disk.trajectory.reads > 0
+
+
+def test_coordinates_outside_the_cell_follow_the_reference_method_choice():
+    """capped_distance's grid search moves the coordinates into the cell in float32 before
+    taking differences, its brute force does not: the GPU
+    path makes the same choice per frame ("auto"), and either can be forced."""
+    rng = np.random.default_rng(123)
+    dims = np.array([24.0, 25.5, 27.0, 90, 90, 90], np.float32)
+    p = ((rng.random((4000, 3)) * 7 - 3) * dims[:3]).astype(np.float32)      # +-3 cells away
+    q = ((rng.random((2500, 3)) * 5 - 2) * dims[:3]).astype(np.float32)
+    p[:3] = [[-1e-9, 3.0, 4.0], [24.0, -25.5, 54.0], [-1e-6, 25.4999, 26.9999]]   # edge cases
+    S, rp = _structure(), _oracle()
+    small, large = (0.0, 3.0), (0.0, 11.5)      # r_max <= 0.3 L: grid search; else brute force
+    for rng_, method in ((small, "nsgrid"), (large, "bruteforce")):
+        for a, b, excl in ((p, p, None), (p, q, (2, 2))):
+            want_auto = rp.radial_histogram(a, b, 60, rng_, dims, exclusion=excl)
+            assert np.array_equal(want_auto, rp.radial_histogram(a, b, 60, rng_, dims,
+                                                                 exclusion=excl, method=method))
+            for mode in ("allpairs", "cells") if rng_ is small else ("allpairs",):
+                for arith in ("auto", "off", "audit"):
+                    st = {}
+                    got = S.radial_histogram(a, b, 60, rng_, dims, exclusion=excl, mode=mode,
+                                             arith=arith, stats=st)
+                    assert np.array_equal(got, want_auto), (rng_, mode, arith)
+                    assert st["audit_violations"] == 0
+    # forcing either semantics
+    brute = rp.radial_histogram(p, q, 60, small, dims, method="bruteforce")
+    grid = rp.radial_histogram(p, q, 60, small, dims, method="nsgrid")
+    assert np.array_equal(S.radial_histogram(p, q, 60, small, dims, wrap="never"), brute)
+    assert np.array_equal(S.radial_histogram(p, q, 60, small, dims, wrap="always"), grid)
+    assert np.array_equal(S.radial_histogram(p, q, 60, small, dims, wrap="never",
+                                             mode="cells"), brute)
+    assert abs(int(brute.sum()) - int(grid.sum())) < 1e-4 * brute.sum() + 10

@@ -252,3 +252,34 @@ def test_triclinic_lattice_translation_invariance():
         return np.sort(dist[:m])
     assert np.array_equal(counts(p), counts(q))
     assert lx > 0 and ly > 0 and lz > 0
+
+
+def test_grid_search_moves_coordinates_into_the_cell_in_float32():
+    """Restated `_ortho_pbc` of MDAnalysis' grid search ("parity unpinned"): the port's
+    nsgrid path equals brute force over the float32-wrapped copies, the identity for
+    coordinates inside the cell, and keeps the known edge cases (-1e-9 -> box)."""
+    import oracle
+    L = oracle.lib()
+    box = np.array([10.0, 11.0, 12.0], np.float32)
+    x = np.array([[-1e-9, 5, 13], [25.5, -30.2, 11.999999], [-0.5, 11.0, 0.0],
+                  [10.0, -11.0, 24.0]], np.float32)
+    y = x.copy()
+    L.mdho_ortho_pbc(y.ctypes.data, len(y), box.ctypes.data)
+    assert y[0, 0] == np.float32(10.0) and y[0, 2] == np.float32(1.0)
+    assert np.all((y >= 0) & (y <= box))
+    d = x.astype(np.float64) - y
+    np.testing.assert_allclose(d - box * np.round(d / box), 0.0, atol=4e-6)    # same point
+    rng = np.random.default_rng(4)
+    dims = np.array([10.0, 11.0, 12.0, 90, 90, 90], np.float32)
+    inside = (rng.random((300, 3)) * box).astype(np.float32)
+    z = inside.copy()
+    L.mdho_ortho_pbc(z.ctypes.data, len(z), box.ctypes.data)
+    assert np.array_equal(z, inside)
+    p = ((rng.random((400, 3)) * 5 - 2) * box).astype(np.float32)
+    w = p.copy()
+    L.mdho_ortho_pbc(w.ctypes.data, len(w), box.ctypes.data)
+    grid = rp.radial_histogram(p, p, 40, (0.0, 3.0), dims, method="nsgrid")
+    assert np.array_equal(grid, rp.radial_histogram(w, w, 40, (0.0, 3.0), dims,
+                                                    method="bruteforce"))
+    # the method rule (SURVEY.md Appendix A item 2): small cut-off -> grid search
+    assert np.array_equal(grid, rp.radial_histogram(p, p, 40, (0.0, 3.0), dims))
