@@ -421,14 +421,17 @@ def run_ours(args):
 
     line = {}
     if not args.strong_only:
+        note("headline: cfg2 pair histogram")
         line = bench_rdf(args, rank, world, local, cpu, dist, torch)
         if not args.no_secondary:
+            note("secondary: cfg4 structure factor")
             sec = bench_sq(args, rank, world, local, cores, dist, torch)
             if rank == 0:
                 line["secondary"] = sec
     if not args.no_strong:
         strong = {}
         for which in [w for w in args.strong.split(",") if w]:
+            note(f"strong scaling pass: {which}")
             res = bench_strong(which, args, rank, world, local, dist, torch)
             if rank == 0:
                 strong[which] = res
@@ -529,6 +532,7 @@ def bench_rdf(args, rank, world, local, cpu, dist, torch):
     del dev
     ctx.close()
 
+    note("headline: end to end through run()")
     # ---- e2e: public class, pinned host memory, H2D + D2H inside the timed region ----
     # weak scaling like `value`: run() shards the frames it is given over the ranks
     # (np.array_split), so every rank exposes a trajectory of world * 2,000 frames whose
@@ -711,6 +715,7 @@ def bench_sq(args, rank, world, local, cores, dist, torch):
     del dev
     ctx.close()
 
+    note("secondary: end to end through run()")
     for s in range(max(1, min(W, 2))):
         sf.run()
     if world > 1:
@@ -908,6 +913,15 @@ def bench_strong(which, args, rank, world, local, dist, torch):
     return out if rank == 0 else None
 
 
+_T0 = time.time()
+
+
+def note(msg: str) -> None:
+    """Progress on stderr (rank 0): which part is running, seconds since start."""
+    if int(os.environ.get("RANK", 0)) == 0:
+        print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def emit(line: dict) -> None:
     """The ONE JSON line of the contract, on the real stdout."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -920,6 +934,10 @@ if __name__ == "__main__":
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     a = parse()
+    # a run that stalls says where: stack traces of all threads on stderr every 5 minutes
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("MDH_BENCH_STALL_S", 300)),
+                                      repeat=True, file=sys.stderr)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -969,6 +969,9 @@ def _isclose_members(unique_q: np.ndarray, wavenumbers: np.ndarray) -> list:
     return out
 
 
+_GROUP_INDEX_CACHE = {}
+
+
 def _grouped_mean(values: np.ndarray, members: list) -> np.ndarray:
     """
     ``np.stack([values[..., m].mean(axis=-1) for m in members], axis=-1)`` -- the
@@ -981,11 +984,21 @@ def _grouped_mean(values: np.ndarray, members: list) -> np.ndarray:
     """
     values = np.asarray(values)
     out = np.empty(values.shape[:-1] + (len(members),), dtype=np.float64)
-    by_size = {}
-    for g, m in enumerate(members):
-        by_size.setdefault(len(m), []).append(g)
-    for size, groups in by_size.items():
-        idx = np.array([members[g] for g in groups], dtype=np.intp).reshape(len(groups), size)
+    # the (groups, index array) pairs per group size depend on `members` only: built once per
+    # membership list (the list object is kept by its analysis instance) and reused by every run
+    plan = _GROUP_INDEX_CACHE.get(id(members))
+    if plan is None or plan[0] is not members:
+        by_size = {}
+        for g, m in enumerate(members):
+            by_size.setdefault(len(m), []).append(g)
+        plan = (members, [(np.array(groups, dtype=np.intp),
+                           np.array([members[g] for g in groups],
+                                    dtype=np.intp).reshape(len(groups), size))
+                          for size, groups in by_size.items()])
+        if len(_GROUP_INDEX_CACHE) > 64:
+            _GROUP_INDEX_CACHE.clear()
+        _GROUP_INDEX_CACHE[id(members)] = plan
+    for groups, idx in plan[1]:
         out[..., groups] = values[..., idx].mean(axis=-1)
     return out
 

@@ -1208,10 +1208,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
         for (int grp = 0; grp < n_groups; ++grp) {
             const float *raw = (grp ? raw2 : raw1) + (int64_t)g0 * (grp ? stride2 : stride1);
             const int n = (int)(grp ? R.n2 : R.n1);
-            // ~4 blocks per SM in all: a block loops over many 256-particle steps, so that
-            // its fixed cost (extents reduction, launch) is paid once per ~30 steps
-            dim3 grid((unsigned)std::max(1, std::min((n + 255) / 256,
-                                                     (4 * c->sm_count + ng - 1) / ng)), ng);
+            dim3 grid((unsigned)std::min((n + 255) / 256, 4096), ng);
             cells_bin_kernel<<<grid, 256, 0, c->stream>>>(
                 raw, grp ? stride2 : stride1, n, gg, d_cnt + (size_t)grp * G * cstride, cstride,
                 R.cell[grp ? 7 : 3].as<int2>(), use_filter ? d_ext + (size_t)grp * G * 6 : nullptr,
@@ -1245,10 +1242,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
         for (int grp = 0; grp < n_groups; ++grp) {
             const float *raw = (grp ? raw2 : raw1) + (int64_t)g0 * (grp ? stride2 : stride1);
             const int n = (int)(grp ? R.n2 : R.n1);
-            // ~4 blocks per SM in all: a block loops over many 256-particle steps, so that
-            // its fixed cost (extents reduction, launch) is paid once per ~30 steps
-            dim3 grid((unsigned)std::max(1, std::min((n + 255) / 256,
-                                                     (4 * c->sm_count + ng - 1) / ng)), ng);
+            dim3 grid((unsigned)std::min((n + 255) / 256, 4096), ng);
             cells_scatter_kernel<<<grid, 256, 0, c->stream>>>(
                 raw, grp ? stride2 : stride1, n, grp ? R.excl2 : R.excl1,
                 d_start + (size_t)grp * G * cstride, cstride, R.cell[grp ? 7 : 3].as<int2>(),
