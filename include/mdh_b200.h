@@ -115,8 +115,11 @@ typedef struct mdh_ctx mdh_ctx;
 int mdh_abi_version(void);
 const char *mdh_last_error(void);
 
-/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream),
- * or NULL to let the context create its own non-blocking stream. */
+/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream), or NULL to
+ * let the context create its own non-blocking stream.  NOTE: the default stream of a
+ * framework has the handle 0 == NULL; pass cudaStreamLegacy ((cudaStream_t)0x1) or
+ * cudaStreamPerThread ((cudaStream_t)0x2) to name it, as the Python layer does -- work on
+ * a private stream is not ordered against the framework's events and collectives. */
 int mdh_ctx_create(int device, void *cuda_stream, mdh_ctx **out);
 int mdh_ctx_destroy(mdh_ctx *ctx);
 int mdh_sync(mdh_ctx *ctx);

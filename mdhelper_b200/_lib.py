@@ -150,6 +150,12 @@ class Context:
         self.device = int(device)
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
+        if not stream:
+            # torch's default stream has the handle 0, which the C ABI reads as "create a
+            # stream of your own" -- work queued there would not be ordered against torch
+            # events, uploads on side streams or NCCL.  cudaStreamLegacy (1) names the
+            # default stream explicitly.
+            stream = 1
         h = _p()
         check(self._lib.mdh_ctx_create(self.device, _p(stream), ctypes.byref(h)))
         self._h = h

@@ -2,12 +2,20 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
+
+bool mdh_trace_on()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("MDH_TRACE"); on = (e && *e && *e != '0') ? 1 : 0; }
+    return on == 1;
+}
 
 void mdh_set_error(const char *fmt, ...)
 {

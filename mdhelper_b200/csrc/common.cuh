@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <algorithm>
 #include <string>
@@ -15,6 +16,12 @@
 #endif
 
 void mdh_set_error(const char *fmt, ...);
+// MDH_TRACE=1: host-side progress on stderr (where a call blocks)
+bool mdh_trace_on();
+#define MDH_TRACE(...)                                                          \
+    do {                                                                        \
+        if (mdh_trace_on()) { fprintf(stderr, "[mdh] " __VA_ARGS__); fputc('\n', stderr); } \
+    } while (0)
 
 #define MDH_CUDA(call)                                                          \
     do {                                                                        \

@@ -431,8 +431,11 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
         R.h_boxes_cap = std::max<size_t>(256, (size_t)n_frames);
         MDH_CUDA(cudaMallocHost(&R.h_boxes_pinned, sizeof(FrameBox) * R.h_boxes_cap));
     }
+    MDH_TRACE("rdf_accumulate: %d frames, location %d; waiting for the previous box upload",
+              n_frames, location);
     if (!R.ev_boxes) MDH_CUDA(cudaEventCreateWithFlags(&R.ev_boxes, cudaEventDisableTiming));
     else MDH_CUDA(cudaEventSynchronize(R.ev_boxes));
+    MDH_TRACE("rdf_accumulate: boxes");
     memcpy(R.h_boxes_pinned, R.h_boxes.data(), sizeof(FrameBox) * n_frames);
     MDH_CUDA(cudaMemcpyAsync(R.boxes.p, R.h_boxes_pinned, sizeof(FrameBox) * n_frames,
                              cudaMemcpyHostToDevice, c->stream));
@@ -458,7 +461,9 @@ int rdf_accumulate_impl(mdh_ctx *c, const float *pos1, int64_t s1, const float *
         }
         return MDH_OK;
     }
-    return rdf_accumulate_piece(c, pos1, s1, pos2, s2, location, 0, n_frames, mode);
+    const int rc = rdf_accumulate_piece(c, pos1, s1, pos2, s2, location, 0, n_frames, mode);
+    MDH_TRACE("rdf_accumulate: queued, rc %d", rc);
+    return rc;
 }
 
 // One piece of an accumulate call: frames [f0, f0 + n_frames) of the batch whose boxes

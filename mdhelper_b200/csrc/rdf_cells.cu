@@ -37,8 +37,9 @@
 // the fixed-point bin coordinate, the uncertainty window and the histogram update are
 // those of rdf_filter.cu (same device functions -> same bits); uncertain pairs go to a
 // per-warp list that is re-evaluated with the fp64 arithmetic as soon as the cell is done,
-// from the same shared-memory buffer.  Cells whose candidate list does not fit the buffer
-// (dense clusters) take a slower path that reads the runs from global memory.
+// from the same shared-memory buffer.  A candidate list that does not fit the buffer (a
+// dense cluster) is copied and computed in segments; a cell with more particles than that
+// is handed to the fp64 kernel, whose thread-per-particle layout spreads it over the device.
 
 #include <stdio.h>
 
@@ -282,7 +283,9 @@ struct CellParams {
     unsigned long long *evals;
     int half;                     // same group: half stencil, weight 2
     const FrameFilter *filt;      // != nullptr: frames with wlim != 0 were done by the
-                                  // fp32-filter kernel and are skipped here
+                                  // fp32-filter kernel and are skipped here -- except the
+    const int *cellflag;          // cells it flagged ([F][cstride], != 0: too crowded for
+    const int *nflag;             // one warp) -- nflag[F]: how many per frame
 };
 
 template <int HIST>
@@ -301,8 +304,14 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
-    // frames the fp32-filter kernel has taken are not done again
-    if (P.filt != nullptr && P.filt[frame].wlim != 0u) return;
+    // frames the fp32-filter kernel has taken are not done again, apart from the cells it
+    // handed over (a cluster far denser than the rest: one thread per particle spreads
+    // that work over the device, one warp per cell would not)
+    bool flagged_only = false;
+    if (P.filt != nullptr && P.filt[frame].wlim != 0u) {
+        if (P.nflag == nullptr || P.nflag[frame] == 0) return;
+        flagged_only = true;
+    }
     const int n_bins = P.n_bins;
     const int n_words = priv_words(n_bins);
     for (int k = tid; k <= n_bins; k += kThreads) sT[k] = P.thr[k];
@@ -326,11 +335,12 @@ __global__ void __launch_bounds__(kThreads, 2) rdf_cells_kernel(const CellParams
     const int *start = P.start2 + (int64_t)frame * P.cstride;
 
     const int i = blockIdx.x * kThreads + tid;
-    const bool valid = i < P.n1;
+    bool valid = i < P.n1;
     const float4 pi = s1[min(i, P.n1 - 1)];
     const int gi = __float_as_int(pi.w);
     int cx, cy, cz;
-    cell_id(pi.x, pi.y, pi.z, g, cx, cy, cz);
+    const int my_cell = cell_id(pi.x, pi.y, pi.z, g, cx, cy, cz);
+    if (flagged_only) valid = valid && P.cellflag[(int64_t)frame * P.cstride + my_cell] != 0;
 
     int steps = 0;                       // warp-uniform: increments since the last flush
     unsigned long long my_evals = 0;
@@ -473,6 +483,7 @@ struct CellPairParams {
     int fast_bins;
     unsigned long long *counts, *evals, *fstats;
     unsigned *work;               // work-item counter (zero at launch)
+    int *cellflag, *nflag;        // cells handed over to the fp64 kernel ([F][cstride], [F])
     int n_frames;
     int max_ncell;                // largest cell count of the frames of this launch
     int chunk_cells;              // cells per work item
@@ -557,37 +568,6 @@ __device__ __noinline__ void cp_fix(const CellPairParams &P, int frame, const fl
             if ((word >> fc.sb) == (unsigned)slot) continue;
             red_shared(hist32 + 4u * word, 0u - weight);
             red_shared(hist32 + 4u * ((unsigned)slot << fc.sb), weight);
-        }
-    }
-}
-
-// A cell whose candidate list does not fit the per-warp buffer (a cluster far denser than
-// the average): every pair through the reference's fp64 arithmetic, straight from global
-// memory, one particle per lane.  wrng: the runs planned by issue().
-template <bool HALF, bool EXCL>
-__device__ __noinline__ void cp_long_cell(const CellPairParams &P, int frame, const int2 *wrng,
-                                          const double *sT, unsigned hist32, int sb, int lane)
-{
-    const FrameBox fb = P.boxes[frame];
-    const float4 *s1 = P.s1 + (int64_t)frame * P.n1;
-    const float4 *s2 = P.s2 + (int64_t)frame * P.n2;
-    const int2 own = wrng[0];
-    for (int i0 = 0; i0 < own.y; i0 += 32) {
-        const int i = i0 + lane;
-        const bool valid = i < own.y;
-        const float4 a = s1[own.x + min(i, own.y - 1)];
-        for (int r = HALF ? 0 : 1; r < kCpRanges; ++r) {
-            const int2 rg = wrng[r];
-            const unsigned w = (HALF && r > 0) ? 2u : 1u;
-            for (int j = 0; j < rg.y; ++j) {
-                const float4 pj = __ldg(s2 + rg.x + j);
-                if (!valid || (HALF && r == 0 && j == i)) continue;
-                if (EXCL && __float_as_int(a.w) == __float_as_int(pj.w)) continue;
-                const double d2 = pair_d2(a.x, a.y, a.z, pj, fb);
-                const int slot = slot_search(d2, sT, P.n_bins);
-                if ((unsigned)(slot - 1) < (unsigned)P.n_bins)
-                    red_shared(hist32 + 4u * ((unsigned)slot << sb), w);
-            }
         }
     }
 }
@@ -707,7 +687,7 @@ __global__ void __launch_bounds__(kCpThreads, MDH_CP_BLOCKS)
         // Stage 2: lays the runs out in buffer `slot` and starts their copy.  Returns
         // (warp-uniform) n_i, total and the mode: 0 nothing to do, 1 buffered (copy in
         // flight), 2 list longer than the buffer (copied and computed in segments), 3 cell
-        // too large for that as well (fp64 fallback).
+        // too crowded for that as well (handed to the fp64 kernel).
         auto launch = [&](int slot, int b, int e, int &n_i, int &total) -> int {
             const int len = e - b;
             int pre = len;
@@ -721,9 +701,10 @@ __global__ void __launch_bounds__(kCpThreads, MDH_CP_BLOCKS)
             n_i = __shfl_sync(0xffffffffu, len, 0);
             if (n_i == 0 || (!HALF && total == n_i)) return 0;
             if (total > cap) {
-                wrng[slot * 32 + lane] = make_int2(b, len);   // the long-list paths walk the runs
+                if (n_i > cap - 64) return 3;
+                wrng[slot * 32 + lane] = make_int2(b, len);   // the segments walk the runs
                 __syncwarp();
-                return n_i <= cap - 64 ? 2 : 3;
+                return 2;
             }
             const unsigned bar = bar32 + 8u * slot;
             if (lane == 0) cp_mbar_expect(bar, (unsigned)total * 16u);
@@ -1009,9 +990,14 @@ __global__ void __launch_bounds__(kCpThreads, MDH_CP_BLOCKS)
                     if (mode_c == 1 || r >= kCpRanges) break;
                 }
             } else if (mode_c == 3) {
-                cp_long_cell<HALF, EXCL>(P, frame, wrng + slot * 32, sT, hist32, fc.sb, lane);
+                // more particles in one cell than a warp should take on: the fp64 kernel
+                // (one thread per particle) does this cell's pairs
+                if (lane == 0) {
+                    P.cellflag[(int64_t)frame * P.cstride + cell] = 1;
+                    atomicAdd(&P.nflag[frame], 1);
+                }
             }
-            if (mode_c != 0 && lane == 0) {
+            if (mode_c != 0 && mode_c != 3 && lane == 0) {
                 my_evals += (unsigned long long)ni_c *
                             (unsigned long long)(HALF ? tot_c : tot_c - ni_c);
                 if (count_self)
@@ -1143,6 +1129,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
         g.ncell = g.nc[0] * g.nc[1] * g.nc[2];
         ncell_max = std::max(ncell_max, g.ncell);
     }
+    MDH_TRACE("cells: %d frames, %d cells", n_frames, ncell_max);
     const int cstride = ncell_max + 1;
     DevBuf &d_grids = R.cell[0];
     if (int rc = d_grids.reserve(sizeof(CellGrid) * n_frames)) return rc;
@@ -1151,6 +1138,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
     MDH_CUDA(cudaMemcpyAsync(d_grids.p, grids.data(), sizeof(CellGrid) * n_frames,
                              cudaMemcpyHostToDevice, c->stream));
 
+    MDH_TRACE("cells: grids uploaded");
     // frames per group: the sorted copies, the (cell, rank) words and the raw floats of a
     // group should stay in L2 between the passes (R.cells_ws_mb, default 48 MB)
     const int n_groups = R.same ? 1 : 2;
@@ -1160,7 +1148,9 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
 
     const size_t cnt_words = (size_t)2 * G * cstride;
     const size_t ext_off = cnt_words, work_off = ext_off + (size_t)2 * G * 6;
-    if (int rc = R.cell[1].reserve(sizeof(int) * (work_off + 4))) return rc;
+    const size_t nflag_off = work_off + 4, flag_off = nflag_off + G;
+    const size_t reset_words = flag_off + (size_t)G * cstride;
+    if (int rc = R.cell[1].reserve(sizeof(int) * reset_words)) return rc;
     if (int rc = R.cell[2].reserve(sizeof(int) * cnt_words)) return rc;
     if (int rc = R.cell[3].reserve(sizeof(int2) * (size_t)R.n1 * G)) return rc;
     if (int rc = R.cell[4].reserve(sizeof(float4) * (size_t)R.n1 * G)) return rc;
@@ -1171,9 +1161,11 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
     if (use_filter)
         if (int rc = R.filt.reserve(sizeof(FrameFilter) * G)) return rc;
 
+    MDH_TRACE("cells: buffers reserved, groups of %d", G);
     int *d_cnt = R.cell[1].as<int>();
     unsigned *d_ext = R.cell[1].as<unsigned>() + ext_off;
     unsigned *d_work = R.cell[1].as<unsigned>() + work_off;
+    int *d_nflag = R.cell[1].as<int>() + nflag_off, *d_cellflag = R.cell[1].as<int>() + flag_off;
     int *d_start = R.cell[2].as<int>();
 
     // candidates per cell the buffers are sized for: mean + 6 sigma (Poisson) + slack
@@ -1203,7 +1195,7 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
         const int ng = std::min(G, n_frames - g0);
         mark();
         // counters, extents and the work counter: one contiguous region, one zero fill
-        MDH_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (work_off + 4), c->stream));
+        MDH_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * reset_words, c->stream));
         const CellGrid *gg = d_grids.as<CellGrid>() + g0;
         for (int grp = 0; grp < n_groups; ++grp) {
             const float *raw = (grp ? raw2 : raw1) + (int64_t)g0 * (grp ? stride2 : stride1);
@@ -1274,6 +1266,8 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
             Q.evals = R.cell[9].as<unsigned long long>();
             Q.fstats = R.fstats.as<unsigned long long>();
             Q.work = d_work;
+            Q.cellflag = d_cellflag;
+            Q.nflag = d_nflag;
             Q.n_frames = ng;
             Q.max_ncell = ncell_max;
             Q.chunk_cells = R.cells_chunk;
@@ -1299,6 +1293,8 @@ int rdf_cells_accumulate(mdh_ctx *c, const float *raw1, int64_t stride1, const f
         P.evals = R.cell[9].as<unsigned long long>();
         P.half = R.same;
         P.filt = use_filter ? R.filt.as<FrameFilter>() : nullptr;
+        P.cellflag = d_cellflag;
+        P.nflag = d_nflag;
         dim3 grid((unsigned)((R.n1 + kThreads - 1) / kThreads), (unsigned)ng);
         int rc;
         if (R.hist == MDH_HIST_LANE_PRIVATE) {

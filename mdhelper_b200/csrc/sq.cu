@@ -1375,6 +1375,7 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
     MDH_REQUIRE(stride >= 3 * S.n_total, MDH_EINVAL, "sq: frame_stride < 3*n_total");
     MDH_REQUIRE(location == MDH_HOST || location == MDH_DEVICE, MDH_EINVAL,
                 "sq: invalid location");
+    MDH_TRACE("sq_accumulate: %d frames, location %d", n_frames, location);
     // host input in pieces: the copy of one piece (copy stream) overlaps the kernels of
     // the previous one (compute stream); the particle chunks are laid out once, for the
     // whole call
