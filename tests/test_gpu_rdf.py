@@ -664,3 +664,39 @@ def test_coordinates_outside_the_cell_follow_the_reference_method_choice():
     assert np.array_equal(S.radial_histogram(p, q, 60, small, dims, wrap="never",
                                              mode="cells"), brute)
     assert abs(int(brute.sum()) - int(grid.sum())) < 1e-4 * brute.sum() + 10
+
+
+def test_filter_bound_fuzz_in_audit_mode():
+    """Seeded fuzz of the fp32 filter's error bound: random (non-cubic) boxes, ranges with
+    and without a lower cut-off, bin counts, coordinate offsets of up to a few cells and group
+    sizes -- all-pairs and cell-list kernels, same group and two groups.  In audit mode
+    every pair is ALSO evaluated with the reference's fp64 arithmetic on the device: no
+    pair the filter calls certain may disagree, and the counts equal the oracle's."""
+    rng = np.random.default_rng(20260618)
+    S, rp = _structure(), _oracle()
+    n_checked = 0
+    for trial in range(24):
+        box = rng.uniform(6.0, 40.0, 3).astype(np.float32)
+        dims = np.concatenate([box, [90, 90, 90]]).astype(np.float32)
+        r_hi = float(np.float32(rng.uniform(0.08, 0.5) * box.min()))
+        r_lo = float(np.float32(rng.choice([0.0, 0.0, rng.uniform(0.05, 0.5) * r_hi])))
+        n_bins = int(rng.choice([1, 7, 64, 201, 500, 1500]))
+        n1, n2 = int(rng.integers(40, 2500)), int(rng.integers(40, 2500))
+        spread = rng.choice([1.0, 1.0, 3.0, 9.0])           # coordinates up to +-4 cells away
+        shift = (rng.random(3) - 0.5) * (spread - 1.0)
+        p1 = ((rng.random((n1, 3)) * spread - shift * 0 - (spread - 1) / 2) * box).astype(np.float32)
+        same = bool(rng.integers(0, 2))
+        p2 = p1 if same else ((rng.random((n2, 3)) * spread - (spread - 1) / 2) * box
+                              ).astype(np.float32)
+        excl = None if rng.random() < 0.6 else ((3, 3) if same else (2, 5))
+        want = rp.radial_histogram(p1, p2, n_bins, (r_lo, r_hi), dims, exclusion=excl)
+        modes = ["allpairs"] + (["cells"] if box.min() / (r_hi * 1.00001) >= 3.0 else [])
+        for mode in modes:
+            st = {}
+            got = S.radial_histogram(p1, p2, n_bins, (r_lo, r_hi), dims, exclusion=excl,
+                                     mode=mode, arith="audit", stats=st)
+            info = (trial, mode, box.tolist(), r_lo, r_hi, n_bins, n1, n2, same, excl, st)
+            assert st["audit_violations"] == 0, info
+            assert np.array_equal(got, want), info
+            n_checked += st["eligible"]
+    assert n_checked >= 20          # the filter really ran for most configurations

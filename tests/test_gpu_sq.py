@@ -445,3 +445,30 @@ def test_structure_factor_of_a_triclinic_universe_uses_the_edge_lengths():
     so = _S().StructureFactor([uo.atoms], n_points=6, verbose=False).run()
     assert np.array_equal(st.results.wavenumbers, so.results.wavenumbers)
     np.testing.assert_allclose(st.results.ssf, so.results.ssf, rtol=1e-12)
+
+
+def test_grids_too_large_for_shared_memory_tables_use_the_general_kernel():
+    """n_points = 96: the phase-factor tables of the lattice kernels (3 KB x n_points per
+    sub-chunk) exceed the 227 KB of shared memory; AUTO then takes the general kernel
+    (the reference has no such limit), an explicit lattice kernel is refused."""
+    from mdhelper_b200 import _lib
+    from mdhelper_b200.universe import SyntheticUniverse
+    rng = np.random.default_rng(5)
+    L = np.float32(9.0)
+    pos = (rng.random((1, 60, 3)) * float(L)).astype(np.float32)
+    u = SyntheticUniverse(pos, np.array([L, L, L, 90, 90, 90], np.float32))
+    q_cut = 2 * np.pi * 14.5 / float(L)
+    # a small sphere of a 96-point grid is fine (tables sized by the largest index used)
+    s = _S().StructureFactor([u.atoms], n_points=96, q_max=q_cut, verbose=False).run()
+    assert s._ctx.sq_kernel() in ("lattice_dmma", "lattice_fp64")
+    # a thin shell reaching index 95 along each axis needs tables of 96 entries per axis
+    idx = np.array([[95, 0, 0], [0, 95, 0], [0, 0, 95], [95, 95, 95], [1, 2, 3], [0, 0, 0]])
+    wv = 2 * np.pi * idx / float(L)
+    s = _S().StructureFactor([u.atoms], wavevectors=wv, unique=False, sort=False,
+                             verbose=False).run()
+    assert s._ctx.sq_kernel() == "general_fp64"
+    want = np.abs(np.exp(1j * pos[0].astype(np.float64) @ wv.T).sum(axis=0)) ** 2 / 60
+    np.testing.assert_allclose(s.results.ssf[0], want, rtol=1e-9, atol=1e-9)
+    with pytest.raises(ValueError):
+        _S().StructureFactor([u.atoms], wavevectors=wv, unique=False, sort=False,
+                             verbose=False, kernel="lattice_fp64").run()
