@@ -228,6 +228,17 @@ int mdh_sq_configure(mdh_ctx *ctx, int64_t n_total, int n_groups,
 int mdh_sq_accumulate(mdh_ctx *ctx, const float *pos, int64_t frame_stride, int location,
                       int n_frames);
 
+/*
+ * The same for float64 coordinates (frame_stride in doubles): what the reference sums over
+ * when its position buffer is float64 -- centres of mass of residues / segments and
+ * unwrapped polymer coordinates (structure.py:1468-1486, polymer.py:1076-1086).  The
+ * kernels read every coordinate as float32 + float32 remainder and add the two in fp64
+ * (relative error 2^-48), so rounding such positions to float32 (phase error
+ * ~ |q||r| 6e-8) is avoided.
+ */
+int mdh_sq_accumulate_f64(mdh_ctx *ctx, const double *pos, int64_t frame_stride, int location,
+                          int n_frames);
+
 int mdh_sq_fetch(mdh_ctx *ctx, double *ssf /* [n_pairs][n_q] host */);
 /* The MDH_SQ_* kernel the current configuration runs (after AUTO / fallback). */
 int mdh_sq_kernel(mdh_ctx *ctx, int *mode);
@@ -266,6 +277,11 @@ int mdh_com_configure(mdh_ctx *ctx, int slot, int64_t n_atoms, int64_t n_entitie
                       const double *masses /* [n_atoms] host */);
 int mdh_com_reduce(mdh_ctx *ctx, int slot, const float *pos, int64_t frame_stride,
                    int location, int n_frames, float *out_device, int64_t out_frame_stride);
+/* The same without the final rounding to float32 (out_frame_stride in doubles): input of
+ * mdh_sq_accumulate_f64. */
+int mdh_com_reduce_f64(mdh_ctx *ctx, int slot, const float *pos, int64_t frame_stride,
+                       int location, int n_frames, double *out_device,
+                       int64_t out_frame_stride);
 
 /*
  * Single-chain structure factor (SingleChainStructureFactor._single_frame,
@@ -296,6 +312,12 @@ int mdh_sq_configure_chains(mdh_ctx *ctx, int64_t n_chains, int64_t n_monomers);
 int mdh_isf_configure(mdh_ctx *ctx, int n_lags, int incoherent, int64_t max_frames);
 int mdh_isf_accumulate(mdh_ctx *ctx, const float *pos, int64_t frame_stride, int location,
                        int n_frames);
+/* float64 coordinates (centres of mass; structure.py:1927-1957 keeps them in a float64
+ * buffer): positions and displacements are formed in fp64 and reach the kernels as
+ * float32 + float32 remainder, as in mdh_sq_accumulate_f64.  One run is all float32 or
+ * all float64 (MDH_ESTATE otherwise). */
+int mdh_isf_accumulate_f64(mdh_ctx *ctx, const double *pos, int64_t frame_stride,
+                           int location, int n_frames);
 /* iisf may be NULL.  Synchronises. */
 int mdh_isf_fetch(mdh_ctx *ctx, double *cisf /* [n_lags][n_pairs][n_q] */,
                   double *iisf /* [n_lags][n_rho][n_q] or NULL */);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "mdh_rdf_filter_stats": (_i32, [_p, _p]),
     "mdh_sq_configure": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i32, _p, _i32]),
     "mdh_sq_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
+    "mdh_sq_accumulate_f64": (_i32, [_p, _p, _i64, _i32, _i32]),
     "mdh_sq_fetch": (_i32, [_p, _p]),
     "mdh_sq_kernel": (_i32, [_p, _p]),
     "mdh_sq_tiling": (_i32, [_p, _p]),
@@ -65,9 +66,11 @@ SIGNATURES = {
     "mdh_sq_fetch_rho": (_i32, [_p, _p]),
     "mdh_com_configure": (_i32, [_p, _i32, _i64, _i64, _p, _p]),
     "mdh_com_reduce": (_i32, [_p, _i32, _p, _i64, _i32, _i32, _p, _i64]),
+    "mdh_com_reduce_f64": (_i32, [_p, _i32, _p, _i64, _i32, _i32, _p, _i64]),
     "mdh_sq_configure_chains": (_i32, [_p, _i64, _i64]),
     "mdh_isf_configure": (_i32, [_p, _i32, _i32, _i64]),
     "mdh_isf_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
+    "mdh_isf_accumulate_f64": (_i32, [_p, _p, _i64, _i32, _i32]),
     "mdh_isf_fetch": (_i32, [_p, _p, _p]),
 }
 
@@ -283,8 +286,11 @@ class Context:
         self._sq_shape = (len(pr), len(wv))
         self._sq_nrho = 1 if (pr < 0).any() else len(goff) - 1
 
-    def sq_accumulate(self, pos, stride, n_frames, *, device=False, keepalive=None):
-        check(self._lib.mdh_sq_accumulate(
+    def sq_accumulate(self, pos, stride, n_frames, *, device=False, keepalive=None,
+                      f64=False):
+        """``f64``: ``pos`` holds float64 coordinates (``stride`` in doubles)."""
+        fn = self._lib.mdh_sq_accumulate_f64 if f64 else self._lib.mdh_sq_accumulate
+        check(fn(
             self._h, _ptr(pos), int(stride),
             MDH_DEVICE if device else MDH_HOST, int(n_frames)))
         if keepalive is not None:
@@ -320,10 +326,12 @@ class Context:
                                           st.ctypes.data, m.ctypes.data))
 
     def com_reduce(self, slot: int, pos, stride, n_frames, out_device, out_stride, *,
-                   device=False):
-        check(self._lib.mdh_com_reduce(self._h, int(slot), _ptr(pos), int(stride),
-                                       MDH_DEVICE if device else MDH_HOST, int(n_frames),
-                                       _ptr(out_device), int(out_stride)))
+                   device=False, f64=False):
+        """``f64``: ``out_device`` is a float64 buffer (``out_stride`` in doubles)."""
+        fn = self._lib.mdh_com_reduce_f64 if f64 else self._lib.mdh_com_reduce
+        check(fn(self._h, int(slot), _ptr(pos), int(stride),
+                 MDH_DEVICE if device else MDH_HOST, int(n_frames),
+                 _ptr(out_device), int(out_stride)))
 
     def sq_configure_chains(self, n_chains: int, n_monomers: int):
         """Single-chain mode: ``sq_accumulate`` adds sum over chains of |rho_chain|^2."""
@@ -336,8 +344,10 @@ class Context:
                                           int(max_frames)))
         self._isf = (int(n_lags), bool(incoherent))
 
-    def isf_accumulate(self, pos, stride, n_frames, *, device=False, keepalive=None):
-        check(self._lib.mdh_isf_accumulate(
+    def isf_accumulate(self, pos, stride, n_frames, *, device=False, keepalive=None,
+                       f64=False):
+        fn = self._lib.mdh_isf_accumulate_f64 if f64 else self._lib.mdh_isf_accumulate
+        check(fn(
             self._h, _ptr(pos), int(stride),
             MDH_DEVICE if device else MDH_HOST, int(n_frames)))
         if keepalive is not None:

@@ -150,12 +150,13 @@ def _runs_in_ring(frames: np.ndarray, step: int, period: int, max_frames: int):
 class Batch:
     """A run of frames ready for the C ABI."""
 
-    __slots__ = ("n_frames", "ptrs", "strides", "dims", "keepalive", "event")
+    __slots__ = ("n_frames", "ptrs", "strides", "dims", "keepalive", "event", "f64")
 
-    def __init__(self, n_frames, ptrs, strides, dims, keepalive):
+    def __init__(self, n_frames, ptrs, strides, dims, keepalive, f64=False):
         self.n_frames = n_frames
         self.ptrs = ptrs            # host addresses, one per index set
-        self.strides = strides      # floats between consecutive frames
+        self.strides = strides      # elements between consecutive frames
+        self.f64 = f64              # float64 coordinates (float32 otherwise)
         self.dims = dims            # float32 [n_frames, 6]
         self.keepalive = keepalive
         self.event = None
@@ -177,8 +178,11 @@ class FrameFeeder:
     """
 
     def __init__(self, trajectory, index_sets, frames, batch_frames,
-                 positions_fn=None):
+                 positions_fn=None, dtype=np.float32):
         self.trajectory = trajectory
+        # float64 staging: for positions_fn results the reference keeps in float64
+        # (centres of mass, unwrapped coordinates in the Fourier sums)
+        self.dtype = np.dtype(dtype)
         self.index_sets = [np.asarray(ix, dtype=np.intp) for ix in index_sets]
         self.frames = np.asarray(frames, dtype=np.intp)
         self.batch_frames = max(1, int(batch_frames))
@@ -236,7 +240,7 @@ class FrameFeeder:
         sizes = [ix.size for ix in self.index_sets]
         if self._staging is None:
             self._staging = [
-                [pinned_empty((self.batch_frames, n, 3)) for n in sizes]
+                [pinned_empty((self.batch_frames, n, 3), self.dtype) for n in sizes]
                 for _ in range(2)
             ]
         self._events = [None, None]
@@ -258,7 +262,8 @@ class FrameFeeder:
                     for (arr, _), ix in zip(bufs, self.index_sets):
                         np.take(pos, ix, axis=0, out=arr[b])
             batch = Batch(len(fr), [arr.ctypes.data for arr, _ in bufs],
-                          [n * 3 for n in sizes], dims, bufs)
+                          [n * 3 for n in sizes], dims, bufs,
+                          f64=self.dtype == np.float64)
             yield batch
             self._events[which] = batch.event
             which ^= 1
@@ -346,6 +351,11 @@ class GpuAnalysisBase:
     def _consume(self, batch, device: bool = False) -> None:
         raise NotImplementedError
 
+    def _staging_dtype(self, positions_fn):
+        """dtype of the host staging buffers ``_consume`` is handed (float32 unless the
+        analysis sums over float64 ``positions_fn`` results)."""
+        return np.float32
+
     def _finish(self) -> None:
         raise NotImplementedError
 
@@ -359,7 +369,8 @@ class GpuAnalysisBase:
             self._empty()
             return
         feeder = FrameFeeder(self._trajectory, sets, frames,
-                             self._default_batch(bytes_per_frame), positions_fn)
+                             self._default_batch(bytes_per_frame), positions_fn,
+                             dtype=self._staging_dtype(positions_fn))
         for batch in feeder:
             self._consume(batch)
         self._finish()
@@ -482,7 +493,8 @@ class CombinedAnalysis:
                     a._empty()
                     continue
                 for batch in FrameFeeder(self._trajectory, sets, local,
-                                         a._default_batch(bpf), fn):
+                                         a._default_batch(bpf), fn,
+                                         dtype=a._staging_dtype(fn)):
                     a._consume(batch)
                 a._finish()
         else:

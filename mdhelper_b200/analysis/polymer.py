@@ -168,7 +168,13 @@ class SingleChainStructureFactor(GpuAnalysisBase):
                     p = pos.reshape(self._n_chains, self._n_monomers, -1, 3)
                     pos = (np.einsum("...a,...ad->...d", m, p)
                            / m.sum(axis=-1, keepdims=True)).reshape(-1, 3)
-            pos = np.asarray(pos, dtype=np.float64)
+            # atoms: the reference unwraps the reader's float32 array in place
+            # (polymer.py:1079, 1091-1093 -- the unwrapped coordinates are rounded to
+            # float32); centres of mass are float64 and stay so
+            if self._grouping == "residues":
+                pos = np.asarray(pos, dtype=np.float64)
+            else:
+                pos = np.array(pos, dtype=np.float32)
             if self._unwrap:
                 if "old" not in state:          # the first analysed frame is the anchor
                     state["old"] = pos.copy()
@@ -179,9 +185,14 @@ class SingleChainStructureFactor(GpuAnalysisBase):
             return [pos]
         return [np.arange(n)], positions_fn, 12 * n
 
+    def _staging_dtype(self, positions_fn):
+        # centres of mass (unwrapped or not) stay float64 up to the trigonometric sums
+        # (polymer.py:1076-1099); atom coordinates are float32 in the reference too
+        return np.float64 if self._grouping == "residues" else np.float32
+
     def _consume(self, batch, device: bool = False) -> None:
         self._ctx.sq_accumulate(batch.ptrs[0], batch.strides[0], batch.n_frames,
-                                device=device, keepalive=batch.keepalive)
+                                device=device, keepalive=batch.keepalive, f64=batch.f64)
         _record(batch)
 
     def _finish(self) -> None:

@@ -728,22 +728,29 @@ class StructureFactor(GpuAnalysisBase):
                 ])]
         return sets, positions_fn, 12 * int(self._N)
 
+    def _staging_dtype(self, positions_fn):
+        # centres of mass found on the host stay float64 up to the Fourier sums, as in
+        # the reference's position buffer (structure.py:1468-1486)
+        return np.float32 if positions_fn is None else np.float64
+
     def _consume(self, batch, device: bool = False) -> None:
         ptr, stride = batch.ptrs[0], batch.strides[0]
+        f64 = batch.f64
         if self._com is not None:
             import torch
             N = int(self._N)
-            out = torch.empty((batch.n_frames, N, 3), dtype=torch.float32,
+            # float64 centres of mass (the reference does not round them either)
+            out = torch.empty((batch.n_frames, N, 3), dtype=torch.float64,
                               device=f"cuda:{self._device}")
             off = 0
             for slot, n in enumerate(self._com):
                 self._ctx.com_reduce(slot, batch.ptrs[slot], batch.strides[slot],
-                                     batch.n_frames, out.data_ptr() + 12 * off, 3 * N,
-                                     device=device)
+                                     batch.n_frames, out.data_ptr() + 24 * off, 3 * N,
+                                     device=device, f64=True)
                 off += n
-            ptr, stride, device = out.data_ptr(), 3 * N, True
+            ptr, stride, device, f64 = out.data_ptr(), 3 * N, True, True
         self._ctx.sq_accumulate(ptr, stride, batch.n_frames, device=device,
-                                keepalive=batch.keepalive)
+                                keepalive=batch.keepalive, f64=f64)
         _record(batch)
 
     def _finish(self) -> None:
@@ -906,12 +913,14 @@ class IntermediateScatteringFunction(StructureFactor):
                     for g, gr in zip(self._groups, self._groupings)
                 ])]
 
+        # centres of mass stay float64 (reference: structure.py:1927-1957)
         feeder = FrameFeeder(self._trajectory, sets, frames,
                              self._default_batch(12 * int(self._N)),
-                             positions_fn)
+                             positions_fn,
+                             dtype=np.float32 if positions_fn is None else np.float64)
         for batch in feeder:
             ctx.isf_accumulate(batch.ptrs[0], batch.strides[0], batch.n_frames,
-                               keepalive=batch.keepalive)
+                               keepalive=batch.keepalive, f64=batch.f64)
             _record(batch)
         cisf, iisf = ctx.isf_fetch()
         self._local[0][:, :, cols] = cisf

@@ -391,6 +391,13 @@ int mdh_sq_accumulate(mdh_ctx *c, const float *pos, int64_t frame_stride, int lo
     return sq_accumulate_impl(c, pos, frame_stride, location, n_frames);
 }
 
+int mdh_sq_accumulate_f64(mdh_ctx *c, const double *pos, int64_t frame_stride, int location,
+                          int n_frames)
+{
+    CTX_GUARD(c);
+    return sq_accumulate_f64_impl(c, pos, frame_stride, location, n_frames);
+}
+
 int mdh_sq_fetch(mdh_ctx *c, double *ssf)
 {
     CTX_GUARD(c);
@@ -470,6 +477,15 @@ int mdh_com_reduce(mdh_ctx *c, int slot, const float *pos, int64_t frame_stride,
                            out_frame_stride);
 }
 
+int mdh_com_reduce_f64(mdh_ctx *c, int slot, const float *pos, int64_t frame_stride,
+                       int location, int n_frames, double *out_device,
+                       int64_t out_frame_stride)
+{
+    CTX_GUARD(c);
+    return com_reduce_f64_impl(c, slot, pos, frame_stride, location, n_frames, out_device,
+                               out_frame_stride);
+}
+
 int mdh_sq_configure_chains(mdh_ctx *c, int64_t n_chains, int64_t n_monomers)
 {
     CTX_GUARD(c);
@@ -489,6 +505,13 @@ int mdh_isf_accumulate(mdh_ctx *c, const float *pos, int64_t frame_stride, int l
 {
     CTX_GUARD(c);
     return isf_accumulate_impl(c, pos, frame_stride, location, n_frames);
+}
+
+int mdh_isf_accumulate_f64(mdh_ctx *c, const double *pos, int64_t frame_stride, int location,
+                           int n_frames)
+{
+    CTX_GUARD(c);
+    return isf_accumulate_f64_impl(c, pos, frame_stride, location, n_frames);
 }
 
 int mdh_isf_fetch(mdh_ctx *c, double *cisf, double *iisf)

@@ -12,13 +12,16 @@
 
 namespace {
 
+// OUT = float: what capped_distance is given (it converts to float32); OUT = double: what
+// the structure-factor classes keep in their float64 position buffer
+template <typename OUT>
 __global__ void com_kernel(const float *__restrict__ raw, int64_t frame_stride,
                            const int64_t *__restrict__ starts, const double *__restrict__ mass,
-                           int64_t n_entities, float *__restrict__ out, int64_t out_stride)
+                           int64_t n_entities, OUT *__restrict__ out, int64_t out_stride)
 {
     const int frame = blockIdx.y;
     const float *src = raw + (int64_t)frame * frame_stride;
-    float *dst = out + (int64_t)frame * out_stride;
+    OUT *dst = out + (int64_t)frame * out_stride;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_entities;
          e += (int64_t)gridDim.x * blockDim.x) {
         double sx = 0.0, sy = 0.0, sz = 0.0, sm = 0.0;
@@ -29,9 +32,9 @@ __global__ void com_kernel(const float *__restrict__ raw, int64_t frame_stride,
             sz = __dadd_rn(sz, __dmul_rn(m, (double)src[3 * a + 2]));
             sm = __dadd_rn(sm, m);
         }
-        dst[3 * e] = (float)(sx / sm);
-        dst[3 * e + 1] = (float)(sy / sm);
-        dst[3 * e + 2] = (float)(sz / sm);
+        dst[3 * e] = (OUT)(sx / sm);
+        dst[3 * e + 1] = (OUT)(sy / sm);
+        dst[3 * e + 2] = (OUT)(sz / sm);
     }
 }
 
@@ -64,8 +67,9 @@ int com_configure_impl(mdh_ctx *c, int slot, int64_t n_atoms, int64_t n_entities
     return MDH_OK;
 }
 
-int com_reduce_impl(mdh_ctx *c, int slot, const float *pos, int64_t stride, int location,
-                    int n_frames, float *out_device, int64_t out_stride)
+template <typename OUT>
+static int com_reduce_any(mdh_ctx *c, int slot, const float *pos, int64_t stride, int location,
+                          int n_frames, OUT *out_device, int64_t out_stride)
 {
     MDH_REQUIRE(slot >= 0 && slot < kComSlots, MDH_EINVAL, "com: slot must be in [0, %d)",
                 kComSlots);
@@ -90,10 +94,22 @@ int com_reduce_impl(mdh_ctx *c, int slot, const float *pos, int64_t stride, int 
         dstride = 3 * K.n_atoms;
     }
     dim3 grid((unsigned)std::min<int64_t>((K.n_entities + 127) / 128, 4096), n_frames);
-    com_kernel<<<grid, 128, 0, c->stream>>>(dsrc, dstride, K.starts.as<int64_t>(),
-                                            K.masses.as<double>(), K.n_entities, out_device,
-                                            out_stride);
+    com_kernel<OUT><<<grid, 128, 0, c->stream>>>(dsrc, dstride, K.starts.as<int64_t>(),
+                                                 K.masses.as<double>(), K.n_entities,
+                                                 out_device, out_stride);
     MDH_CUDA(cudaGetLastError());
     c->launches++;
     return MDH_OK;
+}
+
+int com_reduce_impl(mdh_ctx *c, int slot, const float *pos, int64_t stride, int location,
+                    int n_frames, float *out_device, int64_t out_stride)
+{
+    return com_reduce_any(c, slot, pos, stride, location, n_frames, out_device, out_stride);
+}
+
+int com_reduce_f64_impl(mdh_ctx *c, int slot, const float *pos, int64_t stride, int location,
+                        int n_frames, double *out_device, int64_t out_stride)
+{
+    return com_reduce_any(c, slot, pos, stride, location, n_frames, out_device, out_stride);
 }

@@ -81,7 +81,9 @@ struct FilterConst {       // per configuration (host)
     unsigned cbits;        // bits of the float (1.5 * 2^(23-k)): slot 0 ("below range")
     unsigned span;         // (n_bins + 2) << k: slots 0 .. n_bins + 1
     int k;                 // fraction bits of the fixed-point bin coordinate
-    int sb;                // log2(sub-bins per bin) of the shared-memory histogram
+    int sb;                // log2(sub-bins per bin) of the cell-pair kernel's per-warp histograms
+    int cb;                // all-pairs filter kernel: log2(columns per slot) of the block's histogram
+    int lg;                // 2^lg >= n_bins + 2
     int lower;             // r_lo > 0: pairs below the range exist
 };
 
@@ -151,7 +153,9 @@ struct SqState {
     DevBuf d_pairs;        // int[n_pairs][2]
     DevBuf chunks;         // int4[n_chunks]: {start, end, rho_row, 0}
     int n_chunks = 0, chunk_len = 0;
-    DevBuf raw[2];         // float[F][n][3] staging for host input, one per stager slot
+    DevBuf raw[2];         // float[F][n][3] (or double) staging for host input, one per stager slot
+    DevBuf split;          // float[2F][n][3]: float64 input as float32 + negated remainder
+    DevBuf split_vmap;     // int4[F]: {f, F + f, 0, 0}
     DevBuf tab;            // phase-factor tables of one group of frames
     DevBuf rho;            // double[F][n_rho][n_q][2]
     DevBuf ssf;            // double[n_pairs][n_q]
@@ -174,9 +178,10 @@ struct IsfState {           // intermediate scattering function on top of SqStat
     bool on = false;
     int n_lags = 0;
     bool incoherent = false;
+    bool f64 = false;      // the window holds doubles (mdh_isf_accumulate_f64)
     int64_t max_frames = 0, n_done = 0;
     DevBuf rho_all;        // double2[max_frames][n_rho][n_q]: rho(q, t) of every frame
-    DevBuf window[2];      // float[kept + batch][n_total][3], ping-pong
+    DevBuf window[2];      // float (or double) [kept + batch][n_total][3], ping-pong
     int window_frames = 0, which = 0;
     DevBuf vmap;           // int4 per virtual frame: {frame, reference frame, lag, 0}
     DevBuf cisf;           // double[n_lags][n_pairs][n_q]
@@ -264,6 +269,8 @@ int rdf_filter_prepare(mdh_ctx *c, int f0, int n_frames, double sqrt_err);
 int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *goff,
                       int n_q, const double *wv, const int32_t *lat_n, const double *lat_b,
                       int n_pairs, const int32_t *pairs, int mode);
+int sq_accumulate_f64_impl(mdh_ctx *c, const double *pos, int64_t stride, int location,
+                           int n_frames);
 int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
                        int n_frames);
 // com.cu
@@ -271,10 +278,14 @@ int com_configure_impl(mdh_ctx *c, int slot, int64_t n_atoms, int64_t n_entities
                        const int64_t *starts, const double *masses);
 int com_reduce_impl(mdh_ctx *c, int slot, const float *pos, int64_t stride, int location,
                     int n_frames, float *out_device, int64_t out_stride);
+int com_reduce_f64_impl(mdh_ctx *c, int slot, const float *pos, int64_t stride, int location,
+                        int n_frames, double *out_device, int64_t out_stride);
 int sq_configure_chains_impl(mdh_ctx *c, int64_t n_chains, int64_t n_monomers);
 int sq_plan_impl(int n_q, const int32_t *lat_n, int64_t *stats, int32_t *coverage,
                  int32_t *pair_rule_violations);
 int isf_configure_impl(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frames);
+int isf_accumulate_f64_impl(mdh_ctx *c, const double *pos, int64_t stride, int location,
+                            int n_frames);
 int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
                         int n_frames);
 int isf_fetch_impl(mdh_ctx *c, double *cisf, double *iisf);

@@ -453,6 +453,14 @@ __device__ inline FrameFilter filter_prepare_frame(const FrameBox &fb, const uns
 // RED without the "memory" clobber: the compiler may move the tile loads of the next
 // iteration across it (they never alias the histogram); __syncthreads() orders the
 // histogram against its final read.
+// (a & b) | c in one LOP3 (ALU pipe)
+__device__ __forceinline__ unsigned lop3_and_or(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __device__ __forceinline__ void red_shared_hot(unsigned smem_addr, unsigned v)
 {
     asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(smem_addr), "r"(v));

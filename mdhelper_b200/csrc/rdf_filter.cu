@@ -46,12 +46,18 @@ namespace {
 
 constexpr int kListCap = 3072;           // deferred entries per block and tile
 
-template <int IPT>
-__host__ __device__ inline size_t filter_smem_bytes(int n_bins, int sb)
+// shared memory of a block: histogram ((n_bins + 2) slots x 2^cb columns, first, so that
+// its address is the kernel's shared-memory base + an offset), thresholds, two j-tiles,
+// the deferred list
+__host__ __device__ inline size_t filter_hist_bytes(int n_bins, int cb)
 {
-    return align16(sizeof(double) * (n_bins + 1)) + 2 * kThreads * IPT * sizeof(float4) +
-           sizeof(unsigned) * ((size_t)kWarps * (((size_t)(n_bins + 2) << sb) + 32)) +
-           sizeof(unsigned) * (kListCap + 4);
+    return align16(sizeof(unsigned) * ((size_t)(n_bins + 2) << cb));
+}
+template <int IPT>
+__host__ __device__ inline size_t filter_smem_bytes(int n_bins, int cb)
+{
+    return filter_hist_bytes(n_bins, cb) + align16(sizeof(double) * (n_bins + 1)) +
+           2 * kThreads * IPT * sizeof(float4) + sizeof(unsigned) * (kListCap + 4);
 }
 
 // Exact re-evaluation of the IPT pairs behind one deferred entry (thread te of the
@@ -87,14 +93,16 @@ __device__ __noinline__ void filter_fix(const PairParams &P, int frame, int it, 
             if (!(u < span_l)) continue;
             if (!((u & ((1u << fc.k) - 1u)) < ff.wlim)) continue;
             if (EXCL && __float_as_int(a.w) == __float_as_int(pj.w)) continue;
-            const unsigned word = (LOWER ? u : u - fc.cbits) >> (fc.k - fc.sb);
+            // the main loop added the pair to (slot it saw, column of thread te's lane)
+            const unsigned seen = (LOWER ? u : u - fc.cbits) >> fc.k;
+            const unsigned col = (unsigned)te & ((1u << fc.cb) - 1u);
             const double d2 = pair_d2(a.x, a.y, a.z, pj, fb);
             const int slot = P.fast_bins ? slot_fast(d2, sT, P.n_bins, P.guess)
                                          : slot_search(d2, sT, P.n_bins);
-            if ((word >> fc.sb) == (unsigned)slot) continue;
+            if (seen == (unsigned)slot) continue;
             // slots 0 and n_bins + 1 are scratch words, so no range test is needed
-            red_shared(hist32 + 4u * word, 0u - weight);
-            red_shared(hist32 + 4u * ((unsigned)slot << fc.sb), weight);
+            red_shared(hist32 + 4u * ((seen << fc.cb) + col), 0u - weight);
+            red_shared(hist32 + 4u * (((unsigned)slot << fc.cb) + col), weight);
         }
     }
 }
@@ -114,12 +122,17 @@ __global__ void __launch_bounds__(kThreads, OCC)
     extern __shared__ __align__(16) unsigned char smem[];
     const int n_bins = P.n_bins;
     const FilterConst fc = P.fc;
-    // per warp: (n_bins + 2) slots x 2^sb sub-bins, then 32 per-lane trash words
-    const int hwords = ((n_bins + 2) << fc.sb) + 32;
-    double *sT = reinterpret_cast<double *>(smem);
-    float4 *sJ = reinterpret_cast<float4 *>(smem + align16(sizeof(double) * (n_bins + 1)));
-    unsigned *sH = reinterpret_cast<unsigned *>(sJ + 2 * TILE);
-    unsigned *sList = sH + kWarps * hwords;
+    // ONE histogram per block: (n_bins + 2) slots x 2^cb columns, a lane updates column
+    // lane mod 2^cb -- with 32 columns the 32 updates of a warp instruction fall in 32
+    // different banks whatever the bins are (per-warp histograms with sub-bins took 3.8
+    // wavefronts per instruction on random bins).  Slot n_bins + 1 ("above the range") takes
+    // every pair beyond the range; it is never read.
+    const int hwords = (n_bins + 2) << fc.cb;
+    unsigned *sH = reinterpret_cast<unsigned *>(smem);
+    double *sT = reinterpret_cast<double *>(smem + filter_hist_bytes(n_bins, fc.cb));
+    float4 *sJ = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sT) +
+                                            align16(sizeof(double) * (n_bins + 1)));
+    unsigned *sList = reinterpret_cast<unsigned *>(sJ + 2 * TILE);
     unsigned *sCount = sList + kListCap;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -131,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, OCC)
     if (jt0 >= jt1) return;
 
     for (int k = tid; k <= n_bins; k += kThreads) sT[k] = P.thr[k];
-    for (int k = tid; k < kWarps * hwords; k += kThreads) sH[k] = 0;
+    for (int k = tid; k < hwords; k += kThreads) sH[k] = 0;
     if (tid == 0) *sCount = 0;
 
     const float4 *f1 = P.p1 + (int64_t)frame * P.pad1;
@@ -158,15 +171,20 @@ __global__ void __launch_bounds__(kThreads, OCC)
         nz[ip] = pk2(-zi[2 * ip], -zi[2 * ip + 1]);
     }
 
-    const unsigned hist32 = (unsigned)__cvta_generic_to_shared(sH + warp * hwords);
-    const int shift = fc.k - fc.sb;
-    // !LOWER: the bits of 1.5*2^(23-k) are still in u; fold them into the base
-    const unsigned hbase = hist32 - (LOWER ? 0u : ((fc.cbits >> shift) << 2));
+    const unsigned hist32 = (unsigned)__cvta_generic_to_shared(sH);
+    // Byte offset of a pair's word without touching the FMA pipe (an IMAD per pair there
+    // costs as much as a packed FP32 instruction): t = u >> (k - cb - 2) holds the slot in
+    // bits [cb + 2, cb + 2 + lg) -- above them, for !LOWER, the bits of 1.5*2^(23-k), which
+    // start at bit 24 - k + cb >= cb + 2 + lg --, fraction bits below.  One MIN clamps
+    // everything beyond the range to slot n_bins + 1, one LOP3 keeps the slot field and
+    // inserts the lane's column; the base is the kernel's shared-memory base, an immediate.
+    const int tshift = fc.k - fc.cb - 2;
+    const unsigned low = (4u << fc.cb) - 1u;
+    const unsigned tmask = ((4u << (fc.cb + fc.lg)) - 1u) & ~low;
+    const unsigned tmax = ((((LOWER ? 0u : fc.cbits) >> fc.k) + (unsigned)(n_bins + 1))
+                           << (fc.cb + 2)) | low;
+    const unsigned colbits = ((unsigned)lane & ((1u << fc.cb) - 1u)) << 2;
     const unsigned span_l = LOWER ? fc.span : fc.cbits + fc.span;
-    // word index of this lane's trash word (same offset convention as u >> shift):
-    // every pair issues one unconditional RED; pairs outside the range -- about half
-    // of them when the range ends at L/2 -- land here and never contend
-    const unsigned trash_w = (span_l >> shift) + (unsigned)lane;
     const unsigned fmask = (1u << fc.k) - 1u;      // fraction bits of the bin coordinate
     const float scale = fc.scale, offm = ff.offm;
 
@@ -224,9 +242,9 @@ __global__ void __launch_bounds__(kThreads, OCC)
                     const unsigned u = uu[r][ii];
                     // uncertain iff the fraction bits are below wlim; keep the smallest
                     vmin[r] = min(vmin[r], u & fmask);
-                    unsigned w = min(u >> shift, trash_w);
-                    if (EXCL && gi[ii] == __float_as_int(pj[r].w)) w = trash_w;
-                    red_shared_hot(hbase + (w << 2), wi[ii]);
+                    unsigned t = min(u >> tshift, tmax);
+                    if (EXCL && gi[ii] == __float_as_int(pj[r].w)) t = tmax;
+                    red_shared_hot(hist32 + lop3_and_or(t, tmask, colbits), wi[ii]);
                     if (AUDIT) {
                         const bool unc = (u & fmask) < ff.wlim;
                         const bool in = u < span_l;
@@ -309,13 +327,13 @@ __global__ void __launch_bounds__(kThreads, OCC)
         buf ^= 1;
     }
 
-    // merge into the global int64 histogram.  The warps' words are summed modulo
-    // 2^32 first: a correction may have been subtracted in another warp's copy than
-    // the one that was incremented; the block total itself is below 2^32.
+    // merge into the global int64 histogram.  The columns are summed modulo 2^32 first
+    // (a correction is subtracted from the column that was incremented, but the block
+    // total is what stays below 2^32, not every word).
     for (int k = tid; k < n_bins; k += kThreads) {
         unsigned s = 0;
-        for (int w = 0; w < kWarps; ++w)
-            for (int q = 0; q < (1 << fc.sb); ++q) s += sH[w * hwords + ((k + 1) << fc.sb) + q];
+        for (int q = 0; q < (1 << fc.cb); ++q)
+            s += sH[((k + 1) << fc.cb) + ((q + tid) & ((1 << fc.cb) - 1))];
         if (s) atomicAdd(&P.counts[k], (unsigned long long)s);
     }
     if (AUDIT) {
@@ -358,7 +376,7 @@ __global__ void rdf_filter_prepare_kernel(const PrepareParams Q)
 template <bool EXCL, bool LOWER, bool AUDIT, int IPT, int OCC>
 int launch_filter_o(mdh_ctx *c, const PairParams &P, dim3 grid)
 {
-    const size_t smem = filter_smem_bytes<IPT>(P.n_bins, P.fc.sb);
+    const size_t smem = filter_smem_bytes<IPT>(P.n_bins, P.fc.cb);
     auto kern = rdf_filter_kernel<EXCL, LOWER, AUDIT, IPT, OCC>;
     MDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
@@ -413,8 +431,10 @@ bool rdf_filter_configure(RdfState &R, const double *thr, double sqrt_err)
 {
     R.filter_ok = false;
     const int n_bins = R.n_bins;
+    // 2^lg >= slots + 32: the slot field of the bin coordinate, with room for the cell-pair
+    // kernel's 32 trash words behind the slots (rdf_cells.cu: cp_hist_log2)
     int lg = 0;
-    while ((1 << lg) < n_bins + 2) ++lg;
+    while ((1 << lg) < n_bins + 2 + 32) ++lg;
     const int k = std::min(16, 22 - lg);
     if (k < 9) return false;
     if (!(sqrt_err >= 0.0 && sqrt_err <= 1.0 / 4194304.0)) return false;   // 2^-22
@@ -439,15 +459,19 @@ bool rdf_filter_configure(RdfState &R, const double *thr, double sqrt_err)
     memcpy(&fc.cbits, &mf, 4);
     fc.span = (unsigned)(n_bins + 2) << k;
     fc.lower = R.r_lo > 0.0;
-    // sub-bins: as many as the shared memory of R.filter_occ resident blocks allows
+    fc.lg = lg;
+    // histogram columns: as many (up to one per lane) as the shared memory of
+    // R.filter_occ resident blocks allows
     const size_t budget = (size_t)(224 * 1024) / R.filter_occ - 1024;
-    auto need = [&](int sb) {
-        return R.ipt == 2 ? filter_smem_bytes<2>(n_bins, sb) : filter_smem_bytes<4>(n_bins, sb);
+    auto need = [&](int cb) {
+        return R.ipt == 2 ? filter_smem_bytes<2>(n_bins, cb) : filter_smem_bytes<4>(n_bins, cb);
     };
-    int sb = 2;
-    while (sb > 0 && need(sb) > budget) --sb;
-    fc.sb = std::min(sb, k);
-    if (need(fc.sb) > 200 * 1024) return false;
+    int cb = 5;
+    while (cb > 0 && need(cb) > budget) --cb;
+    fc.cb = std::min(cb, k - 2);
+    if (need(fc.cb) > 200 * 1024) return false;
+    // the cell-pair kernel keeps one histogram per warp with 2^sb sub-bins per bin
+    fc.sb = std::min(2, k);
     R.fc = fc;
     R.filter_ok = true;
     return true;

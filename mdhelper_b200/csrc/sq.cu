@@ -1361,11 +1361,37 @@ static int sq_compute_rho(mdh_ctx *c, const float *raw, int64_t stride, const in
     return MDH_OK;
 }
 
-static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int location,
+// float64 coordinates -> the S(q) kernels' float32 frames without losing a bit that
+// matters: frame f of dst = the coordinate rounded to float32 ("hi"), frame n_frames + f
+// = hi - x rounded to float32 (the NEGATED remainder), vmap[f] = {f, n_frames + f}: the
+// kernels' displacement path then forms (double)hi - (double)(hi - x) = x up to
+// 2^-48 |x| in fp64 -- the reference's float64 position buffer
+// (/root/reference/src/mdhelper/analysis/structure.py:1468-1486) to 14 digits.
+__global__ void sq_split_kernel(const double *__restrict__ src, int64_t src_stride,
+                                float *__restrict__ dst, int64_t n3, int n_frames,
+                                int4 *__restrict__ vmap)
+{
+    const int f = blockIdx.y;
+    const double *s = src + (int64_t)f * src_stride;
+    float *hi = dst + (int64_t)f * n3;
+    float *nlo = dst + (int64_t)(n_frames + f) * n3;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n3;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const double x = s[k];
+        const float h = (float)x;
+        hi[k] = h;
+        nlo[k] = (float)((double)h - x);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) vmap[f] = make_int4(f, n_frames + f, 0, 0);
+}
+
+template <typename T>
+static int sq_accumulate_piece(mdh_ctx *c, const T *pos, int64_t stride, int location,
                                int n_frames, int nominal_frames);
 
-int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
-                       int n_frames)
+template <typename T>
+static int sq_accumulate_any(mdh_ctx *c, const T *pos, int64_t stride, int location,
+                             int n_frames)
 {
     SqState &S = c->sq;
     MDH_REQUIRE(S.configured, MDH_ESTATE, "sq: accumulate before configure");
@@ -1375,13 +1401,14 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
     MDH_REQUIRE(stride >= 3 * S.n_total, MDH_EINVAL, "sq: frame_stride < 3*n_total");
     MDH_REQUIRE(location == MDH_HOST || location == MDH_DEVICE, MDH_EINVAL,
                 "sq: invalid location");
-    MDH_TRACE("sq_accumulate: %d frames, location %d", n_frames, location);
+    MDH_TRACE("sq_accumulate: %d frames of %d-byte coordinates, location %d", n_frames,
+              (int)sizeof(T), location);
     // host input in pieces: the copy of one piece (copy stream) overlaps the kernels of
     // the previous one (compute stream); the particle chunks are laid out once, for the
     // whole call
     if (location == MDH_HOST) {
         int f0 = 0;
-        for (int nf : mdh_plan_pieces(n_frames, 12.0 * (double)S.n_total)) {
+        for (int nf : mdh_plan_pieces(n_frames, 3.0 * sizeof(T) * (double)S.n_total)) {
             if (int rc = sq_accumulate_piece(c, pos + (int64_t)f0 * stride, stride, location, nf,
                                              n_frames)) return rc;
             f0 += nf;
@@ -1391,32 +1418,66 @@ int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locatio
     return sq_accumulate_piece(c, pos, stride, location, n_frames, n_frames);
 }
 
+int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
+                       int n_frames)
+{
+    return sq_accumulate_any(c, pos, stride, location, n_frames);
+}
+
+int sq_accumulate_f64_impl(mdh_ctx *c, const double *pos, int64_t stride, int location,
+                           int n_frames)
+{
+    return sq_accumulate_any(c, pos, stride, location, n_frames);
+}
+
 // nominal_frames: the frame count the particle chunks are laid out for (the whole call;
 // its pieces reuse the layout instead of rebuilding it)
-static int sq_accumulate_piece(mdh_ctx *c, const float *pos, int64_t stride, int location,
+template <typename T>
+static int sq_accumulate_piece(mdh_ctx *c, const T *pos, int64_t stride, int location,
                                int n_frames, int nominal_frames)
 {
+    constexpr bool kF64 = sizeof(T) == 8;
     SqState &S = c->sq;
-    const float *dsrc = pos;
+    const T *dsrc = pos;
     int64_t dstride = stride;
     int slot = 0;
     if (location == MDH_HOST) {
         if (int rc = c->stager.acquire(&slot)) return rc;
         DevBuf &raw = S.raw[slot];
-        if (int rc = raw.reserve(sizeof(float) * 3 * S.n_total * n_frames)) return rc;
-        MDH_CUDA(mdh_copy_frames(raw.p, sizeof(float) * 3 * S.n_total, pos,
-                                   sizeof(float) * stride, sizeof(float) * 3 * S.n_total,
+        if (int rc = raw.reserve(sizeof(T) * 3 * S.n_total * n_frames)) return rc;
+        MDH_CUDA(mdh_copy_frames(raw.p, sizeof(T) * 3 * S.n_total, pos,
+                                   sizeof(T) * stride, sizeof(T) * 3 * S.n_total,
                                    n_frames, cudaMemcpyHostToDevice, c->stager.copy));
         if (int rc = c->stager.publish(c->stream, slot)) return rc;
-        dsrc = raw.as<float>();
+        dsrc = raw.as<T>();
         dstride = 3 * S.n_total;
     }
     const size_t rho_bytes = sizeof(double) * 2 * (size_t)n_frames * S.n_rho * S.n_q;
     if (S.n_chains == 0)
         if (int rc = S.rho.reserve(rho_bytes)) return rc;
+    const float *fsrc;
+    const int4 *vmap = nullptr;
+    if constexpr (kF64) {
+        const int64_t n3 = 3 * S.n_total;
+        if (int rc = S.split.reserve(sizeof(float) * 2 * n3 * n_frames)) return rc;
+        if (int rc = S.split_vmap.reserve(sizeof(int4) * (size_t)n_frames)) return rc;
+        fsrc = S.split.as<float>();
+        vmap = S.split_vmap.as<int4>();
+    } else {
+        fsrc = dsrc;
+    }
 
     if (int rc = c->t_sq.begin(c->stream)) return rc;
-    if (int rc = sq_compute_rho(c, dsrc, dstride, nullptr, n_frames, S.rho.as<double>(),
+    if constexpr (kF64) {
+        const int64_t n3 = 3 * S.n_total;
+        dim3 grid((unsigned)std::min<int64_t>((n3 + 255) / 256, 1024), n_frames);
+        sq_split_kernel<<<grid, 256, 0, c->stream>>>(dsrc, dstride, S.split.as<float>(), n3,
+                                                     n_frames, S.split_vmap.as<int4>());
+        MDH_CUDA(cudaGetLastError());
+        c->launches++;
+        dstride = n3;
+    }
+    if (int rc = sq_compute_rho(c, fsrc, dstride, vmap, n_frames, S.rho.as<double>(),
                                 nominal_frames)) return rc;
     if (S.n_chains > 0) {
         // the kernel has added |rho_chain|^2 to the accumulator itself
@@ -1488,6 +1549,29 @@ __global__ void isf_incoherent_kernel(const double2 *__restrict__ rho_tmp,
     }
 }
 
+// float64 window: displacement of virtual frame v = (t, t0, lag) in fp64, written as
+// float32 + negated float32 remainder (frames v and n_v + v of dst; see sq_split_kernel)
+__global__ void isf_displacement_split_kernel(const double *__restrict__ win, int64_t n3,
+                                              const int4 *__restrict__ vin, int n_v,
+                                              float *__restrict__ dst,
+                                              int4 *__restrict__ vout)
+{
+    const int v = blockIdx.y;
+    const int4 vm = vin[v];
+    const double *a = win + (int64_t)vm.x * n3;
+    const double *b = win + (int64_t)vm.y * n3;
+    float *hi = dst + (int64_t)v * n3;
+    float *nlo = dst + (int64_t)(n_v + v) * n3;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n3;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const double d = a[k] - b[k];
+        const float h = (float)d;
+        hi[k] = h;
+        nlo[k] = (float)((double)h - d);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) vout[v] = make_int4(v, n_v + v, vm.z, 0);
+}
+
 }  // namespace
 
 // Single-chain structure factor (SURVEY.md section 8(f) rank 3;
@@ -1533,9 +1617,14 @@ int isf_configure_impl(mdh_ctx *c, int n_lags, int incoherent, int64_t max_frame
     return MDH_OK;
 }
 
-int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
-                        int n_frames)
+// T = float: the window holds the float32 frames the kernels read directly; T = double
+// (centres of mass: the reference's float64 position buffer, structure.py:1927-1957): the
+// window holds doubles and the kernels get float32 + remainder copies
+template <typename T>
+static int isf_accumulate_any(mdh_ctx *c, const T *pos, int64_t stride, int location,
+                              int n_frames)
 {
+    constexpr bool kF64 = sizeof(T) == 8;
     SqState &S = c->sq;
     IsfState &I = c->isf;
     MDH_REQUIRE(S.configured && I.on, MDH_ESTATE, "isf: accumulate before configure");
@@ -1549,30 +1638,47 @@ int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locati
                 "isf: more frames than announced at configure (%lld)", (long long)I.max_frames);
 
     // coordinate window: [frames kept from earlier calls][the frames of this call]
-    const int64_t fsz = 3 * S.n_total;                     // floats per frame
+    const int64_t fsz = 3 * S.n_total;                     // coordinates per frame
     const int keep = I.window_frames;
     DevBuf &win = I.window[I.which];
-    const size_t need = sizeof(float) * fsz * (size_t)(keep + n_frames);
+    const size_t need = sizeof(T) * fsz * (size_t)(keep + n_frames);
     if (win.cap < need) {
         // grow WITHOUT losing the frames kept from earlier calls (DevBuf::reserve frees)
         DevBuf bigger;
         if (int rc = bigger.reserve(need)) return rc;
         if (keep > 0)
-            MDH_CUDA(cudaMemcpyAsync(bigger.p, win.p, sizeof(float) * fsz * (size_t)keep,
+            MDH_CUDA(cudaMemcpyAsync(bigger.p, win.p, sizeof(T) * fsz * (size_t)keep,
                                      cudaMemcpyDeviceToDevice, c->stream));
         MDH_CUDA(cudaStreamSynchronize(c->stream));
         win.adopt(bigger);
     }
-    MDH_CUDA(mdh_copy_frames(win.as<float>() + fsz * keep, sizeof(float) * fsz, pos,
-                               sizeof(float) * stride, sizeof(float) * fsz, n_frames,
+    MDH_CUDA(mdh_copy_frames(win.as<T>() + fsz * keep, sizeof(T) * fsz, pos,
+                               sizeof(T) * stride, sizeof(T) * fsz, n_frames,
                                location == MDH_HOST ? cudaMemcpyHostToDevice
                                                     : cudaMemcpyDeviceToDevice, c->stream));
     if (int rc = c->t_sq.begin(c->stream)) return rc;
 
     // rho(q, t) of the new frames, straight into the per-frame store
     const size_t row = (size_t)2 * S.n_rho * S.n_q;        // doubles per frame
-    if (int rc = sq_compute_rho(c, win.as<float>() + fsz * keep, fsz, nullptr, n_frames,
-                                I.rho_all.as<double>() + row * I.n_done, n_frames)) return rc;
+    const float *fwin = nullptr;
+    if constexpr (kF64) {
+        if (int rc = S.split.reserve(sizeof(float) * 2 * fsz * n_frames)) return rc;
+        if (int rc = S.split_vmap.reserve(sizeof(int4) * (size_t)n_frames)) return rc;
+        dim3 grid((unsigned)std::min<int64_t>((fsz + 255) / 256, 1024), n_frames);
+        sq_split_kernel<<<grid, 256, 0, c->stream>>>(win.as<T>() + fsz * keep, fsz,
+                                                     S.split.as<float>(), fsz, n_frames,
+                                                     S.split_vmap.as<int4>());
+        MDH_CUDA(cudaGetLastError());
+        c->launches++;
+        if (int rc = sq_compute_rho(c, S.split.as<float>(), fsz, S.split_vmap.as<int4>(),
+                                    n_frames, I.rho_all.as<double>() + row * I.n_done,
+                                    n_frames)) return rc;
+    } else {
+        fwin = win.as<T>();
+        if (int rc = sq_compute_rho(c, fwin + fsz * keep, fsz, nullptr, n_frames,
+                                    I.rho_all.as<double>() + row * I.n_done, n_frames))
+            return rc;
+    }
 
     if (I.incoherent) {
         // virtual frames (t, lag): displacement r(t) - r(t - lag), lag = 0 included
@@ -1588,8 +1694,15 @@ int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locati
                 vm.push_back(make_int4(keep + t, keep + t - lag, lag, 0));
         }
         // batches sized to ~256 MB of temporary rho
-        const int vmax = (int)std::max<size_t>(1, std::min<size_t>(
+        int vmax = (int)std::max<size_t>(1, std::min<size_t>(
             8192, ((size_t)256 << 20) / (sizeof(double) * row)));
+        if constexpr (kF64) {
+            // ... and to ~256 MB of materialised displacements
+            vmax = (int)std::max<size_t>(1, std::min<size_t>(
+                vmax, ((size_t)256 << 20) / (sizeof(float) * 2 * (size_t)fsz)));
+            if (int rc = S.split.reserve(sizeof(float) * 2 * fsz * (size_t)vmax)) return rc;
+            if (int rc = S.split_vmap.reserve(sizeof(int4) * (size_t)vmax)) return rc;
+        }
         if (int rc = I.vmap.reserve(sizeof(int4) * (size_t)vmax)) return rc;
         if (int rc = S.rho.reserve(sizeof(double) * row * (size_t)vmax)) return rc;
         for (size_t v0 = 0; v0 < vm.size(); v0 += vmax) {
@@ -1597,12 +1710,24 @@ int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locati
             // pageable source: staged by the runtime before the call returns
             MDH_CUDA(cudaMemcpyAsync(I.vmap.p, vm.data() + v0, sizeof(int4) * nv,
                                      cudaMemcpyHostToDevice, c->stream));
-            if (int rc = sq_compute_rho(c, win.as<float>(), fsz, I.vmap.as<int4>(), nv,
-                                        S.rho.as<double>(), std::max(nv, 64))) return rc;
+            const int4 *vdev = I.vmap.as<int4>();
+            if constexpr (kF64) {
+                dim3 sgrid((unsigned)std::min<int64_t>((fsz + 255) / 256, 1024), nv);
+                isf_displacement_split_kernel<<<sgrid, 256, 0, c->stream>>>(
+                    win.as<T>(), fsz, I.vmap.as<int4>(), nv, S.split.as<float>(),
+                    S.split_vmap.as<int4>());
+                MDH_CUDA(cudaGetLastError());
+                c->launches++;
+                vdev = S.split_vmap.as<int4>();
+                if (int rc = sq_compute_rho(c, S.split.as<float>(), fsz, vdev, nv,
+                                            S.rho.as<double>(), std::max(nv, 64))) return rc;
+            } else {
+                if (int rc = sq_compute_rho(c, fwin, fsz, vdev, nv, S.rho.as<double>(),
+                                            std::max(nv, 64))) return rc;
+            }
             dim3 grid((S.n_q + 127) / 128, S.n_rho);
             isf_incoherent_kernel<<<grid, 128, 0, c->stream>>>(
-                S.rho.as<double2>(), I.vmap.as<int4>(), nv, S.n_rho, S.n_q,
-                I.iisf.as<double>());
+                S.rho.as<double2>(), vdev, nv, S.n_rho, S.n_q, I.iisf.as<double>());
             MDH_CUDA(cudaGetLastError());
             c->launches++;
         }
@@ -1611,9 +1736,9 @@ int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locati
         const int next_keep = std::min(total, I.n_lags - 1);
         DevBuf &nxt = I.window[I.which ^ 1];
         if (next_keep > 0) {
-            if (int rc = nxt.reserve(sizeof(float) * fsz * (size_t)next_keep)) return rc;
-            MDH_CUDA(cudaMemcpyAsync(nxt.p, win.as<float>() + fsz * (total - next_keep),
-                                     sizeof(float) * fsz * next_keep,
+            if (int rc = nxt.reserve(sizeof(T) * fsz * (size_t)next_keep)) return rc;
+            MDH_CUDA(cudaMemcpyAsync(nxt.p, win.as<T>() + fsz * (total - next_keep),
+                                     sizeof(T) * fsz * next_keep,
                                      cudaMemcpyDeviceToDevice, c->stream));
         }
         I.window_frames = next_keep;
@@ -1622,6 +1747,24 @@ int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int locati
     I.n_done += n_frames;
     S.rho_frames = 0;
     return c->t_sq.end(c->stream);
+}
+
+int isf_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
+                        int n_frames)
+{
+    MDH_REQUIRE(c->isf.n_done == 0 || !c->isf.f64, MDH_ESTATE,
+                "isf: float32 frames after float64 frames in one run");
+    c->isf.f64 = false;
+    return isf_accumulate_any(c, pos, stride, location, n_frames);
+}
+
+int isf_accumulate_f64_impl(mdh_ctx *c, const double *pos, int64_t stride, int location,
+                            int n_frames)
+{
+    MDH_REQUIRE(c->isf.n_done == 0 || c->isf.f64, MDH_ESTATE,
+                "isf: float64 frames after float32 frames in one run");
+    c->isf.f64 = true;
+    return isf_accumulate_any(c, pos, stride, location, n_frames);
 }
 
 int isf_fetch_impl(mdh_ctx *c, double *cisf, double *iisf)

@@ -415,9 +415,9 @@ def test_argument_errors():
 @pytest.mark.parametrize("tag", ["equal", "unequal"])
 def test_residue_structure_factor_against_the_reference(golden, tag):
     """StructureFactor(groupings="residues") vs the reference's own class on its own
-    ``center_of_mass`` (tests/golden/com_ref.npz).  The centres are handed to the kernels
-    as float32 (the reference keeps them in a float64 buffer, structure.py:1468): phase
-    errors of q |r| 6e-8 leave ~1e-6 of S(q), hence the looser bound here."""
+    ``center_of_mass`` (tests/golden/com_ref.npz).  The centres stay float64 up to the
+    Fourier sums, as in the reference's position buffer (structure.py:1468): centres
+    rounded to float32 would leave phase errors of q |r| 6e-8, ~1e-6 of S(q)."""
     from mdhelper_b200.universe import SyntheticUniverse
     g = golden("com_ref")
     u = SyntheticUniverse(g[f"{tag}_positions"], g[f"{tag}_dims"],
@@ -430,7 +430,7 @@ def test_residue_structure_factor_against_the_reference(golden, tag):
                                  verbose=False, host_com=host_com).run()
         np.testing.assert_allclose(s.results.wavenumbers, g[f"{tag}_ssf_wavenumbers"],
                                    rtol=1e-12)
-        np.testing.assert_allclose(s.results.ssf, g[f"{tag}_ssf_res"], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(s.results.ssf, g[f"{tag}_ssf_res"], rtol=1e-9, atol=1e-10)
 
 
 def test_structure_factor_of_a_triclinic_universe_uses_the_edge_lengths():
@@ -472,3 +472,146 @@ def test_grids_too_large_for_shared_memory_tables_use_the_general_kernel():
     with pytest.raises(ValueError):
         _S().StructureFactor([u.atoms], wavevectors=wv, unique=False, sort=False,
                              verbose=False, kernel="lattice_fp64").run()
+
+
+# ---- float64 coordinates (centres of mass, unwrapped positions) ------------------------
+
+@pytest.mark.parametrize("kernel", ["lattice_dmma", "lattice_fp64", "general_fp64"])
+def test_float64_coordinates_are_not_rounded_to_float32(kernel):
+    """mdh_sq_accumulate_f64 vs a numpy direct sum over the same float64 coordinates, far
+    from the origin (|r| ~ 1e3, where a float32 copy is off by 6e-5 and S(q) by far more
+    than the bound): host and device input, more frames than one piece."""
+    import torch
+    from mdhelper_b200 import _lib
+    rng = np.random.default_rng(20260641)
+    n, F, L = 777, 5, 17.0
+    pos = 1000.0 + rng.random((F, n, 3)) * L
+    nvec = np.array([(a, b, c) for a in range(4) for b in range(4) for c in range(5)][1:],
+                    dtype=np.int32)
+    b = 2 * np.pi / np.array([L, L, L])
+    wv = nvec * b
+    want = np.zeros(len(wv))
+    for f in range(F):
+        rho = np.exp(1j * (pos[f] @ wv.T)).sum(axis=0)
+        want += (rho * rho.conj()).real
+    ctx = _lib.Context(0)
+    lat = {} if kernel == "general_fp64" else dict(lattice_n=nvec, lattice_b=b)
+    ctx.sq_configure(n, [0, n], wv, [(-1, -1)], mode=kernel, **lat)
+    ctx.sq_accumulate(pos, 3 * n, F, f64=True)
+    got = ctx.sq_fetch()[0]
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-7)
+    ctx.sq_reset()
+    dev = torch.from_numpy(pos).cuda()
+    ctx.sq_accumulate(dev.data_ptr(), 3 * n, F, device=True, f64=True)
+    np.testing.assert_allclose(ctx.sq_fetch()[0], got, rtol=1e-12, atol=1e-9)
+    # the float32 path on the rounded coordinates is what this entry point avoids
+    ctx.sq_reset()
+    ctx.sq_accumulate(pos.astype(np.float32), 3 * n, F)
+    rounded = ctx.sq_fetch()[0]
+    assert np.abs(rounded - want).max() > 1e3 * np.abs(got - want).max()
+    ctx.close()
+
+
+class _Centres:
+    """What the oracle's loops need from a group: the float64 centres of mass of the
+    residues of ``group`` in the current frame."""
+
+    def __init__(self, group):
+        self._g = group
+        _, self._inv = np.unique(group.resindices, return_inverse=True)
+        self._m = np.asarray(group.masses, dtype=np.float64)
+        self.n_atoms = int(self._inv.max()) + 1
+
+    @property
+    def positions(self):
+        p = np.asarray(self._g.positions, dtype=np.float64)
+        out = np.zeros((self.n_atoms, 3))
+        np.add.at(out, self._inv, self._m[:, None] * p)
+        return out / np.bincount(self._inv, weights=self._m)[:, None]
+
+
+def test_isf_of_residue_centres_against_oracle():
+    """IntermediateScatteringFunction(groupings="residues"): centres of mass and their
+    displacements in float64 (structure.py:1927-1957) vs the oracle's sliding window on
+    float64 centres, several batches so that the coordinate window is carried over."""
+    from mdhelper_b200.universe import SyntheticUniverse
+    from oracle import reference_port as rp
+    rng = np.random.default_rng(20260642)
+    sizes = rng.integers(1, 5, 300)
+    res = np.repeat(np.arange(300), sizes)
+    n, F, L = res.size, 9, 14.0
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    pos = (rng.random((1, n, 3)) * L + rng.normal(0, 0.3, (F, n, 3)).cumsum(axis=0)
+           ).astype(np.float32)
+    u = SyntheticUniverse(pos, dims, resindices=res, masses=rng.uniform(1, 30, n))
+    half = int(np.searchsorted(res, 150))
+    g1, g2 = u.select(slice(0, half)), u.select(slice(half, n))
+    kw = dict(mode="partial", n_points=5, n_lags=4, incoherent=True, dt=1.0)
+    r = _S().IntermediateScatteringFunction([g1, g2], groupings="residues", verbose=False,
+                                            batch_frames=4, **kw).run()
+    o = rp.isf_run(u, [_Centres(g1), _Centres(g2)], n_threads=4, **kw)
+    np.testing.assert_allclose(r.results.cisf, o["cisf"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(r.results.iisf, o["iisf"], rtol=1e-9, atol=1e-10)
+
+
+def _drifting_chains(rng, n_chains, n_mono, F, L, per_bead=1):
+    start = rng.random((n_chains, 1, 3)) * L
+    chain = start + rng.normal(0, 0.5, (n_chains, n_mono, 3)).cumsum(axis=1)
+    drift = np.arange(F)[:, None, None, None] * np.array([4.3, -3.1, 2.2])
+    true = chain[None] + drift + rng.normal(0, 0.05, (F, n_chains, n_mono, 3))
+    true = np.repeat(true.reshape(F, -1, 3), per_bead, axis=1)
+    if per_bead > 1:
+        true = true + rng.normal(0, 0.1, true.shape)
+    wrapped = np.mod(true, L).astype(np.float32)
+    wrapped[wrapped >= L] = 0.0
+    return wrapped
+
+
+def test_scsf_of_unwrapped_chains_far_from_the_origin():
+    """SingleChainStructureFactor(unwrap=True) of chains that drift many box lengths.
+    grouping="atoms": the reference unwraps the reader's float32 array in place
+    (polymer.py:1079, 1091-1093), i.e. rounds the unwrapped coordinates to float32 -- so
+    does this path, vs the oracle.  grouping="residues": centres of mass are float64 and
+    are unwrapped in float64 (polymer.py:1080-1093); vs the same sums in numpy."""
+    from mdhelper_b200.analysis.polymer import SingleChainStructureFactor
+    from mdhelper_b200.universe import SyntheticUniverse
+    from oracle import reference_port as rp
+    rng = np.random.default_rng(20260643)
+    n_chains, n_mono, F, L = 20, 16, 8, 10.0
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    u = SyntheticUniverse(_drifting_chains(rng, n_chains, n_mono, F, L), dims)
+    kw = dict(n_points=5, n_chains=n_chains, n_monomers=n_mono, unwrap=True)
+    r = SingleChainStructureFactor(u.atoms, verbose=False, batch_frames=3, **kw).run()
+    o = rp.scsf_run(u, u.atoms, **kw)
+    np.testing.assert_allclose(r.results.scsf, o["scsf"], rtol=1e-9, atol=1e-10)
+
+    # three atoms per monomer, one residue each
+    per = 3
+    wrapped = _drifting_chains(rng, n_chains, n_mono, F, L, per_bead=per)
+    n = wrapped.shape[1]
+    masses = rng.uniform(1, 20, n)
+    u = SyntheticUniverse(wrapped, dims, resindices=np.arange(n) // per, masses=masses)
+    r = SingleChainStructureFactor(u.atoms, grouping="residues", verbose=False,
+                                   batch_frames=3, **kw).run()
+    m = masses.reshape(-1, per)
+    wv = r._wavevectors
+    scsf = np.zeros(len(wv))
+    old = images = None
+    box = dims[:3].astype(np.float64)
+    for f in range(F):
+        p = wrapped[f].astype(np.float64).reshape(-1, per, 3)
+        com = (m[:, :, None] * p).sum(axis=1) / m.sum(axis=1, keepdims=True)
+        if old is None:
+            old, images = com.copy(), np.zeros(com.shape, dtype=int)
+        d = com - old
+        mask = np.abs(d) >= box / 2
+        images[mask] -= np.sign(d[mask]).astype(int)
+        old = com.copy()
+        com = com + images * box
+        for chain in com.reshape(n_chains, n_mono, 3):
+            arg = chain @ wv.T
+            scsf += np.sin(arg).sum(axis=0) ** 2 + np.cos(arg).sum(axis=0) ** 2
+    scsf /= n_chains * n_mono * F
+    want = np.array([scsf[np.isclose(q, r._wavenumbers)].mean()
+                     for q in r.results.wavenumbers])
+    np.testing.assert_allclose(r.results.scsf, want, rtol=1e-9, atol=1e-10)

@@ -262,6 +262,30 @@ def test_isclose_members_equals_the_reference_scan():
     assert any(len(m) > 1 for m in got)
 
 
+def test_feeder_stages_float64_results_of_positions_fn_unrounded():
+    """positions_fn results the reference keeps in float64 (centres of mass) are staged
+    as float64 when the analysis asks for it, and as float32 otherwise."""
+    u = synthetic.lj_fluid(40, 5, seed=9)
+    shift = 1000.0 + 1e-9
+
+    def fn(ts):
+        return [ts.positions[:10].astype(np.float64) + shift]
+    for dtype in (np.float64, np.float32):
+        feeder = base.FrameFeeder(u.trajectory, [np.arange(10)], np.arange(5), 2, fn,
+                                  dtype=dtype)
+        assert not feeder.zero_copy
+        n = 0
+        for b in feeder:
+            assert b.f64 == (dtype is np.float64) and b.strides == [30]
+            arr = b.keepalive[0][0]
+            assert arr.dtype == dtype and b.ptrs[0] == arr.ctypes.data
+            for k in range(b.n_frames):
+                want = u.trajectory.coordinates[n + k, :10].astype(np.float64) + shift
+                assert np.array_equal(arr[k], want.astype(dtype))
+            n += b.n_frames
+        assert n == 5
+
+
 def test_feeder_accepts_mdanalysis_memoryreader_layout():
     """A reader that keeps the trajectory in memory under MDAnalysis' MemoryReader names
     (coordinate_array / dimensions_array / stored_order) is fed without copies."""
