@@ -491,23 +491,12 @@ struct CellPairParams {
     unsigned long long sign2;     // 0x8000000080000000: the sign bits of a packed f32x2
 };
 
-// A warp's histogram -- (n_bins + 2) slots x 2^sb sub-bins, then 32 per-lane trash words --
-// occupies 2^B bytes at an address that is a multiple of 2^B, so that "base + offset" is
-// an OR (one LOP3 with the masking of the offset; an IMAD there sits on the FMA pipe)
-__host__ __device__ inline int cp_hist_log2(int n_bins, int sb)
-{
-    const size_t bytes = sizeof(unsigned) * ((((size_t)n_bins + 2) << sb) + 32);
-    int b = 4;
-    while (((size_t)1 << b) < bytes) ++b;
-    return b;
-}
-
 __host__ __device__ inline size_t cp_smem_bytes(int n_bins, int sb, int cap)
 {
     return 256 + align16(sizeof(double) * (n_bins + 1)) +
            (size_t)kCpWarps * 2 * (cap + kCpSlack) * sizeof(float4) +
-           sizeof(unsigned) * kCpWarps * kCpListCap + sizeof(int2) * kCpWarps * 2 * 32 +
-           ((size_t)(kCpWarps + 1) << cp_hist_log2(n_bins, sb));      // + alignment slack
+           sizeof(unsigned) * (size_t)kCpWarps * ((((size_t)n_bins + 2) << sb) + 32) +
+           sizeof(unsigned) * kCpWarps * kCpListCap + sizeof(int2) * kCpWarps * 2 * 32;
 }
 
 __device__ __forceinline__ void cp_mbar_init(unsigned bar, unsigned count)
@@ -592,22 +581,15 @@ __global__ void __launch_bounds__(kCpThreads, MDH_CP_BLOCKS)
     const int n_bins = P.n_bins;
     const FilterConst fc = P.fc;
     const int cap = P.cap, bufw = cap + kCpSlack;
-    const int hlog = cp_hist_log2(n_bins, fc.sb);
-    const int hwords = 1 << (hlog - 2);           // words between the warps' histograms
-    // layout: mbarriers | thresholds | candidate buffers | lists | ranges | histograms
-    // (aligned to their size)
+    const int hwords = ((n_bins + 2) << fc.sb) + 32;
+    // layout: mbarriers | thresholds | candidate buffers | histograms | lists | ranges
     unsigned long long *sBar = reinterpret_cast<unsigned long long *>(smem);
     double *sT = reinterpret_cast<double *>(smem + 256);
     float4 *sBuf =
         reinterpret_cast<float4 *>(smem + 256 + align16(sizeof(double) * (n_bins + 1)));
-    unsigned *sList = reinterpret_cast<unsigned *>(sBuf + (size_t)kCpWarps * 2 * bufw);
+    unsigned *sH = reinterpret_cast<unsigned *>(sBuf + (size_t)kCpWarps * 2 * bufw);
+    unsigned *sList = sH + kCpWarps * hwords;
     int2 *sRng = reinterpret_cast<int2 *>(sList + kCpWarps * kCpListCap);
-    unsigned *sH;
-    {
-        unsigned char *end = reinterpret_cast<unsigned char *>(sRng + kCpWarps * 2 * 32);
-        const unsigned a = (unsigned)__cvta_generic_to_shared(end);
-        sH = reinterpret_cast<unsigned *>(end + (((a + (1u << hlog) - 1u) >> hlog << hlog) - a));
-    }
     unsigned *sCount = reinterpret_cast<unsigned *>(smem + 128);      // [kCpWarps]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -629,15 +611,9 @@ __global__ void __launch_bounds__(kCpThreads, MDH_CP_BLOCKS)
     unsigned *wcount = sCount + warp;
     const unsigned hist32 = (unsigned)__cvta_generic_to_shared(sH + warp * hwords);
     const int shift = fc.k - fc.sb;
+    const unsigned hbase = hist32 - (LOWER ? 0u : ((fc.cbits >> shift) << 2));
     const unsigned span_l = LOWER ? fc.span : fc.cbits + fc.span;
-    // byte offset of a pair's word: t = u >> (shift - 2) is the word index times 4 with
-    // fraction bits below and, for !LOWER, the bits of 1.5*2^(23-k) above the histogram's
-    // 2^hlog bytes; one MIN sends everything beyond the range to the lane's trash word
-    // (every pair issues one unconditional RED; 5 of 6 candidates of a cut-off run land
-    // there and must not contend), one LOP3 masks and adds the warp's aligned base
-    const int tshift = shift - 2;
-    const unsigned tmax = ((((span_l >> shift) + (unsigned)lane)) << 2) | 3u;
-    const unsigned tmask = ((1u << hlog) - 1u) & ~3u;
+    const unsigned trash_w = (span_l >> shift) + (unsigned)lane;
     const unsigned fmask = (1u << fc.k) - 1u;
     const float scale = fc.scale;
     // self pairs of a same-group run (distance 0) are not evaluated: their bin is known
@@ -841,15 +817,15 @@ __global__ void __launch_bounds__(kCpThreads, MDH_CP_BLOCKS)
 #pragma unroll
                     for (int k = 0; k < IPT; ++k) {
                         const unsigned u = uu[k];
-                        unsigned t = min(u >> tshift, tmax);
-                        if (EXCL && gi[k] == __float_as_int(pj.w)) t = tmax;
+                        unsigned w = min(u >> shift, trash_w);
+                        if (EXCL && gi[k] == __float_as_int(pj.w)) w = trash_w;
                         if (SELF && jpos == ipos0 + k) {
                             // a particle with itself: never counted here, never uncertain
-                            t = tmax;
+                            w = trash_w;
                         } else {
                             vmin = min(vmin, u & fmask);
                         }
-                        red_shared_hot(lop3_and_or(t, tmask, hist32), wk[k]);
+                        red_shared_hot(hbase + (w << 2), wk[k]);
                         if (AUDIT && wk[k] != 0u && !(SELF && jpos == ipos0 + k)) {
                             const bool unc = (u & fmask) < ff.wlim, in = u < span_l;
                             const float4 a = buf[ipos0 + k];

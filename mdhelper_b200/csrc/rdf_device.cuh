@@ -367,11 +367,9 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
 // neighbours.  Returns the fixed-point bin coordinates u0, u1 (relative to slot 0 when
 // LOWER, else with the bits of 1.5*2^(23-k) still added).  Main loops and exact
 // re-evaluations go through this one function, so they see identical bits.
-template <bool LOWER>
-__device__ __forceinline__ void filter_eval2(f32x2 ax, f32x2 ay, f32x2 az, f32x2 bx, f32x2 by,
-                                             f32x2 bz, const FrameFilter &ff, float scale,
-                                             float offm, unsigned cbits, unsigned &u0,
-                                             unsigned &u1)
+// first half: packed squared minimum-image distances of two pairs
+__device__ __forceinline__ f32x2 filter_d2(f32x2 ax, f32x2 ay, f32x2 az, f32x2 bx, f32x2 by,
+                                           f32x2 bz, const FrameFilter &ff)
 {
     const f32x2 magic = pk2(kMagicF, kMagicF), nmagic = pk2(-kMagicF, -kMagicF);
     const f32x2 dx = add2(bx, ax);
@@ -383,7 +381,14 @@ __device__ __forceinline__ void filter_eval2(f32x2 ax, f32x2 ay, f32x2 az, f32x2
     const f32x2 mx = fma2(pk2(ff.nbox[0], ff.nbox[0]), rx, dx);
     const f32x2 my = fma2(pk2(ff.nbox[1], ff.nbox[1]), ry, dy);
     const f32x2 mz = fma2(pk2(ff.nbox[2], ff.nbox[2]), rz, dz);
-    const f32x2 d2 = fma2(mz, mz, fma2(my, my, mul2(mx, mx)));
+    return fma2(mz, mz, fma2(my, my, mul2(mx, mx)));
+}
+
+// second half: square roots and fixed-point bin coordinates
+template <bool LOWER>
+__device__ __forceinline__ void filter_bin2(f32x2 d2, float scale, float offm, unsigned cbits,
+                                            unsigned &u0, unsigned &u1)
+{
     float a, b, s0, s1;
     upk2(d2, a, b);
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(a));
@@ -392,6 +397,15 @@ __device__ __forceinline__ void filter_eval2(f32x2 ax, f32x2 ay, f32x2 az, f32x2
     upk2(e, a, b);
     u0 = __float_as_uint(a) - (LOWER ? cbits : 0u);
     u1 = __float_as_uint(b) - (LOWER ? cbits : 0u);
+}
+
+template <bool LOWER>
+__device__ __forceinline__ void filter_eval2(f32x2 ax, f32x2 ay, f32x2 az, f32x2 bx, f32x2 by,
+                                             f32x2 bz, const FrameFilter &ff, float scale,
+                                             float offm, unsigned cbits, unsigned &u0,
+                                             unsigned &u1)
+{
+    filter_bin2<LOWER>(filter_d2(ax, ay, az, bx, by, bz, ff), scale, offm, cbits, u0, u1);
 }
 
 // Per-frame parameters of the fp32 filter from the frame's box and coordinate extents

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, OCC)
     unsigned *sList = reinterpret_cast<unsigned *>(sJ + 2 * TILE);
     unsigned *sCount = sList + kListCap;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int it = blockIdx.x / P.n_jchunks;
     const int jc = blockIdx.x - it * P.n_jchunks;
     int jt0 = jc * P.jtiles_per_chunk;
@@ -217,17 +217,26 @@ __global__ void __launch_bounds__(kThreads, OCC)
         const int jn = min(TILE, P.n2 - jt * TILE);
         const float4 *tile = sJ + buf * TILE;
 
-        // Stage A: the packed fp32 arithmetic of NR tile rows against the IPT particles
-        // of this thread -> fixed-point bin coordinates (FMA pipe).
-        auto stage_a = [&](const float4 *pj, unsigned (*uu)[IPT], auto nr_tag) {
+        // Stage A1: packed squared distances of NR tile rows against the IPT particles of
+        // this thread (FMA pipe only).
+        auto stage_a1 = [&](const float4 *pj, f32x2 (*dd)[IPT / 2], auto nr_tag) {
             constexpr int NR = decltype(nr_tag)::value;
 #pragma unroll
             for (int r = 0; r < NR; ++r)
 #pragma unroll
                 for (int ip = 0; ip < IPT / 2; ++ip)
-                    filter_eval2<LOWER>(nx[ip], ny[ip], nz[ip], pk2(pj[r].x, pj[r].x),
-                                        pk2(pj[r].y, pj[r].y), pk2(pj[r].z, pj[r].z), ff, scale,
-                                        offm, fc.cbits, uu[r][2 * ip], uu[r][2 * ip + 1]);
+                    dd[r][ip] = filter_d2(nx[ip], ny[ip], nz[ip], pk2(pj[r].x, pj[r].x),
+                                          pk2(pj[r].y, pj[r].y), pk2(pj[r].z, pj[r].z), ff);
+        };
+        // Stage A2: square roots (MUFU) and fixed-point bin coordinates.
+        auto stage_a2 = [&](const f32x2 (*dd)[IPT / 2], unsigned (*uu)[IPT], auto nr_tag) {
+            constexpr int NR = decltype(nr_tag)::value;
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+#pragma unroll
+                for (int ip = 0; ip < IPT / 2; ++ip)
+                    filter_bin2<LOWER>(dd[r][ip], scale, offm, fc.cbits, uu[r][2 * ip],
+                                       uu[r][2 * ip + 1]);
         };
         // Stage B: histogram updates and the uncertainty test of NR rows (ALU pipe,
         // LSU), then one rarely taken branch for the uncertain pairs of the group.
@@ -280,35 +289,41 @@ __global__ void __launch_bounds__(kThreads, OCC)
                 }
             }
         };
-        // Software pipeline over pairs of rows: stage B of rows (jj, jj+1) is issued
-        // together with stage A of rows (jj+2, jj+3), so that every warp offers the
-        // scheduler FMA-pipe and ALU-pipe work at the same time; the rows after those
-        // are fetched from shared memory one more iteration ahead.  Rows up to
-        // TILE - 1 always exist (the packed arrays are padded), so the last iteration
-        // may evaluate two rows nobody uses.
+        // Software pipeline over pairs of rows.  What crosses the iteration boundary are the
+        // squared distances of rows (jj, jj+1): an iteration starts with their square roots
+        // (MUFU latency) and runs bin coordinates -> histogram updates (ALU pipe, LSU) next
+        // to the independent squared distances of rows (jj+2, jj+3) (FMA pipe), so that
+        // every warp offers both pipes work from its first to its last instruction; the
+        // rows after those are fetched from shared memory one more iteration ahead.  Rows
+        // up to TILE - 1 always exist (the packed arrays are padded), so the last
+        // iteration may evaluate two rows nobody uses.
         using two = std::integral_constant<int, 2>;
         const int jn2 = jn & ~1;
-        unsigned ua[2][IPT];
+        f32x2 da[2][IPT / 2];
         float4 cur[2] = {tile[0], tile[1]};
         float4 nxt[2] = {tile[2], tile[3]};
-        if (jn2 > 0) stage_a(cur, ua, two());
+        if (jn2 > 0) stage_a1(cur, da, two());
         for (int jj = 0; jj < jn2; jj += 2) {
-            unsigned ub[2][IPT];
+            unsigned ua[2][IPT];
+            f32x2 db[2][IPT / 2];
             const float4 nn[2] = {nxt[0], nxt[1]};
             const int jfetch = min(jj + 4, TILE - 2);
             nxt[0] = tile[jfetch];
             nxt[1] = tile[jfetch + 1];
-            stage_a(nn, ub, two());
+            stage_a2(da, ua, two());
+            stage_a1(nn, db, two());
             stage_b(cur, ua, jj, two());
             cur[0] = nn[0]; cur[1] = nn[1];
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int ii = 0; ii < IPT; ++ii) ua[r][ii] = ub[r][ii];
+                for (int ip = 0; ip < IPT / 2; ++ip) da[r][ip] = db[r][ip];
         }
         if (jn2 < jn) {
+            f32x2 d1[1][IPT / 2];
             unsigned u1[1][IPT];
-            stage_a(tile + jn2, u1, std::integral_constant<int, 1>());
+            stage_a1(tile + jn2, d1, std::integral_constant<int, 1>());
+            stage_a2(d1, u1, std::integral_constant<int, 1>());
             stage_b(tile + jn2, u1, jn2, std::integral_constant<int, 1>());
         }
         __syncthreads();
@@ -431,10 +446,8 @@ bool rdf_filter_configure(RdfState &R, const double *thr, double sqrt_err)
 {
     R.filter_ok = false;
     const int n_bins = R.n_bins;
-    // 2^lg >= slots + 32: the slot field of the bin coordinate, with room for the cell-pair
-    // kernel's 32 trash words behind the slots (rdf_cells.cu: cp_hist_log2)
     int lg = 0;
-    while ((1 << lg) < n_bins + 2 + 32) ++lg;
+    while ((1 << lg) < n_bins + 2) ++lg;
     const int k = std::min(16, 22 - lg);
     if (k < 9) return false;
     if (!(sqrt_err >= 0.0 && sqrt_err <= 1.0 / 4194304.0)) return false;   // 2^-22

@@ -1,0 +1,20 @@
+#!/bin/bash
+# round 2, GPU call T: filter kernel loop variants (3-stage pipeline vs 2-stage), IPT / occupancy retune
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+run() {  # name, lib, tune
+  if [ -n "$2" ]; then export MDH_B200_LIB=$PWD/mdhelper_b200/libmdh_b200_$2.so; else unset MDH_B200_LIB; fi
+  MDH_TUNE="$3" timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-strong --no-secondary > gpurun_out/t_$1.json 2> gpurun_out/t_$1.err
+  python -c "
+import json
+d=json.loads(open('gpurun_out/t_$1.json').read().strip().splitlines()[-1]); print('$1', d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['launch_ms'])"
+}
+timeout 300 python -m pytest tests/test_gpu_rdf.py -m gpu -q --timeout 150 -x -k "not cells and not triclinic" > gpurun_out/t_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_pytest.log
+run p3 "" ""
+run p2 p2 ""
+run p3_b "" ""
+run p3_ipt2occ2 "" "ipt=2,occ=2"
+run p3_ipt2occ3 "" "ipt=2,occ=3"
+run p3_ipt4occ3 "" "ipt=4,occ=3"
+run p2_ipt2occ3 p2 "ipt=2,occ=3"
+tail -3 gpurun_out/t_pytest.log
