@@ -5,8 +5,8 @@
 // only when a rigorous error bound proves that the reference's fp64 distance falls in
 // the same bin; every other pair ("uncertain": within the bound of a bin edge, about
 // 1 in 1,500 for the benchmark configurations) is re-evaluated with the exact
-// arithmetic of rdf_device.cuh::pair_d2 and corrected.  The fp32 path costs ~17
-// issue slots per pair (8 packed f32x2 instructions on the FMA pipe, ~6 on the ALU
+// arithmetic of rdf_device.cuh::pair_d2 and corrected.  The fp32 path costs ~16
+// issue slots per pair (8 packed f32x2 instructions on the FMA pipe, ~5 on the ALU
 // pipe, one MUFU, one RED) instead of 21 FP64-pipe instructions plus conversions (46
 // in total) -- it removes the FP64 pipe as the bound.
 //
