@@ -83,7 +83,7 @@ def parse():
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--strong", default="cfg4,cfg3,cfg5",
                     help="comma-separated strong-scaling workloads to run")
-    ap.add_argument("--strong-reps", type=int, default=3)
+    ap.add_argument("--strong-reps", type=int, default=5)
     ap.add_argument("--strong-only", action="store_true",
                     help="skip the headline and the secondary; only the strong passes")
     ap.add_argument("--hist", default="auto")
@@ -873,6 +873,7 @@ def bench_strong(which, args, rank, world, local, dist, torch):
         kern["sq_kernel_ms_rank0"] = sf._ctx.kernel_time()[2] / len(times)
     out = {"workload": name, "n_gpus": world, "frames": n_frames, "scaling": "strong",
            "passes_timed": len(times), "e2e_s_mean": mean, "e2e_s_best": best,
+           "e2e_s_passes": [round(t, 6) for t in times],
            "frames_per_s": n_frames / mean,
            "h2d_bytes_per_pass": n_frames * n_part * 12,
            "api": ("CombinedAnalysis(rdf, ssf).run()" if isinstance(job, CombinedAnalysis)

@@ -58,7 +58,7 @@ void DevBuf::release()
     cap = 0;
 }
 
-std::vector<int> mdh_plan_pieces(int n_frames, double bytes_per_frame)
+std::vector<int> mdh_plan_pieces(int n_frames, double bytes_per_frame, double copy_over_kernel)
 {
     std::vector<int> out;
     const double bpf = std::max(1.0, bytes_per_frame);
@@ -67,12 +67,49 @@ std::vector<int> mdh_plan_pieces(int n_frames, double bytes_per_frame)
     while (done < n_frames) {
         int nf = (int)std::max(1.0, std::floor(want / bpf));
         const int left = n_frames - done;
-        if (left < nf + nf / 2) nf = left;         // no short tail piece
+        if (left <= nf) {
+            nf = left;
+        } else if (left < nf + nf / 2) {
+            // A short remainder joins the last piece (every launch costs the kernels a
+            // partial round of work units) -- unless the measured rates say that the
+            // copy of the merged piece would outlast the kernels of the piece before it
+            // (two staging slots: a copy runs beside the previous piece's kernels only).
+            // Then the remainder is cut in halves.  Seen with eight ranks on one host:
+            // some GPUs get ~25 GB/s, and a merged tail of 3x its predecessor left cfg4's
+            // S(q) kernels waiting 0.7 ms of a 7 ms pass.
+            const int prev = out.empty() ? 0 : out.back();
+            const bool fits = copy_over_kernel <= 0.0 ||
+                              (double)left * copy_over_kernel <= 0.9 * (double)prev;
+            nf = fits ? left : (left + 1) / 2;
+        }
         out.push_back(nf);
         done += nf;
         want = std::min(32e6, want * 2.0);
     }
     return out;
+}
+
+int RateProbe::ensure()
+{
+    for (cudaEvent_t &e : ev)
+        if (!e) MDH_CUDA(cudaEventCreate(&e));
+    return MDH_OK;
+}
+
+void RateProbe::learn()
+{
+    if (!pending) return;
+    if (cudaEventQuery(ev[1]) != cudaSuccess || cudaEventQuery(ev[3]) != cudaSuccess) {
+        cudaGetLastError();                     // not ready: keep the old estimate
+        return;
+    }
+    float tc = 0.f, tk = 0.f;
+    if (cudaEventElapsedTime(&tc, ev[0], ev[1]) == cudaSuccess &&
+        cudaEventElapsedTime(&tk, ev[2], ev[3]) == cudaSuccess && tk > 0.f)
+        copy_over_kernel = (double)tc / (double)tk;
+    else
+        cudaGetLastError();
+    pending = false;
 }
 
 int KernelTimer::begin(cudaStream_t s)

@@ -131,6 +131,20 @@ struct SqWorkItem {        // one thread's tile of the lattice kernels: two (nx,
 constexpr int kSqTM = 2;   // columns per thread
 constexpr int kSqTN = 8;   // nz values per thread
 
+// Two event pairs around the copy and the kernels of the last piece of a host call; the
+// next call reads them (if they have completed) to learn the ratio above.
+struct RateProbe {
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool pending = false;
+    double copy_over_kernel = 0.0;
+    RateProbe() = default;
+    RateProbe(const RateProbe &) = delete;
+    RateProbe &operator=(const RateProbe &) = delete;
+    ~RateProbe() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
+    int ensure();
+    void learn();               // non-blocking
+};
+
 struct SqState {
     bool configured = false;
     int64_t n_total = 0;
@@ -154,6 +168,7 @@ struct SqState {
     DevBuf chunks;         // int4[n_chunks]: {start, end, rho_row, 0}
     int n_chunks = 0, chunk_len = 0;
     DevBuf raw[2];         // float[F][n][3] (or double) staging for host input, one per stager slot
+    RateProbe probe;       // copy vs kernel rate of the last host call (piece planning)
     DevBuf split;          // float[2F][n][3]: float64 input as float32 + negated remainder
     DevBuf split_vmap;     // int4[F]: {f, F + f, 0, 0}
     DevBuf tab;            // phase-factor tables of one group of frames
@@ -225,7 +240,11 @@ struct HostStager {
 // kernels of the previous one.  The pieces grow geometrically: the first copy -- the only
 // one nothing can hide -- is short (~2 MB), later ones are long enough (up to ~32 MB) for
 // their kernels to run at full efficiency.
-std::vector<int> mdh_plan_pieces(int n_frames, double bytes_per_frame);
+// copy_over_kernel: measured (copy time per frame) / (kernel time per frame) of an earlier
+// call with the same configuration, 0 = unknown.
+std::vector<int> mdh_plan_pieces(int n_frames, double bytes_per_frame,
+                                 double copy_over_kernel = 0.0);
+
 
 // Frame-strided copy: one contiguous transfer when the frames are adjacent on both sides
 // (a 2-D copy of rows that happen to be contiguous is split by the driver), else a 2-D copy.

@@ -1121,6 +1121,8 @@ int sq_configure_impl(mdh_ctx *c, int64_t n_total, int n_groups, const int64_t *
                 "sq: a lattice kernel was requested without lattice_n / lattice_b");
 
     S.configured = false;
+    S.probe.pending = false;              // rates of another configuration do not carry over
+    S.probe.copy_over_kernel = 0.0;
     S.n_total = n_total; S.n_groups = n_groups; S.n_q = n_q; S.n_pairs = n_pairs;
     S.n_rho = all ? 1 : n_groups;
     S.group_offsets.assign(goff, goff + n_groups + 1);
@@ -1387,7 +1389,7 @@ __global__ void sq_split_kernel(const double *__restrict__ src, int64_t src_stri
 
 template <typename T>
 static int sq_accumulate_piece(mdh_ctx *c, const T *pos, int64_t stride, int location,
-                               int n_frames, int nominal_frames);
+                               int n_frames, int nominal_frames, bool probe);
 
 template <typename T>
 static int sq_accumulate_any(mdh_ctx *c, const T *pos, int64_t stride, int location,
@@ -1407,15 +1409,20 @@ static int sq_accumulate_any(mdh_ctx *c, const T *pos, int64_t stride, int locat
     // the previous one (compute stream); the particle chunks are laid out once, for the
     // whole call
     if (location == MDH_HOST) {
+        S.probe.learn();
+        const std::vector<int> pieces = mdh_plan_pieces(
+            n_frames, 3.0 * sizeof(T) * (double)S.n_total, S.probe.copy_over_kernel);
         int f0 = 0;
-        for (int nf : mdh_plan_pieces(n_frames, 3.0 * sizeof(T) * (double)S.n_total)) {
-            if (int rc = sq_accumulate_piece(c, pos + (int64_t)f0 * stride, stride, location, nf,
-                                             n_frames)) return rc;
-            f0 += nf;
+        for (size_t k = 0; k < pieces.size(); ++k) {
+            // the last piece of a call with several pieces is the rate probe of the next call
+            const bool probe = pieces.size() > 1 && k + 1 == pieces.size() && !S.probe.pending;
+            if (int rc = sq_accumulate_piece(c, pos + (int64_t)f0 * stride, stride, location,
+                                             pieces[k], n_frames, probe)) return rc;
+            f0 += pieces[k];
         }
         return MDH_OK;
     }
-    return sq_accumulate_piece(c, pos, stride, location, n_frames, n_frames);
+    return sq_accumulate_piece(c, pos, stride, location, n_frames, n_frames, false);
 }
 
 int sq_accumulate_impl(mdh_ctx *c, const float *pos, int64_t stride, int location,
@@ -1434,20 +1441,25 @@ int sq_accumulate_f64_impl(mdh_ctx *c, const double *pos, int64_t stride, int lo
 // its pieces reuse the layout instead of rebuilding it)
 template <typename T>
 static int sq_accumulate_piece(mdh_ctx *c, const T *pos, int64_t stride, int location,
-                               int n_frames, int nominal_frames)
+                               int n_frames, int nominal_frames, bool probe)
 {
     constexpr bool kF64 = sizeof(T) == 8;
     SqState &S = c->sq;
     const T *dsrc = pos;
     int64_t dstride = stride;
     int slot = 0;
+    probe = probe && location == MDH_HOST;
+    if (probe)
+        if (int rc = S.probe.ensure()) return rc;
     if (location == MDH_HOST) {
         if (int rc = c->stager.acquire(&slot)) return rc;
         DevBuf &raw = S.raw[slot];
         if (int rc = raw.reserve(sizeof(T) * 3 * S.n_total * n_frames)) return rc;
+        if (probe) MDH_CUDA(cudaEventRecord(S.probe.ev[0], c->stager.copy));
         MDH_CUDA(mdh_copy_frames(raw.p, sizeof(T) * 3 * S.n_total, pos,
                                    sizeof(T) * stride, sizeof(T) * 3 * S.n_total,
                                    n_frames, cudaMemcpyHostToDevice, c->stager.copy));
+        if (probe) MDH_CUDA(cudaEventRecord(S.probe.ev[1], c->stager.copy));
         if (int rc = c->stager.publish(c->stream, slot)) return rc;
         dsrc = raw.as<T>();
         dstride = 3 * S.n_total;
@@ -1468,6 +1480,7 @@ static int sq_accumulate_piece(mdh_ctx *c, const T *pos, int64_t stride, int loc
     }
 
     if (int rc = c->t_sq.begin(c->stream)) return rc;
+    if (probe) MDH_CUDA(cudaEventRecord(S.probe.ev[2], c->stream));
     if constexpr (kF64) {
         const int64_t n3 = 3 * S.n_total;
         dim3 grid((unsigned)std::min<int64_t>((n3 + 255) / 256, 1024), n_frames);
@@ -1482,6 +1495,10 @@ static int sq_accumulate_piece(mdh_ctx *c, const T *pos, int64_t stride, int loc
     if (S.n_chains > 0) {
         // the kernel has added |rho_chain|^2 to the accumulator itself
         S.rho_frames = 0;
+        if (probe) {
+            MDH_CUDA(cudaEventRecord(S.probe.ev[3], c->stream));
+            S.probe.pending = true;
+        }
         if (location == MDH_HOST)
             if (int rc = c->stager.retire(c->stream, slot)) return rc;
         return c->t_sq.end(c->stream);
@@ -1493,6 +1510,10 @@ static int sq_accumulate_piece(mdh_ctx *c, const T *pos, int64_t stride, int loc
     MDH_CUDA(cudaGetLastError());
     c->launches++;
     S.rho_frames = n_frames;
+    if (probe) {
+        MDH_CUDA(cudaEventRecord(S.probe.ev[3], c->stream));
+        S.probe.pending = true;
+    }
     if (location == MDH_HOST)
         if (int rc = c->stager.retire(c->stream, slot)) return rc;
     return c->t_sq.end(c->stream);
