@@ -509,6 +509,10 @@ def test_float64_coordinates_are_not_rounded_to_float32(kernel):
     ctx.sq_accumulate(pos.astype(np.float32), 3 * n, F)
     rounded = ctx.sq_fetch()[0]
     assert np.abs(rounded - want).max() > 1e3 * np.abs(got - want).max()
+    # float32-valued doubles: the same phases as the float32 entry point
+    ctx.sq_reset()
+    ctx.sq_accumulate(pos.astype(np.float32).astype(np.float64), 3 * n, F, f64=True)
+    np.testing.assert_allclose(ctx.sq_fetch()[0], rounded, rtol=1e-12, atol=1e-9)
     ctx.close()
 
 
