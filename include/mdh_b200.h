@@ -322,6 +322,15 @@ int mdh_isf_accumulate_f64(mdh_ctx *ctx, const double *pos, int64_t frame_stride
 int mdh_isf_fetch(mdh_ctx *ctx, double *cisf /* [n_lags][n_pairs][n_q] */,
                   double *iisf /* [n_lags][n_rho][n_q] or NULL */);
 
+/*
+ * How a host batch is cut into pieces (copy of piece k+1 beside the kernels of piece k):
+ * diagnostic view of the planner behind mdh_rdf_accumulate / mdh_sq_accumulate with
+ * MDH_HOST, no device needed.  copy_over_kernel = measured copy time / kernel time per
+ * frame (0: unknown).  Writes at most cap piece lengths (frames) and their number.
+ */
+int mdh_stage_plan(int n_frames, double bytes_per_frame, double copy_over_kernel,
+                   int32_t *pieces, int cap, int32_t *n_pieces);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,7 @@ SIGNATURES = {
     "mdh_isf_configure": (_i32, [_p, _i32, _i32, _i64]),
     "mdh_isf_accumulate": (_i32, [_p, _p, _i64, _i32, _i32]),
     "mdh_isf_accumulate_f64": (_i32, [_p, _p, _i64, _i32, _i32]),
+    "mdh_stage_plan": (_i32, [_i32, _f64, _f64, _p, _i32, _p]),
     "mdh_isf_fetch": (_i32, [_p, _p, _p]),
 }
 
@@ -135,6 +136,17 @@ def sq_plan(lattice_n) -> dict:
     return {"items": stats[0], "tiles": stats[1], "max_scheduler_tiles": stats[2],
             "schedulers": stats[3], "warps_per_block": stats[4], "smem_bytes": stats[5],
             "coverage": cover, "pair_rule_violations": bad.value}
+
+
+def stage_plan(n_frames: int, bytes_per_frame: float, copy_over_kernel: float = 0.0) -> list:
+    """Frames per piece of a host batch (``mdh_stage_plan``; no device needed): the copy of
+    piece k+1 runs beside the kernels of piece k.  ``copy_over_kernel``: measured copy time
+    over kernel time per frame, 0 when unknown."""
+    pieces = (ctypes.c_int32 * max(1, int(n_frames)))()
+    n = ctypes.c_int32(0)
+    check(lib().mdh_stage_plan(int(n_frames), float(bytes_per_frame), float(copy_over_kernel),
+                               pieces, len(pieces), ctypes.byref(n)))
+    return list(pieces[:n.value])
 
 
 class Context:

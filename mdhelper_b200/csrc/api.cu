@@ -551,6 +551,19 @@ int mdh_isf_accumulate_f64(mdh_ctx *c, const double *pos, int64_t frame_stride, 
     return isf_accumulate_f64_impl(c, pos, frame_stride, location, n_frames);
 }
 
+int mdh_stage_plan(int n_frames, double bytes_per_frame, double copy_over_kernel,
+                   int32_t *pieces, int cap, int32_t *n_pieces)
+{
+    if (n_frames < 0 || !pieces || !n_pieces || cap < 0) {
+        mdh_set_error("stage_plan: invalid argument");
+        return MDH_EINVAL;
+    }
+    const std::vector<int> p = mdh_plan_pieces(n_frames, bytes_per_frame, copy_over_kernel);
+    *n_pieces = (int32_t)p.size();
+    for (size_t k = 0; k < p.size() && (int)k < cap; ++k) pieces[k] = p[k];
+    return MDH_OK;
+}
+
 int mdh_isf_fetch(mdh_ctx *c, double *cisf, double *iisf)
 {
     CTX_GUARD(c);

@@ -508,3 +508,29 @@ def test_staged_feeder_reads_an_on_disk_style_reader(tmp_path):
                 np.testing.assert_array_equal(a, pos[f][sel])
         seen += b.n_frames
     assert seen == 5 and u.trajectory.reads >= 5
+
+
+def test_staging_plan_ramp_and_tail():
+    """How host batches are cut into pieces (mdh_stage_plan): a short first copy, pieces
+    doubling up to ~32 MB, every frame exactly once; a remainder below half a piece joins
+    the last piece unless the measured copy/kernel ratio says its copy would outlast the
+    kernels before it -- then it is cut in halves."""
+    from mdhelper_b200 import _lib
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        n = int(rng.integers(1, 3000))
+        bpf = float(10 ** rng.uniform(2, 7.5))
+        ratio = float(rng.choice([0.0, 0.1, 0.3, 0.6, 1.5]))
+        p = _lib.stage_plan(n, bpf, ratio)
+        assert sum(p) == n and min(p) >= 1
+        assert p[0] < 1.5 * max(1, int(2e6 // bpf)) + 1          # the copy nothing can hide
+        cap = max(1, int(32e6 // bpf))
+        assert max(p) < 1.5 * cap + 1
+        for a, b in zip(p[:-2], p[1:-1]):          # the ramp never more than doubles (+ rounding)
+            assert b <= 2 * a + 1
+    # cfg4's 125-frame call (600 kB per frame): merged tail by default and on a fast link,
+    # halved tail when the copy is slow against the kernels
+    assert _lib.stage_plan(125, 600e3) == [3, 6, 13, 26, 77]
+    assert _lib.stage_plan(125, 600e3, 0.25) == [3, 6, 13, 26, 77]
+    assert _lib.stage_plan(125, 600e3, 0.54) == [3, 6, 13, 26, 39, 38]
+    assert _lib.stage_plan(0, 600e3) == []
