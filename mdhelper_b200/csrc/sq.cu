@@ -1412,6 +1412,17 @@ static int sq_accumulate_any(mdh_ctx *c, const T *pos, int64_t stride, int locat
         S.probe.learn();
         const std::vector<int> pieces = mdh_plan_pieces(
             n_frames, 3.0 * sizeof(T) * (double)S.n_total, S.probe.copy_over_kernel);
+        // staging of the largest piece up front: a buffer that grows between pieces would
+        // be freed (a device synchronisation) while the previous piece is still running
+        const int longest = *std::max_element(pieces.begin(), pieces.end());
+        for (int slot = 0; slot < 2 && pieces.size() > 1; ++slot)
+            if (int rc = S.raw[slot].reserve(sizeof(T) * 3 * S.n_total * (size_t)longest))
+                return rc;
+        if (sizeof(T) == 8) {
+            if (int rc = S.split.reserve(sizeof(float) * 6 * S.n_total * (size_t)longest))
+                return rc;
+            if (int rc = S.split_vmap.reserve(sizeof(int4) * (size_t)longest)) return rc;
+        }
         int f0 = 0;
         for (size_t k = 0; k < pieces.size(); ++k) {
             // the last piece of a call with several pieces is the rate probe of the next call
