@@ -44,6 +44,10 @@ using namespace rdfdev;
 
 namespace {
 
+#ifndef MDH_FILTER_ROWS
+#define MDH_FILTER_ROWS 2
+#endif
+
 constexpr int kListCap = 3072;           // deferred entries per block and tile
 
 // shared memory of a block: histogram ((n_bins + 2) slots x 2^cb columns, first, so that
@@ -240,9 +244,9 @@ __global__ void __launch_bounds__(kThreads, OCC)
         };
         // Stage B: histogram updates and the uncertainty test of NR rows (ALU pipe,
         // LSU), then one rarely taken branch for the uncertain pairs of the group.
-        auto stage_b = [&](const float4 *pj, const unsigned (*uu)[IPT], int jj, auto nr_tag) {
+        auto stage_hist = [&](const float4 *pj, const unsigned (*uu)[IPT], unsigned *vmin,
+                              auto nr_tag) {
             constexpr int NR = decltype(nr_tag)::value;
-            unsigned vmin[NR];
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
                 vmin[r] = 0xffffffffu;
@@ -272,6 +276,10 @@ __global__ void __launch_bounds__(kThreads, OCC)
                     }
                 }
             }
+        };
+        // the rarely taken branch: rows with an uncertain pair go on the block's list
+        auto stage_push = [&](const unsigned *vmin, int jj, auto nr_tag) {
+            constexpr int NR = decltype(nr_tag)::value;
             unsigned vall = vmin[0];
 #pragma unroll
             for (int r = 1; r < NR; ++r) vall = min(vall, vmin[r]);
@@ -289,6 +297,12 @@ __global__ void __launch_bounds__(kThreads, OCC)
                 }
             }
         };
+        auto stage_b = [&](const float4 *pj, const unsigned (*uu)[IPT], int jj, auto nr_tag) {
+            constexpr int NR = decltype(nr_tag)::value;
+            unsigned vmin[NR];
+            stage_hist(pj, uu, vmin, nr_tag);
+            stage_push(vmin, jj, nr_tag);
+        };
         // Software pipeline over pairs of rows.  What crosses the iteration boundary are the
         // squared distances of rows (jj, jj+1): an iteration starts with their square roots
         // (MUFU latency) and runs bin coordinates -> histogram updates (ALU pipe, LSU) next
@@ -303,7 +317,8 @@ __global__ void __launch_bounds__(kThreads, OCC)
         float4 cur[2] = {tile[0], tile[1]};
         float4 nxt[2] = {tile[2], tile[3]};
         if (jn2 > 0) stage_a1(cur, da, two());
-        for (int jj = 0; jj < jn2; jj += 2) {
+        // one step of the pipeline: rows (jj, jj+1) leave it, rows (jj+2, jj+3) enter
+        auto step = [&](int jj, unsigned *vmin) {
             unsigned ua[2][IPT];
             f32x2 db[2][IPT / 2];
             const float4 nn[2] = {nxt[0], nxt[1]};
@@ -312,12 +327,28 @@ __global__ void __launch_bounds__(kThreads, OCC)
             nxt[1] = tile[jfetch + 1];
             stage_a2(da, ua, two());
             stage_a1(nn, db, two());
-            stage_b(cur, ua, jj, two());
+            stage_hist(cur, ua, vmin, two());
             cur[0] = nn[0]; cur[1] = nn[1];
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
                 for (int ip = 0; ip < IPT / 2; ++ip) da[r][ip] = db[r][ip];
+        };
+        int jj = 0;
+#if MDH_FILTER_ROWS == 4
+        // two steps per trip, ONE test for uncertain pairs behind them: no branch between
+        // the steps, so the second step's arithmetic overlaps the first step's updates
+        for (; jj + 4 <= jn2; jj += 4) {
+            unsigned vmin[4];
+            step(jj, vmin);
+            step(jj + 2, vmin + 2);
+            stage_push(vmin, jj, std::integral_constant<int, 4>());
+        }
+#endif
+        for (; jj < jn2; jj += 2) {
+            unsigned vmin[2];
+            step(jj, vmin);
+            stage_push(vmin, jj, two());
         }
         if (jn2 < jn) {
             f32x2 d1[1][IPT / 2];
