@@ -43,6 +43,14 @@ def _worker(rank, world_size, port, out_dir):
                 assert alone.n_local_frames == 5
             assert np.array_equal(alone.results.counts, r.results.counts)
         assert world() == (rank, 2)
+        # the collective itself: exact int64 sums, float64 sums, the caller's array untouched
+        from mdhelper_b200.analysis.base import all_reduce_sum
+        mine = np.arange(6, dtype=np.int64).reshape(2, 3) * (rank + 1) + (1 << 40)
+        keep = mine.copy()
+        total = all_reduce_sum(mine)
+        assert np.array_equal(mine, keep) and total.shape == (2, 3)
+        assert np.array_equal(total, np.arange(6).reshape(2, 3) * 3 + (1 << 41))
+        assert all_reduce_sum(np.array([0.25 * (rank + 1)]))[0] == 0.75
         # a ring trajectory: 12 frames cycling through the 5 in memory, split 6 + 6
         ur = SyntheticUniverse(g["positions"], g["dims"], n_frames=12)
         rr = FakeRDF(ur.atoms, n_bins=int(g["n_bins"]), range=tuple(g["range"]),
