@@ -357,11 +357,66 @@ def com_cases(S):
     np.savez_compressed(OUT / "com_ref.npz", **out)
 
 
+def f64_cases(S):
+    """Positions the reference keeps in float64 on the Fourier path, from its REAL classes:
+    IntermediateScatteringFunction with groupings="residues" (centres of mass and their
+    displacements, structure.py:1927-2033) and SingleChainStructureFactor with
+    grouping="residues" (equal-sized monomers through center_of_mass' array form,
+    polymer.py:1080-1093), wrapped and unwrapped over several box lengths."""
+    P = ref_harness.polymer()
+    rng = np.random.default_rng(20260651)
+    out = {}
+    # ISF: 120 residues of 3 atoms, two groups, drifting coordinates
+    n_res, per, F, L = 120, 3, 8, np.float32(13.0)
+    n = n_res * per
+    pos = (rng.random((1, n, 3)) * float(L)
+           + rng.normal(0, 0.25, (F, n, 3)).cumsum(axis=0)).astype(np.float32)
+    res = np.arange(n) // per
+    masses = rng.choice([1.008, 12.011, 15.999], n)
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    u = SyntheticUniverse(pos, dims, resindices=res, segindices=res // 10, masses=masses)
+    n_a = (n_res // 3) * per
+    a, b = u.select(slice(0, n_a)), u.select(slice(n_a, n))
+    r = S.IntermediateScatteringFunction([a, b], groupings="residues", mode="partial",
+                                         n_points=5, n_lags=4, incoherent=True, dt=1.0,
+                                         verbose=False).run()
+    out.update(isf_positions=pos, isf_dims=dims, isf_resindices=res, isf_masses=masses,
+               isf_n_a=n_a, isf_cisf=r.results.cisf, isf_iisf=r.results.iisf,
+               isf_wavenumbers=r.results.wavenumbers)
+    # SCSF: 10 chains of 12 monomers of 3 atoms, drifting several boxes in 7 frames
+    n_chains, n_mono, F, L = 10, 12, 7, np.float32(9.0)
+    start = rng.random((n_chains, 1, 3)) * float(L)
+    chain = start + rng.normal(0, 0.5, (n_chains, n_mono, 3)).cumsum(axis=1)
+    drift = np.arange(F)[:, None, None, None] * np.array([3.7, -2.9, 2.3])
+    true = chain[None] + drift + rng.normal(0, 0.05, (F, n_chains, n_mono, 3))
+    true = np.repeat(true.reshape(F, -1, 3), per, axis=1)
+    true = true + rng.normal(0, 0.1, true.shape)
+    wrapped = np.mod(true, float(L)).astype(np.float32)
+    wrapped[wrapped >= L] = 0.0
+    n = wrapped.shape[1]
+    masses = rng.uniform(1, 20, n)
+    dims = np.array([L, L, L, 90, 90, 90], np.float32)
+    u = SyntheticUniverse(wrapped, dims, resindices=np.arange(n) // per, masses=masses)
+    out.update(scsf_positions=wrapped, scsf_dims=dims, scsf_masses=masses, scsf_per=per,
+               scsf_n_chains=n_chains, scsf_n_monomers=n_mono)
+    for unwrap in (False, True):
+        r = P.SingleChainStructureFactor(u.atoms, grouping="residues", n_points=5,
+                                         n_chains=n_chains, n_monomers=n_mono, unwrap=unwrap,
+                                         verbose=False).run()
+        out[f"scsf_res_unwrap{int(unwrap)}"] = r.results.scsf
+        out["scsf_wavenumbers"] = r.results.wavenumbers
+    np.savez_compressed(OUT / "f64_ref.npz", **out)
+    print("f64", out["isf_cisf"].shape, out["scsf_res_unwrap1"].shape,
+          np.abs(out["scsf_res_unwrap0"] - out["scsf_res_unwrap1"]).max())
+
+
 if __name__ == "__main__":
     S = ref_harness.load()
-    which = sys.argv[1:] or ["kat", "rdf", "post", "sq", "isf", "scsf", "com"]
+    which = sys.argv[1:] or ["kat", "rdf", "post", "sq", "isf", "scsf", "com", "f64"]
     if "com" in which:
         com_cases(S)
+    if "f64" in which:
+        f64_cases(S)
     if "kat" in which:
         kat_radial_histogram(S)
     if "rdf" in which:

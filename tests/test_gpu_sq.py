@@ -619,3 +619,35 @@ def test_scsf_of_unwrapped_chains_far_from_the_origin():
     want = np.array([scsf[np.isclose(q, r._wavenumbers)].mean()
                      for q in r.results.wavenumbers])
     np.testing.assert_allclose(r.results.scsf, want, rtol=1e-9, atol=1e-10)
+
+
+def test_float64_paths_against_the_reference_classes(golden):
+    """tests/golden/f64_ref.npz: the reference's REAL IntermediateScatteringFunction with
+    groupings="residues" and SingleChainStructureFactor with grouping="residues" (wrapped,
+    and unwrapped over several box lengths) -- positions the reference keeps in float64."""
+    from mdhelper_b200.analysis.polymer import SingleChainStructureFactor
+    from mdhelper_b200.universe import SyntheticUniverse
+    g = golden("f64_ref")
+    u = SyntheticUniverse(g["isf_positions"], g["isf_dims"], resindices=g["isf_resindices"],
+                          masses=g["isf_masses"])
+    n_a, n = int(g["isf_n_a"]), u.atoms.n_atoms
+    a, b = u.select(slice(0, n_a)), u.select(slice(n_a, n))
+    r = _S().IntermediateScatteringFunction([a, b], groupings="residues", mode="partial",
+                                            n_points=5, n_lags=4, incoherent=True, dt=1.0,
+                                            verbose=False, batch_frames=3).run()
+    np.testing.assert_allclose(r.results.wavenumbers, g["isf_wavenumbers"], rtol=1e-12)
+    np.testing.assert_allclose(r.results.cisf, g["isf_cisf"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(r.results.iisf, g["isf_iisf"], rtol=1e-9, atol=1e-10)
+
+    per = int(g["scsf_per"])
+    pos = g["scsf_positions"]
+    u = SyntheticUniverse(pos, g["scsf_dims"], resindices=np.arange(pos.shape[1]) // per,
+                          masses=g["scsf_masses"])
+    for unwrap in (False, True):
+        s = SingleChainStructureFactor(u.atoms, grouping="residues", n_points=5,
+                                       n_chains=int(g["scsf_n_chains"]),
+                                       n_monomers=int(g["scsf_n_monomers"]), unwrap=unwrap,
+                                       verbose=False, batch_frames=3).run()
+        np.testing.assert_allclose(s.results.wavenumbers, g["scsf_wavenumbers"], rtol=1e-12)
+        np.testing.assert_allclose(s.results.scsf, g[f"scsf_res_unwrap{int(unwrap)}"],
+                                   rtol=1e-9, atol=1e-10)
