@@ -283,3 +283,36 @@ def test_grid_search_moves_coordinates_into_the_cell_in_float32():
                                                     method="bruteforce"))
     # the method rule: small cut-off -> grid search
     assert np.array_equal(grid, rp.radial_histogram(p, p, 40, (0.0, 3.0), dims))
+
+
+def test_isf_port_on_float64_centres_matches_the_reference(golden):
+    """tests/golden/f64_ref.npz (the reference's real IntermediateScatteringFunction with
+    groupings="residues"): the port's sliding window, fed the float64 centres of mass of
+    the residues, reproduces it -- the checker of the GPU path that keeps those centres
+    in float64."""
+    from mdhelper_b200.universe import SyntheticUniverse
+
+    class Centres:
+        def __init__(self, group):
+            self._g = group
+            _, self._inv = np.unique(group.resindices, return_inverse=True)
+            self._m = np.asarray(group.masses, dtype=np.float64)
+            self.n_atoms = int(self._inv.max()) + 1
+
+        @property
+        def positions(self):
+            p = np.asarray(self._g.positions, dtype=np.float64)
+            out = np.zeros((self.n_atoms, 3))
+            np.add.at(out, self._inv, self._m[:, None] * p)
+            return out / np.bincount(self._inv, weights=self._m)[:, None]
+
+    g = golden("f64_ref")
+    u = SyntheticUniverse(g["isf_positions"], g["isf_dims"], resindices=g["isf_resindices"],
+                          masses=g["isf_masses"])
+    n_a, n = int(g["isf_n_a"]), u.atoms.n_atoms
+    a, b = u.select(slice(0, n_a)), u.select(slice(n_a, n))
+    o = rp.isf_run(u, [Centres(a), Centres(b)], mode="partial", n_points=5, n_lags=4,
+                   incoherent=True, dt=1.0, n_threads=2)
+    np.testing.assert_allclose(o["wavenumbers"], g["isf_wavenumbers"], rtol=1e-12)
+    np.testing.assert_allclose(o["cisf"], g["isf_cisf"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(o["iisf"], g["isf_iisf"], rtol=1e-10, atol=1e-11)
